@@ -1,0 +1,115 @@
+/*
+ * tagpu — B200-native k-mer counting + de Bruijn graph construction behind TuringAssembler's own
+ * C entry points.  C ABI of libtagpu.so (plain pointers and sizes; no CUDA or torch types).
+ *
+ * Level 1/2 symbols are the reference's own names and signatures, so the reference links against
+ * libtagpu.so instead of libs/KMC/libkmc.a + its own kmer_build.c versions.
+ * There is no CPU fallback: every entry point needs a CUDA device and exits loudly without one.
+ */
+#ifndef TAGPU_H
+#define TAGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ level 1: library boundary
+ * replaces libs/KMC/libkmc.a — /root/reference/include/kmc_skipping.h:8-11
+ * (call sites /root/reference/src/kmer_build.c:726,731,736,800,807,943,999; src/resolve_big.c:240).
+ * Counts canonical ksize-mers of all files on the GPU and writes
+ * working_dir/KMC_<ksize>_count.kmc_pre/.kmc_suf in the layout /root/reference/src/KMC_reader.c:22-150
+ * parses (KMC_VER 0x200, counter_size 4).  Returns 0. */
+int KMC_build_kmer_database(int ksize, const char *working_dir, int n_threads,
+			    int mmem, int n_files, char **files);
+/* /root/reference/include/kmc_skipping.h:11 — exported for link compatibility; never called by the reference. */
+int KMC_arg_kmer_count(int argc, char *argv[]);
+
+/* ------------------------------------------------------------------ level 2: stage boundary
+ * struct asm_graph_t / struct opt_proc_t are the reference's types
+ * (/root/reference/src/assembly_graph.h:52-95, /root/reference/src/attribute.h:49-71); tagpu_graph.h
+ * re-declares them layout-compatibly for callers that do not include the reference headers. */
+struct asm_graph_t;
+struct opt_proc_t;
+
+/* /root/reference/src/kmer_build.h:17-19, body /root/reference/src/kmer_build.c:714-786 */
+void build_graph_from_scratch(int ksize, int n_threads, int mmem, int n_files,
+			      char **files_1, char **files_2, char *work_dir,
+			      struct asm_graph_t *g);
+/* /root/reference/src/kmer_build.h:20-22, body /root/reference/src/kmer_build.c:788-837 (edge counts left 0) */
+void build_graph_from_scratch_without_count(int ksize, int n_threads, int mmem, int n_files,
+					    char **files_1, char **files_2, char *work_dir,
+					    struct asm_graph_t *g);
+/* /root/reference/src/assembly_graph.h:141, body /root/reference/src/kmer_build.c:839-845 */
+void build_initial_graph(struct opt_proc_t *opt, int ksize, struct asm_graph_t *g);
+
+/* ------------------------------------------------------------------ native API (what bench.py, the tests and the
+ * level-1/2 wrappers call) */
+typedef struct tagpu_ctx tagpu_ctx;
+
+struct tagpu_stats {
+	uint64_t n_instances;    /* valid (k+1)-mer windows (SURVEY.md §8d metric numerator) */
+	uint64_t n_distinct;     /* distinct canonical (k+1)-mers */
+	uint64_t n_solid;        /* ... with count >= cutoff */
+	uint64_t sum_solid;      /* sum of their counts */
+	uint64_t n_kmers;        /* canonical k-mers ("Number of kmer", kmer_build.c:758) */
+	uint64_t n_v, n_e;       /* "Number of nodes / edges" (kmer_build.c:763): n_v = 2 * #node k-mers */
+	uint64_t n_seq_words;    /* total 32-bit words of edge sequence */
+	uint64_t n_kp1_on_edge;  /* "Number of (k+1)-mer on edge" (kmer_build.c:772) */
+	uint64_t error;          /* 0 = ok; bit set = internal invariant violated (TAGPU_ERR_*) */
+	uint64_t jump_rounds;    /* pointer-jumping rounds executed */
+	uint64_t gpu_launches;   /* kernels launched by the last build */
+	float ms_count, ms_graph, ms_total; /* CUDA-event times of the last build (device side) */
+};
+
+/* device < 0: current device.  Returns NULL (after printing the reason) if CUDA is unusable. */
+tagpu_ctx *tagpu_create(int device);
+void tagpu_destroy(tagpu_ctx *ctx);
+/* cuda_stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0 = the context's own stream */
+void tagpu_set_stream(tagpu_ctx *ctx, void *cuda_stream);
+/* min count of a solid (k+1)-mer; default 2 (SURVEY.md §8c decision) */
+void tagpu_set_cutoff(tagpu_ctx *ctx, int ci);
+/* 0 (default) = build edge counts; 1 = build_graph_from_scratch_without_count behaviour */
+void tagpu_set_skip_counts(tagpu_ctx *ctx, int skip);
+const char *tagpu_last_error(tagpu_ctx *ctx);
+
+/* Count + build from a flat byte stream already in device memory ('\n' or any non-ACGT byte between reads).
+ * Results stay on the device until copied.  k = node k-mer size (17..63); returns 0 on success. */
+int tagpu_build_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_bytes, int k);
+/* Same from host memory: copies the stream to the device inside the call. */
+int tagpu_build_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n_bytes, int k);
+/* Counting stage only (what KMC_build_kmer_database needs); ksize_plus_1 = K = k + 1 */
+int tagpu_count_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_bytes, int ksize_plus_1);
+int tagpu_count_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n_bytes, int ksize_plus_1);
+
+int tagpu_get_stats(tagpu_ctx *ctx, struct tagpu_stats *out);
+
+/* Device -> host copies of the last build; caller allocates from tagpu_stats sizes.
+ * Keys are (hi, lo) pairs of the 2-bit packed mer, first base most significant. Order is unspecified. */
+int tagpu_copy_solid(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint32_t *count);         /* n_solid each */
+int tagpu_copy_kmers(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint8_t *mask);           /* n_kmers each */
+struct tagpu_flat_graph {
+	uint64_t n_nodes;         /* node k-mers; node ids 2i (canonical) / 2i+1 (reverse complement) */
+	uint64_t n_e, n_seq_words;
+	uint8_t *node_mask;       /* [n_nodes]  low nibble: out-bases of 2i, high nibble: out-bases of 2i+1 */
+	uint32_t *node_ebase;     /* [n_nodes]  first edge id of node 2i; edges of 2i+1 follow those of 2i */
+	uint32_t *e_src, *e_dst, *e_rc, *e_len; /* [n_e] */
+	uint64_t *e_count, *e_off;              /* [n_e] e_off = first word of the edge in e_seq */
+	uint32_t *e_seq;                        /* [n_seq_words] base i at bits 2(i&15) of word i>>4 (assembly_graph.h:182-187) */
+};
+int tagpu_copy_graph(tagpu_ctx *ctx, struct tagpu_flat_graph *host_arrays);
+
+/* Host-side materialisation of the last build (tagpu_host.c) */
+int tagpu_fill_asm_graph(tagpu_ctx *ctx, struct asm_graph_t *g);   /* individually malloc'ed seq/adj, SURVEY.md §8b */
+int tagpu_write_graph_bin(tagpu_ctx *ctx, const char *path);       /* save_asm_graph layout, assembly_graph.c:1173-1248 */
+int tagpu_write_kmc_db(tagpu_ctx *ctx, const char *working_dir);   /* KMC_<K>_count.kmc_pre/.kmc_suf of the last count */
+
+/* FASTQ/FASTA(.gz) files -> pinned host stream of sequence lines joined by '\n' (free with tagpu_free_reads) */
+int64_t tagpu_load_reads(int n_files, char **files, int n_threads, uint8_t **stream);
+void tagpu_free_reads(uint8_t *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAGPU_H */

@@ -1,0 +1,104 @@
+"""ctypes access to the CPU oracle (oracle/liboracle.so). Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+TA_REF = os.path.join(ORACLE_DIR, "_ref", "TA_ref")
+TA_GPU = os.path.join(ORACLE_DIR, "_ref", "TA_gpu")
+
+
+class OraGraph(C.Structure):
+    _fields_ = [
+        ("ksize", C.c_int), ("n_kmer", C.c_int64),
+        ("khi", C.POINTER(C.c_uint64)), ("klo", C.POINTER(C.c_uint64)), ("mask", C.POINTER(C.c_uint8)),
+        ("n_v", C.c_int64), ("n_e", C.c_int64),
+        ("node_rc", C.c_void_p), ("node_deg", C.c_void_p), ("node_adj_off", C.c_void_p), ("node_adj", C.c_void_p),
+        ("e_src", C.c_void_p), ("e_dst", C.c_void_p), ("e_rc", C.c_void_p),
+        ("e_count", C.POINTER(C.c_uint64)), ("e_len", C.POINTER(C.c_uint32)),
+        ("e_seq_off", C.c_void_p), ("e_seq", C.c_void_p), ("n_kp1_on_edge", C.c_uint64),
+    ]
+
+
+class Oracle:
+    def __init__(self, lib):
+        self.lib = lib
+        lib.ora_count_stream.restype = C.c_int64
+        lib.ora_count_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.ora_free.argtypes = [C.c_void_p]
+        lib.ora_build_graph.restype = C.POINTER(OraGraph)
+        lib.ora_build_graph.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ora_graph_free.argtypes = [C.POINTER(OraGraph)]
+        lib.ora_graph_save_bin.argtypes = [C.POINTER(OraGraph), C.c_char_p]
+        lib.ora_canon_dump.restype = C.c_int
+        lib.ora_canon_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        lib.ora_load_reads.restype = C.c_int64
+        lib.ora_load_reads.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p)]
+
+    def count(self, stream, K, ci=2, threads=8):
+        """-> dict(hi, lo, count (sorted by key), n_instances, n_distinct)"""
+        a = np.frombuffer(stream, dtype=np.uint8) if isinstance(stream, (bytes, bytearray)) else stream
+        hi, lo, cnt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        ni, nd = C.c_uint64(), C.c_uint64()
+        n = self.lib.ora_count_stream(a.ctypes.data, a.size, K, ci, threads, C.byref(hi), C.byref(lo), C.byref(cnt),
+                                      C.byref(ni), C.byref(nd))
+        assert n >= 0
+        def take(p, dt):
+            out = np.ctypeslib.as_array(C.cast(p, C.POINTER(dt)), shape=(max(n, 1),))[:n].copy()
+            self.lib.ora_free(p)
+            return out
+        return dict(hi=take(hi, C.c_uint64), lo=take(lo, C.c_uint64), count=take(cnt, C.c_uint32),
+                    n_instances=ni.value, n_distinct=nd.value)
+
+    def graph(self, k, hi, lo, count):
+        hi, lo, count = np.ascontiguousarray(hi, np.uint64), np.ascontiguousarray(lo, np.uint64), np.ascontiguousarray(count, np.uint32)
+        return self.lib.ora_build_graph(k, hi.size, hi.ctypes.data, lo.ctypes.data, count.ctypes.data)
+
+    def graph_masks(self, g):
+        n = g.contents.n_kmer
+        f = lambda p: np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n].copy()
+        return f(g.contents.khi), f(g.contents.klo), f(g.contents.mask)
+
+    def save_bin(self, g, path):
+        assert self.lib.ora_graph_save_bin(g, os.fsencode(path)) == 0
+
+    def free_graph(self, g):
+        self.lib.ora_graph_free(g)
+
+    def canon(self, bin_path, out_path, mode=0):
+        """returns number of structural violations (0 = valid graph)"""
+        return self.lib.ora_canon_dump(os.fsencode(bin_path), os.fsencode(out_path), mode)
+
+    def load_reads(self, files):
+        arr = (C.c_char_p * len(files))()
+        arr[:] = [os.fsencode(f) for f in files]
+        out = C.c_void_p()
+        n = self.lib.ora_load_reads(len(files), arr, C.byref(out))
+        a = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(max(n, 1),))[:n].copy()
+        self.lib.ora_free(out)
+        return a
+
+
+_cached = None
+
+
+def load():
+    global _cached
+    if _cached is None:
+        if not os.path.exists(LIB):
+            subprocess.run(["make", "-C", ORACLE_DIR, "liboracle.so", "ta_oracle"], check=True, capture_output=True)
+        _cached = Oracle(C.CDLL(LIB))
+    return _cached
+
+
+def canon_text(oracle, bin_path, mode=0):
+    out = bin_path + f".canon{mode}.txt"
+    bad = oracle.canon(bin_path, out, mode)
+    with open(out, "rb") as f:
+        return bad, f.read()

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Generates tests/golden/golden.json (+ the small canonical unitig files) by running the UNMODIFIED reference
+(oracle/_ref/TA_ref = reference sources + oracle/kmc_cpu.c for the absent libkmc.a) on seeded synthetic reads.
+
+Run in the build container only (needs /root/reference to have been compiled by `make -C oracle ref`):
+    python tests/golden/make_golden.py
+The fixtures travel to the GPU box; the reference does not have to.
+"""
+import gzip
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import _oracle  # noqa: E402
+import _reads  # noqa: E402
+
+from _cases import CASES, reads_for  # noqa: E402
+
+
+def main():
+    ora = _oracle.load()
+    assert os.path.exists(_oracle.TA_REF), "build oracle/_ref/TA_ref first: make -C oracle ref"
+    golden = {}
+    for name, (kind, kw, ks) in CASES.items():
+        r1, r2 = reads_for(kind, kw)
+        with tempfile.TemporaryDirectory() as td:
+            f1, f2 = os.path.join(td, "R1.fq"), os.path.join(td, "R2.fq")
+            _reads.write_fastq(f1, r1, 1)
+            _reads.write_fastq(f2, r2, 2)
+            fq_md5 = [hashlib.md5(open(f, "rb").read()).hexdigest() for f in (f1, f2)]
+            for k in ks:
+                out = os.path.join(td, f"out{k}")
+                os.makedirs(out)
+                p = subprocess.run([_oracle.TA_REF, "build_0", "-1", f1, "-2", f2, "-l", "ust", "-k0", str(k), "-t", "1", "-o", out],
+                                   capture_output=True, text=True)
+                log = p.stdout + p.stderr
+                assert p.returncode == 0, log[-2000:]
+                g = lambda pat: int(re.search(pat, log).group(1))
+                rec = dict(
+                    k=k, fastq_md5=fq_md5, n_reads=len(r1) + len(r2),
+                    n_kmers=g(r"Number of kmer: (\d+)"), n_v=g(r"Number of nodes: (\d+)"), n_e=g(r"Number of edges: (\d+)"),
+                    n_kp1_on_edge=g(r"\(k\+1\)-mer on edge: (\d+)"), sum_count=g(r"sum_count = (\d+)"),
+                )
+                m = re.search(r"\[oracle-kmc\] K=\d+ instances=(\d+) distinct=(\d+) solid=(\d+)", log)
+                rec.update(n_instances=int(m.group(1)), n_distinct=int(m.group(2)), n_solid=int(m.group(3)))
+                binp = os.path.join(out, f"graph_k_{k}_level_0.bin")
+                for mode in (0, 1):
+                    bad, txt = _oracle.canon_text(ora, binp, mode)
+                    assert bad == 0
+                    rec[f"canon{mode}_md5"] = hashlib.md5(txt).hexdigest()
+                    if mode == 0 and len(txt) < 200000:
+                        with gzip.GzipFile(os.path.join(HERE, f"{name}_k{k}_canon0.txt.gz"), "wb", mtime=0) as gz:
+                            gz.write(txt)
+                golden[f"{name}_k{k}"] = dict(case=name, gen=kind, gen_kwargs=kw, **rec)
+                print(name, k, rec)
+    with open(os.path.join(HERE, "golden.json"), "w") as f:
+        json.dump(golden, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

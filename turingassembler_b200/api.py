@@ -1,0 +1,319 @@
+"""ctypes mirror of include/tagpu.h (and of the reference entry points libtagpu.so exports).
+
+Function names and argument meaning follow the reference:
+  * ``kmc_build_kmer_database``              -> KMC_build_kmer_database   (/root/reference/include/kmc_skipping.h:8-9)
+  * ``build_graph_from_scratch``             -> /root/reference/src/kmer_build.h:17-19
+  * ``build_graph_from_scratch_without_count`` -> /root/reference/src/kmer_build.h:20-22
+Everything is executed by libtagpu.so on the GPU; nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Sequence
+
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtagpu.so")
+
+
+class TagpuError(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n_instances", C.c_uint64),
+        ("n_distinct", C.c_uint64),
+        ("n_solid", C.c_uint64),
+        ("sum_solid", C.c_uint64),
+        ("n_kmers", C.c_uint64),
+        ("n_v", C.c_uint64),
+        ("n_e", C.c_uint64),
+        ("n_seq_words", C.c_uint64),
+        ("n_kp1_on_edge", C.c_uint64),
+        ("error", C.c_uint64),
+        ("jump_rounds", C.c_uint64),
+        ("gpu_launches", C.c_uint64),
+        ("ms_count", C.c_float),
+        ("ms_graph", C.c_float),
+        ("ms_total", C.c_float),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class FlatGraph(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_uint64),
+        ("n_e", C.c_uint64),
+        ("n_seq_words", C.c_uint64),
+        ("node_mask", C.c_void_p),
+        ("node_ebase", C.c_void_p),
+        ("e_src", C.c_void_p),
+        ("e_dst", C.c_void_p),
+        ("e_rc", C.c_void_p),
+        ("e_len", C.c_void_p),
+        ("e_count", C.c_void_p),
+        ("e_off", C.c_void_p),
+        ("e_seq", C.c_void_p),
+    ]
+
+
+# --- the reference's graph ABI (include/tagpu_graph.h) -----------------------------------------------------------
+class BarcodeHash(C.Structure):
+    _fields_ = [("size", C.c_uint32), ("n_item", C.c_uint32), ("n_unique", C.c_uint32),
+                ("keys", C.c_void_p), ("cnts", C.c_void_p)]
+
+
+class PthreadMutex(C.Structure):
+    _fields_ = [("opaque", C.c_char * 40)]  # sizeof(pthread_mutex_t) on x86-64 glibc
+    _align_ = 8
+
+
+class AsmNode(C.Structure):
+    _fields_ = [("rc_id", C.c_int64), ("deg", C.c_int64), ("adj", C.POINTER(C.c_int64))]
+
+
+class AsmEdge(C.Structure):
+    _fields_ = [
+        ("count", C.c_uint64),
+        ("seq", C.POINTER(C.c_uint32)),
+        ("seq_len", C.c_uint32),
+        ("n_holes", C.c_uint32),
+        ("p_holes", C.c_void_p),
+        ("l_holes", C.c_void_p),
+        ("source", C.c_int64),
+        ("target", C.c_int64),
+        ("rc_id", C.c_int64),
+        ("lock", C.c_uint64 * 5),
+        ("barcodes", C.c_void_p),
+        ("barcodes_scaf", BarcodeHash),
+        ("barcodes_cov", BarcodeHash),
+    ]
+
+
+class AsmGraph(C.Structure):
+    _fields_ = [
+        ("ksize", C.c_int),
+        ("bin_size", C.c_int),
+        ("aux_flag", C.c_uint32),
+        ("n_v", C.c_int64),
+        ("n_e", C.c_int64),
+        ("nodes", C.POINTER(AsmNode)),
+        ("edges", C.POINTER(AsmEdge)),
+        ("candidates", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads libtagpu.so; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TagpuError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    lib.tagpu_create.restype = vp
+    lib.tagpu_create.argtypes = [i32]
+    lib.tagpu_destroy.argtypes = [vp]
+    lib.tagpu_set_stream.argtypes = [vp, vp]
+    lib.tagpu_set_cutoff.argtypes = [vp, i32]
+    lib.tagpu_set_skip_counts.argtypes = [vp, i32]
+    lib.tagpu_last_error.restype = C.c_char_p
+    lib.tagpu_last_error.argtypes = [vp]
+    for name in ("tagpu_build_device", "tagpu_build_host", "tagpu_count_device", "tagpu_count_host"):
+        f = getattr(lib, name)
+        f.restype = i32
+        f.argtypes = [vp, vp, u64, i32]
+    lib.tagpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.tagpu_copy_solid.restype = i32
+    lib.tagpu_copy_solid.argtypes = [vp, vp, vp, vp]
+    lib.tagpu_copy_kmers.restype = i32
+    lib.tagpu_copy_kmers.argtypes = [vp, vp, vp, vp]
+    lib.tagpu_copy_graph.restype = i32
+    lib.tagpu_copy_graph.argtypes = [vp, C.POINTER(FlatGraph)]
+    lib.tagpu_fill_asm_graph.restype = i32
+    lib.tagpu_fill_asm_graph.argtypes = [vp, C.POINTER(AsmGraph)]
+    lib.tagpu_write_graph_bin.restype = i32
+    lib.tagpu_write_graph_bin.argtypes = [vp, C.c_char_p]
+    lib.tagpu_write_kmc_db.restype = i32
+    lib.tagpu_write_kmc_db.argtypes = [vp, C.c_char_p]
+    lib.tagpu_load_reads.restype = C.c_int64
+    lib.tagpu_load_reads.argtypes = [i32, C.POINTER(C.c_char_p), i32, C.POINTER(vp)]
+    lib.tagpu_free_reads.argtypes = [vp]
+    lib.KMC_build_kmer_database.restype = i32
+    lib.KMC_build_kmer_database.argtypes = [i32, C.c_char_p, i32, i32, i32, C.POINTER(C.c_char_p)]
+    for name in ("build_graph_from_scratch", "build_graph_from_scratch_without_count"):
+        f = getattr(lib, name)
+        f.restype = None
+        f.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p, C.POINTER(AsmGraph)]
+    _lib = lib
+    return lib
+
+
+def _char_pp(paths: Sequence[str]):
+    arr = (C.c_char_p * len(paths))()
+    arr[:] = [os.fsencode(p) for p in paths]
+    return arr
+
+
+class Tagpu:
+    """One GPU context (tagpu_ctx). All heavy lifting happens inside libtagpu.so."""
+
+    def __init__(self, device: int = -1, cutoff: int = 2):
+        self.lib = load_library()
+        self.ctx = self.lib.tagpu_create(device)
+        if not self.ctx:
+            raise TagpuError("tagpu_create failed: no usable CUDA device (libtagpu has no CPU fallback)")
+        self.lib.tagpu_set_cutoff(self.ctx, cutoff)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.tagpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise TagpuError(self.lib.tagpu_last_error(self.ctx).decode())
+
+    def set_stream(self, cuda_stream: int):
+        self.lib.tagpu_set_stream(self.ctx, C.c_void_p(cuda_stream))
+
+    def set_cutoff(self, ci: int):
+        self.lib.tagpu_set_cutoff(self.ctx, ci)
+
+    def set_skip_counts(self, skip: bool):
+        self.lib.tagpu_set_skip_counts(self.ctx, int(skip))
+
+    # ---- builds ----
+    def build_device(self, d_ptr: int, n_bytes: int, k: int):
+        """d_ptr: device address of the flat read stream (e.g. torch tensor .data_ptr())."""
+        self._check(self.lib.tagpu_build_device(self.ctx, C.c_void_p(d_ptr), n_bytes, k))
+        return self.stats()
+
+    def count_device(self, d_ptr: int, n_bytes: int, K: int):
+        self._check(self.lib.tagpu_count_device(self.ctx, C.c_void_p(d_ptr), n_bytes, K))
+        return self.stats()
+
+    def build_host(self, stream, k: int):
+        """stream: bytes / numpy uint8 array / host address+length tuple."""
+        ptr, n, keep = _host_buffer(stream)
+        self._check(self.lib.tagpu_build_host(self.ctx, ptr, n, k))
+        del keep
+        return self.stats()
+
+    def count_host(self, stream, K: int):
+        ptr, n, keep = _host_buffer(stream)
+        self._check(self.lib.tagpu_count_host(self.ctx, ptr, n, K))
+        del keep
+        return self.stats()
+
+    def stats(self) -> dict:
+        st = Stats()
+        self.lib.tagpu_get_stats(self.ctx, C.byref(st))
+        return st.as_dict()
+
+    # ---- results ----
+    def solid(self):
+        n = self.stats()["n_solid"]
+        hi, lo, cnt = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+        self._check(self.lib.tagpu_copy_solid(self.ctx, hi.ctypes.data, lo.ctypes.data, cnt.ctypes.data))
+        return hi, lo, cnt
+
+    def kmers(self):
+        n = self.stats()["n_kmers"]
+        hi, lo, mask = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(n, np.uint8)
+        self._check(self.lib.tagpu_copy_kmers(self.ctx, hi.ctypes.data, lo.ctypes.data, mask.ctypes.data))
+        return hi, lo, mask
+
+    def graph(self) -> dict:
+        st = self.stats()
+        nn, ne, nw = st["n_v"] // 2, st["n_e"], st["n_seq_words"]
+        arrs = {
+            "node_mask": np.zeros(nn + 1, np.uint8), "node_ebase": np.zeros(nn + 1, np.uint32),
+            "e_src": np.zeros(ne + 1, np.uint32), "e_dst": np.zeros(ne + 1, np.uint32),
+            "e_rc": np.zeros(ne + 1, np.uint32), "e_len": np.zeros(ne + 1, np.uint32),
+            "e_count": np.zeros(ne + 1, np.uint64), "e_off": np.zeros(ne + 1, np.uint64),
+            "e_seq": np.zeros(nw + 1, np.uint32),
+        }
+        fg = FlatGraph()
+        for name, a in arrs.items():
+            setattr(fg, name, a.ctypes.data)
+        self._check(self.lib.tagpu_copy_graph(self.ctx, C.byref(fg)))
+        out = {"n_nodes": nn, "n_e": ne, "n_seq_words": nw}
+        out.update({name: a[: {"node_mask": nn, "node_ebase": nn, "e_seq": nw}.get(name, ne)] for name, a in arrs.items()})
+        return out
+
+    def write_graph_bin(self, path: str):
+        self._check(self.lib.tagpu_write_graph_bin(self.ctx, os.fsencode(path)))
+
+    def write_kmc_db(self, working_dir: str):
+        self._check(self.lib.tagpu_write_kmc_db(self.ctx, os.fsencode(working_dir)))
+
+    def fill_asm_graph(self) -> AsmGraph:
+        g = AsmGraph()
+        self._check(self.lib.tagpu_fill_asm_graph(self.ctx, C.byref(g)))
+        return g
+
+
+def _host_buffer(stream):
+    if isinstance(stream, (bytes, bytearray)):
+        a = np.frombuffer(stream, dtype=np.uint8)
+    elif isinstance(stream, np.ndarray):
+        a = np.ascontiguousarray(stream.view(np.uint8))
+    elif isinstance(stream, tuple):
+        return C.c_void_p(stream[0]), int(stream[1]), None
+    else:
+        raise TypeError(f"unsupported stream type {type(stream)}")
+    return C.c_void_p(a.ctypes.data), int(a.size), a
+
+
+def load_reads(files: Sequence[str], n_threads: int = 4):
+    """FASTQ/FASTA(.gz) -> (pinned host address, n_bytes); release with free_reads."""
+    lib = load_library()
+    out = C.c_void_p()
+    n = lib.tagpu_load_reads(len(files), _char_pp(files), n_threads, C.byref(out))
+    return out.value, n
+
+
+def free_reads(addr: int):
+    load_library().tagpu_free_reads(C.c_void_p(addr))
+
+
+# ---- the reference's entry points, same names and argument order -------------------------------------------------
+def kmc_build_kmer_database(ksize: int, working_dir: str, n_threads: int, mmem: int, files: Sequence[str]) -> int:
+    lib = load_library()
+    return lib.KMC_build_kmer_database(ksize, os.fsencode(working_dir), n_threads, mmem, len(files), _char_pp(files))
+
+
+def build_graph_from_scratch(ksize: int, n_threads: int, mmem: int, files_1: Sequence[str], files_2: Sequence[str],
+                             work_dir: str) -> AsmGraph:
+    lib = load_library()
+    g = AsmGraph()
+    lib.build_graph_from_scratch(ksize, n_threads, mmem, len(files_1), _char_pp(files_1), _char_pp(files_2),
+                                 os.fsencode(work_dir), C.byref(g))
+    return g
+
+
+def build_graph_from_scratch_without_count(ksize: int, n_threads: int, mmem: int, files_1: Sequence[str],
+                                           files_2: Sequence[str], work_dir: str) -> AsmGraph:
+    lib = load_library()
+    g = AsmGraph()
+    lib.build_graph_from_scratch_without_count(ksize, n_threads, mmem, len(files_1), _char_pp(files_1),
+                                               _char_pp(files_2), os.fsencode(work_dir), C.byref(g))
+    return g

@@ -1,0 +1,98 @@
+// Read-stream tile loader and rolling (k+1)-mer extraction shared by the counting kernels.
+//
+// Input model: a flat byte stream; A/C/G/T/a/c/g/t are bases (nt4_table,
+// /root/reference/src/utils.c:26-43), every other byte (newline between reads, 'N', ...) breaks the
+// window (cf. /root/reference/src/k63_build.c:397-410).  A tile is TILE_BASES consecutive byte
+// positions; the CTA packs them (plus a 64-base halo to the left) into shared memory as 2-bit codes,
+// 32 bases per 64-bit word (first base most significant) with a 32-bit invalid mask per word, and then
+// every thread rolls forward and reverse-complement mers over the 32 window-end positions of one word.
+#pragma once
+#include "tagpu_key.cuh"
+
+constexpr int TAGPU_TILE_THREADS = 256;
+constexpr int TAGPU_TILE_WORDS = 256;               // words whose positions are window ends
+constexpr int TAGPU_HALO_WORDS = 2;                 // 64 bases: enough history for K <= 64
+constexpr int TAGPU_TILE_BASES = TAGPU_TILE_WORDS * 32;
+constexpr int TAGPU_SMEM_WORDS = TAGPU_TILE_WORDS + TAGPU_HALO_WORDS;
+
+// 4 ASCII bytes (byte 0 = first base) -> 8 bits of codes (first base in bits 7..6) + 4 invalid bits (first base = bit 3)
+TAGPU_DI void tagpu_pack4(uint32_t w, uint32_t &codes, uint32_t &inv)
+{
+	uint32_t c = (w >> 1) & 0x03030303u;        // A=0 C=1 G=3 T=2
+	c ^= (c >> 1) & 0x01010101u;                // A=0 C=1 G=2 T=3
+	codes = (c * 0x40100401u) >> 24;
+	uint32_t u = w & 0xdfdfdfdfu;               // fold lower case
+	uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+	inv = (((~ok) & 0x01010101u) * 0x08040201u) >> 24 & 0xfu;
+}
+
+// Packs the tile that owns window-end positions [tile_base, tile_base + TILE_BASES) into pk/inv.
+// smem word j covers stream positions tile_base - 64 + 32 j .. +31.
+TAGPU_DI void tagpu_load_tile(const uint8_t *__restrict__ seq, uint64_t n, uint64_t tile_base,
+			       uint64_t *pk, uint32_t *inv)
+{
+	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
+		long long g0 = (long long)tile_base - 64 + 32ll * j;
+		uint64_t word = 0;
+		uint32_t bad = 0;
+		if (g0 >= 0 && (uint64_t)g0 + 32 <= n && ((reinterpret_cast<uintptr_t>(seq) + g0) & 15) == 0) {
+			const uint4 *p = reinterpret_cast<const uint4 *>(seq + g0);
+			uint4 a = __ldg(p), b = __ldg(p + 1);
+			uint32_t w[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+#pragma unroll
+			for (int q = 0; q < 8; ++q) {
+				uint32_t c, iv;
+				tagpu_pack4(w[q], c, iv);
+				word = (word << 8) | c;
+				bad = (bad << 4) | iv;
+			}
+		} else {
+			for (int q = 0; q < 32; ++q) {
+				long long g = g0 + q;
+				uint32_t c = 0, iv = 1;
+				if (g >= 0 && (uint64_t)g < n) {
+					uint32_t ch = seq[g], code, i4;
+					tagpu_pack4(ch, code, i4); // byte 0 only: code in bits 7..6, invalid in bit 3
+					c = code >> 6;
+					iv = (i4 >> 3) & 1u;
+				}
+				word = (word << 2) | c;
+				bad = (bad << 1) | iv;
+			}
+		}
+		pk[j] = word;
+		inv[j] = bad;
+	}
+}
+
+// Calls f(canonical_key, pos_in_word) for every valid window of K bases ending in word `wi` (tile-local, >= HALO_WORDS).
+// Returns the number of valid windows.
+template <int W, typename F>
+TAGPU_DI uint32_t tagpu_roll_word(const uint64_t *pk, const uint32_t *inv, int wi, int K, F &&f)
+{
+	typedef KeyOps<W> KO;
+	typedef Key<W> KT;
+	const KT m = KO::mask(K);
+	KT fw = KO::band(KO::make(pk[wi - 2], pk[wi - 1]), m);
+	KT rv = KO::rc(fw, K);
+	uint32_t i1 = inv[wi - 1], i2 = inv[wi - 2];
+	int run = i1 ? (__ffs(i1) - 1) : 32 + (i2 ? (__ffs(i2) - 1) : 32);
+	uint64_t cur = pk[wi];
+	uint32_t iv = inv[wi];
+	uint32_t n_valid = 0;
+#pragma unroll 4
+	for (int i = 0; i < 32; ++i) {
+		uint32_t c = (uint32_t)(cur >> 62);
+		cur <<= 2;
+		bool bad = (int)iv < 0;
+		iv <<= 1;
+		fw = KO::push(fw, c, m);
+		rv = KO::push_front(rv, 3u - c, K);
+		run = bad ? 0 : run + 1;
+		if (run >= K) {
+			++n_valid;
+			f(KO::le(fw, rv) ? fw : rv, i);
+		}
+	}
+	return n_valid;
+}

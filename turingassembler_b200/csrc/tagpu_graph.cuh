@@ -1,0 +1,384 @@
+// De Bruijn graph stage on the GPU: solid (k+1)-mers -> k-mer table with 8-bit edge masks ->
+// node marking -> successor links over oriented non-branching vertices -> Wyllie pointer jumping ->
+// unitig (edge) emission, reverse-complement links and edge counts.
+//
+// Replaces the reference's split_kmer_from_kedge_multi (/root/reference/src/kmer_build.c:78-129),
+// build_asm_graph_from_kmhash + build_graph_worker (:544-649, :421-542), the rc-link loop (:624-641)
+// and build_edge_kmer_index_multi + assign_count_kedge_multi (:291-338, :143-157).
+//
+// Vertex id v = 2 * slot + orient, orient 0 = the canonical k-mer stored in `slot`, 1 = its reverse
+// complement.  Low nibble of the mask = bases that may follow orient 0, high nibble = orient 1 (App. A.4).
+#pragma once
+#include "tagpu_key.cuh"
+
+constexpr uint32_t TAGPU_NONE = 0xffffffffu;
+constexpr uint32_t TAGPU_TERM = 0x80000000u;
+
+enum {
+	CTR_INSTANCES = 0, CTR_DISTINCT, CTR_SOLID, CTR_KMERS, CTR_NODES, CTR_EDGES, CTR_SEQ_WORDS,
+	CTR_KP1_ON_EDGE, CTR_ERROR, CTR_SUM_SOLID, CTR_SPARE0, CTR_SPARE1, CTR_JUMP_FLAGS /* + 64 */, CTR_TOTAL = CTR_JUMP_FLAGS + 64
+};
+
+enum { TAGPU_ERR_TABLE_FULL = 1, TAGPU_ERR_MISSING_SUCC = 2, TAGPU_ERR_CHAIN = 4, TAGPU_ERR_RC_LINK = 8, TAGPU_ERR_BUCKET_OVERFLOW = 16 };
+
+#define DEG4(x) __popc((x) & 15u)
+
+TAGPU_DI uint32_t tagpu_only4(uint32_t nib) { return (uint32_t)(__ffs(nib & 15u) - 1); }
+TAGPU_DI uint32_t tagpu_rank4(uint32_t nib, uint32_t c) { return (uint32_t)__popc(nib & ((1u << c) - 1u)); }
+
+// All 32 lanes must call.  Returns this lane's base offset in a global bump allocation of `want` units.
+TAGPU_DI unsigned long long tagpu_warp_alloc(unsigned long long *ctr, uint32_t want)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t incl = want;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= (uint32_t)d) incl += t;
+	}
+	uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+	unsigned long long base = 0;
+	if (lane == 31 && total) base = atomicAdd(ctr, (unsigned long long)total);
+	base = __shfl_sync(0xffffffffu, base, 31);
+	return base + (incl - want);
+}
+
+// ---------------------------------------------------------------- k-mer table (open addressing, linear probing)
+// keys[] holds ~key (canonical k-mers are never all-ones, so 0 == empty); mask8[] is byte-addressed through 32-bit atomics.
+
+template <int W> struct KTab {
+	Key<W> *keys;
+	uint32_t *mask32;      // n_slots / 4 words
+	uint32_t slot_mask;    // n_slots - 1
+};
+
+template <int W> TAGPU_DI Key<W> ktab_load(const Key<W> *p);
+template <> TAGPU_DI Key<1> ktab_load<1>(const Key<1> *p) { Key<1> r; r.lo = __ldcg(&p->lo); return r; }
+template <> TAGPU_DI Key<2> ktab_load<2>(const Key<2> *p)
+{
+	ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
+	Key<2> r; r.lo = v.x; r.hi = v.y; return r;
+}
+
+// returns the previous content of the slot (all-zero if we claimed it)
+template <int W> TAGPU_DI Key<W> ktab_cas(Key<W> *p, const Key<W> &stored);
+template <> TAGPU_DI Key<1> ktab_cas<1>(Key<1> *p, const Key<1> &stored)
+{
+	Key<1> r; r.lo = atomicCAS(&p->lo, 0ull, stored.lo); return r;
+}
+template <> TAGPU_DI Key<2> ktab_cas<2>(Key<2> *p, const Key<2> &stored)
+{
+	unsigned __int128 want = ((unsigned __int128)stored.hi << 64) | stored.lo;
+	unsigned __int128 old = atomicCAS(reinterpret_cast<unsigned __int128 *>(p), (unsigned __int128)0, want);
+	Key<2> r; r.lo = (unsigned long long)old; r.hi = (unsigned long long)(old >> 64); return r;
+}
+
+// A 16-byte load is not guaranteed single-copy atomic against a 128-bit CAS: a value with an all-zero half
+// that is neither empty nor ours might be torn, so it is re-read through the CAS unit.
+template <int W> TAGPU_DI bool ktab_maybe_torn(const Key<W> &v);
+template <> TAGPU_DI bool ktab_maybe_torn<1>(const Key<1> &) { return false; }
+template <> TAGPU_DI bool ktab_maybe_torn<2>(const Key<2> &v) { return v.lo == 0 || v.hi == 0; }
+
+// insert-or-find; *claimed = true if this call created the entry
+template <int W>
+TAGPU_DI uint32_t ktab_insert(const KTab<W> &t, const Key<W> &key, bool *claimed, unsigned long long *err)
+{
+	typedef KeyOps<W> KO;
+	const Key<W> stored = KO::bnot(key);
+	uint32_t slot = (uint32_t)(KO::hash(key) >> 20) & t.slot_mask;
+	*claimed = false;
+	for (uint32_t probes = 0; probes <= t.slot_mask; ++probes) {
+		Key<W> cur = ktab_load<W>(t.keys + slot);
+		if (KO::eq(cur, stored)) return slot;
+		if (KO::is_zero(cur) || ktab_maybe_torn<W>(cur)) {
+			Key<W> old = ktab_cas<W>(t.keys + slot, stored);
+			if (KO::is_zero(old)) { *claimed = true; return slot; }
+			if (KO::eq(old, stored)) return slot;
+		}
+		slot = (slot + 1) & t.slot_mask;
+	}
+	atomicOr(err, (unsigned long long)TAGPU_ERR_TABLE_FULL);
+	return 0;
+}
+
+template <int W>
+TAGPU_DI uint32_t ktab_find(const KTab<W> &t, const Key<W> &key)
+{
+	typedef KeyOps<W> KO;
+	const Key<W> stored = KO::bnot(key);
+	uint32_t slot = (uint32_t)(KO::hash(key) >> 20) & t.slot_mask;
+	for (uint32_t probes = 0; probes <= t.slot_mask; ++probes) {
+		Key<W> cur = t.keys[slot];
+		if (KO::eq(cur, stored)) return slot;
+		if (KO::is_zero(cur)) return TAGPU_NONE;
+		slot = (slot + 1) & t.slot_mask;
+	}
+	return TAGPU_NONE;
+}
+
+template <int W> TAGPU_DI uint32_t ktab_mask_of(const KTab<W> &t, uint32_t slot)
+{
+	return (t.mask32[slot >> 2] >> ((slot & 3u) * 8u)) & 0xffu;
+}
+
+// canonical form of an oriented k-mer y (with its reverse complement yr): slot lookup + orientation bit
+template <int W>
+TAGPU_DI uint32_t ktab_vertex_of(const KTab<W> &t, const Key<W> &y, const Key<W> &yr)
+{
+	typedef KeyOps<W> KO;
+	bool fwd = KO::le(y, yr);
+	uint32_t s = ktab_find<W>(t, fwd ? y : yr);
+	return s == TAGPU_NONE ? TAGPU_NONE : (s * 2u + (fwd ? 0u : 1u));
+}
+
+// ---------------------------------------------------------------- B: masks (one thread per solid (k+1)-mer)
+template <int W>
+__global__ void __launch_bounds__(256) k_insert_kmers(const Key<W> *__restrict__ solid, uint64_t n_solid, int k,
+						       KTab<W> t, uint32_t *__restrict__ vL, uint32_t *__restrict__ vR,
+						       unsigned long long *ctr)
+{
+	typedef KeyOps<W> KO;
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t n_new = 0;
+	if (i < n_solid) {
+		const Key<W> x = solid[i];
+		const Key<W> km = KO::mask(k);
+		const Key<W> k1 = KO::shr2(x), k2 = KO::band(x, km);         // kedge_get_left / kedge_get_right
+		const uint32_t c1 = KO::last_base(x), c2 = 3u - KO::first_base(x, k + 1);
+		const Key<W> r1 = KO::rc(k1, k), r2 = KO::rc(k2, k);
+		const bool f1 = KO::le(k1, r1), f2 = KO::le(k2, r2);        // ties -> forward (kmer_build.c:110,120)
+		bool claimed;
+		uint32_t s1 = ktab_insert<W>(t, f1 ? k1 : r1, &claimed, ctr + CTR_ERROR);
+		n_new += claimed;
+		atomicOr(&t.mask32[s1 >> 2], (1u << (f1 ? c1 : c1 + 4u)) << ((s1 & 3u) * 8u));
+		uint32_t s2 = ktab_insert<W>(t, f2 ? k2 : r2, &claimed, ctr + CTR_ERROR);
+		n_new += claimed;
+		atomicOr(&t.mask32[s2 >> 2], (1u << (f2 ? c2 + 4u : c2)) << ((s2 & 3u) * 8u));
+		vL[i] = s1 * 2u + (f1 ? 0u : 1u);   // oriented vertex whose out-base c1 spells this (k+1)-mer
+		vR[i] = s2 * 2u + (f2 ? 1u : 0u);   // oriented vertex rc(k2) whose out-base c2 spells its reverse complement
+	}
+	n_new = __reduce_add_sync(0xffffffffu, n_new);
+	if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(ctr + CTR_KMERS, (unsigned long long)n_new);
+}
+
+// ---------------------------------------------------------------- C1: nodes (one thread per slot)
+template <int W>
+__global__ void __launch_bounds__(256) k_classify(KTab<W> t, uint32_t *__restrict__ node_ord,
+						   uint32_t *__restrict__ node_slot, uint32_t *__restrict__ node_ebase,
+						   unsigned long long *ctr)
+{
+	typedef KeyOps<W> KO;
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; // grid covers exactly n_slots
+	const bool occ = !KO::is_zero(t.keys[slot]);
+	const uint32_t m = ktab_mask_of<W>(t, slot);
+	const uint32_t df = DEG4(m), dr = DEG4(m >> 4);
+	const bool is_node = occ && !(df == 1 && dr == 1);             // kmer_build.c:453,561
+	const uint32_t ord = (uint32_t)tagpu_warp_alloc(ctr + CTR_NODES, is_node ? 1u : 0u);
+	const uint32_t eb = (uint32_t)tagpu_warp_alloc(ctr + CTR_EDGES, is_node ? df + dr : 0u);
+	node_ord[slot] = is_node ? ord : TAGPU_NONE;
+	if (is_node) {
+		node_slot[ord] = slot;
+		node_ebase[ord] = eb;
+	}
+}
+
+TAGPU_DI unsigned long long tagpu_pack_jump(uint32_t ptr, uint32_t dist) { return ((unsigned long long)dist << 32) | ptr; }
+
+// ---------------------------------------------------------------- C2: successor links (one thread per oriented vertex)
+template <int W>
+__global__ void __launch_bounds__(256) k_build_succ(KTab<W> t, int k, const uint32_t *__restrict__ node_ord,
+						     unsigned long long *__restrict__ jump, uint32_t *__restrict__ vsucc,
+						     unsigned long long *ctr)
+{
+	typedef KeyOps<W> KO;
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;      // grid covers exactly 2 * n_slots
+	const uint32_t slot = v >> 1, o = v & 1u;
+	const Key<W> stored = t.keys[slot];
+	unsigned long long j = tagpu_pack_jump(TAGPU_TERM | TAGPU_NONE, 0); // "not a chain vertex"
+	uint32_t succ = TAGPU_NONE;
+	if (!KO::is_zero(stored) && node_ord[slot] == TAGPU_NONE) {
+		const Key<W> key = KO::bnot(stored);
+		const uint32_t m = ktab_mask_of<W>(t, slot);
+		const uint32_t c = tagpu_only4(o ? (m >> 4) : m);
+		const Key<W> krc = KO::rc(key, k);
+		const Key<W> x = o ? krc : key, xr = o ? key : krc;
+		const Key<W> y = KO::push(x, c, KO::mask(k)), yr = KO::push_front(xr, 3u - c, k);
+		succ = ktab_vertex_of<W>(t, y, yr);
+		if (succ == TAGPU_NONE) {
+			atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_MISSING_SUCC); // kmer_build.c:475 assert
+		} else if (node_ord[succ >> 1] != TAGPU_NONE) {
+			j = tagpu_pack_jump(TAGPU_TERM | v, 0);                  // v is the last interior vertex of its chain
+		} else {
+			j = tagpu_pack_jump(succ, 1);
+		}
+	}
+	jump[v] = j;
+	vsucc[v] = succ;
+}
+
+// ---------------------------------------------------------------- C3: one round of in-place pointer jumping
+// (ptr, dist) travel as one 64-bit word, so a concurrent reader always sees a consistent pair.
+__global__ void __launch_bounds__(256) k_jump_round(unsigned long long *jump, uint32_t n_vertices,
+						     const unsigned long long *flag_prev, unsigned long long *flag_cur)
+{
+	if (flag_prev && *flag_prev == 0) return;                      // previous round left nothing to do
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	bool open = false;
+	if (v < n_vertices) {
+		unsigned long long j = __ldcg(jump + v);
+		uint32_t p = (uint32_t)j;
+		if (!(p & TAGPU_TERM)) {
+			unsigned long long jp = __ldcg(jump + p);
+			uint32_t np = (uint32_t)jp;
+			__stcg(jump + v, tagpu_pack_jump(np, (uint32_t)(j >> 32) + (uint32_t)(jp >> 32)));
+			open = !(np & TAGPU_TERM);
+		}
+	}
+	if (__any_sync(0xffffffffu, open) && (threadIdx.x & 31) == 0) *flag_cur = 1;
+}
+
+// ---------------------------------------------------------------- flat graph in device memory
+struct FlatGraph {
+	uint32_t *e_src, *e_dst, *e_rc, *e_len;     // node-vertex ids = 2 * node ordinal + orient
+	unsigned long long *e_count, *e_off;        // e_off: offset of the edge's first 32-bit sequence word
+	uint32_t *e_seq;
+};
+
+// ---------------------------------------------------------------- C4: edge heads (one thread per oriented node)
+template <int W>
+__global__ void __launch_bounds__(128) k_edge_heads(KTab<W> t, int k, uint32_t n_nodes,
+						     const uint32_t *__restrict__ node_ord, const uint32_t *__restrict__ node_slot,
+						     const uint32_t *__restrict__ node_ebase, const unsigned long long *__restrict__ jump,
+						     const uint32_t *__restrict__ vsucc, uint32_t *__restrict__ vedge,
+						     FlatGraph g, unsigned long long *ctr)
+{
+	typedef KeyOps<W> KO;
+	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;       // oriented node id
+	const bool live = u < 2u * n_nodes;
+	uint32_t ord = 0, o = 0, m = 0, nib = 0, e0 = 0;
+	Key<W> x = KO::make(0, 0), xr = KO::make(0, 0);
+	if (live) {
+		ord = u >> 1; o = u & 1u;
+		const uint32_t slot = node_slot[ord];
+		m = ktab_mask_of<W>(t, slot);
+		nib = o ? (m >> 4) : (m & 15u);
+		e0 = node_ebase[ord] + (o ? DEG4(m) : 0u);
+		const Key<W> key = KO::bnot(t.keys[slot]), krc = KO::rc(key, k);
+		x = o ? krc : key; xr = o ? key : krc;
+	}
+	uint32_t r = 0;
+	for (uint32_t c = 0; c < 4; ++c) {                              // all lanes iterate: warp_alloc needs the full warp
+		const bool have = live && ((nib >> c) & 1u);
+		uint32_t len = 0, dst = 0, first = TAGPU_NONE;
+		if (have) {
+			const Key<W> y = KO::push(x, c, KO::mask(k)), yr = KO::push_front(xr, 3u - c, k);
+			const uint32_t tv = ktab_vertex_of<W>(t, y, yr);
+			if (tv == TAGPU_NONE) {
+				atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_MISSING_SUCC);
+			} else if (node_ord[tv >> 1] != TAGPU_NONE) {
+				len = k + 1; dst = node_ord[tv >> 1] * 2u + (tv & 1u);
+			} else {
+				const unsigned long long j = jump[tv];
+				if (!((uint32_t)j & TAGPU_TERM) || ((uint32_t)j & ~TAGPU_TERM) == (TAGPU_NONE & ~TAGPU_TERM)) {
+					atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CHAIN);
+				} else {
+					const uint32_t vm = (uint32_t)j & ~TAGPU_TERM, tn = vsucc[vm];
+					len = k + 1 + (uint32_t)(j >> 32) + 1;
+					dst = node_ord[tn >> 1] * 2u + (tn & 1u);
+					first = tv;
+				}
+			}
+		}
+		const unsigned long long off = tagpu_warp_alloc(ctr + CTR_SEQ_WORDS, have ? (len + 15u) >> 4 : 0u);
+		if (have && len) {
+			const uint32_t e = e0 + r;
+			g.e_src[e] = u; g.e_dst[e] = dst; g.e_len[e] = len; g.e_off[e] = off; g.e_count[e] = 0;
+			if (first != TAGPU_NONE) vedge[first] = e;
+			// first k + 1 bases: the oriented node k-mer, then c (asm_init_edge + first asm_append_edge_char)
+			uint32_t word = 0;
+			for (int b = 0; b <= k; ++b) {
+				const uint32_t base = b < k ? KO::base_at(x, k, b) : c;
+				word |= base << ((b & 15) << 1);
+				if ((b & 15) == 15 || b == k) {
+					atomicOr(g.e_seq + off + (b >> 4), word);
+					word = 0;
+				}
+			}
+		}
+		r += have ? 1u : 0u;
+	}
+}
+
+// ---------------------------------------------------------------- C5: interior vertices write their base and learn their edge
+template <int W>
+__global__ void __launch_bounds__(256) k_interior(KTab<W> t, int k, uint32_t n_vertices,
+						   const unsigned long long *__restrict__ jump, uint32_t *vedge, FlatGraph g)
+{
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= n_vertices) return;
+	const unsigned long long j = jump[v];
+	if (!((uint32_t)j & TAGPU_TERM) || ((uint32_t)j & ~TAGPU_TERM) == (TAGPU_NONE & ~TAGPU_TERM)) return; // node, empty or cycle
+	const unsigned long long jt = jump[v ^ 1u];
+	if (!((uint32_t)jt & TAGPU_TERM)) return;
+	const uint32_t v1 = ((uint32_t)jt & ~TAGPU_TERM) ^ 1u;          // first interior vertex of v's chain
+	const uint32_t e = vedge[v1];
+	if (e == TAGPU_NONE) return;                                    // chain not reachable from a node (cannot happen)
+	const uint32_t pos = k + 1 + (uint32_t)(jt >> 32);
+	const uint32_t m = ktab_mask_of<W>(t, v >> 1);
+	const uint32_t c = tagpu_only4((v & 1u) ? (m >> 4) : m);
+	atomicOr(g.e_seq + g.e_off[e] + (pos >> 4), c << ((pos & 15u) << 1));
+	vedge[v] = e;
+}
+
+// ---------------------------------------------------------------- C6: reverse-complement links (one thread per edge)
+template <int W>
+__global__ void __launch_bounds__(256) k_rc_links(KTab<W> t, int k, uint32_t n_edges,
+						   const uint32_t *__restrict__ node_slot, const uint32_t *__restrict__ node_ebase,
+						   FlatGraph g, unsigned long long *ctr)
+{
+	const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= n_edges) return;
+	const uint32_t len = g.e_len[e], pos = len - k - 1;
+	const uint32_t b = (g.e_seq[g.e_off[e] + (pos >> 4)] >> ((pos & 15u) << 1)) & 3u;
+	const uint32_t tv = g.e_dst[e] ^ 1u, ord = tv >> 1, o = tv & 1u;
+	const uint32_t m = ktab_mask_of<W>(t, node_slot[ord]);
+	const uint32_t nib = o ? (m >> 4) : (m & 15u), cb = 3u - b;
+	if (!((nib >> cb) & 1u)) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_RC_LINK); return; } // kmer_build.c:640 assert
+	g.e_rc[e] = node_ebase[ord] + (o ? DEG4(m) : 0u) + tagpu_rank4(nib, cb);
+}
+
+// ---------------------------------------------------------------- C7: edge counts (one thread per solid (k+1)-mer)
+template <int W>
+__global__ void __launch_bounds__(256) k_edge_counts(const Key<W> *__restrict__ solid, const uint32_t *__restrict__ solid_cnt,
+						      uint64_t n_solid, int k, KTab<W> t, const uint32_t *__restrict__ vL,
+						      const uint32_t *__restrict__ vR, const uint32_t *__restrict__ node_ord,
+						      const uint32_t *__restrict__ node_ebase, const uint32_t *__restrict__ vedge,
+						      FlatGraph g, unsigned long long *ctr)
+{
+	typedef KeyOps<W> KO;
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t on_edge = 0;
+	if (i < n_solid) {
+		const Key<W> x = solid[i];
+		const uint32_t cnt = solid_cnt[i];
+		const uint32_t vv[2] = { vL[i], vR[i] };
+		const uint32_t cc[2] = { KO::last_base(x), 3u - KO::first_base(x, k + 1) };
+#pragma unroll
+		for (int s = 0; s < 2; ++s) {
+			const uint32_t v = vv[s], slot = v >> 1, o = v & 1u, ord = node_ord[slot];
+			uint32_t e;
+			if (ord != TAGPU_NONE) {
+				const uint32_t m = ktab_mask_of<W>(t, slot), nib = o ? (m >> 4) : (m & 15u);
+				e = node_ebase[ord] + (o ? DEG4(m) : 0u) + tagpu_rank4(nib, cc[s]);
+			} else {
+				e = vedge[v];
+			}
+			if (e != TAGPU_NONE) {
+				atomicAdd(g.e_count + e, (unsigned long long)cnt);
+				on_edge = 1;
+			}
+		}
+	}
+	on_edge = __reduce_add_sync(0xffffffffu, on_edge);
+	if ((threadIdx.x & 31) == 0 && on_edge) atomicAdd(ctr + CTR_KP1_ON_EDGE, (unsigned long long)on_edge);
+}

@@ -1,0 +1,512 @@
+/*
+ * libtagpu host layer (plain C, like the reference): FASTQ/FASTA ingest, materialisation of the
+ * reference's struct asm_graph_t, the graph .bin and KMC database writers, and the reference's own
+ * entry points (see include/tagpu.h for the file:line of each interface replaced).
+ *
+ * No CPU fallback lives here: every compute step is a call into the CUDA layer (tagpu_kernels.cu).
+ * Errors follow the reference convention for these void entry points: log with file:line and
+ * exit(1) (/root/reference/src/log.c:207-210).
+ */
+#define _GNU_SOURCE
+#include <fcntl.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include "../../include/tagpu.h"
+#include "../../include/tagpu_graph.h"
+
+void *tagpu_pinned_alloc(size_t bytes);
+void tagpu_pinned_free(void *p);
+int tagpu_ctx_k(tagpu_ctx *ctx);
+int tagpu_ctx_K(tagpu_ctx *ctx);
+int tagpu_ctx_cutoff(tagpu_ctx *ctx);
+
+#define TAGPU_FATAL(...)                                                        \
+	do {                                                                    \
+		fprintf(stderr, "[tagpu] FATAL %s:%d: ", __FILE__, __LINE__);  \
+		fprintf(stderr, __VA_ARGS__);                                   \
+		fputc('\n', stderr);                                            \
+		exit(1);                                                        \
+	} while (0)
+
+static double now_s(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+/* ------------------------------------------------------------------ read ingest */
+
+struct read_file {
+	const char *path;
+	uint8_t *txt;      /* whole (inflated) file */
+	size_t n_txt;
+	size_t n_seq;      /* bytes this file contributes to the stream */
+	uint8_t *dst;      /* where they go */
+};
+
+static void slurp_file(struct read_file *f)
+{
+	int fd = open(f->path, O_RDONLY);
+	if (fd < 0)
+		TAGPU_FATAL("cannot open %s", f->path);
+	unsigned char magic[2] = { 0, 0 };
+	if (read(fd, magic, 2) < 0)
+		TAGPU_FATAL("cannot read %s", f->path);
+	lseek(fd, 0, SEEK_SET);
+	size_t n = 0, cap;
+	uint8_t *buf;
+	if (magic[0] == 0x1f && magic[1] == 0x8b) {
+		gzFile gz = gzdopen(fd, "rb");
+		gzbuffer(gz, 1 << 20);
+		cap = (size_t)1 << 26;
+		buf = malloc(cap);
+		for (;;) {
+			if (n == cap) {
+				cap *= 2;
+				buf = realloc(buf, cap);
+			}
+			if (!buf)
+				TAGPU_FATAL("out of host memory reading %s", f->path);
+			size_t room = cap - n;
+			int r = gzread(gz, buf + n, room > ((size_t)1 << 30) ? (1u << 30) : (unsigned)room);
+			if (r <= 0)
+				break;
+			n += (size_t)r;
+		}
+		gzclose(gz);
+	} else {
+		struct stat st;
+		fstat(fd, &st);
+		cap = (size_t)st.st_size + 1;
+		buf = malloc(cap);
+		if (!buf)
+			TAGPU_FATAL("out of host memory reading %s", f->path);
+		while (n < (size_t)st.st_size) {
+			ssize_t r = read(fd, buf + n, (size_t)st.st_size - n);
+			if (r <= 0)
+				break;
+			n += (size_t)r;
+		}
+		close(fd);
+	}
+	f->txt = buf;
+	f->n_txt = n;
+}
+
+/* Walks the sequence lines of a FASTQ (line 2 of every 4, cf. /root/reference/src/get_buffer.c:339-348)
+ * or FASTA text; with dst == NULL only sizes the output. */
+static size_t walk_sequences(const uint8_t *txt, size_t n, uint8_t *dst)
+{
+	size_t o = 0, p = 0, line = 0;
+	const int fasta = n && txt[0] == '>';
+	int open_record = 0; /* FASTA: sequence lines of one record are joined */
+	while (p < n) {
+		const uint8_t *nl = memchr(txt + p, '\n', n - p);
+		size_t e = nl ? (size_t)(nl - txt) : n;
+		size_t len = e - p;
+		if (len && txt[e - 1] == '\r')
+			--len;
+		if (fasta) {
+			if (len && txt[p] == '>') {
+				if (open_record) {
+					if (dst) dst[o] = '\n';
+					++o;
+					open_record = 0;
+				}
+			} else if (len) {
+				if (dst) memcpy(dst + o, txt + p, len);
+				o += len;
+				open_record = 1;
+			}
+		} else if ((line & 3) == 1) {
+			if (dst) {
+				memcpy(dst + o, txt + p, len);
+				dst[o + len] = '\n';
+			}
+			o += len + 1;
+		}
+		++line;
+		p = e + 1;
+	}
+	if (open_record) {
+		if (dst) dst[o] = '\n';
+		++o;
+	}
+	return o;
+}
+
+static void *ingest_phase1(void *raw)
+{
+	struct read_file *f = raw;
+	slurp_file(f);
+	f->n_seq = walk_sequences(f->txt, f->n_txt, NULL);
+	return NULL;
+}
+
+static void *ingest_phase2(void *raw)
+{
+	struct read_file *f = raw;
+	walk_sequences(f->txt, f->n_txt, f->dst);
+	free(f->txt);
+	f->txt = NULL;
+	return NULL;
+}
+
+int64_t tagpu_load_reads(int n_files, char **files, int n_threads, uint8_t **stream)
+{
+	(void)n_threads; /* one thread per file */
+	struct read_file *f = calloc(n_files, sizeof(*f));
+	pthread_t *th = calloc(n_files, sizeof(pthread_t));
+	for (int i = 0; i < n_files; ++i) {
+		f[i].path = files[i];
+		pthread_create(th + i, NULL, ingest_phase1, f + i);
+	}
+	size_t total = 0;
+	for (int i = 0; i < n_files; ++i) {
+		pthread_join(th[i], NULL);
+		total += f[i].n_seq;
+	}
+	uint8_t *s = tagpu_pinned_alloc(total + 64);
+	if (!s)
+		TAGPU_FATAL("cannot allocate %zu bytes of pinned host memory", total);
+	size_t o = 0;
+	for (int i = 0; i < n_files; ++i) {
+		f[i].dst = s + o;
+		o += f[i].n_seq;
+		pthread_create(th + i, NULL, ingest_phase2, f + i);
+	}
+	for (int i = 0; i < n_files; ++i)
+		pthread_join(th[i], NULL);
+	free(f);
+	free(th);
+	*stream = s;
+	return (int64_t)total;
+}
+
+void tagpu_free_reads(uint8_t *stream) { tagpu_pinned_free(stream); }
+
+/* ------------------------------------------------------------------ flat graph on the host */
+
+static int fetch_graph(tagpu_ctx *ctx, struct tagpu_flat_graph *h, struct tagpu_stats *st)
+{
+	tagpu_get_stats(ctx, st);
+	memset(h, 0, sizeof(*h));
+	uint64_t nn = st->n_v / 2, ne = st->n_e, nw = st->n_seq_words;
+	h->node_mask = malloc(nn + 1);
+	h->node_ebase = malloc((nn + 1) * 4);
+	h->e_src = malloc((ne + 1) * 4);
+	h->e_dst = malloc((ne + 1) * 4);
+	h->e_rc = malloc((ne + 1) * 4);
+	h->e_len = malloc((ne + 1) * 4);
+	h->e_count = malloc((ne + 1) * 8);
+	h->e_off = malloc((ne + 1) * 8);
+	h->e_seq = malloc((nw + 1) * 4);
+	if (!h->node_mask || !h->node_ebase || !h->e_src || !h->e_dst || !h->e_rc || !h->e_len || !h->e_count || !h->e_off || !h->e_seq)
+		return -1;
+	return tagpu_copy_graph(ctx, h);
+}
+
+static void free_flat(struct tagpu_flat_graph *h)
+{
+	free(h->node_mask); free(h->node_ebase); free(h->e_src); free(h->e_dst); free(h->e_rc);
+	free(h->e_len); free(h->e_count); free(h->e_off); free(h->e_seq);
+}
+
+static inline int popc4(unsigned x) { return __builtin_popcount(x & 15u); }
+
+/* Fills a caller-owned, uninitialised struct asm_graph_t exactly as build_asm_graph_from_kmhash leaves it
+ * (/root/reference/src/kmer_build.c:567-575): nodes/edges are single calloc blocks, every adj and every seq is its
+ * own allocation because later stages realloc/free them one by one. g->candidates is not touched. */
+int tagpu_fill_asm_graph(tagpu_ctx *ctx, struct asm_graph_t *g)
+{
+	struct tagpu_flat_graph h;
+	struct tagpu_stats st;
+	if (fetch_graph(ctx, &h, &st))
+		return -1;
+	const int64_t n_nodes = (int64_t)h.n_nodes, n_e = (int64_t)h.n_e;
+	g->ksize = tagpu_ctx_k(ctx);
+	g->aux_flag = 0;
+	g->bin_size = 0;
+	g->n_v = 2 * n_nodes;
+	g->n_e = n_e;
+	g->nodes = calloc(g->n_v ? g->n_v : 1, sizeof(struct asm_node_t));
+	g->edges = calloc(n_e ? n_e : 1, sizeof(struct asm_edge_t));
+	if (!g->nodes || !g->edges)
+		return -1;
+	for (int64_t i = 0; i < n_nodes; ++i) {
+		const unsigned m = h.node_mask[i];
+		int64_t e = h.node_ebase[i];
+		for (int o = 0; o < 2; ++o) {
+			struct asm_node_t *nd = g->nodes + 2 * i + o;
+			const int deg = popc4(o ? m >> 4 : m);
+			nd->rc_id = 2 * i + (o ^ 1);
+			nd->deg = deg;
+			nd->adj = malloc(deg * sizeof(gint_t)); /* malloc(0) for dead ends, like kmer_build.c:605-606 */
+			for (int j = 0; j < deg; ++j)
+				nd->adj[j] = e++;
+		}
+	}
+	for (int64_t e = 0; e < n_e; ++e) {
+		struct asm_edge_t *ed = g->edges + e;
+		const size_t words = ((size_t)h.e_len[e] + 15) >> 4;
+		ed->count = h.e_count[e];
+		ed->seq_len = h.e_len[e];
+		ed->seq = malloc(words * sizeof(uint32_t));
+		if (!ed->seq)
+			return -1;
+		memcpy(ed->seq, h.e_seq + h.e_off[e], words * sizeof(uint32_t));
+		ed->source = h.e_src[e];
+		ed->target = h.e_dst[e];
+		ed->rc_id = h.e_rc[e];
+		/* n_holes, p_holes, l_holes, barcodes, lock: zero from calloc (kmer_build.c:567) */
+	}
+	free_flat(&h);
+	return 0;
+}
+
+/* save_asm_graph layout (/root/reference/src/assembly_graph.c:1173-1248), streamed straight from the
+ * flat arrays without building the pointer-rich struct. */
+int tagpu_write_graph_bin(tagpu_ctx *ctx, const char *path)
+{
+	struct tagpu_flat_graph h;
+	struct tagpu_stats st;
+	if (fetch_graph(ctx, &h, &st))
+		return -1;
+	FILE *fp = fopen(path, "wb");
+	if (!fp) {
+		perror(path);
+		free_flat(&h);
+		return -1;
+	}
+	setvbuf(fp, NULL, _IOFBF, 1 << 22);
+	const uint32_t aux_flag = 0;
+	const int32_t ksize = tagpu_ctx_k(ctx);
+	const int64_t n_v = 2 * (int64_t)h.n_nodes, n_e = (int64_t)h.n_e;
+	fwrite("asmg", 1, 4, fp);
+	fwrite(&aux_flag, 4, 1, fp);
+	fwrite(&ksize, 4, 1, fp);
+	fwrite(&n_v, 8, 1, fp);
+	fwrite(&n_e, 8, 1, fp);
+	for (int64_t i = 0; i < (int64_t)h.n_nodes; ++i) {
+		const unsigned m = h.node_mask[i];
+		int64_t e = h.node_ebase[i];
+		for (int o = 0; o < 2; ++o) {
+			const int64_t rc_id = 2 * i + (o ^ 1), deg = popc4(o ? m >> 4 : m);
+			fwrite(&rc_id, 8, 1, fp);
+			fwrite(&deg, 8, 1, fp);
+			for (int64_t j = 0; j < deg; ++j, ++e)
+				fwrite(&e, 8, 1, fp);
+		}
+	}
+	for (int64_t e = 0; e < n_e; ++e) {
+		const int64_t src = h.e_src[e], dst = h.e_dst[e], rc = h.e_rc[e];
+		const uint64_t len8 = h.e_len[e]; /* seq_len plus the aliased, zero n_holes (App. F.2) */
+		const uint32_t n_holes = 0;
+		fwrite(&src, 8, 1, fp);
+		fwrite(&dst, 8, 1, fp);
+		fwrite(&rc, 8, 1, fp);
+		fwrite(&h.e_count[e], 8, 1, fp);
+		fwrite(&len8, 8, 1, fp);
+		fwrite(h.e_seq + h.e_off[e], 4, ((size_t)h.e_len[e] + 15) >> 4, fp);
+		fwrite(&n_holes, 4, 1, fp);
+	}
+	int rc = ferror(fp) ? -1 : 0;
+	fclose(fp);
+	free_flat(&h);
+	return rc;
+}
+
+/* ------------------------------------------------------------------ KMC database writer */
+
+struct solid_rec { uint64_t hi, lo; uint32_t cnt; };
+
+static int cmp_solid_rec(const void *a, const void *b)
+{
+	const struct solid_rec *x = a, *y = b;
+	if (x->hi != y->hi) return x->hi < y->hi ? -1 : 1;
+	if (x->lo != y->lo) return x->lo < y->lo ? -1 : 1;
+	return 0;
+}
+
+struct kmc_trailer {
+	uint32_t kmer_length, mode, counter_size, lut_prefix_length, signature_length, min_count, max_count;
+	uint64_t total_kmers;
+	uint8_t both_strands, pad8[3];
+	uint32_t pad32[6];
+	uint32_t version;
+} __attribute__((packed));
+
+/* Writes what /root/reference/src/KMC_reader.c:22-74 (prefix file) and :204-256 (suffix records) read back:
+ * records sorted by value, prefix LUT over the top lut_prefix_length bases, 4-byte little-endian counters. */
+int tagpu_write_kmc_db(tagpu_ctx *ctx, const char *working_dir)
+{
+	struct tagpu_stats st;
+	tagpu_get_stats(ctx, &st);
+	const int K = tagpu_ctx_K(ctx);
+	const uint64_t n = st.n_solid;
+	uint64_t *hi = malloc((n + 1) * 8), *lo = malloc((n + 1) * 8);
+	uint32_t *cnt = malloc((n + 1) * 4);
+	struct solid_rec *rec = malloc((n + 1) * sizeof(*rec));
+	if (!hi || !lo || !cnt || !rec || tagpu_copy_solid(ctx, hi, lo, cnt))
+		return -1;
+	for (uint64_t i = 0; i < n; ++i) {
+		rec[i].hi = hi[i]; rec[i].lo = lo[i]; rec[i].cnt = cnt[i];
+	}
+	free(hi); free(lo); free(cnt);
+	qsort(rec, n, sizeof(*rec), cmp_solid_rec);
+
+	const int p = (K % 4) + 4, suf_bases = K - p, suf_bytes = suf_bases / 4;
+	const uint64_t n_lut = (uint64_t)1 << (2 * p);
+	uint64_t *lut = calloc(n_lut + 1, 8);
+	char path[4096];
+	snprintf(path, sizeof(path), "%s/KMC_%d_count.kmc_suf", working_dir, K);
+	FILE *fs = fopen(path, "wb");
+	if (!fs) { perror(path); return -1; }
+	setvbuf(fs, NULL, _IOFBF, 1 << 22);
+	fwrite("KMCS", 1, 4, fs);
+	for (uint64_t i = 0; i < n; ++i) {
+		unsigned __int128 x = ((unsigned __int128)rec[i].hi << 64) | rec[i].lo;
+		uint8_t out[40];
+		++lut[(uint64_t)(x >> (2 * suf_bases)) + 1];
+		for (int j = 0; j < suf_bytes; ++j)
+			out[j] = (uint8_t)(x >> (8 * (suf_bytes - 1 - j)));
+		memcpy(out + suf_bytes, &rec[i].cnt, 4);
+		fwrite(out, 1, suf_bytes + 4, fs);
+	}
+	fwrite("KMCS", 1, 4, fs);
+	fclose(fs);
+	free(rec);
+	for (uint64_t i = 0; i < n_lut; ++i)
+		lut[i + 1] += lut[i];
+	snprintf(path, sizeof(path), "%s/KMC_%d_count.kmc_pre", working_dir, K);
+	FILE *fp = fopen(path, "wb");
+	if (!fp) { perror(path); return -1; }
+	const uint32_t sigmap[2] = { 0, 0 };
+	struct kmc_trailer t;
+	memset(&t, 0, sizeof(t));
+	t.kmer_length = K; t.counter_size = 4; t.lut_prefix_length = p; t.signature_length = 0;
+	t.min_count = tagpu_ctx_cutoff(ctx); t.max_count = 0xffffffffu; t.total_kmers = n; t.both_strands = 1;
+	t.version = 0x200;
+	const uint32_t trailer_size = sizeof(t);
+	fwrite("KMCP", 1, 4, fp);
+	fwrite(lut, 8, n_lut + 1, fp);
+	fwrite(sigmap, 4, 2, fp);
+	fwrite(&t, sizeof(t), 1, fp);
+	fwrite(&trailer_size, 4, 1, fp);
+	fwrite("KMCP", 1, 4, fp);
+	fclose(fp);
+	free(lut);
+	return 0;
+}
+
+/* ------------------------------------------------------------------ the reference's entry points */
+
+static tagpu_ctx *g_ctx;
+
+static tagpu_ctx *global_ctx(void)
+{
+	if (!g_ctx) {
+		g_ctx = tagpu_create(-1);
+		if (!g_ctx)
+			TAGPU_FATAL("no usable CUDA device; libtagpu has no CPU path");
+		const char *ci = getenv("TAGPU_CUTOFF");
+		if (ci)
+			tagpu_set_cutoff(g_ctx, atoi(ci));
+	}
+	return g_ctx;
+}
+
+static int64_t gather_files(int n_files, char **files_1, char **files_2, int n_threads, uint8_t **stream)
+{
+	/* files_1[0..n) ++ files_2[0..n): /root/reference/src/kmer_build.c:733-735.  n_files < 0 is the reference's dormant
+	 * "contig file appended" mode (kmer_build.c:677-679,722-731) that no CLI path sets. */
+	if (n_files < 0)
+		TAGPU_FATAL("n_files < 0 (contig-file mode) is not supported by the GPU path");
+	char **all = malloc(2 * (size_t)n_files * sizeof(char *));
+	memcpy(all, files_1, n_files * sizeof(char *));
+	memcpy(all + n_files, files_2, n_files * sizeof(char *));
+	int64_t n = tagpu_load_reads(2 * n_files, all, n_threads, stream);
+	free(all);
+	return n;
+}
+
+static void stage_entry(int ksize, int n_threads, int n_files, char **files_1, char **files_2, char *work_dir,
+			struct asm_graph_t *g, int skip_counts)
+{
+	tagpu_ctx *ctx = global_ctx();
+	double t0 = now_s();
+	uint8_t *stream;
+	int64_t n = gather_files(n_files, files_1, files_2, n_threads, &stream);
+	double t1 = now_s();
+	tagpu_set_skip_counts(ctx, skip_counts);
+	if (tagpu_build_host(ctx, stream, (uint64_t)n, ksize))
+		TAGPU_FATAL("GPU graph build failed: %s", tagpu_last_error(ctx));
+	tagpu_free_reads(stream);
+	double t2 = now_s();
+	if (getenv("TAGPU_WRITE_KMC_DB") && tagpu_write_kmc_db(ctx, work_dir))
+		TAGPU_FATAL("cannot write the KMC database into %s", work_dir);
+	struct tagpu_stats st;
+	tagpu_get_stats(ctx, &st);
+	/* the reference's three known-answer log lines: kmer_build.c:758,763,772 */
+	fprintf(stderr, "[tagpu] Number of kmer: %lu\n", (unsigned long)st.n_kmers);
+	fprintf(stderr, "[tagpu] Number of nodes: %ld; Number of edges: %ld\n", (long)st.n_v, (long)st.n_e);
+	if (!skip_counts)
+		fprintf(stderr, "[tagpu] Number of (k+1)-mer on edge: %lu\n", (unsigned long)st.n_kp1_on_edge);
+	if (tagpu_fill_asm_graph(ctx, g))
+		TAGPU_FATAL("cannot materialise the assembly graph: %s", tagpu_last_error(ctx));
+	double t3 = now_s();
+	fprintf(stderr, "[tagpu] k=%d: %lu (k+1)-mer instances, %lu solid; ingest %.3f s, H2D+GPU %.3f s (device %.3f ms), "
+			"graph materialisation %.3f s\n", ksize, (unsigned long)st.n_instances, (unsigned long)st.n_solid,
+		t1 - t0, t2 - t1, st.ms_total, t3 - t2);
+}
+
+void build_graph_from_scratch(int ksize, int n_threads, int mmem, int n_files, char **files_1, char **files_2,
+			      char *work_dir, struct asm_graph_t *g)
+{
+	(void)mmem;
+	stage_entry(ksize, n_threads, n_files, files_1, files_2, work_dir, g, 0);
+}
+
+void build_graph_from_scratch_without_count(int ksize, int n_threads, int mmem, int n_files, char **files_1,
+					    char **files_2, char *work_dir, struct asm_graph_t *g)
+{
+	(void)mmem;
+	stage_entry(ksize, n_threads, n_files, files_1, files_2, work_dir, g, 1);
+}
+
+void build_initial_graph(struct opt_proc_t *opt, int ksize, struct asm_graph_t *g)
+{
+	double t0 = now_s();
+	build_graph_from_scratch(ksize, opt->n_threads, opt->mmem, opt->n_files, opt->files_1, opt->files_2, opt->out_dir, g);
+	fprintf(stderr, "[tagpu] Building graph time: %.3f\n", now_s() - t0); /* kmer_build.c:844 */
+}
+
+int KMC_build_kmer_database(int ksize, const char *working_dir, int n_threads, int mmem, int n_files, char **files)
+{
+	(void)mmem;
+	tagpu_ctx *ctx = global_ctx();
+	uint8_t *stream;
+	int64_t n = tagpu_load_reads(n_files, files, n_threads, &stream);
+	if (tagpu_count_host(ctx, stream, (uint64_t)n, ksize))
+		TAGPU_FATAL("GPU k-mer counting failed: %s", tagpu_last_error(ctx));
+	tagpu_free_reads(stream);
+	if (tagpu_write_kmc_db(ctx, working_dir))
+		TAGPU_FATAL("cannot write the KMC database into %s", working_dir);
+	return 0;
+}
+
+int KMC_arg_kmer_count(int argc, char *argv[])
+{
+	(void)argc; (void)argv;
+	fprintf(stderr, "[tagpu] KMC_arg_kmer_count is not on the hot path and is not implemented\n");
+	return -1;
+}

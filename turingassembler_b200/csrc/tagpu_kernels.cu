@@ -1,0 +1,394 @@
+// libtagpu device layer: owns the CUDA context state, launches the sm_100a kernels and exposes the
+// native half of include/tagpu.h.  The reference-facing entry points and all file I/O live in
+// tagpu_host.c (plain C), which only calls the functions declared in include/tagpu.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/tagpu.h"
+#include "tagpu_count_v1.cuh"
+#include "tagpu_extract.cuh"
+#include "tagpu_graph.cuh"
+#include "tagpu_key.cuh"
+
+struct Buf {
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
+struct tagpu_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr, own_stream = nullptr;
+	int ci = 2, skip_counts = 0;
+	int k = 0, K = 0, W = 0;
+	char err[512] = { 0 };
+	unsigned long long *d_ctr = nullptr, *h_ctr = nullptr;
+	Buf seq, ctab, clist, solid_key, solid_cnt, kt_keys, kt_mask, node_ord, node_slot, node_ebase, vL, vR, jump, vsucc,
+		vedge, e_src, e_dst, e_rc, e_len, e_count, e_off, e_seq;
+	uint64_t ctab_slots = 0;
+	int ctab_W = 0;
+	uint32_t kt_slots = 0;
+	bool have_count = false, have_graph = false;
+	tagpu_stats st;
+	cudaEvent_t ev[4];
+	uint64_t launches = 0;
+};
+
+static int fail(tagpu_ctx *c, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(c->err, sizeof(c->err), fmt, ap);
+	va_end(ap);
+	fprintf(stderr, "[tagpu] ERROR: %s\n", c->err);
+	return -1;
+}
+
+#define CU(call)                                                                                         \
+	do {                                                                                             \
+		cudaError_t e_ = (call);                                                                 \
+		if (e_ != cudaSuccess)                                                                   \
+			return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+static int ensure(tagpu_ctx *ctx, Buf &b, size_t bytes, bool *grew = nullptr)
+{
+	if (grew) *grew = false;
+	if (bytes <= b.cap && b.p) return 0;
+	if (b.p) CU(cudaFree(b.p));
+	b.p = nullptr;
+	b.cap = 0;
+	size_t want = bytes < 256 ? 256 : bytes;
+	CU(cudaMalloc(&b.p, want));
+	b.cap = want;
+	if (grew) *grew = true;
+	return 0;
+}
+
+static uint64_t pow2_at_least(uint64_t x)
+{
+	uint64_t p = 1;
+	while (p < x) p <<= 1;
+	return p;
+}
+
+extern "C" tagpu_ctx *tagpu_create(int device)
+{
+	int n_dev = 0;
+	cudaError_t e = cudaGetDeviceCount(&n_dev);
+	if (e != cudaSuccess || n_dev == 0) {
+		fprintf(stderr, "[tagpu] ERROR: no CUDA device (%s); libtagpu has no CPU fallback\n",
+			e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+		return nullptr;
+	}
+	tagpu_ctx *ctx = new tagpu_ctx();
+	if (device < 0) cudaGetDevice(&device);
+	ctx->device = device;
+	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaMalloc(&ctx->d_ctr, CTR_TOTAL * sizeof(unsigned long long)) != cudaSuccess ||
+	    cudaMallocHost(&ctx->h_ctr, CTR_TOTAL * sizeof(unsigned long long)) != cudaSuccess) {
+		fprintf(stderr, "[tagpu] ERROR: cannot initialise device %d: %s\n", device, cudaGetErrorString(cudaGetLastError()));
+		delete ctx;
+		return nullptr;
+	}
+	ctx->stream = ctx->own_stream;
+	for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+	memset(&ctx->st, 0, sizeof(ctx->st));
+	return ctx;
+}
+
+extern "C" void tagpu_destroy(tagpu_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	Buf *bufs[] = { &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
+			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
+	for (Buf *b : bufs)
+		if (b->p) cudaFree(b->p);
+	cudaFree(ctx->d_ctr);
+	cudaFreeHost(ctx->h_ctr);
+	for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
+	cudaStreamDestroy(ctx->own_stream);
+	delete ctx;
+}
+
+extern "C" void tagpu_set_stream(tagpu_ctx *ctx, void *s) { ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; }
+extern "C" void tagpu_set_cutoff(tagpu_ctx *ctx, int ci) { ctx->ci = ci < 1 ? 1 : ci; }
+extern "C" void tagpu_set_skip_counts(tagpu_ctx *ctx, int skip) { ctx->skip_counts = skip; }
+extern "C" const char *tagpu_last_error(tagpu_ctx *ctx) { return ctx->err; }
+
+static int read_counters(tagpu_ctx *ctx)
+{
+	CU(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, CTR_TOTAL * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	if (ctx->h_ctr[CTR_ERROR])
+		return fail(ctx, "device-side invariant violated (error bits 0x%llx)", ctx->h_ctr[CTR_ERROR]);
+	return 0;
+}
+
+#define LAUNCH(kernel, grid, block, ...)                                                   \
+	do {                                                                               \
+		kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                  \
+		++ctx->launches;                                                           \
+		CU(cudaGetLastError());                                                    \
+	} while (0)
+
+// ------------------------------------------------------------------------------------------------ count stage
+template <int W>
+static int count_stage(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n)
+{
+	const int K = ctx->K;
+	uint64_t slots = pow2_at_least(n / 2 + 1024);
+	if (slots < (1ull << 20)) slots = 1ull << 20;
+	if (slots > (1ull << 32)) return fail(ctx, "input too large for the direct count table (%llu bytes)", (unsigned long long)n);
+	bool grew;
+	if (ensure(ctx, ctx->ctab, slots * sizeof(CSlot<W>), &grew)) return -1;
+	if (grew || ctx->ctab_W != W || ctx->ctab_slots != slots) {
+		CU(cudaMemsetAsync(ctx->ctab.p, 0, ctx->ctab.cap, ctx->stream)); // once; afterwards kept clean by k_compact_solid
+		ctx->ctab_W = W;
+		ctx->ctab_slots = slots;
+	}
+	if (ensure(ctx, ctx->clist, (n + 1024) * sizeof(uint32_t))) return -1;
+	const uint64_t n_tiles = (n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES;
+	if (n_tiles)
+		LAUNCH(k_count_direct<W>, (unsigned)n_tiles, TAGPU_TILE_THREADS, d_seq, n, K, (CSlot<W> *)ctx->ctab.p, slots - 1,
+		       (uint32_t *)ctx->clist.p, ctx->d_ctr);
+	if (read_counters(ctx)) return -1;
+	const uint64_t n_distinct = ctx->h_ctr[CTR_DISTINCT];
+	if (ensure(ctx, ctx->solid_key, (n_distinct + 1) * sizeof(Key<W>))) return -1;
+	if (ensure(ctx, ctx->solid_cnt, (n_distinct + 1) * sizeof(uint32_t))) return -1;
+	if (n_distinct)
+		LAUNCH(k_compact_solid<W>, (unsigned)((n_distinct + 1023) / 1024), 1024, (CSlot<W> *)ctx->ctab.p,
+		       (const uint32_t *)ctx->clist.p, ctx->d_ctr, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p,
+		       (uint32_t *)ctx->solid_cnt.p, ctx->d_ctr);
+	if (read_counters(ctx)) return -1;
+	ctx->st.n_instances = ctx->h_ctr[CTR_INSTANCES];
+	ctx->st.n_distinct = n_distinct;
+	ctx->st.n_solid = ctx->h_ctr[CTR_SOLID];
+	ctx->st.sum_solid = ctx->h_ctr[CTR_SUM_SOLID];
+	ctx->have_count = true;
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ graph stage
+template <int W>
+static int graph_stage(tagpu_ctx *ctx)
+{
+	const int k = ctx->k;
+	const uint64_t n_solid = ctx->st.n_solid;
+	uint64_t slots64 = pow2_at_least(3 * n_solid + 1024);
+	if (slots64 > (1ull << 29)) return fail(ctx, "k-mer table would need %llu slots (> 2^29)", (unsigned long long)slots64);
+	const uint32_t n_slots = (uint32_t)slots64, n_vert = 2 * n_slots;
+	ctx->kt_slots = n_slots;
+	if (ensure(ctx, ctx->kt_keys, (size_t)n_slots * sizeof(Key<W>)) || ensure(ctx, ctx->kt_mask, n_slots) ||
+	    ensure(ctx, ctx->node_ord, (size_t)n_slots * 4) || ensure(ctx, ctx->vL, (n_solid + 1) * 4) ||
+	    ensure(ctx, ctx->vR, (n_solid + 1) * 4) || ensure(ctx, ctx->node_slot, (2 * n_solid + 1) * 4) ||
+	    ensure(ctx, ctx->node_ebase, (2 * n_solid + 1) * 4) || ensure(ctx, ctx->jump, (size_t)n_vert * 8) ||
+	    ensure(ctx, ctx->vsucc, (size_t)n_vert * 4) || ensure(ctx, ctx->vedge, (size_t)n_vert * 4))
+		return -1;
+	KTab<W> t;
+	t.keys = (Key<W> *)ctx->kt_keys.p;
+	t.mask32 = (uint32_t *)ctx->kt_mask.p;
+	t.slot_mask = n_slots - 1;
+	CU(cudaMemsetAsync(t.keys, 0, (size_t)n_slots * sizeof(Key<W>), ctx->stream));
+	CU(cudaMemsetAsync(t.mask32, 0, n_slots, ctx->stream));
+	CU(cudaMemsetAsync(ctx->vedge.p, 0xff, (size_t)n_vert * 4, ctx->stream));
+	uint32_t *node_ord = (uint32_t *)ctx->node_ord.p, *node_slot = (uint32_t *)ctx->node_slot.p,
+		 *node_ebase = (uint32_t *)ctx->node_ebase.p, *vL = (uint32_t *)ctx->vL.p, *vR = (uint32_t *)ctx->vR.p,
+		 *vsucc = (uint32_t *)ctx->vsucc.p, *vedge = (uint32_t *)ctx->vedge.p;
+	unsigned long long *jump = (unsigned long long *)ctx->jump.p, *ctr = ctx->d_ctr;
+	const Key<W> *solid = (const Key<W> *)ctx->solid_key.p;
+
+	if (n_solid) LAUNCH(k_insert_kmers<W>, (unsigned)((n_solid + 255) / 256), 256, solid, n_solid, k, t, vL, vR, ctr);
+	LAUNCH(k_classify<W>, n_slots / 256, 256, t, node_ord, node_slot, node_ebase, ctr);
+	LAUNCH(k_build_succ<W>, n_vert / 256, 256, t, k, node_ord, jump, vsucc, ctr);
+	const int max_rounds = 40;
+	for (int r = 0; r < max_rounds; ++r)
+		LAUNCH(k_jump_round, n_vert / 256, 256, jump, n_vert, r ? ctr + CTR_JUMP_FLAGS + r - 1 : nullptr, ctr + CTR_JUMP_FLAGS + r);
+	if (read_counters(ctx)) return -1;
+	const uint64_t n_nodes = ctx->h_ctr[CTR_NODES], n_e = ctx->h_ctr[CTR_EDGES];
+	ctx->st.n_kmers = ctx->h_ctr[CTR_KMERS];
+	ctx->st.n_v = 2 * n_nodes;
+	ctx->st.n_e = n_e;
+	uint64_t rounds = 0;
+	while (rounds < (uint64_t)max_rounds && ctx->h_ctr[CTR_JUMP_FLAGS + rounds]) ++rounds;
+	ctx->st.jump_rounds = rounds + 1;
+	if (n_e > 0xfffffff0ull) return fail(ctx, "too many edges (%llu)", (unsigned long long)n_e);
+	const uint64_t seq_cap = (n_e * (uint64_t)k + 2 * n_solid) / 16 + n_e + 16;
+	if (ensure(ctx, ctx->e_src, (n_e + 1) * 4) || ensure(ctx, ctx->e_dst, (n_e + 1) * 4) || ensure(ctx, ctx->e_rc, (n_e + 1) * 4) ||
+	    ensure(ctx, ctx->e_len, (n_e + 1) * 4) || ensure(ctx, ctx->e_count, (n_e + 1) * 8) || ensure(ctx, ctx->e_off, (n_e + 1) * 8) ||
+	    ensure(ctx, ctx->e_seq, seq_cap * 4))
+		return -1;
+	FlatGraph g;
+	g.e_src = (uint32_t *)ctx->e_src.p; g.e_dst = (uint32_t *)ctx->e_dst.p; g.e_rc = (uint32_t *)ctx->e_rc.p;
+	g.e_len = (uint32_t *)ctx->e_len.p; g.e_count = (unsigned long long *)ctx->e_count.p;
+	g.e_off = (unsigned long long *)ctx->e_off.p; g.e_seq = (uint32_t *)ctx->e_seq.p;
+	CU(cudaMemsetAsync(g.e_seq, 0, seq_cap * 4, ctx->stream));
+	if (n_nodes)
+		LAUNCH(k_edge_heads<W>, (unsigned)((2 * n_nodes + 127) / 128), 128, t, k, (uint32_t)n_nodes, node_ord, node_slot, node_ebase,
+		       jump, vsucc, vedge, g, ctr);
+	LAUNCH(k_interior<W>, n_vert / 256, 256, t, k, n_vert, jump, vedge, g);
+	if (n_e) LAUNCH(k_rc_links<W>, (unsigned)((n_e + 255) / 256), 256, t, k, (uint32_t)n_e, node_slot, node_ebase, g, ctr);
+	if (n_solid && !ctx->skip_counts)
+		LAUNCH(k_edge_counts<W>, (unsigned)((n_solid + 255) / 256), 256, solid, (const uint32_t *)ctx->solid_cnt.p, n_solid, k, t,
+		       vL, vR, node_ord, node_ebase, vedge, g, ctr);
+	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+	if (read_counters(ctx)) return -1;
+	ctx->st.n_seq_words = ctx->h_ctr[CTR_SEQ_WORDS];
+	ctx->st.n_kp1_on_edge = ctx->h_ctr[CTR_KP1_ON_EDGE];
+	if (ctx->st.n_seq_words > seq_cap) return fail(ctx, "edge sequence buffer overflow (%llu > %llu words)",
+						       (unsigned long long)ctx->st.n_seq_words, (unsigned long long)seq_cap);
+	ctx->have_graph = true;
+	return 0;
+}
+
+static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool with_graph)
+{
+	CU(cudaSetDevice(ctx->device));
+	if (K < 18 || K > 64) return fail(ctx, "unsupported k-mer size: k + 1 = %d (supported: 18..64)", K);
+	ctx->K = K;
+	ctx->k = K - 1;
+	ctx->W = K <= 32 ? 1 : 2;
+	ctx->have_count = ctx->have_graph = false;
+	ctx->launches = 0;
+	ctx->err[0] = 0;
+	memset(&ctx->st, 0, sizeof(ctx->st));
+	CU(cudaMemsetAsync(ctx->d_ctr, 0, CTR_TOTAL * sizeof(unsigned long long), ctx->stream));
+	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+	int rc = ctx->W == 1 ? count_stage<1>(ctx, d_seq, n) : count_stage<2>(ctx, d_seq, n);
+	if (rc) return rc;
+	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+	if (with_graph) {
+		rc = ctx->W == 1 ? graph_stage<1>(ctx) : graph_stage<2>(ctx);
+		if (rc) return rc;
+	} else {
+		CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+	}
+	CU(cudaEventElapsedTime(&ctx->st.ms_count, ctx->ev[0], ctx->ev[1]));
+	CU(cudaEventElapsedTime(&ctx->st.ms_graph, ctx->ev[1], ctx->ev[2]));
+	CU(cudaEventElapsedTime(&ctx->st.ms_total, ctx->ev[0], ctx->ev[2]));
+	ctx->st.gpu_launches = ctx->launches;
+	return 0;
+}
+
+static int upload(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n)
+{
+	CU(cudaSetDevice(ctx->device));
+	if (ensure(ctx, ctx->seq, n + 64)) return -1;
+	if (n) CU(cudaMemcpyAsync(ctx->seq.p, h_seq, n, cudaMemcpyHostToDevice, ctx->stream));
+	return 0;
+}
+
+extern "C" int tagpu_build_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int k) { return run(ctx, d_seq, n, k + 1, true); }
+extern "C" int tagpu_count_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K) { return run(ctx, d_seq, n, K, false); }
+extern "C" int tagpu_build_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n, int k)
+{
+	if (upload(ctx, h_seq, n)) return -1;
+	return run(ctx, (const uint8_t *)ctx->seq.p, n, k + 1, true);
+}
+extern "C" int tagpu_count_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n, int K)
+{
+	if (upload(ctx, h_seq, n)) return -1;
+	return run(ctx, (const uint8_t *)ctx->seq.p, n, K, false);
+}
+
+extern "C" int tagpu_get_stats(tagpu_ctx *ctx, struct tagpu_stats *out)
+{
+	*out = ctx->st;
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device -> host
+extern "C" int tagpu_copy_solid(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint32_t *count)
+{
+	if (!ctx->have_count) return fail(ctx, "no count result to copy");
+	CU(cudaSetDevice(ctx->device));
+	const uint64_t n = ctx->st.n_solid;
+	if (!n) return 0;
+	CU(cudaMemcpyAsync(count, ctx->solid_cnt.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (ctx->W == 1) {
+		CU(cudaMemcpyAsync(lo, ctx->solid_key.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		memset(hi, 0, n * 8);
+	} else {
+		std::vector<Key<2>> tmp(n);
+		CU(cudaMemcpyAsync(tmp.data(), ctx->solid_key.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		for (uint64_t i = 0; i < n; ++i) { hi[i] = tmp[i].hi; lo[i] = tmp[i].lo; }
+	}
+	return 0;
+}
+
+extern "C" int tagpu_copy_kmers(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint8_t *mask)
+{
+	if (!ctx->have_graph) return fail(ctx, "no graph result to copy");
+	CU(cudaSetDevice(ctx->device));
+	const uint32_t n_slots = ctx->kt_slots;
+	std::vector<uint8_t> m(n_slots);
+	std::vector<uint64_t> keys((size_t)n_slots * ctx->W);
+	CU(cudaMemcpyAsync(m.data(), ctx->kt_mask.p, n_slots, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(keys.data(), ctx->kt_keys.p, (size_t)n_slots * 8 * ctx->W, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	uint64_t o = 0;
+	for (uint32_t s = 0; s < n_slots; ++s) {
+		uint64_t l = keys[(size_t)s * ctx->W], h = ctx->W == 2 ? keys[(size_t)s * 2 + 1] : 0;
+		if ((l | h) == 0) continue;
+		if (o >= ctx->st.n_kmers) return fail(ctx, "k-mer table holds more entries than counted");
+		lo[o] = ~l;
+		hi[o] = ctx->W == 2 ? ~h : 0;
+		mask[o] = m[s];
+		++o;
+	}
+	if (o != ctx->st.n_kmers) return fail(ctx, "k-mer table holds %llu entries, counted %llu", (unsigned long long)o, (unsigned long long)ctx->st.n_kmers);
+	return 0;
+}
+
+extern "C" int tagpu_copy_graph(tagpu_ctx *ctx, struct tagpu_flat_graph *h)
+{
+	if (!ctx->have_graph) return fail(ctx, "no graph result to copy");
+	CU(cudaSetDevice(ctx->device));
+	const uint64_t n_nodes = ctx->st.n_v / 2, n_e = ctx->st.n_e, n_w = ctx->st.n_seq_words;
+	h->n_nodes = n_nodes; h->n_e = n_e; h->n_seq_words = n_w;
+	if (n_nodes) {
+		std::vector<uint32_t> slot(n_nodes);
+		std::vector<uint8_t> m(ctx->kt_slots);
+		CU(cudaMemcpyAsync(slot.data(), ctx->node_slot.p, n_nodes * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaMemcpyAsync(m.data(), ctx->kt_mask.p, ctx->kt_slots, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaMemcpyAsync(h->node_ebase, ctx->node_ebase.p, n_nodes * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		for (uint64_t i = 0; i < n_nodes; ++i) h->node_mask[i] = m[slot[i]];
+	}
+	if (n_e) {
+		CU(cudaMemcpyAsync(h->e_src, ctx->e_src.p, n_e * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaMemcpyAsync(h->e_dst, ctx->e_dst.p, n_e * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaMemcpyAsync(h->e_rc, ctx->e_rc.p, n_e * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaMemcpyAsync(h->e_len, ctx->e_len.p, n_e * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaMemcpyAsync(h->e_count, ctx->e_count.p, n_e * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaMemcpyAsync(h->e_off, ctx->e_off.p, n_e * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaMemcpyAsync(h->e_seq, ctx->e_seq.p, n_w * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CU(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+// pinned host allocation for the FASTQ loader in tagpu_host.c (keeps cuda_runtime.h out of the C file)
+extern "C" void *tagpu_pinned_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+extern "C" void tagpu_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" int tagpu_ctx_k(tagpu_ctx *ctx) { return ctx->k; }
+extern "C" int tagpu_ctx_K(tagpu_ctx *ctx) { return ctx->K; }
+extern "C" int tagpu_ctx_cutoff(tagpu_ctx *ctx) { return ctx->ci; }
