@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json metric: k-mers/sec counted + graph built; HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C1|small]
+
+One "step" = one pass of the whole path (count -> solid set -> edge masks -> unitig graph, flat arrays in HBM) over one
+batch of synthetic reads.  At N = 1 the workload is BASELINE.json configs[1] ("C2": E. coli-scale, 2 M pairs x 151 bp,
+k0 = 45, 128-bit keys).  `value` is measured with the read stream already resident in HBM; `e2e` is the same metric
+through the host-buffer C-ABI call (pinned host stream -> H2D -> build -> stats back).  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: genome_len, n_pairs, k   ("small" is for quick checks only)
+    "C2": dict(genome_len=4_641_652, n_pairs=2_000_000, k=45, seed=1),
+    "C1": dict(genome_len=4_641_652, n_pairs=2_000_000, k=31, seed=1),
+    "small": dict(genome_len=400_000, n_pairs=150_000, k=45, seed=1),
+}
+L = 151
+
+
+def gen_reads_gpu(torch, genome_len, n_pairs, seed, device, sub_err=0.005, n_rate=0.02, n_repeats=40, repeat_len=600):
+    """Synthetic paired reads generated on the device (SURVEY.md §8d shape: uniform genome + planted 600 bp repeats,
+    insert ~U[300,500], 0.5 % substitutions, 2 % of reads carry one N).  Returns a uint8 tensor: R1 reads then R2 reads,
+    each followed by a newline."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    genome = torch.randint(0, 4, (genome_len,), generator=g, device=device, dtype=torch.uint8)
+    src = torch.randint(0, genome_len - repeat_len, (n_repeats,), generator=g, device=device)
+    dst = torch.randint(0, genome_len - repeat_len, (n_repeats,), generator=g, device=device)
+    for a, b in zip(src.tolist(), dst.tolist()):
+        genome[b:b + repeat_len] = genome[a:a + repeat_len].clone()
+    lut = torch.tensor(list(b"ACGT"), device=device, dtype=torch.uint8)
+    out = torch.empty((2 * n_pairs, L + 1), device=device, dtype=torch.uint8)
+    chunk = 250_000
+    idx = torch.arange(L, device=device)[None, :]
+    for s in range(0, n_pairs, chunk):
+        m = min(chunk, n_pairs - s)
+        ins = torch.randint(300, 501, (m,), generator=g, device=device)
+        pos = (torch.rand(m, generator=g, device=device, dtype=torch.float64) * (genome_len - ins)).long()
+        flip = torch.rand(m, generator=g, device=device) < 0.5
+        fwd = genome[pos[:, None] + idx]
+        rev = 3 - genome[(pos + ins - 1)[:, None] - idx]
+        for mate, codes in ((0, torch.where(flip[:, None], rev, fwd)), (1, torch.where(flip[:, None], fwd, rev))):
+            err = torch.rand((m, L), generator=g, device=device) < sub_err
+            rnd = torch.randint(0, 4, (m, L), generator=g, device=device, dtype=torch.uint8)
+            codes = torch.where(err, rnd, codes)
+            chars = lut[codes.long()]
+            with_n = torch.rand(m, generator=g, device=device) < n_rate
+            n_pos = torch.randint(0, L, (m,), generator=g, device=device)
+            rows = torch.nonzero(with_n).squeeze(1)
+            chars[rows, n_pos[rows]] = ord("N")
+            out[mate * n_pairs + s: mate * n_pairs + s + m, :L] = chars
+    out[:, L] = ord("\n")
+    return out.reshape(-1)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def algorithmic_bytes(st, k, n_stream):
+    """Bytes = N_i (B_in + W + 8) + N_distinct (W + 4) + N_solid (3W + 28) + N_kmer (W + 33.5)."""
+    K = k + 1
+    W = 8 if K <= 32 else 16
+    b_in = n_stream / max(st["n_instances"], 1)          # ASCII bytes actually read per window
+    count = st["n_instances"] * (b_in + W + 8) + st["n_distinct"] * (W + 4)
+    graph = st["n_solid"] * (3 * W + 28) + st["n_kmers"] * (W + 33.5)
+    return count, graph
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(host_stream, k, target_s=15.0):
+    """The oracle's multithreaded KMC-stage restatement + graph restatement, timed on a bounded sample of the same
+    workload on this box's host cores (kind 'port')."""
+    import numpy as np
+    import _oracle
+    ora = _oracle.load()
+    cores = os.cpu_count() or 1
+    n_reads_total = host_stream.size // (L + 1)
+    n_reads = min(n_reads_total, 400_000)
+    # same coverage profile as the full set: take R1 and R2 halves proportionally
+    half = n_reads_total // 2
+    take = n_reads // 2
+    sample = np.concatenate([host_stream[: take * (L + 1)], host_stream[half * (L + 1): (half + take) * (L + 1)]])
+    t0 = time.perf_counter()
+    cnt = ora.count(sample, k + 1, ci=2, threads=cores)
+    t1 = time.perf_counter()
+    g = ora.graph(k, cnt["hi"], cnt["lo"], cnt["count"])
+    t2 = time.perf_counter()
+    ora.free_graph(g)
+    return {"value": cnt["n_instances"] / (t2 - t0), "unit": "kmers/s", "cores": cores, "kind": "port",
+            "sample": f"{2 * take} of {n_reads_total} reads ({cnt['n_instances']} (k+1)-mer instances): count {t1 - t0:.2f} s on "
+                      f"{cores} threads + graph {t2 - t1:.2f} s on 1 thread"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref/TA_ref build_0 = unmodified reference
+    sources + oracle/kmc_cpu.c for the absent libkmc.a; else the oracle port) on a bounded sample, all host threads."""
+    import numpy as np
+    import _oracle
+    import _reads
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    n_pairs = min(wl["n_pairs"], 100_000)
+    stream = _reads.gen_stream(wl["genome_len"] // 20, n_pairs, seed=wl["seed"], n_repeats=2)
+    reads = stream.reshape(-1, L + 1)[:, :L]
+    ora = _oracle.load()
+    n_inst = ora.count(stream, wl["k"] + 1, ci=2, threads=cores)["n_instances"]
+    have_ref = os.path.exists(_oracle.TA_REF)
+    times = []
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+        f1, f2 = os.path.join(td, "R1.fq"), os.path.join(td, "R2.fq")
+        for path, block, mate in ((f1, reads[:n_pairs], 1), (f2, reads[n_pairs:], 2)):
+            with open(path, "wb") as f:
+                q = b"I" * L
+                for i, r in enumerate(block):
+                    f.write(b"@r%d/%d\n" % (i, mate) + r.tobytes() + b"\n+\n" + q + b"\n")
+        for step in range(args.warmup + args.steps):
+            out = os.path.join(td, f"out{step}")
+            os.makedirs(out)
+            exe = _oracle.TA_REF if have_ref else os.path.join(ROOT, "oracle", "ta_oracle")
+            cmd = [exe, "build_0", "-1", f1, "-2", f2, "-l", "ust", "-k0", str(wl["k"]), "-t", str(cores), "-o", out]
+            t0 = time.perf_counter()
+            p = subprocess.run(cmd, capture_output=True, text=True)
+            dt = time.perf_counter() - t0
+            if p.returncode != 0:
+                sys.stderr.write((p.stdout + p.stderr)[-2000:])
+                raise SystemExit(1)
+            if step >= args.warmup:
+                times.append(dt)
+    sec = sum(times) / len(times)
+    val = n_inst / sec
+    sample = (f"{2 * n_pairs} reads x {L} bp from a {wl['genome_len'] // 20} bp genome ({n_inst} (k+1)-mer instances), "
+              f"FASTQ files -> graph_k_{wl['k']}_level_0.bin via build_0 -t {cores}")
+    print(json.dumps({
+        "impl": "reference", "metric": "kmers_per_sec_counted_and_graph_built", "value": val, "unit": "kmers/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u128" if wl["k"] + 1 > 32 else "u64", "data": "synthetic",
+        "config": {"workload": f"{args.workload} (bounded sample): {sample}"},
+        "cpu_baseline": {"value": val, "unit": "kmers/s", "cores": cores, "kind": "reference" if have_ref else "port", "sample": sample},
+        "e2e": {"value": val, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="tagpu", choices=["tagpu", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    from turingassembler_b200 import Tagpu
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    wl = WORKLOADS[args.workload]
+    k = wl["k"]
+
+    # "replicas" until the hash-partitioned exchange lands: every rank processes the full read set
+    d_stream = gen_reads_gpu(torch, wl["genome_len"], wl["n_pairs"], wl["seed"], dev)
+    n_stream = d_stream.numel()
+    h_stream = torch.empty(n_stream, dtype=torch.uint8, pin_memory=True)
+    h_stream.copy_(d_stream)
+    torch.cuda.synchronize()
+
+    t = Tagpu(local_rank)
+    stream = torch.cuda.current_stream()
+    t.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        st = t.build_device(d_stream.data_ptr(), n_stream, k)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_count = ms_graph = 0.0
+    launches = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        st = t.build_device(d_stream.data_ptr(), n_stream, k)
+        ms_count += st["ms_count"]
+        ms_graph += st["ms_graph"]
+        launches += st["gpu_launches"]
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    # e2e: pinned host stream -> C-ABI host call (H2D inside) -> stats back
+    t.build_host((h_stream.data_ptr(), n_stream), k)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        st_e = t.build_host((h_stream.data_ptr(), n_stream), k)
+    e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    sampler.join()
+
+    tm = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = tm.tolist()
+    if rank != 0:
+        return
+    n_inst = st["n_instances"]
+    ms_step = ms / args.steps
+    value = n_inst / (ms_step * 1e-3)
+    b_count, b_graph = algorithmic_bytes(st, k, n_stream)
+    peak, peak_src = peaks()
+    count_ms = ms_count / args.steps
+    achieved = b_count / (count_ms * 1e-3) / 1e9
+    line = {
+        "metric": "kmers_per_sec_counted_and_graph_built", "value": value, "unit": "kmers/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u128" if k + 1 > 32 else "u64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['genome_len']} bp genome, {wl['n_pairs']} pairs x {L} bp, k0={k} "
+                               f"(K={k + 1}), cutoff 2; {n_stream} stream bytes resident in HBM (> L2, no flush needed)",
+                   "n_instances": n_inst, "n_distinct": st["n_distinct"], "n_solid": st["n_solid"], "n_kmers": st["n_kmers"],
+                   "n_v": st["n_v"], "n_e": st["n_e"], "parallelism": f"replicas x{world}" if world > 1 else "1 gpu"},
+        "stage_ms": {"count": count_ms, "graph": ms_graph / args.steps},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "count stage (all kernels of the (k+1)-mer counting stage)",
+                     "algorithmic_bytes": b_count, "peak_source": peak_src,
+                     "whole_path": {"achieved": (b_count + b_graph) / (ms_step * 1e-3) / 1e9,
+                                    "frac": (b_count + b_graph) / (ms_step * 1e-3) / 1e9 / peak}},
+        "e2e": {"value": st_e["n_instances"] / (ms_e2e / args.steps * 1e-3), "unit": "kmers/s",
+                "h2d_bytes_per_step": n_stream, "d2h_bytes_per_step": 8 * 140, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(h_stream.numpy(), k)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

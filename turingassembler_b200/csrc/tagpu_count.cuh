@@ -1,0 +1,421 @@
+// Counting stage: canonical (k+1)-mer counting with ALL hash-table traffic in shared memory.
+//
+// Why: on this B200 a (load + compare + atomic add) against an HBM-resident table sustains ~18 Gop/s and an
+// L2-resident one ~60-95 Gop/s, while the same sequence on a shared-memory table sustains ~840 Gop/s chip-wide
+// (tools/ubench_atomics.cu, profiles/ubench_r1.txt).  So the key space is cut into P buckets small enough that one
+// bucket's distinct keys fit a shared-memory table, and buckets are shipped through HBM in a compact form:
+//
+//   pass 1  k_partition   reads the ASCII stream once; every maximal run of consecutive valid windows whose
+//                         minimizer maps to the same bucket ("super-k-mer", as in KMC 2/3 — the design of the
+//                         library the reference delegates this stage to) becomes ONE fixed-size record
+//                         (2-bit bases + length) appended to the bucket's region.  ~1.5-2 B per instance
+//                         instead of 8/16 B for a raw key.
+//   pass 2  k_count_buckets  one CTA per bucket: re-expands records into canonical keys and counts them in a
+//                         shared-memory open-addressing table (LDS + ATOMS only), then emits the keys with
+//                         count >= ci.  A bucket with too many distinct keys is re-run on hash sub-classes.
+//
+// The bucket of a window is a function of its canonical key only (minimum over the hashes of the canonical m-mers it
+// contains), so all instances of a key — on either strand — meet in the same bucket and counts are exact.
+#pragma once
+#include "tagpu_extract.cuh"
+#include "tagpu_graph.cuh"
+
+constexpr int TAGPU_MINIMIZER_M = 11;                 // m-mer length (22 bits)
+constexpr uint32_t TAGPU_H_INVALID = 0xffffffffu;
+constexpr int TAGPU_HM_LEN = TAGPU_SMEM_WORDS * 32;   // m-mer hash per position of the packed tile (incl. halo)
+
+template <int W> struct SkRec;                        // super-k-mer record: bases right-aligned, length in the top byte
+template <> struct __align__(16) SkRec<1> { unsigned long long w[2]; };   // <= 60 bases
+template <> struct __align__(32) SkRec<2> { unsigned long long w[4]; };   // <= 124 bases
+template <int W> struct SkCap { static constexpr int bases = W == 1 ? 60 : 124; };
+
+struct PartCfg {
+	int K;
+	int log2_buckets;
+	uint32_t cap_records;         // records per bucket region
+	uint32_t overflow_cap;        // records in the shared overflow area
+};
+
+TAGPU_DI uint32_t tagpu_bucket_of(uint32_t minhash, int log2_buckets)
+{
+	return (minhash * 0x85ebca6bu) >> (32 - log2_buckets);
+}
+
+// the 32 bases ending at packed-tile position end_q (inclusive), first base most significant
+TAGPU_DI uint64_t tagpu_extract32(const uint64_t *pk, int end_q)
+{
+	const int wi = end_q >> 5, r = (end_q & 31) + 1;
+	if (r == 32) return pk[wi];
+	const uint64_t prev = wi > 0 ? pk[wi - 1] : 0ull;
+	return (prev << (2 * r)) | (pk[wi] >> (64 - 2 * r));
+}
+
+template <int W>
+TAGPU_DI SkRec<W> tagpu_make_record(const uint64_t *pk, int end_q, int n_bases, int n_windows)
+{
+	SkRec<W> r;
+#pragma unroll
+	for (int i = 0; i < 2 * W; ++i) {
+		const int have = n_bases - 32 * i;              // bases that belong in word i
+		uint64_t v = 0;
+		if (have > 0) {
+			v = tagpu_extract32(pk, end_q - 32 * i);
+			if (have < 32) v &= (1ull << (2 * have)) - 1;
+		}
+		r.w[i] = v;
+	}
+	r.w[2 * W - 1] |= (unsigned long long)n_windows << 56;
+	return r;
+}
+
+// ---------------------------------------------------------------- pass 1
+template <int W>
+__global__ void __launch_bounds__(TAGPU_TILE_THREADS)
+k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *__restrict__ regions,
+	    unsigned long long *__restrict__ cursor, SkRec<W> *__restrict__ overflow, uint32_t *__restrict__ overflow_bucket,
+	    unsigned long long *ctr)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	uint64_t *pk = reinterpret_cast<uint64_t *>(smem_raw);
+	uint32_t *inv = reinterpret_cast<uint32_t *>(pk + TAGPU_SMEM_WORDS);
+	uint32_t *ha = inv + TAGPU_SMEM_WORDS + 2;          // two ping-pong arrays of per-position m-mer hashes / running minima
+	uint32_t *hb = ha + TAGPU_HM_LEN;
+	const int K = cfg.K, m = TAGPU_MINIMIZER_M;
+
+	tagpu_load_tile(seq, n, (uint64_t)blockIdx.x * TAGPU_TILE_BASES, pk, inv);
+	__syncthreads();
+
+	// A. hash of the canonical m-mer ending at every position (invalid if the m-mer touches a non-ACGT byte)
+	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
+		const uint32_t mm = (1u << (2 * m)) - 1;
+		uint32_t fw = j ? (uint32_t)pk[j - 1] & mm : 0u;
+		uint32_t rv = 0;
+		for (int b = 0; b < m; ++b) rv |= (3u - ((fw >> (2 * b)) & 3u)) << (2 * (m - 1 - b));
+		const uint32_t i1 = j ? inv[j - 1] : 0xffffffffu;
+		int run = i1 ? (__ffs(i1) - 1) : 32;
+		uint64_t cur = pk[j];
+		uint32_t iv = inv[j];
+#pragma unroll 8
+		for (int i = 0; i < 32; ++i) {
+			const uint32_t c = (uint32_t)(cur >> 62);
+			cur <<= 2;
+			const bool bad = (int)iv < 0;
+			iv <<= 1;
+			fw = ((fw << 2) | c) & mm;
+			rv = (rv >> 2) | ((3u - c) << (2 * (m - 1)));
+			run = bad ? 0 : run + 1;
+			const uint32_t cm = min(fw, rv);
+			ha[j * 32 + i] = run >= m ? (cm * 0x9e3779b1u) >> 10 : TAGPU_H_INVALID;
+		}
+	}
+	__syncthreads();
+
+	// B. minimum over the w = K - m + 1 m-mers of every window, by doubling: after the pass with step s,
+	//    x[q] = min(h[q - 2s + 1 .. q]); the last pass combines two overlapping power-of-two windows.
+	const int w = K - m + 1;
+	uint32_t *src = ha, *dst = hb;
+	int span = 1;
+	while (span * 2 <= w) {
+		for (int q = threadIdx.x; q < TAGPU_HM_LEN; q += blockDim.x)
+			dst[q] = q >= span ? min(src[q], src[q - span]) : src[q];
+		__syncthreads();
+		uint32_t *t = src; src = dst; dst = t;
+		span *= 2;
+	}
+	if (span < w) {
+		const int d = w - span;
+		for (int q = threadIdx.x; q < TAGPU_HM_LEN; q += blockDim.x)
+			dst[q] = q >= d ? min(src[q], src[q - d]) : src[q];
+		__syncthreads();
+		uint32_t *t = src; src = dst; dst = t;
+	}
+	const uint32_t *minh = src;
+
+	// C. every thread cuts the 32 window-end positions of its word into runs and appends one record per run
+	const int wi = threadIdx.x + TAGPU_HALO_WORDS;
+	const uint32_t i1 = inv[wi - 1], i2 = inv[wi - 2];
+	int run = i1 ? (__ffs(i1) - 1) : 32 + (i2 ? (__ffs(i2) - 1) : 32);
+	uint32_t iv = inv[wi];
+	const int max_windows = min(32, SkCap<W>::bases - (K - 1));
+	int cur_n = 0;
+	uint32_t cur_b = 0, n_win = 0;
+	auto flush = [&](int end_q) {
+		if (!cur_n) return;
+		const SkRec<W> rec = tagpu_make_record<W>(pk, end_q, cur_n + K - 1, cur_n);
+		const unsigned long long old = atomicAdd(cursor + cur_b, 1ull | ((unsigned long long)cur_n << 32));
+		const uint32_t idx = (uint32_t)old;
+		if (idx < cfg.cap_records) {
+			regions[(size_t)cur_b * cfg.cap_records + idx] = rec;
+		} else {
+			const unsigned long long o = atomicAdd(ctr + CTR_SPARE0, 1ull);
+			if (o < cfg.overflow_cap) { overflow[o] = rec; overflow_bucket[o] = cur_b; }
+			else atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_BUCKET_OVERFLOW);
+		}
+		cur_n = 0;
+	};
+	for (int i = 0; i < 32; ++i) {
+		const bool bad = (int)iv < 0;
+		iv <<= 1;
+		run = bad ? 0 : run + 1;
+		const int q = wi * 32 + i;
+		if (run >= K) {
+			const uint32_t b = tagpu_bucket_of(minh[q], cfg.log2_buckets);
+			if (cur_n && (b != cur_b || cur_n == max_windows)) flush(q - 1);
+			cur_b = b;
+			++cur_n;
+			++n_win;
+		} else {
+			flush(q - 1);
+		}
+	}
+	flush(wi * 32 + 31);
+	// instance total (the metric's numerator): one atomic per CTA
+	__shared__ uint32_t s_inst;
+	if (threadIdx.x == 0) s_inst = 0;
+	__syncthreads();
+	n_win = __reduce_add_sync(0xffffffffu, n_win);
+	if ((threadIdx.x & 31) == 0 && n_win) atomicAdd(&s_inst, n_win);
+	__syncthreads();
+	if (threadIdx.x == 0 && s_inst) atomicAdd(ctr + CTR_INSTANCES, (unsigned long long)s_inst);
+}
+
+// ---------------------------------------------------------------- overflow handling (only launched when a bucket region filled up)
+__global__ void k_overflow_hist(const uint32_t *__restrict__ overflow_bucket, uint64_t n_over, uint32_t *__restrict__ ext_count)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_over) atomicAdd(ext_count + overflow_bucket[i], 1u);
+}
+
+// single block: exclusive scan of ext_count into ext_off (n_buckets + 1 entries), ext_count reset to 0 for reuse as cursor
+__global__ void __launch_bounds__(1024) k_overflow_scan(uint32_t *ext_count, uint32_t *ext_off, uint32_t n_buckets)
+{
+	__shared__ uint32_t s_part[1024];
+	const uint32_t per = (n_buckets + 1023) / 1024, lo = threadIdx.x * per, hi = min(lo + per, n_buckets);
+	uint32_t sum = 0;
+	for (uint32_t b = lo; b < hi; ++b) sum += ext_count[b];
+	s_part[threadIdx.x] = sum;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t acc = 0;
+		for (int t = 0; t < 1024; ++t) { uint32_t v = s_part[t]; s_part[t] = acc; acc += v; }
+		ext_off[n_buckets] = acc;
+	}
+	__syncthreads();
+	uint32_t acc = s_part[threadIdx.x];
+	for (uint32_t b = lo; b < hi; ++b) { ext_off[b] = acc; acc += ext_count[b]; ext_count[b] = 0; }
+}
+
+template <int W>
+__global__ void k_overflow_scatter(const SkRec<W> *__restrict__ overflow, const uint32_t *__restrict__ overflow_bucket,
+				   uint64_t n_over, const uint32_t *__restrict__ ext_off, uint32_t *__restrict__ ext_cursor,
+				   SkRec<W> *__restrict__ ext)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_over) return;
+	const uint32_t b = overflow_bucket[i];
+	ext[ext_off[b] + atomicAdd(ext_cursor + b, 1u)] = overflow[i];
+}
+
+// ---------------------------------------------------------------- pass 2
+template <int W> struct BucketCfg {
+	static constexpr int THREADS = 512;
+	static constexpr int SLOTS = 4096;                          // shared-memory table slots per CTA
+	static constexpr int LIMIT = SLOTS * 13 / 16;               // claims beyond this abort the attempt (re-run on sub-classes)
+	static constexpr int CHUNK = W == 1 ? 512 : 256;            // records staged per iteration
+	static constexpr int MAXN = 32;                             // windows per record (k_partition cuts runs at 32)
+	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + CHUNK * sizeof(SkRec<W>) + (CHUNK + 1) * 4 + CHUNK * MAXN * 2;
+};
+
+// window j (0 = first) of a record holding n windows of K bases
+template <int W> TAGPU_DI Key<W> tagpu_record_window(const SkRec<W> &r, int n, int j, int K);
+template <> TAGPU_DI Key<1> tagpu_record_window<1>(const SkRec<1> &r, int n, int j, int K)
+{
+	const int sh = 2 * (n - 1 - j);                             // 0..62
+	const uint64_t hi = r.w[1] & 0x00ffffffffffffffull;
+	Key<1> k;
+	k.lo = sh ? (r.w[0] >> sh) | (hi << (64 - sh)) : r.w[0];
+	if (K < 32) k.lo &= (1ull << (2 * K)) - 1;
+	return k;
+}
+template <> TAGPU_DI Key<2> tagpu_record_window<2>(const SkRec<2> &r, int n, int j, int K)
+{
+	const int sh = 2 * (n - 1 - j);                             // 0..62 (n <= 32)
+	const uint64_t w3 = r.w[3] & 0x00ffffffffffffffull;
+	Key<2> k;
+	if (sh) {
+		k.lo = (r.w[0] >> sh) | (r.w[1] << (64 - sh));
+		k.hi = (r.w[1] >> sh) | (r.w[2] << (64 - sh));
+	} else {
+		k.lo = r.w[0];
+		k.hi = r.w[1];
+	}
+	(void)w3; // windows never reach word 3: n + K - 1 <= 32 + 63 bases = 190 bits
+	return KeyOps<2>::band(k, KeyOps<2>::mask(K));
+}
+
+template <int W>
+__global__ void __launch_bounds__(BucketCfg<W>::THREADS, 2)
+k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *__restrict__ cursor, uint32_t cap_records,
+		const SkRec<W> *__restrict__ ext, const uint32_t *__restrict__ ext_off, uint32_t n_buckets, int K, uint32_t ci,
+		Key<W> *__restrict__ solid, uint32_t *__restrict__ solid_cnt, unsigned long long *ctr)
+{
+	typedef KeyOps<W> KO;
+	typedef BucketCfg<W> C;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	Key<W> *t_key = reinterpret_cast<Key<W> *>(smem_raw);
+	uint32_t *t_cnt = reinterpret_cast<uint32_t *>(t_key + C::SLOTS);
+	SkRec<W> *s_rec = reinterpret_cast<SkRec<W> *>(t_cnt + C::SLOTS);
+	uint32_t *s_pref = reinterpret_cast<uint32_t *>(s_rec + C::CHUNK);
+	uint16_t *s_owner = reinterpret_cast<uint16_t *>(s_pref + C::CHUNK + 1);
+	__shared__ uint32_t s_bucket, s_claims, s_overflow, s_warp[C::THREADS / 32], s_stack[64], s_sp;
+	__shared__ unsigned long long s_out_base;
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+	for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) { t_key[i] = KO::make(0, 0); t_cnt[i] = 0; }
+
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) s_bucket = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);
+		__syncthreads();
+		const uint32_t b = s_bucket;
+		if (b >= n_buckets) break;
+		const unsigned long long cur = cursor[b];
+		const uint32_t n_total = (uint32_t)cur, n_inst = (uint32_t)(cur >> 32);
+		if (!n_total) continue;
+		const uint32_t n_main = min(n_total, cap_records), n_ext = n_total - n_main;
+		const SkRec<W> *main_rec = regions + (size_t)b * cap_records;
+		const SkRec<W> *ext_rec = n_ext ? ext + ext_off[b] : nullptr;
+		if (tid == 0) {
+			// start on 2^L hash classes if the bucket is obviously too big for one table
+			uint32_t L = 0;
+			while (L < 5 && (n_inst >> L) > 3u * C::SLOTS) ++L;            // at most 32 initial classes; overflow splits further
+			s_sp = 0;
+			for (uint32_t c = 0; c < (1u << L); ++c) s_stack[s_sp++] = (L << 24) | c;
+		}
+		__syncthreads();
+		while (*(volatile uint32_t *)&s_sp) {
+			__syncthreads();
+			const uint32_t top = s_stack[s_sp - 1];
+			const uint32_t L = top >> 24, cls = top & 0xffffffu;
+			__syncthreads();
+			if (tid == 0) { --s_sp; s_claims = 0; s_overflow = 0; }
+			__syncthreads();
+			// ---- insert every window of the bucket that belongs to hash class (L, cls)
+			for (uint32_t base = 0; base < n_total && !*(volatile uint32_t *)&s_overflow; base += C::CHUNK) {
+				const uint32_t n_here = min((uint32_t)C::CHUNK, n_total - base);
+				uint32_t my_n = 0;
+				if (tid < n_here) {
+					const uint32_t g = base + tid;
+					const SkRec<W> r = g < n_main ? main_rec[g] : ext_rec[g - n_main];
+					s_rec[tid] = r;
+					my_n = (uint32_t)(r.w[2 * W - 1] >> 56);
+				}
+				// exclusive prefix sum of my_n over the first CHUNK threads
+				uint32_t incl = my_n;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+					if (lane >= (uint32_t)d) incl += t;
+				}
+				if (lane == 31) s_warp[warp] = incl;
+				__syncthreads();
+				if (warp == 0) {
+					uint32_t x = lane < C::THREADS / 32 ? s_warp[lane] : 0, in2 = x;
+#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) {
+						uint32_t t = __shfl_up_sync(0xffffffffu, in2, d);
+						if (lane >= (uint32_t)d) in2 += t;
+					}
+					if (lane < C::THREADS / 32) s_warp[lane] = in2 - x;
+				}
+				__syncthreads();
+				const uint32_t excl = s_warp[warp] + incl - my_n;
+				if (tid < (uint32_t)C::CHUNK) {
+					s_pref[tid] = excl;
+					for (uint32_t j = 0; j < my_n; ++j) s_owner[excl + j] = (uint16_t)tid;
+				}
+				if (tid == C::CHUNK - 1) s_pref[C::CHUNK] = excl + my_n;
+				__syncthreads();
+				const uint32_t total = s_pref[C::CHUNK];
+				for (uint32_t x = tid; x < total; x += C::THREADS) {
+					const uint32_t ri = s_owner[x];
+					const SkRec<W> &r = s_rec[ri];
+					const int nn = (int)(r.w[2 * W - 1] >> 56);
+					const Key<W> fw = tagpu_record_window<W>(r, nn, (int)(x - s_pref[ri]), K);
+					const Key<W> rv = KO::rc(fw, K);
+					const Key<W> key = KO::le(fw, rv) ? fw : rv;
+					const uint64_t h = KO::hash(key);
+					if (L && ((uint32_t)(h >> 40) & ((1u << L) - 1u)) != cls) continue;
+					const Key<W> stored = KO::bnot(key);
+					uint32_t slot = (uint32_t)h & (C::SLOTS - 1);
+					for (;;) {
+						const Key<W> have = t_key[slot];
+						if (KO::eq(have, stored)) { atomicAdd(t_cnt + slot, 1u); break; }
+						if (KO::is_zero(have) || ktab_maybe_torn<W>(have)) {
+							if (*(volatile uint32_t *)&s_claims >= (uint32_t)C::LIMIT) { s_overflow = 1; break; }
+							const Key<W> old = ktab_cas<W>(t_key + slot, stored);   // ATOMS.CAS.64 / .128
+							if (KO::is_zero(old)) { atomicAdd(&s_claims, 1u); atomicAdd(t_cnt + slot, 1u); break; }
+							if (KO::eq(old, stored)) { atomicAdd(t_cnt + slot, 1u); break; }
+						}
+						slot = (slot + 1) & (C::SLOTS - 1);
+					}
+				}
+				__syncthreads();
+			}
+			// ---- harvest (or discard on overflow) and leave the table zeroed
+			const bool failed = *(volatile uint32_t *)&s_overflow != 0;
+			uint32_t mine = 0;
+			if (!failed)
+				for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) mine += t_cnt[i] >= ci ? 1u : 0u;
+			uint32_t incl = mine;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+				if (lane >= (uint32_t)d) incl += t;
+			}
+			if (lane == 31) s_warp[warp] = incl;
+			__syncthreads();
+			if (warp == 0) {
+				uint32_t x = lane < C::THREADS / 32 ? s_warp[lane] : 0, in2 = x;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					uint32_t t = __shfl_up_sync(0xffffffffu, in2, d);
+					if (lane >= (uint32_t)d) in2 += t;
+				}
+				if (lane < C::THREADS / 32) s_warp[lane] = in2 - x;
+				if (lane == C::THREADS / 32 - 1) {
+					s_out_base = in2 ? atomicAdd(ctr + CTR_SOLID, (unsigned long long)in2) : 0ull;
+					if (!failed) atomicAdd(ctr + CTR_DISTINCT, (unsigned long long)s_claims);
+				}
+			}
+			__syncthreads();
+			unsigned long long o = s_out_base + s_warp[warp] + incl - mine;
+			unsigned long long sum = 0;
+			for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) {
+				const uint32_t c = t_cnt[i];
+				if (c) {
+					if (!failed && c >= ci) {
+						solid[o] = KO::bnot(t_key[i]);
+						solid_cnt[o] = c;
+						sum += c;
+						++o;
+					}
+					t_key[i] = KO::make(0, 0);
+					t_cnt[i] = 0;
+				}
+			}
+#pragma unroll
+			for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+			if (lane == 0 && sum) atomicAdd(ctr + CTR_SUM_SOLID, sum);
+			__syncthreads();
+			if (tid == 0 && failed) {
+				if (L >= 20 || s_sp + 2 > 64) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_TABLE_FULL);
+				else {
+					s_stack[s_sp++] = ((L + 1) << 24) | cls;
+					s_stack[s_sp++] = ((L + 1) << 24) | (cls + (1u << L));
+				}
+			}
+			__syncthreads();
+		}
+	}
+}

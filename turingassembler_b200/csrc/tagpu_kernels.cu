@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/tagpu.h"
+#include "tagpu_count.cuh"
 #include "tagpu_count_v1.cuh"
 #include "tagpu_extract.cuh"
 #include "tagpu_graph.cuh"
@@ -27,6 +28,8 @@ struct tagpu_ctx {
 	int k = 0, K = 0, W = 0;
 	char err[512] = { 0 };
 	unsigned long long *d_ctr = nullptr, *h_ctr = nullptr;
+	Buf regions, cursor, overflow, overflow_bucket, ext, ext_off, ext_count;
+	int n_sm = 0;
 	Buf seq, ctab, clist, solid_key, solid_cnt, kt_keys, kt_mask, node_ord, node_slot, node_ebase, vL, vR, jump, vsucc,
 		vedge, e_src, e_dst, e_rc, e_len, e_count, e_off, e_seq;
 	uint64_t ctab_slots = 0;
@@ -96,6 +99,7 @@ extern "C" tagpu_ctx *tagpu_create(int device)
 		return nullptr;
 	}
 	ctx->stream = ctx->own_stream;
+	cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
 	for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
 	memset(&ctx->st, 0, sizeof(ctx->st));
 	return ctx;
@@ -106,7 +110,7 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	Buf *bufs[] = { &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
 			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
 	for (Buf *b : bufs)
@@ -170,6 +174,74 @@ static int count_stage(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n)
 	if (read_counters(ctx)) return -1;
 	ctx->st.n_instances = ctx->h_ctr[CTR_INSTANCES];
 	ctx->st.n_distinct = n_distinct;
+	ctx->st.n_solid = ctx->h_ctr[CTR_SOLID];
+	ctx->st.sum_solid = ctx->h_ctr[CTR_SUM_SOLID];
+	ctx->have_count = true;
+	return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------ count stage (partitioned)
+#define LAUNCH_SMEM(kernel, grid, block, smem, ...)                                        \
+	do {                                                                               \
+		kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);             \
+		++ctx->launches;                                                           \
+		CU(cudaGetLastError());                                                    \
+	} while (0)
+
+template <int W>
+static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n)
+{
+	typedef BucketCfg<W> BC;
+	const int K = ctx->K;
+	// bucket count: aim at <= ~1400 distinct keys per 4096-slot table, guessing distinct ~ stream bytes / 8
+	uint64_t want = n / 8 / 1400 + 1;
+	int log2p = 10;
+	while ((1ull << log2p) < want && log2p < 22) ++log2p;
+	const uint32_t n_buckets = 1u << log2p;
+	// region capacity: ~4x the expected records per bucket (one record per ~8 windows), at least 64
+	uint64_t cap = n / 8 / n_buckets * 4 + 64;
+	PartCfg cfg;
+	cfg.K = K;
+	cfg.log2_buckets = log2p;
+	cfg.cap_records = (uint32_t)cap;
+	cfg.overflow_cap = (uint32_t)(n / 16 + 4096);
+	if (ensure(ctx, ctx->regions, (size_t)n_buckets * cap * sizeof(SkRec<W>)) || ensure(ctx, ctx->cursor, (size_t)n_buckets * 8) ||
+	    ensure(ctx, ctx->overflow, (size_t)cfg.overflow_cap * sizeof(SkRec<W>)) ||
+	    ensure(ctx, ctx->overflow_bucket, (size_t)cfg.overflow_cap * 4) || ensure(ctx, ctx->ext_off, (size_t)(n_buckets + 1) * 4) ||
+	    ensure(ctx, ctx->ext_count, (size_t)n_buckets * 4))
+		return -1;
+	CU(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)n_buckets * 8, ctx->stream));
+	const size_t smem1 = TAGPU_SMEM_WORDS * 8 + (TAGPU_SMEM_WORDS + 2) * 4 + 2 * (size_t)TAGPU_HM_LEN * 4;
+	static bool attr_done[3] = { false, false, false };
+	if (!attr_done[W]) {
+		CU(cudaFuncSetAttribute(k_partition<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+		CU(cudaFuncSetAttribute(k_count_buckets<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BC::SMEM));
+		attr_done[W] = true;
+	}
+	const uint64_t n_tiles = (n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES;
+	if (n_tiles)
+		LAUNCH_SMEM(k_partition<W>, (unsigned)n_tiles, TAGPU_TILE_THREADS, smem1, d_seq, n, cfg, (SkRec<W> *)ctx->regions.p,
+			    (unsigned long long *)ctx->cursor.p, (SkRec<W> *)ctx->overflow.p, (uint32_t *)ctx->overflow_bucket.p, ctx->d_ctr);
+	if (read_counters(ctx)) return -1;
+	const uint64_t n_inst = ctx->h_ctr[CTR_INSTANCES], n_over = ctx->h_ctr[CTR_SPARE0];
+	if (n_over) {
+		if (ensure(ctx, ctx->ext, n_over * sizeof(SkRec<W>))) return -1;
+		CU(cudaMemsetAsync(ctx->ext_count.p, 0, (size_t)n_buckets * 4, ctx->stream));
+		LAUNCH(k_overflow_hist, (unsigned)((n_over + 255) / 256), 256, (const uint32_t *)ctx->overflow_bucket.p, n_over, (uint32_t *)ctx->ext_count.p);
+		LAUNCH(k_overflow_scan, 1, 1024, (uint32_t *)ctx->ext_count.p, (uint32_t *)ctx->ext_off.p, n_buckets);
+		LAUNCH(k_overflow_scatter<W>, (unsigned)((n_over + 255) / 256), 256, (const SkRec<W> *)ctx->overflow.p,
+		       (const uint32_t *)ctx->overflow_bucket.p, n_over, (const uint32_t *)ctx->ext_off.p, (uint32_t *)ctx->ext_count.p,
+		       (SkRec<W> *)ctx->ext.p);
+	}
+	const uint64_t solid_cap = n_inst / (uint64_t)ctx->ci + 1; // every solid key owns >= ci instances
+	if (ensure(ctx, ctx->solid_key, solid_cap * sizeof(Key<W>)) || ensure(ctx, ctx->solid_cnt, solid_cap * 4)) return -1;
+	LAUNCH_SMEM(k_count_buckets<W>, 2 * ctx->n_sm, BC::THREADS, BC::SMEM, (const SkRec<W> *)ctx->regions.p,
+		    (const unsigned long long *)ctx->cursor.p, cfg.cap_records, (const SkRec<W> *)ctx->ext.p, (const uint32_t *)ctx->ext_off.p,
+		    n_buckets, K, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p, ctx->d_ctr);
+	if (read_counters(ctx)) return -1;
+	ctx->st.n_instances = n_inst;
+	ctx->st.n_distinct = ctx->h_ctr[CTR_DISTINCT];
 	ctx->st.n_solid = ctx->h_ctr[CTR_SOLID];
 	ctx->st.sum_solid = ctx->h_ctr[CTR_SUM_SOLID];
 	ctx->have_count = true;
@@ -261,7 +333,9 @@ static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool wit
 	memset(&ctx->st, 0, sizeof(ctx->st));
 	CU(cudaMemsetAsync(ctx->d_ctr, 0, CTR_TOTAL * sizeof(unsigned long long), ctx->stream));
 	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-	int rc = ctx->W == 1 ? count_stage<1>(ctx, d_seq, n) : count_stage<2>(ctx, d_seq, n);
+	static const bool direct = getenv("TAGPU_COUNT_DIRECT") != nullptr; // bring-up cross-check only
+	int rc = direct ? (ctx->W == 1 ? count_stage<1>(ctx, d_seq, n) : count_stage<2>(ctx, d_seq, n))
+			: (ctx->W == 1 ? count_stage_partitioned<1>(ctx, d_seq, n) : count_stage_partitioned<2>(ctx, d_seq, n));
 	if (rc) return rc;
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
 	if (with_graph) {
