@@ -73,6 +73,9 @@ void tagpu_set_cutoff(tagpu_ctx *ctx, int ci);
 /* 0 (default) = build edge counts; 1 = build_graph_from_scratch_without_count behaviour */
 void tagpu_set_skip_counts(tagpu_ctx *ctx, int skip);
 const char *tagpu_last_error(tagpu_ctx *ctx);
+/* per-kernel CUDA-event timing of the next builds: JSON {"kernel": {"ms": total, "launches": n}, ...} */
+void tagpu_set_profile(tagpu_ctx *ctx, int on);
+const char *tagpu_profile_json(tagpu_ctx *ctx);
 
 /* Count + build from a flat byte stream already in device memory ('\n' or any non-ACGT byte between reads).
  * Results stay on the device until copied.  k = node k-mer size (17..63); returns 0 on success. */

@@ -128,6 +128,9 @@ def load_library() -> C.CDLL:
     lib.tagpu_set_stream.argtypes = [vp, vp]
     lib.tagpu_set_cutoff.argtypes = [vp, i32]
     lib.tagpu_set_skip_counts.argtypes = [vp, i32]
+    lib.tagpu_set_profile.argtypes = [vp, i32]
+    lib.tagpu_profile_json.restype = C.c_char_p
+    lib.tagpu_profile_json.argtypes = [vp]
     lib.tagpu_last_error.restype = C.c_char_p
     lib.tagpu_last_error.argtypes = [vp]
     for name in ("tagpu_build_device", "tagpu_build_host", "tagpu_count_device", "tagpu_count_host"):
@@ -196,6 +199,13 @@ class Tagpu:
 
     def set_cutoff(self, ci: int):
         self.lib.tagpu_set_cutoff(self.ctx, ci)
+
+    def set_profile(self, on: bool):
+        self.lib.tagpu_set_profile(self.ctx, int(on))
+
+    def profile(self) -> dict:
+        import json
+        return json.loads(self.lib.tagpu_profile_json(self.ctx).decode())
 
     def set_skip_counts(self, skip: bool):
         self.lib.tagpu_set_skip_counts(self.ctx, int(skip))

@@ -22,7 +22,9 @@
 
 constexpr int TAGPU_MINIMIZER_M = 11;                 // m-mer length (22 bits)
 constexpr uint32_t TAGPU_H_INVALID = 0xffffffffu;
-constexpr int TAGPU_HM_LEN = TAGPU_SMEM_WORDS * 32;   // m-mer hash per position of the packed tile (incl. halo)
+constexpr int TAGPU_HM_POS = TAGPU_SMEM_WORDS * 32;   // positions of the packed tile (incl. halo)
+constexpr int TAGPU_HM_LEN = TAGPU_SMEM_WORDS * 33;   // padded: index q + q/32, so word-major and position-major accesses are both conflict-free
+#define HIDX(q) ((q) + ((q) >> 5))
 
 template <int W> struct SkRec;                        // super-k-mer record: bases right-aligned, length in the top byte
 template <> struct __align__(16) SkRec<1> { unsigned long long w[2]; };   // <= 60 bases
@@ -105,7 +107,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 			rv = (rv >> 2) | ((3u - c) << (2 * (m - 1)));
 			run = bad ? 0 : run + 1;
 			const uint32_t cm = min(fw, rv);
-			ha[j * 32 + i] = run >= m ? (cm * 0x9e3779b1u) >> 10 : TAGPU_H_INVALID;
+			ha[j * 33 + i] = run >= m ? (cm * 0x9e3779b1u) >> 10 : TAGPU_H_INVALID;
 		}
 	}
 	__syncthreads();
@@ -116,16 +118,16 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 	uint32_t *src = ha, *dst = hb;
 	int span = 1;
 	while (span * 2 <= w) {
-		for (int q = threadIdx.x; q < TAGPU_HM_LEN; q += blockDim.x)
-			dst[q] = q >= span ? min(src[q], src[q - span]) : src[q];
+		for (int q = threadIdx.x; q < TAGPU_HM_POS; q += blockDim.x)
+			dst[HIDX(q)] = q >= span ? min(src[HIDX(q)], src[HIDX(q - span)]) : src[HIDX(q)];
 		__syncthreads();
 		uint32_t *t = src; src = dst; dst = t;
 		span *= 2;
 	}
 	if (span < w) {
 		const int d = w - span;
-		for (int q = threadIdx.x; q < TAGPU_HM_LEN; q += blockDim.x)
-			dst[q] = q >= d ? min(src[q], src[q - d]) : src[q];
+		for (int q = threadIdx.x; q < TAGPU_HM_POS; q += blockDim.x)
+			dst[HIDX(q)] = q >= d ? min(src[HIDX(q)], src[HIDX(q - d)]) : src[HIDX(q)];
 		__syncthreads();
 		uint32_t *t = src; src = dst; dst = t;
 	}
@@ -159,7 +161,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 		run = bad ? 0 : run + 1;
 		const int q = wi * 32 + i;
 		if (run >= K) {
-			const uint32_t b = tagpu_bucket_of(minh[q], cfg.log2_buckets);
+			const uint32_t b = tagpu_bucket_of(minh[HIDX(q)], cfg.log2_buckets);
 			if (cur_n && (b != cur_b || cur_n == max_windows)) flush(q - 1);
 			cur_b = b;
 			++cur_n;
@@ -218,58 +220,54 @@ __global__ void k_overflow_scatter(const SkRec<W> *__restrict__ overflow, const 
 
 // ---------------------------------------------------------------- pass 2
 template <int W> struct BucketCfg {
-	static constexpr int THREADS = 512;
-	static constexpr int SLOTS = 4096;                          // shared-memory table slots per CTA
+	static constexpr int THREADS = 1024;
+	static constexpr int SLOTS = W == 1 ? 16384 : 8192;         // shared-memory table slots per CTA (192 KB / 160 KB)
 	static constexpr int LIMIT = SLOTS * 13 / 16;               // claims beyond this abort the attempt (re-run on sub-classes)
-	static constexpr int CHUNK = W == 1 ? 512 : 256;            // records staged per iteration
-	static constexpr int MAXN = 32;                             // windows per record (k_partition cuts runs at 32)
-	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + CHUNK * sizeof(SkRec<W>) + (CHUNK + 1) * 4 + CHUNK * MAXN * 2;
+	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4);
 };
 
-// window j (0 = first) of a record holding n windows of K bases
-template <int W> TAGPU_DI Key<W> tagpu_record_window(const SkRec<W> &r, int n, int j, int K);
-template <> TAGPU_DI Key<1> tagpu_record_window<1>(const SkRec<1> &r, int n, int j, int K)
+// window j (0 = first) of a record holding n windows of K bases; w[] = the record's low words (header stripped)
+TAGPU_DI Key<1> tagpu_record_window(const unsigned long long (&w)[2], int n, int j, int K)
 {
 	const int sh = 2 * (n - 1 - j);                             // 0..62
-	const uint64_t hi = r.w[1] & 0x00ffffffffffffffull;
 	Key<1> k;
-	k.lo = sh ? (r.w[0] >> sh) | (hi << (64 - sh)) : r.w[0];
+	k.lo = sh ? (w[0] >> sh) | (w[1] << (64 - sh)) : w[0];
 	if (K < 32) k.lo &= (1ull << (2 * K)) - 1;
 	return k;
 }
-template <> TAGPU_DI Key<2> tagpu_record_window<2>(const SkRec<2> &r, int n, int j, int K)
+TAGPU_DI Key<2> tagpu_record_window(const unsigned long long (&w)[3], int n, int j, int K)
 {
-	const int sh = 2 * (n - 1 - j);                             // 0..62 (n <= 32)
-	const uint64_t w3 = r.w[3] & 0x00ffffffffffffffull;
+	const int sh = 2 * (n - 1 - j);                             // 0..62 (n <= 32): windows never reach word 3
 	Key<2> k;
 	if (sh) {
-		k.lo = (r.w[0] >> sh) | (r.w[1] << (64 - sh));
-		k.hi = (r.w[1] >> sh) | (r.w[2] << (64 - sh));
+		k.lo = (w[0] >> sh) | (w[1] << (64 - sh));
+		k.hi = (w[1] >> sh) | (w[2] << (64 - sh));
 	} else {
-		k.lo = r.w[0];
-		k.hi = r.w[1];
+		k.lo = w[0];
+		k.hi = w[1];
 	}
-	(void)w3; // windows never reach word 3: n + K - 1 <= 32 + 63 bases = 190 bits
 	return KeyOps<2>::band(k, KeyOps<2>::mask(K));
 }
 
+// One CTA per bucket (persistent CTAs pull bucket ids from a global counter).  Warps stream the bucket's records
+// independently: a warp holds 32 records in registers, spreads their windows evenly over its lanes (prefix sum +
+// shuffle search), and every lane inserts its canonical key into the CTA's shared-memory table.
 template <int W>
-__global__ void __launch_bounds__(BucketCfg<W>::THREADS, 2)
+__global__ void __launch_bounds__(BucketCfg<W>::THREADS, 1)
 k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *__restrict__ cursor, uint32_t cap_records,
 		const SkRec<W> *__restrict__ ext, const uint32_t *__restrict__ ext_off, uint32_t n_buckets, int K, uint32_t ci,
 		Key<W> *__restrict__ solid, uint32_t *__restrict__ solid_cnt, unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
 	typedef BucketCfg<W> C;
+	constexpr int NW = W + 1;                                   // record words that can hold window bases
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Key<W> *t_key = reinterpret_cast<Key<W> *>(smem_raw);
 	uint32_t *t_cnt = reinterpret_cast<uint32_t *>(t_key + C::SLOTS);
-	SkRec<W> *s_rec = reinterpret_cast<SkRec<W> *>(t_cnt + C::SLOTS);
-	uint32_t *s_pref = reinterpret_cast<uint32_t *>(s_rec + C::CHUNK);
-	uint16_t *s_owner = reinterpret_cast<uint16_t *>(s_pref + C::CHUNK + 1);
 	__shared__ uint32_t s_bucket, s_claims, s_overflow, s_warp[C::THREADS / 32], s_stack[64], s_sp;
 	__shared__ unsigned long long s_out_base;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	constexpr uint32_t N_WARPS = C::THREADS / 32;
 
 	for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) { t_key[i] = KO::make(0, 0); t_cnt[i] = 0; }
 
@@ -282,13 +280,13 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 		const unsigned long long cur = cursor[b];
 		const uint32_t n_total = (uint32_t)cur, n_inst = (uint32_t)(cur >> 32);
 		if (!n_total) continue;
-		const uint32_t n_main = min(n_total, cap_records), n_ext = n_total - n_main;
+		const uint32_t n_main = min(n_total, cap_records);
 		const SkRec<W> *main_rec = regions + (size_t)b * cap_records;
-		const SkRec<W> *ext_rec = n_ext ? ext + ext_off[b] : nullptr;
+		const SkRec<W> *ext_rec = n_total > n_main ? ext + ext_off[b] : nullptr;
 		if (tid == 0) {
 			// start on 2^L hash classes if the bucket is obviously too big for one table
 			uint32_t L = 0;
-			while (L < 5 && (n_inst >> L) > 3u * C::SLOTS) ++L;            // at most 32 initial classes; overflow splits further
+			while (L < 5 && (n_inst >> L) > 4u * C::SLOTS) ++L;            // at most 32 initial classes; overflow splits further
 			s_sp = 0;
 			for (uint32_t c = 0; c < (1u << L); ++c) s_stack[s_sp++] = (L << 24) | c;
 		}
@@ -301,47 +299,46 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 			if (tid == 0) { --s_sp; s_claims = 0; s_overflow = 0; }
 			__syncthreads();
 			// ---- insert every window of the bucket that belongs to hash class (L, cls)
-			for (uint32_t base = 0; base < n_total && !*(volatile uint32_t *)&s_overflow; base += C::CHUNK) {
-				const uint32_t n_here = min((uint32_t)C::CHUNK, n_total - base);
+			for (uint32_t base = warp * 32; base < n_total; base += N_WARPS * 32) {
+				if (*(volatile uint32_t *)&s_overflow) break;
+				const uint32_t g = base + lane;
+				unsigned long long rw[NW];
 				uint32_t my_n = 0;
-				if (tid < n_here) {
-					const uint32_t g = base + tid;
+				if (g < n_total) {
 					const SkRec<W> r = g < n_main ? main_rec[g] : ext_rec[g - n_main];
-					s_rec[tid] = r;
 					my_n = (uint32_t)(r.w[2 * W - 1] >> 56);
+#pragma unroll
+					for (int i = 0; i < NW; ++i) rw[i] = r.w[i];
+					if (W == 1) rw[1] &= 0x00ffffffffffffffull;
+				} else {
+#pragma unroll
+					for (int i = 0; i < NW; ++i) rw[i] = 0;
 				}
-				// exclusive prefix sum of my_n over the first CHUNK threads
 				uint32_t incl = my_n;
 #pragma unroll
 				for (int d = 1; d < 32; d <<= 1) {
 					uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
 					if (lane >= (uint32_t)d) incl += t;
 				}
-				if (lane == 31) s_warp[warp] = incl;
-				__syncthreads();
-				if (warp == 0) {
-					uint32_t x = lane < C::THREADS / 32 ? s_warp[lane] : 0, in2 = x;
+				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+				for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+					const uint32_t t = t0 + lane;
+					const bool active = t < total;
+					// owner record = number of lanes whose inclusive prefix is <= t
+					uint32_t r = 0;
 #pragma unroll
-					for (int d = 1; d < 32; d <<= 1) {
-						uint32_t t = __shfl_up_sync(0xffffffffu, in2, d);
-						if (lane >= (uint32_t)d) in2 += t;
+					for (int step = 16; step; step >>= 1) {
+						const uint32_t e = __shfl_sync(0xffffffffu, incl, (r + step - 1) & 31u);
+						if (e <= t && r + step <= 32) r += step;
 					}
-					if (lane < C::THREADS / 32) s_warp[lane] = in2 - x;
-				}
-				__syncthreads();
-				const uint32_t excl = s_warp[warp] + incl - my_n;
-				if (tid < (uint32_t)C::CHUNK) {
-					s_pref[tid] = excl;
-					for (uint32_t j = 0; j < my_n; ++j) s_owner[excl + j] = (uint16_t)tid;
-				}
-				if (tid == C::CHUNK - 1) s_pref[C::CHUNK] = excl + my_n;
-				__syncthreads();
-				const uint32_t total = s_pref[C::CHUNK];
-				for (uint32_t x = tid; x < total; x += C::THREADS) {
-					const uint32_t ri = s_owner[x];
-					const SkRec<W> &r = s_rec[ri];
-					const int nn = (int)(r.w[2 * W - 1] >> 56);
-					const Key<W> fw = tagpu_record_window<W>(r, nn, (int)(x - s_pref[ri]), K);
+					r = active ? r : 0u;
+					const uint32_t r_incl = __shfl_sync(0xffffffffu, incl, r), r_n = __shfl_sync(0xffffffffu, my_n, r);
+					unsigned long long ow[NW];
+#pragma unroll
+					for (int i = 0; i < NW; ++i) ow[i] = __shfl_sync(0xffffffffu, rw[i], r);
+					if (!active) continue;
+					const int j = (int)(t - (r_incl - r_n));
+					const Key<W> fw = tagpu_record_window(ow, (int)r_n, j, K);
 					const Key<W> rv = KO::rc(fw, K);
 					const Key<W> key = KO::le(fw, rv) ? fw : rv;
 					const uint64_t h = KO::hash(key);
@@ -360,8 +357,8 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 						slot = (slot + 1) & (C::SLOTS - 1);
 					}
 				}
-				__syncthreads();
 			}
+			__syncthreads();
 			// ---- harvest (or discard on overflow) and leave the table zeroed
 			const bool failed = *(volatile uint32_t *)&s_overflow != 0;
 			uint32_t mine = 0;
@@ -376,14 +373,14 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 			if (lane == 31) s_warp[warp] = incl;
 			__syncthreads();
 			if (warp == 0) {
-				uint32_t x = lane < C::THREADS / 32 ? s_warp[lane] : 0, in2 = x;
+				uint32_t x = s_warp[lane], in2 = x;
 #pragma unroll
 				for (int d = 1; d < 32; d <<= 1) {
 					uint32_t t = __shfl_up_sync(0xffffffffu, in2, d);
 					if (lane >= (uint32_t)d) in2 += t;
 				}
-				if (lane < C::THREADS / 32) s_warp[lane] = in2 - x;
-				if (lane == C::THREADS / 32 - 1) {
+				s_warp[lane] = in2 - x;
+				if (lane == 31) {
 					s_out_base = in2 ? atomicAdd(ctr + CTR_SOLID, (unsigned long long)in2) : 0ull;
 					if (!failed) atomicAdd(ctr + CTR_DISTINCT, (unsigned long long)s_claims);
 				}

@@ -6,17 +6,23 @@
 // build_asm_graph_from_kmhash + build_graph_worker (:544-649, :421-542), the rc-link loop (:624-641)
 // and build_edge_kmer_index_multi + assign_count_kedge_multi (:291-338, :143-157).
 //
-// Vertex id v = 2 * slot + orient, orient 0 = the canonical k-mer stored in `slot`, 1 = its reverse
+// Table vertex id tv = 2 * slot + orient, orient 0 = the canonical k-mer stored in `slot`, 1 = its reverse
 // complement.  Low nibble of the mask = bases that may follow orient 0, high nibble = orient 1 (App. A.4).
+// Non-branching ("chain") k-mers are renumbered densely (cid) so that every per-vertex array of the list-ranking
+// phase is compact: chain vertex cv = 2 * cid + orient.  Node k-mers get ordinals; node vertex = 2 * ord + orient.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "tagpu_key.cuh"
 
 constexpr uint32_t TAGPU_NONE = 0xffffffffu;
 constexpr uint32_t TAGPU_TERM = 0x80000000u;
+constexpr uint32_t TAGPU_CHAIN = 0x80000000u;   // kind[] entry: chain k-mer (low bits = cid); otherwise node ordinal
 
 enum {
 	CTR_INSTANCES = 0, CTR_DISTINCT, CTR_SOLID, CTR_KMERS, CTR_NODES, CTR_EDGES, CTR_SEQ_WORDS,
-	CTR_KP1_ON_EDGE, CTR_ERROR, CTR_SUM_SOLID, CTR_SPARE0, CTR_SPARE1, CTR_JUMP_FLAGS /* + 64 */, CTR_TOTAL = CTR_JUMP_FLAGS + 64
+	CTR_KP1_ON_EDGE, CTR_ERROR, CTR_SUM_SOLID, CTR_SPARE0, CTR_SPARE1, CTR_CHAIN, CTR_JUMP_ROUNDS,
+	CTR_JUMP_FLAGS /* + 64 */, CTR_TOTAL = CTR_JUMP_FLAGS + 64
 };
 
 enum { TAGPU_ERR_TABLE_FULL = 1, TAGPU_ERR_MISSING_SUCC = 2, TAGPU_ERR_CHAIN = 4, TAGPU_ERR_RC_LINK = 8, TAGPU_ERR_BUCKET_OVERFLOW = 16 };
@@ -44,13 +50,20 @@ TAGPU_DI unsigned long long tagpu_warp_alloc(unsigned long long *ctr, uint32_t w
 }
 
 // ---------------------------------------------------------------- k-mer table (open addressing, linear probing)
-// keys[] holds ~key (canonical k-mers are never all-ones, so 0 == empty); mask8[] is byte-addressed through 32-bit atomics.
+// keys[] holds ~key (canonical k-mers are never all-ones, so 0 == empty); mask bytes are updated through 32-bit atomics.
+// Any slot count works: the home slot is mulhi(hash, n_slots).
 
 template <int W> struct KTab {
 	Key<W> *keys;
-	uint32_t *mask32;      // n_slots / 4 words
-	uint32_t slot_mask;    // n_slots - 1
+	uint32_t *mask32;      // ceil(n_slots / 4) words
+	uint32_t n_slots;
 };
+
+template <int W> TAGPU_DI uint32_t ktab_home(const KTab<W> &t, const Key<W> &key)
+{
+	return __umulhi((uint32_t)(KeyOps<W>::hash(key) >> 32), t.n_slots);
+}
+TAGPU_DI uint32_t ktab_next(uint32_t slot, uint32_t n_slots) { return slot + 1 == n_slots ? 0u : slot + 1; }
 
 template <int W> TAGPU_DI Key<W> ktab_load(const Key<W> *p);
 template <> TAGPU_DI Key<1> ktab_load<1>(const Key<1> *p) { Key<1> r; r.lo = __ldcg(&p->lo); return r; }
@@ -60,7 +73,7 @@ template <> TAGPU_DI Key<2> ktab_load<2>(const Key<2> *p)
 	Key<2> r; r.lo = v.x; r.hi = v.y; return r;
 }
 
-// returns the previous content of the slot (all-zero if we claimed it)
+// returns the previous content of the slot (all-zero if we claimed it); works on global and shared memory
 template <int W> TAGPU_DI Key<W> ktab_cas(Key<W> *p, const Key<W> &stored);
 template <> TAGPU_DI Key<1> ktab_cas<1>(Key<1> *p, const Key<1> &stored)
 {
@@ -85,9 +98,9 @@ TAGPU_DI uint32_t ktab_insert(const KTab<W> &t, const Key<W> &key, bool *claimed
 {
 	typedef KeyOps<W> KO;
 	const Key<W> stored = KO::bnot(key);
-	uint32_t slot = (uint32_t)(KO::hash(key) >> 20) & t.slot_mask;
+	uint32_t slot = ktab_home<W>(t, key);
 	*claimed = false;
-	for (uint32_t probes = 0; probes <= t.slot_mask; ++probes) {
+	for (uint32_t probes = 0; probes < t.n_slots; ++probes) {
 		Key<W> cur = ktab_load<W>(t.keys + slot);
 		if (KO::eq(cur, stored)) return slot;
 		if (KO::is_zero(cur) || ktab_maybe_torn<W>(cur)) {
@@ -95,7 +108,7 @@ TAGPU_DI uint32_t ktab_insert(const KTab<W> &t, const Key<W> &key, bool *claimed
 			if (KO::is_zero(old)) { *claimed = true; return slot; }
 			if (KO::eq(old, stored)) return slot;
 		}
-		slot = (slot + 1) & t.slot_mask;
+		slot = ktab_next(slot, t.n_slots);
 	}
 	atomicOr(err, (unsigned long long)TAGPU_ERR_TABLE_FULL);
 	return 0;
@@ -106,12 +119,12 @@ TAGPU_DI uint32_t ktab_find(const KTab<W> &t, const Key<W> &key)
 {
 	typedef KeyOps<W> KO;
 	const Key<W> stored = KO::bnot(key);
-	uint32_t slot = (uint32_t)(KO::hash(key) >> 20) & t.slot_mask;
-	for (uint32_t probes = 0; probes <= t.slot_mask; ++probes) {
+	uint32_t slot = ktab_home<W>(t, key);
+	for (uint32_t probes = 0; probes < t.n_slots; ++probes) {
 		Key<W> cur = t.keys[slot];
 		if (KO::eq(cur, stored)) return slot;
 		if (KO::is_zero(cur)) return TAGPU_NONE;
-		slot = (slot + 1) & t.slot_mask;
+		slot = ktab_next(slot, t.n_slots);
 	}
 	return TAGPU_NONE;
 }
@@ -161,80 +174,91 @@ __global__ void __launch_bounds__(256) k_insert_kmers(const Key<W> *__restrict__
 	if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(ctr + CTR_KMERS, (unsigned long long)n_new);
 }
 
-// ---------------------------------------------------------------- C1: nodes (one thread per slot)
+// ---------------------------------------------------------------- C1: nodes and chain k-mers (one thread per slot)
 template <int W>
-__global__ void __launch_bounds__(256) k_classify(KTab<W> t, uint32_t *__restrict__ node_ord,
+__global__ void __launch_bounds__(256) k_classify(KTab<W> t, uint32_t *__restrict__ kind,
 						   uint32_t *__restrict__ node_slot, uint32_t *__restrict__ node_ebase,
-						   unsigned long long *ctr)
+						   uint32_t *__restrict__ chain_slot, unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; // grid covers exactly n_slots
-	const bool occ = !KO::is_zero(t.keys[slot]);
-	const uint32_t m = ktab_mask_of<W>(t, slot);
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool in = slot < t.n_slots;
+	const bool occ = in && !KO::is_zero(t.keys[slot]);
+	const uint32_t m = occ ? ktab_mask_of<W>(t, slot) : 0u;
 	const uint32_t df = DEG4(m), dr = DEG4(m >> 4);
 	const bool is_node = occ && !(df == 1 && dr == 1);             // kmer_build.c:453,561
+	const bool is_chain = occ && !is_node;
 	const uint32_t ord = (uint32_t)tagpu_warp_alloc(ctr + CTR_NODES, is_node ? 1u : 0u);
 	const uint32_t eb = (uint32_t)tagpu_warp_alloc(ctr + CTR_EDGES, is_node ? df + dr : 0u);
-	node_ord[slot] = is_node ? ord : TAGPU_NONE;
+	const uint32_t cid = (uint32_t)tagpu_warp_alloc(ctr + CTR_CHAIN, is_chain ? 1u : 0u);
+	if (in) kind[slot] = is_node ? ord : (is_chain ? (TAGPU_CHAIN | cid) : TAGPU_NONE);
 	if (is_node) {
 		node_slot[ord] = slot;
 		node_ebase[ord] = eb;
 	}
+	if (is_chain) chain_slot[cid] = slot;
 }
 
 TAGPU_DI unsigned long long tagpu_pack_jump(uint32_t ptr, uint32_t dist) { return ((unsigned long long)dist << 32) | ptr; }
 
-// ---------------------------------------------------------------- C2: successor links (one thread per oriented vertex)
+// ---------------------------------------------------------------- C2: successor links (one thread per chain vertex)
+// jump[cv] = (ptr, dist): "cv reaches ptr in dist hops".  The last chain vertex before a node points at itself with
+// the TERM bit set; vsucc[cv] then holds the node vertex that follows it.
 template <int W>
-__global__ void __launch_bounds__(256) k_build_succ(KTab<W> t, int k, const uint32_t *__restrict__ node_ord,
-						     unsigned long long *__restrict__ jump, uint32_t *__restrict__ vsucc,
-						     unsigned long long *ctr)
+__global__ void __launch_bounds__(256) k_build_succ(KTab<W> t, int k, uint32_t n_chain_vertices, const uint32_t *__restrict__ kind,
+						     const uint32_t *__restrict__ chain_slot, unsigned long long *__restrict__ jump,
+						     uint32_t *__restrict__ vsucc, unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
-	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;      // grid covers exactly 2 * n_slots
-	const uint32_t slot = v >> 1, o = v & 1u;
-	const Key<W> stored = t.keys[slot];
-	unsigned long long j = tagpu_pack_jump(TAGPU_TERM | TAGPU_NONE, 0); // "not a chain vertex"
-	uint32_t succ = TAGPU_NONE;
-	if (!KO::is_zero(stored) && node_ord[slot] == TAGPU_NONE) {
-		const Key<W> key = KO::bnot(stored);
-		const uint32_t m = ktab_mask_of<W>(t, slot);
-		const uint32_t c = tagpu_only4(o ? (m >> 4) : m);
-		const Key<W> krc = KO::rc(key, k);
-		const Key<W> x = o ? krc : key, xr = o ? key : krc;
-		const Key<W> y = KO::push(x, c, KO::mask(k)), yr = KO::push_front(xr, 3u - c, k);
-		succ = ktab_vertex_of<W>(t, y, yr);
-		if (succ == TAGPU_NONE) {
-			atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_MISSING_SUCC); // kmer_build.c:475 assert
-		} else if (node_ord[succ >> 1] != TAGPU_NONE) {
-			j = tagpu_pack_jump(TAGPU_TERM | v, 0);                  // v is the last interior vertex of its chain
-		} else {
-			j = tagpu_pack_jump(succ, 1);
-		}
+	const uint32_t cv = blockIdx.x * blockDim.x + threadIdx.x;
+	if (cv >= n_chain_vertices) return;
+	const uint32_t slot = chain_slot[cv >> 1], o = cv & 1u;
+	const Key<W> key = KO::bnot(t.keys[slot]);
+	const uint32_t m = ktab_mask_of<W>(t, slot);
+	const uint32_t c = tagpu_only4(o ? (m >> 4) : m);
+	const Key<W> krc = KO::rc(key, k);
+	const Key<W> x = o ? krc : key, xr = o ? key : krc;
+	const Key<W> y = KO::push(x, c, KO::mask(k)), yr = KO::push_front(xr, 3u - c, k);
+	const uint32_t tv = ktab_vertex_of<W>(t, y, yr);
+	unsigned long long j = tagpu_pack_jump(TAGPU_TERM | cv, 0);
+	uint32_t succ_node = TAGPU_NONE;
+	if (tv == TAGPU_NONE) {
+		atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_MISSING_SUCC);  // kmer_build.c:475 assert
+	} else {
+		const uint32_t kd = kind[tv >> 1];
+		if (kd & TAGPU_CHAIN) j = tagpu_pack_jump((kd & ~TAGPU_CHAIN) * 2u + (tv & 1u), 1);
+		else succ_node = kd * 2u + (tv & 1u);
 	}
-	jump[v] = j;
-	vsucc[v] = succ;
+	jump[cv] = j;
+	vsucc[cv] = succ_node;
 }
 
-// ---------------------------------------------------------------- C3: one round of in-place pointer jumping
-// (ptr, dist) travel as one 64-bit word, so a concurrent reader always sees a consistent pair.
-__global__ void __launch_bounds__(256) k_jump_round(unsigned long long *jump, uint32_t n_vertices,
-						     const unsigned long long *flag_prev, unsigned long long *flag_cur)
+// ---------------------------------------------------------------- C3: in-place pointer jumping, all rounds in one cooperative launch
+// (ptr, dist) travel as one 64-bit word, so a concurrent reader always sees a consistent pair.  Vertices on
+// node-free cycles never terminate; the round cap leaves them unterminated and later stages skip them
+// (the reference never emits such unitigs either).
+__global__ void __launch_bounds__(512) k_jump_all(unsigned long long *jump, uint32_t n_vertices, unsigned long long *ctr, int max_rounds)
 {
-	if (flag_prev && *flag_prev == 0) return;                      // previous round left nothing to do
-	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-	bool open = false;
-	if (v < n_vertices) {
-		unsigned long long j = __ldcg(jump + v);
-		uint32_t p = (uint32_t)j;
-		if (!(p & TAGPU_TERM)) {
-			unsigned long long jp = __ldcg(jump + p);
-			uint32_t np = (uint32_t)jp;
+	namespace cg = cooperative_groups;
+	cg::grid_group grid = cg::this_grid();
+	const uint32_t stride = gridDim.x * blockDim.x;
+	int round = 0;
+	for (; round < max_rounds; ++round) {
+		bool open = false;
+		for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_vertices; v += stride) {
+			const unsigned long long j = __ldcg(jump + v);
+			const uint32_t p = (uint32_t)j;
+			if (p & TAGPU_TERM) continue;
+			const unsigned long long jp = __ldcg(jump + p);
+			const uint32_t np = (uint32_t)jp;
 			__stcg(jump + v, tagpu_pack_jump(np, (uint32_t)(j >> 32) + (uint32_t)(jp >> 32)));
-			open = !(np & TAGPU_TERM);
+			open |= !(np & TAGPU_TERM);
 		}
+		if (__any_sync(0xffffffffu, open) && (threadIdx.x & 31) == 0) ctr[CTR_JUMP_FLAGS + round] = 1;
+		grid.sync();
+		if (__ldcg(ctr + CTR_JUMP_FLAGS + round) == 0) break;
 	}
-	if (__any_sync(0xffffffffu, open) && (threadIdx.x & 31) == 0) *flag_cur = 1;
+	if (blockIdx.x == 0 && threadIdx.x == 0) ctr[CTR_JUMP_ROUNDS] = (unsigned long long)round + 1;
 }
 
 // ---------------------------------------------------------------- flat graph in device memory
@@ -247,7 +271,7 @@ struct FlatGraph {
 // ---------------------------------------------------------------- C4: edge heads (one thread per oriented node)
 template <int W>
 __global__ void __launch_bounds__(128) k_edge_heads(KTab<W> t, int k, uint32_t n_nodes,
-						     const uint32_t *__restrict__ node_ord, const uint32_t *__restrict__ node_slot,
+						     const uint32_t *__restrict__ kind, const uint32_t *__restrict__ node_slot,
 						     const uint32_t *__restrict__ node_ebase, const unsigned long long *__restrict__ jump,
 						     const uint32_t *__restrict__ vsucc, uint32_t *__restrict__ vedge,
 						     FlatGraph g, unsigned long long *ctr)
@@ -255,12 +279,12 @@ __global__ void __launch_bounds__(128) k_edge_heads(KTab<W> t, int k, uint32_t n
 	typedef KeyOps<W> KO;
 	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;       // oriented node id
 	const bool live = u < 2u * n_nodes;
-	uint32_t ord = 0, o = 0, m = 0, nib = 0, e0 = 0;
+	uint32_t nib = 0, e0 = 0;
 	Key<W> x = KO::make(0, 0), xr = KO::make(0, 0);
 	if (live) {
-		ord = u >> 1; o = u & 1u;
+		const uint32_t ord = u >> 1, o = u & 1u;
 		const uint32_t slot = node_slot[ord];
-		m = ktab_mask_of<W>(t, slot);
+		const uint32_t m = ktab_mask_of<W>(t, slot);
 		nib = o ? (m >> 4) : (m & 15u);
 		e0 = node_ebase[ord] + (o ? DEG4(m) : 0u);
 		const Key<W> key = KO::bnot(t.keys[slot]), krc = KO::rc(key, k);
@@ -273,19 +297,21 @@ __global__ void __launch_bounds__(128) k_edge_heads(KTab<W> t, int k, uint32_t n
 		if (have) {
 			const Key<W> y = KO::push(x, c, KO::mask(k)), yr = KO::push_front(xr, 3u - c, k);
 			const uint32_t tv = ktab_vertex_of<W>(t, y, yr);
-			if (tv == TAGPU_NONE) {
+			const uint32_t kd = tv == TAGPU_NONE ? TAGPU_NONE : kind[tv >> 1];
+			if (kd == TAGPU_NONE) {
 				atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_MISSING_SUCC);
-			} else if (node_ord[tv >> 1] != TAGPU_NONE) {
-				len = k + 1; dst = node_ord[tv >> 1] * 2u + (tv & 1u);
+			} else if (!(kd & TAGPU_CHAIN)) {
+				len = k + 1; dst = kd * 2u + (tv & 1u);
 			} else {
-				const unsigned long long j = jump[tv];
-				if (!((uint32_t)j & TAGPU_TERM) || ((uint32_t)j & ~TAGPU_TERM) == (TAGPU_NONE & ~TAGPU_TERM)) {
-					atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CHAIN);
+				const uint32_t cv = (kd & ~TAGPU_CHAIN) * 2u + (tv & 1u);
+				const unsigned long long j = jump[cv];
+				if (!((uint32_t)j & TAGPU_TERM)) {
+					atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CHAIN); // a chain entered from a node must end at a node
 				} else {
-					const uint32_t vm = (uint32_t)j & ~TAGPU_TERM, tn = vsucc[vm];
+					const uint32_t vm = (uint32_t)j & ~TAGPU_TERM;
 					len = k + 1 + (uint32_t)(j >> 32) + 1;
-					dst = node_ord[tn >> 1] * 2u + (tn & 1u);
-					first = tv;
+					dst = vsucc[vm];
+					first = cv;
 				}
 			}
 		}
@@ -311,23 +337,21 @@ __global__ void __launch_bounds__(128) k_edge_heads(KTab<W> t, int k, uint32_t n
 
 // ---------------------------------------------------------------- C5: interior vertices write their base and learn their edge
 template <int W>
-__global__ void __launch_bounds__(256) k_interior(KTab<W> t, int k, uint32_t n_vertices,
+__global__ void __launch_bounds__(256) k_interior(KTab<W> t, int k, uint32_t n_chain_vertices, const uint32_t *__restrict__ chain_slot,
 						   const unsigned long long *__restrict__ jump, uint32_t *vedge, FlatGraph g)
 {
-	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= n_vertices) return;
-	const unsigned long long j = jump[v];
-	if (!((uint32_t)j & TAGPU_TERM) || ((uint32_t)j & ~TAGPU_TERM) == (TAGPU_NONE & ~TAGPU_TERM)) return; // node, empty or cycle
-	const unsigned long long jt = jump[v ^ 1u];
-	if (!((uint32_t)jt & TAGPU_TERM)) return;
-	const uint32_t v1 = ((uint32_t)jt & ~TAGPU_TERM) ^ 1u;          // first interior vertex of v's chain
+	const uint32_t cv = blockIdx.x * blockDim.x + threadIdx.x;
+	if (cv >= n_chain_vertices) return;
+	const unsigned long long j = jump[cv], jt = jump[cv ^ 1u];
+	if (!((uint32_t)j & TAGPU_TERM) || !((uint32_t)jt & TAGPU_TERM)) return;  // node-free cycle
+	const uint32_t v1 = ((uint32_t)jt & ~TAGPU_TERM) ^ 1u;          // first interior vertex of cv's chain
 	const uint32_t e = vedge[v1];
-	if (e == TAGPU_NONE) return;                                    // chain not reachable from a node (cannot happen)
+	if (e == TAGPU_NONE) return;
 	const uint32_t pos = k + 1 + (uint32_t)(jt >> 32);
-	const uint32_t m = ktab_mask_of<W>(t, v >> 1);
-	const uint32_t c = tagpu_only4((v & 1u) ? (m >> 4) : m);
+	const uint32_t m = ktab_mask_of<W>(t, chain_slot[cv >> 1]);
+	const uint32_t c = tagpu_only4((cv & 1u) ? (m >> 4) : m);
 	atomicOr(g.e_seq + g.e_off[e] + (pos >> 4), c << ((pos & 15u) << 1));
-	vedge[v] = e;
+	vedge[cv] = e;
 }
 
 // ---------------------------------------------------------------- C6: reverse-complement links (one thread per edge)
@@ -351,7 +375,7 @@ __global__ void __launch_bounds__(256) k_rc_links(KTab<W> t, int k, uint32_t n_e
 template <int W>
 __global__ void __launch_bounds__(256) k_edge_counts(const Key<W> *__restrict__ solid, const uint32_t *__restrict__ solid_cnt,
 						      uint64_t n_solid, int k, KTab<W> t, const uint32_t *__restrict__ vL,
-						      const uint32_t *__restrict__ vR, const uint32_t *__restrict__ node_ord,
+						      const uint32_t *__restrict__ vR, const uint32_t *__restrict__ kind,
 						      const uint32_t *__restrict__ node_ebase, const uint32_t *__restrict__ vedge,
 						      FlatGraph g, unsigned long long *ctr)
 {
@@ -365,13 +389,13 @@ __global__ void __launch_bounds__(256) k_edge_counts(const Key<W> *__restrict__ 
 		const uint32_t cc[2] = { KO::last_base(x), 3u - KO::first_base(x, k + 1) };
 #pragma unroll
 		for (int s = 0; s < 2; ++s) {
-			const uint32_t v = vv[s], slot = v >> 1, o = v & 1u, ord = node_ord[slot];
+			const uint32_t v = vv[s], slot = v >> 1, o = v & 1u, kd = kind[slot];
 			uint32_t e;
-			if (ord != TAGPU_NONE) {
+			if (!(kd & TAGPU_CHAIN)) {
 				const uint32_t m = ktab_mask_of<W>(t, slot), nib = o ? (m >> 4) : (m & 15u);
-				e = node_ebase[ord] + (o ? DEG4(m) : 0u) + tagpu_rank4(nib, cc[s]);
+				e = node_ebase[kd] + (o ? DEG4(m) : 0u) + tagpu_rank4(nib, cc[s]);
 			} else {
-				e = vedge[v];
+				e = vedge[(kd & ~TAGPU_CHAIN) * 2u + o];
 			}
 			if (e != TAGPU_NONE) {
 				atomicAdd(g.e_count + e, (unsigned long long)cnt);

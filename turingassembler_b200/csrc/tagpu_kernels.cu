@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -29,7 +31,8 @@ struct tagpu_ctx {
 	char err[512] = { 0 };
 	unsigned long long *d_ctr = nullptr, *h_ctr = nullptr;
 	Buf regions, cursor, overflow, overflow_bucket, ext, ext_off, ext_count;
-	int n_sm = 0;
+	int n_sm = 0, jump_grid = 0;
+	Buf chain_slot;
 	Buf seq, ctab, clist, solid_key, solid_cnt, kt_keys, kt_mask, node_ord, node_slot, node_ebase, vL, vR, jump, vsucc,
 		vedge, e_src, e_dst, e_rc, e_len, e_count, e_off, e_seq;
 	uint64_t ctab_slots = 0;
@@ -39,7 +42,64 @@ struct tagpu_ctx {
 	tagpu_stats st;
 	cudaEvent_t ev[4];
 	uint64_t launches = 0;
+	// optional per-kernel timing (tagpu_set_profile): one CUDA event pair around every launch
+	int profile = 0;
+	std::vector<cudaEvent_t> ev_pool;
+	size_t ev_used = 0;
+	struct ProfRec { const char *name; cudaEvent_t a, b; };
+	std::vector<ProfRec> prof;
+	std::string prof_json;
 };
+
+static cudaEvent_t prof_event(tagpu_ctx *ctx)
+{
+	if (ctx->ev_used == ctx->ev_pool.size()) {
+		cudaEvent_t e;
+		cudaEventCreate(&e);
+		ctx->ev_pool.push_back(e);
+	}
+	return ctx->ev_pool[ctx->ev_used++];
+}
+
+struct ProfScope {
+	tagpu_ctx *ctx;
+	cudaEvent_t a = nullptr;
+	const char *name;
+	ProfScope(tagpu_ctx *c, const char *n) : ctx(c), name(n)
+	{
+		if (ctx->profile) { a = prof_event(ctx); cudaEventRecord(a, ctx->stream); }
+	}
+	~ProfScope()
+	{
+		if (ctx->profile) { cudaEvent_t b = prof_event(ctx); cudaEventRecord(b, ctx->stream); ctx->prof.push_back({ name, a, b }); }
+	}
+};
+
+static void prof_finish(tagpu_ctx *ctx)
+{
+	ctx->prof_json = "{";
+	if (ctx->profile) {
+		std::map<std::string, std::pair<double, int>> agg;
+		std::vector<std::string> order;
+		for (auto &r : ctx->prof) {
+			float ms = 0;
+			cudaEventElapsedTime(&ms, r.a, r.b);
+			if (!agg.count(r.name)) order.push_back(r.name);
+			agg[r.name].first += ms;
+			agg[r.name].second += 1;
+		}
+		bool first = true;
+		for (auto &n : order) {
+			char buf[256];
+			snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"launches\": %d}", first ? "" : ", ", n.c_str(), agg[n].first, agg[n].second);
+			ctx->prof_json += buf;
+			first = false;
+		}
+	}
+	ctx->prof_json += "}";
+	ctx->prof.clear();
+	ctx->ev_used = 0;
+}
 
 static int fail(tagpu_ctx *c, const char *fmt, ...)
 {
@@ -110,7 +170,7 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->chain_slot, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
 			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
 	for (Buf *b : bufs)
@@ -118,6 +178,7 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	cudaFree(ctx->d_ctr);
 	cudaFreeHost(ctx->h_ctr);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
+	for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
@@ -126,6 +187,8 @@ extern "C" void tagpu_set_stream(tagpu_ctx *ctx, void *s) { ctx->stream = s ? (c
 extern "C" void tagpu_set_cutoff(tagpu_ctx *ctx, int ci) { ctx->ci = ci < 1 ? 1 : ci; }
 extern "C" void tagpu_set_skip_counts(tagpu_ctx *ctx, int skip) { ctx->skip_counts = skip; }
 extern "C" const char *tagpu_last_error(tagpu_ctx *ctx) { return ctx->err; }
+extern "C" void tagpu_set_profile(tagpu_ctx *ctx, int on) { ctx->profile = on; }
+extern "C" const char *tagpu_profile_json(tagpu_ctx *ctx) { return ctx->prof_json.c_str(); }
 
 static int read_counters(tagpu_ctx *ctx)
 {
@@ -138,6 +201,7 @@ static int read_counters(tagpu_ctx *ctx)
 
 #define LAUNCH(kernel, grid, block, ...)                                                   \
 	do {                                                                               \
+		ProfScope ps_(ctx, #kernel);                                               \
 		kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                  \
 		++ctx->launches;                                                           \
 		CU(cudaGetLastError());                                                    \
@@ -154,7 +218,7 @@ static int count_stage(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n)
 	bool grew;
 	if (ensure(ctx, ctx->ctab, slots * sizeof(CSlot<W>), &grew)) return -1;
 	if (grew || ctx->ctab_W != W || ctx->ctab_slots != slots) {
-		CU(cudaMemsetAsync(ctx->ctab.p, 0, ctx->ctab.cap, ctx->stream)); // once; afterwards kept clean by k_compact_solid
+		{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->ctab.p, 0, ctx->ctab.cap, ctx->stream)); } // once; afterwards kept clean by k_compact_solid
 		ctx->ctab_W = W;
 		ctx->ctab_slots = slots;
 	}
@@ -184,6 +248,7 @@ static int count_stage(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n)
 // ------------------------------------------------------------------------------------------------ count stage (partitioned)
 #define LAUNCH_SMEM(kernel, grid, block, smem, ...)                                        \
 	do {                                                                               \
+		ProfScope ps_(ctx, #kernel);                                               \
 		kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);             \
 		++ctx->launches;                                                           \
 		CU(cudaGetLastError());                                                    \
@@ -194,8 +259,8 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 {
 	typedef BucketCfg<W> BC;
 	const int K = ctx->K;
-	// bucket count: aim at <= ~1400 distinct keys per 4096-slot table, guessing distinct ~ stream bytes / 8
-	uint64_t want = n / 8 / 1400 + 1;
+	// bucket count: aim at a mean load of ~0.4 per table, guessing distinct ~ stream bytes / 8
+	uint64_t want = n / 8 / (BC::SLOTS * 2 / 5) + 1;
 	int log2p = 10;
 	while ((1ull << log2p) < want && log2p < 22) ++log2p;
 	const uint32_t n_buckets = 1u << log2p;
@@ -211,7 +276,7 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 	    ensure(ctx, ctx->overflow_bucket, (size_t)cfg.overflow_cap * 4) || ensure(ctx, ctx->ext_off, (size_t)(n_buckets + 1) * 4) ||
 	    ensure(ctx, ctx->ext_count, (size_t)n_buckets * 4))
 		return -1;
-	CU(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)n_buckets * 8, ctx->stream));
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)n_buckets * 8, ctx->stream)); }
 	const size_t smem1 = TAGPU_SMEM_WORDS * 8 + (TAGPU_SMEM_WORDS + 2) * 4 + 2 * (size_t)TAGPU_HM_LEN * 4;
 	static bool attr_done[3] = { false, false, false };
 	if (!attr_done[W]) {
@@ -227,7 +292,7 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 	const uint64_t n_inst = ctx->h_ctr[CTR_INSTANCES], n_over = ctx->h_ctr[CTR_SPARE0];
 	if (n_over) {
 		if (ensure(ctx, ctx->ext, n_over * sizeof(SkRec<W>))) return -1;
-		CU(cudaMemsetAsync(ctx->ext_count.p, 0, (size_t)n_buckets * 4, ctx->stream));
+		{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->ext_count.p, 0, (size_t)n_buckets * 4, ctx->stream)); }
 		LAUNCH(k_overflow_hist, (unsigned)((n_over + 255) / 256), 256, (const uint32_t *)ctx->overflow_bucket.p, n_over, (uint32_t *)ctx->ext_count.p);
 		LAUNCH(k_overflow_scan, 1, 1024, (uint32_t *)ctx->ext_count.p, (uint32_t *)ctx->ext_off.p, n_buckets);
 		LAUNCH(k_overflow_scatter<W>, (unsigned)((n_over + 255) / 256), 256, (const SkRec<W> *)ctx->overflow.p,
@@ -236,7 +301,7 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 	}
 	const uint64_t solid_cap = n_inst / (uint64_t)ctx->ci + 1; // every solid key owns >= ci instances
 	if (ensure(ctx, ctx->solid_key, solid_cap * sizeof(Key<W>)) || ensure(ctx, ctx->solid_cnt, solid_cap * 4)) return -1;
-	LAUNCH_SMEM(k_count_buckets<W>, 2 * ctx->n_sm, BC::THREADS, BC::SMEM, (const SkRec<W> *)ctx->regions.p,
+	LAUNCH_SMEM(k_count_buckets<W>, ctx->n_sm, BC::THREADS, BC::SMEM, (const SkRec<W> *)ctx->regions.p,
 		    (const unsigned long long *)ctx->cursor.p, cfg.cap_records, (const SkRec<W> *)ctx->ext.p, (const uint32_t *)ctx->ext_off.p,
 		    n_buckets, K, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p, ctx->d_ctr);
 	if (read_counters(ctx)) return -1;
@@ -254,64 +319,80 @@ static int graph_stage(tagpu_ctx *ctx)
 {
 	const int k = ctx->k;
 	const uint64_t n_solid = ctx->st.n_solid;
-	uint64_t slots64 = pow2_at_least(3 * n_solid + 1024);
-	if (slots64 > (1ull << 29)) return fail(ctx, "k-mer table would need %llu slots (> 2^29)", (unsigned long long)slots64);
-	const uint32_t n_slots = (uint32_t)slots64, n_vert = 2 * n_slots;
+	// every solid (k+1)-mer touches two k-mers; in practice #k-mers ~ #solid, so 2.5x keeps the load near 0.4
+	const uint64_t slots64 = (n_solid * 5) / 2 + 1024;
+	if (slots64 > (1ull << 30)) return fail(ctx, "k-mer table would need %llu slots (> 2^30)", (unsigned long long)slots64);
+	const uint32_t n_slots = (uint32_t)slots64;
 	ctx->kt_slots = n_slots;
-	if (ensure(ctx, ctx->kt_keys, (size_t)n_slots * sizeof(Key<W>)) || ensure(ctx, ctx->kt_mask, n_slots) ||
+	const size_t mask_bytes = ((size_t)n_slots + 3) / 4 * 4;
+	if (ensure(ctx, ctx->kt_keys, (size_t)n_slots * sizeof(Key<W>)) || ensure(ctx, ctx->kt_mask, mask_bytes) ||
 	    ensure(ctx, ctx->node_ord, (size_t)n_slots * 4) || ensure(ctx, ctx->vL, (n_solid + 1) * 4) ||
 	    ensure(ctx, ctx->vR, (n_solid + 1) * 4) || ensure(ctx, ctx->node_slot, (2 * n_solid + 1) * 4) ||
-	    ensure(ctx, ctx->node_ebase, (2 * n_solid + 1) * 4) || ensure(ctx, ctx->jump, (size_t)n_vert * 8) ||
-	    ensure(ctx, ctx->vsucc, (size_t)n_vert * 4) || ensure(ctx, ctx->vedge, (size_t)n_vert * 4))
+	    ensure(ctx, ctx->node_ebase, (2 * n_solid + 1) * 4) || ensure(ctx, ctx->chain_slot, (2 * n_solid + 1) * 4))
 		return -1;
 	KTab<W> t;
 	t.keys = (Key<W> *)ctx->kt_keys.p;
 	t.mask32 = (uint32_t *)ctx->kt_mask.p;
-	t.slot_mask = n_slots - 1;
-	CU(cudaMemsetAsync(t.keys, 0, (size_t)n_slots * sizeof(Key<W>), ctx->stream));
-	CU(cudaMemsetAsync(t.mask32, 0, n_slots, ctx->stream));
-	CU(cudaMemsetAsync(ctx->vedge.p, 0xff, (size_t)n_vert * 4, ctx->stream));
-	uint32_t *node_ord = (uint32_t *)ctx->node_ord.p, *node_slot = (uint32_t *)ctx->node_slot.p,
-		 *node_ebase = (uint32_t *)ctx->node_ebase.p, *vL = (uint32_t *)ctx->vL.p, *vR = (uint32_t *)ctx->vR.p,
-		 *vsucc = (uint32_t *)ctx->vsucc.p, *vedge = (uint32_t *)ctx->vedge.p;
-	unsigned long long *jump = (unsigned long long *)ctx->jump.p, *ctr = ctx->d_ctr;
+	t.n_slots = n_slots;
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(t.keys, 0, (size_t)n_slots * sizeof(Key<W>), ctx->stream)); }
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(t.mask32, 0, mask_bytes, ctx->stream)); }
+	uint32_t *kind = (uint32_t *)ctx->node_ord.p, *node_slot = (uint32_t *)ctx->node_slot.p,
+		 *node_ebase = (uint32_t *)ctx->node_ebase.p, *chain_slot = (uint32_t *)ctx->chain_slot.p,
+		 *vL = (uint32_t *)ctx->vL.p, *vR = (uint32_t *)ctx->vR.p;
+	unsigned long long *ctr = ctx->d_ctr;
 	const Key<W> *solid = (const Key<W> *)ctx->solid_key.p;
 
 	if (n_solid) LAUNCH(k_insert_kmers<W>, (unsigned)((n_solid + 255) / 256), 256, solid, n_solid, k, t, vL, vR, ctr);
-	LAUNCH(k_classify<W>, n_slots / 256, 256, t, node_ord, node_slot, node_ebase, ctr);
-	LAUNCH(k_build_succ<W>, n_vert / 256, 256, t, k, node_ord, jump, vsucc, ctr);
-	const int max_rounds = 40;
-	for (int r = 0; r < max_rounds; ++r)
-		LAUNCH(k_jump_round, n_vert / 256, 256, jump, n_vert, r ? ctr + CTR_JUMP_FLAGS + r - 1 : nullptr, ctr + CTR_JUMP_FLAGS + r);
+	LAUNCH(k_classify<W>, (n_slots + 255) / 256, 256, t, kind, node_slot, node_ebase, chain_slot, ctr);
 	if (read_counters(ctx)) return -1;
-	const uint64_t n_nodes = ctx->h_ctr[CTR_NODES], n_e = ctx->h_ctr[CTR_EDGES];
+	const uint64_t n_nodes = ctx->h_ctr[CTR_NODES], n_e = ctx->h_ctr[CTR_EDGES], n_chain = ctx->h_ctr[CTR_CHAIN];
 	ctx->st.n_kmers = ctx->h_ctr[CTR_KMERS];
 	ctx->st.n_v = 2 * n_nodes;
 	ctx->st.n_e = n_e;
-	uint64_t rounds = 0;
-	while (rounds < (uint64_t)max_rounds && ctx->h_ctr[CTR_JUMP_FLAGS + rounds]) ++rounds;
-	ctx->st.jump_rounds = rounds + 1;
 	if (n_e > 0xfffffff0ull) return fail(ctx, "too many edges (%llu)", (unsigned long long)n_e);
+	const uint32_t n_cv = (uint32_t)(2 * n_chain);
 	const uint64_t seq_cap = (n_e * (uint64_t)k + 2 * n_solid) / 16 + n_e + 16;
-	if (ensure(ctx, ctx->e_src, (n_e + 1) * 4) || ensure(ctx, ctx->e_dst, (n_e + 1) * 4) || ensure(ctx, ctx->e_rc, (n_e + 1) * 4) ||
-	    ensure(ctx, ctx->e_len, (n_e + 1) * 4) || ensure(ctx, ctx->e_count, (n_e + 1) * 8) || ensure(ctx, ctx->e_off, (n_e + 1) * 8) ||
-	    ensure(ctx, ctx->e_seq, seq_cap * 4))
+	if (ensure(ctx, ctx->jump, ((size_t)n_cv + 1) * 8) || ensure(ctx, ctx->vsucc, ((size_t)n_cv + 1) * 4) ||
+	    ensure(ctx, ctx->vedge, ((size_t)n_cv + 1) * 4) || ensure(ctx, ctx->e_src, (n_e + 1) * 4) ||
+	    ensure(ctx, ctx->e_dst, (n_e + 1) * 4) || ensure(ctx, ctx->e_rc, (n_e + 1) * 4) || ensure(ctx, ctx->e_len, (n_e + 1) * 4) ||
+	    ensure(ctx, ctx->e_count, (n_e + 1) * 8) || ensure(ctx, ctx->e_off, (n_e + 1) * 8) || ensure(ctx, ctx->e_seq, seq_cap * 4))
 		return -1;
+	unsigned long long *jump = (unsigned long long *)ctx->jump.p;
+	uint32_t *vsucc = (uint32_t *)ctx->vsucc.p, *vedge = (uint32_t *)ctx->vedge.p;
 	FlatGraph g;
 	g.e_src = (uint32_t *)ctx->e_src.p; g.e_dst = (uint32_t *)ctx->e_dst.p; g.e_rc = (uint32_t *)ctx->e_rc.p;
 	g.e_len = (uint32_t *)ctx->e_len.p; g.e_count = (unsigned long long *)ctx->e_count.p;
 	g.e_off = (unsigned long long *)ctx->e_off.p; g.e_seq = (uint32_t *)ctx->e_seq.p;
-	CU(cudaMemsetAsync(g.e_seq, 0, seq_cap * 4, ctx->stream));
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(vedge, 0xff, ((size_t)n_cv + 1) * 4, ctx->stream)); }
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(g.e_seq, 0, seq_cap * 4, ctx->stream)); }
+	if (n_cv) {
+		LAUNCH(k_build_succ<W>, (n_cv + 255) / 256, 256, t, k, n_cv, kind, chain_slot, jump, vsucc, ctr);
+		// all pointer-jumping rounds in one cooperative launch (grid-wide sync between rounds)
+		if (!ctx->jump_grid) {
+			int per_sm = 0;
+			CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jump_all, 512, 0));
+			ctx->jump_grid = ctx->n_sm * (per_sm > 0 ? per_sm : 1);
+		}
+		int max_rounds = 40;
+		uint32_t n_cv_arg = n_cv;
+		void *args[] = { &jump, &n_cv_arg, &ctr, &max_rounds };
+		{
+			ProfScope ps_(ctx, "k_jump_all");
+			CU(cudaLaunchCooperativeKernel((void *)k_jump_all, dim3(ctx->jump_grid), dim3(512), args, 0, ctx->stream));
+			++ctx->launches;
+		}
+	}
 	if (n_nodes)
-		LAUNCH(k_edge_heads<W>, (unsigned)((2 * n_nodes + 127) / 128), 128, t, k, (uint32_t)n_nodes, node_ord, node_slot, node_ebase,
+		LAUNCH(k_edge_heads<W>, (unsigned)((2 * n_nodes + 127) / 128), 128, t, k, (uint32_t)n_nodes, kind, node_slot, node_ebase,
 		       jump, vsucc, vedge, g, ctr);
-	LAUNCH(k_interior<W>, n_vert / 256, 256, t, k, n_vert, jump, vedge, g);
+	if (n_cv) LAUNCH(k_interior<W>, (n_cv + 255) / 256, 256, t, k, n_cv, chain_slot, jump, vedge, g);
 	if (n_e) LAUNCH(k_rc_links<W>, (unsigned)((n_e + 255) / 256), 256, t, k, (uint32_t)n_e, node_slot, node_ebase, g, ctr);
 	if (n_solid && !ctx->skip_counts)
 		LAUNCH(k_edge_counts<W>, (unsigned)((n_solid + 255) / 256), 256, solid, (const uint32_t *)ctx->solid_cnt.p, n_solid, k, t,
-		       vL, vR, node_ord, node_ebase, vedge, g, ctr);
+		       vL, vR, kind, node_ebase, vedge, g, ctr);
 	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
 	if (read_counters(ctx)) return -1;
+	ctx->st.jump_rounds = ctx->h_ctr[CTR_JUMP_ROUNDS];
 	ctx->st.n_seq_words = ctx->h_ctr[CTR_SEQ_WORDS];
 	ctx->st.n_kp1_on_edge = ctx->h_ctr[CTR_KP1_ON_EDGE];
 	if (ctx->st.n_seq_words > seq_cap) return fail(ctx, "edge sequence buffer overflow (%llu > %llu words)",
@@ -331,7 +412,7 @@ static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool wit
 	ctx->launches = 0;
 	ctx->err[0] = 0;
 	memset(&ctx->st, 0, sizeof(ctx->st));
-	CU(cudaMemsetAsync(ctx->d_ctr, 0, CTR_TOTAL * sizeof(unsigned long long), ctx->stream));
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->d_ctr, 0, CTR_TOTAL * sizeof(unsigned long long), ctx->stream)); }
 	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
 	static const bool direct = getenv("TAGPU_COUNT_DIRECT") != nullptr; // bring-up cross-check only
 	int rc = direct ? (ctx->W == 1 ? count_stage<1>(ctx, d_seq, n) : count_stage<2>(ctx, d_seq, n))
@@ -349,6 +430,7 @@ static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool wit
 	CU(cudaEventElapsedTime(&ctx->st.ms_graph, ctx->ev[1], ctx->ev[2]));
 	CU(cudaEventElapsedTime(&ctx->st.ms_total, ctx->ev[0], ctx->ev[2]));
 	ctx->st.gpu_launches = ctx->launches;
+	prof_finish(ctx);
 	return 0;
 }
 
@@ -466,3 +548,12 @@ extern "C" void tagpu_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" int tagpu_ctx_k(tagpu_ctx *ctx) { return ctx->k; }
 extern "C" int tagpu_ctx_K(tagpu_ctx *ctx) { return ctx->K; }
 extern "C" int tagpu_ctx_cutoff(tagpu_ctx *ctx) { return ctx->ci; }
+
+// developer introspection: per-bucket cursors of the last partition pass (low 32 bits records, high 32 bits instances)
+extern "C" uint64_t tagpu_debug_bucket_cursors(tagpu_ctx *ctx, uint64_t *out, uint64_t max_n)
+{
+	uint64_t n = ctx->cursor.cap / 8;
+	if (n > max_n) n = max_n;
+	cudaMemcpy(out, ctx->cursor.p, n * 8, cudaMemcpyDeviceToHost);
+	return n;
+}
