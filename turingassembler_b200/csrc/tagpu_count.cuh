@@ -43,13 +43,12 @@ TAGPU_DI uint32_t tagpu_bucket_of(uint32_t minhash, int log2_buckets)
 	return (minhash * 0x85ebca6bu) >> (32 - log2_buckets);
 }
 
-// the 32 bases ending at packed-tile position end_q (inclusive), first base most significant
+// the 32 bases ending at packed-tile position end_q (inclusive, >= 31), first base most significant
 TAGPU_DI uint64_t tagpu_extract32(const uint64_t *pk, int end_q)
 {
-	const int wi = end_q >> 5, r = (end_q & 31) + 1;
-	if (r == 32) return pk[wi];
-	const uint64_t prev = wi > 0 ? pk[wi - 1] : 0ull;
-	return (prev << (2 * r)) | (pk[wi] >> (64 - 2 * r));
+	const int wi = end_q >> 5, sh = 62 - 2 * (end_q & 31);      // bits of pk[wi] that lie beyond end_q
+	const unsigned __int128 two = ((unsigned __int128)pk[wi > 0 ? wi - 1 : 0] << 64) | pk[wi];
+	return (uint64_t)(two >> sh);
 }
 
 template <int W>
@@ -59,11 +58,8 @@ TAGPU_DI SkRec<W> tagpu_make_record(const uint64_t *pk, int end_q, int n_bases, 
 #pragma unroll
 	for (int i = 0; i < 2 * W; ++i) {
 		const int have = n_bases - 32 * i;              // bases that belong in word i
-		uint64_t v = 0;
-		if (have > 0) {
-			v = tagpu_extract32(pk, end_q - 32 * i);
-			if (have < 32) v &= (1ull << (2 * have)) - 1;
-		}
+		uint64_t v = have > 0 ? tagpu_extract32(pk, end_q - 32 * i) : 0ull;
+		if (have < 32) v &= have > 0 ? (1ull << (2 * have)) - 1 : 0ull;
 		r.w[i] = v;
 	}
 	r.w[2 * W - 1] |= (unsigned long long)n_windows << 56;
@@ -80,8 +76,8 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	uint64_t *pk = reinterpret_cast<uint64_t *>(smem_raw);
 	uint32_t *inv = reinterpret_cast<uint32_t *>(pk + TAGPU_SMEM_WORDS);
-	uint32_t *ha = inv + TAGPU_SMEM_WORDS + 2;          // two ping-pong arrays of per-position m-mer hashes / running minima
-	uint32_t *hb = ha + TAGPU_HM_LEN;
+	uint32_t *hp = inv + TAGPU_SMEM_WORDS + 2;          // m-mer hash per position, then block-wise prefix minima (in place)
+	uint32_t *hs = hp + TAGPU_HM_LEN;                   // block-wise suffix minima
 	const int K = cfg.K, m = TAGPU_MINIMIZER_M;
 
 	tagpu_load_tile(seq, n, (uint64_t)blockIdx.x * TAGPU_TILE_BASES, pk, inv);
@@ -91,8 +87,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
 		const uint32_t mm = (1u << (2 * m)) - 1;
 		uint32_t fw = j ? (uint32_t)pk[j - 1] & mm : 0u;
-		uint32_t rv = 0;
-		for (int b = 0; b < m; ++b) rv |= (3u - ((fw >> (2 * b)) & 3u)) << (2 * (m - 1 - b));
+		uint32_t rv = (uint32_t)(tagpu_rc64_full((uint64_t)fw) >> (64 - 2 * m));
 		const uint32_t i1 = j ? inv[j - 1] : 0xffffffffu;
 		int run = i1 ? (__ffs(i1) - 1) : 32;
 		uint64_t cur = pk[j];
@@ -107,31 +102,24 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 			rv = (rv >> 2) | ((3u - c) << (2 * (m - 1)));
 			run = bad ? 0 : run + 1;
 			const uint32_t cm = min(fw, rv);
-			ha[j * 33 + i] = run >= m ? (cm * 0x9e3779b1u) >> 10 : TAGPU_H_INVALID;
+			hp[j * 33 + i] = run >= m ? (cm * 0x9e3779b1u) >> 10 : TAGPU_H_INVALID;
 		}
 	}
 	__syncthreads();
 
-	// B. minimum over the w = K - m + 1 m-mers of every window, by doubling: after the pass with step s,
-	//    x[q] = min(h[q - 2s + 1 .. q]); the last pass combines two overlapping power-of-two windows.
+	// B. sliding minimum over the w = K - m + 1 m-mers of every window (van Herk / Gil-Werman): positions are cut
+	//    into blocks of w; one thread scans a block backwards (suffix minima -> hs) and forwards (prefix minima, in
+	//    place); min over [q - w + 1, q] is then min(hs[q - w + 1], hp[q]) — two sequential passes instead of log2(w).
 	const int w = K - m + 1;
-	uint32_t *src = ha, *dst = hb;
-	int span = 1;
-	while (span * 2 <= w) {
-		for (int q = threadIdx.x; q < TAGPU_HM_POS; q += blockDim.x)
-			dst[HIDX(q)] = q >= span ? min(src[HIDX(q)], src[HIDX(q - span)]) : src[HIDX(q)];
-		__syncthreads();
-		uint32_t *t = src; src = dst; dst = t;
-		span *= 2;
+	const int n_blocks = (TAGPU_HM_POS + w - 1) / w;
+	for (int blk = threadIdx.x; blk < n_blocks; blk += blockDim.x) {
+		const int lo = blk * w, hi = min(lo + w, TAGPU_HM_POS);
+		uint32_t acc = TAGPU_H_INVALID;
+		for (int q = hi - 1; q >= lo; --q) { acc = min(acc, hp[HIDX(q)]); hs[HIDX(q)] = acc; }
+		acc = TAGPU_H_INVALID;
+		for (int q = lo; q < hi; ++q) { acc = min(acc, hp[HIDX(q)]); hp[HIDX(q)] = acc; }
 	}
-	if (span < w) {
-		const int d = w - span;
-		for (int q = threadIdx.x; q < TAGPU_HM_POS; q += blockDim.x)
-			dst[HIDX(q)] = q >= d ? min(src[HIDX(q)], src[HIDX(q - d)]) : src[HIDX(q)];
-		__syncthreads();
-		uint32_t *t = src; src = dst; dst = t;
-	}
-	const uint32_t *minh = src;
+	__syncthreads();
 
 	// C. every thread cuts the 32 window-end positions of its word into runs and appends one record per run
 	const int wi = threadIdx.x + TAGPU_HALO_WORDS;
@@ -161,7 +149,8 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 		run = bad ? 0 : run + 1;
 		const int q = wi * 32 + i;
 		if (run >= K) {
-			const uint32_t b = tagpu_bucket_of(minh[HIDX(q)], cfg.log2_buckets);
+			const uint32_t mh = min(hs[HIDX(q - w + 1)], hp[HIDX(q)]);
+			const uint32_t b = tagpu_bucket_of(mh, cfg.log2_buckets);
 			if (cur_n && (b != cur_b || cur_n == max_windows)) flush(q - 1);
 			cur_b = b;
 			++cur_n;
@@ -221,37 +210,44 @@ __global__ void k_overflow_scatter(const SkRec<W> *__restrict__ overflow, const 
 // ---------------------------------------------------------------- pass 2
 template <int W> struct BucketCfg {
 	static constexpr int THREADS = 1024;
-	static constexpr int SLOTS = W == 1 ? 16384 : 8192;         // shared-memory table slots per CTA (192 KB / 160 KB)
+	static constexpr int LOG2_SLOTS = W == 1 ? 14 : 13;
+	static constexpr int SLOTS = 1 << LOG2_SLOTS;               // shared-memory table slots per CTA (192 KB / 160 KB)
 	static constexpr int LIMIT = SLOTS * 13 / 16;               // claims beyond this abort the attempt (re-run on sub-classes)
-	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4);
+	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + THREADS * sizeof(SkRec<W>);
 };
 
-// window j (0 = first) of a record holding n windows of K bases; w[] = the record's low words (header stripped)
-TAGPU_DI Key<1> tagpu_record_window(const unsigned long long (&w)[2], int n, int j, int K)
+// table hash: one multiply per key word; the top bits pick the slot, the next ones the sub-class
+template <int W> TAGPU_DI uint64_t tagpu_table_hash(const Key<W> &k);
+template <> TAGPU_DI uint64_t tagpu_table_hash<1>(const Key<1> &k) { uint64_t h = k.lo * 0x9e3779b97f4a7c15ull; return h ^ (h >> 32); }
+template <> TAGPU_DI uint64_t tagpu_table_hash<2>(const Key<2> &k)
+{
+	uint64_t h = (k.lo ^ (k.hi * 0xd6e8feb86659fd93ull)) * 0x9e3779b97f4a7c15ull;
+	return h ^ (h >> 32);
+}
+
+// first window (j = 0) .. of a record: w[] = low words with the length byte stripped, n = windows in the record
+TAGPU_DI Key<1> tagpu_record_window(const SkRec<1> &r, int n, int j, int K)
 {
 	const int sh = 2 * (n - 1 - j);                             // 0..62
+	const unsigned long long w1 = r.w[1] & 0x00ffffffffffffffull;
 	Key<1> k;
-	k.lo = sh ? (w[0] >> sh) | (w[1] << (64 - sh)) : w[0];
+	k.lo = (uint64_t)((((unsigned __int128)w1 << 64) | r.w[0]) >> sh);
 	if (K < 32) k.lo &= (1ull << (2 * K)) - 1;
 	return k;
 }
-TAGPU_DI Key<2> tagpu_record_window(const unsigned long long (&w)[3], int n, int j, int K)
+TAGPU_DI Key<2> tagpu_record_window(const SkRec<2> &r, int n, int j, int K)
 {
 	const int sh = 2 * (n - 1 - j);                             // 0..62 (n <= 32): windows never reach word 3
 	Key<2> k;
-	if (sh) {
-		k.lo = (w[0] >> sh) | (w[1] << (64 - sh));
-		k.hi = (w[1] >> sh) | (w[2] << (64 - sh));
-	} else {
-		k.lo = w[0];
-		k.hi = w[1];
-	}
+	k.lo = (uint64_t)((((unsigned __int128)r.w[1] << 64) | r.w[0]) >> sh);
+	k.hi = (uint64_t)((((unsigned __int128)r.w[2] << 64) | r.w[1]) >> sh);
 	return KeyOps<2>::band(k, KeyOps<2>::mask(K));
 }
 
-// One CTA per bucket (persistent CTAs pull bucket ids from a global counter).  Warps stream the bucket's records
-// independently: a warp holds 32 records in registers, spreads their windows evenly over its lanes (prefix sum +
-// shuffle search), and every lane inserts its canonical key into the CTA's shared-memory table.
+// One CTA per bucket (persistent CTAs pull bucket ids from a global counter).  Each warp stages 32 records in
+// shared memory, splits their windows into 32 equal contiguous segments (one per lane) and every lane ROLLS the
+// forward / reverse-complement keys through its segment (re-seeding only at record boundaries), inserting the
+// canonical key into the CTA's shared-memory table.
 template <int W>
 __global__ void __launch_bounds__(BucketCfg<W>::THREADS, 1)
 k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *__restrict__ cursor, uint32_t cap_records,
@@ -260,14 +256,16 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 {
 	typedef KeyOps<W> KO;
 	typedef BucketCfg<W> C;
-	constexpr int NW = W + 1;                                   // record words that can hold window bases
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Key<W> *t_key = reinterpret_cast<Key<W> *>(smem_raw);
 	uint32_t *t_cnt = reinterpret_cast<uint32_t *>(t_key + C::SLOTS);
+	SkRec<W> *s_rec = reinterpret_cast<SkRec<W> *>(t_cnt + C::SLOTS);
 	__shared__ uint32_t s_bucket, s_claims, s_overflow, s_warp[C::THREADS / 32], s_stack[64], s_sp;
 	__shared__ unsigned long long s_out_base;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	constexpr uint32_t N_WARPS = C::THREADS / 32;
+	SkRec<W> *my_recs = s_rec + warp * 32;
+	const Key<W> kmask = KO::mask(K);
 
 	for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) { t_key[i] = KO::make(0, 0); t_cnt[i] = 0; }
 
@@ -302,17 +300,11 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 			for (uint32_t base = warp * 32; base < n_total; base += N_WARPS * 32) {
 				if (*(volatile uint32_t *)&s_overflow) break;
 				const uint32_t g = base + lane;
-				unsigned long long rw[NW];
 				uint32_t my_n = 0;
 				if (g < n_total) {
 					const SkRec<W> r = g < n_main ? main_rec[g] : ext_rec[g - n_main];
 					my_n = (uint32_t)(r.w[2 * W - 1] >> 56);
-#pragma unroll
-					for (int i = 0; i < NW; ++i) rw[i] = r.w[i];
-					if (W == 1) rw[1] &= 0x00ffffffffffffffull;
-				} else {
-#pragma unroll
-					for (int i = 0; i < NW; ++i) rw[i] = 0;
+					my_recs[lane] = r;
 				}
 				uint32_t incl = my_n;
 #pragma unroll
@@ -321,42 +313,59 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 					if (lane >= (uint32_t)d) incl += t;
 				}
 				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-				for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-					const uint32_t t = t0 + lane;
-					const bool active = t < total;
-					// owner record = number of lanes whose inclusive prefix is <= t
-					uint32_t r = 0;
+				const uint32_t seg = (total + 31) >> 5;
+				const uint32_t t0 = min(total, lane * seg), t1 = min(total, t0 + seg);
+				// owner record of window t0 = number of lanes whose inclusive prefix is <= t0
+				uint32_t r = 0;
 #pragma unroll
-					for (int step = 16; step; step >>= 1) {
-						const uint32_t e = __shfl_sync(0xffffffffu, incl, (r + step - 1) & 31u);
-						if (e <= t && r + step <= 32) r += step;
-					}
-					r = active ? r : 0u;
-					const uint32_t r_incl = __shfl_sync(0xffffffffu, incl, r), r_n = __shfl_sync(0xffffffffu, my_n, r);
-					unsigned long long ow[NW];
-#pragma unroll
-					for (int i = 0; i < NW; ++i) ow[i] = __shfl_sync(0xffffffffu, rw[i], r);
-					if (!active) continue;
-					const int j = (int)(t - (r_incl - r_n));
-					const Key<W> fw = tagpu_record_window(ow, (int)r_n, j, K);
-					const Key<W> rv = KO::rc(fw, K);
-					const Key<W> key = KO::le(fw, rv) ? fw : rv;
-					const uint64_t h = KO::hash(key);
-					if (L && ((uint32_t)(h >> 40) & ((1u << L) - 1u)) != cls) continue;
-					const Key<W> stored = KO::bnot(key);
-					uint32_t slot = (uint32_t)h & (C::SLOTS - 1);
+				for (int step = 16; step; step >>= 1) {
+					const uint32_t e = __shfl_sync(0xffffffffu, incl, (r + step - 1) & 31u);
+					if (e <= t0 && r + step <= 32) r += step;
+				}
+				r &= 31u;
+				const uint32_t r_incl = __shfl_sync(0xffffffffu, incl, r), r_n0 = __shfl_sync(0xffffffffu, my_n, r);
+				__syncwarp();
+				uint32_t left = t1 - t0;
+				if (left) {
+					int n_r = (int)r_n0, j = (int)(t0 - (r_incl - r_n0));
+					const SkRec<W> *rp = my_recs + r;
+					unsigned long long w0 = rp->w[0];
+					Key<W> fw = tagpu_record_window(*rp, n_r, j, K);
+					Key<W> rv = KO::rc(fw, K);
 					for (;;) {
-						const Key<W> have = t_key[slot];
-						if (KO::eq(have, stored)) { atomicAdd(t_cnt + slot, 1u); break; }
-						if (KO::is_zero(have) || ktab_maybe_torn<W>(have)) {
-							if (*(volatile uint32_t *)&s_claims >= (uint32_t)C::LIMIT) { s_overflow = 1; break; }
-							const Key<W> old = ktab_cas<W>(t_key + slot, stored);   // ATOMS.CAS.64 / .128
-							if (KO::is_zero(old)) { atomicAdd(&s_claims, 1u); atomicAdd(t_cnt + slot, 1u); break; }
-							if (KO::eq(old, stored)) { atomicAdd(t_cnt + slot, 1u); break; }
+						const Key<W> key = KO::le(fw, rv) ? fw : rv;
+						const uint64_t h = tagpu_table_hash<W>(key);
+						if (!L || ((uint32_t)(h >> (64 - C::LOG2_SLOTS - 20)) & ((1u << L) - 1u)) == cls) {
+							const Key<W> stored = KO::bnot(key);
+							uint32_t slot = (uint32_t)(h >> (64 - C::LOG2_SLOTS));
+							for (;;) {
+								const Key<W> have = t_key[slot];
+								if (KO::eq(have, stored)) { atomicAdd(t_cnt + slot, 1u); break; }
+								if (KO::is_zero(have) || ktab_maybe_torn<W>(have)) {
+									if (*(volatile uint32_t *)&s_claims >= (uint32_t)C::LIMIT) { s_overflow = 1; break; }
+									const Key<W> old = ktab_cas<W>(t_key + slot, stored);   // ATOMS.CAS.64 / .128
+									if (KO::is_zero(old)) { atomicAdd(&s_claims, 1u); atomicAdd(t_cnt + slot, 1u); break; }
+									if (KO::eq(old, stored)) { atomicAdd(t_cnt + slot, 1u); break; }
+								}
+								slot = (slot + 1) & (C::SLOTS - 1);
+							}
 						}
-						slot = (slot + 1) & (C::SLOTS - 1);
+						if (!--left) break;
+						if (++j == n_r) {                                    // next record: re-seed
+							++rp;
+							n_r = (int)(rp->w[2 * W - 1] >> 56);
+							j = 0;
+							w0 = rp->w[0];
+							fw = tagpu_record_window(*rp, n_r, 0, K);
+							rv = KO::rc(fw, K);
+						} else {                                             // next window of the same record: roll one base
+							const uint32_t c = (uint32_t)(w0 >> (2 * (n_r - 1 - j))) & 3u;
+							fw = KO::push(fw, c, kmask);
+							rv = KO::push_front(rv, 3u - c, K);
+						}
 					}
 				}
+				__syncwarp();
 			}
 			__syncthreads();
 			// ---- harvest (or discard on overflow) and leave the table zeroed
