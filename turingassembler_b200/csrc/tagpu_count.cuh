@@ -20,7 +20,7 @@
 #include "tagpu_extract.cuh"
 #include "tagpu_graph.cuh"
 
-constexpr int TAGPU_MINIMIZER_M = 11;                 // m-mer length (22 bits)
+constexpr int TAGPU_MINIMIZER_M = 15;                 // m-mer length (30 bits): long enough that one m-mer value ~ one genomic site
 constexpr uint32_t TAGPU_H_INVALID = 0xffffffffu;
 constexpr int TAGPU_HM_POS = TAGPU_SMEM_WORDS * 32;   // positions of the packed tile (incl. halo)
 constexpr int TAGPU_HM_LEN = TAGPU_SMEM_WORDS * 33;   // padded: index q + q/32, so word-major and position-major accesses are both conflict-free
@@ -121,28 +121,17 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 	}
 	__syncthreads();
 
-	// C. every thread cuts the 32 window-end positions of its word into runs and appends one record per run
+	// C. every thread cuts the 32 window-end positions of its word into runs of equal bucket.  The scan only records
+	//    run starts / ends as two bit masks; the records are built afterwards, one run per lane per iteration, so the
+	//    expensive part (128/256-bit extraction, cursor atomic, 16/32-byte store) runs converged instead of lane by lane.
 	const int wi = threadIdx.x + TAGPU_HALO_WORDS;
 	const uint32_t i1 = inv[wi - 1], i2 = inv[wi - 2];
 	int run = i1 ? (__ffs(i1) - 1) : 32 + (i2 ? (__ffs(i2) - 1) : 32);
 	uint32_t iv = inv[wi];
 	const int max_windows = min(32, SkCap<W>::bases - (K - 1));
 	int cur_n = 0;
-	uint32_t cur_b = 0, n_win = 0;
-	auto flush = [&](int end_q) {
-		if (!cur_n) return;
-		const SkRec<W> rec = tagpu_make_record<W>(pk, end_q, cur_n + K - 1, cur_n);
-		const unsigned long long old = atomicAdd(cursor + cur_b, 1ull | ((unsigned long long)cur_n << 32));
-		const uint32_t idx = (uint32_t)old;
-		if (idx < cfg.cap_records) {
-			regions[(size_t)cur_b * cfg.cap_records + idx] = rec;
-		} else {
-			const unsigned long long o = atomicAdd(ctr + CTR_SPARE0, 1ull);
-			if (o < cfg.overflow_cap) { overflow[o] = rec; overflow_bucket[o] = cur_b; }
-			else atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_BUCKET_OVERFLOW);
-		}
-		cur_n = 0;
-	};
+	uint32_t cur_b = 0, n_win = 0, starts = 0, ends = 0;
+#pragma unroll 4
 	for (int i = 0; i < 32; ++i) {
 		const bool bad = (int)iv < 0;
 		iv <<= 1;
@@ -151,15 +140,34 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 		if (run >= K) {
 			const uint32_t mh = min(hs[HIDX(q - w + 1)], hp[HIDX(q)]);
 			const uint32_t b = tagpu_bucket_of(mh, cfg.log2_buckets);
-			if (cur_n && (b != cur_b || cur_n == max_windows)) flush(q - 1);
+			if (cur_n && (b != cur_b || cur_n == max_windows)) { ends |= 1u << (i - 1); cur_n = 0; }
+			if (!cur_n) starts |= 1u << i;
 			cur_b = b;
 			++cur_n;
 			++n_win;
-		} else {
-			flush(q - 1);
+		} else if (cur_n) {
+			ends |= 1u << (i - 1);
+			cur_n = 0;
 		}
 	}
-	flush(wi * 32 + 31);
+	if (cur_n) ends |= 1u << 31;
+	while (ends) {
+		const int e = __ffs(ends) - 1, st = __ffs(starts) - 1;
+		ends &= ends - 1;
+		starts &= starts - 1;
+		const int nw = e - st + 1, end_q = wi * 32 + e;
+		const uint32_t b = tagpu_bucket_of(min(hs[HIDX(end_q - w + 1)], hp[HIDX(end_q)]), cfg.log2_buckets);
+		const SkRec<W> rec = tagpu_make_record<W>(pk, end_q, nw + K - 1, nw);
+		const unsigned long long old = atomicAdd(cursor + b, 1ull | ((unsigned long long)nw << 32));
+		const uint32_t idx = (uint32_t)old;
+		if (idx < cfg.cap_records) {
+			regions[(size_t)b * cfg.cap_records + idx] = rec;
+		} else {
+			const unsigned long long o = atomicAdd(ctr + CTR_SPARE0, 1ull);
+			if (o < cfg.overflow_cap) { overflow[o] = rec; overflow_bucket[o] = b; }
+			else atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_BUCKET_OVERFLOW);
+		}
+	}
 	// instance total (the metric's numerator): one atomic per CTA
 	__shared__ uint32_t s_inst;
 	if (threadIdx.x == 0) s_inst = 0;
@@ -212,8 +220,9 @@ template <int W> struct BucketCfg {
 	static constexpr int THREADS = 1024;
 	static constexpr int LOG2_SLOTS = W == 1 ? 14 : 13;
 	static constexpr int SLOTS = 1 << LOG2_SLOTS;               // shared-memory table slots per CTA (192 KB / 160 KB)
-	static constexpr int LIMIT = SLOTS * 13 / 16;               // claims beyond this abort the attempt (re-run on sub-classes)
-	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + THREADS * sizeof(SkRec<W>);
+	static constexpr int MAX_PROBES = 48;                       // a longer probe sequence aborts the attempt (re-run on sub-classes)
+	static constexpr int LIMIT = SLOTS * 7 / 8;                 // ... as does a harvest that finds the table this full
+	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + 2 * THREADS * sizeof(SkRec<W>);
 };
 
 // table hash: one multiply per key word; the top bits pick the slot, the next ones the sub-class
@@ -225,23 +234,44 @@ template <> TAGPU_DI uint64_t tagpu_table_hash<2>(const Key<2> &k)
 	return h ^ (h >> 32);
 }
 
-// first window (j = 0) .. of a record: w[] = low words with the length byte stripped, n = windows in the record
-TAGPU_DI Key<1> tagpu_record_window(const SkRec<1> &r, int n, int j, int K)
+// K bases of a right-aligned record value, `sh` bits above its right end (sh <= 62)
+TAGPU_DI Key<1> tagpu_record_window(const SkRec<1> &r, int sh, int K)
 {
-	const int sh = 2 * (n - 1 - j);                             // 0..62
 	const unsigned long long w1 = r.w[1] & 0x00ffffffffffffffull;
 	Key<1> k;
 	k.lo = (uint64_t)((((unsigned __int128)w1 << 64) | r.w[0]) >> sh);
 	if (K < 32) k.lo &= (1ull << (2 * K)) - 1;
 	return k;
 }
-TAGPU_DI Key<2> tagpu_record_window(const SkRec<2> &r, int n, int j, int K)
+TAGPU_DI Key<2> tagpu_record_window(const SkRec<2> &r, int sh, int K)
 {
-	const int sh = 2 * (n - 1 - j);                             // 0..62 (n <= 32): windows never reach word 3
-	Key<2> k;
+	Key<2> k;                                                    // n <= 32 windows: bases never reach word 3
 	k.lo = (uint64_t)((((unsigned __int128)r.w[1] << 64) | r.w[0]) >> sh);
 	k.hi = (uint64_t)((((unsigned __int128)r.w[2] << 64) | r.w[1]) >> sh);
 	return KeyOps<2>::band(k, KeyOps<2>::mask(K));
+}
+
+// reverse complement of the nb bases of a record, right-aligned again (no length byte)
+TAGPU_DI SkRec<1> tagpu_record_rc(const SkRec<1> &r, int nb)
+{
+	const unsigned __int128 f = ((unsigned __int128)tagpu_rc64_full(r.w[0]) << 64) | tagpu_rc64_full(r.w[1] & 0x00ffffffffffffffull);
+	const unsigned __int128 v = f >> (2 * (64 - nb));
+	SkRec<1> o;
+	o.w[0] = (uint64_t)v;
+	o.w[1] = (uint64_t)(v >> 64);
+	return o;
+}
+TAGPU_DI SkRec<2> tagpu_record_rc(const SkRec<2> &r, int nb)
+{
+	const uint64_t f0 = tagpu_rc64_full(r.w[2]), f1 = tagpu_rc64_full(r.w[1]), f2 = tagpu_rc64_full(r.w[0]); // f2:f1:f0 = rc of 96 bases
+	const int s = 2 * (96 - nb), ws = s >> 6, bs = s & 63;      // drop the complemented padding: shift right by s bits
+	const uint64_t a0 = ws == 0 ? f0 : (ws == 1 ? f1 : f2), a1 = ws == 0 ? f1 : (ws == 1 ? f2 : 0ull), a2 = ws == 0 ? f2 : 0ull;
+	SkRec<2> o;
+	o.w[0] = (uint64_t)((((unsigned __int128)a1 << 64) | a0) >> bs);
+	o.w[1] = (uint64_t)((((unsigned __int128)a2 << 64) | a1) >> bs);
+	o.w[2] = a2 >> bs;
+	o.w[3] = 0;
+	return o;
 }
 
 // One CTA per bucket (persistent CTAs pull bucket ids from a global counter).  Each warp stages 32 records in
@@ -264,7 +294,8 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 	__shared__ unsigned long long s_out_base;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	constexpr uint32_t N_WARPS = C::THREADS / 32;
-	SkRec<W> *my_recs = s_rec + warp * 32;
+	SkRec<W> *my_recs = s_rec + warp * 32;                      // forward records of the warp's current batch
+	SkRec<W> *my_rcs = s_rec + C::THREADS + warp * 32;          // ... and their reverse complements
 	const Key<W> kmask = KO::mask(K);
 
 	for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) { t_key[i] = KO::make(0, 0); t_cnt[i] = 0; }
@@ -297,14 +328,22 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 			if (tid == 0) { --s_sp; s_claims = 0; s_overflow = 0; }
 			__syncthreads();
 			// ---- insert every window of the bucket that belongs to hash class (L, cls)
+			SkRec<W> pre;                                                // software prefetch of the next batch's record
+			if (warp * 32 + lane < n_total) {
+				const uint32_t g = warp * 32 + lane;
+				pre = g < n_main ? main_rec[g] : ext_rec[g - n_main];
+			}
 			for (uint32_t base = warp * 32; base < n_total; base += N_WARPS * 32) {
 				if (*(volatile uint32_t *)&s_overflow) break;
-				const uint32_t g = base + lane;
 				uint32_t my_n = 0;
-				if (g < n_total) {
-					const SkRec<W> r = g < n_main ? main_rec[g] : ext_rec[g - n_main];
-					my_n = (uint32_t)(r.w[2 * W - 1] >> 56);
-					my_recs[lane] = r;
+				if (base + lane < n_total) {
+					my_n = (uint32_t)(pre.w[2 * W - 1] >> 56);
+					my_recs[lane] = pre;
+					my_rcs[lane] = tagpu_record_rc(pre, (int)my_n + K - 1);
+				}
+				{
+					const uint32_t g = base + N_WARPS * 32 + lane;
+					if (g < n_total) pre = g < n_main ? main_rec[g] : ext_rec[g - n_main];
 				}
 				uint32_t incl = my_n;
 #pragma unroll
@@ -330,34 +369,37 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 					int n_r = (int)r_n0, j = (int)(t0 - (r_incl - r_n0));
 					const SkRec<W> *rp = my_recs + r;
 					unsigned long long w0 = rp->w[0];
-					Key<W> fw = tagpu_record_window(*rp, n_r, j, K);
-					Key<W> rv = KO::rc(fw, K);
+					Key<W> fw = tagpu_record_window(*rp, 2 * (n_r - 1 - j), K);
+					Key<W> rv = tagpu_record_window(my_rcs[r], 2 * j, K);
 					for (;;) {
 						const Key<W> key = KO::le(fw, rv) ? fw : rv;
 						const uint64_t h = tagpu_table_hash<W>(key);
 						if (!L || ((uint32_t)(h >> (64 - C::LOG2_SLOTS - 20)) & ((1u << L) - 1u)) == cls) {
+							// probe: the hit / claim decision is the only divergent part; the count increment is shared
 							const Key<W> stored = KO::bnot(key);
 							uint32_t slot = (uint32_t)(h >> (64 - C::LOG2_SLOTS));
+							int probes = 0;
 							for (;;) {
 								const Key<W> have = t_key[slot];
-								if (KO::eq(have, stored)) { atomicAdd(t_cnt + slot, 1u); break; }
+								if (KO::eq(have, stored)) break;
 								if (KO::is_zero(have) || ktab_maybe_torn<W>(have)) {
-									if (*(volatile uint32_t *)&s_claims >= (uint32_t)C::LIMIT) { s_overflow = 1; break; }
 									const Key<W> old = ktab_cas<W>(t_key + slot, stored);   // ATOMS.CAS.64 / .128
-									if (KO::is_zero(old)) { atomicAdd(&s_claims, 1u); atomicAdd(t_cnt + slot, 1u); break; }
-									if (KO::eq(old, stored)) { atomicAdd(t_cnt + slot, 1u); break; }
+									if (KO::is_zero(old) || KO::eq(old, stored)) break;
 								}
 								slot = (slot + 1) & (C::SLOTS - 1);
+								if (++probes > C::MAX_PROBES) { s_overflow = 1; break; }       // table too full: re-run on sub-classes
 							}
+							atomicAdd(t_cnt + slot, 1u);
 						}
 						if (!--left) break;
-						if (++j == n_r) {                                    // next record: re-seed
+						if (++j == n_r) {                                    // next record: re-seed from the staged forward / rc records
 							++rp;
+							++r;
 							n_r = (int)(rp->w[2 * W - 1] >> 56);
 							j = 0;
 							w0 = rp->w[0];
-							fw = tagpu_record_window(*rp, n_r, 0, K);
-							rv = KO::rc(fw, K);
+							fw = tagpu_record_window(*rp, 2 * (n_r - 1), K);
+							rv = tagpu_record_window(my_rcs[r], 0, K);
 						} else {                                             // next window of the same record: roll one base
 							const uint32_t c = (uint32_t)(w0 >> (2 * (n_r - 1 - j))) & 3u;
 							fw = KO::push(fw, c, kmask);
@@ -370,9 +412,15 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 			__syncthreads();
 			// ---- harvest (or discard on overflow) and leave the table zeroed
 			const bool failed = *(volatile uint32_t *)&s_overflow != 0;
-			uint32_t mine = 0;
+			uint32_t mine = 0, used = 0;
 			if (!failed)
-				for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) mine += t_cnt[i] >= ci ? 1u : 0u;
+				for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) {
+					const uint32_t c = t_cnt[i];
+					mine += c >= ci ? 1u : 0u;
+					used += c ? 1u : 0u;
+				}
+			used = __reduce_add_sync(0xffffffffu, used);
+			if (lane == 0 && used) atomicAdd(&s_claims, used);
 			uint32_t incl = mine;
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1) {

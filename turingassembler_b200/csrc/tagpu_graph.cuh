@@ -175,22 +175,50 @@ __global__ void __launch_bounds__(256) k_insert_kmers(const Key<W> *__restrict__
 }
 
 // ---------------------------------------------------------------- C1: nodes and chain k-mers (one thread per slot)
+// Node ordinals, edge-id bases and chain ids are bump-allocated with ONE atomic per counter per 1024-thread block.
 template <int W>
-__global__ void __launch_bounds__(256) k_classify(KTab<W> t, uint32_t *__restrict__ kind,
-						   uint32_t *__restrict__ node_slot, uint32_t *__restrict__ node_ebase,
-						   uint32_t *__restrict__ chain_slot, unsigned long long *ctr)
+__global__ void __launch_bounds__(1024) k_classify(KTab<W> t, uint32_t *__restrict__ kind,
+						    uint32_t *__restrict__ node_slot, uint32_t *__restrict__ node_ebase,
+						    uint32_t *__restrict__ chain_slot, unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	__shared__ uint32_t s_w[3][32];
+	__shared__ unsigned long long s_base[3];
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const bool in = slot < t.n_slots;
 	const bool occ = in && !KO::is_zero(t.keys[slot]);
 	const uint32_t m = occ ? ktab_mask_of<W>(t, slot) : 0u;
 	const uint32_t df = DEG4(m), dr = DEG4(m >> 4);
 	const bool is_node = occ && !(df == 1 && dr == 1);             // kmer_build.c:453,561
 	const bool is_chain = occ && !is_node;
-	const uint32_t ord = (uint32_t)tagpu_warp_alloc(ctr + CTR_NODES, is_node ? 1u : 0u);
-	const uint32_t eb = (uint32_t)tagpu_warp_alloc(ctr + CTR_EDGES, is_node ? df + dr : 0u);
-	const uint32_t cid = (uint32_t)tagpu_warp_alloc(ctr + CTR_CHAIN, is_chain ? 1u : 0u);
+	uint32_t v[3] = { is_node ? 1u : 0u, is_node ? df + dr : 0u, is_chain ? 1u : 0u }, incl[3];
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		uint32_t x = v[c];
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+			if (lane >= (uint32_t)d) x += y;
+		}
+		incl[c] = x;
+		if (lane == 31) s_w[c][warp] = x;
+	}
+	__syncthreads();
+	if (warp < 3) {
+		const uint32_t x = s_w[warp][lane];
+		uint32_t y = x;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			uint32_t z = __shfl_up_sync(0xffffffffu, y, d);
+			if (lane >= (uint32_t)d) y += z;
+		}
+		s_w[warp][lane] = y - x;
+		if (lane == 31) s_base[warp] = y ? atomicAdd(ctr + (warp == 0 ? CTR_NODES : (warp == 1 ? CTR_EDGES : CTR_CHAIN)), (unsigned long long)y) : 0ull;
+	}
+	__syncthreads();
+	const uint32_t ord = (uint32_t)s_base[0] + s_w[0][warp] + incl[0] - v[0];
+	const uint32_t eb = (uint32_t)s_base[1] + s_w[1][warp] + incl[1] - v[1];
+	const uint32_t cid = (uint32_t)s_base[2] + s_w[2][warp] + incl[2] - v[2];
 	if (in) kind[slot] = is_node ? ord : (is_chain ? (TAGPU_CHAIN | cid) : TAGPU_NONE);
 	if (is_node) {
 		node_slot[ord] = slot;

@@ -259,8 +259,8 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 {
 	typedef BucketCfg<W> BC;
 	const int K = ctx->K;
-	// bucket count: aim at a mean load of ~0.4 per table, guessing distinct ~ stream bytes / 8
-	uint64_t want = n / 8 / (BC::SLOTS * 2 / 5) + 1;
+	// bucket count: aim at a mean load of ~0.2 per table (bucket sizes are skewed: CV ~0.9), guessing distinct ~ stream bytes / 8
+	uint64_t want = n / 8 / (BC::SLOTS / 5) + 1;
 	int log2p = 10;
 	while ((1ull << log2p) < want && log2p < 22) ++log2p;
 	const uint32_t n_buckets = 1u << log2p;
@@ -343,7 +343,7 @@ static int graph_stage(tagpu_ctx *ctx)
 	const Key<W> *solid = (const Key<W> *)ctx->solid_key.p;
 
 	if (n_solid) LAUNCH(k_insert_kmers<W>, (unsigned)((n_solid + 255) / 256), 256, solid, n_solid, k, t, vL, vR, ctr);
-	LAUNCH(k_classify<W>, (n_slots + 255) / 256, 256, t, kind, node_slot, node_ebase, chain_slot, ctr);
+	LAUNCH(k_classify<W>, (n_slots + 1023) / 1024, 1024, t, kind, node_slot, node_ebase, chain_slot, ctr);
 	if (read_counters(ctx)) return -1;
 	const uint64_t n_nodes = ctx->h_ctr[CTR_NODES], n_e = ctx->h_ctr[CTR_EDGES], n_chain = ctx->h_ctr[CTR_CHAIN];
 	ctx->st.n_kmers = ctx->h_ctr[CTR_KMERS];
