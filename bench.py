@@ -28,6 +28,9 @@ WORKLOADS = {
     "small": dict(genome_len=400_000, n_pairs=150_000, k=45, seed=1),
 }
 L = 151
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the last `ncu --set full` capture of the C2 workload
+# (profiles/), keyed by kernel; None until such a capture exists for the current kernels
+TRAFFIC = {}
 
 
 def gen_reads_gpu(torch, genome_len, n_pairs, seed, device, sub_err=0.005, n_rate=0.02, n_repeats=40, repeat_len=600):
@@ -236,21 +239,28 @@ def main():
 
     for _ in range(args.warmup):
         st = t.build_device(d_stream.data_ptr(), n_stream, k)
+    t.set_profile(True)   # one CUDA-event pair around every kernel launch, on the launching stream
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms_count = ms_graph = 0.0
     launches = 0
+    kern = {}
     ev0.record(stream)
     for _ in range(args.steps):
         st = t.build_device(d_stream.data_ptr(), n_stream, k)
         ms_count += st["ms_count"]
         ms_graph += st["ms_graph"]
         launches += st["gpu_launches"]
+        for name, v in t.profile().items():
+            a = kern.setdefault(name, [0.0, 0])
+            a[0] += v["ms"]
+            a[1] += v["launches"]
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
+    t.set_profile(False)
     # e2e: pinned host stream -> C-ABI host call (H2D inside) -> stats back
     t.build_host((h_stream.data_ptr(), n_stream), k)
     barrier()
@@ -276,7 +286,17 @@ def main():
     b_count, b_graph = algorithmic_bytes(st, k, n_stream)
     peak, peak_src = peaks()
     count_ms = ms_count / args.steps
-    achieved = b_count / (count_ms * 1e-3) / 1e9
+    # dominant kernel = the one with the largest share of the step; its algorithmic bytes:
+    #   k_count_buckets: N_i (W + 8) + N_distinct (W + 4)   (key compare + count read/write, first touch per distinct key)
+    #   k_partition:     N_i B_in                            (the ASCII stream is read exactly once)
+    W = 8 if k + 1 <= 32 else 16
+    kbytes = {"k_count_buckets<W>": st["n_instances"] * (W + 8) + st["n_distinct"] * (W + 4), "k_partition<W>": float(n_stream)}
+    kernels = {name: {"ms_per_launch": v[0] / max(v[1], 1), "launches_per_step": v[1] / args.steps,
+                      "share_of_step": v[0] / args.steps / ms_step} for name, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
+    top = next(iter(kernels))
+    top_ms = kernels[top]["ms_per_launch"]
+    top_bytes = kbytes.get(top, b_count)
+    achieved = top_bytes / (top_ms * 1e-3) / 1e9
     line = {
         "metric": "kmers_per_sec_counted_and_graph_built", "value": value, "unit": "kmers/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -287,13 +307,16 @@ def main():
                    "n_v": st["n_v"], "n_e": st["n_e"], "parallelism": f"replicas x{world}" if world > 1 else "1 gpu"},
         "stage_ms": {"count": count_ms, "graph": ms_graph / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "count stage (all kernels of the (k+1)-mer counting stage)",
-                     "algorithmic_bytes": b_count, "peak_source": peak_src,
+                     "traffic": TRAFFIC.get(top), "kernel": top, "ms_per_launch": top_ms,
+                     "algorithmic_bytes": top_bytes, "peak_source": peak_src,
+                     "count_stage": {"achieved": b_count / (count_ms * 1e-3) / 1e9, "frac": b_count / (count_ms * 1e-3) / 1e9 / peak,
+                                     "algorithmic_bytes": b_count},
                      "whole_path": {"achieved": (b_count + b_graph) / (ms_step * 1e-3) / 1e9,
                                     "frac": (b_count + b_graph) / (ms_step * 1e-3) / 1e9 / peak}},
         "e2e": {"value": st_e["n_instances"] / (ms_e2e / args.steps * 1e-3), "unit": "kmers/s",
                 "h2d_bytes_per_step": n_stream, "d2h_bytes_per_step": 8 * 140, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "kernels": kernels,
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline:

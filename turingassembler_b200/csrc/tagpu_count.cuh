@@ -217,11 +217,15 @@ __global__ void k_overflow_scatter(const SkRec<W> *__restrict__ overflow, const 
 
 // ---------------------------------------------------------------- pass 2
 template <int W> struct BucketCfg {
-	static constexpr int THREADS = 1024;
+	static constexpr int THREADS = 1024;                        // one CTA per SM with the biggest table that fits
+	static constexpr int CTAS_PER_SM = 1;
 	static constexpr int LOG2_SLOTS = W == 1 ? 14 : 13;
 	static constexpr int SLOTS = 1 << LOG2_SLOTS;               // shared-memory table slots per CTA (192 KB / 160 KB)
 	static constexpr int MAX_PROBES = 48;                       // a longer probe sequence aborts the attempt (re-run on sub-classes)
-	static constexpr int LIMIT = SLOTS * 7 / 8;                 // ... as does a harvest that finds the table this full
+	static constexpr int GROUP_MAX = 64;                        // buckets per group
+	// a group is closed once it holds this many windows: ~0.3 load if a fifth of the windows are distinct keys (probe
+	// sequences diverge within a warp, so a sparse table is worth more than fewer harvests)
+	static constexpr uint32_t GROUP_TARGET = SLOTS * 3 / 2;
 	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + 2 * THREADS * sizeof(SkRec<W>);
 };
 
@@ -274,15 +278,63 @@ TAGPU_DI SkRec<2> tagpu_record_rc(const SkRec<2> &r, int nb)
 	return o;
 }
 
-// One CTA per bucket (persistent CTAs pull bucket ids from a global counter).  Each warp stages 32 records in
-// shared memory, splits their windows into 32 equal contiguous segments (one per lane) and every lane ROLLS the
-// forward / reverse-complement keys through its segment (re-seeding only at record boundaries), inserting the
-// canonical key into the CTA's shared-memory table.
+// ---------------------------------------------------------------- bucket grouping
+// Bucket sizes are very uneven (a bucket is a handful of minimizer sites; measured CV ~0.9), so pass 2 does not take
+// buckets one by one: consecutive buckets are packed greedily into groups of ~GROUP_TARGET windows (<= GROUP_MAX
+// buckets), and one CTA counts a whole group in one shared-memory table.  Single block; thread t owns a contiguous
+// chunk of buckets.  grp_start[g] = first bucket of group g, grp_start[n_groups] = n_buckets.
+__global__ void __launch_bounds__(1024) k_group_buckets(const unsigned long long *__restrict__ cursor, uint32_t n_buckets,
+							uint32_t target, uint32_t group_max, uint32_t *__restrict__ grp_start,
+							unsigned long long *ctr)
+{
+	__shared__ unsigned long long s_sum[1024];
+	__shared__ uint32_t s_cnt[1024];
+	const uint32_t per = (n_buckets + 1023) / 1024, lo = min(threadIdx.x * per, n_buckets), hi = min(lo + per, n_buckets);
+	unsigned long long sum = 0;
+	for (uint32_t b = lo; b < hi; ++b) sum += cursor[b] >> 32;
+	s_sum[threadIdx.x] = sum;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned long long acc = 0;
+		for (int t = 0; t < 1024; ++t) { unsigned long long v = s_sum[t]; s_sum[t] = acc; acc += v; }
+	}
+	__syncthreads();
+	// A bucket starts a group when the running total crosses a multiple of `target`, or every group_max buckets.
+	// Both rules depend only on global prefix values / indices, so chunks can be processed independently.
+	for (int pass = 0; pass < 2; ++pass) {
+		unsigned long long acc = s_sum[threadIdx.x];                  // windows before bucket b
+		unsigned long long prev = lo ? acc - (cursor[lo - 1] >> 32) : 0;  // ... and before bucket b - 1
+		uint32_t n = 0, out = pass ? s_cnt[threadIdx.x] : 0;
+		for (uint32_t b = lo; b < hi; ++b) {
+			const bool start = b == 0 || acc / target != prev / target || (b % group_max) == 0;
+			if (start) { if (pass) grp_start[out + n] = b; ++n; }
+			prev = acc;
+			acc += cursor[b] >> 32;
+		}
+		if (!pass) {
+			s_cnt[threadIdx.x] = n;
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				uint32_t a = 0;
+				for (int t = 0; t < 1024; ++t) { uint32_t v = s_cnt[t]; s_cnt[t] = a; a += v; }
+				grp_start[a] = n_buckets;
+				ctr[CTR_SPARE1] = 0;          // work counter of k_count_buckets
+				ctr[CTR_GROUPS] = a;
+			}
+			__syncthreads();
+		}
+	}
+}
+
+// Persistent CTAs pull groups of buckets from a global counter.  Each warp stages 32 records in shared memory
+// (forward and reverse-complemented), splits their windows into 32 equal contiguous segments (one per lane) and every
+// lane ROLLS the forward / reverse-complement keys through its segment (re-seeding only at record boundaries),
+// inserting the canonical key into the CTA's shared-memory table.
 template <int W>
-__global__ void __launch_bounds__(BucketCfg<W>::THREADS, 1)
+__global__ void __launch_bounds__(BucketCfg<W>::THREADS, BucketCfg<W>::CTAS_PER_SM)
 k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *__restrict__ cursor, uint32_t cap_records,
-		const SkRec<W> *__restrict__ ext, const uint32_t *__restrict__ ext_off, uint32_t n_buckets, int K, uint32_t ci,
-		Key<W> *__restrict__ solid, uint32_t *__restrict__ solid_cnt, unsigned long long *ctr)
+		const SkRec<W> *__restrict__ ext, const uint32_t *__restrict__ ext_off, const uint32_t *__restrict__ grp_start,
+		int K, uint32_t ci, Key<W> *__restrict__ solid, uint32_t *__restrict__ solid_cnt, unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
 	typedef BucketCfg<W> C;
@@ -290,36 +342,53 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 	Key<W> *t_key = reinterpret_cast<Key<W> *>(smem_raw);
 	uint32_t *t_cnt = reinterpret_cast<uint32_t *>(t_key + C::SLOTS);
 	SkRec<W> *s_rec = reinterpret_cast<SkRec<W> *>(t_cnt + C::SLOTS);
-	__shared__ uint32_t s_bucket, s_claims, s_overflow, s_warp[C::THREADS / 32], s_stack[64], s_sp;
+	__shared__ uint32_t s_group, s_claims, s_overflow, s_warp[C::THREADS / 32], s_stack[64], s_sp;
+	__shared__ uint32_t s_nrec[C::GROUP_MAX], s_bpre[C::GROUP_MAX + 1];   // per bucket of the group: records, batches before it
 	__shared__ unsigned long long s_out_base;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	constexpr uint32_t N_WARPS = C::THREADS / 32;
 	SkRec<W> *my_recs = s_rec + warp * 32;                      // forward records of the warp's current batch
 	SkRec<W> *my_rcs = s_rec + C::THREADS + warp * 32;          // ... and their reverse complements
 	const Key<W> kmask = KO::mask(K);
+	const uint32_t n_groups = (uint32_t)ctr[CTR_GROUPS];
 
 	for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) { t_key[i] = KO::make(0, 0); t_cnt[i] = 0; }
 
 	for (;;) {
 		__syncthreads();
-		if (tid == 0) s_bucket = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);
+		if (tid == 0) s_group = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);
 		__syncthreads();
-		const uint32_t b = s_bucket;
-		if (b >= n_buckets) break;
-		const unsigned long long cur = cursor[b];
-		const uint32_t n_total = (uint32_t)cur, n_inst = (uint32_t)(cur >> 32);
-		if (!n_total) continue;
-		const uint32_t n_main = min(n_total, cap_records);
-		const SkRec<W> *main_rec = regions + (size_t)b * cap_records;
-		const SkRec<W> *ext_rec = n_total > n_main ? ext + ext_off[b] : nullptr;
-		if (tid == 0) {
-			// start on 2^L hash classes if the bucket is obviously too big for one table
-			uint32_t L = 0;
-			while (L < 5 && (n_inst >> L) > 4u * C::SLOTS) ++L;            // at most 32 initial classes; overflow splits further
-			s_sp = 0;
-			for (uint32_t c = 0; c < (1u << L); ++c) s_stack[s_sp++] = (L << 24) | c;
+		const uint32_t grp = s_group;
+		if (grp >= n_groups) break;
+		const uint32_t b0 = grp_start[grp], nb = grp_start[grp + 1] - b0;          // nb <= GROUP_MAX
+		if (warp == 0) {
+			// per-bucket record counts and the exclusive prefix of their 32-record batches (two buckets per lane)
+			uint32_t tot_inst = 0, carry = 0;
+			for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
+				const uint32_t i = i0 + lane;
+				const unsigned long long cur = i < nb ? cursor[b0 + i] : 0ull;
+				const uint32_t nrec = (uint32_t)cur, nbat = (nrec + 31) >> 5;
+				tot_inst += (uint32_t)(cur >> 32);
+				uint32_t incl = nbat;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+					if (lane >= (uint32_t)d) incl += t;
+				}
+				if (i < nb) { s_nrec[i] = nrec; s_bpre[i] = carry + incl - nbat; }
+				carry += __shfl_sync(0xffffffffu, incl, 31);
+			}
+			tot_inst = __reduce_add_sync(0xffffffffu, tot_inst);
+			if (lane == 0) {
+				s_bpre[nb] = carry;
+				uint32_t L = 0;                                          // a single oversized bucket starts on 2^L hash classes
+				while (L < 5 && (tot_inst >> L) > 2u * C::GROUP_TARGET) ++L;
+				s_sp = 0;
+				for (uint32_t c = 0; c < (1u << L); ++c) s_stack[s_sp++] = (L << 24) | c;
+			}
 		}
 		__syncthreads();
+		const uint32_t n_batches = s_bpre[nb];
 		while (*(volatile uint32_t *)&s_sp) {
 			__syncthreads();
 			const uint32_t top = s_stack[s_sp - 1];
@@ -327,24 +396,31 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 			__syncthreads();
 			if (tid == 0) { --s_sp; s_claims = 0; s_overflow = 0; }
 			__syncthreads();
-			// ---- insert every window of the bucket that belongs to hash class (L, cls)
+			// ---- insert every window of the group that belongs to hash class (L, cls); a batch = 32 records of one bucket
+			auto fetch = [&](uint32_t bt, SkRec<W> &out) -> bool {
+				if (bt >= n_batches) return false;
+				uint32_t i = 0;                                          // bucket of batch bt: last i with s_bpre[i] <= bt
+				for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
+					const uint32_t v = i0 + lane < nb ? s_bpre[i0 + lane] : 0xffffffffu;
+					i += __popc(__ballot_sync(0xffffffffu, v <= bt));
+				}
+				i -= 1;
+				const uint32_t g = (bt - s_bpre[i]) * 32 + lane, nrec = s_nrec[i], b = b0 + i;
+				if (g >= nrec) return false;
+				out = g < cap_records ? regions[(size_t)b * cap_records + g] : ext[ext_off[b] + (g - cap_records)];
+				return true;
+			};
 			SkRec<W> pre;                                                // software prefetch of the next batch's record
-			if (warp * 32 + lane < n_total) {
-				const uint32_t g = warp * 32 + lane;
-				pre = g < n_main ? main_rec[g] : ext_rec[g - n_main];
-			}
-			for (uint32_t base = warp * 32; base < n_total; base += N_WARPS * 32) {
+			bool have_pre = fetch(warp, pre);
+			for (uint32_t bt = warp; bt < n_batches; bt += N_WARPS) {
 				if (*(volatile uint32_t *)&s_overflow) break;
 				uint32_t my_n = 0;
-				if (base + lane < n_total) {
+				if (have_pre) {
 					my_n = (uint32_t)(pre.w[2 * W - 1] >> 56);
 					my_recs[lane] = pre;
 					my_rcs[lane] = tagpu_record_rc(pre, (int)my_n + K - 1);
 				}
-				{
-					const uint32_t g = base + N_WARPS * 32 + lane;
-					if (g < n_total) pre = g < n_main ? main_rec[g] : ext_rec[g - n_main];
-				}
+				have_pre = fetch(bt + N_WARPS, pre);
 				uint32_t incl = my_n;
 #pragma unroll
 				for (int d = 1; d < 32; d <<= 1) {
@@ -430,13 +506,13 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 			if (lane == 31) s_warp[warp] = incl;
 			__syncthreads();
 			if (warp == 0) {
-				uint32_t x = s_warp[lane], in2 = x;
+				uint32_t x = lane < N_WARPS ? s_warp[lane] : 0u, in2 = x;
 #pragma unroll
 				for (int d = 1; d < 32; d <<= 1) {
 					uint32_t t = __shfl_up_sync(0xffffffffu, in2, d);
 					if (lane >= (uint32_t)d) in2 += t;
 				}
-				s_warp[lane] = in2 - x;
+				if (lane < N_WARPS) s_warp[lane] = in2 - x;
 				if (lane == 31) {
 					s_out_base = in2 ? atomicAdd(ctr + CTR_SOLID, (unsigned long long)in2) : 0ull;
 					if (!failed) atomicAdd(ctr + CTR_DISTINCT, (unsigned long long)s_claims);

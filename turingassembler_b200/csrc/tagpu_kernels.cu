@@ -32,7 +32,7 @@ struct tagpu_ctx {
 	unsigned long long *d_ctr = nullptr, *h_ctr = nullptr;
 	Buf regions, cursor, overflow, overflow_bucket, ext, ext_off, ext_count;
 	int n_sm = 0, jump_grid = 0;
-	Buf chain_slot;
+	Buf chain_slot, grp_start;
 	Buf seq, ctab, clist, solid_key, solid_cnt, kt_keys, kt_mask, node_ord, node_slot, node_ebase, vL, vR, jump, vsucc,
 		vedge, e_src, e_dst, e_rc, e_len, e_count, e_off, e_seq;
 	uint64_t ctab_slots = 0;
@@ -170,7 +170,7 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->chain_slot, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
 			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
 	for (Buf *b : bufs)
@@ -259,13 +259,14 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 {
 	typedef BucketCfg<W> BC;
 	const int K = ctx->K;
-	// bucket count: aim at a mean load of ~0.2 per table (bucket sizes are skewed: CV ~0.9), guessing distinct ~ stream bytes / 8
-	uint64_t want = n / 8 / (BC::SLOTS / 5) + 1;
+	// bucket count: buckets are packed into groups of ~GROUP_TARGET windows by k_group_buckets; fine buckets keep the
+	// packing tight although bucket sizes are skewed (CV ~0.9).  Guess: windows ~ stream bytes, a fifth of them distinct.
+	uint64_t want = n / 8 / (BC::GROUP_TARGET / 5 / 4) + 1;   // mean bucket ~ a quarter of a group
 	int log2p = 10;
 	while ((1ull << log2p) < want && log2p < 22) ++log2p;
 	const uint32_t n_buckets = 1u << log2p;
 	// region capacity: ~4x the expected records per bucket (one record per ~8 windows), at least 64
-	uint64_t cap = n / 8 / n_buckets * 4 + 64;
+	uint64_t cap = n / 8 / n_buckets * 6 + 64;          // measured: max bucket ~6x the mean; the rest spills to the overflow area
 	PartCfg cfg;
 	cfg.K = K;
 	cfg.log2_buckets = log2p;
@@ -301,9 +302,12 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 	}
 	const uint64_t solid_cap = n_inst / (uint64_t)ctx->ci + 1; // every solid key owns >= ci instances
 	if (ensure(ctx, ctx->solid_key, solid_cap * sizeof(Key<W>)) || ensure(ctx, ctx->solid_cnt, solid_cap * 4)) return -1;
-	LAUNCH_SMEM(k_count_buckets<W>, ctx->n_sm, BC::THREADS, BC::SMEM, (const SkRec<W> *)ctx->regions.p,
+	if (ensure(ctx, ctx->grp_start, ((size_t)n_buckets + 2) * 4)) return -1;
+	LAUNCH(k_group_buckets, 1, 1024, (const unsigned long long *)ctx->cursor.p, n_buckets, (uint32_t)BC::GROUP_TARGET,
+	       (uint32_t)BC::GROUP_MAX, (uint32_t *)ctx->grp_start.p, ctx->d_ctr);
+	LAUNCH_SMEM(k_count_buckets<W>, BC::CTAS_PER_SM * ctx->n_sm, BC::THREADS, BC::SMEM, (const SkRec<W> *)ctx->regions.p,
 		    (const unsigned long long *)ctx->cursor.p, cfg.cap_records, (const SkRec<W> *)ctx->ext.p, (const uint32_t *)ctx->ext_off.p,
-		    n_buckets, K, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p, ctx->d_ctr);
+		    (const uint32_t *)ctx->grp_start.p, K, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p, ctx->d_ctr);
 	if (read_counters(ctx)) return -1;
 	ctx->st.n_instances = n_inst;
 	ctx->st.n_distinct = ctx->h_ctr[CTR_DISTINCT];
