@@ -221,16 +221,42 @@ def main():
     wl = WORKLOADS[args.workload]
     k = wl["k"]
 
-    # "replicas" until the hash-partitioned exchange lands: every rank processes the full read set
-    d_stream = gen_reads_gpu(torch, wl["genome_len"], wl["n_pairs"], wl["seed"], dev)
+    # Strong scaling (north_star): the SAME read set is split over the ranks.  Every rank generates the identical seeded
+    # stream and keeps its contiguous 1/world slice of the reads (R1 block and R2 block are both cut at read boundaries).
+    d_full = gen_reads_gpu(torch, wl["genome_len"], wl["n_pairs"], wl["seed"], dev)
+    n_total = d_full.numel()
+    if world > 1:
+        from turingassembler_b200.dist import DistTagpu, shard_reads
+        first, last = shard_reads(n_total // (L + 1), rank, world)
+        d_stream = d_full[first * (L + 1): last * (L + 1)].clone()
+    else:
+        d_stream = d_full
+    del d_full
     n_stream = d_stream.numel()
     h_stream = torch.empty(n_stream, dtype=torch.uint8, pin_memory=True)
     h_stream.copy_(d_stream)
+    d_e2e = torch.empty_like(d_stream) if world > 1 else None
     torch.cuda.synchronize()
 
     t = Tagpu(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)      # one explicit stream for the library's kernels, the copies and the timing events
+    torch.cuda.set_stream(stream)
     t.set_stream(stream.cuda_stream)
+    if world > 1:
+        dt = DistTagpu(t, rank, world)
+        dt.plan(n_total, k)
+
+    def step_device():
+        if world > 1:
+            return dt.build(d_stream.data_ptr(), n_stream)
+        return t.build_device(d_stream.data_ptr(), n_stream, k)
+
+    def step_host():
+        # end to end: this rank's reads start in pinned HOST memory; H2D copy, build, stats back to the host
+        if world > 1:
+            d_e2e.copy_(h_stream, non_blocking=True)
+            return dt.build(d_e2e.data_ptr(), n_stream)
+        return t.build_host((h_stream.data_ptr(), n_stream), k)
 
     def barrier():
         if world > 1:
@@ -238,7 +264,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        st = t.build_device(d_stream.data_ptr(), n_stream, k)
+        st = step_device()
     t.set_profile(True)   # one CUDA-event pair around every kernel launch, on the launching stream
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -249,7 +275,7 @@ def main():
     kern = {}
     ev0.record(stream)
     for _ in range(args.steps):
-        st = t.build_device(d_stream.data_ptr(), n_stream, k)
+        st = step_device()
         ms_count += st["ms_count"]
         ms_graph += st["ms_graph"]
         launches += st["gpu_launches"]
@@ -261,19 +287,22 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     t.set_profile(False)
-    # e2e: pinned host stream -> C-ABI host call (H2D inside) -> stats back
-    t.build_host((h_stream.data_ptr(), n_stream), k)
+    step_host()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        st_e = t.build_host((h_stream.data_ptr(), n_stream), k)
+        st_e = step_host()
     e1.record(stream)
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     sampler.stop_flag = True
     sampler.join()
 
+    if world > 1:
+        ln = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(ln)
+        launches = int(ln.item())
     tm = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -283,14 +312,15 @@ def main():
     n_inst = st["n_instances"]
     ms_step = ms / args.steps
     value = n_inst / (ms_step * 1e-3)
-    b_count, b_graph = algorithmic_bytes(st, k, n_stream)
+    b_count, b_graph = algorithmic_bytes(st, k, n_total)
     peak, peak_src = peaks()
     count_ms = ms_count / args.steps
     # dominant kernel = the one with the largest share of the step; its algorithmic bytes:
     #   k_count_buckets: N_i (W + 8) + N_distinct (W + 4)   (key compare + count read/write, first touch per distinct key)
     #   k_partition:     N_i B_in                            (the ASCII stream is read exactly once)
     W = 8 if k + 1 <= 32 else 16
-    kbytes = {"k_count_buckets<W>": st["n_instances"] * (W + 8) + st["n_distinct"] * (W + 4), "k_partition<W>": float(n_stream)}
+    # (per launch = per rank: 1/world of the instances, distinct keys and stream bytes)
+    kbytes = {"k_count_buckets<W>": (st["n_instances"] * (W + 8) + st["n_distinct"] * (W + 4)) / world, "k_partition<W>": float(n_total) / world}
     kernels = {name: {"ms_per_launch": v[0] / max(v[1], 1), "launches_per_step": v[1] / args.steps,
                       "share_of_step": v[0] / args.steps / ms_step} for name, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
     top = next(iter(kernels))
@@ -302,9 +332,12 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u128" if k + 1 > 32 else "u64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['genome_len']} bp genome, {wl['n_pairs']} pairs x {L} bp, k0={k} "
-                               f"(K={k + 1}), cutoff 2; {n_stream} stream bytes resident in HBM (> L2, no flush needed)",
+                               f"(K={k + 1}), cutoff 2; {n_total} stream bytes resident in HBM (> L2, no flush needed)",
                    "n_instances": n_inst, "n_distinct": st["n_distinct"], "n_solid": st["n_solid"], "n_kmers": st["n_kmers"],
-                   "n_v": st["n_v"], "n_e": st["n_e"], "parallelism": f"replicas x{world}" if world > 1 else "1 gpu"},
+                   "n_v": st["n_v"], "n_e": st["n_e"],
+                   "parallelism": (f"{world} ranks: reads split 1/{world} per rank, (k+1)-mer buckets hash-partitioned to owner GPUs "
+                                   f"(k_count_buckets reads every rank's records through NVLink peer loads), solid sets gathered over NVLink, graph stage "
+                                   f"replicated") if world > 1 else "1 gpu"},
         "stage_ms": {"count": count_ms, "graph": ms_graph / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": TRAFFIC.get(top), "kernel": top, "ms_per_launch": top_ms,
@@ -314,12 +347,12 @@ def main():
                      "whole_path": {"achieved": (b_count + b_graph) / (ms_step * 1e-3) / 1e9,
                                     "frac": (b_count + b_graph) / (ms_step * 1e-3) / 1e9 / peak}},
         "e2e": {"value": st_e["n_instances"] / (ms_e2e / args.steps * 1e-3), "unit": "kmers/s",
-                "h2d_bytes_per_step": n_stream, "d2h_bytes_per_step": 8 * 140, "ms_per_step": ms_e2e / args.steps},
+                "h2d_bytes_per_step": n_total, "d2h_bytes_per_step": 8 * 140 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "kernels": kernels,
         "clocks": sampler.summary(),
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(h_stream.numpy(), k)
     print(json.dumps(line))
 

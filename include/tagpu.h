@@ -108,6 +108,33 @@ int tagpu_fill_asm_graph(tagpu_ctx *ctx, struct asm_graph_t *g);   /* individual
 int tagpu_write_graph_bin(tagpu_ctx *ctx, const char *path);       /* save_asm_graph layout, assembly_graph.c:1173-1248 */
 int tagpu_write_kmc_db(tagpu_ctx *ctx, const char *working_dir);   /* KMC_<K>_count.kmc_pre/.kmc_suf of the last count */
 
+/* ------------------------------------------------------------------ multi-GPU: one process per GPU
+ * The (k+1)-mer space is hash-partitioned: every rank owns a contiguous range of minimizer buckets.  The reference has no
+ * counterpart (single process, pthreads only); this is the north-star extension "each k-mer is hash-partitioned to an
+ * owner GPU".  The host program (MPI, torch.distributed, ...) supplies rendezvous and barriers; per build the order is
+ *
+ *   once:   tagpu_dist_plan -> exchange the 64-byte handles of all ranks -> tagpu_dist_connect -> BARRIER
+ *   step:   tagpu_dist_partition  -> BARRIER ->      (pass 1 over this rank's slice of the reads, into its OWN bucket regions)
+ *           tagpu_dist_count      -> ALL-GATHER of the 4 stats values (doubles as the barrier) ->
+ *                                                    (pass 2 over the buckets this rank owns; the counting kernel reads the
+ *                                                     records of every rank through NVLink peer loads, overlapped with counting)
+ *           tagpu_dist_graph                         (pulls all solid sets over NVLink, builds the graph on every rank)
+ *
+ * All ranks must pass the same n_total_bytes (size of the WHOLE read stream), k and cutoff.  After tagpu_dist_graph the
+ * stats / copy / write calls above describe the global result on every rank. */
+#define TAGPU_IPC_HANDLE_BYTES 64
+int tagpu_dist_plan(tagpu_ctx *ctx, int rank, int world, uint64_t n_total_bytes, int k, void *handle_out);
+int tagpu_dist_connect(tagpu_ctx *ctx, const void *all_handles /* world x TAGPU_IPC_HANDLE_BYTES, rank order */);
+int tagpu_dist_partition(tagpu_ctx *ctx, const uint8_t *d_seq_local, uint64_t n_local_bytes);
+int tagpu_dist_count(tagpu_ctx *ctx, uint64_t stats_out[4]);
+int tagpu_dist_graph(tagpu_ctx *ctx, const uint64_t *all_stats /* world x 4, rank order */, int with_graph);
+/* Teardown / re-plan: every rank calls tagpu_dist_disconnect (unmaps the peers' arenas) -> BARRIER -> tagpu_dist_close or a
+ * new tagpu_dist_plan (frees its own arena, which nobody maps any more). */
+void tagpu_dist_disconnect(tagpu_ctx *ctx);
+void tagpu_dist_close(tagpu_ctx *ctx);
+/* [begin, end) of rank's share of a host read stream, cut at read boundaries ('\n') so no window is lost or doubled */
+void tagpu_dist_shard_range(const uint8_t *h_seq, uint64_t n_bytes, int rank, int world, uint64_t *begin, uint64_t *end);
+
 /* FASTQ/FASTA(.gz) files -> pinned host stream of sequence lines joined by '\n' (free with tagpu_free_reads) */
 int64_t tagpu_load_reads(int n_files, char **files, int n_threads, uint8_t **stream);
 void tagpu_free_reads(uint8_t *stream);

@@ -14,6 +14,7 @@ from typing import Sequence
 
 import numpy as np
 
+IPC_HANDLE_BYTES = 64  # TAGPU_IPC_HANDLE_BYTES
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtagpu.so")
 
 
@@ -153,6 +154,20 @@ def load_library() -> C.CDLL:
     lib.tagpu_load_reads.restype = C.c_int64
     lib.tagpu_load_reads.argtypes = [i32, C.POINTER(C.c_char_p), i32, C.POINTER(vp)]
     lib.tagpu_free_reads.argtypes = [vp]
+    lib.tagpu_dist_plan.restype = i32
+    lib.tagpu_dist_plan.argtypes = [vp, i32, i32, u64, i32, vp]
+    lib.tagpu_dist_connect.restype = i32
+    lib.tagpu_dist_connect.argtypes = [vp, vp]
+    lib.tagpu_dist_partition.restype = i32
+    lib.tagpu_dist_partition.argtypes = [vp, vp, u64]
+    lib.tagpu_dist_count.restype = i32
+    lib.tagpu_dist_count.argtypes = [vp, C.POINTER(u64)]
+    lib.tagpu_dist_graph.restype = i32
+    lib.tagpu_dist_graph.argtypes = [vp, C.POINTER(u64), i32]
+    lib.tagpu_dist_close.argtypes = [vp]
+    lib.tagpu_dist_disconnect.argtypes = [vp]
+    lib.tagpu_dist_shard_range.restype = None
+    lib.tagpu_dist_shard_range.argtypes = [vp, u64, i32, i32, C.POINTER(u64), C.POINTER(u64)]
     lib.KMC_build_kmer_database.restype = i32
     lib.KMC_build_kmer_database.argtypes = [i32, C.c_char_p, i32, i32, i32, C.POINTER(C.c_char_p)]
     for name in ("build_graph_from_scratch", "build_graph_from_scratch_without_count"):
@@ -233,6 +248,35 @@ class Tagpu:
         del keep
         return self.stats()
 
+    # ---- multi-GPU phases (include/tagpu.h "multi-GPU"; orchestration in turingassembler_b200/dist.py) ----
+    def dist_plan(self, rank: int, world: int, n_total_bytes: int, k: int) -> bytes:
+        h = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self.lib.tagpu_dist_plan(self.ctx, rank, world, n_total_bytes, k, h))
+        return h.raw
+
+    def dist_connect(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        self._check(self.lib.tagpu_dist_connect(self.ctx, C.c_char_p(blob)))
+
+    def dist_partition(self, d_ptr: int, n_local_bytes: int):
+        self._check(self.lib.tagpu_dist_partition(self.ctx, C.c_void_p(d_ptr), n_local_bytes))
+
+    def dist_count(self):
+        out = (C.c_uint64 * 4)()
+        self._check(self.lib.tagpu_dist_count(self.ctx, out))
+        return list(out)
+
+    def dist_graph(self, all_stats: Sequence[int], with_graph: bool = True):
+        arr = (C.c_uint64 * len(all_stats))(*all_stats)
+        self._check(self.lib.tagpu_dist_graph(self.ctx, arr, int(with_graph)))
+        return self.stats()
+
+    def dist_disconnect(self):
+        self.lib.tagpu_dist_disconnect(self.ctx)
+
+    def dist_close(self):
+        self.lib.tagpu_dist_close(self.ctx)
+
     def stats(self) -> dict:
         st = Stats()
         self.lib.tagpu_get_stats(self.ctx, C.byref(st))
@@ -299,6 +343,15 @@ def load_reads(files: Sequence[str], n_threads: int = 4):
     out = C.c_void_p()
     n = lib.tagpu_load_reads(len(files), _char_pp(files), n_threads, C.byref(out))
     return out.value, n
+
+
+def shard_range(stream: np.ndarray, rank: int, world: int):
+    """[begin, end) of `rank`'s share of a host read stream, cut at read boundaries (tagpu_dist_shard_range)."""
+    lib = load_library()
+    a = np.ascontiguousarray(stream.view(np.uint8))
+    b, e = C.c_uint64(), C.c_uint64()
+    lib.tagpu_dist_shard_range(C.c_void_p(a.ctypes.data), a.size, rank, world, C.byref(b), C.byref(e))
+    return b.value, e.value
 
 
 def free_reads(addr: int):

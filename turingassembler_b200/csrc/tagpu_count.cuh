@@ -31,11 +31,27 @@ template <> struct __align__(16) SkRec<1> { unsigned long long w[2]; };   // <= 
 template <> struct __align__(32) SkRec<2> { unsigned long long w[4]; };   // <= 124 bases
 template <int W> struct SkCap { static constexpr int bases = W == 1 ? 60 : 124; };
 
+constexpr int TAGPU_MAX_RANKS = 8;
+
 struct PartCfg {
 	int K;
 	int log2_buckets;
 	uint32_t cap_records;         // records per bucket region
-	uint32_t overflow_cap;        // records in the shared overflow area
+	uint32_t overflow_cap;        // records in the overflow area
+	uint32_t world;               // GPUs sharing the key space (1 = single GPU)
+	uint32_t per_rank;            // buckets owned by each rank: owner(b) = b / per_rank
+};
+
+// Where pass 2 finds the records of a bucket: every rank ("source") partitions ITS slice of the reads into its own
+// regions, for all buckets; the rank that owns a bucket then reads that bucket's records from every source.  With
+// world > 1 the entries of the other ranks are CUDA-IPC mappings of THEIR allocations, so those reads are NVLink peer
+// loads issued by the counting kernel itself: the hash-partitioned exchange of SURVEY.md §8e is fused into pass 2 and
+// overlaps its shared-memory counting (records are prefetched one batch ahead).
+template <int W> struct CountPeers {
+	const SkRec<W> *regions[TAGPU_MAX_RANKS];          // [n_buckets x cap_records]
+	const unsigned long long *cursor[TAGPU_MAX_RANKS]; // [n_buckets] low word records, high word windows
+	const SkRec<W> *ext[TAGPU_MAX_RANKS];              // overflow records sorted by bucket
+	const uint32_t *ext_off[TAGPU_MAX_RANKS];          // [n_buckets + 1] (valid when the source overflowed)
 };
 
 TAGPU_DI uint32_t tagpu_bucket_of(uint32_t minhash, int log2_buckets)
@@ -223,6 +239,7 @@ template <int W> struct BucketCfg {
 	static constexpr int SLOTS = 1 << LOG2_SLOTS;               // shared-memory table slots per CTA (192 KB / 160 KB)
 	static constexpr int MAX_PROBES = 48;                       // a longer probe sequence aborts the attempt (re-run on sub-classes)
 	static constexpr int GROUP_MAX = 64;                        // buckets per group
+	static constexpr int SUB_MAX = 256;                         // (bucket, source rank) pairs per group: group_max = min(GROUP_MAX, SUB_MAX / world)
 	// a group is closed once it holds this many windows: ~0.3 load if a fifth of the windows are distinct keys (probe
 	// sequences diverge within a warp, so a sparse table is worth more than fewer harvests)
 	static constexpr uint32_t GROUP_TARGET = SLOTS * 3 / 2;
@@ -278,20 +295,46 @@ TAGPU_DI SkRec<2> tagpu_record_rc(const SkRec<2> &r, int nb)
 	return o;
 }
 
+// ---------------------------------------------------------------- cursors of the owned buckets, from every source
+// One coalesced sweep (remote for the other ranks) instead of per-group remote reads inside the counting kernel.
+// cur_all[lb * world + s] = cursor of owned bucket lb at source s; ext_all[...] = where its overflow records start.
+template <int W>
+__global__ void __launch_bounds__(256) k_pull_cursors(const __grid_constant__ CountPeers<W> peers, uint32_t world, uint32_t first_bucket,
+							      uint32_t n_owned, uint32_t n_buckets, uint32_t cap_records,
+							      unsigned long long *__restrict__ cur_all, uint32_t *__restrict__ ext_all)
+{
+	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= (uint64_t)n_owned * world) return;
+	const uint32_t s = (uint32_t)(idx / n_owned), lb = (uint32_t)(idx - (uint64_t)s * n_owned), gb = first_bucket + lb;
+	unsigned long long cur = 0;
+	uint32_t eo = 0;
+	if (gb < n_buckets) {
+		cur = peers.cursor[s][gb];
+		if ((uint32_t)cur > cap_records) eo = peers.ext_off[s][gb];
+	}
+	cur_all[(size_t)lb * world + s] = cur;
+	ext_all[(size_t)lb * world + s] = eo;
+}
+
 // ---------------------------------------------------------------- bucket grouping
 // Bucket sizes are very uneven (a bucket is a handful of minimizer sites; measured CV ~0.9), so pass 2 does not take
 // buckets one by one: consecutive buckets are packed greedily into groups of ~GROUP_TARGET windows (<= GROUP_MAX
 // buckets), and one CTA counts a whole group in one shared-memory table.  Single block; thread t owns a contiguous
 // chunk of buckets.  grp_start[g] = first bucket of group g, grp_start[n_groups] = n_buckets.
-__global__ void __launch_bounds__(1024) k_group_buckets(const unsigned long long *__restrict__ cursor, uint32_t n_buckets,
+__global__ void __launch_bounds__(1024) k_group_buckets(const unsigned long long *__restrict__ cur_all, uint32_t world, uint32_t n_buckets,
 							uint32_t target, uint32_t group_max, uint32_t *__restrict__ grp_start,
 							unsigned long long *ctr)
 {
 	__shared__ unsigned long long s_sum[1024];
 	__shared__ uint32_t s_cnt[1024];
 	const uint32_t per = (n_buckets + 1023) / 1024, lo = min(threadIdx.x * per, n_buckets), hi = min(lo + per, n_buckets);
+	auto windows = [&](uint32_t b) {                              // windows of bucket b over all sources
+		unsigned long long w = 0;
+		for (uint32_t s = 0; s < world; ++s) w += cur_all[(size_t)b * world + s] >> 32;
+		return w;
+	};
 	unsigned long long sum = 0;
-	for (uint32_t b = lo; b < hi; ++b) sum += cursor[b] >> 32;
+	for (uint32_t b = lo; b < hi; ++b) sum += windows(b);
 	s_sum[threadIdx.x] = sum;
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -303,13 +346,13 @@ __global__ void __launch_bounds__(1024) k_group_buckets(const unsigned long long
 	// Both rules depend only on global prefix values / indices, so chunks can be processed independently.
 	for (int pass = 0; pass < 2; ++pass) {
 		unsigned long long acc = s_sum[threadIdx.x];                  // windows before bucket b
-		unsigned long long prev = lo ? acc - (cursor[lo - 1] >> 32) : 0;  // ... and before bucket b - 1
+		unsigned long long prev = lo ? acc - windows(lo - 1) : 0;     // ... and before bucket b - 1
 		uint32_t n = 0, out = pass ? s_cnt[threadIdx.x] : 0;
 		for (uint32_t b = lo; b < hi; ++b) {
 			const bool start = b == 0 || acc / target != prev / target || (b % group_max) == 0;
 			if (start) { if (pass) grp_start[out + n] = b; ++n; }
 			prev = acc;
-			acc += cursor[b] >> 32;
+			acc += windows(b);
 		}
 		if (!pass) {
 			s_cnt[threadIdx.x] = n;
@@ -332,9 +375,10 @@ __global__ void __launch_bounds__(1024) k_group_buckets(const unsigned long long
 // inserting the canonical key into the CTA's shared-memory table.
 template <int W>
 __global__ void __launch_bounds__(BucketCfg<W>::THREADS, BucketCfg<W>::CTAS_PER_SM)
-k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *__restrict__ cursor, uint32_t cap_records,
-		const SkRec<W> *__restrict__ ext, const uint32_t *__restrict__ ext_off, const uint32_t *__restrict__ grp_start,
-		int K, uint32_t ci, Key<W> *__restrict__ solid, uint32_t *__restrict__ solid_cnt, unsigned long long *ctr)
+k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uint32_t first_bucket, uint32_t cap_records,
+		const unsigned long long *__restrict__ cur_all, const uint32_t *__restrict__ ext_all, const uint32_t *__restrict__ grp_start,
+		int K, uint32_t ci, Key<W> *__restrict__ solid, uint32_t *__restrict__ solid_cnt, unsigned long long solid_cap,
+		unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
 	typedef BucketCfg<W> C;
@@ -343,7 +387,7 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 	uint32_t *t_cnt = reinterpret_cast<uint32_t *>(t_key + C::SLOTS);
 	SkRec<W> *s_rec = reinterpret_cast<SkRec<W> *>(t_cnt + C::SLOTS);
 	__shared__ uint32_t s_group, s_claims, s_overflow, s_warp[C::THREADS / 32], s_stack[64], s_sp;
-	__shared__ uint32_t s_nrec[C::GROUP_MAX], s_bpre[C::GROUP_MAX + 1];   // per bucket of the group: records, batches before it
+	__shared__ uint32_t s_nrec[C::SUB_MAX], s_bpre[C::SUB_MAX + 1];   // per (bucket, source) of the group: records, batches before it
 	__shared__ unsigned long long s_out_base;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	constexpr uint32_t N_WARPS = C::THREADS / 32;
@@ -360,13 +404,13 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 		__syncthreads();
 		const uint32_t grp = s_group;
 		if (grp >= n_groups) break;
-		const uint32_t b0 = grp_start[grp], nb = grp_start[grp + 1] - b0;          // nb <= GROUP_MAX
+		const uint32_t b0 = grp_start[grp], nb = (grp_start[grp + 1] - b0) * world;  // nb (bucket, source) pairs <= SUB_MAX
 		if (warp == 0) {
-			// per-bucket record counts and the exclusive prefix of their 32-record batches (two buckets per lane)
+			// per-pair record counts and the exclusive prefix of their 32-record batches
 			uint32_t tot_inst = 0, carry = 0;
 			for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
 				const uint32_t i = i0 + lane;
-				const unsigned long long cur = i < nb ? cursor[b0 + i] : 0ull;
+				const unsigned long long cur = i < nb ? cur_all[(size_t)b0 * world + i] : 0ull;
 				const uint32_t nrec = (uint32_t)cur, nbat = (nrec + 31) >> 5;
 				tot_inst += (uint32_t)(cur >> 32);
 				uint32_t incl = nbat;
@@ -399,15 +443,18 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 			// ---- insert every window of the group that belongs to hash class (L, cls); a batch = 32 records of one bucket
 			auto fetch = [&](uint32_t bt, SkRec<W> &out) -> bool {
 				if (bt >= n_batches) return false;
-				uint32_t i = 0;                                          // bucket of batch bt: last i with s_bpre[i] <= bt
+				uint32_t i = 0;                                          // pair of batch bt: last i with s_bpre[i] <= bt
 				for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
 					const uint32_t v = i0 + lane < nb ? s_bpre[i0 + lane] : 0xffffffffu;
 					i += __popc(__ballot_sync(0xffffffffu, v <= bt));
 				}
 				i -= 1;
-				const uint32_t g = (bt - s_bpre[i]) * 32 + lane, nrec = s_nrec[i], b = b0 + i;
+				const uint32_t g = (bt - s_bpre[i]) * 32 + lane, nrec = s_nrec[i];
 				if (g >= nrec) return false;
-				out = g < cap_records ? regions[(size_t)b * cap_records + g] : ext[ext_off[b] + (g - cap_records)];
+				const uint32_t lb = b0 + i / world, src = i - (i / world) * world;
+				const size_t gb = (size_t)first_bucket + lb;                // the source indexes its regions by global bucket id
+				out = g < cap_records ? peers.regions[src][gb * cap_records + g]
+						      : peers.ext[src][ext_all[(size_t)lb * world + src] + (g - cap_records)];
 				return true;
 			};
 			SkRec<W> pre;                                                // software prefetch of the next batch's record
@@ -525,8 +572,10 @@ k_count_buckets(const SkRec<W> *__restrict__ regions, const unsigned long long *
 				const uint32_t c = t_cnt[i];
 				if (c) {
 					if (!failed && c >= ci) {
-						solid[o] = KO::bnot(t_key[i]);
-						solid_cnt[o] = c;
+						if (o < solid_cap) {                         // the host reports the overflow (n_solid > solid_cap)
+							solid[o] = KO::bnot(t_key[i]);
+							solid_cnt[o] = c;
+						}
 						sum += c;
 						++o;
 					}

@@ -194,6 +194,24 @@ int64_t tagpu_load_reads(int n_files, char **files, int n_threads, uint8_t **str
 
 void tagpu_free_reads(uint8_t *stream) { tagpu_pinned_free(stream); }
 
+/* Rank's share of a read stream: nominal byte split, each cut moved forward to just after the next newline, so every
+ * read belongs to exactly one rank (windows never span reads: App. A.1). */
+static uint64_t shard_cut(const uint8_t *s, uint64_t n, uint64_t pos)
+{
+	if (pos == 0 || pos >= n)
+		return pos > n ? n : pos;
+	if (s[pos - 1] == '\n')
+		return pos;
+	const uint8_t *nl = memchr(s + pos, '\n', n - pos);
+	return nl ? (uint64_t)(nl - s) + 1 : n;
+}
+
+void tagpu_dist_shard_range(const uint8_t *h_seq, uint64_t n_bytes, int rank, int world, uint64_t *begin, uint64_t *end)
+{
+	*begin = shard_cut(h_seq, n_bytes, n_bytes / world * rank);
+	*end = rank + 1 == world ? n_bytes : shard_cut(h_seq, n_bytes, n_bytes / world * (rank + 1));
+}
+
 /* ------------------------------------------------------------------ flat graph on the host */
 
 static int fetch_graph(tagpu_ctx *ctx, struct tagpu_flat_graph *h, struct tagpu_stats *st)

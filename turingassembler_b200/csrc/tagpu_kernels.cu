@@ -23,6 +23,7 @@ struct Buf {
 	size_t cap = 0;
 };
 
+struct DistState;
 struct tagpu_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr, own_stream = nullptr;
@@ -30,7 +31,7 @@ struct tagpu_ctx {
 	int k = 0, K = 0, W = 0;
 	char err[512] = { 0 };
 	unsigned long long *d_ctr = nullptr, *h_ctr = nullptr;
-	Buf regions, cursor, overflow, overflow_bucket, ext, ext_off, ext_count;
+	Buf regions, cursor, overflow, overflow_bucket, ext, ext_off, ext_count, cur_all, ext_all;
 	int n_sm = 0, jump_grid = 0;
 	Buf chain_slot, grp_start;
 	Buf seq, ctab, clist, solid_key, solid_cnt, kt_keys, kt_mask, node_ord, node_slot, node_ebase, vL, vR, jump, vsucc,
@@ -39,6 +40,8 @@ struct tagpu_ctx {
 	int ctab_W = 0;
 	uint32_t kt_slots = 0;
 	bool have_count = false, have_graph = false;
+	void *cur_solid_key = nullptr, *cur_solid_cnt = nullptr; // solid set the graph stage reads (local, or gathered from all ranks)
+	struct DistState *dist = nullptr;
 	tagpu_stats st;
 	cudaEvent_t ev[4];
 	uint64_t launches = 0;
@@ -165,12 +168,15 @@ extern "C" tagpu_ctx *tagpu_create(int device)
 	return ctx;
 }
 
+static void dist_release(tagpu_ctx *ctx);
+
 extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+	dist_release(ctx);
+	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
 			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
 	for (Buf *b : bufs)
@@ -240,6 +246,8 @@ static int count_stage(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n)
 	ctx->st.n_distinct = n_distinct;
 	ctx->st.n_solid = ctx->h_ctr[CTR_SOLID];
 	ctx->st.sum_solid = ctx->h_ctr[CTR_SUM_SOLID];
+	ctx->cur_solid_key = ctx->solid_key.p;
+	ctx->cur_solid_cnt = ctx->solid_cnt.p;
 	ctx->have_count = true;
 	return 0;
 }
@@ -254,30 +262,34 @@ static int count_stage(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n)
 		CU(cudaGetLastError());                                                    \
 	} while (0)
 
-template <int W>
-static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n)
+// Sizing of the bucket space for a read stream of n_total bytes shared by `world` ranks.  Every rank computes the same
+// plan, so bucket -> owner and all region geometry agree without communication.
+static PartCfg plan_cfg(uint64_t n_total, int K, int world, uint32_t group_target)
 {
-	typedef BucketCfg<W> BC;
-	const int K = ctx->K;
 	// bucket count: buckets are packed into groups of ~GROUP_TARGET windows by k_group_buckets; fine buckets keep the
 	// packing tight although bucket sizes are skewed (CV ~0.9).  Guess: windows ~ stream bytes, a fifth of them distinct.
-	uint64_t want = n / 8 / (BC::GROUP_TARGET / 5 / 4) + 1;   // mean bucket ~ a quarter of a group
+	uint64_t want = n_total / 8 / (group_target / 5 / 4) + 1;   // mean bucket ~ a quarter of a group
 	int log2p = 10;
 	while ((1ull << log2p) < want && log2p < 22) ++log2p;
-	const uint32_t n_buckets = 1u << log2p;
-	// region capacity: ~4x the expected records per bucket (one record per ~8 windows), at least 64
-	uint64_t cap = n / 8 / n_buckets * 6 + 64;          // measured: max bucket ~6x the mean; the rest spills to the overflow area
+	const uint64_t n_buckets = 1ull << log2p;
+	const uint64_t n_source = n_total / world + 1;              // bytes each rank partitions
 	PartCfg cfg;
 	cfg.K = K;
 	cfg.log2_buckets = log2p;
-	cfg.cap_records = (uint32_t)cap;
-	cfg.overflow_cap = (uint32_t)(n / 16 + 4096);
-	if (ensure(ctx, ctx->regions, (size_t)n_buckets * cap * sizeof(SkRec<W>)) || ensure(ctx, ctx->cursor, (size_t)n_buckets * 8) ||
-	    ensure(ctx, ctx->overflow, (size_t)cfg.overflow_cap * sizeof(SkRec<W>)) ||
-	    ensure(ctx, ctx->overflow_bucket, (size_t)cfg.overflow_cap * 4) || ensure(ctx, ctx->ext_off, (size_t)(n_buckets + 1) * 4) ||
-	    ensure(ctx, ctx->ext_count, (size_t)n_buckets * 4))
-		return -1;
-	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)n_buckets * 8, ctx->stream)); }
+	// region capacity at each source: measured max bucket ~6x the mean (one record per ~8 windows); the rest spills
+	cfg.cap_records = (uint32_t)(n_source / 8 / n_buckets * 6 + 64);
+	cfg.world = (uint32_t)world;
+	cfg.per_rank = (uint32_t)((n_buckets + world - 1) / world);
+	cfg.overflow_cap = (uint32_t)(n_source / 16 + 4096);
+	return cfg;
+}
+
+// Pass 1 over this rank's reads + the bucket sort of the records that overflowed their region.  Purely local.
+template <int W>
+static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, const PartCfg &cfg)
+{
+	typedef BucketCfg<W> BC;
+	const uint32_t n_buckets = 1u << cfg.log2_buckets;
 	const size_t smem1 = TAGPU_SMEM_WORDS * 8 + (TAGPU_SMEM_WORDS + 2) * 4 + 2 * (size_t)TAGPU_HM_LEN * 4;
 	static bool attr_done[3] = { false, false, false };
 	if (!attr_done[W]) {
@@ -285,14 +297,19 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 		CU(cudaFuncSetAttribute(k_count_buckets<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BC::SMEM));
 		attr_done[W] = true;
 	}
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)n_buckets * 8, ctx->stream)); }
 	const uint64_t n_tiles = (n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES;
 	if (n_tiles)
 		LAUNCH_SMEM(k_partition<W>, (unsigned)n_tiles, TAGPU_TILE_THREADS, smem1, d_seq, n, cfg, (SkRec<W> *)ctx->regions.p,
 			    (unsigned long long *)ctx->cursor.p, (SkRec<W> *)ctx->overflow.p, (uint32_t *)ctx->overflow_bucket.p, ctx->d_ctr);
 	if (read_counters(ctx)) return -1;
-	const uint64_t n_inst = ctx->h_ctr[CTR_INSTANCES], n_over = ctx->h_ctr[CTR_SPARE0];
+	ctx->st.n_instances = ctx->h_ctr[CTR_INSTANCES];
+	const uint64_t n_over = ctx->h_ctr[CTR_SPARE0];
 	if (n_over) {
-		if (ensure(ctx, ctx->ext, n_over * sizeof(SkRec<W>))) return -1;
+		if (n_over * sizeof(SkRec<W>) > ctx->ext.cap) {
+			if (ctx->dist) return fail(ctx, "bucket overflow area too small (%llu records)", (unsigned long long)n_over);
+			if (ensure(ctx, ctx->ext, n_over * sizeof(SkRec<W>))) return -1;
+		}
 		{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->ext_count.p, 0, (size_t)n_buckets * 4, ctx->stream)); }
 		LAUNCH(k_overflow_hist, (unsigned)((n_over + 255) / 256), 256, (const uint32_t *)ctx->overflow_bucket.p, n_over, (uint32_t *)ctx->ext_count.p);
 		LAUNCH(k_overflow_scan, 1, 1024, (uint32_t *)ctx->ext_count.p, (uint32_t *)ctx->ext_off.p, n_buckets);
@@ -300,21 +317,63 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 		       (const uint32_t *)ctx->overflow_bucket.p, n_over, (const uint32_t *)ctx->ext_off.p, (uint32_t *)ctx->ext_count.p,
 		       (SkRec<W> *)ctx->ext.p);
 	}
-	const uint64_t solid_cap = n_inst / (uint64_t)ctx->ci + 1; // every solid key owns >= ci instances
-	if (ensure(ctx, ctx->solid_key, solid_cap * sizeof(Key<W>)) || ensure(ctx, ctx->solid_cnt, solid_cap * 4)) return -1;
-	if (ensure(ctx, ctx->grp_start, ((size_t)n_buckets + 2) * 4)) return -1;
-	LAUNCH(k_group_buckets, 1, 1024, (const unsigned long long *)ctx->cursor.p, n_buckets, (uint32_t)BC::GROUP_TARGET,
-	       (uint32_t)BC::GROUP_MAX, (uint32_t *)ctx->grp_start.p, ctx->d_ctr);
-	LAUNCH_SMEM(k_count_buckets<W>, BC::CTAS_PER_SM * ctx->n_sm, BC::THREADS, BC::SMEM, (const SkRec<W> *)ctx->regions.p,
-		    (const unsigned long long *)ctx->cursor.p, cfg.cap_records, (const SkRec<W> *)ctx->ext.p, (const uint32_t *)ctx->ext_off.p,
-		    (const uint32_t *)ctx->grp_start.p, K, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p, ctx->d_ctr);
+	return 0;
+}
+
+// Pass 2 over the buckets [first_bucket, first_bucket + n_owned) — all of them when world == 1 — reading every source's
+// records through `peers`.  solid_cap bounds the output arrays.
+template <int W>
+static int count_owned(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &peers, uint32_t first_bucket, uint64_t solid_cap)
+{
+	typedef BucketCfg<W> BC;
+	const uint32_t n_buckets = 1u << cfg.log2_buckets, world = cfg.world;
+	const uint32_t n_owned = first_bucket >= n_buckets ? 0u : (n_buckets - first_bucket < cfg.per_rank ? n_buckets - first_bucket : cfg.per_rank);
+	const uint32_t group_max = BC::SUB_MAX / world < BC::GROUP_MAX ? BC::SUB_MAX / world : BC::GROUP_MAX;
+	if (ensure(ctx, ctx->cur_all, ((size_t)cfg.per_rank * world + 1) * 8) || ensure(ctx, ctx->ext_all, ((size_t)cfg.per_rank * world + 1) * 4) ||
+	    ensure(ctx, ctx->grp_start, ((size_t)cfg.per_rank + 2) * 4))
+		return -1;
+	const uint64_t n_pairs = (uint64_t)n_owned * world;
+	if (n_pairs)
+		LAUNCH(k_pull_cursors<W>, (unsigned)((n_pairs + 255) / 256), 256, peers, world, first_bucket, n_owned, n_buckets, cfg.cap_records,
+		       (unsigned long long *)ctx->cur_all.p, (uint32_t *)ctx->ext_all.p);
+	LAUNCH(k_group_buckets, 1, 1024, (const unsigned long long *)ctx->cur_all.p, world, n_owned, (uint32_t)BC::GROUP_TARGET,
+	       group_max, (uint32_t *)ctx->grp_start.p, ctx->d_ctr);
+	LAUNCH_SMEM(k_count_buckets<W>, BC::CTAS_PER_SM * ctx->n_sm, BC::THREADS, BC::SMEM, peers, world, first_bucket, cfg.cap_records,
+		    (const unsigned long long *)ctx->cur_all.p, (const uint32_t *)ctx->ext_all.p, (const uint32_t *)ctx->grp_start.p, cfg.K,
+		    (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p, (unsigned long long)solid_cap, ctx->d_ctr);
 	if (read_counters(ctx)) return -1;
-	ctx->st.n_instances = n_inst;
 	ctx->st.n_distinct = ctx->h_ctr[CTR_DISTINCT];
 	ctx->st.n_solid = ctx->h_ctr[CTR_SOLID];
 	ctx->st.sum_solid = ctx->h_ctr[CTR_SUM_SOLID];
+	if (ctx->st.n_solid > solid_cap) return fail(ctx, "solid (k+1)-mer buffer too small (%llu > %llu)", (unsigned long long)ctx->st.n_solid, (unsigned long long)solid_cap);
+	ctx->cur_solid_key = ctx->solid_key.p;
+	ctx->cur_solid_cnt = ctx->solid_cnt.p;
 	ctx->have_count = true;
 	return 0;
+}
+
+template <int W>
+static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n)
+{
+	typedef BucketCfg<W> BC;
+	const PartCfg cfg = plan_cfg(n, ctx->K, 1, BC::GROUP_TARGET);
+	const uint32_t n_buckets = 1u << cfg.log2_buckets;
+	if (ensure(ctx, ctx->regions, (size_t)n_buckets * cfg.cap_records * sizeof(SkRec<W>)) || ensure(ctx, ctx->cursor, (size_t)n_buckets * 8) ||
+	    ensure(ctx, ctx->overflow, (size_t)cfg.overflow_cap * sizeof(SkRec<W>)) ||
+	    ensure(ctx, ctx->overflow_bucket, (size_t)cfg.overflow_cap * 4) || ensure(ctx, ctx->ext_off, (size_t)(n_buckets + 1) * 4) ||
+	    ensure(ctx, ctx->ext_count, (size_t)n_buckets * 4))
+		return -1;
+	// every solid key owns >= ci instances and there are fewer windows than stream bytes
+	const uint64_t solid_cap = n / (uint64_t)ctx->ci + 1;
+	if (ensure(ctx, ctx->solid_key, solid_cap * sizeof(Key<W>)) || ensure(ctx, ctx->solid_cnt, solid_cap * 4)) return -1;
+	if (partition_local<W>(ctx, d_seq, n, cfg)) return -1;
+	CountPeers<W> peers;
+	memset(&peers, 0, sizeof(peers));
+	peers.regions[0] = (const SkRec<W> *)ctx->regions.p;
+	peers.cursor[0] = (const unsigned long long *)ctx->cursor.p;
+	peers.ext[0] = (const SkRec<W> *)ctx->ext.p;
+	peers.ext_off[0] = (const uint32_t *)ctx->ext_off.p;
+	return count_owned<W>(ctx, cfg, peers, 0, solid_cap);
 }
 
 // ------------------------------------------------------------------------------------------------ graph stage
@@ -344,7 +403,7 @@ static int graph_stage(tagpu_ctx *ctx)
 		 *node_ebase = (uint32_t *)ctx->node_ebase.p, *chain_slot = (uint32_t *)ctx->chain_slot.p,
 		 *vL = (uint32_t *)ctx->vL.p, *vR = (uint32_t *)ctx->vR.p;
 	unsigned long long *ctr = ctx->d_ctr;
-	const Key<W> *solid = (const Key<W> *)ctx->solid_key.p;
+	const Key<W> *solid = (const Key<W> *)ctx->cur_solid_key;
 
 	if (n_solid) LAUNCH(k_insert_kmers<W>, (unsigned)((n_solid + 255) / 256), 256, solid, n_solid, k, t, vL, vR, ctr);
 	LAUNCH(k_classify<W>, (n_slots + 1023) / 1024, 1024, t, kind, node_slot, node_ebase, chain_slot, ctr);
@@ -392,7 +451,7 @@ static int graph_stage(tagpu_ctx *ctx)
 	if (n_cv) LAUNCH(k_interior<W>, (n_cv + 255) / 256, 256, t, k, n_cv, chain_slot, jump, vedge, g);
 	if (n_e) LAUNCH(k_rc_links<W>, (unsigned)((n_e + 255) / 256), 256, t, k, (uint32_t)n_e, node_slot, node_ebase, g, ctr);
 	if (n_solid && !ctx->skip_counts)
-		LAUNCH(k_edge_counts<W>, (unsigned)((n_solid + 255) / 256), 256, solid, (const uint32_t *)ctx->solid_cnt.p, n_solid, k, t,
+		LAUNCH(k_edge_counts<W>, (unsigned)((n_solid + 255) / 256), 256, solid, (const uint32_t *)ctx->cur_solid_cnt, n_solid, k, t,
 		       vL, vR, kind, node_ebase, vedge, g, ctr);
 	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
 	if (read_counters(ctx)) return -1;
@@ -409,6 +468,7 @@ static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool wit
 {
 	CU(cudaSetDevice(ctx->device));
 	if (K < 18 || K > 64) return fail(ctx, "unsupported k-mer size: k + 1 = %d (supported: 18..64)", K);
+	if (ctx->dist) return fail(ctx, "context is in multi-GPU mode (tagpu_dist_plan): use the tagpu_dist_* calls or tagpu_dist_close first");
 	ctx->K = K;
 	ctx->k = K - 1;
 	ctx->W = K <= 32 ? 1 : 2;
@@ -436,6 +496,237 @@ static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool wit
 	ctx->st.gpu_launches = ctx->launches;
 	prof_finish(ctx);
 	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU
+// One process per GPU.  Every rank partitions ITS slice of the reads into its own bucket regions (pass 1, local) and
+// owns a contiguous range of buckets, whose records it reads from every rank's regions through CUDA-IPC mappings inside
+// the counting kernel (pass 2: NVLink peer loads overlapped with shared-memory counting).  All buffers a peer touches
+// live in ONE allocation per rank (the "arena") with identical offsets everywhere, so a single 64-byte IPC handle per
+// rank is all the host has to exchange.  The host program supplies the barriers between phases (include/tagpu.h).
+struct DistState {
+	int rank = 0, world = 1, W = 0;
+	uint64_t n_total = 0;
+	PartCfg cfg;
+	uint64_t solid_cap = 0;
+	char *arena = nullptr;
+	size_t arena_bytes = 0;
+	size_t off_cursor = 0, off_extoff = 0, off_ext = 0, off_regions = 0, off_scnt = 0, off_skey = 0;
+	char *peer[TAGPU_MAX_RANKS] = { nullptr };      // arena of every rank as mapped here (peer[rank] = arena)
+	bool connected = false;
+	Buf g_key, g_cnt;                               // solid set gathered from all ranks
+};
+
+static void borrow(Buf &b, void *p, size_t bytes)
+{
+	b.p = p;
+	b.cap = bytes;
+}
+
+static void dist_unmap(tagpu_ctx *ctx)
+{
+	DistState *d = ctx->dist;
+	if (!d) return;
+	cudaDeviceSynchronize();
+	for (int r = 0; r < d->world; ++r)
+		if (r != d->rank && d->peer[r]) { cudaIpcCloseMemHandle(d->peer[r]); d->peer[r] = nullptr; }
+	d->connected = false;
+}
+
+static Buf *const *dist_borrowed(tagpu_ctx *ctx, int *n)
+{
+	static thread_local Buf *b[6];
+	b[0] = &ctx->regions; b[1] = &ctx->cursor; b[2] = &ctx->ext; b[3] = &ctx->ext_off; b[4] = &ctx->solid_key; b[5] = &ctx->solid_cnt;
+	*n = 6;
+	return b;
+}
+
+static void dist_release(tagpu_ctx *ctx)
+{
+	DistState *d = ctx->dist;
+	if (!d) return;
+	dist_unmap(ctx);
+	int n;
+	Buf *const *bb = dist_borrowed(ctx, &n);
+	for (int i = 0; i < n; ++i) { bb[i]->p = nullptr; bb[i]->cap = 0; }
+	if (d->arena) cudaFree(d->arena);
+	if (d->g_key.p) cudaFree(d->g_key.p);
+	if (d->g_cnt.p) cudaFree(d->g_cnt.p);
+	delete d;
+	ctx->dist = nullptr;
+}
+
+extern "C" int tagpu_dist_plan(tagpu_ctx *ctx, int rank, int world, uint64_t n_total_bytes, int k, void *handle_out)
+{
+	CU(cudaSetDevice(ctx->device));
+	if (world < 1 || world > TAGPU_MAX_RANKS || rank < 0 || rank >= world) return fail(ctx, "bad rank/world %d/%d (max %d ranks)", rank, world, TAGPU_MAX_RANKS);
+	const int K = k + 1;
+	if (K < 18 || K > 64) return fail(ctx, "unsupported k-mer size: k + 1 = %d (supported: 18..64)", K);
+	dist_release(ctx);
+	// the single-GPU buffers with the same roles are dropped: from now on they alias the arena
+	int nb;
+	Buf *const *bb = dist_borrowed(ctx, &nb);
+	for (int i = 0; i < nb; ++i) { if (bb[i]->p) CU(cudaFree(bb[i]->p)); bb[i]->p = nullptr; bb[i]->cap = 0; }
+	DistState *d = new DistState();
+	ctx->dist = d;
+	d->rank = rank; d->world = world; d->n_total = n_total_bytes;
+	d->W = K <= 32 ? 1 : 2;
+	ctx->K = K; ctx->k = k; ctx->W = d->W;
+	d->cfg = plan_cfg(n_total_bytes, K, world, d->W == 1 ? BucketCfg<1>::GROUP_TARGET : BucketCfg<2>::GROUP_TARGET);
+	const size_t rec = d->W == 1 ? sizeof(SkRec<1>) : sizeof(SkRec<2>), key = d->W == 1 ? sizeof(Key<1>) : sizeof(Key<2>);
+	const size_t n_buckets = (size_t)1 << d->cfg.log2_buckets;
+	// owned windows ~ N_i / world, bucket ownership is uneven: 1.5x head-room (checked, see count_owned)
+	d->solid_cap = n_total_bytes / world / (uint64_t)ctx->ci * 3 / 2 + (1u << 20);
+	size_t off = 0;
+	auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+	d->off_cursor = take(n_buckets * 8);
+	d->off_extoff = take((n_buckets + 1) * 4);
+	d->off_ext = take((size_t)d->cfg.overflow_cap * rec);
+	d->off_scnt = take(d->solid_cap * 4);
+	d->off_skey = take(d->solid_cap * key);
+	d->off_regions = take(n_buckets * d->cfg.cap_records * rec);
+	d->arena_bytes = off < (8u << 20) ? (8u << 20) : off;       // large enough to be an allocation of its own (IPC maps whole allocations)
+	CU(cudaMalloc(&d->arena, d->arena_bytes));
+	d->peer[rank] = d->arena;
+	borrow(ctx->cursor, d->arena + d->off_cursor, n_buckets * 8);
+	borrow(ctx->ext_off, d->arena + d->off_extoff, (n_buckets + 1) * 4);
+	borrow(ctx->ext, d->arena + d->off_ext, (size_t)d->cfg.overflow_cap * rec);
+	borrow(ctx->solid_cnt, d->arena + d->off_scnt, d->solid_cap * 4);
+	borrow(ctx->solid_key, d->arena + d->off_skey, d->solid_cap * key);
+	borrow(ctx->regions, d->arena + d->off_regions, n_buckets * d->cfg.cap_records * rec);
+	if (ensure(ctx, ctx->overflow, (size_t)d->cfg.overflow_cap * rec) || ensure(ctx, ctx->overflow_bucket, (size_t)d->cfg.overflow_cap * 4) ||
+	    ensure(ctx, ctx->ext_count, n_buckets * 4))
+		return -1;
+	cudaIpcMemHandle_t h;
+	memset(&h, 0, sizeof(h));
+	if (world > 1) CU(cudaIpcGetMemHandle(&h, d->arena));
+	static_assert(sizeof(cudaIpcMemHandle_t) == TAGPU_IPC_HANDLE_BYTES, "IPC handle size");
+	memcpy(handle_out, &h, sizeof(h));
+	d->connected = world == 1;
+	return 0;
+}
+
+extern "C" int tagpu_dist_connect(tagpu_ctx *ctx, const void *all_handles)
+{
+	DistState *d = ctx->dist;
+	if (!d) return fail(ctx, "tagpu_dist_connect before tagpu_dist_plan");
+	CU(cudaSetDevice(ctx->device));
+	for (int r = 0; r < d->world; ++r) {
+		if (r == d->rank) continue;
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const char *)all_handles + (size_t)r * TAGPU_IPC_HANDLE_BYTES, sizeof(h));
+		void *p = nullptr;
+		CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		d->peer[r] = (char *)p;
+	}
+	d->connected = true;
+	return 0;
+}
+
+extern "C" int tagpu_dist_partition(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_local_bytes)
+{
+	DistState *d = ctx->dist;
+	if (!d || !d->connected) return fail(ctx, "tagpu_dist_partition before tagpu_dist_plan / tagpu_dist_connect");
+	CU(cudaSetDevice(ctx->device));
+	if (n_local_bytes > d->n_total / d->world + (1u << 20))
+		return fail(ctx, "this rank's slice (%llu bytes) is larger than planned (%llu total over %d ranks)", (unsigned long long)n_local_bytes,
+			    (unsigned long long)d->n_total, d->world);
+	ctx->have_count = ctx->have_graph = false;
+	ctx->launches = 0;
+	ctx->err[0] = 0;
+	memset(&ctx->st, 0, sizeof(ctx->st));
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->d_ctr, 0, CTR_TOTAL * sizeof(unsigned long long), ctx->stream)); }
+	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+	// partition_local ends with a stream synchronisation: when the host enters the barrier, this rank's regions are complete
+	return d->W == 1 ? partition_local<1>(ctx, d_seq, n_local_bytes, d->cfg) : partition_local<2>(ctx, d_seq, n_local_bytes, d->cfg);
+}
+
+template <int W>
+static int dist_count(tagpu_ctx *ctx)
+{
+	DistState *d = ctx->dist;
+	CountPeers<W> peers;
+	memset(&peers, 0, sizeof(peers));
+	for (int r = 0; r < d->world; ++r) {
+		peers.regions[r] = (const SkRec<W> *)(d->peer[r] + d->off_regions);
+		peers.cursor[r] = (const unsigned long long *)(d->peer[r] + d->off_cursor);
+		peers.ext[r] = (const SkRec<W> *)(d->peer[r] + d->off_ext);
+		peers.ext_off[r] = (const uint32_t *)(d->peer[r] + d->off_extoff);
+	}
+	return count_owned<W>(ctx, d->cfg, peers, (uint32_t)d->rank * d->cfg.per_rank, d->solid_cap);
+}
+
+extern "C" int tagpu_dist_count(tagpu_ctx *ctx, uint64_t stats_out[4])
+{
+	DistState *d = ctx->dist;
+	if (!d || !d->connected) return fail(ctx, "tagpu_dist_count before tagpu_dist_plan / tagpu_dist_connect");
+	CU(cudaSetDevice(ctx->device));
+	const int rc = d->W == 1 ? dist_count<1>(ctx) : dist_count<2>(ctx);
+	if (rc) return rc;
+	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+	stats_out[0] = ctx->st.n_instances;   // windows of THIS rank's reads
+	stats_out[1] = ctx->st.n_distinct;    // distinct / solid keys of THIS rank's buckets
+	stats_out[2] = ctx->st.n_solid;
+	stats_out[3] = ctx->st.sum_solid;
+	return 0;
+}
+
+// all_stats: world x 4 values, the stats_out of every rank in rank order.  Pulls every rank's solid set over NVLink
+// (peer copies out of the mapped arenas), then runs the graph stage on the union.  with_graph = 0 stops after the gather.
+extern "C" int tagpu_dist_graph(tagpu_ctx *ctx, const uint64_t *all_stats, int with_graph)
+{
+	DistState *d = ctx->dist;
+	if (!d || !ctx->have_count) return fail(ctx, "tagpu_dist_graph before tagpu_dist_count");
+	CU(cudaSetDevice(ctx->device));
+	uint64_t tot[4] = { 0, 0, 0, 0 };
+	for (int r = 0; r < d->world; ++r)
+		for (int j = 0; j < 4; ++j) tot[j] += all_stats[r * 4 + j];
+	const size_t key = d->W == 1 ? sizeof(Key<1>) : sizeof(Key<2>);
+	if (d->world > 1) {
+		if (ensure(ctx, d->g_key, (tot[2] + 1) * key) || ensure(ctx, d->g_cnt, (tot[2] + 1) * 4)) return -1;
+		uint64_t o = 0;
+		ProfScope ps_(ctx, "peer_gather_solid");
+		for (int r = 0; r < d->world; ++r) {
+			const uint64_t n = all_stats[r * 4 + 2];
+			if (n > d->solid_cap) return fail(ctx, "rank %d reports %llu solid (k+1)-mers, more than the planned %llu", r, (unsigned long long)n, (unsigned long long)d->solid_cap);
+			if (n) {
+				CU(cudaMemcpyAsync((char *)d->g_key.p + o * key, d->peer[r] + d->off_skey, n * key, cudaMemcpyDeviceToDevice, ctx->stream));
+				CU(cudaMemcpyAsync((char *)d->g_cnt.p + o * 4, d->peer[r] + d->off_scnt, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+			}
+			o += n;
+		}
+		ctx->cur_solid_key = d->g_key.p;
+		ctx->cur_solid_cnt = d->g_cnt.p;
+	}
+	ctx->st.n_instances = tot[0];
+	ctx->st.n_distinct = tot[1];
+	ctx->st.n_solid = tot[2];
+	ctx->st.sum_solid = tot[3];
+	if (with_graph) {
+		const int rc = d->W == 1 ? graph_stage<1>(ctx) : graph_stage<2>(ctx);
+		if (rc) return rc;
+	} else {
+		CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+	}
+	CU(cudaEventElapsedTime(&ctx->st.ms_count, ctx->ev[0], ctx->ev[1]));
+	CU(cudaEventElapsedTime(&ctx->st.ms_graph, ctx->ev[1], ctx->ev[2]));
+	CU(cudaEventElapsedTime(&ctx->st.ms_total, ctx->ev[0], ctx->ev[2]));
+	ctx->st.gpu_launches = ctx->launches;
+	prof_finish(ctx);
+	return 0;
+}
+
+extern "C" void tagpu_dist_disconnect(tagpu_ctx *ctx)
+{
+	cudaSetDevice(ctx->device);
+	dist_unmap(ctx);
+}
+
+extern "C" void tagpu_dist_close(tagpu_ctx *ctx)
+{
+	cudaSetDevice(ctx->device);
+	dist_release(ctx);
 }
 
 static int upload(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n)
@@ -472,14 +763,14 @@ extern "C" int tagpu_copy_solid(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint
 	CU(cudaSetDevice(ctx->device));
 	const uint64_t n = ctx->st.n_solid;
 	if (!n) return 0;
-	CU(cudaMemcpyAsync(count, ctx->solid_cnt.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(count, ctx->cur_solid_cnt, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	if (ctx->W == 1) {
-		CU(cudaMemcpyAsync(lo, ctx->solid_key.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaMemcpyAsync(lo, ctx->cur_solid_key, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
 		CU(cudaStreamSynchronize(ctx->stream));
 		memset(hi, 0, n * 8);
 	} else {
 		std::vector<Key<2>> tmp(n);
-		CU(cudaMemcpyAsync(tmp.data(), ctx->solid_key.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaMemcpyAsync(tmp.data(), ctx->cur_solid_key, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
 		CU(cudaStreamSynchronize(ctx->stream));
 		for (uint64_t i = 0; i < n; ++i) { hi[i] = tmp[i].hi; lo[i] = tmp[i].lo; }
 	}

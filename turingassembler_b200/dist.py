@@ -1,0 +1,99 @@
+"""Multi-GPU orchestration of the k-mer stage: one process per GPU (include/tagpu.h "multi-GPU").
+
+This module is host plumbing only.  torch.distributed supplies rendezvous, the barriers between phases and the two tiny
+host-side exchanges (IPC handles once, 4 stats values per step); the data path — super-k-mer records travelling to the GPU
+that owns their bucket, and the solid sets travelling back — is done by libtagpu.so itself over NVLink peer memory
+(peer loads inside k_count_buckets, peer copies in tagpu_dist_graph).  The reference has no counterpart: it is a single
+process (pthreads only).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+
+def shard_reads(n_reads: int, rank: int, world: int):
+    """Contiguous 1/world slice of the read list for `rank`: [first, last).  Every read belongs to exactly one rank."""
+    return n_reads * rank // world, n_reads * (rank + 1) // world
+
+
+def owner_of_bucket(bucket: int, n_buckets: int, world: int) -> int:
+    """Rank that counts `bucket` (mirror of PartCfg.per_rank in csrc/tagpu_count.cuh): contiguous ranges."""
+    per_rank = (n_buckets + world - 1) // world
+    return bucket // per_rank
+
+
+class DistTagpu:
+    """Drives the tagpu_dist_* phases of one rank.  `tagpu` is a turingassembler_b200.Tagpu bound to this rank's GPU."""
+
+    def __init__(self, tagpu, rank: int, world: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.t, self.rank, self.world, self.group = tagpu, rank, world, group
+        self.torch, self.dist = torch, dist
+        self.on_gpu = dist.get_backend(group) == "nccl"
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if self.on_gpu else torch.device("cpu")
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._stats = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        self._all = torch.zeros(4 * world, dtype=torch.int64, device=self.dev)
+
+    def plan(self, n_total_bytes: int, k: int):
+        """Same n_total_bytes / k on every rank.  Allocates this rank's arena and maps everybody else's."""
+        self.t.dist_disconnect()          # a previous plan: unmap the peers, and only free our arena once everybody has
+        self.barrier()
+        handle = self.t.dist_plan(self.rank, self.world, n_total_bytes, k)
+        handles = exchange_bytes(self.dist, handle, self.world, self.group)
+        self.t.dist_connect(handles)
+        self.barrier()
+
+    def barrier(self):
+        # A 4-byte all-reduce followed by a host wait: a true barrier whatever stream the library launches on (the
+        # tagpu_dist_* phases synchronise their own stream before returning, so "every rank called barrier()" means
+        # "every rank's previous phase is complete and visible").
+        self.dist.all_reduce(self._flag, group=self.group)
+        self._sync()
+
+    def build(self, d_ptr: int, n_local_bytes: int, with_graph: bool = True) -> dict:
+        """One pass of the hot path over this rank's slice of the reads; returns the GLOBAL stats on every rank."""
+        t = self.t
+        t.dist_partition(d_ptr, n_local_bytes)
+        self.barrier()
+        local = t.dist_count()
+        all_stats = gather_stats(self.dist, self._stats, self._all, local, self.group)
+        return t.dist_graph(all_stats, with_graph)
+
+    def _sync(self):
+        if self.on_gpu:
+            self.torch.cuda.current_stream().synchronize()
+
+    def close(self):
+        self.t.dist_disconnect()
+        self.barrier()
+        self.t.dist_close()
+
+
+def exchange_bytes(dist, blob: bytes, world: int, group=None):
+    """all-gather of one fixed-size byte string per rank (the 64-byte CUDA IPC handles)."""
+    out = [None] * world
+    dist.all_gather_object(out, blob, group=group)
+    return out
+
+
+def gather_stats(dist, buf, all_buf, local, group=None):
+    """all-gather of the 4 per-rank counters (n_instances, n_distinct, n_solid, sum_solid) -> flat list, rank order.
+    The collective doubles as the barrier between counting and the solid-set gather."""
+    import torch
+    buf.copy_(torch.tensor([int(v) for v in local], dtype=torch.int64))
+    dist.all_gather_into_tensor(all_buf, buf, group=group) if buf.is_cuda else _gather_cpu(dist, all_buf, buf, group)
+    return [int(v) for v in all_buf.cpu().tolist()]
+
+
+def _gather_cpu(dist, all_buf, buf, group):
+    parts = list(all_buf.view(-1, buf.numel()).unbind(0))
+    dist.all_gather(parts, buf, group=group)
+
+
+def sum_stats(all_stats, world: int):
+    a = np.asarray(all_stats, dtype=np.uint64).reshape(world, 4)
+    return dict(zip(("n_instances", "n_distinct", "n_solid", "sum_solid"), (int(x) for x in a.sum(axis=0))))
