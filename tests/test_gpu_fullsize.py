@@ -43,10 +43,10 @@ def test_full_size_invariants(tagpu, oracle, k):
     assert np.array_equal(rc[rc], np.arange(n_e))                                   # involution
     assert np.array_equal(length[rc], length) and np.array_equal(g["e_count"][rc], g["e_count"])
     assert np.array_equal(g["e_src"][rc] ^ 1, g["e_dst"]) and np.array_equal(g["e_dst"][rc] ^ 1, g["e_src"])
-    assert int((length - k).sum()) == 2 * st["n_kp1_on_edge"] + int((length[rc == np.arange(n_e)] - k).sum())
+    # every solid (k+1)-mer on an edge is one window of the edge and one of its twin (a self-rc edge holds both windows
+    # itself; only a central palindromic (k+1)-mer of an odd self-rc edge breaks the pairing)
+    assert abs(int((length - k).sum()) - 2 * st["n_kp1_on_edge"]) <= int((rc == np.arange(n_e)).sum())
     # counts: every solid (k+1)-mer on an edge adds its count to the edge and to its twin
-    self_rc = rc == np.arange(n_e)
-    assert not self_rc.any() or k % 2 == 0 or True
     total = int(g["e_count"].astype(np.uint64).sum())
     hi, lo, cnt = tagpu.solid()
     assert int(cnt.astype(np.uint64).sum()) == st["sum_solid"]
