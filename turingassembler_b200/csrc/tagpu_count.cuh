@@ -83,6 +83,12 @@ TAGPU_DI SkRec<W> tagpu_make_record(const uint64_t *pk, int end_q, int n_bases, 
 }
 
 // ---------------------------------------------------------------- pass 1
+// Super-k-mer = maximal run of consecutive valid windows that share the SAME minimizer occurrence (hash and position),
+// so a run never exceeds w = K - m + 1 windows and — unlike a cut at thread or tile boundaries — it is a function of the
+// sequence alone: error-free reads that cover a genomic minimizer site produce bit-identical records, which pass 2
+// collapses before counting (tagpu_count.cuh: "duplicate records").  A run is emitted by the tile that contains its END;
+// the 96-base left halo lets it reach back to its start, the right halo word tells whether the run ends at the tile's
+// last position.
 template <int W>
 __global__ void __launch_bounds__(TAGPU_TILE_THREADS)
 k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *__restrict__ regions,
@@ -92,14 +98,17 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	uint64_t *pk = reinterpret_cast<uint64_t *>(smem_raw);
 	uint32_t *inv = reinterpret_cast<uint32_t *>(pk + TAGPU_SMEM_WORDS);
-	uint32_t *hp = inv + TAGPU_SMEM_WORDS + 2;          // m-mer hash per position, then block-wise prefix minima (in place)
+	uint32_t *vw = inv + TAGPU_SMEM_WORDS;              // per word: bit i = position i ends a valid window
+	uint32_t *bw = vw + TAGPU_SMEM_WORDS;               // per word: bit i = position i starts a run
+	uint32_t *hp = bw + TAGPU_SMEM_WORDS;               // m-mer (hash, position) per position, then block-wise prefix minima (in place)
 	uint32_t *hs = hp + TAGPU_HM_LEN;                   // block-wise suffix minima
 	const int K = cfg.K, m = TAGPU_MINIMIZER_M;
 
 	tagpu_load_tile(seq, n, (uint64_t)blockIdx.x * TAGPU_TILE_BASES, pk, inv);
 	__syncthreads();
 
-	// A. hash of the canonical m-mer ending at every position (invalid if the m-mer touches a non-ACGT byte)
+	// A. hash of the canonical m-mer ending at every position (invalid if the m-mer touches a non-ACGT byte), with the
+	//    position (mod 64) in the low bits: the minimum over a window then identifies one m-mer OCCURRENCE
 	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
 		const uint32_t mm = (1u << (2 * m)) - 1;
 		uint32_t fw = j ? (uint32_t)pk[j - 1] & mm : 0u;
@@ -118,7 +127,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 			rv = (rv >> 2) | ((3u - c) << (2 * (m - 1)));
 			run = bad ? 0 : run + 1;
 			const uint32_t cm = min(fw, rv);
-			hp[j * 33 + i] = run >= m ? (cm * 0x9e3779b1u) >> 10 : TAGPU_H_INVALID;
+			hp[j * 33 + i] = run >= m ? (((cm * 0x9e3779b1u) & ~63u) | (uint32_t)((j & 1) * 32 + i)) : TAGPU_H_INVALID;
 		}
 	}
 	__syncthreads();
@@ -137,42 +146,52 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 	}
 	__syncthreads();
 
-	// C. every thread cuts the 32 window-end positions of its word into runs of equal bucket.  The scan only records
-	//    run starts / ends as two bit masks; the records are built afterwards, one run per lane per iteration, so the
-	//    expensive part (128/256-bit extraction, cursor atomic, 16/32-byte store) runs converged instead of lane by lane.
-	const int wi = threadIdx.x + TAGPU_HALO_WORDS;
-	const uint32_t i1 = inv[wi - 1], i2 = inv[wi - 2];
-	int run = i1 ? (__ffs(i1) - 1) : 32 + (i2 ? (__ffs(i2) - 1) : 32);
-	uint32_t iv = inv[wi];
-	const int max_windows = min(32, SkCap<W>::bases - (K - 1));
-	int cur_n = 0;
-	uint32_t cur_b = 0, n_win = 0, starts = 0, ends = 0;
+	// C1. per word: which positions end a valid window (vw) and which of those start a new run (bw): the window before
+	//     is invalid or has another minimizer occurrence.  With w > 32 a run could outgrow a record, so word starts cut too.
+	uint32_t n_win = 0;
+	for (int j = threadIdx.x + 1; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
+		const uint32_t i1 = inv[j - 1], i2 = j >= 2 ? inv[j - 2] : 0xffffffffu;
+		int run = i1 ? (__ffs(i1) - 1) : 32 + (i2 ? (__ffs(i2) - 1) : 32);
+		uint32_t iv = inv[j];
+		bool pv = run >= K;
+		uint32_t pm = pv ? min(hs[HIDX(j * 32 - w)], hp[HIDX(j * 32 - 1)]) : 0u;
+		uint32_t vmask = 0, bmask = 0;
 #pragma unroll 4
-	for (int i = 0; i < 32; ++i) {
-		const bool bad = (int)iv < 0;
-		iv <<= 1;
-		run = bad ? 0 : run + 1;
-		const int q = wi * 32 + i;
-		if (run >= K) {
-			const uint32_t mh = min(hs[HIDX(q - w + 1)], hp[HIDX(q)]);
-			const uint32_t b = tagpu_bucket_of(mh, cfg.log2_buckets);
-			if (cur_n && (b != cur_b || cur_n == max_windows)) { ends |= 1u << (i - 1); cur_n = 0; }
-			if (!cur_n) starts |= 1u << i;
-			cur_b = b;
-			++cur_n;
-			++n_win;
-		} else if (cur_n) {
-			ends |= 1u << (i - 1);
-			cur_n = 0;
+		for (int i = 0; i < 32; ++i) {
+			const bool bad = (int)iv < 0;
+			iv <<= 1;
+			run = bad ? 0 : run + 1;
+			const bool v = run >= K;
+			uint32_t cm = 0;
+			if (v) {
+				const int q = j * 32 + i;
+				cm = min(hs[HIDX(q - w + 1)], hp[HIDX(q)]);
+				vmask |= 1u << i;
+				if (!pv || cm != pm || (w > 32 && i == 0)) bmask |= 1u << i;
+			}
+			pv = v;
+			pm = cm;
 		}
+		vw[j] = vmask;
+		bw[j] = bmask;
+		if (j >= TAGPU_HALO_WORDS && j < TAGPU_HALO_WORDS + TAGPU_TILE_WORDS) n_win += __popc(vmask);
 	}
-	if (cur_n) ends |= 1u << 31;
+	__syncthreads();
+
+	// C2. every thread emits the runs that END in its word: one record (2-bit bases + window count) appended to the
+	//     bucket of the run's minimizer.
+	const int wi = threadIdx.x + TAGPU_HALO_WORDS;
+	const uint32_t V = vw[wi], B = bw[wi], Bprev = bw[wi - 1];
+	const uint32_t Vn = (V >> 1) | (vw[wi + 1] << 31), Bn = (B >> 1) | (bw[wi + 1] << 31);
+	uint32_t ends = V & (~Vn | Bn);
 	while (ends) {
-		const int e = __ffs(ends) - 1, st = __ffs(starts) - 1;
+		const int e = __ffs(ends) - 1;
 		ends &= ends - 1;
-		starts &= starts - 1;
+		const uint32_t upto = B & (0xffffffffu >> (31 - e));
+		const int st = upto ? 31 - __clz(upto) : -1 - __clz(Bprev);
 		const int nw = e - st + 1, end_q = wi * 32 + e;
-		const uint32_t b = tagpu_bucket_of(min(hs[HIDX(end_q - w + 1)], hp[HIDX(end_q)]), cfg.log2_buckets);
+		if (nw > 32) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_RUN_LENGTH); continue; }
+		const uint32_t b = tagpu_bucket_of(min(hs[HIDX(end_q - w + 1)], hp[HIDX(end_q)]) >> 6, cfg.log2_buckets);
 		const SkRec<W> rec = tagpu_make_record<W>(pk, end_q, nw + K - 1, nw);
 		const unsigned long long old = atomicAdd(cursor + b, 1ull | ((unsigned long long)nw << 32));
 		const uint32_t idx = (uint32_t)old;
@@ -246,13 +265,21 @@ template <int W> struct BucketCfg {
 	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + 2 * THREADS * sizeof(SkRec<W>);
 };
 
-// table hash: one multiply per key word; the top bits pick the slot, the next ones the sub-class
-template <int W> TAGPU_DI uint64_t tagpu_table_hash(const Key<W> &k);
-template <> TAGPU_DI uint64_t tagpu_table_hash<1>(const Key<1> &k) { uint64_t h = k.lo * 0x9e3779b97f4a7c15ull; return h ^ (h >> 32); }
-template <> TAGPU_DI uint64_t tagpu_table_hash<2>(const Key<2> &k)
+// table hash: the key words are folded to 32 bits (one 32-bit multiply per extra word) and mixed by one more multiply;
+// the top bits pick the slot, the next ones the sub-class
+template <int W> TAGPU_DI uint32_t tagpu_table_hash(const Key<W> &k);
+template <> TAGPU_DI uint32_t tagpu_table_hash<1>(const Key<1> &k)
 {
-	uint64_t h = (k.lo ^ (k.hi * 0xd6e8feb86659fd93ull)) * 0x9e3779b97f4a7c15ull;
-	return h ^ (h >> 32);
+	const uint32_t x = (uint32_t)k.lo ^ ((uint32_t)(k.lo >> 32) * 0x85ebca6bu);
+	const uint32_t h = x * 0x9e3779b1u;
+	return h ^ (h >> 15);
+}
+template <> TAGPU_DI uint32_t tagpu_table_hash<2>(const Key<2> &k)
+{
+	const uint32_t x = (uint32_t)k.lo ^ ((uint32_t)(k.lo >> 32) * 0x85ebca6bu) ^ ((uint32_t)k.hi * 0xc2b2ae35u) ^
+			   ((uint32_t)(k.hi >> 32) * 0x27d4eb2fu);
+	const uint32_t h = x * 0x9e3779b1u;
+	return h ^ (h >> 15);
 }
 
 // K bases of a right-aligned record value, `sh` bits above its right end (sh <= 62)
@@ -293,6 +320,39 @@ TAGPU_DI SkRec<2> tagpu_record_rc(const SkRec<2> &r, int nb)
 	o.w[2] = a2 >> bs;
 	o.w[3] = 0;
 	return o;
+}
+
+// ---------------------------------------------------------------- duplicate records
+// Pass 1 cuts super-k-mers at minimizer occurrences only, so reads that cover the same genomic site without an error in
+// it produce the same record (or its reverse complement).  Pass 2 brings every record into its canonical orientation
+// (the smaller of the two base strings), finds equal records among the 32 of a chunk with one __match_any_sync on a hash
+// plus a full compare, and counts the windows of one representative with the multiplicity of the class.
+template <int W> TAGPU_DI bool tagpu_record_less(const SkRec<W> &a, const SkRec<W> &b);   // base words only (no length byte)
+template <> TAGPU_DI bool tagpu_record_less<1>(const SkRec<1> &a, const SkRec<1> &b)
+{
+	return a.w[1] != b.w[1] ? a.w[1] < b.w[1] : a.w[0] < b.w[0];
+}
+template <> TAGPU_DI bool tagpu_record_less<2>(const SkRec<2> &a, const SkRec<2> &b)
+{
+	if (a.w[2] != b.w[2]) return a.w[2] < b.w[2];
+	return a.w[1] != b.w[1] ? a.w[1] < b.w[1] : a.w[0] < b.w[0];
+}
+template <int W> TAGPU_DI bool tagpu_record_equal(const SkRec<W> &a, const SkRec<W> &b)
+{
+	bool eq = true;
+#pragma unroll
+	for (int i = 0; i < 2 * W; ++i) eq = eq && a.w[i] == b.w[i];
+	return eq;
+}
+template <int W> TAGPU_DI uint32_t tagpu_record_hash(const SkRec<W> &a)
+{
+	uint32_t x = 0;
+#pragma unroll
+	for (int i = 0; i < 2 * W; ++i) {
+		x = (x ^ (uint32_t)a.w[i]) * 0x85ebca6bu;
+		x = (x ^ (uint32_t)(a.w[i] >> 32)) * 0xc2b2ae35u;
+	}
+	return (x ^ (x >> 15)) & 0x7fffffffu;
 }
 
 // ---------------------------------------------------------------- cursors of the owned buckets, from every source
@@ -387,11 +447,12 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 	uint32_t *t_cnt = reinterpret_cast<uint32_t *>(t_key + C::SLOTS);
 	SkRec<W> *s_rec = reinterpret_cast<SkRec<W> *>(t_cnt + C::SLOTS);
 	__shared__ uint32_t s_group, s_claims, s_overflow, s_warp[C::THREADS / 32], s_stack[64], s_sp;
-	__shared__ uint32_t s_nrec[C::SUB_MAX], s_bpre[C::SUB_MAX + 1];   // per (bucket, source) of the group: records, batches before it
+	__shared__ uint32_t s_rpre[C::SUB_MAX + 1];                  // per (bucket, source) pair of the group: records before it
+	__shared__ uint32_t s_next;                                  // next record of the group to hand out
 	__shared__ unsigned long long s_out_base;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	constexpr uint32_t N_WARPS = C::THREADS / 32;
-	SkRec<W> *my_recs = s_rec + warp * 32;                      // forward records of the warp's current batch
+	SkRec<W> *my_recs = s_rec + warp * 32;                      // forward records of the warp's current chunk
 	SkRec<W> *my_rcs = s_rec + C::THREADS + warp * 32;          // ... and their reverse complements
 	const Key<W> kmask = KO::mask(K);
 	const uint32_t n_groups = (uint32_t)ctr[CTR_GROUPS];
@@ -406,25 +467,25 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 		if (grp >= n_groups) break;
 		const uint32_t b0 = grp_start[grp], nb = (grp_start[grp + 1] - b0) * world;  // nb (bucket, source) pairs <= SUB_MAX
 		if (warp == 0) {
-			// per-pair record counts and the exclusive prefix of their 32-record batches
+			// exclusive prefix of the record counts of the pairs
 			uint32_t tot_inst = 0, carry = 0;
 			for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
 				const uint32_t i = i0 + lane;
 				const unsigned long long cur = i < nb ? cur_all[(size_t)b0 * world + i] : 0ull;
-				const uint32_t nrec = (uint32_t)cur, nbat = (nrec + 31) >> 5;
+				const uint32_t nrec = (uint32_t)cur;
 				tot_inst += (uint32_t)(cur >> 32);
-				uint32_t incl = nbat;
+				uint32_t incl = nrec;
 #pragma unroll
 				for (int d = 1; d < 32; d <<= 1) {
 					uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
 					if (lane >= (uint32_t)d) incl += t;
 				}
-				if (i < nb) { s_nrec[i] = nrec; s_bpre[i] = carry + incl - nbat; }
+				if (i < nb) s_rpre[i] = carry + incl - nrec;
 				carry += __shfl_sync(0xffffffffu, incl, 31);
 			}
 			tot_inst = __reduce_add_sync(0xffffffffu, tot_inst);
 			if (lane == 0) {
-				s_bpre[nb] = carry;
+				s_rpre[nb] = carry;
 				uint32_t L = 0;                                          // a single oversized bucket starts on 2^L hash classes
 				while (L < 5 && (tot_inst >> L) > 2u * C::GROUP_TARGET) ++L;
 				s_sp = 0;
@@ -432,42 +493,76 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 			}
 		}
 		__syncthreads();
-		const uint32_t n_batches = s_bpre[nb];
+		const uint32_t n_recs = s_rpre[nb];
 		while (*(volatile uint32_t *)&s_sp) {
 			__syncthreads();
 			const uint32_t top = s_stack[s_sp - 1];
 			const uint32_t L = top >> 24, cls = top & 0xffffffu;
 			__syncthreads();
-			if (tid == 0) { --s_sp; s_claims = 0; s_overflow = 0; }
+			if (tid == 0) { --s_sp; s_claims = 0; s_overflow = 0; s_next = 0; }
 			__syncthreads();
-			// ---- insert every window of the group that belongs to hash class (L, cls); a batch = 32 records of one bucket
-			auto fetch = [&](uint32_t bt, SkRec<W> &out) -> bool {
-				if (bt >= n_batches) return false;
-				uint32_t i = 0;                                          // pair of batch bt: last i with s_bpre[i] <= bt
-				for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
-					const uint32_t v = i0 + lane < nb ? s_bpre[i0 + lane] : 0xffffffffu;
-					i += __popc(__ballot_sync(0xffffffffu, v <= bt));
+			// ---- insert every window of the group that belongs to hash class (L, cls).
+			// Work is handed out dynamically in chunks of 32 consecutive records of the group (across its pairs).
+			auto grab = [&](uint32_t &start, uint32_t &n) {
+				uint32_t st = 0, c = 0;
+				if (lane == 0) {
+					c = 32u;
+					st = atomicAdd(&s_next, c);
 				}
-				i -= 1;
-				const uint32_t g = (bt - s_bpre[i]) * 32 + lane, nrec = s_nrec[i];
-				if (g >= nrec) return false;
-				const uint32_t lb = b0 + i / world, src = i - (i / world) * world;
+				st = __shfl_sync(0xffffffffu, st, 0);
+				c = __shfl_sync(0xffffffffu, c, 0);
+				start = st;
+				n = st < n_recs ? min(c, n_recs - st) : 0u;
+			};
+			auto fetch = [&](uint32_t start, uint32_t n, SkRec<W> &out) -> bool {
+				if (lane >= n) return false;
+				const uint32_t g_idx = start + lane;
+				uint32_t lo = 0, hi = nb;                                // pair of record g_idx: last i with s_rpre[i] <= g_idx
+				while (hi - lo > 1) {
+					const uint32_t mid = (lo + hi) >> 1;
+					if (s_rpre[mid] <= g_idx) lo = mid; else hi = mid;
+				}
+				const uint32_t i = lo, g = g_idx - s_rpre[i];
+				uint32_t lb = b0 + i, src = 0;
+				if (world > 1) { lb = b0 + i / world; src = i - (i / world) * world; }
 				const size_t gb = (size_t)first_bucket + lb;                // the source indexes its regions by global bucket id
 				out = g < cap_records ? peers.regions[src][gb * cap_records + g]
 						      : peers.ext[src][ext_all[(size_t)lb * world + src] + (g - cap_records)];
 				return true;
 			};
-			SkRec<W> pre;                                                // software prefetch of the next batch's record
-			bool have_pre = fetch(warp, pre);
-			for (uint32_t bt = warp; bt < n_batches; bt += N_WARPS) {
+			SkRec<W> pre;                                                // software prefetch of the next chunk's records
+			uint32_t c_start, c_n;
+			grab(c_start, c_n);
+			bool have_pre = fetch(c_start, c_n, pre);
+			while (c_n) {
 				if (*(volatile uint32_t *)&s_overflow) break;
-				uint32_t my_n = 0;
+				uint32_t my_n = 0, rhash = 0x80000000u | lane;           // lanes without a record never match anybody
+				SkRec<W> canon, other;
 				if (have_pre) {
 					my_n = (uint32_t)(pre.w[2 * W - 1] >> 56);
-					my_recs[lane] = pre;
-					my_rcs[lane] = tagpu_record_rc(pre, (int)my_n + K - 1);
+					pre.w[2 * W - 1] &= 0x00ffffffffffffffull;
+					const SkRec<W> rc = tagpu_record_rc(pre, (int)my_n + K - 1);
+					const bool swap = tagpu_record_less<W>(rc, pre);
+					canon = swap ? rc : pre;
+					other = swap ? pre : rc;
+					canon.w[2 * W - 1] = (canon.w[2 * W - 1] & 0x00ffffffffffffffull) | ((unsigned long long)my_n << 56);
+					my_recs[lane] = canon;
+					rhash = tagpu_record_hash<W>(canon);
 				}
-				have_pre = fetch(bt + N_WARPS, pre);
+				const uint32_t peers_eq = __match_any_sync(0xffffffffu, rhash);
+				const uint32_t leader = (uint32_t)__ffs(peers_eq) - 1u;
+				__syncwarp();
+				const bool dup = have_pre && leader != lane && tagpu_record_equal<W>(my_recs[leader], canon);
+				const uint32_t dup_mask = __ballot_sync(0xffffffffu, dup);
+				if (have_pre) {
+					const unsigned long long mult = leader == lane ? 1u + (uint32_t)__popc(peers_eq & dup_mask) : 1u;
+					other.w[2 * W - 1] = (other.w[2 * W - 1] & 0x00ffffffffffffffull) | (mult << 56);
+					my_rcs[lane] = other;
+				}
+				if (dup) my_n = 0;                                       // counted through its class representative
+				const uint32_t live = __ballot_sync(0xffffffffu, my_n != 0u);
+				grab(c_start, c_n);
+				have_pre = fetch(c_start, c_n, pre);
 				uint32_t incl = my_n;
 #pragma unroll
 				for (int d = 1; d < 32; d <<= 1) {
@@ -492,15 +587,16 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 					int n_r = (int)r_n0, j = (int)(t0 - (r_incl - r_n0));
 					const SkRec<W> *rp = my_recs + r;
 					unsigned long long w0 = rp->w[0];
+					uint32_t mult = (uint32_t)(my_rcs[r].w[2 * W - 1] >> 56);
 					Key<W> fw = tagpu_record_window(*rp, 2 * (n_r - 1 - j), K);
 					Key<W> rv = tagpu_record_window(my_rcs[r], 2 * j, K);
 					for (;;) {
 						const Key<W> key = KO::le(fw, rv) ? fw : rv;
-						const uint64_t h = tagpu_table_hash<W>(key);
-						if (!L || ((uint32_t)(h >> (64 - C::LOG2_SLOTS - 20)) & ((1u << L) - 1u)) == cls) {
+						const uint32_t h = tagpu_table_hash<W>(key);
+						if (!L || ((h >> (32 - C::LOG2_SLOTS - 16)) & ((1u << L) - 1u)) == cls) {
 							// probe: the hit / claim decision is the only divergent part; the count increment is shared
 							const Key<W> stored = KO::bnot(key);
-							uint32_t slot = (uint32_t)(h >> (64 - C::LOG2_SLOTS));
+							uint32_t slot = h >> (32 - C::LOG2_SLOTS);
 							int probes = 0;
 							for (;;) {
 								const Key<W> have = t_key[slot];
@@ -512,12 +608,13 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 								slot = (slot + 1) & (C::SLOTS - 1);
 								if (++probes > C::MAX_PROBES) { s_overflow = 1; break; }       // table too full: re-run on sub-classes
 							}
-							atomicAdd(t_cnt + slot, 1u);
+							atomicAdd(t_cnt + slot, mult);
 						}
 						if (!--left) break;
-						if (++j == n_r) {                                    // next record: re-seed from the staged forward / rc records
-							++rp;
-							++r;
+						if (++j == n_r) {                                    // next live record: re-seed from the staged forward / rc records
+							r += (uint32_t)__ffs(live >> (r + 1u));
+							rp = my_recs + r;
+							mult = (uint32_t)(my_rcs[r].w[2 * W - 1] >> 56);
 							n_r = (int)(rp->w[2 * W - 1] >> 56);
 							j = 0;
 							w0 = rp->w[0];
@@ -588,7 +685,7 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 			if (lane == 0 && sum) atomicAdd(ctr + CTR_SUM_SOLID, sum);
 			__syncthreads();
 			if (tid == 0 && failed) {
-				if (L >= 20 || s_sp + 2 > 64) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_TABLE_FULL);
+				if (L >= 16 || s_sp + 2 > 64) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_TABLE_FULL);
 				else {
 					s_stack[s_sp++] = ((L + 1) << 24) | cls;
 					s_stack[s_sp++] = ((L + 1) << 24) | (cls + (1u << L));

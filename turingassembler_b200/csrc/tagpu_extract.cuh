@@ -11,9 +11,10 @@
 
 constexpr int TAGPU_TILE_THREADS = 256;
 constexpr int TAGPU_TILE_WORDS = 256;               // words whose positions are window ends
-constexpr int TAGPU_HALO_WORDS = 2;                 // 64 bases: enough history for K <= 64
+constexpr int TAGPU_HALO_WORDS = 3;                 // 96 bases to the left: K <= 64 of history for a window, plus the 31 windows a super-k-mer may reach back
+constexpr int TAGPU_RHALO_WORDS = 1;                // one word to the right: whether a super-k-mer ends at the tile's last position depends on the next window
 constexpr int TAGPU_TILE_BASES = TAGPU_TILE_WORDS * 32;
-constexpr int TAGPU_SMEM_WORDS = TAGPU_TILE_WORDS + TAGPU_HALO_WORDS;
+constexpr int TAGPU_SMEM_WORDS = TAGPU_TILE_WORDS + TAGPU_HALO_WORDS + TAGPU_RHALO_WORDS;
 
 // 4 ASCII bytes (byte 0 = first base) -> 8 bits of codes (first base in bits 7..6) + 4 invalid bits (first base = bit 3)
 TAGPU_DI void tagpu_pack4(uint32_t w, uint32_t &codes, uint32_t &inv)
@@ -27,12 +28,12 @@ TAGPU_DI void tagpu_pack4(uint32_t w, uint32_t &codes, uint32_t &inv)
 }
 
 // Packs the tile that owns window-end positions [tile_base, tile_base + TILE_BASES) into pk/inv.
-// smem word j covers stream positions tile_base - 64 + 32 j .. +31.
+// smem word j covers stream positions tile_base - 32 HALO_WORDS + 32 j .. +31.
 TAGPU_DI void tagpu_load_tile(const uint8_t *__restrict__ seq, uint64_t n, uint64_t tile_base,
 			       uint64_t *pk, uint32_t *inv)
 {
 	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
-		long long g0 = (long long)tile_base - 64 + 32ll * j;
+		long long g0 = (long long)tile_base - 32 * TAGPU_HALO_WORDS + 32ll * j;
 		uint64_t word = 0;
 		uint32_t bad = 0;
 		if (g0 >= 0 && (uint64_t)g0 + 32 <= n && ((reinterpret_cast<uintptr_t>(seq) + g0) & 15) == 0) {

@@ -25,7 +25,7 @@ enum {
 	CTR_JUMP_FLAGS /* + 64 */, CTR_TOTAL = CTR_JUMP_FLAGS + 64
 };
 
-enum { TAGPU_ERR_TABLE_FULL = 1, TAGPU_ERR_MISSING_SUCC = 2, TAGPU_ERR_CHAIN = 4, TAGPU_ERR_RC_LINK = 8, TAGPU_ERR_BUCKET_OVERFLOW = 16 };
+enum { TAGPU_ERR_TABLE_FULL = 1, TAGPU_ERR_MISSING_SUCC = 2, TAGPU_ERR_CHAIN = 4, TAGPU_ERR_RC_LINK = 8, TAGPU_ERR_BUCKET_OVERFLOW = 16, TAGPU_ERR_RUN_LENGTH = 32 };
 
 #define DEG4(x) __popc((x) & 15u)
 

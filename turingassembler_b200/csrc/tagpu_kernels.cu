@@ -290,7 +290,7 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 {
 	typedef BucketCfg<W> BC;
 	const uint32_t n_buckets = 1u << cfg.log2_buckets;
-	const size_t smem1 = TAGPU_SMEM_WORDS * 8 + (TAGPU_SMEM_WORDS + 2) * 4 + 2 * (size_t)TAGPU_HM_LEN * 4;
+	const size_t smem1 = TAGPU_SMEM_WORDS * 8 + 3 * (size_t)TAGPU_SMEM_WORDS * 4 + 2 * (size_t)TAGPU_HM_LEN * 4;
 	static bool attr_done[3] = { false, false, false };
 	if (!attr_done[W]) {
 		CU(cudaFuncSetAttribute(k_partition<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
