@@ -149,6 +149,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 	// C1. per word: which positions end a valid window (vw) and which of those start a new run (bw): the window before
 	//     is invalid or has another minimizer occurrence.  With w > 32 a run could outgrow a record, so word starts cut too.
 	uint32_t n_win = 0;
+	static_assert(TAGPU_TILE_THREADS >= TAGPU_SMEM_WORDS, "per-word phases assume one word per thread");
 	for (int j = threadIdx.x + 1; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
 		const uint32_t i1 = inv[j - 1], i2 = j >= 2 ? inv[j - 2] : 0xffffffffu;
 		int run = i1 ? (__ffs(i1) - 1) : 32 + (i2 ? (__ffs(i2) - 1) : 32);
@@ -181,9 +182,14 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 	// C2. every thread emits the runs that END in its word: one record (2-bit bases + window count) appended to the
 	//     bucket of the run's minimizer.
 	const int wi = threadIdx.x + TAGPU_HALO_WORDS;
-	const uint32_t V = vw[wi], B = bw[wi], Bprev = bw[wi - 1];
-	const uint32_t Vn = (V >> 1) | (vw[wi + 1] << 31), Bn = (B >> 1) | (bw[wi + 1] << 31);
-	uint32_t ends = V & (~Vn | Bn);
+	uint32_t ends = 0, B = 0, Bprev = 0;
+	if (threadIdx.x < TAGPU_TILE_WORDS) {
+		const uint32_t V = vw[wi];
+		B = bw[wi];
+		Bprev = bw[wi - 1];
+		const uint32_t Vn = (V >> 1) | (vw[wi + 1] << 31), Bn = (B >> 1) | (bw[wi + 1] << 31);
+		ends = V & (~Vn | Bn);
+	}
 	while (ends) {
 		const int e = __ffs(ends) - 1;
 		ends &= ends - 1;
@@ -252,10 +258,11 @@ __global__ void k_overflow_scatter(const SkRec<W> *__restrict__ overflow, const 
 
 // ---------------------------------------------------------------- pass 2
 template <int W> struct BucketCfg {
-	static constexpr int THREADS = 1024;                        // one CTA per SM with the biggest table that fits
-	static constexpr int CTAS_PER_SM = 1;
-	static constexpr int LOG2_SLOTS = W == 1 ? 14 : 13;
-	static constexpr int SLOTS = 1 << LOG2_SLOTS;               // shared-memory table slots per CTA (192 KB / 160 KB)
+	static constexpr int THREADS = 512;                         // two CTAs per SM: one CTA's barriers / harvest overlap the other's inserts
+	static constexpr int CTAS_PER_SM = 2;
+	// shared-memory table slots per CTA (any number: the home slot is mulhi(hash, SLOTS)); sized so that two CTAs of
+	// table + record staging + static + the 1 KB the hardware reserves per CTA fit the SM's 228 KB
+	static constexpr int SLOTS = W == 1 ? 7936 : 3968;
 	static constexpr int MAX_PROBES = 48;                       // a longer probe sequence aborts the attempt (re-run on sub-classes)
 	static constexpr int GROUP_MAX = 64;                        // buckets per group
 	static constexpr int SUB_MAX = 256;                         // (bucket, source rank) pairs per group: group_max = min(GROUP_MAX, SUB_MAX / world)
@@ -355,89 +362,129 @@ template <int W> TAGPU_DI uint32_t tagpu_record_hash(const SkRec<W> &a)
 	return (x ^ (x >> 15)) & 0x7fffffffu;
 }
 
-// ---------------------------------------------------------------- cursors of the owned buckets, from every source
-// One coalesced sweep (remote for the other ranks) instead of per-group remote reads inside the counting kernel.
-// cur_all[lb * world + s] = cursor of owned bucket lb at source s; ext_all[...] = where its overflow records start.
-template <int W>
-__global__ void __launch_bounds__(256) k_pull_cursors(const __grid_constant__ CountPeers<W> peers, uint32_t world, uint32_t first_bucket,
-							      uint32_t n_owned, uint32_t n_buckets, uint32_t cap_records,
-							      unsigned long long *__restrict__ cur_all, uint32_t *__restrict__ ext_all)
-{
-	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= (uint64_t)n_owned * world) return;
-	const uint32_t s = (uint32_t)(idx / n_owned), lb = (uint32_t)(idx - (uint64_t)s * n_owned), gb = first_bucket + lb;
-	unsigned long long cur = 0;
-	uint32_t eo = 0;
-	if (gb < n_buckets) {
-		cur = peers.cursor[s][gb];
-		if ((uint32_t)cur > cap_records) eo = peers.ext_off[s][gb];
-	}
-	cur_all[(size_t)lb * world + s] = cur;
-	ext_all[(size_t)lb * world + s] = eo;
-}
-
-// ---------------------------------------------------------------- bucket grouping
+// ---------------------------------------------------------------- cursors of the owned buckets + bucket grouping
 // Bucket sizes are very uneven (a bucket is a handful of minimizer sites; measured CV ~0.9), so pass 2 does not take
-// buckets one by one: consecutive buckets are packed greedily into groups of ~GROUP_TARGET windows (<= GROUP_MAX
-// buckets), and one CTA counts a whole group in one shared-memory table.  Single block; thread t owns a contiguous
-// chunk of buckets.  grp_start[g] = first bucket of group g, grp_start[n_groups] = n_buckets.
-__global__ void __launch_bounds__(1024) k_group_buckets(const unsigned long long *__restrict__ cur_all, uint32_t world, uint32_t n_buckets,
-							uint32_t target, uint32_t group_max, uint32_t *__restrict__ grp_start,
-							unsigned long long *ctr)
+// buckets one by one: consecutive buckets are packed into groups of ~GROUP_TARGET windows, and one CTA counts a whole
+// group in one shared-memory table.  With E[b] = windows of the owned buckets before b, bucket b belongs to group
+// floor(E[b] / target); groups are therefore found with one prefix sum, computed by three small grid-wide kernels:
+//   k_pull_cursors   one thread per owned bucket: its cursor at every source rank (one coalesced sweep, remote for the
+//                    other ranks) -> cur_all[lb * world + s], ext_all[...]; block-level scan of the window totals
+//   k_scan_blocks    exclusive scan of the block totals, number of groups
+//   k_mark_groups    first / end bucket of every group (a group id nobody maps to stays empty)
+constexpr int TAGPU_SCAN_BLOCK = 1024;
+
+template <int W>
+__global__ void __launch_bounds__(TAGPU_SCAN_BLOCK) k_pull_cursors(const __grid_constant__ CountPeers<W> peers, uint32_t world,
+									  uint32_t first_bucket, uint32_t n_owned, uint32_t n_buckets,
+									  uint32_t cap_records, unsigned long long *__restrict__ cur_all,
+									  uint32_t *__restrict__ ext_all, unsigned long long *__restrict__ pex,
+									  unsigned long long *__restrict__ bsum)
 {
-	__shared__ unsigned long long s_sum[1024];
-	__shared__ uint32_t s_cnt[1024];
-	const uint32_t per = (n_buckets + 1023) / 1024, lo = min(threadIdx.x * per, n_buckets), hi = min(lo + per, n_buckets);
-	auto windows = [&](uint32_t b) {                              // windows of bucket b over all sources
-		unsigned long long w = 0;
-		for (uint32_t s = 0; s < world; ++s) w += cur_all[(size_t)b * world + s] >> 32;
-		return w;
-	};
-	unsigned long long sum = 0;
-	for (uint32_t b = lo; b < hi; ++b) sum += windows(b);
-	s_sum[threadIdx.x] = sum;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		unsigned long long acc = 0;
-		for (int t = 0; t < 1024; ++t) { unsigned long long v = s_sum[t]; s_sum[t] = acc; acc += v; }
-	}
-	__syncthreads();
-	// A bucket starts a group when the running total crosses a multiple of `target`, or every group_max buckets.
-	// Both rules depend only on global prefix values / indices, so chunks can be processed independently.
-	for (int pass = 0; pass < 2; ++pass) {
-		unsigned long long acc = s_sum[threadIdx.x];                  // windows before bucket b
-		unsigned long long prev = lo ? acc - windows(lo - 1) : 0;     // ... and before bucket b - 1
-		uint32_t n = 0, out = pass ? s_cnt[threadIdx.x] : 0;
-		for (uint32_t b = lo; b < hi; ++b) {
-			const bool start = b == 0 || acc / target != prev / target || (b % group_max) == 0;
-			if (start) { if (pass) grp_start[out + n] = b; ++n; }
-			prev = acc;
-			acc += windows(b);
-		}
-		if (!pass) {
-			s_cnt[threadIdx.x] = n;
-			__syncthreads();
-			if (threadIdx.x == 0) {
-				uint32_t a = 0;
-				for (int t = 0; t < 1024; ++t) { uint32_t v = s_cnt[t]; s_cnt[t] = a; a += v; }
-				grp_start[a] = n_buckets;
-				ctr[CTR_SPARE1] = 0;          // work counter of k_count_buckets
-				ctr[CTR_GROUPS] = a;
+	__shared__ unsigned long long s_w[32];
+	const uint32_t lb = blockIdx.x * blockDim.x + threadIdx.x, gb = first_bucket + lb, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	unsigned long long wsum = 0;
+	if (lb < n_owned)
+		for (uint32_t s = 0; s < world; ++s) {
+			unsigned long long cur = 0;
+			uint32_t eo = 0;
+			if (gb < n_buckets) {
+				cur = peers.cursor[s][gb];
+				if ((uint32_t)cur > cap_records) eo = peers.ext_off[s][gb];
 			}
-			__syncthreads();
+			cur_all[(size_t)lb * world + s] = cur;
+			ext_all[(size_t)lb * world + s] = eo;
+			wsum += cur >> 32;
 		}
+	unsigned long long incl = wsum;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= (uint32_t)d) incl += t;
 	}
+	if (lane == 31) s_w[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		unsigned long long x = s_w[lane], y = x;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			unsigned long long t = __shfl_up_sync(0xffffffffu, y, d);
+			if (lane >= (uint32_t)d) y += t;
+		}
+		s_w[lane] = y - x;
+		if (lane == 31) bsum[blockIdx.x] = y;
+	}
+	__syncthreads();
+	if (lb < n_owned) pex[lb] = s_w[warp] + incl - wsum;        // windows of this block's buckets before lb
 }
 
-// Persistent CTAs pull groups of buckets from a global counter.  Each warp stages 32 records in shared memory
-// (forward and reverse-complemented), splits their windows into 32 equal contiguous segments (one per lane) and every
-// lane ROLLS the forward / reverse-complement keys through its segment (re-seeding only at record boundaries),
-// inserting the canonical key into the CTA's shared-memory table.
+// single block: bsum[i] -> windows before block i; ctr[CTR_GROUPS] = number of group ids; resets the work counter
+__global__ void __launch_bounds__(1024) k_scan_blocks(unsigned long long *__restrict__ bsum, uint32_t n_blocks, uint32_t target, unsigned long long *ctr)
+{
+	__shared__ unsigned long long s_part[1024];
+	const uint32_t per = (n_blocks + 1023) / 1024, lo = min(threadIdx.x * per, n_blocks), hi = min(lo + per, n_blocks);
+	unsigned long long sum = 0;
+	for (uint32_t i = lo; i < hi; ++i) sum += bsum[i];
+	s_part[threadIdx.x] = sum;
+	__syncthreads();
+	if (threadIdx.x < 32) {                                     // 1024 partials: 32 per lane, then a warp scan
+		unsigned long long mine = 0;
+		for (int t = 0; t < 32; ++t) mine += s_part[threadIdx.x * 32 + t];
+		unsigned long long incl = mine;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+			if (threadIdx.x >= (uint32_t)d) incl += t;
+		}
+		unsigned long long acc = incl - mine;
+		for (int t = 0; t < 32; ++t) { const unsigned long long v = s_part[threadIdx.x * 32 + t]; s_part[threadIdx.x * 32 + t] = acc; acc += v; }
+		if (threadIdx.x == 31) {
+			ctr[CTR_GROUPS] = incl / target + 1;
+			ctr[CTR_SPARE1] = 0;                                // work counter of k_count_buckets
+		}
+	}
+	__syncthreads();
+	unsigned long long acc = s_part[threadIdx.x];
+	for (uint32_t i = lo; i < hi; ++i) { const unsigned long long v = bsum[i]; bsum[i] = acc; acc += v; }
+}
+
+// grp_first[g] = first owned bucket of group g (TAGPU_NONE if no bucket starts in its window interval), grp_end[g] = one
+// past its last bucket.  grp_first must be pre-filled with 0xff.
+__global__ void __launch_bounds__(TAGPU_SCAN_BLOCK) k_mark_groups(const unsigned long long *__restrict__ pex, const unsigned long long *__restrict__ bsum,
+									 uint32_t n_owned, uint32_t target, uint32_t *__restrict__ grp_first,
+									 uint32_t *__restrict__ grp_end)
+{
+	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_owned) return;
+	const unsigned long long g = (bsum[b / TAGPU_SCAN_BLOCK] + pex[b]) / target;
+	const unsigned long long gp = b ? (bsum[(b - 1) / TAGPU_SCAN_BLOCK] + pex[b - 1]) / target : ~0ull;
+	if (g != gp) {
+		grp_first[g] = b;
+		if (b) grp_end[gp] = b;
+	}
+	if (b + 1 == n_owned) grp_end[g] = n_owned;
+}
+
+// Persistent CTAs pull groups of buckets from a global counter.  Each warp stages a chunk of <= 32 records in shared
+// memory (canonical orientation + the other strand), collapses duplicate records, splits the remaining windows into 32
+// equal contiguous segments (one per lane) and every lane ROLLS the forward / reverse-complement keys through its
+// segment (re-seeding only at record boundaries), inserting the canonical key into the CTA's shared-memory table.
+//
+// Per group the CTA meets at five barriers only.  Everything with a global round trip is taken off the critical path:
+// the id of the next group is fetched while the current one is being counted, and the output offset of the harvest
+// (one global atomic) travels while the solid keys are compacted into the shared-memory staging area.
+#ifdef TAGPU_TIMING
+#define TM_DECL() long long tm_setup = 0, tm_insert = 0, tm_wait = 0, tm_harvest = 0, tm_ha = 0, tm_hb = 0, tm_iters = 0, tm_failed = 0, tm_t = clock64()
+#define TM_ADD(x) do { long long n_ = clock64(); x += n_ - tm_t; tm_t = n_; } while (0)
+#else
+#define TM_DECL()
+#define TM_ADD(x)
+#endif
+
 template <int W>
 __global__ void __launch_bounds__(BucketCfg<W>::THREADS, BucketCfg<W>::CTAS_PER_SM)
 k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uint32_t first_bucket, uint32_t cap_records,
-		const unsigned long long *__restrict__ cur_all, const uint32_t *__restrict__ ext_all, const uint32_t *__restrict__ grp_start,
-		int K, uint32_t ci, Key<W> *__restrict__ solid, uint32_t *__restrict__ solid_cnt, unsigned long long solid_cap,
+		const unsigned long long *__restrict__ cur_all, const uint32_t *__restrict__ ext_all, const uint32_t *__restrict__ grp_first,
+		const uint32_t *__restrict__ grp_end, uint32_t group_max, int K, uint32_t ci, Key<W> *__restrict__ solid, uint32_t *__restrict__ solid_cnt, unsigned long long solid_cap,
 		unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
@@ -446,73 +493,94 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 	Key<W> *t_key = reinterpret_cast<Key<W> *>(smem_raw);
 	uint32_t *t_cnt = reinterpret_cast<uint32_t *>(t_key + C::SLOTS);
 	SkRec<W> *s_rec = reinterpret_cast<SkRec<W> *>(t_cnt + C::SLOTS);
-	__shared__ uint32_t s_group, s_claims, s_overflow, s_warp[C::THREADS / 32], s_stack[64], s_sp;
+	// during the harvest the record staging area holds the compacted solid (key, count) pairs of the group
+	constexpr uint32_t OUT_CAP = 2 * C::THREADS * sizeof(SkRec<W>) / (sizeof(Key<W>) + 4);
+	Key<W> *o_key = reinterpret_cast<Key<W> *>(s_rec);
+	uint32_t *o_cnt = reinterpret_cast<uint32_t *>(o_key + OUT_CAP);
+	constexpr uint32_t TOP_NONE = 0xffffffffu;
+	__shared__ uint32_t s_b0, s_nb, s_bs, s_be, s_top, s_claims, s_overflow, s_next, s_sp, s_warp_solid[C::THREADS / 32], s_stack[64];
 	__shared__ uint32_t s_rpre[C::SUB_MAX + 1];                  // per (bucket, source) pair of the group: records before it
-	__shared__ uint32_t s_next;                                  // next record of the group to hand out
 	__shared__ unsigned long long s_out_base;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	constexpr uint32_t N_WARPS = C::THREADS / 32;
-	SkRec<W> *my_recs = s_rec + warp * 32;                      // forward records of the warp's current chunk
-	SkRec<W> *my_rcs = s_rec + C::THREADS + warp * 32;          // ... and their reverse complements
+	SkRec<W> *my_recs = s_rec + warp * 32;                      // canonical records of the warp's current chunk
+	SkRec<W> *my_rcs = s_rec + C::THREADS + warp * 32;          // ... and their other strand (+ multiplicity in the top byte)
 	const Key<W> kmask = KO::mask(K);
 	const uint32_t n_groups = (uint32_t)ctr[CTR_GROUPS];
+	TM_DECL();
 
 	for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) { t_key[i] = KO::make(0, 0); t_cnt[i] = 0; }
+	// thread 0 always holds the id of the NEXT group in a register (requested one group ahead)
+	uint32_t next_group = 0;
+	if (tid == 0) { next_group = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull); s_bs = 0; s_be = 0; }
 
 	for (;;) {
-		__syncthreads();
-		if (tid == 0) s_group = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);
-		__syncthreads();
-		const uint32_t grp = s_group;
-		if (grp >= n_groups) break;
-		const uint32_t b0 = grp_start[grp], nb = (grp_start[grp + 1] - b0) * world;  // nb (bucket, source) pairs <= SUB_MAX
+		__syncthreads();                                            // B0: previous group fully harvested, staging area free
 		if (warp == 0) {
-			// exclusive prefix of the record counts of the pairs
-			uint32_t tot_inst = 0, carry = 0;
-			for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
-				const uint32_t i = i0 + lane;
-				const unsigned long long cur = i < nb ? cur_all[(size_t)b0 * world + i] : 0ull;
-				const uint32_t nrec = (uint32_t)cur;
-				tot_inst += (uint32_t)(cur >> 32);
-				uint32_t incl = nrec;
-#pragma unroll
-				for (int d = 1; d < 32; d <<= 1) {
-					uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-					if (lane >= (uint32_t)d) incl += t;
-				}
-				if (i < nb) s_rpre[i] = carry + incl - nrec;
-				carry += __shfl_sync(0xffffffffu, incl, 31);
+			// ---- group setup by warp 0: next <= group_max buckets of the current group id (or of the next non-empty
+			// one), record prefix over their (bucket, source) pairs, first hash class on the stack
+			uint32_t bs = s_bs, be = s_be;
+			while (bs >= be) {
+				const uint32_t grp = __shfl_sync(0xffffffffu, next_group, 0);
+				if (grp >= n_groups) { bs = be = TAGPU_NONE; break; }
+				if (lane == 0) next_group = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);   // lands during the inserts
+				bs = grp_first[grp];
+				be = bs == TAGPU_NONE ? 0u : grp_end[grp];
+				if (bs == TAGPU_NONE) bs = 0;                                          // empty group id: take the next one
 			}
-			tot_inst = __reduce_add_sync(0xffffffffu, tot_inst);
-			if (lane == 0) {
-				s_rpre[nb] = carry;
-				uint32_t L = 0;                                          // a single oversized bucket starts on 2^L hash classes
-				while (L < 5 && (tot_inst >> L) > 2u * C::GROUP_TARGET) ++L;
-				s_sp = 0;
-				for (uint32_t c = 0; c < (1u << L); ++c) s_stack[s_sp++] = (L << 24) | c;
+			if (bs == TAGPU_NONE) {
+				if (lane == 0) s_nb = TAGPU_NONE;
+			} else {
+				const uint32_t b0 = bs, nb = min(be - bs, group_max) * world;
+				uint32_t tot_inst = 0, carry = 0;
+				for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
+					const uint32_t i = i0 + lane;
+					const unsigned long long cur = i < nb ? cur_all[(size_t)b0 * world + i] : 0ull;
+					const uint32_t nrec = (uint32_t)cur;
+					tot_inst += (uint32_t)(cur >> 32);
+					uint32_t incl = nrec;
+#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) {
+						uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+						if (lane >= (uint32_t)d) incl += t;
+					}
+					if (i < nb) s_rpre[i] = carry + incl - nrec;
+					carry += __shfl_sync(0xffffffffu, incl, 31);
+				}
+				tot_inst = __reduce_add_sync(0xffffffffu, tot_inst);
+				if (lane == 0) {
+					s_rpre[nb] = carry;
+					uint32_t L = 0;                                  // a single oversized bucket starts on 2^L hash classes
+					while (L < 5 && (tot_inst >> L) > 2u * C::GROUP_TARGET) ++L;
+					uint32_t sp = 0;
+					for (uint32_t c = 1; c < (1u << L); ++c) s_stack[sp++] = (L << 24) | c;
+					s_sp = sp;
+					s_top = L << 24;                                 // class 0 of level L goes first
+					s_claims = 0; s_overflow = 0; s_next = 0;
+					s_b0 = b0; s_nb = nb;
+					s_bs = b0 + nb / world; s_be = be;
+				}
 			}
 		}
-		__syncthreads();
+		__syncthreads();                                            // B1
+		const uint32_t b0 = s_b0, nb = s_nb;                            // nb (bucket, source) pairs <= SUB_MAX
+		if (nb == TAGPU_NONE) break;
 		const uint32_t n_recs = s_rpre[nb];
-		while (*(volatile uint32_t *)&s_sp) {
-			__syncthreads();
-			const uint32_t top = s_stack[s_sp - 1];
+		// Work is handed out dynamically in chunks of consecutive records of the group (across its pairs).  The chunk size
+		// (<= 32 records, one per lane) is chosen so that the chunks fill whole waves of the CTA's warps.
+		const uint32_t waves = (n_recs + 32u * N_WARPS - 1u) / (32u * N_WARPS);
+		const uint32_t chunk = max(1u, min(32u, (n_recs + waves * N_WARPS - 1u) / max(1u, waves * N_WARPS)));
+		TM_ADD(tm_setup);
+		for (;;) {                                                  // one iteration per hash class (L, cls) of the group
+			const uint32_t top = s_top;
 			const uint32_t L = top >> 24, cls = top & 0xffffffu;
-			__syncthreads();
-			if (tid == 0) { --s_sp; s_claims = 0; s_overflow = 0; s_next = 0; }
-			__syncthreads();
-			// ---- insert every window of the group that belongs to hash class (L, cls).
-			// Work is handed out dynamically in chunks of 32 consecutive records of the group (across its pairs).
+			// ---- insert every window of the group that belongs to hash class (L, cls)
 			auto grab = [&](uint32_t &start, uint32_t &n) {
-				uint32_t st = 0, c = 0;
-				if (lane == 0) {
-					c = 32u;
-					st = atomicAdd(&s_next, c);
-				}
+				uint32_t st = 0;
+				if (lane == 0) st = atomicAdd(&s_next, chunk);
 				st = __shfl_sync(0xffffffffu, st, 0);
-				c = __shfl_sync(0xffffffffu, c, 0);
 				start = st;
-				n = st < n_recs ? min(c, n_recs - st) : 0u;
+				n = st < n_recs ? min(chunk, n_recs - st) : 0u;
 			};
 			auto fetch = [&](uint32_t start, uint32_t n, SkRec<W> &out) -> bool {
 				if (lane >= n) return false;
@@ -593,10 +661,10 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 					for (;;) {
 						const Key<W> key = KO::le(fw, rv) ? fw : rv;
 						const uint32_t h = tagpu_table_hash<W>(key);
-						if (!L || ((h >> (32 - C::LOG2_SLOTS - 16)) & ((1u << L) - 1u)) == cls) {
+						if (!L || (h & ((1u << L) - 1u)) == cls) {
 							// probe: the hit / claim decision is the only divergent part; the count increment is shared
 							const Key<W> stored = KO::bnot(key);
-							uint32_t slot = h >> (32 - C::LOG2_SLOTS);
+							uint32_t slot = __umulhi(h, (uint32_t)C::SLOTS);
 							int probes = 0;
 							for (;;) {
 								const Key<W> have = t_key[slot];
@@ -605,13 +673,13 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 									const Key<W> old = ktab_cas<W>(t_key + slot, stored);   // ATOMS.CAS.64 / .128
 									if (KO::is_zero(old) || KO::eq(old, stored)) break;
 								}
-								slot = (slot + 1) & (C::SLOTS - 1);
+								slot = slot + 1 == C::SLOTS ? 0u : slot + 1;
 								if (++probes > C::MAX_PROBES) { s_overflow = 1; break; }       // table too full: re-run on sub-classes
 							}
 							atomicAdd(t_cnt + slot, mult);
 						}
 						if (!--left) break;
-						if (++j == n_r) {                                    // next live record: re-seed from the staged forward / rc records
+						if (++j == n_r) {                                    // next live record: re-seed from the staged records
 							r += (uint32_t)__ffs(live >> (r + 1u));
 							rp = my_recs + r;
 							mult = (uint32_t)(my_rcs[r].w[2 * W - 1] >> 56);
@@ -629,7 +697,9 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 				}
 				__syncwarp();
 			}
-			__syncthreads();
+			TM_ADD(tm_insert);
+			__syncthreads();                                        // B2: all inserts of this class are in the table
+			TM_ADD(tm_wait);
 			// ---- harvest (or discard on overflow) and leave the table zeroed
 			const bool failed = *(volatile uint32_t *)&s_overflow != 0;
 			uint32_t mine = 0, used = 0;
@@ -647,32 +717,42 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 				uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
 				if (lane >= (uint32_t)d) incl += t;
 			}
-			if (lane == 31) s_warp[warp] = incl;
-			__syncthreads();
-			if (warp == 0) {
-				uint32_t x = lane < N_WARPS ? s_warp[lane] : 0u, in2 = x;
-#pragma unroll
-				for (int d = 1; d < 32; d <<= 1) {
-					uint32_t t = __shfl_up_sync(0xffffffffu, in2, d);
-					if (lane >= (uint32_t)d) in2 += t;
+			if (lane == 31) s_warp_solid[warp] = incl;
+			TM_ADD(tm_ha);
+			__syncthreads();                                        // B3: per-warp solid totals (and s_claims) are complete
+			// every warp derives its own offset from the per-warp totals (no second scan phase)
+			const uint32_t wt = lane < N_WARPS ? s_warp_solid[lane] : 0u;
+			const uint32_t n_out = __reduce_add_sync(0xffffffffu, wt);
+			const uint32_t before = __reduce_add_sync(0xffffffffu, lane < warp ? wt : 0u);
+			const bool staged = n_out <= OUT_CAP;                       // else (huge group) write straight to the global arrays
+			if (tid == 0) {
+				// the global offset is requested now and consumed after the compaction pass
+				s_out_base = n_out ? atomicAdd(ctr + CTR_SOLID, (unsigned long long)n_out) : 0ull;
+				if (!failed) atomicAdd(ctr + CTR_DISTINCT, (unsigned long long)s_claims);
+				// next hash class: children of a failed class first, then whatever is left on the stack
+				uint32_t sp = s_sp;
+				if (failed) {
+					if (L >= 16 || sp + 2 > 64) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_TABLE_FULL);
+					else {
+						s_stack[sp++] = ((L + 1) << 24) | cls;
+						s_stack[sp++] = ((L + 1) << 24) | (cls + (1u << L));
+					}
 				}
-				if (lane < N_WARPS) s_warp[lane] = in2 - x;
-				if (lane == 31) {
-					s_out_base = in2 ? atomicAdd(ctr + CTR_SOLID, (unsigned long long)in2) : 0ull;
-					if (!failed) atomicAdd(ctr + CTR_DISTINCT, (unsigned long long)s_claims);
-				}
+				s_top = sp ? s_stack[--sp] : TOP_NONE;
+				s_sp = sp;
+				s_claims = 0; s_overflow = 0; s_next = 0;
 			}
-			__syncthreads();
-			unsigned long long o = s_out_base + s_warp[warp] + incl - mine;
+			if (!staged) __syncthreads();                           // (rare) the direct path needs s_out_base now
+			const unsigned long long gbase = staged ? 0ull : s_out_base;
+			uint32_t o = before + incl - mine;
 			unsigned long long sum = 0;
 			for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) {
 				const uint32_t c = t_cnt[i];
 				if (c) {
 					if (!failed && c >= ci) {
-						if (o < solid_cap) {                         // the host reports the overflow (n_solid > solid_cap)
-							solid[o] = KO::bnot(t_key[i]);
-							solid_cnt[o] = c;
-						}
+						const Key<W> key = KO::bnot(t_key[i]);
+						if (staged) { o_key[o] = key; o_cnt[o] = c; }
+						else if (gbase + o < solid_cap) { solid[gbase + o] = key; solid_cnt[gbase + o] = c; }
 						sum += c;
 						++o;
 					}
@@ -683,15 +763,33 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 #pragma unroll
 			for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
 			if (lane == 0 && sum) atomicAdd(ctr + CTR_SUM_SOLID, sum);
-			__syncthreads();
-			if (tid == 0 && failed) {
-				if (L >= 16 || s_sp + 2 > 64) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_TABLE_FULL);
-				else {
-					s_stack[s_sp++] = ((L + 1) << 24) | cls;
-					s_stack[s_sp++] = ((L + 1) << 24) | (cls + (1u << L));
-				}
+			TM_ADD(tm_hb);
+#ifdef TAGPU_TIMING
+			tm_iters += 1; tm_failed += failed ? 1 : 0;
+#endif
+			__syncthreads();                                        // B4: table zeroed, compacted output + s_out_base + s_top visible
+			if (staged) {
+				const unsigned long long base = s_out_base;
+				for (uint32_t i = tid; i < n_out; i += C::THREADS)
+					if (base + i < solid_cap) {                     // the host reports the overflow (n_solid > solid_cap)
+						solid[base + i] = o_key[i];
+						solid_cnt[base + i] = o_cnt[i];
+					}
 			}
-			__syncthreads();
+			TM_ADD(tm_harvest);
+			if (s_top == TOP_NONE) break;                           // group done (B0 of the next group protects the staging area)
+			__syncthreads();                                        // another class of the same group: staging area must be drained first
 		}
 	}
+#ifdef TAGPU_TIMING
+	if (lane == 0) {          // cycles summed over all warps: setup / insert / wait at the post-insert barrier / harvest
+		atomicAdd(ctr + CTR_JUMP_FLAGS + 48, (unsigned long long)tm_setup);
+		atomicAdd(ctr + CTR_JUMP_FLAGS + 49, (unsigned long long)tm_insert);
+		atomicAdd(ctr + CTR_JUMP_FLAGS + 50, (unsigned long long)tm_wait);
+		atomicAdd(ctr + CTR_JUMP_FLAGS + 51, (unsigned long long)tm_harvest);
+		atomicAdd(ctr + CTR_JUMP_FLAGS + 52, (unsigned long long)tm_ha);
+		atomicAdd(ctr + CTR_JUMP_FLAGS + 53, (unsigned long long)tm_hb);
+		if (warp == 0) { atomicAdd(ctr + CTR_JUMP_FLAGS + 54, (unsigned long long)tm_iters); atomicAdd(ctr + CTR_JUMP_FLAGS + 55, (unsigned long long)tm_failed); }
+	}
+#endif
 }

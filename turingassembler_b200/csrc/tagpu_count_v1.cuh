@@ -27,7 +27,7 @@ k_count_direct(const uint8_t *__restrict__ seq, uint64_t n, int K, CSlot<W> *tab
 	if (threadIdx.x == 0) { s_n = 0; s_inst = 0; }
 	tagpu_load_tile(seq, n, (uint64_t)blockIdx.x * TAGPU_TILE_BASES, pk, inv);
 	__syncthreads();
-	uint32_t n_valid = tagpu_roll_word<W>(pk, inv, threadIdx.x + TAGPU_HALO_WORDS, K, [&](const Key<W> &key, int) {
+	uint32_t n_valid = threadIdx.x >= TAGPU_TILE_WORDS ? 0u : tagpu_roll_word<W>(pk, inv, threadIdx.x + TAGPU_HALO_WORDS, K, [&](const Key<W> &key, int) {
 		const Key<W> stored = KO::bnot(key);
 		uint64_t slot = (KO::hash(key) >> 16) & slot_mask;
 		for (uint64_t probes = 0;; ++probes) {

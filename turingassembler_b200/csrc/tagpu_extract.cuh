@@ -9,7 +9,7 @@
 #pragma once
 #include "tagpu_key.cuh"
 
-constexpr int TAGPU_TILE_THREADS = 256;
+constexpr int TAGPU_TILE_THREADS = 288;              // >= SMEM_WORDS: every per-word phase (halo words included) is ONE pass over the threads
 constexpr int TAGPU_TILE_WORDS = 256;               // words whose positions are window ends
 constexpr int TAGPU_HALO_WORDS = 3;                 // 96 bases to the left: K <= 64 of history for a window, plus the 31 windows a super-k-mer may reach back
 constexpr int TAGPU_RHALO_WORDS = 1;                // one word to the right: whether a super-k-mer ends at the tile's last position depends on the next window

@@ -31,7 +31,8 @@ struct tagpu_ctx {
 	int k = 0, K = 0, W = 0;
 	char err[512] = { 0 };
 	unsigned long long *d_ctr = nullptr, *h_ctr = nullptr;
-	Buf regions, cursor, overflow, overflow_bucket, ext, ext_off, ext_count, cur_all, ext_all;
+	Buf regions, cursor, overflow, overflow_bucket, ext, ext_off, ext_count, cur_all, ext_all, pex, bsum, grp_end;
+	uint64_t count_stream_bytes = 0;   // bytes of the WHOLE read stream of the current build (all ranks)
 	int n_sm = 0, jump_grid = 0;
 	Buf chain_slot, grp_start;
 	Buf seq, ctab, clist, solid_key, solid_cnt, kt_keys, kt_mask, node_ord, node_slot, node_ebase, vL, vR, jump, vsucc,
@@ -176,7 +177,7 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	dist_release(ctx);
-	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
 			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
 	for (Buf *b : bufs)
@@ -329,22 +330,41 @@ static int count_owned(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &
 	const uint32_t n_buckets = 1u << cfg.log2_buckets, world = cfg.world;
 	const uint32_t n_owned = first_bucket >= n_buckets ? 0u : (n_buckets - first_bucket < cfg.per_rank ? n_buckets - first_bucket : cfg.per_rank);
 	const uint32_t group_max = BC::SUB_MAX / world < BC::GROUP_MAX ? BC::SUB_MAX / world : BC::GROUP_MAX;
+	const uint32_t n_scan_blocks = (n_owned + TAGPU_SCAN_BLOCK - 1) / TAGPU_SCAN_BLOCK;
+	// owned windows <= windows of the whole stream <= stream bytes: upper bound of the group ids
+	const uint64_t n_groups_cap = ctx->count_stream_bytes / BC::GROUP_TARGET + 2;
 	if (ensure(ctx, ctx->cur_all, ((size_t)cfg.per_rank * world + 1) * 8) || ensure(ctx, ctx->ext_all, ((size_t)cfg.per_rank * world + 1) * 4) ||
-	    ensure(ctx, ctx->grp_start, ((size_t)cfg.per_rank + 2) * 4))
+	    ensure(ctx, ctx->pex, ((size_t)cfg.per_rank + 1) * 8) || ensure(ctx, ctx->bsum, ((size_t)n_scan_blocks + 1) * 8) ||
+	    ensure(ctx, ctx->grp_start, n_groups_cap * 4) || ensure(ctx, ctx->grp_end, n_groups_cap * 4))
 		return -1;
-	const uint64_t n_pairs = (uint64_t)n_owned * world;
-	if (n_pairs)
-		LAUNCH(k_pull_cursors<W>, (unsigned)((n_pairs + 255) / 256), 256, peers, world, first_bucket, n_owned, n_buckets, cfg.cap_records,
-		       (unsigned long long *)ctx->cur_all.p, (uint32_t *)ctx->ext_all.p);
-	LAUNCH(k_group_buckets, 1, 1024, (const unsigned long long *)ctx->cur_all.p, world, n_owned, (uint32_t)BC::GROUP_TARGET,
-	       group_max, (uint32_t *)ctx->grp_start.p, ctx->d_ctr);
-	LAUNCH_SMEM(k_count_buckets<W>, BC::CTAS_PER_SM * ctx->n_sm, BC::THREADS, BC::SMEM, peers, world, first_bucket, cfg.cap_records,
-		    (const unsigned long long *)ctx->cur_all.p, (const uint32_t *)ctx->ext_all.p, (const uint32_t *)ctx->grp_start.p, cfg.K,
-		    (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p, (unsigned long long)solid_cap, ctx->d_ctr);
+	if (n_owned) {
+		{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->grp_start.p, 0xff, n_groups_cap * 4, ctx->stream)); }
+		LAUNCH(k_pull_cursors<W>, n_scan_blocks, TAGPU_SCAN_BLOCK, peers, world, first_bucket, n_owned, n_buckets, cfg.cap_records,
+		       (unsigned long long *)ctx->cur_all.p, (uint32_t *)ctx->ext_all.p, (unsigned long long *)ctx->pex.p, (unsigned long long *)ctx->bsum.p);
+		LAUNCH(k_scan_blocks, 1, 1024, (unsigned long long *)ctx->bsum.p, n_scan_blocks, (uint32_t)BC::GROUP_TARGET, ctx->d_ctr);
+		LAUNCH(k_mark_groups, n_scan_blocks, TAGPU_SCAN_BLOCK, (const unsigned long long *)ctx->pex.p, (const unsigned long long *)ctx->bsum.p, n_owned,
+		       (uint32_t)BC::GROUP_TARGET, (uint32_t *)ctx->grp_start.p, (uint32_t *)ctx->grp_end.p);
+		LAUNCH_SMEM(k_count_buckets<W>, BC::CTAS_PER_SM * ctx->n_sm, BC::THREADS, BC::SMEM, peers, world, first_bucket, cfg.cap_records,
+			    (const unsigned long long *)ctx->cur_all.p, (const uint32_t *)ctx->ext_all.p, (const uint32_t *)ctx->grp_start.p,
+			    (const uint32_t *)ctx->grp_end.p, group_max, cfg.K, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p,
+			    (unsigned long long)solid_cap, ctx->d_ctr);
+	}
 	if (read_counters(ctx)) return -1;
 	ctx->st.n_distinct = ctx->h_ctr[CTR_DISTINCT];
 	ctx->st.n_solid = ctx->h_ctr[CTR_SOLID];
 	ctx->st.sum_solid = ctx->h_ctr[CTR_SUM_SOLID];
+#ifdef TAGPU_TIMING
+	{
+		const double tot = (double)(ctx->h_ctr[CTR_JUMP_FLAGS + 48] + ctx->h_ctr[CTR_JUMP_FLAGS + 49] + ctx->h_ctr[CTR_JUMP_FLAGS + 50] + ctx->h_ctr[CTR_JUMP_FLAGS + 51] +
+					  ctx->h_ctr[CTR_JUMP_FLAGS + 52] + ctx->h_ctr[CTR_JUMP_FLAGS + 53]);
+		fprintf(stderr, "[tagpu timing] harvest pass A %.1f%%  pass B %.1f%%  rest(copy+syncs) %.1f%%; class iterations %llu, failed %llu\n",
+			100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 52] / tot, 100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 53] / tot, 100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 51] / tot,
+			(unsigned long long)ctx->h_ctr[CTR_JUMP_FLAGS + 54], (unsigned long long)ctx->h_ctr[CTR_JUMP_FLAGS + 55]);
+		fprintf(stderr, "[tagpu timing] k_count_buckets warp-cycles: setup %.1f%%  insert %.1f%%  barrier-wait %.1f%%  harvest %.1f%%  (groups %llu)\n",
+			100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 48] / tot, 100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 49] / tot, 100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 50] / tot,
+			100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 51] / tot, (unsigned long long)ctx->h_ctr[CTR_GROUPS]);
+	}
+#endif
 	if (ctx->st.n_solid > solid_cap) return fail(ctx, "solid (k+1)-mer buffer too small (%llu > %llu)", (unsigned long long)ctx->st.n_solid, (unsigned long long)solid_cap);
 	ctx->cur_solid_key = ctx->solid_key.p;
 	ctx->cur_solid_cnt = ctx->solid_cnt.p;
@@ -358,6 +378,7 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 	typedef BucketCfg<W> BC;
 	const PartCfg cfg = plan_cfg(n, ctx->K, 1, BC::GROUP_TARGET);
 	const uint32_t n_buckets = 1u << cfg.log2_buckets;
+	ctx->count_stream_bytes = n;
 	if (ensure(ctx, ctx->regions, (size_t)n_buckets * cfg.cap_records * sizeof(SkRec<W>)) || ensure(ctx, ctx->cursor, (size_t)n_buckets * 8) ||
 	    ensure(ctx, ctx->overflow, (size_t)cfg.overflow_cap * sizeof(SkRec<W>)) ||
 	    ensure(ctx, ctx->overflow_bucket, (size_t)cfg.overflow_cap * 4) || ensure(ctx, ctx->ext_off, (size_t)(n_buckets + 1) * 4) ||
@@ -570,6 +591,7 @@ extern "C" int tagpu_dist_plan(tagpu_ctx *ctx, int rank, int world, uint64_t n_t
 	DistState *d = new DistState();
 	ctx->dist = d;
 	d->rank = rank; d->world = world; d->n_total = n_total_bytes;
+	ctx->count_stream_bytes = n_total_bytes;
 	d->W = K <= 32 ? 1 : 2;
 	ctx->K = K; ctx->k = k; ctx->W = d->W;
 	d->cfg = plan_cfg(n_total_bytes, K, world, d->W == 1 ? BucketCfg<1>::GROUP_TARGET : BucketCfg<2>::GROUP_TARGET);
