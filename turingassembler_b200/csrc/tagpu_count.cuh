@@ -262,7 +262,7 @@ template <int W> struct BucketCfg {
 	static constexpr int CTAS_PER_SM = 2;
 	// shared-memory table slots per CTA (any number: the home slot is mulhi(hash, SLOTS)); sized so that two CTAs of
 	// table + record staging + static + the 1 KB the hardware reserves per CTA fit the SM's 228 KB
-	static constexpr int SLOTS = W == 1 ? 7936 : 3968;
+	static constexpr int SLOTS = W == 1 ? 7728 : 3840;
 	static constexpr int MAX_PROBES = 48;                       // a longer probe sequence aborts the attempt (re-run on sub-classes)
 	static constexpr int GROUP_MAX = 64;                        // buckets per group
 	static constexpr int SUB_MAX = 256;                         // (bucket, source rank) pairs per group: group_max = min(GROUP_MAX, SUB_MAX / world)
@@ -292,7 +292,7 @@ template <> TAGPU_DI uint32_t tagpu_table_hash<2>(const Key<2> &k)
 // K bases of a right-aligned record value, `sh` bits above its right end (sh <= 62)
 TAGPU_DI Key<1> tagpu_record_window(const SkRec<1> &r, int sh, int K)
 {
-	const unsigned long long w1 = r.w[1] & 0x00ffffffffffffffull;
+	const unsigned long long w1 = r.w[1] & 0x0000ffffffffffffull;   // top 16 bits: window count, multiplicity
 	Key<1> k;
 	k.lo = (uint64_t)((((unsigned __int128)w1 << 64) | r.w[0]) >> sh);
 	if (K < 32) k.lo &= (1ull << (2 * K)) - 1;
@@ -464,10 +464,10 @@ __global__ void __launch_bounds__(TAGPU_SCAN_BLOCK) k_mark_groups(const unsigned
 	if (b + 1 == n_owned) grp_end[g] = n_owned;
 }
 
-// Persistent CTAs pull groups of buckets from a global counter.  Each warp stages a chunk of <= 32 records in shared
-// memory (canonical orientation + the other strand), collapses duplicate records, splits the remaining windows into 32
-// equal contiguous segments (one per lane) and every lane ROLLS the forward / reverse-complement keys through its
-// segment (re-seeding only at record boundaries), inserting the canonical key into the CTA's shared-memory table.
+// Persistent CTAs pull groups of buckets from a global counter.  The CTA stages the group's records in shared memory
+// (canonical orientation, duplicates collapsed), splits the live windows into THREADS equal contiguous segments and every
+// thread ROLLS the forward / reverse-complement keys through its segment (re-seeding only at record boundaries),
+// inserting the canonical key into the CTA's shared-memory table.
 //
 // Per group the CTA meets at five barriers only.  Everything with a global round trip is taken off the critical path:
 // the id of the next group is fetched while the current one is being counted, and the output offset of the harvest
@@ -498,13 +498,13 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 	Key<W> *o_key = reinterpret_cast<Key<W> *>(s_rec);
 	uint32_t *o_cnt = reinterpret_cast<uint32_t *>(o_key + OUT_CAP);
 	constexpr uint32_t TOP_NONE = 0xffffffffu;
-	__shared__ uint32_t s_b0, s_nb, s_bs, s_be, s_top, s_claims, s_overflow, s_next, s_sp, s_warp_solid[C::THREADS / 32], s_stack[64];
+	__shared__ uint32_t s_b0, s_nb, s_bs, s_be, s_top, s_claims, s_overflow, s_sp, s_warp_solid[C::THREADS / 32], s_stack[64];
+	__shared__ uint16_t s_scan[2 * C::THREADS + 2];              // live windows of the round before the k-th live record
+	__shared__ uint16_t s_live[2 * C::THREADS];                  // staged index of the k-th live record
 	__shared__ uint32_t s_rpre[C::SUB_MAX + 1];                  // per (bucket, source) pair of the group: records before it
 	__shared__ unsigned long long s_out_base;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	constexpr uint32_t N_WARPS = C::THREADS / 32;
-	SkRec<W> *my_recs = s_rec + warp * 32;                      // canonical records of the warp's current chunk
-	SkRec<W> *my_rcs = s_rec + C::THREADS + warp * 32;          // ... and their other strand (+ multiplicity in the top byte)
 	const Key<W> kmask = KO::mask(K);
 	const uint32_t n_groups = (uint32_t)ctr[CTR_GROUPS];
 	TM_DECL();
@@ -556,7 +556,7 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 					for (uint32_t c = 1; c < (1u << L); ++c) s_stack[sp++] = (L << 24) | c;
 					s_sp = sp;
 					s_top = L << 24;                                 // class 0 of level L goes first
-					s_claims = 0; s_overflow = 0; s_next = 0;
+					s_claims = 0; s_overflow = 0;
 					s_b0 = b0; s_nb = nb;
 					s_bs = b0 + nb / world; s_be = be;
 				}
@@ -566,98 +566,102 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 		const uint32_t b0 = s_b0, nb = s_nb;                            // nb (bucket, source) pairs <= SUB_MAX
 		if (nb == TAGPU_NONE) break;
 		const uint32_t n_recs = s_rpre[nb];
-		// Work is handed out dynamically in chunks of consecutive records of the group (across its pairs).  The chunk size
-		// (<= 32 records, one per lane) is chosen so that the chunks fill whole waves of the CTA's warps.
-		const uint32_t waves = (n_recs + 32u * N_WARPS - 1u) / (32u * N_WARPS);
-		const uint32_t chunk = max(1u, min(32u, (n_recs + waves * N_WARPS - 1u) / max(1u, waves * N_WARPS)));
 		TM_ADD(tm_setup);
 		for (;;) {                                                  // one iteration per hash class (L, cls) of the group
 			const uint32_t top = s_top;
 			const uint32_t L = top >> 24, cls = top & 0xffffffu;
-			// ---- insert every window of the group that belongs to hash class (L, cls)
-			auto grab = [&](uint32_t &start, uint32_t &n) {
-				uint32_t st = 0;
-				if (lane == 0) st = atomicAdd(&s_next, chunk);
-				st = __shfl_sync(0xffffffffu, st, 0);
-				start = st;
-				n = st < n_recs ? min(chunk, n_recs - st) : 0u;
-			};
-			auto fetch = [&](uint32_t start, uint32_t n, SkRec<W> &out) -> bool {
-				if (lane >= n) return false;
-				const uint32_t g_idx = start + lane;
-				uint32_t lo = 0, hi = nb;                                // pair of record g_idx: last i with s_rpre[i] <= g_idx
-				while (hi - lo > 1) {
-					const uint32_t mid = (lo + hi) >> 1;
-					if (s_rpre[mid] <= g_idx) lo = mid; else hi = mid;
-				}
-				const uint32_t i = lo, g = g_idx - s_rpre[i];
-				uint32_t lb = b0 + i, src = 0;
-				if (world > 1) { lb = b0 + i / world; src = i - (i / world) * world; }
-				const size_t gb = (size_t)first_bucket + lb;                // the source indexes its regions by global bucket id
-				out = g < cap_records ? peers.regions[src][gb * cap_records + g]
-						      : peers.ext[src][ext_all[(size_t)lb * world + src] + (g - cap_records)];
-				return true;
-			};
-			SkRec<W> pre;                                                // software prefetch of the next chunk's records
-			uint32_t c_start, c_n;
-			grab(c_start, c_n);
-			bool have_pre = fetch(c_start, c_n, pre);
-			while (c_n) {
+			// ---- insert every window of the group that belongs to hash class (L, cls).
+			// The CTA works in lock step on rounds of <= 2 * THREADS records: every thread stages two adjacent records
+			// (canonical orientation; duplicates among the 32 records of a warp collapse into one with a multiplicity),
+			// a block-wide prefix sum of the live window counts follows, and then the live windows of the round are cut
+			// into THREADS equal contiguous segments — one per thread, whatever the records look like.
+			const uint32_t n_rounds = (n_recs + 2u * C::THREADS - 1u) / (2u * C::THREADS);
+			const uint32_t per_round = n_rounds ? (n_recs + n_rounds - 1u) / n_rounds : 0u;   // rounds of equal size
+			for (uint32_t rbase = 0; rbase < n_recs; rbase += per_round) {
+				if (rbase) __syncthreads();                         // the previous round's records are no longer needed
 				if (*(volatile uint32_t *)&s_overflow) break;
-				uint32_t my_n = 0, rhash = 0x80000000u | lane;           // lanes without a record never match anybody
-				SkRec<W> canon, other;
-				if (have_pre) {
-					my_n = (uint32_t)(pre.w[2 * W - 1] >> 56);
-					pre.w[2 * W - 1] &= 0x00ffffffffffffffull;
-					const SkRec<W> rc = tagpu_record_rc(pre, (int)my_n + K - 1);
-					const bool swap = tagpu_record_less<W>(rc, pre);
-					canon = swap ? rc : pre;
-					other = swap ? pre : rc;
-					canon.w[2 * W - 1] = (canon.w[2 * W - 1] & 0x00ffffffffffffffull) | ((unsigned long long)my_n << 56);
-					my_recs[lane] = canon;
-					rhash = tagpu_record_hash<W>(canon);
+				const uint32_t n_round = min(per_round, n_recs - rbase);
+				uint32_t n_eff[2];
+#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					const uint32_t idx = 2u * tid + h;
+					const bool have = idx < n_round;
+					uint32_t my_n = 0, rhash = 0x80000000u | lane;   // lanes without a record never match anybody
+					SkRec<W> canon;
+					if (have) {
+						const uint32_t g_idx = rbase + idx;
+						uint32_t lo = 0, hi = nb;                        // pair of record g_idx: last i with s_rpre[i] <= g_idx
+						while (hi - lo > 1) {
+							const uint32_t mid = (lo + hi) >> 1;
+							if (s_rpre[mid] <= g_idx) lo = mid; else hi = mid;
+						}
+						const uint32_t i = lo, g = g_idx - s_rpre[i];
+						uint32_t lb = b0 + i, src = 0;
+						if (world > 1) { lb = b0 + i / world; src = i - (i / world) * world; }
+						const size_t gb = (size_t)first_bucket + lb;     // the source indexes its regions by global bucket id
+						SkRec<W> pre = g < cap_records ? peers.regions[src][gb * cap_records + g]
+									       : peers.ext[src][ext_all[(size_t)lb * world + src] + (g - cap_records)];
+						my_n = (uint32_t)(pre.w[2 * W - 1] >> 56);
+						pre.w[2 * W - 1] &= 0x00ffffffffffffffull;
+						const SkRec<W> rc = tagpu_record_rc(pre, (int)my_n + K - 1);
+						canon = tagpu_record_less<W>(rc, pre) ? rc : pre;
+						canon.w[2 * W - 1] = (canon.w[2 * W - 1] & 0x0000ffffffffffffull) | ((unsigned long long)my_n << 56);
+						s_rec[idx] = canon;
+						rhash = tagpu_record_hash<W>(canon);
+					}
+					const uint32_t peers_eq = __match_any_sync(0xffffffffu, rhash);
+					const uint32_t leader = (uint32_t)__ffs(peers_eq) - 1u;
+					__syncwarp();
+					const bool dup = have && leader != lane && tagpu_record_equal<W>(s_rec[2u * (tid - lane + leader) + h], canon);
+					const uint32_t dup_mask = __ballot_sync(0xffffffffu, dup);
+					if (have && !dup) {                                  // multiplicity in bits 48..55 of the staged record
+						const unsigned long long mult = leader == lane ? 1u + (uint32_t)__popc(peers_eq & dup_mask) : 1u;
+						s_rec[idx].w[2 * W - 1] = canon.w[2 * W - 1] | (mult << 48);
+					}
+					__syncwarp();
+					n_eff[h] = dup ? 0u : my_n;                          // a duplicate is counted through its representative
 				}
-				const uint32_t peers_eq = __match_any_sync(0xffffffffu, rhash);
-				const uint32_t leader = (uint32_t)__ffs(peers_eq) - 1u;
-				__syncwarp();
-				const bool dup = have_pre && leader != lane && tagpu_record_equal<W>(my_recs[leader], canon);
-				const uint32_t dup_mask = __ballot_sync(0xffffffffu, dup);
-				if (have_pre) {
-					const unsigned long long mult = leader == lane ? 1u + (uint32_t)__popc(peers_eq & dup_mask) : 1u;
-					other.w[2 * W - 1] = (other.w[2 * W - 1] & 0x00ffffffffffffffull) | (mult << 56);
-					my_rcs[lane] = other;
-				}
-				if (dup) my_n = 0;                                       // counted through its class representative
-				const uint32_t live = __ballot_sync(0xffffffffu, my_n != 0u);
-				grab(c_start, c_n);
-				have_pre = fetch(c_start, c_n, pre);
-				uint32_t incl = my_n;
+				// block-wide exclusive prefix over the LIVE records only (rank in the high half, windows in the low half of
+				// one packed word): s_live[k] = staged index of the k-th live record, s_scan[k] = live windows before it
+				const uint32_t pair = ((n_eff[0] ? 1u : 0u) + (n_eff[1] ? 1u : 0u)) << 16 | (n_eff[0] + n_eff[1]);
+				uint32_t incl = pair;
 #pragma unroll
 				for (int d = 1; d < 32; d <<= 1) {
 					uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
 					if (lane >= (uint32_t)d) incl += t;
 				}
-				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-				const uint32_t seg = (total + 31) >> 5;
-				const uint32_t t0 = min(total, lane * seg), t1 = min(total, t0 + seg);
-				// owner record of window t0 = number of lanes whose inclusive prefix is <= t0
-				uint32_t r = 0;
+				if (lane == 31) s_warp_solid[warp] = incl;
+				__syncthreads();
+				const uint32_t wt = lane < N_WARPS ? s_warp_solid[lane] : 0u;
+				const uint32_t tot_packed = __reduce_add_sync(0xffffffffu, wt);
+				const uint32_t total = tot_packed & 0xffffu, n_live = tot_packed >> 16;
+				uint32_t excl = __reduce_add_sync(0xffffffffu, lane < warp ? wt : 0u) + incl - pair;
 #pragma unroll
-				for (int step = 16; step; step >>= 1) {
-					const uint32_t e = __shfl_sync(0xffffffffu, incl, (r + step - 1) & 31u);
-					if (e <= t0 && r + step <= 32) r += step;
-				}
-				r &= 31u;
-				const uint32_t r_incl = __shfl_sync(0xffffffffu, incl, r), r_n0 = __shfl_sync(0xffffffffu, my_n, r);
-				__syncwarp();
+				for (int h = 0; h < 2; ++h)
+					if (n_eff[h]) {
+						s_live[excl >> 16] = (uint16_t)(2u * tid + h);
+						s_scan[excl >> 16] = (uint16_t)excl;
+						excl += (1u << 16) + n_eff[h];
+					}
+				if (tid == 0) s_scan[n_live] = (uint16_t)total;
+				__syncthreads();                                    // staged records + prefix visible to everybody
+				const uint32_t seg = (total + C::THREADS - 1) / C::THREADS;
+				const uint32_t t0 = min(total, tid * seg), t1 = min(total, t0 + seg);
 				uint32_t left = t1 - t0;
 				if (left) {
-					int n_r = (int)r_n0, j = (int)(t0 - (r_incl - r_n0));
-					const SkRec<W> *rp = my_recs + r;
+					uint32_t lo = 0, hi = n_live;                        // owner of window t0: last live record k with s_scan[k] <= t0
+					while (hi - lo > 1) {
+						const uint32_t mid = (lo + hi) >> 1;
+						if (s_scan[mid] <= t0) lo = mid; else hi = mid;
+					}
+					uint32_t r = lo;
+					const SkRec<W> *rp = s_rec + s_live[r];
+					unsigned long long wl = rp->w[2 * W - 1];
+					int n_r = (int)(wl >> 56), j = (int)(t0 - s_scan[r]);
+					uint32_t mult = (uint32_t)(wl >> 48) & 0xffu;
 					unsigned long long w0 = rp->w[0];
-					uint32_t mult = (uint32_t)(my_rcs[r].w[2 * W - 1] >> 56);
 					Key<W> fw = tagpu_record_window(*rp, 2 * (n_r - 1 - j), K);
-					Key<W> rv = tagpu_record_window(my_rcs[r], 2 * j, K);
+					Key<W> rv = KO::rc(fw, K);
 					for (;;) {
 						const Key<W> key = KO::le(fw, rv) ? fw : rv;
 						const uint32_t h = tagpu_table_hash<W>(key);
@@ -679,15 +683,15 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 							atomicAdd(t_cnt + slot, mult);
 						}
 						if (!--left) break;
-						if (++j == n_r) {                                    // next live record: re-seed from the staged records
-							r += (uint32_t)__ffs(live >> (r + 1u));
-							rp = my_recs + r;
-							mult = (uint32_t)(my_rcs[r].w[2 * W - 1] >> 56);
-							n_r = (int)(rp->w[2 * W - 1] >> 56);
+						if (++j == n_r) {                                    // next live record: re-seed from the staged record
+							rp = s_rec + s_live[++r];
+							wl = rp->w[2 * W - 1];
+							n_r = (int)(wl >> 56);
+							mult = (uint32_t)(wl >> 48) & 0xffu;
 							j = 0;
 							w0 = rp->w[0];
 							fw = tagpu_record_window(*rp, 2 * (n_r - 1), K);
-							rv = tagpu_record_window(my_rcs[r], 0, K);
+							rv = KO::rc(fw, K);
 						} else {                                             // next window of the same record: roll one base
 							const uint32_t c = (uint32_t)(w0 >> (2 * (n_r - 1 - j))) & 3u;
 							fw = KO::push(fw, c, kmask);
@@ -695,7 +699,6 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 						}
 					}
 				}
-				__syncwarp();
 			}
 			TM_ADD(tm_insert);
 			__syncthreads();                                        // B2: all inserts of this class are in the table
@@ -740,7 +743,7 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 				}
 				s_top = sp ? s_stack[--sp] : TOP_NONE;
 				s_sp = sp;
-				s_claims = 0; s_overflow = 0; s_next = 0;
+				s_claims = 0; s_overflow = 0;
 			}
 			if (!staged) __syncthreads();                           // (rare) the direct path needs s_out_base now
 			const unsigned long long gbase = staged ? 0ull : s_out_base;
