@@ -266,9 +266,10 @@ template <int W> struct BucketCfg {
 	static constexpr int MAX_PROBES = 48;                       // a longer probe sequence aborts the attempt (re-run on sub-classes)
 	static constexpr int GROUP_MAX = 64;                        // buckets per group
 	static constexpr int SUB_MAX = 256;                         // (bucket, source rank) pairs per group: group_max = min(GROUP_MAX, SUB_MAX / world)
-	// a group is closed once it holds this many windows: ~0.3 load if a fifth of the windows are distinct keys (probe
-	// sequences diverge within a warp, so a sparse table is worth more than fewer harvests)
-	static constexpr uint32_t GROUP_TARGET = SLOTS * 3 / 2;
+	// a group is closed once it holds this many windows: ~0.3-0.4 load if a sixth of the windows are distinct keys.
+	// Measured on C1/C2 with 1.5x / 2x / 2.5x / 3x SLOTS: 2x is best for 128-bit keys (3x overflows into re-runs), 2.5x-3x
+	// for 64-bit keys; duplicate-record collapse made inserts cheap relative to the per-group harvest.
+	static constexpr uint32_t GROUP_TARGET = W == 1 ? SLOTS * 5 / 2 : SLOTS * 2;
 	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + 2 * THREADS * sizeof(SkRec<W>);
 };
 
