@@ -132,47 +132,76 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 	}
 	__syncthreads();
 
-	// B. sliding minimum over the w = K - m + 1 m-mers of every window (van Herk / Gil-Werman): positions are cut
-	//    into blocks of w; one thread scans a block backwards (suffix minima -> hs) and forwards (prefix minima, in
-	//    place); min over [q - w + 1, q] is then min(hs[q - w + 1], hp[q]) — two sequential passes instead of log2(w).
+	// B. sliding minimum over the w = K - m + 1 m-mers of every window (van Herk / Gil-Werman): positions are cut into
+	//    blocks of w.  The thread of block b first writes the suffix minima of block b - 1 into hs, then walks block b
+	//    forwards with a running prefix minimum and replaces hs[q - w + 1] by the minimum of window q — so afterwards
+	//    hs[q - w + 1] IS the minimizer of the window ending at q.  Everything a thread writes (the hs region of block
+	//    b - 1) is read only by itself, so the two passes need no barrier between them; hp stays read-only.
 	const int w = K - m + 1;
 	const int n_blocks = (TAGPU_HM_POS + w - 1) / w;
 	for (int blk = threadIdx.x; blk < n_blocks; blk += blockDim.x) {
 		const int lo = blk * w, hi = min(lo + w, TAGPU_HM_POS);
+		// (both passes are unrolled by four with the loads issued first: the chain through `acc` is only the min)
 		uint32_t acc = TAGPU_H_INVALID;
-		for (int q = hi - 1; q >= lo; --q) { acc = min(acc, hp[HIDX(q)]); hs[HIDX(q)] = acc; }
+		int q = lo - 1;
+		const int stop = max(lo - w, 0);
+		for (; q - 3 >= stop; q -= 4) {
+			const uint32_t h0 = hp[HIDX(q)], h1 = hp[HIDX(q - 1)], h2 = hp[HIDX(q - 2)], h3 = hp[HIDX(q - 3)];
+			const uint32_t a0 = min(acc, h0), a1 = min(a0, h1), a2 = min(a1, h2), a3 = min(a2, h3);
+			hs[HIDX(q)] = a0; hs[HIDX(q - 1)] = a1; hs[HIDX(q - 2)] = a2; hs[HIDX(q - 3)] = a3;
+			acc = a3;
+		}
+		for (; q >= stop; --q) { acc = min(acc, hp[HIDX(q)]); hs[HIDX(q)] = acc; }
 		acc = TAGPU_H_INVALID;
-		for (int q = lo; q < hi; ++q) { acc = min(acc, hp[HIDX(q)]); hp[HIDX(q)] = acc; }
+		q = lo;
+		// windows q = lo .. hi - 1 store at sidx = q - w + 1; the last one of a full block (sidx == lo) is the block minimum:
+		// the first suffix minimum the thread of block b + 1 writes to the same slot (same value, never read here)
+		if (lo - w + 1 >= 0)
+			for (; q + 3 < hi && q + 3 - w + 1 < lo; q += 4) {
+				const int sidx = q - w + 1;
+				const uint32_t h0 = hp[HIDX(q)], h1 = hp[HIDX(q + 1)], h2 = hp[HIDX(q + 2)], h3 = hp[HIDX(q + 3)];
+				const uint32_t s0 = hs[HIDX(sidx)], s1 = hs[HIDX(sidx + 1)], s2 = hs[HIDX(sidx + 2)], s3 = hs[HIDX(sidx + 3)];
+				const uint32_t a0 = min(acc, h0), a1 = min(a0, h1), a2 = min(a1, h2), a3 = min(a2, h3);
+				hs[HIDX(sidx)] = min(a0, s0); hs[HIDX(sidx + 1)] = min(a1, s1); hs[HIDX(sidx + 2)] = min(a2, s2); hs[HIDX(sidx + 3)] = min(a3, s3);
+				acc = a3;
+			}
+		for (; q < hi; ++q) {
+			acc = min(acc, hp[HIDX(q)]);
+			const int sidx = q - w + 1;
+			if (sidx == lo) hs[HIDX(sidx)] = acc;
+			else if (sidx >= 0) hs[HIDX(sidx)] = min(acc, hs[HIDX(sidx)]);
+		}
 	}
 	__syncthreads();
 
 	// C1. per word: which positions end a valid window (vw) and which of those start a new run (bw): the window before
 	//     is invalid or has another minimizer occurrence.  With w > 32 a run could outgrow a record, so word starts cut too.
-	uint32_t n_win = 0;
+	//     The valid mask is bit-parallel: a window is valid iff no invalid base lies in the K positions it covers, i.e.
+	//     the invalid masks of this word and the two before it, OR-smeared over K positions (log steps).
 	static_assert(TAGPU_TILE_THREADS >= TAGPU_SMEM_WORDS, "per-word phases assume one word per thread");
+	uint32_t n_win = 0;
 	for (int j = threadIdx.x + 1; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
-		const uint32_t i1 = inv[j - 1], i2 = j >= 2 ? inv[j - 2] : 0xffffffffu;
-		int run = i1 ? (__ffs(i1) - 1) : 32 + (i2 ? (__ffs(i2) - 1) : 32);
-		uint32_t iv = inv[j];
-		bool pv = run >= K;
-		uint32_t pm = pv ? min(hs[HIDX(j * 32 - w)], hp[HIDX(j * 32 - 1)]) : 0u;
-		uint32_t vmask = 0, bmask = 0;
-#pragma unroll 4
+		uint32_t a = j >= 2 ? inv[j - 2] : 0xffffffffu, b = inv[j - 1], c = inv[j];     // position order a:b:c, first position = MSB
+		auto smear = [&](int sft) {                                  // x |= x >> sft over the 96-bit sequence, 0 < sft < 32
+			const uint32_t nc = __funnelshift_r(c, b, sft), nb_ = __funnelshift_r(b, a, sft), na = a >> sft;
+			c |= nc; b |= nb_; a |= na;
+		};
+		smear(1); smear(2); smear(4); smear(8);                      // 16 positions
+		int extra = K - 16;
+		if (K >= 32) { smear(16); extra = K - 32; }                  // 32 positions
+		if (extra == 32) { c |= b; b |= a; }
+		else if (extra > 0) smear(extra);
+		const uint32_t vmask = __brev(~c);                          // bit i = position i of this word ends a valid window
+		const uint32_t pv = ~b & 1u;                                // ... and so does the last position of the word before
+		const int q0 = j * 32 - w + 1;                              // hs index of the window ending at this word's position 0
+		uint32_t pm = hs[HIDX(max(q0 - 1, 0))], ne = 0;
+#pragma unroll
 		for (int i = 0; i < 32; ++i) {
-			const bool bad = (int)iv < 0;
-			iv <<= 1;
-			run = bad ? 0 : run + 1;
-			const bool v = run >= K;
-			uint32_t cm = 0;
-			if (v) {
-				const int q = j * 32 + i;
-				cm = min(hs[HIDX(q - w + 1)], hp[HIDX(q)]);
-				vmask |= 1u << i;
-				if (!pv || cm != pm || (w > 32 && i == 0)) bmask |= 1u << i;
-			}
-			pv = v;
+			const uint32_t cm = hs[HIDX(max(q0 + i, 0))];
+			ne |= (cm != pm ? 1u : 0u) << i;
 			pm = cm;
 		}
+		const uint32_t bmask = vmask & (~((vmask << 1) | pv) | ne | (w > 32 ? 1u : 0u));
 		vw[j] = vmask;
 		bw[j] = bmask;
 		if (j >= TAGPU_HALO_WORDS && j < TAGPU_HALO_WORDS + TAGPU_TILE_WORDS) n_win += __popc(vmask);
@@ -197,7 +226,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 		const int st = upto ? 31 - __clz(upto) : -1 - __clz(Bprev);
 		const int nw = e - st + 1, end_q = wi * 32 + e;
 		if (nw > 32) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_RUN_LENGTH); continue; }
-		const uint32_t b = tagpu_bucket_of(min(hs[HIDX(end_q - w + 1)], hp[HIDX(end_q)]) >> 6, cfg.log2_buckets);
+		const uint32_t b = tagpu_bucket_of(hs[HIDX(end_q - w + 1)] >> 6, cfg.log2_buckets);
 		const SkRec<W> rec = tagpu_make_record<W>(pk, end_q, nw + K - 1, nw);
 		const unsigned long long old = atomicAdd(cursor + b, 1ull | ((unsigned long long)nw << 32));
 		const uint32_t idx = (uint32_t)old;
