@@ -215,6 +215,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = os.environ.get("TAGPU_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -235,7 +236,6 @@ def main():
     n_stream = d_stream.numel()
     h_stream = torch.empty(n_stream, dtype=torch.uint8, pin_memory=True)
     h_stream.copy_(d_stream)
-    d_e2e = torch.empty_like(d_stream) if world > 1 else None
     torch.cuda.synchronize()
 
     t = Tagpu(local_rank)
@@ -254,8 +254,7 @@ def main():
     def step_host():
         # end to end: this rank's reads start in pinned HOST memory; H2D copy, build, stats back to the host
         if world > 1:
-            d_e2e.copy_(h_stream, non_blocking=True)
-            return dt.build(d_e2e.data_ptr(), n_stream)
+            return dt.build(h_stream.data_ptr(), n_stream, host=True)
         return t.build_host((h_stream.data_ptr(), n_stream), k)
 
     def barrier():
@@ -307,6 +306,10 @@ def main():
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms, ms_e2e = tm.tolist()
+    if world > 1:
+        dt.close()
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     n_inst = st["n_instances"]

@@ -80,7 +80,8 @@ const char *tagpu_profile_json(tagpu_ctx *ctx);
 /* Count + build from a flat byte stream already in device memory ('\n' or any non-ACGT byte between reads).
  * Results stay on the device until copied.  k = node k-mer size (17..63); returns 0 on success. */
 int tagpu_build_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_bytes, int k);
-/* Same from host memory: copies the stream to the device inside the call. */
+/* Same from host memory: the stream is uploaded inside the call, in chunks overlapped with the partition pass
+ * (pass pinned memory — e.g. from tagpu_load_reads — for the copy to be asynchronous). */
 int tagpu_build_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n_bytes, int k);
 /* Counting stage only (what KMC_build_kmer_database needs); ksize_plus_1 = K = k + 1 */
 int tagpu_count_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_bytes, int ksize_plus_1);
@@ -126,6 +127,8 @@ int tagpu_write_kmc_db(tagpu_ctx *ctx, const char *working_dir);   /* KMC_<K>_co
 int tagpu_dist_plan(tagpu_ctx *ctx, int rank, int world, uint64_t n_total_bytes, int k, void *handle_out);
 int tagpu_dist_connect(tagpu_ctx *ctx, const void *all_handles /* world x TAGPU_IPC_HANDLE_BYTES, rank order */);
 int tagpu_dist_partition(tagpu_ctx *ctx, const uint8_t *d_seq_local, uint64_t n_local_bytes);
+/* same, with this rank's slice still in (pinned) host memory: the upload is overlapped with pass 1 */
+int tagpu_dist_partition_host(tagpu_ctx *ctx, const uint8_t *h_seq_local, uint64_t n_local_bytes);
 int tagpu_dist_count(tagpu_ctx *ctx, uint64_t stats_out[4]);
 int tagpu_dist_graph(tagpu_ctx *ctx, const uint64_t *all_stats /* world x 4, rank order */, int with_graph);
 /* Teardown / re-plan: every rank calls tagpu_dist_disconnect (unmaps the peers' arenas) -> BARRIER -> tagpu_dist_close or a

@@ -160,6 +160,8 @@ def load_library() -> C.CDLL:
     lib.tagpu_dist_connect.argtypes = [vp, vp]
     lib.tagpu_dist_partition.restype = i32
     lib.tagpu_dist_partition.argtypes = [vp, vp, u64]
+    lib.tagpu_dist_partition_host.restype = i32
+    lib.tagpu_dist_partition_host.argtypes = [vp, vp, u64]
     lib.tagpu_dist_count.restype = i32
     lib.tagpu_dist_count.argtypes = [vp, C.POINTER(u64)]
     lib.tagpu_dist_graph.restype = i32
@@ -260,6 +262,9 @@ class Tagpu:
 
     def dist_partition(self, d_ptr: int, n_local_bytes: int):
         self._check(self.lib.tagpu_dist_partition(self.ctx, C.c_void_p(d_ptr), n_local_bytes))
+
+    def dist_partition_host(self, h_ptr: int, n_local_bytes: int):
+        self._check(self.lib.tagpu_dist_partition_host(self.ctx, C.c_void_p(h_ptr), n_local_bytes))
 
     def dist_count(self):
         out = (C.c_uint64 * 4)()

@@ -91,7 +91,7 @@ TAGPU_DI SkRec<W> tagpu_make_record(const uint64_t *pk, int end_q, int n_bases, 
 // last position.
 template <int W>
 __global__ void __launch_bounds__(TAGPU_TILE_THREADS)
-k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *__restrict__ regions,
+k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg cfg, SkRec<W> *__restrict__ regions,
 	    unsigned long long *__restrict__ cursor, SkRec<W> *__restrict__ overflow, uint32_t *__restrict__ overflow_bucket,
 	    unsigned long long *ctr)
 {
@@ -104,7 +104,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, PartCfg cfg, SkRec<W> *
 	uint32_t *hs = hp + TAGPU_HM_LEN;                   // block-wise suffix minima
 	const int K = cfg.K, m = TAGPU_MINIMIZER_M;
 
-	tagpu_load_tile(seq, n, (uint64_t)blockIdx.x * TAGPU_TILE_BASES, pk, inv);
+	tagpu_load_tile(seq, n, ((uint64_t)blockIdx.x + tile0) * TAGPU_TILE_BASES, pk, inv);
 	__syncthreads();
 
 	// A. hash of the canonical m-mer ending at every position (invalid if the m-mer touches a non-ACGT byte), with the

@@ -18,6 +18,9 @@
 #include "tagpu_graph.cuh"
 #include "tagpu_key.cuh"
 
+constexpr int TAGPU_UPLOAD_CHUNKS = 16;      // pieces the host read stream is uploaded in (copy overlapped with pass 1)
+constexpr int TAGPU_UPLOAD_CHUNKS_MAX = 32;
+
 struct Buf {
 	void *p = nullptr;
 	size_t cap = 0;
@@ -26,7 +29,9 @@ struct Buf {
 struct DistState;
 struct tagpu_ctx {
 	int device = 0;
-	cudaStream_t stream = nullptr, own_stream = nullptr;
+	cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
+	cudaEvent_t ev_chunk[TAGPU_UPLOAD_CHUNKS_MAX];
+	const uint8_t *h_src = nullptr;    // host source of the read stream while its upload is pending (tagpu_*_host calls)
 	int ci = 2, skip_counts = 0;
 	int k = 0, K = 0, W = 0;
 	char err[512] = { 0 };
@@ -165,6 +170,8 @@ extern "C" tagpu_ctx *tagpu_create(int device)
 	ctx->stream = ctx->own_stream;
 	cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
 	for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+	cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+	for (int i = 0; i < TAGPU_UPLOAD_CHUNKS_MAX; ++i) cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
 	memset(&ctx->st, 0, sizeof(ctx->st));
 	return ctx;
 }
@@ -185,6 +192,8 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	cudaFree(ctx->d_ctr);
 	cudaFreeHost(ctx->h_ctr);
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
+	for (int i = 0; i < TAGPU_UPLOAD_CHUNKS_MAX; ++i) cudaEventDestroy(ctx->ev_chunk[i]);
+	cudaStreamDestroy(ctx->copy_stream);
 	for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
@@ -300,9 +309,30 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 	}
 	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)n_buckets * 8, ctx->stream)); }
 	const uint64_t n_tiles = (n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES;
-	if (n_tiles)
-		LAUNCH_SMEM(k_partition<W>, (unsigned)n_tiles, TAGPU_TILE_THREADS, smem1, d_seq, n, cfg, (SkRec<W> *)ctx->regions.p,
+	if (n_tiles && !ctx->h_src) {
+		LAUNCH_SMEM(k_partition<W>, (unsigned)n_tiles, TAGPU_TILE_THREADS, smem1, d_seq, n, 0u, cfg, (SkRec<W> *)ctx->regions.p,
 			    (unsigned long long *)ctx->cursor.p, (SkRec<W> *)ctx->overflow.p, (uint32_t *)ctx->overflow_bucket.p, ctx->d_ctr);
+	} else if (n_tiles) {
+		// The reads are still in host memory (d_seq is our staging buffer): upload them in chunks on a second stream and
+		// run pass 1 over every chunk as soon as it has landed, so the PCIe copy hides the partition pass.  A tile needs
+		// one word of look-ahead, so a launch covers the tiles whose right halo is already on the device.
+		const uint64_t chunk_tiles = n_tiles / TAGPU_UPLOAD_CHUNKS + 1;
+		const uint8_t *h_src = ctx->h_src;
+		ctx->h_src = nullptr;
+		uint64_t copied = 0, tile0 = 0;
+		for (int c = 0; tile0 < n_tiles; ++c) {
+			const uint64_t tile1 = tile0 + chunk_tiles < n_tiles ? tile0 + chunk_tiles : n_tiles;
+			const uint64_t want = tile1 == n_tiles ? n : tile1 * TAGPU_TILE_BASES + 32 * TAGPU_RHALO_WORDS;
+			if (want > copied) CU(cudaMemcpyAsync((uint8_t *)ctx->seq.p + copied, h_src + copied, want - copied, cudaMemcpyHostToDevice, ctx->copy_stream));
+			copied = want > copied ? want : copied;
+			CU(cudaEventRecord(ctx->ev_chunk[c % TAGPU_UPLOAD_CHUNKS_MAX], ctx->copy_stream));
+			CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c % TAGPU_UPLOAD_CHUNKS_MAX], 0));
+			LAUNCH_SMEM(k_partition<W>, (unsigned)(tile1 - tile0), TAGPU_TILE_THREADS, smem1, d_seq, n, (uint32_t)tile0, cfg, (SkRec<W> *)ctx->regions.p,
+				    (unsigned long long *)ctx->cursor.p, (SkRec<W> *)ctx->overflow.p, (uint32_t *)ctx->overflow_bucket.p, ctx->d_ctr);
+			tile0 = tile1;
+		}
+	}
+	ctx->h_src = nullptr;
 	if (read_counters(ctx)) return -1;
 	ctx->st.n_instances = ctx->h_ctr[CTR_INSTANCES];
 	const uint64_t n_over = ctx->h_ctr[CTR_SPARE0];
@@ -645,7 +675,23 @@ extern "C" int tagpu_dist_connect(tagpu_ctx *ctx, const void *all_handles)
 	return 0;
 }
 
+static int dist_partition_impl(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_local_bytes);
+static int upload(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n);
+
 extern "C" int tagpu_dist_partition(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_local_bytes)
+{
+	ctx->h_src = nullptr;
+	return dist_partition_impl(ctx, d_seq, n_local_bytes);
+}
+
+// same with this rank's slice of the reads still in (pinned) host memory: the upload is overlapped with pass 1
+extern "C" int tagpu_dist_partition_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n_local_bytes)
+{
+	if (upload(ctx, h_seq, n_local_bytes)) return -1;
+	return dist_partition_impl(ctx, (const uint8_t *)ctx->seq.p, n_local_bytes);
+}
+
+static int dist_partition_impl(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_local_bytes)
 {
 	DistState *d = ctx->dist;
 	if (!d || !d->connected) return fail(ctx, "tagpu_dist_partition before tagpu_dist_plan / tagpu_dist_connect");
@@ -755,12 +801,17 @@ static int upload(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n)
 {
 	CU(cudaSetDevice(ctx->device));
 	if (ensure(ctx, ctx->seq, n + 64)) return -1;
-	if (n) CU(cudaMemcpyAsync(ctx->seq.p, h_seq, n, cudaMemcpyHostToDevice, ctx->stream));
+	static const bool direct = getenv("TAGPU_COUNT_DIRECT") != nullptr;
+	if (direct) {
+		if (n) CU(cudaMemcpyAsync(ctx->seq.p, h_seq, n, cudaMemcpyHostToDevice, ctx->stream));
+	} else {
+		ctx->h_src = h_seq;            // uploaded chunk by chunk inside partition_local, overlapped with pass 1
+	}
 	return 0;
 }
 
-extern "C" int tagpu_build_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int k) { return run(ctx, d_seq, n, k + 1, true); }
-extern "C" int tagpu_count_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K) { return run(ctx, d_seq, n, K, false); }
+extern "C" int tagpu_build_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int k) { ctx->h_src = nullptr; return run(ctx, d_seq, n, k + 1, true); }
+extern "C" int tagpu_count_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K) { ctx->h_src = nullptr; return run(ctx, d_seq, n, K, false); }
 extern "C" int tagpu_build_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n, int k)
 {
 	if (upload(ctx, h_seq, n)) return -1;

@@ -54,10 +54,14 @@ class DistTagpu:
         self.dist.all_reduce(self._flag, group=self.group)
         self._sync()
 
-    def build(self, d_ptr: int, n_local_bytes: int, with_graph: bool = True) -> dict:
-        """One pass of the hot path over this rank's slice of the reads; returns the GLOBAL stats on every rank."""
+    def build(self, ptr: int, n_local_bytes: int, with_graph: bool = True, host: bool = False) -> dict:
+        """One pass of the hot path over this rank's slice of the reads (device address, or pinned host address with
+        host=True); returns the GLOBAL stats on every rank."""
         t = self.t
-        t.dist_partition(d_ptr, n_local_bytes)
+        if host:
+            t.dist_partition_host(ptr, n_local_bytes)
+        else:
+            t.dist_partition(ptr, n_local_bytes)
         self.barrier()
         local = t.dist_count()
         all_stats = gather_stats(self.dist, self._stats, self._all, local, self.group)
