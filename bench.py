@@ -118,59 +118,34 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(host_stream, k, target_s=15.0):
-    """The oracle's multithreaded KMC-stage restatement + graph restatement, timed on a bounded sample of the same
-    workload on this box's host cores (kind 'port')."""
-    import numpy as np
-    import _oracle
-    ora = _oracle.load()
-    cores = os.cpu_count() or 1
-    n_reads_total = host_stream.size // (L + 1)
-    n_reads = min(n_reads_total, 400_000)
-    # same coverage profile as the full set: take R1 and R2 halves proportionally
-    half = n_reads_total // 2
-    take = n_reads // 2
-    sample = np.concatenate([host_stream[: take * (L + 1)], host_stream[half * (L + 1): (half + take) * (L + 1)]])
-    t0 = time.perf_counter()
-    cnt = ora.count(sample, k + 1, ci=2, threads=cores)
-    t1 = time.perf_counter()
-    g = ora.graph(k, cnt["hi"], cnt["lo"], cnt["count"])
-    t2 = time.perf_counter()
-    ora.free_graph(g)
-    return {"value": cnt["n_instances"] / (t2 - t0), "unit": "kmers/s", "cores": cores, "kind": "port",
-            "sample": f"{2 * take} of {n_reads_total} reads ({cnt['n_instances']} (k+1)-mer instances): count {t1 - t0:.2f} s on "
-                      f"{cores} threads + graph {t2 - t1:.2f} s on 1 thread"}
-
-
-def run_reference(args):
-    """--impl reference: the reference's own CPU implementation (oracle/_ref/TA_ref build_0 = unmodified reference
-    sources + oracle/kmc_cpu.c for the absent libkmc.a; else the oracle port) on a bounded sample, all host threads."""
-    import numpy as np
+def reference_cpu(workload, steps, warmup):
+    """Times the reference's own CPU implementation of the path on this box's host cores, all threads, on a BOUNDED sample
+    of the workload (same read length, error model and coverage; a fifth of the genome and of the reads):
+    oracle/_ref/TA_ref build_0 = the unmodified reference sources + oracle/kmc_cpu.c standing in for the absent libkmc.a
+    (kind "reference"); the oracle port's own driver if that binary was not built (kind "port").
+    FASTQ files on a RAM disk -> graph_k_<k>_level_0.bin, i.e. the reference's whole stage including its file I/O."""
     import _oracle
     import _reads
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS[workload]
     cores = os.cpu_count() or 1
-    n_pairs = min(wl["n_pairs"], 100_000)
-    stream = _reads.gen_stream(wl["genome_len"] // 20, n_pairs, seed=wl["seed"], n_repeats=2)
+    n_pairs = min(wl["n_pairs"], 400_000)
+    genome_len = max(wl["genome_len"] * n_pairs // wl["n_pairs"], 20_000)
+    stream = _reads.gen_stream(genome_len, n_pairs, seed=wl["seed"], n_repeats=8)
     reads = stream.reshape(-1, L + 1)[:, :L]
     ora = _oracle.load()
     n_inst = ora.count(stream, wl["k"] + 1, ci=2, threads=cores)["n_instances"]
     have_ref = os.path.exists(_oracle.TA_REF)
+    exe = _oracle.TA_REF if have_ref else os.path.join(ROOT, "oracle", "ta_oracle")
     times = []
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
         f1, f2 = os.path.join(td, "R1.fq"), os.path.join(td, "R2.fq")
+        q = b"+\n" + b"I" * L + b"\n"
         for path, block, mate in ((f1, reads[:n_pairs], 1), (f2, reads[n_pairs:], 2)):
             with open(path, "wb") as f:
-                q = b"I" * L
-                for i, r in enumerate(block):
-                    f.write(b"@r%d/%d\n" % (i, mate) + r.tobytes() + b"\n+\n" + q + b"\n")
-        for step in range(args.warmup + args.steps):
+                f.write(b"".join(b"@r%d/%d\n" % (i, mate) + r.tobytes() + b"\n" + q for i, r in enumerate(block)))
+        for step in range(warmup + steps):
             out = os.path.join(td, f"out{step}")
             os.makedirs(out)
-            exe = _oracle.TA_REF if have_ref else os.path.join(ROOT, "oracle", "ta_oracle")
             cmd = [exe, "build_0", "-1", f1, "-2", f2, "-l", "ust", "-k0", str(wl["k"]), "-t", str(cores), "-o", out]
             t0 = time.perf_counter()
             p = subprocess.run(cmd, capture_output=True, text=True)
@@ -178,19 +153,28 @@ def run_reference(args):
             if p.returncode != 0:
                 sys.stderr.write((p.stdout + p.stderr)[-2000:])
                 raise SystemExit(1)
-            if step >= args.warmup:
+            subprocess.run(["rm", "-rf", out])
+            if step >= warmup:
                 times.append(dt)
     sec = sum(times) / len(times)
-    val = n_inst / sec
-    sample = (f"{2 * n_pairs} reads x {L} bp from a {wl['genome_len'] // 20} bp genome ({n_inst} (k+1)-mer instances), "
+    sample = (f"{2 * n_pairs} reads x {L} bp from a {genome_len} bp genome ({n_inst} (k+1)-mer instances), "
               f"FASTQ files -> graph_k_{wl['k']}_level_0.bin via build_0 -t {cores}")
+    return {"value": n_inst / sec, "unit": "kmers/s", "cores": cores, "kind": "reference" if have_ref else "port", "sample": sample}, sec
+
+
+def run_reference(args):
+    """--impl reference: see reference_cpu(); rank 0 alone runs and prints, the other ranks exit without work."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    base, sec = reference_cpu(args.workload, args.steps, args.warmup)
     print(json.dumps({
-        "impl": "reference", "metric": "kmers_per_sec_counted_and_graph_built", "value": val, "unit": "kmers/s",
+        "impl": "reference", "metric": "kmers_per_sec_counted_and_graph_built", "value": base["value"], "unit": "kmers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u128" if wl["k"] + 1 > 32 else "u64", "data": "synthetic",
-        "config": {"workload": f"{args.workload} (bounded sample): {sample}"},
-        "cpu_baseline": {"value": val, "unit": "kmers/s", "cores": cores, "kind": "reference" if have_ref else "port", "sample": sample},
-        "e2e": {"value": val, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": f"{args.workload} (bounded sample): {base['sample']}"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
@@ -356,7 +340,7 @@ def main():
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(h_stream.numpy(), k)
+        line["cpu_baseline"] = reference_cpu(args.workload, 2, 1)[0]
     print(json.dumps(line))
 
 
