@@ -203,3 +203,29 @@ def test_dropin_reference_binary(oracle, tmp_path):
         assert f"sum_count = {gold['sum_count']}" in log
         bad, txt = _oracle.canon_text(oracle, str(out / f"graph_k_{k}_level_0.bin"), 0)
         assert bad == 0 and hashlib.md5(txt).hexdigest() == gold["canon0_md5"]
+
+
+def test_bucket_overflow_path(oracle, tmp_path):
+    """TAGPU_REGION_CAP=4 leaves room for four records per bucket region, so nearly every super-k-mer record takes the
+    overflow route (overflow list -> histogram -> scan -> scatter -> read back through ext_off in pass 2).  Runs in a
+    subprocess because the knob is read once per process."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {repr(os.path.dirname(HERE))}); sys.path.insert(0, {repr(HERE)})\n"
+        "import _oracle, _reads\n"
+        "from turingassembler_b200 import Tagpu\n"
+        "t = Tagpu(); ora = _oracle.load()\n"
+        "for k, seed in ((31, 3), (45, 4)):\n"
+        "    s = _reads.gen_stream(120000, 12000, seed=seed)\n"
+        "    st = t.build_host(s, k); want = ora.count(s, k + 1)\n"
+        "    hi, lo, cnt = t.solid(); o = np.lexsort((lo, hi))\n"
+        "    assert st['n_instances'] == want['n_instances'] and st['n_distinct'] == want['n_distinct']\n"
+        "    assert np.array_equal(hi[o], want['hi']) and np.array_equal(lo[o], want['lo']) and np.array_equal(cnt[o], want['count'])\n"
+        "    g = ora.graph(k, want['hi'], want['lo'], want['count'])\n"
+        "    assert (st['n_kmers'], st['n_v'], st['n_e']) == (g.contents.n_kmer, g.contents.n_v, g.contents.n_e)\n"
+        "print('OVERFLOW-OK')\n")
+    env = dict(os.environ, TAGPU_REGION_CAP="4")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0 and "OVERFLOW-OK" in p.stdout, (p.stdout + p.stderr)[-3000:]

@@ -286,11 +286,16 @@ static PartCfg plan_cfg(uint64_t n_total, int K, int world, uint32_t group_targe
 	PartCfg cfg;
 	cfg.K = K;
 	cfg.log2_buckets = log2p;
-	// region capacity at each source: measured max bucket ~6x the mean (one record per ~8 windows); the rest spills
-	cfg.cap_records = (uint32_t)(n_source / 8 / n_buckets * 6 + 64);
+	// region capacity at each source: ~5x the mean bucket (a super-k-mer record holds ~14 windows on 151 bp reads; the
+	// estimate assumes 10); what does not fit spills to the overflow list, which is sorted by bucket after the pass.
+	// TAGPU_REGION_CAP overrides it (tests use a tiny value to drive everything through the overflow path).
+	cfg.cap_records = (uint32_t)(n_source / 10 / n_buckets * 5 + 64);
+	static const char *cap_env = getenv("TAGPU_REGION_CAP");
+	if (cap_env && atoi(cap_env) > 0) cfg.cap_records = (uint32_t)atoi(cap_env);
 	cfg.world = (uint32_t)world;
 	cfg.per_rank = (uint32_t)((n_buckets + world - 1) / world);
 	cfg.overflow_cap = (uint32_t)(n_source / 16 + 4096);
+	if (cap_env && atoi(cap_env) > 0) cfg.overflow_cap = (uint32_t)(n_source / 4 + 4096);
 	return cfg;
 }
 
