@@ -9,6 +9,8 @@
 #   TA_gpu      same objects, but build_initial_graph / build_graph_from_scratch(_without_count)
 #               and KMC_build_kmer_database resolve to libtagpu.so (drop-in test; only built when
 #               ../turingassembler_b200/libtagpu.so exists)
+#   TA_kmc      all reference objects unmodified, libtagpu.so only replaces libkmc.a
+#               (KMC_build_kmer_database on the GPU, the reference's own reader and graph code after it)
 set -e
 REF=${1:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
@@ -50,4 +52,10 @@ if [ -f "$TAGPU" ]; then
 	g++ -pthread -o "$OUT/TA_gpu" $OBJS "$OUT/obj/dropin_kmer_build.o" \
 		-L "$HERE/../turingassembler_b200" -ltagpu -Wl,-rpath,'$ORIGIN/../../turingassembler_b200' $LIBS
 	echo "built $OUT/TA_gpu"
+	# Library-boundary drop-in (INTEGRATION.md option B): ALL reference objects untouched — its own
+	# build_graph_from_scratch, KMC_reader, kmhash ... — and libtagpu.so only in place of libkmc.a, i.e. the GPU
+	# writes the KMC database and the reference's reader / graph builder consume it.
+	g++ -pthread -o "$OUT/TA_kmc" $(ls "$OUT"/obj/src_*.o) \
+		-L "$HERE/../turingassembler_b200" -ltagpu -Wl,-rpath,'$ORIGIN/../../turingassembler_b200' $LIBS
+	echo "built $OUT/TA_kmc"
 fi

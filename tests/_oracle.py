@@ -10,6 +10,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 TA_REF = os.path.join(ORACLE_DIR, "_ref", "TA_ref")
 TA_GPU = os.path.join(ORACLE_DIR, "_ref", "TA_gpu")
+TA_KMC = os.path.join(ORACLE_DIR, "_ref", "TA_kmc")
 
 
 class OraGraph(C.Structure):

@@ -229,3 +229,29 @@ def test_bucket_overflow_path(oracle, tmp_path):
     env = dict(os.environ, TAGPU_REGION_CAP="4")
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert p.returncode == 0 and "OVERFLOW-OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
+@pytest.mark.skipif(not os.path.exists(_oracle.TA_KMC), reason="oracle/_ref/TA_kmc (reference + libtagpu.so in place of libkmc.a) not built")
+def test_dropin_library_boundary(oracle, tmp_path):
+    """INTEGRATION.md option B: every reference object unmodified, libtagpu.so only supplies KMC_build_kmer_database.
+    The GPU writes KMC_<k+1>_count.kmc_pre/.kmc_suf; the reference's own KMC_read_prefix / KMC_retrieve_kmer_multi parse
+    them and its own kmhash / build_asm_graph_from_kmhash / assign_count_kedge_multi build the graph from them — which
+    must be the graph of the golden vectors (rows a1-a3 of SURVEY.md §8)."""
+    import subprocess
+    from _cases import CASES, reads_for
+    r1, r2 = reads_for(*CASES["P1"][:2])
+    f1, f2 = str(tmp_path / "R1.fq"), str(tmp_path / "R2.fq")
+    _reads.write_fastq(f1, r1, 1)
+    _reads.write_fastq(f2, r2, 2)
+    for k in (31, 45):
+        out = tmp_path / f"o{k}"
+        out.mkdir()
+        p = subprocess.run([_oracle.TA_KMC, "build_0", "-1", f1, "-2", f2, "-l", "ust", "-k0", str(k), "-t", "4", "-o", str(out)],
+                           capture_output=True, text=True)
+        log = p.stdout + p.stderr
+        assert p.returncode == 0, log[-3000:]
+        gold = GOLDEN[f"P1_k{k}"]
+        assert f"Number of kmer: {gold['n_kmers']}" in log and f"sum_count = {gold['sum_count']}" in log
+        assert (out / f"KMC_{k + 1}_count.kmc_suf").exists()
+        bad, txt = _oracle.canon_text(oracle, str(out / f"graph_k_{k}_level_0.bin"), 0)
+        assert bad == 0 and hashlib.md5(txt).hexdigest() == gold["canon0_md5"]
