@@ -44,6 +44,12 @@ void build_graph_from_scratch_without_count(int ksize, int n_threads, int mmem, 
 /* /root/reference/src/assembly_graph.h:141, body /root/reference/src/kmer_build.c:839-845 */
 void build_initial_graph(struct opt_proc_t *opt, int ksize, struct asm_graph_t *g);
 
+/* /root/reference/src/assembly_graph.h:160-162, body /root/reference/src/kmer_build.c:991-1044 — the same stage re-entered per
+ * gap by local assembly, with the two flanking edges of the global graph forced in */
+void build_local_assembly_graph(int ksize, int n_threads, int mmem, int n_files,
+				char **files_1, char **files_2, char *work_dir, struct asm_graph_t *g,
+				struct asm_graph_t *g0, int64_t e1, int64_t e2);
+
 /* ------------------------------------------------------------------ native API (what bench.py, the tests and the
  * level-1/2 wrappers call) */
 typedef struct tagpu_ctx tagpu_ctx;
@@ -86,6 +92,13 @@ int tagpu_build_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n_bytes, int
 /* Counting stage only (what KMC_build_kmer_database needs); ksize_plus_1 = K = k + 1 */
 int tagpu_count_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_bytes, int ksize_plus_1);
 int tagpu_count_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n_bytes, int ksize_plus_1);
+
+/* build_local_assembly_graph on host buffers: reads as above; h_contigs = the flanking contigs as ACGT text, contig c at
+ * [contig_off[c], contig_off[c] + contig_len[c]) and followed by a newline; contig_cov[c] = its coverage in the global
+ * graph (__get_edge_cov).  n_contigs <= 4. */
+int tagpu_build_local_host(tagpu_ctx *ctx, const uint8_t *h_reads, uint64_t n_bytes, int k, const uint8_t *h_contigs,
+			   uint64_t n_contig_bytes, int n_contigs, const uint64_t *contig_off, const uint32_t *contig_len,
+			   const double *contig_cov);
 
 int tagpu_get_stats(tagpu_ctx *ctx, struct tagpu_stats *out);
 

@@ -39,6 +39,10 @@ gcc -std=gnu99 -O2 -g -fPIC -pthread -I "$HERE" -c "$HERE/kmc_cpu.c" -o "$OUT/ob
 LIBS="$REF/libs/zlib/libz.a $REF/libs/bzip2/libbz2.a $REF/libs/bwa/libbwa.a -lm"
 g++ -pthread -o "$OUT/TA_ref" $(ls "$OUT"/obj/src_*.o) "$OUT/obj/kmc_cpu_shim.o" $LIBS
 echo "built $OUT/TA_ref"
+# build_local_assembly_graph has no sub-command of its own: our 40-line driver + the unmodified reference objects
+gcc $CFLAGS -c "$HERE/local_ref_main.c" -o "$OUT/obj/local_ref_main.o"
+g++ -pthread -o "$OUT/TA_local_ref" $(ls "$OUT"/obj/src_*.o | grep -v src_main.o) "$OUT/obj/local_ref_main.o" "$OUT/obj/kmc_cpu_shim.o" $LIBS
+echo "built $OUT/TA_local_ref"
 
 TAGPU=$HERE/../turingassembler_b200/libtagpu.so
 if [ -f "$TAGPU" ]; then
@@ -58,4 +62,9 @@ if [ -f "$TAGPU" ]; then
 	g++ -pthread -o "$OUT/TA_kmc" $(ls "$OUT"/obj/src_*.o) \
 		-L "$HERE/../turingassembler_b200" -ltagpu -Wl,-rpath,'$ORIGIN/../../turingassembler_b200' $LIBS
 	echo "built $OUT/TA_kmc"
+	# drop-in for the local-assembly re-entry
+	objcopy --localize-symbol=build_local_assembly_graph "$OUT/obj/dropin_kmer_build.o" "$OUT/obj/dropin_local_kmer_build.o"
+	g++ -pthread -o "$OUT/TA_local_gpu" $(echo "$OBJS" | tr ' ' '\n' | grep -v src_main.o) "$OUT/obj/dropin_local_kmer_build.o" \
+		"$OUT/obj/local_ref_main.o" -L "$HERE/../turingassembler_b200" -ltagpu -Wl,-rpath,'$ORIGIN/../../turingassembler_b200' $LIBS
+	echo "built $OUT/TA_local_gpu"
 fi

@@ -108,20 +108,51 @@ static int is_seq_rc(const uint32_t *s1, uint32_t l1, const uint32_t *s2, uint32
 	return 1;
 }
 
-struct ora_graph *ora_build_graph(int k, int64_t n_solid, const uint64_t *hi,
-				  const uint64_t *lo, const uint32_t *count)
+/* Graph of the solid (k+1)-mers plus, for build_local_assembly_graph (/root/reference/src/kmer_build.c:991-1044), the
+ * "garbage" of n_contigs flanking contigs (2-bit codes, one byte per base): add_garbage (:847-888) applies App. A.4 to
+ * every (k+1)-mer of a contig whether or not the reads support it — i.e. those (k+1)-mers join the edge-bearing set with
+ * the count the reads gave them (0 if they are not solid) — and assign_count_garbage (:890-926) lifts the count of every
+ * edge that carries a contig (k+1)-mer to the contig's coverage. */
+static struct ora_graph *build_graph_impl(int k, int64_t n_solid_in, const uint64_t *hi, const uint64_t *lo, const uint32_t *count,
+					  int n_contigs, const uint8_t *const *contig, const uint32_t *contig_len, const double *old_cov)
 {
 	struct ora_graph *g = calloc(1, sizeof(*g));
 	const int K = k + 1;
 	const u128 kmask = mask_of(k), Kmask = mask_of(K);
 	g->ksize = k;
 
-	struct solid *sol = malloc((n_solid ? n_solid : 1) * sizeof(*sol));
+	int64_t n_garbage = 0;
+	for (int c = 0; c < n_contigs; ++c)
+		if (contig_len[c] > (uint32_t)k) n_garbage += contig_len[c] - k;
+	int64_t n_solid = n_solid_in;
+	struct solid *sol = malloc((n_solid + n_garbage ? n_solid + n_garbage : 1) * sizeof(*sol));
 	for (int64_t i = 0; i < n_solid; ++i) {
 		sol[i].key = ((u128)hi[i] << 64) | lo[i];
 		sol[i].cnt = count[i];
 	}
 	qsort(sol, n_solid, sizeof(*sol), cmp_solid);
+	if (n_garbage) {
+		/* add_garbage: at base i >= k the pair (k-mer ending at i - 1, k-mer ending at i) gets the bits of the
+		 * (k+1)-mer ending at i (:861-887); a (k+1)-mer the reads did not make solid enters with count 0 */
+		int64_t n_all = n_solid;
+		for (int c = 0; c < n_contigs; ++c) {
+			u128 fw = 0, rv = 0;
+			for (uint32_t i = 0; i < contig_len[c]; ++i) {
+				const uint32_t b = contig[c][i] & 3;
+				fw = ((fw << 2) | b) & Kmask;
+				rv = (rv >> 2) | ((u128)(b ^ 3) << (2 * (K - 1)));
+				if (i + 1 > (uint32_t)k) {                      /* :865 */
+					const u128 x = fw <= rv ? fw : rv;
+					if (find_solid(sol, n_solid, x) < 0) { sol[n_all].key = x; sol[n_all].cnt = 0; ++n_all; }
+				}
+			}
+		}
+		qsort(sol, n_all, sizeof(*sol), cmp_solid);
+		int64_t o = 0;
+		for (int64_t i = 0; i < n_all; ++i)
+			if (i == 0 || sol[i].key != sol[o - 1].key) sol[o++] = sol[i];
+		n_solid = o;
+	}
 
 	/* ---- masks: split_kmer_from_kedge_multi, /root/reference/src/kmer_build.c:78-129 (App. A.4) */
 	struct kbit *kb = malloc((n_solid ? 2 * n_solid : 1) * sizeof(*kb));
@@ -284,8 +315,41 @@ struct ora_graph *ora_build_graph(int k, int64_t n_solid, const uint64_t *hi,
 		g->e_count[idx[i]] += sol[i].cnt;
 		g->e_count[g->e_rc[idx[i]]] += sol[i].cnt;
 	}
+	/* ---- assign_count_garbage(ksize + 1, ...), /root/reference/src/kmer_build.c:890-926, contig by contig in call order
+	 * (:1040-1041).  Its loop tests i + 1 > ksize with ksize = k + 1, so the FIRST (k+1)-mer of a contig is never looked up. */
+	for (int c = 0; c < n_contigs; ++c) {
+		u128 fw = 0, rv = 0;
+		for (uint32_t i = 0; i < contig_len[c]; ++i) {
+			const uint32_t b = contig[c][i] & 3;
+			fw = ((fw << 2) | b) & Kmask;
+			rv = (rv >> 2) | ((u128)(b ^ 3) << (2 * (K - 1)));
+			if (i + 1 > (uint32_t)K) {                              /* :905 */
+				const int64_t s = find_solid(sol, n_solid, fw <= rv ? fw : rv);
+				if (s < 0 || idx[s] < 0)
+					continue;                               /* :913 not on any edge */
+				const int64_t new_e = idx[s];
+				const double new_cov = g->e_count[new_e] * 1.0 / (g->e_len[new_e] - (uint32_t)k);   /* __get_edge_cov, n_holes = 0 */
+				if (new_cov < old_cov[c]) {                     /* :918 */
+					const uint64_t v = (uint64_t)old_cov[c] * (g->e_len[new_e] - (uint32_t)K + 1);
+					g->e_count[new_e] = g->e_count[g->e_rc[new_e]] = v;
+				}
+			}
+		}
+	}
 	free(idx); free(ord); free(sol);
 	return g;
+}
+
+struct ora_graph *ora_build_graph(int k, int64_t n_solid, const uint64_t *hi,
+				  const uint64_t *lo, const uint32_t *count)
+{
+	return build_graph_impl(k, n_solid, hi, lo, count, 0, NULL, NULL, NULL);
+}
+
+struct ora_graph *ora_build_graph_local(int k, int64_t n_solid, const uint64_t *hi, const uint64_t *lo, const uint32_t *count,
+					int n_contigs, const uint8_t *const *contig, const uint32_t *contig_len, const double *old_cov)
+{
+	return build_graph_impl(k, n_solid, hi, lo, count, n_contigs, contig, contig_len, old_cov);
 }
 
 void ora_graph_free(struct ora_graph *g)

@@ -47,6 +47,10 @@ struct ora_graph {
 /* solid (k+1)-mers (sorted or not) -> masks -> nodes -> unitigs -> counts */
 struct ora_graph *ora_build_graph(int k, int64_t n_solid, const uint64_t *hi,
 				  const uint64_t *lo, const uint32_t *count);
+/* build_local_assembly_graph (/root/reference/src/kmer_build.c:991-1044): same, plus the "garbage" of the flanking contigs
+ * (one byte per base, codes 0-3) and their coverages old_cov[c] = __get_edge_cov(g0->edges + e_c, g0->ksize) */
+struct ora_graph *ora_build_graph_local(int k, int64_t n_solid, const uint64_t *hi, const uint64_t *lo, const uint32_t *count,
+					int n_contigs, const uint8_t *const *contig, const uint32_t *contig_len, const double *old_cov);
 void ora_graph_free(struct ora_graph *g);
 int ora_graph_save_bin(const struct ora_graph *g, const char *path);
 

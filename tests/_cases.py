@@ -39,3 +39,34 @@ def case_stream(name, cases=None):
     kind, kw, _ = (cases or CASES)[name]
     r1, r2 = reads_for(kind, kw)
     return _reads.stream_of(r1, r2)
+
+
+# ---- build_local_assembly_graph cases: global graph g0 = the oracle's level-0 graph of `case` at k0,
+# flanking edges = the two longest edges with e < rc(e), local reads = the first `n_pairs` read pairs of the case, local k = lk
+LOCAL_CASES = {
+    "L1": dict(case="P1", k0=45, lk=31, n_pairs=1200),
+    "L2": dict(case="M1", k0=45, lk=31, n_pairs=2500),
+    "L3": dict(case="P1", k0=31, lk=21, n_pairs=600),
+}
+
+
+def local_case(oracle, name, workdir):
+    """-> dict(g0_bin, e1, e2, contigs, covs, r1, r2, stream, lk)"""
+    import os
+    import _oracle
+    spec = LOCAL_CASES[name]
+    kind, kw, _ = CASES[spec["case"]]
+    r1, r2 = reads_for(kind, kw)
+    full = _reads.stream_of(r1, r2)
+    cnt = oracle.count(full, spec["k0"] + 1)
+    g = oracle.graph(spec["k0"], cnt["hi"], cnt["lo"], cnt["count"])
+    g0_bin = os.path.join(str(workdir), f"g0_{name}.bin")
+    oracle.save_bin(g, g0_bin)
+    oracle.free_graph(g)
+    g0 = _oracle.load_bin(g0_bin)
+    cand = sorted((e for e, ed in enumerate(g0["edges"]) if ed and e < ed["rc"]), key=lambda e: (-g0["edges"][e]["seq_len"], e))
+    e1, e2 = cand[0], cand[1]
+    contigs = [g0["edges"][e]["seq"] for e in (e1, e2)]
+    covs = [g0["edges"][e]["count"] * 1.0 / (g0["edges"][e]["seq_len"] - (g0["edges"][e]["n_holes"] + 1) * g0["ksize"]) for e in (e1, e2)]
+    lr1, lr2 = r1[: spec["n_pairs"]], r2[: spec["n_pairs"]]
+    return dict(g0_bin=g0_bin, e1=e1, e2=e2, contigs=contigs, covs=covs, r1=lr1, r2=lr2, stream=_reads.stream_of(lr1, lr2), lk=spec["lk"])

@@ -35,6 +35,9 @@ class Oracle:
         lib.ora_free.argtypes = [C.c_void_p]
         lib.ora_build_graph.restype = C.POINTER(OraGraph)
         lib.ora_build_graph.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ora_build_graph_local.restype = C.POINTER(OraGraph)
+        lib.ora_build_graph_local.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                              C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
         lib.ora_graph_free.argtypes = [C.POINTER(OraGraph)]
         lib.ora_graph_save_bin.argtypes = [C.POINTER(OraGraph), C.c_char_p]
         lib.ora_canon_dump.restype = C.c_int
@@ -60,6 +63,15 @@ class Oracle:
     def graph(self, k, hi, lo, count):
         hi, lo, count = np.ascontiguousarray(hi, np.uint64), np.ascontiguousarray(lo, np.uint64), np.ascontiguousarray(count, np.uint32)
         return self.lib.ora_build_graph(k, hi.size, hi.ctypes.data, lo.ctypes.data, count.ctypes.data)
+
+    def graph_local(self, k, hi, lo, count, contigs, covs):
+        """build_local_assembly_graph restatement: contigs = list of ACGT byte strings, covs = their coverages in g0"""
+        hi, lo, count = np.ascontiguousarray(hi, np.uint64), np.ascontiguousarray(lo, np.uint64), np.ascontiguousarray(count, np.uint32)
+        codes = [bytes(b"ACGT".index(ch) for ch in c) for c in contigs]
+        n = len(codes)
+        arr = (C.c_char_p * n)(*codes)
+        return self.lib.ora_build_graph_local(k, hi.size, hi.ctypes.data, lo.ctypes.data, count.ctypes.data, n, arr,
+                                              (C.c_uint32 * n)(*[len(c) for c in codes]), (C.c_double * n)(*covs))
 
     def graph_masks(self, g):
         n = g.contents.n_kmer
@@ -103,3 +115,33 @@ def canon_text(oracle, bin_path, mode=0):
     bad = oracle.canon(bin_path, out, mode)
     with open(out, "rb") as f:
         return bad, f.read()
+
+
+def load_bin(path):
+    """Parses a graph .bin (save_asm_graph layout) -> dict(ksize, n_v, n_e, edges=[dict(...)])."""
+    import struct
+    b = open(path, "rb").read()
+    assert b[:4] == b"asmg"
+    aux, ksize, n_v, n_e = struct.unpack_from("<Iiqq", b, 4)
+    o = 28
+    for _ in range(n_v):
+        _, deg = struct.unpack_from("<qq", b, o)
+        o += 16 + 8 * deg
+    edges = []
+    for e in range(n_e):
+        src, dst = struct.unpack_from("<qq", b, o)
+        o += 16
+        if src == -1:
+            edges.append(None)
+            continue
+        rc, count, len8 = struct.unpack_from("<qQQ", b, o)
+        o += 24
+        seq_len = len8 & 0xffffffff
+        nw = (seq_len + 15) >> 4
+        words = struct.unpack_from(f"<{nw}I", b, o)
+        o += 4 * nw
+        (n_holes,) = struct.unpack_from("<I", b, o)
+        o += 4 + 8 * n_holes
+        seq = bytes(b"ACGT"[(words[i >> 4] >> ((i & 15) << 1)) & 3] for i in range(seq_len))
+        edges.append(dict(src=src, dst=dst, rc=rc, count=count, seq_len=seq_len, n_holes=n_holes, seq=seq))
+    return dict(ksize=ksize, n_v=n_v, n_e=n_e, edges=edges)

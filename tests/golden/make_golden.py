@@ -61,6 +61,39 @@ def main():
                 print(name, k, rec)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(golden, f, indent=1, sort_keys=True)
+    make_local_golden(ora)
+
+
+def make_local_golden(ora):
+    """build_local_assembly_graph (row f1): the UNMODIFIED reference function, reached through oracle/local_ref_main.c
+    (oracle/_ref/TA_local_ref), on the cases of tests/_cases.py:LOCAL_CASES -> tests/golden/golden_local.json."""
+    from _cases import LOCAL_CASES, local_case
+    exe = os.path.join(os.path.dirname(_oracle.TA_REF), "TA_local_ref")
+    assert os.path.exists(exe), "build oracle/_ref/TA_local_ref first: make -C oracle ref"
+    out = {}
+    for name in LOCAL_CASES:
+        with tempfile.TemporaryDirectory() as td:
+            lc = local_case(ora, name, td)
+            f1, f2 = os.path.join(td, "R1.fq"), os.path.join(td, "R2.fq")
+            _reads.write_fastq(f1, lc["r1"], 1)
+            _reads.write_fastq(f2, lc["r2"], 2)
+            binp = os.path.join(td, "local.bin")
+            p = subprocess.run([exe, lc["g0_bin"], str(lc["e1"]), str(lc["e2"]), str(lc["lk"]), f1, f2, td, binp, "1"],
+                               capture_output=True, text=True)
+            log = p.stdout + p.stderr
+            assert p.returncode == 0, log[-2000:]
+            g = lambda pat: int(re.search(pat, log).group(1))
+            rec = dict(lk=lc["lk"], e1=lc["e1"], e2=lc["e2"], contig_len=[len(c) for c in lc["contigs"]], covs=lc["covs"],
+                       n_kmers=g(r"Number of kmer: (\d+)"), n_v=g(r"Number of nodes: (\d+)"), n_e=g(r"Number of edges: (\d+)"),
+                       n_kp1_on_edge=g(r"\(k\+1\)-mer on edge: (\d+)"), sum_count=g(r"sum_count = (\d+)"))
+            for mode in (0, 1):
+                bad, txt = _oracle.canon_text(ora, binp, mode)
+                assert bad == 0
+                rec[f"canon{mode}_md5"] = hashlib.md5(txt).hexdigest()
+            out[name] = rec
+            print(name, rec)
+    with open(os.path.join(HERE, "golden_local.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":

@@ -138,6 +138,11 @@ def load_library() -> C.CDLL:
         f = getattr(lib, name)
         f.restype = i32
         f.argtypes = [vp, vp, u64, i32]
+    lib.tagpu_build_local_host.restype = i32
+    lib.tagpu_build_local_host.argtypes = [vp, vp, u64, i32, vp, u64, i32, C.POINTER(u64), C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
+    lib.build_local_assembly_graph.restype = None
+    lib.build_local_assembly_graph.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p,
+                                               C.POINTER(AsmGraph), C.POINTER(AsmGraph), C.c_int64, C.c_int64]
     lib.tagpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.tagpu_copy_solid.restype = i32
     lib.tagpu_copy_solid.argtypes = [vp, vp, vp, vp]
@@ -241,6 +246,21 @@ class Tagpu:
         """stream: bytes / numpy uint8 array / host address+length tuple."""
         ptr, n, keep = _host_buffer(stream)
         self._check(self.lib.tagpu_build_host(self.ctx, ptr, n, k))
+        del keep
+        return self.stats()
+
+    def build_local_host(self, stream, k: int, contigs: Sequence[bytes], contig_cov: Sequence[float]):
+        """build_local_assembly_graph on host buffers: reads + flanking contigs (ACGT bytes) with their coverages."""
+        ptr, n, keep = _host_buffer(stream)
+        txt = b"".join(c + b"\n" for c in contigs)
+        offs, o = [], 0
+        for c in contigs:
+            offs.append(o)
+            o += len(c) + 1
+        nc = len(contigs)
+        self._check(self.lib.tagpu_build_local_host(
+            self.ctx, ptr, n, k, C.c_char_p(txt), len(txt), nc, (C.c_uint64 * nc)(*offs),
+            (C.c_uint32 * nc)(*[len(c) for c in contigs]), (C.c_double * nc)(*contig_cov)))
         del keep
         return self.stats()
 

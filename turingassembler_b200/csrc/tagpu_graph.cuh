@@ -145,13 +145,16 @@ TAGPU_DI uint32_t ktab_vertex_of(const KTab<W> &t, const Key<W> &y, const Key<W>
 }
 
 // ---------------------------------------------------------------- B: masks (one thread per solid (k+1)-mer)
+// Entries [first, end).  garbage != 0 (second launch of build_local_assembly_graph, after all solid entries): the entry
+// is a (k+1)-mer of a flanking contig (add_garbage, /root/reference/src/kmer_build.c:847-888); if its out-bit is already
+// set, the same (k+1)-mer is in the table (solid) and the entry is dropped (vL = vR = NONE) so it is not counted twice.
 template <int W>
-__global__ void __launch_bounds__(256) k_insert_kmers(const Key<W> *__restrict__ solid, uint64_t n_solid, int k,
+__global__ void __launch_bounds__(256) k_insert_kmers(const Key<W> *__restrict__ solid, uint64_t first, uint64_t n_solid, int garbage, int k,
 						       KTab<W> t, uint32_t *__restrict__ vL, uint32_t *__restrict__ vR,
 						       unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t i = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t n_new = 0;
 	if (i < n_solid) {
 		const Key<W> x = solid[i];
@@ -163,12 +166,18 @@ __global__ void __launch_bounds__(256) k_insert_kmers(const Key<W> *__restrict__
 		bool claimed;
 		uint32_t s1 = ktab_insert<W>(t, f1 ? k1 : r1, &claimed, ctr + CTR_ERROR);
 		n_new += claimed;
-		atomicOr(&t.mask32[s1 >> 2], (1u << (f1 ? c1 : c1 + 4u)) << ((s1 & 3u) * 8u));
-		uint32_t s2 = ktab_insert<W>(t, f2 ? k2 : r2, &claimed, ctr + CTR_ERROR);
-		n_new += claimed;
-		atomicOr(&t.mask32[s2 >> 2], (1u << (f2 ? c2 + 4u : c2)) << ((s2 & 3u) * 8u));
-		vL[i] = s1 * 2u + (f1 ? 0u : 1u);   // oriented vertex whose out-base c1 spells this (k+1)-mer
-		vR[i] = s2 * 2u + (f2 ? 1u : 0u);   // oriented vertex rc(k2) whose out-base c2 spells its reverse complement
+		const uint32_t bit1 = (1u << (f1 ? c1 : c1 + 4u)) << ((s1 & 3u) * 8u);
+		const uint32_t before = atomicOr(&t.mask32[s1 >> 2], bit1);
+		if (garbage && (before & bit1)) {
+			vL[i] = TAGPU_NONE;
+			vR[i] = TAGPU_NONE;
+		} else {
+			uint32_t s2 = ktab_insert<W>(t, f2 ? k2 : r2, &claimed, ctr + CTR_ERROR);
+			n_new += claimed;
+			atomicOr(&t.mask32[s2 >> 2], (1u << (f2 ? c2 + 4u : c2)) << ((s2 & 3u) * 8u));
+			vL[i] = s1 * 2u + (f1 ? 0u : 1u);   // oriented vertex whose out-base c1 spells this (k+1)-mer
+			vR[i] = s2 * 2u + (f2 ? 1u : 0u);   // oriented vertex rc(k2) whose out-base c2 spells its reverse complement
+		}
 	}
 	n_new = __reduce_add_sync(0xffffffffu, n_new);
 	if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(ctr + CTR_KMERS, (unsigned long long)n_new);
@@ -417,6 +426,7 @@ __global__ void __launch_bounds__(256) k_edge_counts(const Key<W> *__restrict__ 
 		const uint32_t cc[2] = { KO::last_base(x), 3u - KO::first_base(x, k + 1) };
 #pragma unroll
 		for (int s = 0; s < 2; ++s) {
+			if (vv[s] == TAGPU_NONE) continue;                  // garbage entry that duplicates a solid (k+1)-mer
 			const uint32_t v = vv[s], slot = v >> 1, o = v & 1u, kd = kind[slot];
 			uint32_t e;
 			if (!(kd & TAGPU_CHAIN)) {
@@ -433,4 +443,57 @@ __global__ void __launch_bounds__(256) k_edge_counts(const Key<W> *__restrict__ 
 	}
 	on_edge = __reduce_add_sync(0xffffffffu, on_edge);
 	if ((threadIdx.x & 31) == 0 && on_edge) atomicAdd(ctr + CTR_KP1_ON_EDGE, (unsigned long long)on_edge);
+}
+
+// ---------------------------------------------------------------- C8: assign_count_garbage (build_local_assembly_graph only)
+// /root/reference/src/kmer_build.c:890-926, called with ksize + 1 (:1040-1041): every (k+1)-mer of the flanking contig
+// EXCEPT ITS FIRST (the loop tests i + 1 > k + 1) that lies on an edge of the new graph lifts that edge (and its twin) to
+// the contig's coverage when the edge's own coverage is lower.  One thread per contig position; writers of one edge all
+// write the same value, and re-evaluating after a write changes nothing, so the result equals the sequential loop.
+// Launched once per contig, in the reference's order.
+template <int W>
+__global__ void __launch_bounds__(256) k_garbage_counts(const uint8_t *__restrict__ contig, uint32_t len, int k, KTab<W> t,
+							 const uint32_t *__restrict__ kind, const uint32_t *__restrict__ node_ebase,
+							 const uint32_t *__restrict__ vedge, FlatGraph g, double old_cov)
+{
+	typedef KeyOps<W> KO;
+	const int K = k + 1;
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;       // position of the window's last base
+	if (i >= len || i + 1 <= (uint32_t)K) return;
+	Key<W> fw = KO::make(0, 0);
+	const Key<W> Km = KO::mask(K);
+	for (int b = 0; b < K; ++b) {
+		const uint32_t ch = contig[i - K + 1 + b];
+		uint32_t c = (ch >> 1) & 3u;                                // A=0 C=1 G=3 T=2 ...
+		c ^= c >> 1;                                                // ... A=0 C=1 G=2 T=3
+		fw = KO::push(fw, c, Km);
+	}
+	const Key<W> rv = KO::rc(fw, K);
+	const Key<W> x = KO::le(fw, rv) ? fw : rv;
+	const Key<W> k1 = KO::shr2(x), r1 = KO::rc(k1, k);
+	const uint32_t c1 = KO::last_base(x);
+	const bool f1 = KO::le(k1, r1);
+	const uint32_t slot = ktab_find<W>(t, f1 ? k1 : r1);
+	if (slot == TAGPU_NONE) return;
+	const uint32_t o = f1 ? 0u : 1u, kd = kind[slot];
+	uint32_t e;
+	if (!(kd & TAGPU_CHAIN)) {
+		const uint32_t m = ktab_mask_of<W>(t, slot), nib = o ? (m >> 4) : (m & 15u);
+		if (!((nib >> c1) & 1u)) return;
+		e = node_ebase[kd] + (o ? DEG4(m) : 0u) + tagpu_rank4(nib, c1);
+	} else {
+		const uint32_t m = ktab_mask_of<W>(t, slot), nib = o ? (m >> 4) : (m & 15u);
+		if (!((nib >> c1) & 1u)) return;
+		e = vedge[(kd & ~TAGPU_CHAIN) * 2u + o];
+	}
+	if (e == TAGPU_NONE) return;
+	const uint32_t rc = g.e_rc[e], new_e = min(e, rc);                 // the reference indexes a (k+1)-mer by min(e, e_rc), :219-223
+	const uint32_t elen = g.e_len[new_e];
+	const unsigned long long cnt = *(volatile unsigned long long *)(g.e_count + new_e);
+	const double new_cov = cnt * 1.0 / (elen - (uint32_t)k);           // __get_edge_cov, n_holes = 0 (assembly_graph.h:191-192)
+	if (new_cov < old_cov) {
+		const unsigned long long v = (unsigned long long)old_cov * (elen - (uint32_t)K + 1u);
+		*(volatile unsigned long long *)(g.e_count + new_e) = v;
+		*(volatile unsigned long long *)(g.e_count + g.e_rc[new_e]) = v;
+	}
 }

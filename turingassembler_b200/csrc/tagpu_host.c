@@ -501,6 +501,52 @@ void build_graph_from_scratch_without_count(int ksize, int n_threads, int mmem, 
 	stage_entry(ksize, n_threads, n_files, files_1, files_2, work_dir, g, 1);
 }
 
+/* /root/reference/src/assembly_graph.h:160-162, body /root/reference/src/kmer_build.c:991-1044: the stage re-entered per
+ * gap by local assembly (get_local_assembly, /root/reference/src/barcode_resolve2.c:2100) — reads of the gap plus the
+ * "garbage" of the two flanking edges e1, e2 of the global graph g0 (add_garbage / assign_count_garbage). */
+void build_local_assembly_graph(int ksize, int n_threads, int mmem, int n_files, char **files_1, char **files_2,
+				char *work_dir, struct asm_graph_t *g, struct asm_graph_t *g0, gint_t e1, gint_t e2)
+{
+	(void)mmem; (void)work_dir;
+	tagpu_ctx *ctx = global_ctx();
+	uint8_t *stream;
+	int64_t n = gather_files(n_files, files_1, files_2, n_threads, &stream);
+	/* the two contigs as text, each followed by a newline (add_garbage walks the 2-bit sequence base by base) */
+	const gint_t ee[2] = { e1, e2 };
+	uint64_t off[2], total = 0;
+	uint32_t len[2];
+	double cov[2];
+	for (int c = 0; c < 2; ++c) {
+		const struct asm_edge_t *ed = g0->edges + ee[c];
+		off[c] = total;
+		len[c] = ed->seq_len;
+		/* __get_edge_cov(g0->edges + e, g0->ksize), /root/reference/src/assembly_graph.h:191-192 */
+		cov[c] = ed->count * 1.0 / (ed->seq_len - (ed->n_holes + 1) * (g0->ksize));
+		total += (uint64_t)ed->seq_len + 1;
+	}
+	uint8_t *txt = malloc(total + 1);
+	if (!txt)
+		TAGPU_FATAL("out of host memory for the flanking contigs");
+	for (int c = 0; c < 2; ++c) {
+		const struct asm_edge_t *ed = g0->edges + ee[c];
+		for (uint32_t i = 0; i < ed->seq_len; ++i)
+			txt[off[c] + i] = "ACGT"[(ed->seq[i >> 4] >> ((i & 15) << 1)) & 3];
+		txt[off[c] + ed->seq_len] = '\n';
+	}
+	tagpu_set_skip_counts(ctx, 0);
+	if (tagpu_build_local_host(ctx, stream, (uint64_t)n, ksize, txt, total, 2, off, len, cov))
+		TAGPU_FATAL("GPU local graph build failed: %s", tagpu_last_error(ctx));
+	free(txt);
+	tagpu_free_reads(stream);
+	struct tagpu_stats st;
+	tagpu_get_stats(ctx, &st);
+	fprintf(stderr, "[tagpu] Number of kmer: %lu\n", (unsigned long)st.n_kmers);                    /* kmer_build.c:1020 */
+	fprintf(stderr, "[tagpu] Number of nodes: %ld; Number of edges: %ld\n", (long)st.n_v, (long)st.n_e); /* :1026 */
+	fprintf(stderr, "[tagpu] Number of (k+1)-mer on edge: %lu\n", (unsigned long)st.n_kp1_on_edge);   /* :1032 */
+	if (tagpu_fill_asm_graph(ctx, g))
+		TAGPU_FATAL("cannot materialise the assembly graph: %s", tagpu_last_error(ctx));
+}
+
 void build_initial_graph(struct opt_proc_t *opt, int ksize, struct asm_graph_t *g)
 {
 	double t0 = now_s();

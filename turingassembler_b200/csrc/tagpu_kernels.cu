@@ -47,6 +47,14 @@ struct tagpu_ctx {
 	uint32_t kt_slots = 0;
 	bool have_count = false, have_graph = false;
 	void *cur_solid_key = nullptr, *cur_solid_cnt = nullptr; // solid set the graph stage reads (local, or gathered from all ranks)
+	// build_local_assembly_graph: (k+1)-mers of the flanking contigs appended behind the solid ones (count 0), and the contigs
+	uint64_t n_garbage = 0;
+	bool local_mode = false;
+	Buf g_key, comb_key, comb_cnt, g_seq;
+	int n_contigs = 0;
+	uint64_t contig_off[4] = { 0 };
+	uint32_t contig_len[4] = { 0 };
+	double contig_cov[4] = { 0 };
 	struct DistState *dist = nullptr;
 	tagpu_stats st;
 	cudaEvent_t ev[4];
@@ -184,7 +192,7 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	dist_release(ctx);
-	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
 			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
 	for (Buf *b : bufs)
@@ -437,7 +445,8 @@ template <int W>
 static int graph_stage(tagpu_ctx *ctx)
 {
 	const int k = ctx->k;
-	const uint64_t n_solid = ctx->st.n_solid;
+	const uint64_t n_reads_solid = ctx->st.n_solid;
+	const uint64_t n_solid = n_reads_solid + ctx->n_garbage;        // entries of the (k+1)-mer list: solid ones, then contig garbage
 	// every solid (k+1)-mer touches two k-mers; in practice #k-mers ~ #solid, so 2.5x keeps the load near 0.4
 	const uint64_t slots64 = (n_solid * 5) / 2 + 1024;
 	if (slots64 > (1ull << 30)) return fail(ctx, "k-mer table would need %llu slots (> 2^30)", (unsigned long long)slots64);
@@ -461,7 +470,9 @@ static int graph_stage(tagpu_ctx *ctx)
 	unsigned long long *ctr = ctx->d_ctr;
 	const Key<W> *solid = (const Key<W> *)ctx->cur_solid_key;
 
-	if (n_solid) LAUNCH(k_insert_kmers<W>, (unsigned)((n_solid + 255) / 256), 256, solid, n_solid, k, t, vL, vR, ctr);
+	if (n_reads_solid) LAUNCH(k_insert_kmers<W>, (unsigned)((n_reads_solid + 255) / 256), 256, solid, 0ull, n_reads_solid, 0, k, t, vL, vR, ctr);
+	if (ctx->n_garbage)
+		LAUNCH(k_insert_kmers<W>, (unsigned)((ctx->n_garbage + 255) / 256), 256, solid, n_reads_solid, n_solid, 1, k, t, vL, vR, ctr);
 	LAUNCH(k_classify<W>, (n_slots + 1023) / 1024, 1024, t, kind, node_slot, node_ebase, chain_slot, ctr);
 	if (read_counters(ctx)) return -1;
 	const uint64_t n_nodes = ctx->h_ctr[CTR_NODES], n_e = ctx->h_ctr[CTR_EDGES], n_chain = ctx->h_ctr[CTR_CHAIN];
@@ -509,6 +520,12 @@ static int graph_stage(tagpu_ctx *ctx)
 	if (n_solid && !ctx->skip_counts)
 		LAUNCH(k_edge_counts<W>, (unsigned)((n_solid + 255) / 256), 256, solid, (const uint32_t *)ctx->cur_solid_cnt, n_solid, k, t,
 		       vL, vR, kind, node_ebase, vedge, g, ctr);
+	// assign_count_garbage, contig by contig in the reference's call order (kmer_build.c:1040-1041)
+	if (!ctx->skip_counts)
+		for (int c = 0; c < ctx->n_contigs; ++c)
+			if (ctx->contig_len[c] > (uint32_t)(k + 1) && n_e)
+				LAUNCH(k_garbage_counts<W>, (ctx->contig_len[c] + 255) / 256, 256, (const uint8_t *)ctx->g_seq.p + ctx->contig_off[c],
+				       ctx->contig_len[c], k, t, kind, node_ebase, vedge, g, ctx->contig_cov[c]);
 	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
 	if (read_counters(ctx)) return -1;
 	ctx->st.jump_rounds = ctx->h_ctr[CTR_JUMP_ROUNDS];
@@ -532,6 +549,7 @@ static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool wit
 	ctx->launches = 0;
 	ctx->err[0] = 0;
 	memset(&ctx->st, 0, sizeof(ctx->st));
+	if (!ctx->local_mode) { ctx->n_garbage = 0; ctx->n_contigs = 0; }
 	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->d_ctr, 0, CTR_TOTAL * sizeof(unsigned long long), ctx->stream)); }
 	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
 	static const bool direct = getenv("TAGPU_COUNT_DIRECT") != nullptr; // bring-up cross-check only
@@ -539,6 +557,20 @@ static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool wit
 			: (ctx->W == 1 ? count_stage_partitioned<1>(ctx, d_seq, n) : count_stage_partitioned<2>(ctx, d_seq, n));
 	if (rc) return rc;
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+	if (with_graph && ctx->n_garbage) {
+		// (k+1)-mer list of the graph stage = solid (k+1)-mers of the reads, then the contig garbage with count 0
+		const size_t key = ctx->W == 1 ? sizeof(Key<1>) : sizeof(Key<2>);
+		const uint64_t ns = ctx->st.n_solid, ng = ctx->n_garbage;
+		if (ensure(ctx, ctx->comb_key, (ns + ng + 1) * key) || ensure(ctx, ctx->comb_cnt, (ns + ng + 1) * 4)) return -1;
+		if (ns) {
+			CU(cudaMemcpyAsync(ctx->comb_key.p, ctx->cur_solid_key, ns * key, cudaMemcpyDeviceToDevice, ctx->stream));
+			CU(cudaMemcpyAsync(ctx->comb_cnt.p, ctx->cur_solid_cnt, ns * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+		}
+		CU(cudaMemcpyAsync((char *)ctx->comb_key.p + ns * key, ctx->g_key.p, ng * key, cudaMemcpyDeviceToDevice, ctx->stream));
+		CU(cudaMemsetAsync((char *)ctx->comb_cnt.p + ns * 4, 0, ng * 4, ctx->stream));
+		ctx->cur_solid_key = ctx->comb_key.p;
+		ctx->cur_solid_cnt = ctx->comb_cnt.p;
+	}
 	if (with_graph) {
 		rc = ctx->W == 1 ? graph_stage<1>(ctx) : graph_stage<2>(ctx);
 		if (rc) return rc;
@@ -826,6 +858,50 @@ extern "C" int tagpu_count_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n
 {
 	if (upload(ctx, h_seq, n)) return -1;
 	return run(ctx, (const uint8_t *)ctx->seq.p, n, K, false);
+}
+
+// build_local_assembly_graph: reads + the two flanking contigs of the global graph.
+// 1. the contigs alone go through the count stage with cutoff 1 -> their distinct canonical (k+1)-mers (the "garbage");
+// 2. the reads are counted with the context's cutoff; 3. the graph stage runs on solid ++ garbage; 4. k_garbage_counts.
+extern "C" int tagpu_build_local_host(tagpu_ctx *ctx, const uint8_t *h_reads, uint64_t n_bytes, int k, const uint8_t *h_contigs,
+				      uint64_t n_contig_bytes, int n_contigs, const uint64_t *contig_off, const uint32_t *contig_len,
+				      const double *contig_cov)
+{
+	if (n_contigs < 0 || n_contigs > 4) return fail(ctx, "at most 4 flanking contigs (got %d)", n_contigs);
+	if (ctx->dist) return fail(ctx, "context is in multi-GPU mode");
+	CU(cudaSetDevice(ctx->device));
+	ctx->local_mode = false;
+	ctx->n_garbage = 0;
+	ctx->n_contigs = 0;
+	if (n_contigs && n_contig_bytes) {
+		if (ensure(ctx, ctx->g_seq, n_contig_bytes + 64)) return -1;
+		CU(cudaMemcpyAsync(ctx->g_seq.p, h_contigs, n_contig_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		const int ci = ctx->ci;
+		ctx->ci = 1;
+		ctx->h_src = nullptr;
+		const int rc = run(ctx, (const uint8_t *)ctx->g_seq.p, n_contig_bytes, k + 1, false);
+		ctx->ci = ci;
+		if (rc) return rc;
+		const size_t key = ctx->W == 1 ? sizeof(Key<1>) : sizeof(Key<2>);
+		const uint64_t ng = ctx->st.n_solid;
+		if (ensure(ctx, ctx->g_key, (ng + 1) * key)) return -1;
+		if (ng) CU(cudaMemcpyAsync(ctx->g_key.p, ctx->cur_solid_key, ng * key, cudaMemcpyDeviceToDevice, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		ctx->n_garbage = ng;
+		ctx->n_contigs = n_contigs;
+		for (int c = 0; c < n_contigs; ++c) {
+			ctx->contig_off[c] = contig_off[c];
+			ctx->contig_len[c] = contig_len[c];
+			ctx->contig_cov[c] = contig_cov[c];
+		}
+	}
+	ctx->local_mode = true;                                     // keeps the garbage across the run() of the reads
+	int rc = upload(ctx, h_reads, n_bytes);
+	if (!rc) rc = run(ctx, (const uint8_t *)ctx->seq.p, n_bytes, k + 1, true);
+	ctx->local_mode = false;
+	ctx->n_garbage = 0;
+	ctx->n_contigs = 0;
+	return rc;
 }
 
 extern "C" int tagpu_get_stats(tagpu_ctx *ctx, struct tagpu_stats *out)
