@@ -30,7 +30,7 @@ WORKLOADS = {
 L = 151
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the last `ncu --set full` capture of the C2 workload
 # (profiles/), keyed by kernel; None until such a capture exists for the current kernels
-TRAFFIC = {"k_count_buckets<W>": 1.345711e9 + 0.141952e9, "k_partition<W>": 0.609145e9 + 1.289572e9}  # profiles/r1_ncu_count_kernels_lines.txt
+TRAFFIC = {"k_count_buckets<W>": 0.973974e9 + 0.144152e9, "k_partition<W>": 0.610278e9 + 0.909922e9}  # profiles/r1_ncu_top_kernels_raw.txt
 
 
 def gen_reads_gpu(torch, genome_len, n_pairs, seed, device, sub_err=0.005, n_rate=0.02, n_repeats=40, repeat_len=600):
@@ -181,7 +181,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="tagpu", choices=["tagpu", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
