@@ -422,21 +422,22 @@ __global__ void __launch_bounds__(256) k_edge_counts(const Key<W> *__restrict__ 
 	if (i < n_solid) {
 		const Key<W> x = solid[i];
 		const uint32_t cnt = solid_cnt[i];
-		const uint32_t vv[2] = { vL[i], vR[i] };
-		const uint32_t cc[2] = { KO::last_base(x), 3u - KO::first_base(x, k + 1) };
-#pragma unroll
-		for (int s = 0; s < 2; ++s) {
-			if (vv[s] == TAGPU_NONE) continue;                  // garbage entry that duplicates a solid (k+1)-mer
-			const uint32_t v = vv[s], slot = v >> 1, o = v & 1u, kd = kind[slot];
+		// The (k+1)-mer lies on the edge through vL (via its last base) and its reverse complement on that edge's twin:
+		// one lookup, then e_rc — exactly the reference's "edges[e].count += c; edges[edges[e].rc_id].count += c"
+		// (/root/reference/src/kmer_build.c:154-156), self-rc edges included (they get 2c).
+		const uint32_t v = vL[i], c1 = KO::last_base(x);
+		if (v != TAGPU_NONE) {                                      // NONE: garbage entry that duplicates a solid (k+1)-mer
+			const uint32_t slot = v >> 1, o = v & 1u, kd = kind[slot];
 			uint32_t e;
 			if (!(kd & TAGPU_CHAIN)) {
 				const uint32_t m = ktab_mask_of<W>(t, slot), nib = o ? (m >> 4) : (m & 15u);
-				e = node_ebase[kd] + (o ? DEG4(m) : 0u) + tagpu_rank4(nib, cc[s]);
+				e = node_ebase[kd] + (o ? DEG4(m) : 0u) + tagpu_rank4(nib, c1);
 			} else {
 				e = vedge[(kd & ~TAGPU_CHAIN) * 2u + o];
 			}
 			if (e != TAGPU_NONE) {
 				atomicAdd(g.e_count + e, (unsigned long long)cnt);
+				atomicAdd(g.e_count + g.e_rc[e], (unsigned long long)cnt);
 				on_edge = 1;
 			}
 		}
