@@ -26,6 +26,9 @@ WORKLOADS = {
     "C2": dict(genome_len=4_641_652, n_pairs=2_000_000, k=45, seed=1),
     "C1": dict(genome_len=4_641_652, n_pairs=2_000_000, k=31, seed=1),
     "small": dict(genome_len=400_000, n_pairs=150_000, k=45, seed=1),
+    # BASELINE.json configs[2]: metagenomic mock community, ~20 M pairs, uneven coverage, k0 = 45 (multi-GPU sized: the
+    # 6 GB read stream needs >= 2 B200s with today's region sizing)
+    "C3": dict(n_genomes=20, n_pairs=20_000_000, k=45, seed=3, genome_len=90_000_000),
 }
 L = 151
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the last `ncu --set full` capture of the C2 workload
@@ -33,40 +36,72 @@ L = 151
 TRAFFIC = {"k_count_buckets<W>": 0.973974e9 + 0.144152e9, "k_partition<W>": 0.610278e9 + 0.909922e9}  # profiles/r1_ncu_top_kernels_raw.txt
 
 
-def gen_reads_gpu(torch, genome_len, n_pairs, seed, device, sub_err=0.005, n_rate=0.02, n_repeats=40, repeat_len=600):
-    """Synthetic paired reads generated on the device (SURVEY.md §8d shape: uniform genome + planted 600 bp repeats,
-    insert ~U[300,500], 0.5 % substitutions, 2 % of reads carry one N).  Returns a uint8 tensor: R1 reads then R2 reads,
-    each followed by a newline."""
+N_CHUNKS = 16   # the read set is generated in 16 independently seeded chunks of pairs, so a rank can make just its share
+
+
+def make_genomes(torch, wl, device):
+    """Concatenated synthetic genome(s) of a workload + (start, length, weight) of each replicon.  Uniform bases plus
+    planted 600 bp repeats so that branching exists; C3 = 20 genomes, log-uniform lengths, log-normal
+    abundances (a metagenomic mock community)."""
     g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    genome = torch.randint(0, 4, (genome_len,), generator=g, device=device, dtype=torch.uint8)
-    src = torch.randint(0, genome_len - repeat_len, (n_repeats,), generator=g, device=device)
-    dst = torch.randint(0, genome_len - repeat_len, (n_repeats,), generator=g, device=device)
+    g.manual_seed(wl["seed"])
+    if wl.get("n_genomes", 1) > 1:
+        cpu = torch.Generator().manual_seed(wl["seed"])
+        lens = torch.exp(torch.rand(wl["n_genomes"], generator=cpu) * (torch.log(torch.tensor(8e6)) - torch.log(torch.tensor(1e6))) +
+                         torch.log(torch.tensor(1e6))).long()
+        abund = torch.exp(torch.randn(wl["n_genomes"], generator=cpu) * 1.5)
+    else:
+        lens = torch.tensor([wl["genome_len"]])
+        abund = torch.ones(1)
+    total = int(lens.sum())
+    genome = torch.randint(0, 4, (total,), generator=g, device=device, dtype=torch.uint8)
+    n_rep = wl.get("n_repeats", 40) * len(lens)
+    src = torch.randint(0, total - 600, (n_rep,), generator=g, device=device)
+    dst = torch.randint(0, total - 600, (n_rep,), generator=g, device=device)
     for a, b in zip(src.tolist(), dst.tolist()):
-        genome[b:b + repeat_len] = genome[a:a + repeat_len].clone()
+        genome[b:b + 600] = genome[a:a + 600].clone()
+    starts = torch.cumsum(lens, 0) - lens
+    weight = (abund * lens.double()).double()
+    return genome, starts.to(device), lens.to(device), (weight / weight.sum()).to(device)
+
+
+def gen_reads_gpu(torch, wl, device, chunks=None, sub_err=0.005, n_rate=0.02):
+    """Synthetic paired reads generated on the device (SURVEY.md §8d shape: insert ~U[300,500], 0.5 % substitutions, 2 % of
+    reads carry one N).  Returns a uint8 tensor of reads, each followed by a newline: for every chunk of pairs its R1 reads,
+    then its R2 reads.  `chunks` = range of chunk ids to generate (default: all N_CHUNKS); chunk c is seeded by
+    (seed, c) alone, so every rank of a multi-GPU run produces exactly its slice of the same read set."""
+    genome, starts, lens, weight = make_genomes(torch, wl, device)
+    n_pairs = wl["n_pairs"]
+    chunks = range(N_CHUNKS) if chunks is None else chunks
     lut = torch.tensor(list(b"ACGT"), device=device, dtype=torch.uint8)
-    out = torch.empty((2 * n_pairs, L + 1), device=device, dtype=torch.uint8)
-    chunk = 250_000
     idx = torch.arange(L, device=device)[None, :]
-    for s in range(0, n_pairs, chunk):
-        m = min(chunk, n_pairs - s)
-        ins = torch.randint(300, 501, (m,), generator=g, device=device)
-        pos = (torch.rand(m, generator=g, device=device, dtype=torch.float64) * (genome_len - ins)).long()
-        flip = torch.rand(m, generator=g, device=device) < 0.5
-        fwd = genome[pos[:, None] + idx]
-        rev = 3 - genome[(pos + ins - 1)[:, None] - idx]
-        for mate, codes in ((0, torch.where(flip[:, None], rev, fwd)), (1, torch.where(flip[:, None], fwd, rev))):
-            err = torch.rand((m, L), generator=g, device=device) < sub_err
-            rnd = torch.randint(0, 4, (m, L), generator=g, device=device, dtype=torch.uint8)
-            codes = torch.where(err, rnd, codes)
-            chars = lut[codes.long()]
-            with_n = torch.rand(m, generator=g, device=device) < n_rate
-            n_pos = torch.randint(0, L, (m,), generator=g, device=device)
-            rows = torch.nonzero(with_n).squeeze(1)
-            chars[rows, n_pos[rows]] = ord("N")
-            out[mate * n_pairs + s: mate * n_pairs + s + m, :L] = chars
-    out[:, L] = ord("\n")
-    return out.reshape(-1)
+    parts = []
+    for c in chunks:
+        p0, p1 = n_pairs * c // N_CHUNKS, n_pairs * (c + 1) // N_CHUNKS
+        g = torch.Generator(device=device)
+        g.manual_seed(wl["seed"] * 1000003 + c + 1)
+        for s in range(p0, p1, 250_000):
+            m = min(250_000, p1 - s)
+            which = torch.multinomial(weight, m, replacement=True, generator=g) if len(lens) > 1 else torch.zeros(m, dtype=torch.long, device=device)
+            ins = torch.randint(300, 501, (m,), generator=g, device=device)
+            pos = starts[which] + (torch.rand(m, generator=g, device=device, dtype=torch.float64) * (lens[which] - ins)).long()
+            flip = torch.rand(m, generator=g, device=device) < 0.5
+            fwd = genome[pos[:, None] + idx]
+            rev = 3 - genome[(pos + ins - 1)[:, None] - idx]
+            out = torch.empty((2, m, L + 1), device=device, dtype=torch.uint8)
+            for mate, codes in ((0, torch.where(flip[:, None], rev, fwd)), (1, torch.where(flip[:, None], fwd, rev))):
+                err = torch.rand((m, L), generator=g, device=device) < sub_err
+                rnd = torch.randint(0, 4, (m, L), generator=g, device=device, dtype=torch.uint8)
+                codes = torch.where(err, rnd, codes)
+                chars = lut[codes.long()]
+                with_n = torch.rand(m, generator=g, device=device) < n_rate
+                n_pos = torch.randint(0, L, (m,), generator=g, device=device)
+                rows = torch.nonzero(with_n).squeeze(1)
+                chars[rows, n_pos[rows]] = ord("N")
+                out[mate, :, :L] = chars
+            out[:, :, L] = ord("\n")
+            parts.append(out.reshape(-1))
+    return torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=device)
 
 
 class ClockSampler(threading.Thread):
@@ -206,17 +241,14 @@ def main():
     wl = WORKLOADS[args.workload]
     k = wl["k"]
 
-    # Strong scaling (north_star): the SAME read set is split over the ranks.  Every rank generates the identical seeded
-    # stream and keeps its contiguous 1/world slice of the reads (R1 block and R2 block are both cut at read boundaries).
-    d_full = gen_reads_gpu(torch, wl["genome_len"], wl["n_pairs"], wl["seed"], dev)
-    n_total = d_full.numel()
+    # Strong scaling (north_star): the SAME read set is split over the ranks.  The set is generated in N_CHUNKS
+    # independently seeded chunks of pairs; rank r generates (only) chunks [r N_CHUNKS / world, (r + 1) N_CHUNKS / world).
+    n_total = 2 * wl["n_pairs"] * (L + 1)
     if world > 1:
-        from turingassembler_b200.dist import DistTagpu, shard_reads
-        first, last = shard_reads(n_total // (L + 1), rank, world)
-        d_stream = d_full[first * (L + 1): last * (L + 1)].clone()
+        from turingassembler_b200.dist import DistTagpu
+        d_stream = gen_reads_gpu(torch, wl, dev, range(N_CHUNKS * rank // world, N_CHUNKS * (rank + 1) // world))
     else:
-        d_stream = d_full
-    del d_full
+        d_stream = gen_reads_gpu(torch, wl, dev)
     n_stream = d_stream.numel()
     h_stream = torch.empty(n_stream, dtype=torch.uint8, pin_memory=True)
     h_stream.copy_(d_stream)
@@ -318,7 +350,7 @@ def main():
         "metric": "kmers_per_sec_counted_and_graph_built", "value": value, "unit": "kmers/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u128" if k + 1 > 32 else "u64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['genome_len']} bp genome, {wl['n_pairs']} pairs x {L} bp, k0={k} "
+        "config": {"workload": f"{args.workload}: {wl.get('n_genomes', 1)} genome(s), {wl['genome_len']} bp, {wl['n_pairs']} pairs x {L} bp, k0={k} "
                                f"(K={k + 1}), cutoff 2; {n_total} stream bytes resident in HBM (> L2, no flush needed)",
                    "n_instances": n_inst, "n_distinct": st["n_distinct"], "n_solid": st["n_solid"], "n_kmers": st["n_kmers"],
                    "n_v": st["n_v"], "n_e": st["n_e"],

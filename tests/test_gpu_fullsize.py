@@ -30,7 +30,7 @@ def test_full_size_invariants(tagpu, oracle, k):
     import torch
     import bench
     wl = bench.WORKLOADS["C2"]
-    d = bench.gen_reads_gpu(torch, wl["genome_len"], wl["n_pairs"], wl["seed"], torch.device("cuda", 0))
+    d = bench.gen_reads_gpu(torch, wl, torch.device("cuda", 0))
     tagpu.set_cutoff(2)
     st = tagpu.build_device(d.data_ptr(), d.numel(), k)
     g = tagpu.graph()

@@ -14,7 +14,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "C2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 wl = bench.WORKLOADS[name]
 dev = torch.device("cuda", 0)
-d = bench.gen_reads_gpu(torch, wl["genome_len"], wl["n_pairs"], wl["seed"], dev)
+d = bench.gen_reads_gpu(torch, wl, dev)
 t = Tagpu(0)
 for _ in range(2):
     st = t.build_device(d.data_ptr(), d.numel(), wl["k"])
