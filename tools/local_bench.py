@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Developer tool: latency of one build_local_assembly_graph call (row f1) on the GPU vs the reference's CPU function.
+    python tools/local_bench.py [L1|L2|L3] [reps]"""
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _oracle  # noqa: E402
+import _reads  # noqa: E402
+from _cases import local_case  # noqa: E402
+from turingassembler_b200 import Tagpu  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "L2"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+ora = _oracle.load()
+with tempfile.TemporaryDirectory() as td:
+    lc = local_case(ora, name, td)
+    t = Tagpu(0)
+    for _ in range(3):
+        st = t.build_local_host(lc["stream"], lc["lk"], lc["contigs"], lc["covs"])
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        st = t.build_local_host(lc["stream"], lc["lk"], lc["contigs"], lc["covs"])
+    gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    print(f"{name}: {len(lc['r1']) * 2} reads, lk={lc['lk']}, contigs {[len(c) for c in lc['contigs']]}: n_instances={st['n_instances']} "
+          f"n_solid={st['n_solid']} n_v={st['n_v']} n_e={st['n_e']}")
+    print(f"GPU  tagpu_build_local_host: {gpu_ms:.3f} ms per call (host wall clock, {reps} calls; device {st['ms_total']:.3f} ms in the last)")
+    exe = os.path.join(os.path.dirname(_oracle.TA_REF), "TA_local_ref")
+    if os.path.exists(exe):
+        f1, f2 = os.path.join(td, "R1.fq"), os.path.join(td, "R2.fq")
+        _reads.write_fastq(f1, lc["r1"], 1)
+        _reads.write_fastq(f2, lc["r2"], 2)
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            p = subprocess.run([exe, lc["g0_bin"], str(lc["e1"]), str(lc["e2"]), str(lc["lk"]), f1, f2, td, os.path.join(td, "o.bin"), str(os.cpu_count())],
+                               capture_output=True, text=True)
+            best = min(best, time.perf_counter() - t0)
+        print(f"CPU  reference build_local_assembly_graph via TA_local_ref (process start + load g0 + FASTQ + build + save, {os.cpu_count()} threads): {best * 1e3:.1f} ms")

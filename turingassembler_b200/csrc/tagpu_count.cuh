@@ -255,13 +255,43 @@ __global__ void k_overflow_hist(const uint32_t *__restrict__ overflow_bucket, ui
 	if (i < n_over) atomicAdd(ext_count + overflow_bucket[i], 1u);
 }
 
-// single block: exclusive scan of ext_count into ext_off (n_buckets + 1 entries), ext_count reset to 0 for reuse as cursor
-__global__ void __launch_bounds__(1024) k_overflow_scan(uint32_t *ext_count, uint32_t *ext_off, uint32_t n_buckets)
+// Exclusive scan of ext_count into ext_off (n_buckets + 1 entries), grid-wide in three small steps: per-block scan
+// (k_overflow_scan_blocks), scan of the block totals (k_overflow_scan_tops, one block), and the add-back that also resets
+// ext_count to 0 for its reuse as the scatter cursor (k_overflow_scan_finish).
+__global__ void __launch_bounds__(1024) k_overflow_scan_blocks(const uint32_t *__restrict__ ext_count, uint32_t *__restrict__ ext_off,
+							       uint32_t *__restrict__ tops, uint32_t n_buckets)
+{
+	__shared__ uint32_t s_w[32];
+	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t v = b < n_buckets ? ext_count[b] : 0u;
+	uint32_t incl = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= (uint32_t)d) incl += t;
+	}
+	if (lane == 31) s_w[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t x = s_w[lane], y = x;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			uint32_t t = __shfl_up_sync(0xffffffffu, y, d);
+			if (lane >= (uint32_t)d) y += t;
+		}
+		s_w[lane] = y - x;
+		if (lane == 31) tops[blockIdx.x] = y;
+	}
+	__syncthreads();
+	if (b < n_buckets) ext_off[b] = s_w[warp] + incl - v;
+}
+
+__global__ void __launch_bounds__(1024) k_overflow_scan_tops(uint32_t *__restrict__ tops, uint32_t n_blocks, uint32_t *__restrict__ ext_off, uint32_t n_buckets)
 {
 	__shared__ uint32_t s_part[1024];
-	const uint32_t per = (n_buckets + 1023) / 1024, lo = threadIdx.x * per, hi = min(lo + per, n_buckets);
+	const uint32_t per = (n_blocks + 1023) / 1024, lo = min(threadIdx.x * per, n_blocks), hi = min(lo + per, n_blocks);
 	uint32_t sum = 0;
-	for (uint32_t b = lo; b < hi; ++b) sum += ext_count[b];
+	for (uint32_t i = lo; i < hi; ++i) sum += tops[i];
 	s_part[threadIdx.x] = sum;
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -271,7 +301,16 @@ __global__ void __launch_bounds__(1024) k_overflow_scan(uint32_t *ext_count, uin
 	}
 	__syncthreads();
 	uint32_t acc = s_part[threadIdx.x];
-	for (uint32_t b = lo; b < hi; ++b) { ext_off[b] = acc; acc += ext_count[b]; ext_count[b] = 0; }
+	for (uint32_t i = lo; i < hi; ++i) { const uint32_t v = tops[i]; tops[i] = acc; acc += v; }
+}
+
+__global__ void __launch_bounds__(1024) k_overflow_scan_finish(uint32_t *__restrict__ ext_count, uint32_t *__restrict__ ext_off,
+							       const uint32_t *__restrict__ tops, uint32_t n_buckets)
+{
+	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_buckets) return;
+	ext_off[b] += tops[blockIdx.x];
+	ext_count[b] = 0;
 }
 
 template <int W>

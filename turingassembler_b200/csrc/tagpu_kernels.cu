@@ -356,7 +356,11 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 		}
 		{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->ext_count.p, 0, (size_t)n_buckets * 4, ctx->stream)); }
 		LAUNCH(k_overflow_hist, (unsigned)((n_over + 255) / 256), 256, (const uint32_t *)ctx->overflow_bucket.p, n_over, (uint32_t *)ctx->ext_count.p);
-		LAUNCH(k_overflow_scan, 1, 1024, (uint32_t *)ctx->ext_count.p, (uint32_t *)ctx->ext_off.p, n_buckets);
+		const uint32_t n_ob = (n_buckets + 1023) / 1024;
+		if (ensure(ctx, ctx->bsum, ((size_t)n_ob + 1) * 8)) return -1;       // scratch: block totals of the scan
+		LAUNCH(k_overflow_scan_blocks, n_ob, 1024, (const uint32_t *)ctx->ext_count.p, (uint32_t *)ctx->ext_off.p, (uint32_t *)ctx->bsum.p, n_buckets);
+		LAUNCH(k_overflow_scan_tops, 1, 1024, (uint32_t *)ctx->bsum.p, n_ob, (uint32_t *)ctx->ext_off.p, n_buckets);
+		LAUNCH(k_overflow_scan_finish, n_ob, 1024, (uint32_t *)ctx->ext_count.p, (uint32_t *)ctx->ext_off.p, (const uint32_t *)ctx->bsum.p, n_buckets);
 		LAUNCH(k_overflow_scatter<W>, (unsigned)((n_over + 255) / 256), 256, (const SkRec<W> *)ctx->overflow.p,
 		       (const uint32_t *)ctx->overflow_bucket.p, n_over, (const uint32_t *)ctx->ext_off.p, (uint32_t *)ctx->ext_count.p,
 		       (SkRec<W> *)ctx->ext.p);
