@@ -29,6 +29,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]: metagenomic mock community, ~20 M pairs, uneven coverage, k0 = 45 (multi-GPU sized: the
     # 6 GB read stream needs >= 2 B200s with today's region sizing)
     "C3": dict(n_genomes=20, n_pairs=20_000_000, k=45, seed=3, genome_len=90_000_000),
+    # BASELINE.json configs[3]: human chr1-scale, ~250 Mbp, 40x, ~35 M pairs, k0 = 45, hash-partitioned over 8 B200s
+    # (planted repeats stand in for the repeat families of the spec)
+    "C4": dict(genome_len=250_000_000, n_pairs=35_000_000, k=45, seed=4, n_repeats=20_000),
 }
 L = 151
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the last `ncu --set full` capture of the C2 workload
