@@ -149,6 +149,49 @@ def algorithmic_bytes(st, k, n_stream):
     return count, graph
 
 
+def files_e2e(torch, h_stream, k, reps=3):
+    """The reference-facing call on FILES: build_graph_from_scratch(k, n_threads, mmem, 1, &R1.fq, &R2.fq, dir, &g)
+    (/root/reference/src/kmer_build.h:17-19) on FASTQ files in a RAM disk -> the caller's struct asm_graph_t in host memory
+    (SURVEY.md §8d T_e2e: parse FASTQ, upload, count, build, copy back, one malloc per node / edge).  Informative only."""
+    import numpy as np
+    from turingassembler_b200 import build_graph_from_scratch
+    a = h_stream.numpy().reshape(-1, L + 1)
+    n = a.shape[0] // 2
+    td = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    paths = []
+    try:
+        for mate, block in ((1, a[:n]), (2, a[n:])):
+            rec = np.empty((n, 12 + L + 1 + 2 + L + 1), np.uint8)
+            ids = np.arange(n)
+            rec[:, 0] = ord("@")
+            for d in range(9):
+                rec[:, 1 + d] = ord("0") + (ids // 10 ** (8 - d)) % 10
+            rec[:, 10] = ord("/"); rec[:, 11] = ord("0") + mate
+            rec[:, 12:12 + L + 1] = block                      # sequence + newline
+            o = 12 + L + 1
+            rec[:, o] = ord("+"); rec[:, o + 1] = 10
+            rec[:, o + 2:o + 2 + L] = ord("I"); rec[:, o + 2 + L] = 10
+            p = os.path.join(td, f"R{mate}.fq")
+            # header line needs its own newline: "@000000001/1\n"
+            hdr = rec[:, :12]
+            with open(p, "wb") as f:
+                f.write(np.concatenate([hdr, np.full((n, 1), 10, np.uint8), rec[:, 12:]], axis=1).tobytes())
+            paths.append(p)
+        threads = os.cpu_count() or 4
+        times = []
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            g = build_graph_from_scratch(k, threads, 32, [paths[0]], [paths[1]], td)
+            times.append(time.perf_counter() - t0)
+        sec = sum(times[1:]) / reps
+        return {"ms_per_step": sec * 1e3, "n_e": int(g.n_e), "threads": threads,
+                "what": "build_graph_from_scratch on 2 FASTQ files (RAM disk) -> struct asm_graph_t in host memory"}
+    finally:
+        for p in paths:
+            os.remove(p)
+        os.rmdir(td)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -224,6 +267,7 @@ def main():
     ap.add_argument("--impl", default="tagpu", choices=["tagpu", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-files", action="store_true", help="skip the informative FASTQ-files end-to-end measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -374,6 +418,11 @@ def main():
         "kernels": kernels,
         "clocks": sampler.summary(),
     }
+    if world == 1 and not args.no_files:
+        fe = files_e2e(torch, h_stream, k)
+        fe["value"] = n_inst / (fe["ms_per_step"] * 1e-3)
+        fe["unit"] = "kmers/s"
+        line["e2e_files"] = fe
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = reference_cpu(args.workload, 2, 1)[0]
     print(json.dumps(line))

@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
@@ -144,6 +145,191 @@ static size_t walk_sequences(const uint8_t *txt, size_t n, uint8_t *dst)
 	return o;
 }
 
+/* The pinned stream buffer is kept across calls (callers never run concurrently, SURVEY.md §8b "Threading"). */
+static uint8_t *g_stream_buf;
+static size_t g_stream_cap;
+static int g_stream_busy;
+
+static uint8_t *stream_buffer(size_t bytes)
+{
+	if (!g_stream_busy && g_stream_buf && g_stream_cap >= bytes) {
+		g_stream_busy = 1;
+		return g_stream_buf;
+	}
+	uint8_t *s = tagpu_pinned_alloc(bytes);
+	if (!s)
+		TAGPU_FATAL("cannot allocate %zu bytes of pinned host memory", bytes);
+	if (!g_stream_busy) {
+		tagpu_pinned_free(g_stream_buf);
+		g_stream_buf = s;
+		g_stream_cap = bytes;
+		g_stream_busy = 1;
+	}
+	return s;
+}
+
+/* ---- tiny task pool: n_tasks independent tasks on up to n_threads pthreads */
+struct task_pool {
+	void (*fn)(size_t task, void *arg);
+	void *arg;
+	size_t n_tasks;
+	size_t next; /* __sync counter */
+};
+
+static void *task_pool_worker(void *raw)
+{
+	struct task_pool *tp = raw;
+	for (;;) {
+		size_t t = __sync_fetch_and_add(&tp->next, 1);
+		if (t >= tp->n_tasks)
+			return NULL;
+		tp->fn(t, tp->arg);
+	}
+}
+
+static void run_tasks(size_t n_tasks, int n_threads, void (*fn)(size_t, void *), void *arg)
+{
+	struct task_pool tp = { fn, arg, n_tasks, 0 };
+	if (n_threads > 64) n_threads = 64;
+	if ((size_t)n_threads > n_tasks) n_threads = (int)n_tasks;
+	if (n_threads <= 1) {
+		task_pool_worker(&tp);
+		return;
+	}
+	pthread_t th[64];
+	for (int i = 0; i < n_threads; ++i)
+		pthread_create(th + i, NULL, task_pool_worker, &tp);
+	for (int i = 0; i < n_threads; ++i)
+		pthread_join(th[i], NULL);
+}
+
+/* ---- plain (uncompressed) FASTQ, exact and parallel: the file is cut into chunks; newlines are counted per chunk, a
+ * prefix sum gives every chunk the number of the line it starts in, and then every chunk copies the bytes that lie on
+ * sequence lines (line 2 of every 4, /root/reference/src/get_buffer.c:339-348) — no record-boundary guessing. */
+#define INGEST_CHUNK ((size_t)16 << 20)
+
+struct pfq {
+	struct read_file *f;
+	int fd;
+	size_t n_chunks;
+	int mapped;        /* txt is an mmap of the file */
+	size_t *nl;        /* newlines in chunk, then: line number of the chunk's first byte */
+	size_t *out;       /* sequence bytes of the chunk, then: their offset in dst */
+};
+
+static void pfq_read(size_t c, void *raw)
+{
+	struct pfq *p = raw;
+	size_t lo = c * INGEST_CHUNK, hi = lo + INGEST_CHUNK < p->f->n_txt ? lo + INGEST_CHUNK : p->f->n_txt;
+	while (lo < hi) {
+		ssize_t r = pread(p->fd, p->f->txt + lo, hi - lo, (off_t)lo);
+		if (r <= 0)
+			TAGPU_FATAL("cannot read %s", p->f->path);
+		lo += (size_t)r;
+	}
+}
+
+static void pfq_count_nl(size_t c, void *raw)
+{
+	struct pfq *p = raw;
+	const uint8_t *t = p->f->txt;
+	size_t lo = c * INGEST_CHUNK, hi = lo + INGEST_CHUNK < p->f->n_txt ? lo + INGEST_CHUNK : p->f->n_txt, n = 0;
+	while (lo < hi) {
+		const uint8_t *q = memchr(t + lo, '\n', hi - lo);
+		if (!q)
+			break;
+		++n;
+		lo = (size_t)(q - t) + 1;
+	}
+	p->nl[c] = n;
+}
+
+/* bytes [lo, hi) of the chunk that lie on sequence lines; with dst != NULL they are copied.  A '\r' right before the
+ * line's '\n' is dropped; a last sequence line without a newline gets one. */
+static size_t pfq_walk(struct pfq *p, size_t c, uint8_t *dst)
+{
+	const uint8_t *t = p->f->txt;
+	const size_t n = p->f->n_txt;
+	size_t lo = c * INGEST_CHUNK, hi = lo + INGEST_CHUNK < n ? lo + INGEST_CHUNK : n, line = p->nl[c], o = 0;
+	while (lo < hi) {
+		const uint8_t *q = memchr(t + lo, '\n', hi - lo);
+		size_t e = q ? (size_t)(q - t) : hi;                 /* end of this line's bytes inside the chunk */
+		if ((line & 3) == 1) {
+			size_t len = e - lo;
+			const int ends_line = q != NULL || e == n;       /* the line really ends at e (not just the chunk) */
+			if (len && ends_line && t[e - 1] == '\r')
+				--len;
+			else if (len && !ends_line && e == hi && t[e - 1] == '\r' && hi < n && t[hi] == '\n')
+				--len;                                   /* "\r" | "\n" split by the chunk border */
+			if (dst) memcpy(dst + o, t + lo, len);
+			o += len;
+			if (q || e == n) {                               /* terminate the read (also when the file lacks the last newline) */
+				if (dst) dst[o] = '\n';
+				++o;
+			}
+		}
+		if (!q)
+			break;
+		++line;
+		lo = e + 1;
+	}
+	return o;
+}
+
+static void pfq_size(size_t c, void *raw)
+{
+	struct pfq *p = raw;
+	p->out[c] = pfq_walk(p, c, NULL);
+}
+
+static void pfq_copy(size_t c, void *raw)
+{
+	struct pfq *p = raw;
+	pfq_walk(p, c, p->f->dst + p->out[c]);
+}
+
+/* returns 1 and fills f->txt / n_txt / n_seq (+ keeps per-chunk tables in *keep) if the file is plain FASTQ */
+static int pfq_open(struct read_file *f, int n_threads, struct pfq *p)
+{
+	int fd = open(f->path, O_RDONLY);
+	if (fd < 0)
+		TAGPU_FATAL("cannot open %s", f->path);
+	unsigned char magic[2] = { 0, 0 };
+	struct stat st;
+	if (pread(fd, magic, 2, 0) < 1 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || magic[0] != '@') {
+		close(fd);
+		return 0;                                                /* gzip, FASTA, pipe, empty: serial path */
+	}
+	memset(p, 0, sizeof(*p));
+	p->f = f;
+	p->fd = fd;
+	f->n_txt = (size_t)st.st_size;
+	p->n_chunks = (f->n_txt + INGEST_CHUNK - 1) / INGEST_CHUNK;
+	p->nl = calloc(p->n_chunks + 1, sizeof(size_t));
+	p->out = calloc(p->n_chunks + 1, sizeof(size_t));
+	/* map the file (page-cache pages, no copy); fall back to reading it into memory */
+	void *m = mmap(NULL, f->n_txt, PROT_READ, MAP_PRIVATE, fd, 0);
+	if (m != MAP_FAILED) {
+		f->txt = m;
+		p->mapped = 1;
+		madvise(m, f->n_txt, MADV_SEQUENTIAL);
+	} else {
+		f->txt = malloc(f->n_txt + 1);
+		if (!f->txt)
+			TAGPU_FATAL("out of host memory reading %s", f->path);
+		run_tasks(p->n_chunks, n_threads, pfq_read, p);
+	}
+	close(fd);
+	run_tasks(p->n_chunks, n_threads, pfq_count_nl, p);
+	size_t acc = 0;
+	for (size_t c = 0; c < p->n_chunks; ++c) { size_t v = p->nl[c]; p->nl[c] = acc; acc += v; }
+	run_tasks(p->n_chunks, n_threads, pfq_size, p);
+	acc = 0;
+	for (size_t c = 0; c < p->n_chunks; ++c) { size_t v = p->out[c]; p->out[c] = acc; acc += v; }
+	f->n_seq = acc;
+	return 1;
+}
+
 static void *ingest_phase1(void *raw)
 {
 	struct read_file *f = raw;
@@ -163,36 +349,56 @@ static void *ingest_phase2(void *raw)
 
 int64_t tagpu_load_reads(int n_files, char **files, int n_threads, uint8_t **stream)
 {
-	(void)n_threads; /* one thread per file */
+	if (n_threads < 1) n_threads = 1;
 	struct read_file *f = calloc(n_files, sizeof(*f));
+	struct pfq *pq = calloc(n_files, sizeof(*pq));
+	int *plain = calloc(n_files, sizeof(int));
 	pthread_t *th = calloc(n_files, sizeof(pthread_t));
+	/* plain FASTQ files: parallel inside the file; everything else (gzip, FASTA): one thread per file */
 	for (int i = 0; i < n_files; ++i) {
 		f[i].path = files[i];
-		pthread_create(th + i, NULL, ingest_phase1, f + i);
+		plain[i] = pfq_open(f + i, n_threads, pq + i);
 	}
+	for (int i = 0; i < n_files; ++i)
+		if (!plain[i]) pthread_create(th + i, NULL, ingest_phase1, f + i);
 	size_t total = 0;
 	for (int i = 0; i < n_files; ++i) {
-		pthread_join(th[i], NULL);
+		if (!plain[i]) pthread_join(th[i], NULL);
 		total += f[i].n_seq;
 	}
-	uint8_t *s = tagpu_pinned_alloc(total + 64);
-	if (!s)
-		TAGPU_FATAL("cannot allocate %zu bytes of pinned host memory", total);
+	uint8_t *s = stream_buffer(total + 64);
 	size_t o = 0;
 	for (int i = 0; i < n_files; ++i) {
 		f[i].dst = s + o;
 		o += f[i].n_seq;
-		pthread_create(th + i, NULL, ingest_phase2, f + i);
+		if (!plain[i]) pthread_create(th + i, NULL, ingest_phase2, f + i);
+	}
+	for (int i = 0; i < n_files; ++i) {
+		if (plain[i]) {
+			run_tasks(pq[i].n_chunks, n_threads, pfq_copy, pq + i);
+			if (pq[i].mapped) munmap(f[i].txt, f[i].n_txt);
+			else free(f[i].txt);
+			free(pq[i].nl);
+			free(pq[i].out);
+		}
 	}
 	for (int i = 0; i < n_files; ++i)
-		pthread_join(th[i], NULL);
+		if (!plain[i]) pthread_join(th[i], NULL);
 	free(f);
+	free(pq);
+	free(plain);
 	free(th);
 	*stream = s;
 	return (int64_t)total;
 }
 
-void tagpu_free_reads(uint8_t *stream) { tagpu_pinned_free(stream); }
+void tagpu_free_reads(uint8_t *stream)
+{
+	if (stream && stream == g_stream_buf)
+		g_stream_busy = 0;      /* kept for the next call (pinning 600 MB costs more than parsing it) */
+	else
+		tagpu_pinned_free(stream);
+}
 
 /* Rank's share of a read stream: nominal byte split, each cut moved forward to just after the next newline, so every
  * read belongs to exactly one rank (windows never span reads: App. A.1). */

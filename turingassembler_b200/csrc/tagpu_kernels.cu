@@ -987,17 +987,29 @@ extern "C" int tagpu_copy_graph(tagpu_ctx *ctx, struct tagpu_flat_graph *h)
 	return 0;
 }
 
-// pinned host allocation for the FASTQ loader in tagpu_host.c (keeps cuda_runtime.h out of the C file)
+// pinned host allocation for the FASTQ loader in tagpu_host.c (keeps cuda_runtime.h out of the C file).  Without a
+// usable CUDA device (the CPU-only test box exercises the ingest logic) the buffer is ordinary memory; no compute
+// path exists there anyway (tagpu_create fails).
+static void *g_unpinned[16];
+
 extern "C" void *tagpu_pinned_alloc(size_t bytes)
 {
 	void *p = nullptr;
-	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
-		cudaGetLastError();
-		return nullptr;
-	}
-	return p;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess) return p;
+	cudaGetLastError();
+	p = malloc(bytes ? bytes : 1);
+	for (int i = 0; p && i < 16; ++i)
+		if (!g_unpinned[i]) { g_unpinned[i] = p; return p; }
+	free(p);
+	return nullptr;
 }
-extern "C" void tagpu_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" void tagpu_pinned_free(void *p)
+{
+	if (!p) return;
+	for (int i = 0; i < 16; ++i)
+		if (g_unpinned[i] == p) { g_unpinned[i] = nullptr; free(p); return; }
+	cudaFreeHost(p);
+}
 extern "C" int tagpu_ctx_k(tagpu_ctx *ctx) { return ctx->k; }
 extern "C" int tagpu_ctx_K(tagpu_ctx *ctx) { return ctx->K; }
 extern "C" int tagpu_ctx_cutoff(tagpu_ctx *ctx) { return ctx->ci; }
