@@ -82,6 +82,15 @@ TAGPU_DI SkRec<W> tagpu_make_record(const uint64_t *pk, int end_q, int n_bases, 
 	return r;
 }
 
+// Minimizer (hash, position) of the window ending at tile position q.  General case: phase B left it at hs[q - w + 1].
+// w == 32 (k0 = 45, the reference's default): the van Herk blocks coincide with the 32-position words, phase A leaves
+// per-word prefix minima in hp and suffix minima in hs, and the window is a suffix of one word plus a prefix of the next.
+TAGPU_DI uint32_t tagpu_window_min(const uint32_t *hs, const uint32_t *hp, int q, int w)
+{
+	const int s = max(q - w + 1, 0);
+	return w == 32 ? min(hs[HIDX(s)], hp[HIDX(q)]) : hs[HIDX(s)];
+}
+
 // ---------------------------------------------------------------- pass 1
 // Super-k-mer = maximal run of consecutive valid windows that share the SAME minimizer occurrence (hash and position),
 // so a run never exceeds w = K - m + 1 windows and — unlike a cut at thread or tile boundaries — it is a function of the
@@ -109,6 +118,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 
 	// A. hash of the canonical m-mer ending at every position (invalid if the m-mer touches a non-ACGT byte), with the
 	//    position (mod 64) in the low bits: the minimum over a window then identifies one m-mer OCCURRENCE
+	const int w = K - m + 1;
 	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
 		const uint32_t mm = (1u << (2 * m)) - 1;
 		uint32_t fw = j ? (uint32_t)pk[j - 1] & mm : 0u;
@@ -117,17 +127,43 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 		int run = i1 ? (__ffs(i1) - 1) : 32;
 		uint64_t cur = pk[j];
 		uint32_t iv = inv[j];
+		if (w == 32) {
+			// the word IS a van Herk block: hashes stay in registers, prefix minima go to hp, suffix minima to hs
+			uint32_t h[32];
+			uint32_t acc = TAGPU_H_INVALID;
+#pragma unroll
+			for (int i = 0; i < 32; ++i) {
+				const uint32_t c = (uint32_t)(cur >> 62);
+				cur <<= 2;
+				const bool bad = (int)iv < 0;
+				iv <<= 1;
+				fw = ((fw << 2) | c) & mm;
+				rv = (rv >> 2) | ((3u - c) << (2 * (m - 1)));
+				run = bad ? 0 : run + 1;
+				const uint32_t cm = min(fw, rv);
+				h[i] = run >= m ? (((cm * 0x9e3779b1u) & ~63u) | (uint32_t)((j & 1) * 32 + i)) : TAGPU_H_INVALID;
+				acc = min(acc, h[i]);
+				hp[j * 33 + i] = acc;
+			}
+			acc = TAGPU_H_INVALID;
+#pragma unroll
+			for (int i = 31; i >= 0; --i) {
+				acc = min(acc, h[i]);
+				hs[j * 33 + i] = acc;
+			}
+		} else {
 #pragma unroll 8
-		for (int i = 0; i < 32; ++i) {
-			const uint32_t c = (uint32_t)(cur >> 62);
-			cur <<= 2;
-			const bool bad = (int)iv < 0;
-			iv <<= 1;
-			fw = ((fw << 2) | c) & mm;
-			rv = (rv >> 2) | ((3u - c) << (2 * (m - 1)));
-			run = bad ? 0 : run + 1;
-			const uint32_t cm = min(fw, rv);
-			hp[j * 33 + i] = run >= m ? (((cm * 0x9e3779b1u) & ~63u) | (uint32_t)((j & 1) * 32 + i)) : TAGPU_H_INVALID;
+			for (int i = 0; i < 32; ++i) {
+				const uint32_t c = (uint32_t)(cur >> 62);
+				cur <<= 2;
+				const bool bad = (int)iv < 0;
+				iv <<= 1;
+				fw = ((fw << 2) | c) & mm;
+				rv = (rv >> 2) | ((3u - c) << (2 * (m - 1)));
+				run = bad ? 0 : run + 1;
+				const uint32_t cm = min(fw, rv);
+				hp[j * 33 + i] = run >= m ? (((cm * 0x9e3779b1u) & ~63u) | (uint32_t)((j & 1) * 32 + i)) : TAGPU_H_INVALID;
+			}
 		}
 	}
 	__syncthreads();
@@ -137,8 +173,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 	//    forwards with a running prefix minimum and replaces hs[q - w + 1] by the minimum of window q — so afterwards
 	//    hs[q - w + 1] IS the minimizer of the window ending at q.  Everything a thread writes (the hs region of block
 	//    b - 1) is read only by itself, so the two passes need no barrier between them; hp stays read-only.
-	const int w = K - m + 1;
-	const int n_blocks = (TAGPU_HM_POS + w - 1) / w;
+	const int n_blocks = w == 32 ? 0 : (TAGPU_HM_POS + w - 1) / w;     // (w == 32: done in phase A)
 	for (int blk = threadIdx.x; blk < n_blocks; blk += blockDim.x) {
 		const int lo = blk * w, hi = min(lo + w, TAGPU_HM_POS);
 		// (both passes are unrolled by four with the loads issued first: the chain through `acc` is only the min)
@@ -193,11 +228,10 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 		else if (extra > 0) smear(extra);
 		const uint32_t vmask = __brev(~c);                          // bit i = position i of this word ends a valid window
 		const uint32_t pv = ~b & 1u;                                // ... and so does the last position of the word before
-		const int q0 = j * 32 - w + 1;                              // hs index of the window ending at this word's position 0
-		uint32_t pm = hs[HIDX(max(q0 - 1, 0))], ne = 0;
+		uint32_t pm = tagpu_window_min(hs, hp, j * 32 - 1, w), ne = 0;
 #pragma unroll
 		for (int i = 0; i < 32; ++i) {
-			const uint32_t cm = hs[HIDX(max(q0 + i, 0))];
+			const uint32_t cm = tagpu_window_min(hs, hp, j * 32 + i, w);
 			ne |= (cm != pm ? 1u : 0u) << i;
 			pm = cm;
 		}
@@ -226,7 +260,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 		const int st = upto ? 31 - __clz(upto) : -1 - __clz(Bprev);
 		const int nw = e - st + 1, end_q = wi * 32 + e;
 		if (nw > 32) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_RUN_LENGTH); continue; }
-		const uint32_t b = tagpu_bucket_of(hs[HIDX(end_q - w + 1)] >> 6, cfg.log2_buckets);
+		const uint32_t b = tagpu_bucket_of(tagpu_window_min(hs, hp, end_q, w) >> 6, cfg.log2_buckets);
 		const SkRec<W> rec = tagpu_make_record<W>(pk, end_q, nw + K - 1, nw);
 		const unsigned long long old = atomicAdd(cursor + b, 1ull | ((unsigned long long)nw << 32));
 		const uint32_t idx = (uint32_t)old;
