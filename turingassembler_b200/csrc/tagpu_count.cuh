@@ -739,12 +739,25 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 				const uint32_t tot_packed = __reduce_add_sync(0xffffffffu, wt);
 				const uint32_t total = tot_packed & 0xffffu, n_live = tot_packed >> 16;
 				uint32_t excl = __reduce_add_sync(0xffffffffu, lane < warp ? wt : 0u) + incl - pair;
+				// When the round leaves room behind its records (the usual case), every live record also gets its first
+				// window precomputed — forward and reverse complement — so that re-seeding in the window loop, which
+				// some lane of a warp does in almost every iteration, is two loads instead of funnel shifts and an rc.
+				const bool have_seeds = n_round + n_live <= 2u * C::THREADS;
 #pragma unroll
 				for (int h = 0; h < 2; ++h)
 					if (n_eff[h]) {
-						s_live[excl >> 16] = (uint16_t)(2u * tid + h);
-						s_scan[excl >> 16] = (uint16_t)excl;
+						const uint32_t rank = excl >> 16;
+						s_live[rank] = (uint16_t)(2u * tid + h);
+						s_scan[rank] = (uint16_t)excl;
 						excl += (1u << 16) + n_eff[h];
+						if (have_seeds) {
+							const Key<W> f0 = tagpu_record_window(s_rec[2u * tid + h], 2 * ((int)n_eff[h] - 1), K);
+							const Key<W> r0 = KO::rc(f0, K);
+							SkRec<W> sd;
+							if (W == 1) { sd.w[0] = f0.lo; sd.w[1] = r0.lo; }
+							else { sd.w[0] = f0.lo; sd.w[1] = KO::hi(f0); sd.w[2 * W - 2] = r0.lo; sd.w[2 * W - 1] = KO::hi(r0); }
+							s_rec[n_round + rank] = sd;
+						}
 					}
 				if (tid == 0) s_scan[n_live] = (uint16_t)total;
 				__syncthreads();                                    // staged records + prefix visible to everybody
@@ -793,8 +806,14 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 							mult = (uint32_t)(wl >> 48) & 0xffu;
 							j = 0;
 							w0 = rp->w[0];
-							fw = tagpu_record_window(*rp, 2 * (n_r - 1), K);
-							rv = KO::rc(fw, K);
+							if (have_seeds) {
+								const SkRec<W> sd = s_rec[n_round + r];
+								fw = KO::make(W == 1 ? 0ull : sd.w[1], sd.w[0]);
+								rv = KO::make(W == 1 ? 0ull : sd.w[2 * W - 1], W == 1 ? sd.w[1] : sd.w[2 * W - 2]);
+							} else {
+								fw = tagpu_record_window(*rp, 2 * (n_r - 1), K);
+								rv = KO::rc(fw, K);
+							}
 						} else {                                             // next window of the same record: roll one base
 							const uint32_t c = (uint32_t)(w0 >> (2 * (n_r - 1 - j))) & 3u;
 							fw = KO::push(fw, c, kmask);
