@@ -255,3 +255,14 @@ def test_dropin_library_boundary(oracle, tmp_path):
         assert (out / f"KMC_{k + 1}_count.kmc_suf").exists()
         bad, txt = _oracle.canon_text(oracle, str(out / f"graph_k_{k}_level_0.bin"), 0)
         assert bad == 0 and hashlib.md5(txt).hexdigest() == gold["canon0_md5"]
+
+
+def test_list_ranking_variant():
+    """The work-efficient list ranking (Helman-JaJa; default above 48 M chain vertices) must give the same graphs as pointer
+    jumping: the golden, adversarial-topology and edge-case tests again in a subprocess with TAGPU_LIST_RANKING=hj."""
+    import subprocess
+    import sys
+    env = dict(os.environ, TAGPU_LIST_RANKING="hj")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-q", "-m", "gpu", "-x",
+                        "-k", "golden or hairpins or edge_cases or every_key_width"], capture_output=True, text=True, env=env, timeout=1200)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]

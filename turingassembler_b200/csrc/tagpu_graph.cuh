@@ -298,6 +298,67 @@ __global__ void __launch_bounds__(512) k_jump_all(unsigned long long *jump, uint
 	if (blockIdx.x == 0 && threadIdx.x == 0) ctr[CTR_JUMP_ROUNDS] = (unsigned long long)round + 1;
 }
 
+// ---------------------------------------------------------------- C3': list ranking for large inputs (Helman-JaJa)
+// Wyllie's pointer jumping above touches every vertex in each of ceil(log2(longest unitig)) rounds; when the per-vertex
+// arrays are far larger than L2 (hundreds of millions of k-mers, unitigs of 10^4..10^5 k-mers) that is 15-20 random
+// HBM accesses per vertex.  Work-efficient alternative, ~2 random accesses per vertex whatever the unitig lengths:
+//   k_hj_mark     every ~64th chain vertex (by hash) and every chain head (its predecessor is a node, i.e. the successor
+//                 of its reverse-complement twin is a node) becomes a SPLITTER; splitters are listed compactly
+//   k_hj_walk     one thread per splitter walks its sublist to the next splitter / the chain end, leaving
+//                 (splitter index, hops) in own[] of every vertex it passes -> reduced list jump2[splitter index]
+//   k_jump_all    Wyllie on the reduced list (1/40 of the vertices: L2-resident)
+//   k_hj_finish   every vertex takes terminal and distance from its splitter
+// Vertices of node-free cycles end up unterminated exactly as with Wyllie (never visited, or their splitters never
+// terminate within the round cap) and are skipped by the later stages.
+TAGPU_DI bool tagpu_hj_sampled(uint32_t cv) { return ((cv * 0x9e3779b1u) >> 26) == 0u; }
+
+__global__ void __launch_bounds__(256) k_hj_mark(const unsigned long long *__restrict__ jump, uint32_t n_cv, uint32_t *__restrict__ spl_bits,
+						  uint32_t *__restrict__ spl_list, unsigned long long *__restrict__ own, unsigned long long *ctr)
+{
+	const uint32_t cv = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+	bool spl = false;
+	if (cv < n_cv) spl = tagpu_hj_sampled(cv) || ((uint32_t)jump[cv ^ 1u] & TAGPU_TERM);
+	const uint32_t word = __ballot_sync(0xffffffffu, spl);
+	if (lane == 0 && cv < n_cv) spl_bits[cv >> 5] = word;
+	const unsigned long long base = tagpu_warp_alloc(ctr + CTR_CHAIN, spl ? 1u : 0u);   // CTR_CHAIN: number of splitters
+	if (spl) {
+		spl_list[base] = cv;
+		own[cv] = ((unsigned long long)0xffffffffu << 32) | (uint32_t)base;             // a splitter remembers its own index
+	}
+}
+
+__global__ void __launch_bounds__(256) k_hj_walk(const unsigned long long *__restrict__ jump, const uint32_t *__restrict__ spl_bits,
+						  const uint32_t *__restrict__ spl_list, uint32_t n_spl, unsigned long long *__restrict__ own,
+						  unsigned long long *__restrict__ jump2)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_spl) return;
+	uint32_t cur = spl_list[t], hops = 0;
+	for (;;) {
+		const uint32_t p = (uint32_t)jump[cur];
+		if (p & TAGPU_TERM) { jump2[t] = tagpu_pack_jump(TAGPU_TERM | cur, hops); return; }   // chain ends at cur
+		++hops;
+		if ((spl_bits[p >> 5] >> (p & 31u)) & 1u) { jump2[t] = tagpu_pack_jump((uint32_t)own[p], hops); return; }  // next splitter's index
+		own[p] = ((unsigned long long)hops << 32) | t;
+		cur = p;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_hj_finish(unsigned long long *__restrict__ jump, uint32_t n_cv, const unsigned long long *__restrict__ own,
+						    const unsigned long long *__restrict__ jump2)
+{
+	const uint32_t cv = blockIdx.x * blockDim.x + threadIdx.x;
+	if (cv >= n_cv) return;
+	const unsigned long long o = own[cv];
+	unsigned long long out = tagpu_pack_jump(cv, 0);                // unterminated (node-free cycle) unless shown otherwise
+	if (o != ~0ull) {
+		const uint32_t t = (uint32_t)o, hops = (uint32_t)(o >> 32) == 0xffffffffu ? 0u : (uint32_t)(o >> 32);
+		const unsigned long long j2 = jump2[t];
+		if ((uint32_t)j2 & TAGPU_TERM) out = tagpu_pack_jump((uint32_t)j2, (uint32_t)(j2 >> 32) - hops);
+	}
+	jump[cv] = out;
+}
+
 // ---------------------------------------------------------------- flat graph in device memory
 struct FlatGraph {
 	uint32_t *e_src, *e_dst, *e_rc, *e_len;     // node-vertex ids = 2 * node ordinal + orient

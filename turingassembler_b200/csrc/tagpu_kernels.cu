@@ -50,7 +50,7 @@ struct tagpu_ctx {
 	// build_local_assembly_graph: (k+1)-mers of the flanking contigs appended behind the solid ones (count 0), and the contigs
 	uint64_t n_garbage = 0;
 	bool local_mode = false;
-	Buf g_key, comb_key, comb_cnt, g_seq;
+	Buf g_key, comb_key, comb_cnt, g_seq, hj_own, hj_bits, hj_list, hj_jump2;
 	int n_contigs = 0;
 	uint64_t contig_off[4] = { 0 };
 	uint32_t contig_len[4] = { 0 };
@@ -192,7 +192,7 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	dist_release(ctx);
-	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->hj_own, &ctx->hj_bits, &ctx->hj_list, &ctx->hj_jump2, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
 			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
 	for (Buf *b : bufs)
@@ -508,12 +508,37 @@ static int graph_stage(tagpu_ctx *ctx)
 			ctx->jump_grid = ctx->n_sm * (per_sm > 0 ? per_sm : 1);
 		}
 		int max_rounds = 40;
-		uint32_t n_cv_arg = n_cv;
-		void *args[] = { &jump, &n_cv_arg, &ctr, &max_rounds };
-		{
+		// small inputs: plain pointer jumping (the arrays sit in L2); large ones: work-efficient list ranking
+		static const char *rank_env = getenv("TAGPU_LIST_RANKING");      // "hj" / "wyllie" force one of them (tests)
+		const bool hj = rank_env ? !strcmp(rank_env, "hj") : n_cv >= (48u << 20);
+		if (!hj) {
+			uint32_t n_cv_arg = n_cv;
+			void *args[] = { &jump, &n_cv_arg, &ctr, &max_rounds };
 			ProfScope ps_(ctx, "k_jump_all");
 			CU(cudaLaunchCooperativeKernel((void *)k_jump_all, dim3(ctx->jump_grid), dim3(512), args, 0, ctx->stream));
 			++ctx->launches;
+		} else {
+			if (ensure(ctx, ctx->hj_own, ((size_t)n_cv + 1) * 8) || ensure(ctx, ctx->hj_bits, ((size_t)n_cv / 32 + 2) * 4) ||
+			    ensure(ctx, ctx->hj_list, ((size_t)n_cv + 1) * 4))
+				return -1;
+			unsigned long long *own = (unsigned long long *)ctx->hj_own.p;
+			uint32_t *bits = (uint32_t *)ctx->hj_bits.p, *list = (uint32_t *)ctx->hj_list.p;
+			{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(own, 0xff, ((size_t)n_cv + 1) * 8, ctx->stream)); }
+			{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctr + CTR_CHAIN, 0, 8, ctx->stream)); }
+			LAUNCH(k_hj_mark, (n_cv + 255) / 256, 256, jump, n_cv, bits, list, own, ctr);
+			if (read_counters(ctx)) return -1;
+			const uint32_t n_spl = (uint32_t)ctx->h_ctr[CTR_CHAIN];
+			if (ensure(ctx, ctx->hj_jump2, ((size_t)n_spl + 1) * 8)) return -1;
+			unsigned long long *jump2 = (unsigned long long *)ctx->hj_jump2.p;
+			if (n_spl) {
+				LAUNCH(k_hj_walk, (n_spl + 255) / 256, 256, jump, bits, list, n_spl, own, jump2);
+				uint32_t n_arg = n_spl;
+				void *args[] = { &jump2, &n_arg, &ctr, &max_rounds };
+				ProfScope ps_(ctx, "k_jump_all");
+				CU(cudaLaunchCooperativeKernel((void *)k_jump_all, dim3(ctx->jump_grid), dim3(512), args, 0, ctx->stream));
+				++ctx->launches;
+			}
+			LAUNCH(k_hj_finish, (n_cv + 255) / 256, 256, jump, n_cv, own, jump2);
 		}
 	}
 	if (n_nodes)
