@@ -2,17 +2,22 @@
 //
 // Why: on this B200 a (load + compare + atomic add) against an HBM-resident table sustains ~18 Gop/s and an
 // L2-resident one ~60-95 Gop/s, while the same sequence on a shared-memory table sustains ~840 Gop/s chip-wide
-// (tools/ubench_atomics.cu, profiles/ubench_r1.txt).  So the key space is cut into P buckets small enough that one
+// (tools/ubench_atomics.cu, profiles/r1_ubench_atomics.txt).  So the key space is cut into P buckets small enough that one
 // bucket's distinct keys fit a shared-memory table, and buckets are shipped through HBM in a compact form:
 //
-//   pass 1  k_partition   reads the ASCII stream once; every maximal run of consecutive valid windows whose
-//                         minimizer maps to the same bucket ("super-k-mer", as in KMC 2/3 — the design of the
-//                         library the reference delegates this stage to) becomes ONE fixed-size record
-//                         (2-bit bases + length) appended to the bucket's region.  ~1.5-2 B per instance
-//                         instead of 8/16 B for a raw key.
-//   pass 2  k_count_buckets  one CTA per bucket: re-expands records into canonical keys and counts them in a
-//                         shared-memory open-addressing table (LDS + ATOMS only), then emits the keys with
-//                         count >= ci.  A bucket with too many distinct keys is re-run on hash sub-classes.
+//   pass 1  k_partition   reads the ASCII stream once; every maximal run of consecutive valid windows that share
+//                         one minimizer OCCURRENCE ("super-k-mer", as in KMC 2/3 — the design of the library the
+//                         reference delegates this stage to) becomes ONE fixed-size record (2-bit bases + window
+//                         count) appended to the region of the minimizer's bucket.  ~2.2 B per instance instead of
+//                         8/16 B for a raw key, and identical genomic sites yield identical records.
+//   grouping              k_pull_cursors / k_scan_blocks / k_mark_groups: consecutive buckets are packed into groups
+//                         of ~2 x table-slots windows with one grid-wide prefix sum.
+//   pass 2  k_count_buckets  persistent CTAs, one group at a time: records staged in shared memory in canonical
+//                         orientation, duplicate records collapsed, live windows cut into equal per-thread segments,
+//                         canonical keys counted in a shared-memory open-addressing table (LDS + ATOMS only), keys
+//                         with count >= ci emitted.  A group with too many distinct keys is re-run on hash
+//                         sub-classes.  With several GPUs the records of a bucket are read from every rank's regions
+//                         through NVLink peer loads (CountPeers).
 //
 // The bucket of a window is a function of its canonical key only (minimum over the hashes of the canonical m-mers it
 // contains), so all instances of a key — on either strand — meet in the same bucket and counts are exact.
