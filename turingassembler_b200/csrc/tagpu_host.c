@@ -447,6 +447,57 @@ static void free_flat(struct tagpu_flat_graph *h)
 
 static inline int popc4(unsigned x) { return __builtin_popcount(x & 15u); }
 
+#define FILL_CHUNK 8192
+
+struct fill_job {
+	struct tagpu_flat_graph *h;
+	struct asm_graph_t *g;
+	int failed;
+};
+
+static void fill_nodes_task(size_t c, void *raw)
+{
+	struct fill_job *j = raw;
+	const struct tagpu_flat_graph *h = j->h;
+	const int64_t lo = (int64_t)c * FILL_CHUNK, hi = lo + FILL_CHUNK < (int64_t)h->n_nodes ? lo + FILL_CHUNK : (int64_t)h->n_nodes;
+	for (int64_t i = lo; i < hi; ++i) {
+		const unsigned m = h->node_mask[i];
+		int64_t e = h->node_ebase[i];
+		for (int o = 0; o < 2; ++o) {
+			struct asm_node_t *nd = j->g->nodes + 2 * i + o;
+			const int deg = popc4(o ? m >> 4 : m);
+			nd->rc_id = 2 * i + (o ^ 1);
+			nd->deg = deg;
+			nd->adj = malloc(deg * sizeof(gint_t)); /* malloc(0) for dead ends, like kmer_build.c:605-606 */
+			for (int a = 0; a < deg; ++a)
+				nd->adj[a] = e++;
+		}
+	}
+}
+
+static void fill_edges_task(size_t c, void *raw)
+{
+	struct fill_job *j = raw;
+	const struct tagpu_flat_graph *h = j->h;
+	const int64_t lo = (int64_t)c * FILL_CHUNK, hi = lo + FILL_CHUNK < (int64_t)h->n_e ? lo + FILL_CHUNK : (int64_t)h->n_e;
+	for (int64_t e = lo; e < hi; ++e) {
+		struct asm_edge_t *ed = j->g->edges + e;
+		const size_t words = ((size_t)h->e_len[e] + 15) >> 4;
+		ed->count = h->e_count[e];
+		ed->seq_len = h->e_len[e];
+		ed->seq = malloc(words * sizeof(uint32_t));
+		if (!ed->seq) {
+			j->failed = 1;
+			return;
+		}
+		memcpy(ed->seq, h->e_seq + h->e_off[e], words * sizeof(uint32_t));
+		ed->source = h->e_src[e];
+		ed->target = h->e_dst[e];
+		ed->rc_id = h->e_rc[e];
+		/* n_holes, p_holes, l_holes, barcodes, lock: zero from calloc (kmer_build.c:567) */
+	}
+}
+
 /* Fills a caller-owned, uninitialised struct asm_graph_t exactly as build_asm_graph_from_kmhash leaves it
  * (/root/reference/src/kmer_build.c:567-575): nodes/edges are single calloc blocks, every adj and every seq is its
  * own allocation because later stages realloc/free them one by one. g->candidates is not touched. */
@@ -466,33 +517,14 @@ int tagpu_fill_asm_graph(tagpu_ctx *ctx, struct asm_graph_t *g)
 	g->edges = calloc(n_e ? n_e : 1, sizeof(struct asm_edge_t));
 	if (!g->nodes || !g->edges)
 		return -1;
-	for (int64_t i = 0; i < n_nodes; ++i) {
-		const unsigned m = h.node_mask[i];
-		int64_t e = h.node_ebase[i];
-		for (int o = 0; o < 2; ++o) {
-			struct asm_node_t *nd = g->nodes + 2 * i + o;
-			const int deg = popc4(o ? m >> 4 : m);
-			nd->rc_id = 2 * i + (o ^ 1);
-			nd->deg = deg;
-			nd->adj = malloc(deg * sizeof(gint_t)); /* malloc(0) for dead ends, like kmer_build.c:605-606 */
-			for (int j = 0; j < deg; ++j)
-				nd->adj[j] = e++;
-		}
-	}
-	for (int64_t e = 0; e < n_e; ++e) {
-		struct asm_edge_t *ed = g->edges + e;
-		const size_t words = ((size_t)h.e_len[e] + 15) >> 4;
-		ed->count = h.e_count[e];
-		ed->seq_len = h.e_len[e];
-		ed->seq = malloc(words * sizeof(uint32_t));
-		if (!ed->seq)
-			return -1;
-		memcpy(ed->seq, h.e_seq + h.e_off[e], words * sizeof(uint32_t));
-		ed->source = h.e_src[e];
-		ed->target = h.e_dst[e];
-		ed->rc_id = h.e_rc[e];
-		/* n_holes, p_holes, l_holes, barcodes, lock: zero from calloc (kmer_build.c:567) */
-	}
+	/* millions of small allocations: spread over the host threads (glibc malloc keeps one arena per thread) */
+	struct fill_job job = { &h, g, 0 };
+	int n_threads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+	if (n_threads > 16) n_threads = 16;
+	run_tasks((size_t)((n_nodes + FILL_CHUNK - 1) / FILL_CHUNK), n_threads, fill_nodes_task, &job);
+	run_tasks((size_t)((n_e + FILL_CHUNK - 1) / FILL_CHUNK), n_threads, fill_edges_task, &job);
+	if (job.failed)
+		return -1;
 	free_flat(&h);
 	return 0;
 }
