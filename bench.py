@@ -36,7 +36,7 @@ WORKLOADS = {
 L = 151
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the last `ncu --set full` capture of the C2 workload
 # (profiles/), keyed by kernel; None until such a capture exists for the current kernels
-TRAFFIC = {"k_count_buckets<W>": 0.973974e9 + 0.144152e9, "k_partition<W>": 0.610278e9 + 0.909922e9}  # profiles/r1_ncu_top_kernels_raw.txt
+TRAFFIC = {"k_count_buckets<W>": 0.973014e9 + 0.140346e9, "k_partition<W>": 0.610491e9 + 0.909045e9}  # profiles/r1_ncu_top_kernels_raw.txt
 
 
 N_CHUNKS = 16   # the read set is generated in 16 independently seeded chunks of pairs, so a rank can make just its share

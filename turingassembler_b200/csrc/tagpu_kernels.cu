@@ -329,7 +329,8 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 		// The reads are still in host memory (d_seq is our staging buffer): upload them in chunks on a second stream and
 		// run pass 1 over every chunk as soon as it has landed, so the PCIe copy hides the partition pass.  A tile needs
 		// one word of look-ahead, so a launch covers the tiles whose right halo is already on the device.
-		const uint64_t chunk_tiles = n_tiles / TAGPU_UPLOAD_CHUNKS + 1;
+		uint64_t chunk_tiles = n_tiles / TAGPU_UPLOAD_CHUNKS + 1;
+		if (chunk_tiles < 512) chunk_tiles = 512;                // >= 4 MB per copy: small inputs go up in one piece
 		const uint8_t *h_src = ctx->h_src;
 		ctx->h_src = nullptr;
 		uint64_t copied = 0, tile0 = 0;
