@@ -529,7 +529,9 @@ static int graph_stage(tagpu_ctx *ctx)
 			LAUNCH(k_hj_mark, (n_cv + 255) / 256, 256, jump, n_cv, bits, list, own, ctr);
 			if (read_counters(ctx)) return -1;
 			const uint32_t n_spl = (uint32_t)ctx->h_ctr[CTR_CHAIN];
-			if (ensure(ctx, ctx->hj_jump2, ((size_t)n_spl + 1) * 8)) return -1;
+			// (sized with head-room: the splitter count varies a little from build to build with the table layout)
+			const size_t spl_cap = (size_t)n_spl + 1 > (size_t)n_cv / 16 ? (size_t)n_spl + 1 : (size_t)n_cv / 16;
+			if (ensure(ctx, ctx->hj_jump2, spl_cap * 8)) return -1;
 			unsigned long long *jump2 = (unsigned long long *)ctx->hj_jump2.p;
 			if (n_spl) {
 				LAUNCH(k_hj_walk, (n_spl + 255) / 256, 256, jump, bits, list, n_spl, own, jump2);
