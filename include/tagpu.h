@@ -79,6 +79,10 @@ void tagpu_set_cutoff(tagpu_ctx *ctx, int ci);
 /* 0 (default) = build edge counts; 1 = build_graph_from_scratch_without_count behaviour */
 void tagpu_set_skip_counts(tagpu_ctx *ctx, int skip);
 const char *tagpu_last_error(tagpu_ctx *ctx);
+/* 1 = two-level graph stage: the solid (k+1)-mers are first contracted into paths inside the bucket groups of the count stage
+ * (csrc/tagpu_contract.cuh); same graph, but tagpu_copy_kmers is then unavailable (hidden k-mers never reach the table).
+ * Single-GPU builds without contig garbage only; everything else uses the one-level stage. */
+void tagpu_set_contract(tagpu_ctx *ctx, int on);
 /* per-kernel CUDA-event timing of the next builds: JSON {"kernel": {"ms": total, "launches": n}, ...} */
 void tagpu_set_profile(tagpu_ctx *ctx, int on);
 const char *tagpu_profile_json(tagpu_ctx *ctx);

@@ -130,6 +130,7 @@ def load_library() -> C.CDLL:
     lib.tagpu_set_cutoff.argtypes = [vp, i32]
     lib.tagpu_set_skip_counts.argtypes = [vp, i32]
     lib.tagpu_set_profile.argtypes = [vp, i32]
+    lib.tagpu_set_contract.argtypes = [vp, i32]
     lib.tagpu_profile_json.restype = C.c_char_p
     lib.tagpu_profile_json.argtypes = [vp]
     lib.tagpu_last_error.restype = C.c_char_p
@@ -200,6 +201,7 @@ class Tagpu:
         if not self.ctx:
             raise TagpuError("tagpu_create failed: no usable CUDA device (libtagpu has no CPU fallback)")
         self.lib.tagpu_set_cutoff(self.ctx, cutoff)
+        self.contract = False
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -221,6 +223,10 @@ class Tagpu:
 
     def set_cutoff(self, ci: int):
         self.lib.tagpu_set_cutoff(self.ctx, ci)
+
+    def set_contract(self, on: bool):
+        self.contract = bool(on)
+        self.lib.tagpu_set_contract(self.ctx, int(on))
 
     def set_profile(self, on: bool):
         self.lib.tagpu_set_profile(self.ctx, int(on))

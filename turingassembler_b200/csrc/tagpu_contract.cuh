@@ -1,0 +1,448 @@
+// Graph stage, two-level variant: contract the solid (k+1)-mer list inside the bucket groups of the count stage first,
+// then run the global stage on the contracted paths.
+//
+// Every harvest of k_count_buckets leaves a contiguous block of solid (k+1)-mers whose minimizers lie in one group of
+// buckets (SolidBlock).  A k-mer z met in such a block can be HIDDEN when
+//   (i)   the bucket of its own minimizer mu(z) belongs to the block's group, and
+//   (ii)  none of its 8 possible one-base extensions brings an m-mer that hashes below mu(z)
+// — then every (k+1)-mer containing z has minimizer mu(z) and lives in this very block, so the block-local edge mask of z
+// is its global one — and
+//   (iii) that mask is 1-in-1-out.
+// Hidden k-mers are interior to a unitig by construction.  k_contract chains the (k+1)-mers of a block across hidden
+// k-mers into PATHS (first / last (k+1)-mer, number of (k+1)-mers, summed count, packed interior bases) entirely in
+// shared memory; the global kernels below are the path-driven, base-weighted counterparts of tagpu_graph.cuh: only the
+// END k-mers of the paths enter the HBM table, and list ranking carries distances in bases.
+// A path and its reverse complement are one object (like a canonical (k+1)-mer); a cycle made of hidden k-mers only is a
+// node-free component and is dropped here exactly as the reference never emits it.
+#pragma once
+#include "tagpu_count.cuh"
+#include "tagpu_graph.cuh"
+
+constexpr int TAGPU_CONTRACT_MAXN = 512;          // (k+1)-mers of a block that k_contract handles; larger blocks stay single
+constexpr int TAGPU_CONTRACT_THREADS = 256;
+constexpr uint32_t TAGPU_OE_END = 0xffffu;
+
+template <int W> struct PathStore {
+	Key<W> *first, *last;             // first / last (k+1)-mer of the path, oriented along the path
+	uint32_t *n;                      // (k+1)-mers on the path
+	unsigned long long *cnt;          // sum of their counts
+	unsigned long long *off;          // first word of the interior bases (bases k+1 .. k+n-1 of the path, 2 bits each)
+	uint32_t *interior;
+	unsigned long long cap_paths, cap_words;
+};
+
+// hash (26 bits) of the canonical m-mer `fw` (m = TAGPU_MINIMIZER_M), exactly as k_partition computes it
+TAGPU_DI uint32_t tagpu_mmer_hash26(uint32_t fw)
+{
+	const int m = TAGPU_MINIMIZER_M;
+	const uint32_t rv = (uint32_t)(tagpu_rc64_full((uint64_t)fw) >> (64 - 2 * m));
+	return (min(fw, rv) * 0x9e3779b1u) >> 6;
+}
+
+// (i) + (ii) for the k-mer z: home bucket in [b0, b0 + nbk) and no potentially foreign extension
+template <int W>
+TAGPU_DI bool tagpu_kmer_is_local(const Key<W> &z, int k, int log2_buckets, uint32_t b0, uint32_t nbk)
+{
+	typedef KeyOps<W> KO;
+	const int m = TAGPU_MINIMIZER_M;
+	const uint32_t mm = (1u << (2 * m)) - 1u;
+	uint32_t mu = 0xffffffffu, fw = 0;
+	for (int i = 0; i < k; ++i) {
+		fw = ((fw << 2) | KO::base_at(z, k, i)) & mm;
+		if (i >= m - 1) mu = min(mu, tagpu_mmer_hash26(fw));
+	}
+	const uint32_t b = tagpu_bucket_of(mu, log2_buckets);
+	if (b < b0 || b >= b0 + nbk) return false;
+	// right extensions: last m-1 bases of z + c; left extensions: c + first m-1 bases of z
+	const uint32_t tail = fw & (mm >> 2);
+	uint32_t head = 0;
+	for (int i = 0; i < m - 1; ++i) head = (head << 2) | KO::base_at(z, k, i);
+	for (uint32_t c = 0; c < 4; ++c) {
+		if (tagpu_mmer_hash26((tail << 2) | c) < mu) return false;
+		if (tagpu_mmer_hash26((c << (2 * (m - 1))) | head) < mu) return false;
+	}
+	return true;
+}
+
+// ---------------------------------------------------------------- contraction of one block in shared memory
+// Oriented entry oe = 2 i + o: o = 0 the stored canonical (k+1)-mer x_i, o = 1 its reverse complement.
+template <int W>
+__global__ void __launch_bounds__(TAGPU_CONTRACT_THREADS)
+k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W> *__restrict__ solid, const uint32_t *__restrict__ solid_cnt,
+	   int k, int log2_buckets, int enable, PathStore<W> ps, unsigned long long *ctr)
+{
+	typedef KeyOps<W> KO;
+	constexpr int MAXN = TAGPU_CONTRACT_MAXN, TS_MAX = 4 * MAXN, T = TAGPU_CONTRACT_THREADS;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	Key<W> *e_key = reinterpret_cast<Key<W> *>(smem_raw);               // [MAXN]
+	Key<W> *t_key = e_key + MAXN;                                       // [TS_MAX] canonical k-mers, ~key (0 = empty)
+	uint32_t *e_cnt = reinterpret_cast<uint32_t *>(t_key + TS_MAX);     // [MAXN]
+	uint32_t *t_mask = e_cnt + MAXN;                                    // [TS_MAX] local edge mask (low 8 bits), bit 8 = hidden
+	uint16_t *t_out = reinterpret_cast<uint16_t *>(t_mask + TS_MAX);    // [TS_MAX][2] an oriented entry leaving (k-mer, orient)
+	uint16_t *nxt = t_out + 2 * TS_MAX;                                 // [2 MAXN] next oriented entry on the path / END
+	__shared__ uint32_t s_block, s_warp[2][T / 32];
+	__shared__ unsigned long long s_base[2];
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	const int K = k + 1;
+	const Key<W> kmask = KO::mask(k);
+
+	auto find = [&](const Key<W> &z, uint32_t ts) -> uint32_t {          // slot of canonical k-mer z (must be present)
+		const Key<W> stored = KO::bnot(z);
+		uint32_t s = (uint32_t)KO::hash(z) & (ts - 1);
+		for (uint32_t p = 0; p < ts; ++p) {
+			if (KO::eq(t_key[s], stored)) return s;
+			s = (s + 1) & (ts - 1);
+		}
+		return 0xffffffffu;
+	};
+
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) s_block = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);
+		__syncthreads();
+		const uint32_t blk = s_block;
+		if (blk >= n_blocks) break;
+		const SolidBlock sb = blocks[blk];
+		const uint32_t n = sb.n;
+		if (!enable || sb.flags || n > (uint32_t)MAXN) {
+			// not contractible: every (k+1)-mer is a path of its own
+			unsigned long long base = 0;
+			if (tid == 0) s_base[0] = atomicAdd(ctr + CTR_PATHS, (unsigned long long)n);
+			__syncthreads();
+			base = s_base[0];
+			for (uint32_t i = tid; i < n; i += T) {
+				if (base + i >= ps.cap_paths) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT); break; }
+				const Key<W> x = solid[sb.base + i];
+				ps.first[base + i] = x; ps.last[base + i] = x; ps.n[base + i] = 1u; ps.cnt[base + i] = solid_cnt[sb.base + i];
+				ps.off[base + i] = 0ull;
+			}
+			continue;
+		}
+		uint32_t ts = 64;
+		while (ts < 4u * n) ts <<= 1;                                // load <= 0.5 (at most 2 n k-mers)
+		for (uint32_t i = tid; i < ts; i += T) { t_key[i] = KO::make(0, 0); t_mask[i] = 0; }
+		for (uint32_t i = tid; i < n; i += T) { e_key[i] = solid[sb.base + i]; e_cnt[i] = solid_cnt[sb.base + i]; }
+		__syncthreads();
+		// ---- local k-mer table with masks and one leaving entry per (k-mer, orientation)
+		for (uint32_t oe = tid; oe < 2u * n; oe += T) {
+			const Key<W> x = e_key[oe >> 1];
+			const Key<W> y = (oe & 1u) ? KO::rc(x, K) : x;
+			const Key<W> q = KO::shr2(y), qr = KO::rc(q, k);              // head k-mer of the oriented entry
+			const bool fwd = KO::le(q, qr);
+			const Key<W> z = fwd ? q : qr, stored = KO::bnot(z);
+			uint32_t s = (uint32_t)KO::hash(z) & (ts - 1);
+			for (;;) {
+				const Key<W> have = t_key[s];
+				if (KO::eq(have, stored)) break;
+				if (KO::is_zero(have) || ktab_maybe_torn<W>(have)) {
+					const Key<W> old = ktab_cas<W>(t_key + s, stored);
+					if (KO::is_zero(old) || KO::eq(old, stored)) break;
+				}
+				s = (s + 1) & (ts - 1);
+			}
+			const uint32_t oz = fwd ? 0u : 1u;
+			atomicOr(t_mask + s, 1u << (oz * 4u + KO::last_base(y)));
+			t_out[2u * s + oz] = (uint16_t)oe;
+		}
+		__syncthreads();
+		// ---- which k-mers can be hidden
+		uint32_t n_hidden = 0;
+		for (uint32_t s = tid; s < ts; s += T) {
+			const Key<W> st = t_key[s];
+			if (KO::is_zero(st)) continue;
+			const uint32_t m = t_mask[s];
+			if (DEG4(m) != 1 || DEG4(m >> 4) != 1) continue;
+			// the two (k+1)-mers through z must be two different, non-palindromic entries: a hairpin (z followed by its own
+			// reverse complement) or a palindromic (k+1)-mer would make a path that is its own reverse complement, and
+			// those stay with the (k+1)-mer-level rules of the global stage
+			const uint32_t i0 = t_out[2u * s] >> 1, i1 = t_out[2u * s + 1u] >> 1;
+			if (i0 == i1) continue;
+			const Key<W> x0 = e_key[i0], x1 = e_key[i1];
+			if (KO::eq(x0, KO::rc(x0, K)) || KO::eq(x1, KO::rc(x1, K))) continue;
+			if (tagpu_kmer_is_local<W>(KO::bnot(st), k, log2_buckets, sb.b0, sb.nbk)) {
+				t_mask[s] = m | 0x100u;
+				++n_hidden;
+			}
+		}
+		__syncthreads();
+		// ---- links: the entry that continues an oriented entry across a hidden k-mer
+		for (uint32_t oe = tid; oe < 2u * n; oe += T) {
+			const Key<W> x = e_key[oe >> 1];
+			const Key<W> y = (oe & 1u) ? KO::rc(x, K) : x;
+			const Key<W> q = KO::band(y, kmask), qr = KO::rc(q, k);       // tail k-mer
+			const bool fwd = KO::le(q, qr);
+			const uint32_t s = find(fwd ? q : qr, ts);
+			uint16_t nx = (uint16_t)TAGPU_OE_END;
+			if (s == 0xffffffffu) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT);
+			else if (t_mask[s] & 0x100u) nx = t_out[2u * s + (fwd ? 0u : 1u)];
+			nxt[oe] = nx;
+		}
+		__syncthreads();
+		// ---- heads walk their paths: a path is emitted by its smaller end (head <= rc of its last entry)
+		// pass 0 counts paths and interior words, pass 1 writes
+		for (int pass = 0; pass < 2; ++pass) {
+			uint32_t my_paths = 0, my_words = 0, out_p = 0, out_w = 0;
+			if (pass) {
+				out_p = s_warp[0][warp];
+				out_w = s_warp[1][warp];
+			}
+			for (uint32_t oe0 = 0; oe0 < 2u * n; oe0 += T) {
+				const uint32_t oe = oe0 + tid;
+				bool emit = false;
+				uint32_t len = 0, last = 0;
+				unsigned long long csum = 0;
+				if (oe < 2u * n && nxt[oe ^ 1u] == TAGPU_OE_END) {           // head: the k-mer before it is not hidden
+					uint32_t cur = oe;
+					for (;;) {
+						++len;
+						csum += e_cnt[cur >> 1];
+						last = cur;
+						const uint32_t nx = nxt[cur];
+						if (nx == TAGPU_OE_END) break;
+						if (len > 2u * n) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT); break; }
+						cur = nx;
+					}
+					emit = oe <= (last ^ 1u);
+				}
+				const uint32_t words = emit && len > 1 ? (len - 1 + 15) >> 4 : 0u;
+				// warp-level exclusive prefix of (paths, words) among the emitting lanes of this sweep
+				uint32_t ip = emit ? 1u : 0u, iw = words;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const uint32_t a = __shfl_up_sync(0xffffffffu, ip, d), b = __shfl_up_sync(0xffffffffu, iw, d);
+					if (lane >= (uint32_t)d) { ip += a; iw += b; }
+				}
+				const uint32_t tp = __shfl_sync(0xffffffffu, ip, 31), tw = __shfl_sync(0xffffffffu, iw, 31);
+				if (pass && emit) {
+					const unsigned long long pi = s_base[0] + out_p + ip - 1u, wo = s_base[1] + out_w + iw - words;
+					if (pi >= ps.cap_paths || wo + words > ps.cap_words) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT);
+					else {
+						const Key<W> xf = (oe & 1u) ? KO::rc(e_key[oe >> 1], K) : e_key[oe >> 1];
+						const Key<W> xl = (last & 1u) ? KO::rc(e_key[last >> 1], K) : e_key[last >> 1];
+						ps.first[pi] = xf; ps.last[pi] = xl; ps.n[pi] = len; ps.cnt[pi] = csum; ps.off[pi] = wo;
+						uint32_t cur = nxt[oe], word = 0;
+						for (uint32_t j = 0; j + 1 < len; ++j) {            // interior base j = last base of the (j + 2)-th entry
+							const Key<W> xe = e_key[cur >> 1];
+							const uint32_t base = (cur & 1u) ? 3u - KO::first_base(xe, K) : KO::last_base(xe);
+							word |= base << ((j & 15u) << 1);
+							if ((j & 15u) == 15u || j + 2 == len) { ps.interior[wo + (j >> 4)] = word; word = 0; }
+							cur = nxt[cur];
+						}
+					}
+				}
+				my_paths += tp;
+				my_words += tw;
+				out_p += tp;
+				out_w += tw;
+			}
+			if (!pass) {
+				// per-warp totals -> exclusive offsets, one pair of global atomics per block
+				if (lane == 0) { s_warp[0][warp] = my_paths; s_warp[1][warp] = my_words; }
+				__syncthreads();
+				if (tid == 0) {
+					uint32_t ap = 0, aw = 0;
+					for (int w2 = 0; w2 < T / 32; ++w2) {
+						const uint32_t vp = s_warp[0][w2], vw = s_warp[1][w2];
+						s_warp[0][w2] = ap; s_warp[1][w2] = aw;
+						ap += vp; aw += vw;
+					}
+					s_base[0] = ap ? atomicAdd(ctr + CTR_PATHS, (unsigned long long)ap) : 0ull;
+					s_base[1] = aw ? atomicAdd(ctr + CTR_PATH_WORDS, (unsigned long long)aw) : 0ull;
+				}
+				__syncthreads();
+			}
+		}
+		n_hidden = __reduce_add_sync(0xffffffffu, n_hidden);
+		if (lane == 0 && n_hidden) atomicAdd(ctr + CTR_KMERS, (unsigned long long)n_hidden);
+	}
+}
+
+// base i (0 .. k + n - 1) of a path: the first k + 1 from its first (k+1)-mer, the rest from the interior words
+template <int W>
+TAGPU_DI uint32_t tagpu_path_base(const PathStore<W> &ps, unsigned long long p, const Key<W> &xf, int k, uint32_t i)
+{
+	if (i <= (uint32_t)k) return KeyOps<W>::base_at(xf, k + 1, (int)i);
+	const uint32_t j = i - (uint32_t)k - 1u;
+	return (ps.interior[ps.off[p] + (j >> 4)] >> ((j & 15u) << 1)) & 3u;
+}
+
+// ---------------------------------------------------------------- B': end k-mers of the paths into the HBM table
+template <int W>
+__global__ void __launch_bounds__(256) k_insert_paths(PathStore<W> ps, uint64_t n_paths, int k, KTab<W> t, uint32_t *__restrict__ vL,
+						       uint32_t *__restrict__ vR, unsigned long long *ctr)
+{
+	typedef KeyOps<W> KO;
+	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t n_new = 0;
+	if (p < n_paths) {
+		const Key<W> xf = ps.first[p], xl = ps.last[p];
+		const Key<W> km = KO::mask(k);
+		const Key<W> k1 = KO::shr2(xf), k2 = KO::band(xl, km);
+		const uint32_t c1 = KO::last_base(xf), c2 = 3u - KO::first_base(xl, k + 1);
+		const Key<W> r1 = KO::rc(k1, k), r2 = KO::rc(k2, k);
+		const bool f1 = KO::le(k1, r1), f2 = KO::le(k2, r2);
+		bool claimed;
+		const uint32_t s1 = ktab_insert<W>(t, f1 ? k1 : r1, &claimed, ctr + CTR_ERROR);
+		n_new += claimed;
+		atomicOr(&t.mask32[s1 >> 2], (1u << (f1 ? c1 : c1 + 4u)) << ((s1 & 3u) * 8u));
+		const uint32_t s2 = ktab_insert<W>(t, f2 ? k2 : r2, &claimed, ctr + CTR_ERROR);
+		n_new += claimed;
+		atomicOr(&t.mask32[s2 >> 2], (1u << (f2 ? c2 + 4u : c2)) << ((s2 & 3u) * 8u));
+		vL[p] = s1 * 2u + (f1 ? 0u : 1u);   // oriented vertex the path leaves (out-base c1)
+		vR[p] = s2 * 2u + (f2 ? 1u : 0u);   // oriented vertex its reverse complement leaves (out-base c2)
+	}
+	n_new = __reduce_add_sync(0xffffffffu, n_new);
+	if ((threadIdx.x & 31) == 0 && n_new) atomicAdd(ctr + CTR_KMERS, (unsigned long long)n_new);
+}
+
+// ---------------------------------------------------------------- C2': successor links, one thread per path and direction
+// jump[cv] = (next chain vertex, bases of the connecting path); the last chain vertex before a node points at itself with
+// TERM, vsucc = that node vertex, wlast = bases of the final path.
+template <int W>
+__global__ void __launch_bounds__(256) k_succ_paths(PathStore<W> ps, uint64_t n_paths, const uint32_t *__restrict__ vL, const uint32_t *__restrict__ vR,
+						     const uint32_t *__restrict__ kind, unsigned long long *__restrict__ jump,
+						     uint32_t *__restrict__ vsucc, uint32_t *__restrict__ wlast)
+{
+	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= 2 * n_paths) return;
+	const uint64_t p = idx >> 1;
+	const uint32_t dir = (uint32_t)idx & 1u;
+	const uint32_t a = dir ? vR[p] : vL[p], b = (dir ? vL[p] : vR[p]) ^ 1u, w = ps.n[p];
+	const uint32_t ka = kind[a >> 1];
+	if (!(ka & TAGPU_CHAIN)) return;                                 // leaves a node: k_heads_paths
+	const uint32_t cva = (ka & ~TAGPU_CHAIN) * 2u + (a & 1u), kb = kind[b >> 1];
+	if (kb & TAGPU_CHAIN) {
+		jump[cva] = tagpu_pack_jump((kb & ~TAGPU_CHAIN) * 2u + (b & 1u), w);
+		vsucc[cva] = TAGPU_NONE;
+	} else {
+		jump[cva] = tagpu_pack_jump(TAGPU_TERM | cva, 0);
+		vsucc[cva] = kb * 2u + (b & 1u);
+		wlast[cva] = w;
+	}
+}
+
+// ---------------------------------------------------------------- C4': edge heads, one thread per path and direction
+template <int W>
+__global__ void __launch_bounds__(128) k_heads_paths(PathStore<W> ps, uint64_t n_paths, int k, KTab<W> t, const uint32_t *__restrict__ vL,
+						      const uint32_t *__restrict__ vR, const uint32_t *__restrict__ kind,
+						      const uint32_t *__restrict__ node_ebase, const unsigned long long *__restrict__ jump,
+						      const uint32_t *__restrict__ vsucc, const uint32_t *__restrict__ wlast, uint32_t *__restrict__ vedge,
+						      FlatGraph g, unsigned long long *ctr)
+{
+	typedef KeyOps<W> KO;
+	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool in = idx < 2 * n_paths;
+	const uint64_t p = in ? idx >> 1 : 0;
+	const uint32_t dir = (uint32_t)idx & 1u;
+	bool have = false;
+	uint32_t a = 0, b = 0, w = 0, ord = 0, len = 0, dst = 0, first = TAGPU_NONE, e = 0;
+	Key<W> xf = KO::make(0, 0);
+	if (in) {
+		a = dir ? vR[p] : vL[p];
+		b = (dir ? vL[p] : vR[p]) ^ 1u;
+		w = ps.n[p];
+		const uint32_t ka = kind[a >> 1];
+		if (!(ka & TAGPU_CHAIN)) {                                   // the path leaves a node: it starts an edge
+			have = true;
+			ord = ka;
+			xf = ps.first[p];
+			const Key<W> xl = ps.last[p];
+			const uint32_t c = dir ? 3u - KO::first_base(xl, k + 1) : KO::last_base(xf);
+			const uint32_t m = ktab_mask_of<W>(t, a >> 1), o = a & 1u, nib = o ? (m >> 4) : (m & 15u);
+			e = node_ebase[ord] + (o ? DEG4(m) : 0u) + tagpu_rank4(nib, c);
+			const uint32_t kb = kind[b >> 1];
+			if (!(kb & TAGPU_CHAIN)) {
+				len = (uint32_t)k + w;
+				dst = kb * 2u + (b & 1u);
+			} else {
+				const uint32_t cvb = (kb & ~TAGPU_CHAIN) * 2u + (b & 1u);
+				const unsigned long long j = jump[cvb];
+				if (!((uint32_t)j & TAGPU_TERM)) {
+					atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CHAIN);
+					have = false;
+				} else {
+					const uint32_t tv = (uint32_t)j & ~TAGPU_TERM;
+					len = (uint32_t)k + w + (uint32_t)(j >> 32) + wlast[tv];
+					dst = vsucc[tv];
+					first = cvb;
+				}
+			}
+		}
+	}
+	const unsigned long long off = tagpu_warp_alloc(ctr + CTR_SEQ_WORDS, have ? (len + 15u) >> 4 : 0u);
+	if (have) {
+		g.e_src[e] = ord * 2u + (a & 1u); g.e_dst[e] = dst; g.e_len[e] = len; g.e_off[e] = off; g.e_count[e] = 0;
+		if (first != TAGPU_NONE) vedge[first] = e;
+		// first k bases: the node k-mer as the edge sees it; then the w bases of this path
+		const uint32_t n = w;
+		uint32_t word = 0;
+		for (uint32_t i = 0; i < (uint32_t)k + n; ++i) {
+			// forward: path bases 0 .. k+n-1; backward: complement of path bases k+n-1 .. 0
+			const uint32_t base = dir ? 3u - tagpu_path_base<W>(ps, p, xf, k, (uint32_t)k + n - 1u - i) : tagpu_path_base<W>(ps, p, xf, k, i);
+			word |= base << ((i & 15u) << 1);
+			if ((i & 15u) == 15u || i + 1 == (uint32_t)k + n) {
+				atomicOr(g.e_seq + off + (i >> 4), word);
+				word = 0;
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------- C5': every path that leaves a chain vertex writes its bases
+template <int W>
+__global__ void __launch_bounds__(256) k_interior_paths(PathStore<W> ps, uint64_t n_paths, int k, const uint32_t *__restrict__ vL,
+							 const uint32_t *__restrict__ vR, const uint32_t *__restrict__ kind,
+							 const unsigned long long *__restrict__ jump, const uint32_t *__restrict__ wlast,
+							 uint32_t *vedge, FlatGraph g)
+{
+	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= 2 * n_paths) return;
+	const uint64_t p = idx >> 1;
+	const uint32_t dir = (uint32_t)idx & 1u;
+	const uint32_t a = dir ? vR[p] : vL[p], ka = kind[a >> 1];
+	if (!(ka & TAGPU_CHAIN)) return;
+	const uint32_t cv = (ka & ~TAGPU_CHAIN) * 2u + (a & 1u);
+	const unsigned long long j = jump[cv], jt = jump[cv ^ 1u];
+	if (!((uint32_t)j & TAGPU_TERM) || !((uint32_t)jt & TAGPU_TERM)) return;  // node-free cycle
+	const uint32_t tr = (uint32_t)jt & ~TAGPU_TERM;                  // last chain vertex of the reverse walk = twin of the edge's first one
+	const uint32_t e = vedge[tr ^ 1u];
+	if (e == TAGPU_NONE) return;
+	const uint32_t pos = (uint32_t)k + wlast[tr] + (uint32_t)(jt >> 32), n = ps.n[p];
+	const Key<W> xf = ps.first[p];
+	const unsigned long long off = g.e_off[e];
+	for (uint32_t i = 0; i < n; ++i) {
+		const uint32_t base = dir ? 3u - tagpu_path_base<W>(ps, p, xf, k, n - 1u - i) : tagpu_path_base<W>(ps, p, xf, k, (uint32_t)k + i);
+		atomicOr(g.e_seq + off + ((pos + i) >> 4), base << (((pos + i) & 15u) << 1));
+	}
+	if (cv != (tr ^ 1u)) vedge[cv] = e;
+}
+
+// ---------------------------------------------------------------- C7': edge counts, one thread per path
+template <int W>
+__global__ void __launch_bounds__(256) k_counts_paths(PathStore<W> ps, uint64_t n_paths, int k, KTab<W> t, const uint32_t *__restrict__ vL,
+						       const uint32_t *__restrict__ kind, const uint32_t *__restrict__ node_ebase,
+						       const uint32_t *__restrict__ vedge, FlatGraph g, unsigned long long *ctr)
+{
+	typedef KeyOps<W> KO;
+	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long on_edge = 0;
+	if (p < n_paths) {
+		const uint32_t v = vL[p], slot = v >> 1, o = v & 1u, kd = kind[slot];
+		uint32_t e;
+		if (!(kd & TAGPU_CHAIN)) {
+			const uint32_t m = ktab_mask_of<W>(t, slot), nib = o ? (m >> 4) : (m & 15u);
+			e = node_ebase[kd] + (o ? DEG4(m) : 0u) + tagpu_rank4(nib, KO::last_base(ps.first[p]));
+		} else {
+			e = vedge[(kd & ~TAGPU_CHAIN) * 2u + o];
+		}
+		if (e != TAGPU_NONE) {
+			const unsigned long long c = ps.cnt[p];
+			atomicAdd(g.e_count + e, c);
+			atomicAdd(g.e_count + g.e_rc[e], c);
+			on_edge = ps.n[p];
+		}
+	}
+#pragma unroll
+	for (int d = 16; d; d >>= 1) on_edge += __shfl_xor_sync(0xffffffffu, on_edge, d);
+	if ((threadIdx.x & 31) == 0 && on_edge) atomicAdd(ctr + CTR_KP1_ON_EDGE, on_edge);
+}

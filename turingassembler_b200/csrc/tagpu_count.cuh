@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(BucketCfg<W>::THREADS, BucketCfg<W>::CTAS_PER_
 k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uint32_t first_bucket, uint32_t cap_records,
 		const unsigned long long *__restrict__ cur_all, const uint32_t *__restrict__ ext_all, const uint32_t *__restrict__ grp_first,
 		const uint32_t *__restrict__ grp_end, uint32_t group_max, int K, uint32_t ci, Key<W> *__restrict__ solid, uint32_t *__restrict__ solid_cnt, unsigned long long solid_cap,
-		unsigned long long *ctr)
+		SolidBlock *__restrict__ blocks, uint32_t blocks_cap, unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
 	typedef BucketCfg<W> C;
@@ -859,6 +859,15 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 				// the global offset is requested now and consumed after the compaction pass
 				s_out_base = n_out ? atomicAdd(ctr + CTR_SOLID, (unsigned long long)n_out) : 0ull;
 				if (!failed) atomicAdd(ctr + CTR_DISTINCT, (unsigned long long)s_claims);
+				if (n_out) {                                         // directory of the solid list, for the graph stage
+					const uint32_t id = (uint32_t)atomicAdd(ctr + CTR_BLOCKS, 1ull);
+					if (id < blocks_cap) {
+						SolidBlock sb;
+						sb.base = s_out_base; sb.n = n_out; sb.b0 = first_bucket + b0; sb.nbk = nb / world;
+						sb.flags = (L || !staged) ? 1u : 0u;
+						blocks[id] = sb;
+					} else atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_BLOCKS);
+				}
 				// next hash class: children of a failed class first, then whatever is left on the stack
 				uint32_t sp = s_sp;
 				if (failed) {

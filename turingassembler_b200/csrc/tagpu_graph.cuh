@@ -22,10 +22,19 @@ constexpr uint32_t TAGPU_CHAIN = 0x80000000u;   // kind[] entry: chain k-mer (lo
 enum {
 	CTR_INSTANCES = 0, CTR_DISTINCT, CTR_SOLID, CTR_KMERS, CTR_NODES, CTR_EDGES, CTR_SEQ_WORDS,
 	CTR_KP1_ON_EDGE, CTR_ERROR, CTR_SUM_SOLID, CTR_SPARE0, CTR_SPARE1, CTR_CHAIN, CTR_JUMP_ROUNDS, CTR_GROUPS,
+	CTR_BLOCKS, CTR_PATHS, CTR_PATH_WORDS,
 	CTR_JUMP_FLAGS /* + 64 */, CTR_TOTAL = CTR_JUMP_FLAGS + 64
 };
 
-enum { TAGPU_ERR_TABLE_FULL = 1, TAGPU_ERR_MISSING_SUCC = 2, TAGPU_ERR_CHAIN = 4, TAGPU_ERR_RC_LINK = 8, TAGPU_ERR_BUCKET_OVERFLOW = 16, TAGPU_ERR_RUN_LENGTH = 32 };
+// One harvest of k_count_buckets = one contiguous block of the solid (k+1)-mer list: keys that share the minimizers of
+// the buckets [b0, b0 + nbk).  flags != 0: the block does not hold ALL solid (k+1)-mers of those buckets (hash sub-class
+// pass, or written past the staging area) and must not be contracted.
+struct SolidBlock {
+	unsigned long long base;
+	uint32_t n, b0, nbk, flags;
+};
+
+enum { TAGPU_ERR_TABLE_FULL = 1, TAGPU_ERR_MISSING_SUCC = 2, TAGPU_ERR_CHAIN = 4, TAGPU_ERR_RC_LINK = 8, TAGPU_ERR_BUCKET_OVERFLOW = 16, TAGPU_ERR_RUN_LENGTH = 32, TAGPU_ERR_BLOCKS = 64, TAGPU_ERR_CONTRACT = 128 };
 
 #define DEG4(x) __popc((x) & 15u)
 
@@ -333,11 +342,12 @@ __global__ void __launch_bounds__(256) k_hj_walk(const unsigned long long *__res
 {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n_spl) return;
-	uint32_t cur = spl_list[t], hops = 0;
+	uint32_t cur = spl_list[t], hops = 0;                          // hops: distance walked, in link weights (1 per (k+1)-mer)
 	for (;;) {
-		const uint32_t p = (uint32_t)jump[cur];
+		const unsigned long long jc = jump[cur];
+		const uint32_t p = (uint32_t)jc;
 		if (p & TAGPU_TERM) { jump2[t] = tagpu_pack_jump(TAGPU_TERM | cur, hops); return; }   // chain ends at cur
-		++hops;
+		hops += (uint32_t)(jc >> 32);
 		if ((spl_bits[p >> 5] >> (p & 31u)) & 1u) { jump2[t] = tagpu_pack_jump((uint32_t)own[p], hops); return; }  // next splitter's index
 		own[p] = ((unsigned long long)hops << 32) | t;
 		cur = p;

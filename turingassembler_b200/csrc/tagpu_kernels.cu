@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/tagpu.h"
+#include "tagpu_contract.cuh"
 #include "tagpu_count.cuh"
 #include "tagpu_count_v1.cuh"
 #include "tagpu_extract.cuh"
@@ -33,6 +34,9 @@ struct tagpu_ctx {
 	cudaEvent_t ev_chunk[TAGPU_UPLOAD_CHUNKS_MAX];
 	const uint8_t *h_src = nullptr;    // host source of the read stream while its upload is pending (tagpu_*_host calls)
 	int ci = 2, skip_counts = 0;
+	int contract = 0;                  // two-level graph stage (tagpu_contract.cuh)
+	bool contracted = false;           // the last graph was built that way (hidden k-mers are not in the table)
+	int log2_buckets = 0;              // of the last count stage
 	int k = 0, K = 0, W = 0;
 	char err[512] = { 0 };
 	unsigned long long *d_ctr = nullptr, *h_ctr = nullptr;
@@ -48,9 +52,9 @@ struct tagpu_ctx {
 	bool have_count = false, have_graph = false;
 	void *cur_solid_key = nullptr, *cur_solid_cnt = nullptr; // solid set the graph stage reads (local, or gathered from all ranks)
 	// build_local_assembly_graph: (k+1)-mers of the flanking contigs appended behind the solid ones (count 0), and the contigs
-	uint64_t n_garbage = 0;
+	uint64_t n_garbage = 0, n_blocks = 0;                    // n_blocks: directory entries of the local solid list (0 = no directory)
 	bool local_mode = false;
-	Buf g_key, comb_key, comb_cnt, g_seq, hj_own, hj_bits, hj_list, hj_jump2;
+	Buf blocks, p_first, p_last, p_n, p_cnt, p_off, p_int, wlast, g_key, comb_key, comb_cnt, g_seq, hj_own, hj_bits, hj_list, hj_jump2;
 	int n_contigs = 0;
 	uint64_t contig_off[4] = { 0 };
 	uint32_t contig_len[4] = { 0 };
@@ -192,7 +196,7 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	dist_release(ctx);
-	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->hj_own, &ctx->hj_bits, &ctx->hj_list, &ctx->hj_jump2, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->blocks, &ctx->p_first, &ctx->p_last, &ctx->p_n, &ctx->p_cnt, &ctx->p_off, &ctx->p_int, &ctx->wlast, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->hj_own, &ctx->hj_bits, &ctx->hj_list, &ctx->hj_jump2, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
 			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
 	for (Buf *b : bufs)
@@ -212,6 +216,7 @@ extern "C" void tagpu_set_cutoff(tagpu_ctx *ctx, int ci) { ctx->ci = ci < 1 ? 1 
 extern "C" void tagpu_set_skip_counts(tagpu_ctx *ctx, int skip) { ctx->skip_counts = skip; }
 extern "C" const char *tagpu_last_error(tagpu_ctx *ctx) { return ctx->err; }
 extern "C" void tagpu_set_profile(tagpu_ctx *ctx, int on) { ctx->profile = on; }
+extern "C" void tagpu_set_contract(tagpu_ctx *ctx, int on) { ctx->contract = on; }
 extern "C" const char *tagpu_profile_json(tagpu_ctx *ctx) { return ctx->prof_json.c_str(); }
 
 static int read_counters(tagpu_ctx *ctx)
@@ -383,8 +388,10 @@ static int count_owned(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &
 	const uint64_t n_groups_cap = ctx->count_stream_bytes / BC::GROUP_TARGET + 2;
 	if (ensure(ctx, ctx->cur_all, ((size_t)cfg.per_rank * world + 1) * 8) || ensure(ctx, ctx->ext_all, ((size_t)cfg.per_rank * world + 1) * 4) ||
 	    ensure(ctx, ctx->pex, ((size_t)cfg.per_rank + 1) * 8) || ensure(ctx, ctx->bsum, ((size_t)n_scan_blocks + 1) * 8) ||
-	    ensure(ctx, ctx->grp_start, n_groups_cap * 4) || ensure(ctx, ctx->grp_end, n_groups_cap * 4))
+	    ensure(ctx, ctx->grp_start, n_groups_cap * 4) || ensure(ctx, ctx->grp_end, n_groups_cap * 4) ||
+	    ensure(ctx, ctx->blocks, (2 * n_groups_cap + 4096) * sizeof(SolidBlock)))
 		return -1;
+	const uint32_t blocks_cap = (uint32_t)(2 * n_groups_cap + 4096);
 	if (n_owned) {
 		{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->grp_start.p, 0xff, n_groups_cap * 4, ctx->stream)); }
 		LAUNCH(k_pull_cursors<W>, n_scan_blocks, TAGPU_SCAN_BLOCK, peers, world, first_bucket, n_owned, n_buckets, cfg.cap_records,
@@ -395,12 +402,13 @@ static int count_owned(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &
 		LAUNCH_SMEM(k_count_buckets<W>, BC::CTAS_PER_SM * ctx->n_sm, BC::THREADS, BC::SMEM, peers, world, first_bucket, cfg.cap_records,
 			    (const unsigned long long *)ctx->cur_all.p, (const uint32_t *)ctx->ext_all.p, (const uint32_t *)ctx->grp_start.p,
 			    (const uint32_t *)ctx->grp_end.p, group_max, cfg.K, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p,
-			    (unsigned long long)solid_cap, ctx->d_ctr);
+			    (unsigned long long)solid_cap, (SolidBlock *)ctx->blocks.p, blocks_cap, ctx->d_ctr);
 	}
 	if (read_counters(ctx)) return -1;
 	ctx->st.n_distinct = ctx->h_ctr[CTR_DISTINCT];
 	ctx->st.n_solid = ctx->h_ctr[CTR_SOLID];
 	ctx->st.sum_solid = ctx->h_ctr[CTR_SUM_SOLID];
+	ctx->n_blocks = ctx->h_ctr[CTR_BLOCKS];
 #ifdef TAGPU_TIMING
 	{
 		const double tot = (double)(ctx->h_ctr[CTR_JUMP_FLAGS + 48] + ctx->h_ctr[CTR_JUMP_FLAGS + 49] + ctx->h_ctr[CTR_JUMP_FLAGS + 50] + ctx->h_ctr[CTR_JUMP_FLAGS + 51] +
@@ -427,6 +435,7 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 	const PartCfg cfg = plan_cfg(n, ctx->K, 1, BC::GROUP_TARGET);
 	const uint32_t n_buckets = 1u << cfg.log2_buckets;
 	ctx->count_stream_bytes = n;
+	ctx->log2_buckets = cfg.log2_buckets;
 	if (ensure(ctx, ctx->regions, (size_t)n_buckets * cfg.cap_records * sizeof(SkRec<W>)) || ensure(ctx, ctx->cursor, (size_t)n_buckets * 8) ||
 	    ensure(ctx, ctx->overflow, (size_t)cfg.overflow_cap * sizeof(SkRec<W>)) ||
 	    ensure(ctx, ctx->overflow_bucket, (size_t)cfg.overflow_cap * 4) || ensure(ctx, ctx->ext_off, (size_t)(n_buckets + 1) * 4) ||
@@ -569,6 +578,114 @@ static int graph_stage(tagpu_ctx *ctx)
 	return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ graph stage, two-level (paths)
+template <int W>
+static int graph_stage_paths(tagpu_ctx *ctx)
+{
+	const int k = ctx->k;
+	const uint64_t n_solid = ctx->st.n_solid;
+	unsigned long long *ctr = ctx->d_ctr;
+	// ---- level 1: contraction inside the blocks of the solid list
+	PathStore<W> ps;
+	ps.cap_paths = n_solid + 1;
+	ps.cap_words = n_solid / 16 + n_solid / 2 + 16;
+	if (ensure(ctx, ctx->p_first, ps.cap_paths * sizeof(Key<W>)) || ensure(ctx, ctx->p_last, ps.cap_paths * sizeof(Key<W>)) ||
+	    ensure(ctx, ctx->p_n, ps.cap_paths * 4) || ensure(ctx, ctx->p_cnt, ps.cap_paths * 8) || ensure(ctx, ctx->p_off, ps.cap_paths * 8) ||
+	    ensure(ctx, ctx->p_int, ps.cap_words * 4))
+		return -1;
+	ps.first = (Key<W> *)ctx->p_first.p; ps.last = (Key<W> *)ctx->p_last.p; ps.n = (uint32_t *)ctx->p_n.p;
+	ps.cnt = (unsigned long long *)ctx->p_cnt.p; ps.off = (unsigned long long *)ctx->p_off.p; ps.interior = (uint32_t *)ctx->p_int.p;
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctr + CTR_SPARE1, 0, 8, ctx->stream)); }
+	constexpr size_t smem_c = (size_t)TAGPU_CONTRACT_MAXN * sizeof(Key<W>) + (size_t)4 * TAGPU_CONTRACT_MAXN * sizeof(Key<W>) +
+				  (size_t)TAGPU_CONTRACT_MAXN * 4 + (size_t)4 * TAGPU_CONTRACT_MAXN * 4 + (size_t)8 * TAGPU_CONTRACT_MAXN * 2 +
+				  (size_t)2 * TAGPU_CONTRACT_MAXN * 2;
+	static bool attr_done[3] = { false, false, false };
+	if (!attr_done[W]) {
+		CU(cudaFuncSetAttribute(k_contract<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+		attr_done[W] = true;
+	}
+	if (ctx->n_blocks)
+		LAUNCH_SMEM(k_contract<W>, 3 * ctx->n_sm, TAGPU_CONTRACT_THREADS, smem_c, (const SolidBlock *)ctx->blocks.p, (uint32_t)ctx->n_blocks,
+			    (const Key<W> *)ctx->cur_solid_key, (const uint32_t *)ctx->cur_solid_cnt, k, ctx->log2_buckets, 1, ps, ctr);
+	if (read_counters(ctx)) return -1;
+	const uint64_t n_paths = ctx->h_ctr[CTR_PATHS];
+	// ---- level 2: the global stage on the paths
+	const uint64_t slots64 = (n_paths * 5) / 2 + 1024;
+	if (slots64 > (1ull << 30)) return fail(ctx, "k-mer table would need %llu slots (> 2^30)", (unsigned long long)slots64);
+	const uint32_t n_slots = (uint32_t)slots64;
+	ctx->kt_slots = n_slots;
+	const size_t mask_bytes = ((size_t)n_slots + 3) / 4 * 4;
+	if (ensure(ctx, ctx->kt_keys, (size_t)n_slots * sizeof(Key<W>)) || ensure(ctx, ctx->kt_mask, mask_bytes) ||
+	    ensure(ctx, ctx->node_ord, (size_t)n_slots * 4) || ensure(ctx, ctx->vL, (n_paths + 1) * 4) ||
+	    ensure(ctx, ctx->vR, (n_paths + 1) * 4) || ensure(ctx, ctx->node_slot, (2 * n_paths + 1) * 4) ||
+	    ensure(ctx, ctx->node_ebase, (2 * n_paths + 1) * 4) || ensure(ctx, ctx->chain_slot, (2 * n_paths + 1) * 4))
+		return -1;
+	KTab<W> t;
+	t.keys = (Key<W> *)ctx->kt_keys.p;
+	t.mask32 = (uint32_t *)ctx->kt_mask.p;
+	t.n_slots = n_slots;
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(t.keys, 0, (size_t)n_slots * sizeof(Key<W>), ctx->stream)); }
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(t.mask32, 0, mask_bytes, ctx->stream)); }
+	uint32_t *kind = (uint32_t *)ctx->node_ord.p, *node_slot = (uint32_t *)ctx->node_slot.p,
+		 *node_ebase = (uint32_t *)ctx->node_ebase.p, *chain_slot = (uint32_t *)ctx->chain_slot.p,
+		 *vL = (uint32_t *)ctx->vL.p, *vR = (uint32_t *)ctx->vR.p;
+	if (n_paths) LAUNCH(k_insert_paths<W>, (unsigned)((n_paths + 255) / 256), 256, ps, n_paths, k, t, vL, vR, ctr);
+	LAUNCH(k_classify<W>, (n_slots + 1023) / 1024, 1024, t, kind, node_slot, node_ebase, chain_slot, ctr);
+	if (read_counters(ctx)) return -1;
+	const uint64_t n_nodes = ctx->h_ctr[CTR_NODES], n_e = ctx->h_ctr[CTR_EDGES], n_chain = ctx->h_ctr[CTR_CHAIN];
+	ctx->st.n_kmers = ctx->h_ctr[CTR_KMERS];
+	ctx->st.n_v = 2 * n_nodes;
+	ctx->st.n_e = n_e;
+	if (n_e > 0xfffffff0ull) return fail(ctx, "too many edges (%llu)", (unsigned long long)n_e);
+	const uint32_t n_cv = (uint32_t)(2 * n_chain);
+	const uint64_t seq_cap = (n_e * (uint64_t)k + 2 * n_solid) / 16 + n_e + 16;
+	if (ensure(ctx, ctx->jump, ((size_t)n_cv + 1) * 8) || ensure(ctx, ctx->vsucc, ((size_t)n_cv + 1) * 4) ||
+	    ensure(ctx, ctx->wlast, ((size_t)n_cv + 1) * 4) ||
+	    ensure(ctx, ctx->vedge, ((size_t)n_cv + 1) * 4) || ensure(ctx, ctx->e_src, (n_e + 1) * 4) ||
+	    ensure(ctx, ctx->e_dst, (n_e + 1) * 4) || ensure(ctx, ctx->e_rc, (n_e + 1) * 4) || ensure(ctx, ctx->e_len, (n_e + 1) * 4) ||
+	    ensure(ctx, ctx->e_count, (n_e + 1) * 8) || ensure(ctx, ctx->e_off, (n_e + 1) * 8) || ensure(ctx, ctx->e_seq, seq_cap * 4))
+		return -1;
+	unsigned long long *jump = (unsigned long long *)ctx->jump.p;
+	uint32_t *vsucc = (uint32_t *)ctx->vsucc.p, *vedge = (uint32_t *)ctx->vedge.p, *wlast = (uint32_t *)ctx->wlast.p;
+	FlatGraph g;
+	g.e_src = (uint32_t *)ctx->e_src.p; g.e_dst = (uint32_t *)ctx->e_dst.p; g.e_rc = (uint32_t *)ctx->e_rc.p;
+	g.e_len = (uint32_t *)ctx->e_len.p; g.e_count = (unsigned long long *)ctx->e_count.p;
+	g.e_off = (unsigned long long *)ctx->e_off.p; g.e_seq = (uint32_t *)ctx->e_seq.p;
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(vedge, 0xff, ((size_t)n_cv + 1) * 4, ctx->stream)); }
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(g.e_seq, 0, seq_cap * 4, ctx->stream)); }
+	if (n_cv) {
+		LAUNCH(k_succ_paths<W>, (unsigned)((2 * n_paths + 255) / 256), 256, ps, n_paths, vL, vR, kind, jump, vsucc, wlast);
+		if (!ctx->jump_grid) {
+			int per_sm = 0;
+			CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jump_all, 512, 0));
+			ctx->jump_grid = ctx->n_sm * (per_sm > 0 ? per_sm : 1);
+		}
+		int max_rounds = 40;
+		uint32_t n_cv_arg = n_cv;
+		void *args[] = { &jump, &n_cv_arg, &ctr, &max_rounds };
+		ProfScope ps_(ctx, "k_jump_all");
+		CU(cudaLaunchCooperativeKernel((void *)k_jump_all, dim3(ctx->jump_grid), dim3(512), args, 0, ctx->stream));
+		++ctx->launches;
+	}
+	if (n_paths) {
+		LAUNCH(k_heads_paths<W>, (unsigned)((2 * n_paths + 127) / 128), 128, ps, n_paths, k, t, vL, vR, kind, node_ebase, jump, vsucc, wlast, vedge, g, ctr);
+		LAUNCH(k_interior_paths<W>, (unsigned)((2 * n_paths + 255) / 256), 256, ps, n_paths, k, vL, vR, kind, jump, wlast, vedge, g);
+	}
+	if (n_e) LAUNCH(k_rc_links<W>, (unsigned)((n_e + 255) / 256), 256, t, k, (uint32_t)n_e, node_slot, node_ebase, g, ctr);
+	if (n_paths && !ctx->skip_counts)
+		LAUNCH(k_counts_paths<W>, (unsigned)((n_paths + 255) / 256), 256, ps, n_paths, k, t, vL, kind, node_ebase, vedge, g, ctr);
+	CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+	if (read_counters(ctx)) return -1;
+	ctx->st.jump_rounds = ctx->h_ctr[CTR_JUMP_ROUNDS];
+	ctx->st.n_seq_words = ctx->h_ctr[CTR_SEQ_WORDS];
+	ctx->st.n_kp1_on_edge = ctx->h_ctr[CTR_KP1_ON_EDGE];
+	if (ctx->st.n_seq_words > seq_cap) return fail(ctx, "edge sequence buffer overflow (%llu > %llu words)",
+						       (unsigned long long)ctx->st.n_seq_words, (unsigned long long)seq_cap);
+	ctx->have_graph = true;
+	ctx->contracted = true;
+	return 0;
+}
+
 static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool with_graph)
 {
 	CU(cudaSetDevice(ctx->device));
@@ -603,7 +720,11 @@ static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool wit
 		ctx->cur_solid_key = ctx->comb_key.p;
 		ctx->cur_solid_cnt = ctx->comb_cnt.p;
 	}
-	if (with_graph) {
+	ctx->contracted = false;
+	if (with_graph && ctx->contract && !ctx->n_garbage && ctx->n_blocks && !direct) {
+		rc = ctx->W == 1 ? graph_stage_paths<1>(ctx) : graph_stage_paths<2>(ctx);
+		if (rc) return rc;
+	} else if (with_graph) {
 		rc = ctx->W == 1 ? graph_stage<1>(ctx) : graph_stage<2>(ctx);
 		if (rc) return rc;
 	} else {
@@ -966,6 +1087,7 @@ extern "C" int tagpu_copy_solid(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint
 extern "C" int tagpu_copy_kmers(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint8_t *mask)
 {
 	if (!ctx->have_graph) return fail(ctx, "no graph result to copy");
+	if (ctx->contracted) return fail(ctx, "the k-mer table of a contracted build holds the path-end k-mers only (tagpu_set_contract(ctx, 0) for the full table)");
 	CU(cudaSetDevice(ctx->device));
 	const uint32_t n_slots = ctx->kt_slots;
 	std::vector<uint8_t> m(n_slots);
