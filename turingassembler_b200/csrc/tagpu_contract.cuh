@@ -18,8 +18,10 @@
 #include "tagpu_count.cuh"
 #include "tagpu_graph.cuh"
 
-constexpr int TAGPU_CONTRACT_MAXN = 512;          // (k+1)-mers of a block that k_contract handles; larger blocks stay single
-constexpr int TAGPU_CONTRACT_THREADS = 256;
+// (k+1)-mers of a block that k_contract handles (larger blocks stay single): sized so that ~30-40 KB of shared memory per
+// CTA keep 5-7 CTAs on an SM
+template <int W> struct ContractCfg { static constexpr int MAXN = W == 1 ? 512 : 256; };
+constexpr int TAGPU_CONTRACT_THREADS = 128;
 constexpr uint32_t TAGPU_OE_END = 0xffffu;
 
 template <int W> struct PathStore {
@@ -39,24 +41,39 @@ TAGPU_DI uint32_t tagpu_mmer_hash26(uint32_t fw)
 	return (min(fw, rv) * 0x9e3779b1u) >> 6;
 }
 
-// (i) + (ii) for the k-mer z: home bucket in [b0, b0 + nbk) and no potentially foreign extension
+// the k bases of z, first base in the top bits of a 128-bit register pair (so that a 2-bit left shift yields the next base)
+template <int W> TAGPU_DI void tagpu_left_align(const Key<W> &z, int k, uint64_t &hi, uint64_t &lo);
+template <> TAGPU_DI void tagpu_left_align<1>(const Key<1> &z, int k, uint64_t &hi, uint64_t &lo) { hi = z.lo << (64 - 2 * k); lo = 0; }
+template <> TAGPU_DI void tagpu_left_align<2>(const Key<2> &z, int k, uint64_t &hi, uint64_t &lo)
+{
+	const int sh = 128 - 2 * k;                                     // 2 .. 126 (k = 32..63 with two words)
+	if (sh >= 64) { hi = z.lo << (sh - 64); lo = 0; }
+	else { hi = (z.hi << sh) | (z.lo >> (64 - sh)); lo = z.lo << sh; }
+}
+
+// (i) + (ii) for the k-mer z: home bucket in [b0, b0 + nbk) and no potentially foreign extension.
+// Forward and reverse-complement m-mers are both rolled (3 + 3 operations per base), two bases per iteration.
 template <int W>
 TAGPU_DI bool tagpu_kmer_is_local(const Key<W> &z, int k, int log2_buckets, uint32_t b0, uint32_t nbk)
 {
-	typedef KeyOps<W> KO;
 	const int m = TAGPU_MINIMIZER_M;
 	const uint32_t mm = (1u << (2 * m)) - 1u;
-	uint32_t mu = 0xffffffffu, fw = 0;
+	uint64_t hi, lo;
+	tagpu_left_align<W>(z, k, hi, lo);
+	uint32_t mu = 0xffffffffu, fw = 0, rv = 0, head = 0;
 	for (int i = 0; i < k; ++i) {
-		fw = ((fw << 2) | KO::base_at(z, k, i)) & mm;
-		if (i >= m - 1) mu = min(mu, tagpu_mmer_hash26(fw));
+		const uint32_t c = (uint32_t)(hi >> 62);
+		hi = (hi << 2) | (lo >> 62);
+		lo <<= 2;
+		fw = ((fw << 2) | c) & mm;
+		rv = (rv >> 2) | ((3u - c) << (2 * (m - 1)));
+		if (i == m - 2) head = fw;                                  // first m - 1 bases
+		if (i >= m - 1) mu = min(mu, (min(fw, rv) * 0x9e3779b1u) >> 6);
 	}
 	const uint32_t b = tagpu_bucket_of(mu, log2_buckets);
 	if (b < b0 || b >= b0 + nbk) return false;
 	// right extensions: last m-1 bases of z + c; left extensions: c + first m-1 bases of z
 	const uint32_t tail = fw & (mm >> 2);
-	uint32_t head = 0;
-	for (int i = 0; i < m - 1; ++i) head = (head << 2) | KO::base_at(z, k, i);
 	for (uint32_t c = 0; c < 4; ++c) {
 		if (tagpu_mmer_hash26((tail << 2) | c) < mu) return false;
 		if (tagpu_mmer_hash26((c << (2 * (m - 1))) | head) < mu) return false;
@@ -66,13 +83,16 @@ TAGPU_DI bool tagpu_kmer_is_local(const Key<W> &z, int k, int log2_buckets, uint
 
 // ---------------------------------------------------------------- contraction of one block in shared memory
 // Oriented entry oe = 2 i + o: o = 0 the stored canonical (k+1)-mer x_i, o = 1 its reverse complement.
+// Output without global bookkeeping: the paths of a block are packed at the front of its own slot range [base, base + n) of
+// the path arrays (the remaining slots get n = 0 = "no path here"), and their interior words are carved out of
+// interior[base, base + n) with a shared-memory bump counter (a path of len entries needs < len words).
 template <int W>
 __global__ void __launch_bounds__(TAGPU_CONTRACT_THREADS)
 k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W> *__restrict__ solid, const uint32_t *__restrict__ solid_cnt,
 	   int k, int log2_buckets, int enable, PathStore<W> ps, unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
-	constexpr int MAXN = TAGPU_CONTRACT_MAXN, TS_MAX = 4 * MAXN, T = TAGPU_CONTRACT_THREADS;
+	constexpr int MAXN = ContractCfg<W>::MAXN, TS_MAX = 4 * MAXN, T = TAGPU_CONTRACT_THREADS;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Key<W> *e_key = reinterpret_cast<Key<W> *>(smem_raw);               // [MAXN]
 	Key<W> *t_key = e_key + MAXN;                                       // [TS_MAX] canonical k-mers, ~key (0 = empty)
@@ -80,25 +100,26 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 	uint32_t *t_mask = e_cnt + MAXN;                                    // [TS_MAX] local edge mask (low 8 bits), bit 8 = hidden
 	uint16_t *t_out = reinterpret_cast<uint16_t *>(t_mask + TS_MAX);    // [TS_MAX][2] an oriented entry leaving (k-mer, orient)
 	uint16_t *nxt = t_out + 2 * TS_MAX;                                 // [2 MAXN] next oriented entry on the path / END
-	__shared__ uint32_t s_block, s_warp[2][T / 32];
-	__shared__ unsigned long long s_base[2];
-	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	__shared__ uint32_t s_block, s_words, s_paths, s_hidden, s_cand;
+	const uint32_t tid = threadIdx.x;
 	const int K = k + 1;
 	const Key<W> kmask = KO::mask(k);
-
-	auto find = [&](const Key<W> &z, uint32_t ts) -> uint32_t {          // slot of canonical k-mer z (must be present)
-		const Key<W> stored = KO::bnot(z);
-		uint32_t s = (uint32_t)KO::hash(z) & (ts - 1);
-		for (uint32_t p = 0; p < ts; ++p) {
-			if (KO::eq(t_key[s], stored)) return s;
-			s = (s + 1) & (ts - 1);
-		}
-		return 0xffffffffu;
-	};
+	uint32_t next_block = 0;                                            // thread 0: id requested one block ahead
+	if (tid == 0) next_block = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);
+#ifdef TAGPU_TIMING
+	long long tc[6] = { 0, 0, 0, 0, 0, 0 }, tc_t = clock64();
+#define TC(i) do { long long n_ = clock64(); tc[i] += n_ - tc_t; tc_t = n_; } while (0)
+#else
+#define TC(i)
+#endif
 
 	for (;;) {
 		__syncthreads();
-		if (tid == 0) s_block = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);
+		if (tid == 0) {
+			s_block = next_block;
+			if (next_block < n_blocks) next_block = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);
+			s_words = 0; s_paths = 0; s_hidden = 0; s_cand = 0;
+		}
 		__syncthreads();
 		const uint32_t blk = s_block;
 		if (blk >= n_blocks) break;
@@ -106,16 +127,12 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 		const uint32_t n = sb.n;
 		if (!enable || sb.flags || n > (uint32_t)MAXN) {
 			// not contractible: every (k+1)-mer is a path of its own
-			unsigned long long base = 0;
-			if (tid == 0) s_base[0] = atomicAdd(ctr + CTR_PATHS, (unsigned long long)n);
-			__syncthreads();
-			base = s_base[0];
 			for (uint32_t i = tid; i < n; i += T) {
-				if (base + i >= ps.cap_paths) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT); break; }
 				const Key<W> x = solid[sb.base + i];
-				ps.first[base + i] = x; ps.last[base + i] = x; ps.n[base + i] = 1u; ps.cnt[base + i] = solid_cnt[sb.base + i];
-				ps.off[base + i] = 0ull;
+				ps.first[sb.base + i] = x; ps.last[sb.base + i] = x; ps.n[sb.base + i] = 1u; ps.cnt[sb.base + i] = solid_cnt[sb.base + i];
+				ps.off[sb.base + i] = 0ull;
 			}
+			if (tid == 0) atomicAdd(ctr + CTR_PATHS, (unsigned long long)n);
 			continue;
 		}
 		uint32_t ts = 64;
@@ -123,6 +140,7 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 		for (uint32_t i = tid; i < ts; i += T) { t_key[i] = KO::make(0, 0); t_mask[i] = 0; }
 		for (uint32_t i = tid; i < n; i += T) { e_key[i] = solid[sb.base + i]; e_cnt[i] = solid_cnt[sb.base + i]; }
 		__syncthreads();
+		TC(0);
 		// ---- local k-mer table with masks and one leaving entry per (k-mer, orientation)
 		for (uint32_t oe = tid; oe < 2u * n; oe += T) {
 			const Key<W> x = e_key[oe >> 1];
@@ -145,8 +163,9 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 			t_out[2u * s + oz] = (uint16_t)oe;
 		}
 		__syncthreads();
-		// ---- which k-mers can be hidden
-		uint32_t n_hidden = 0;
+		TC(1);
+		// ---- which k-mers can be hidden.  The cheap conditions first, candidates compacted (nxt[] is free until the link
+		// phase), so that the expensive minimizer test runs on full warps.
 		for (uint32_t s = tid; s < ts; s += T) {
 			const Key<W> st = t_key[s];
 			if (KO::is_zero(st)) continue;
@@ -159,102 +178,84 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 			if (i0 == i1) continue;
 			const Key<W> x0 = e_key[i0], x1 = e_key[i1];
 			if (KO::eq(x0, KO::rc(x0, K)) || KO::eq(x1, KO::rc(x1, K))) continue;
-			if (tagpu_kmer_is_local<W>(KO::bnot(st), k, log2_buckets, sb.b0, sb.nbk)) {
-				t_mask[s] = m | 0x100u;
+			nxt[atomicAdd(&s_cand, 1u)] = (uint16_t)s;
+		}
+		__syncthreads();
+		uint32_t n_hidden = 0;
+		for (uint32_t c = tid; c < s_cand; c += T) {
+			const uint32_t s = nxt[c];
+			if (tagpu_kmer_is_local<W>(KO::bnot(t_key[s]), k, log2_buckets, sb.b0, sb.nbk)) {
+				t_mask[s] |= 0x100u;
 				++n_hidden;
 			}
 		}
+		if (n_hidden) atomicAdd(&s_hidden, n_hidden);
 		__syncthreads();
+		TC(2);
 		// ---- links: the entry that continues an oriented entry across a hidden k-mer
 		for (uint32_t oe = tid; oe < 2u * n; oe += T) {
 			const Key<W> x = e_key[oe >> 1];
 			const Key<W> y = (oe & 1u) ? KO::rc(x, K) : x;
 			const Key<W> q = KO::band(y, kmask), qr = KO::rc(q, k);       // tail k-mer
 			const bool fwd = KO::le(q, qr);
-			const uint32_t s = find(fwd ? q : qr, ts);
+			const Key<W> stored = KO::bnot(fwd ? q : qr);
+			uint32_t s = (uint32_t)KO::hash(fwd ? q : qr) & (ts - 1), probes = 0;
+			while (!KO::eq(t_key[s], stored) && probes < ts) { s = (s + 1) & (ts - 1); ++probes; }
 			uint16_t nx = (uint16_t)TAGPU_OE_END;
-			if (s == 0xffffffffu) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT);
+			if (probes >= ts) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT);
 			else if (t_mask[s] & 0x100u) nx = t_out[2u * s + (fwd ? 0u : 1u)];
 			nxt[oe] = nx;
 		}
 		__syncthreads();
-		// ---- heads walk their paths: a path is emitted by its smaller end (head <= rc of its last entry)
-		// pass 0 counts paths and interior words, pass 1 writes
-		for (int pass = 0; pass < 2; ++pass) {
-			uint32_t my_paths = 0, my_words = 0, out_p = 0, out_w = 0;
-			if (pass) {
-				out_p = s_warp[0][warp];
-				out_w = s_warp[1][warp];
-			}
-			for (uint32_t oe0 = 0; oe0 < 2u * n; oe0 += T) {
-				const uint32_t oe = oe0 + tid;
-				bool emit = false;
-				uint32_t len = 0, last = 0;
+		TC(3);
+		// ---- every entry: does one of its orientations head a path that this orientation emits?  (a path is emitted by
+		// its smaller end: head <= reverse complement of its last entry)
+		for (uint32_t i = tid; i < n; i += T) {
+			uint32_t out_n = 0;
+			for (uint32_t o = 0; o < 2 && !out_n; ++o) {
+				const uint32_t oe = 2u * i + o;
+				if (nxt[oe ^ 1u] != TAGPU_OE_END) continue;              // not a head: the k-mer before it is hidden
+				uint32_t len = 0, last = oe, cur = oe;
 				unsigned long long csum = 0;
-				if (oe < 2u * n && nxt[oe ^ 1u] == TAGPU_OE_END) {           // head: the k-mer before it is not hidden
-					uint32_t cur = oe;
-					for (;;) {
-						++len;
-						csum += e_cnt[cur >> 1];
-						last = cur;
-						const uint32_t nx = nxt[cur];
-						if (nx == TAGPU_OE_END) break;
-						if (len > 2u * n) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT); break; }
-						cur = nx;
-					}
-					emit = oe <= (last ^ 1u);
+				for (;;) {
+					++len;
+					csum += e_cnt[cur >> 1];
+					last = cur;
+					const uint32_t nx = nxt[cur];
+					if (nx == TAGPU_OE_END) break;
+					if (len > 2u * n) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT); break; }
+					cur = nx;
 				}
-				const uint32_t words = emit && len > 1 ? (len - 1 + 15) >> 4 : 0u;
-				// warp-level exclusive prefix of (paths, words) among the emitting lanes of this sweep
-				uint32_t ip = emit ? 1u : 0u, iw = words;
-#pragma unroll
-				for (int d = 1; d < 32; d <<= 1) {
-					const uint32_t a = __shfl_up_sync(0xffffffffu, ip, d), b = __shfl_up_sync(0xffffffffu, iw, d);
-					if (lane >= (uint32_t)d) { ip += a; iw += b; }
+				if (oe > (last ^ 1u)) continue;                           // the twin path emits
+				if (oe == (last ^ 1u) && o == 1) continue;                // (self-twin single entry: emitted once, as o = 0)
+				const uint32_t words = len > 1 ? (len - 1 + 15) >> 4 : 0u;
+				const unsigned long long wo = sb.base + (words ? atomicAdd(&s_words, words) : 0u);
+				const unsigned long long pi = sb.base + atomicAdd(&s_paths, 1u);   // the block's paths are packed at its front
+				const Key<W> xf = o ? KO::rc(e_key[i], K) : e_key[i];
+				const Key<W> xl = (last & 1u) ? KO::rc(e_key[last >> 1], K) : e_key[last >> 1];
+				ps.first[pi] = xf; ps.last[pi] = xl; ps.cnt[pi] = csum; ps.off[pi] = wo; ps.n[pi] = len;
+				uint32_t c2 = nxt[oe], word = 0;
+				for (uint32_t j = 0; j + 1 < len; ++j) {                 // interior base j = last base of the (j + 2)-th entry
+					const Key<W> xe = e_key[c2 >> 1];
+					const uint32_t base = (c2 & 1u) ? 3u - KO::first_base(xe, K) : KO::last_base(xe);
+					word |= base << ((j & 15u) << 1);
+					if ((j & 15u) == 15u || j + 2 == len) { ps.interior[wo + (j >> 4)] = word; word = 0; }
+					c2 = nxt[c2];
 				}
-				const uint32_t tp = __shfl_sync(0xffffffffu, ip, 31), tw = __shfl_sync(0xffffffffu, iw, 31);
-				if (pass && emit) {
-					const unsigned long long pi = s_base[0] + out_p + ip - 1u, wo = s_base[1] + out_w + iw - words;
-					if (pi >= ps.cap_paths || wo + words > ps.cap_words) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT);
-					else {
-						const Key<W> xf = (oe & 1u) ? KO::rc(e_key[oe >> 1], K) : e_key[oe >> 1];
-						const Key<W> xl = (last & 1u) ? KO::rc(e_key[last >> 1], K) : e_key[last >> 1];
-						ps.first[pi] = xf; ps.last[pi] = xl; ps.n[pi] = len; ps.cnt[pi] = csum; ps.off[pi] = wo;
-						uint32_t cur = nxt[oe], word = 0;
-						for (uint32_t j = 0; j + 1 < len; ++j) {            // interior base j = last base of the (j + 2)-th entry
-							const Key<W> xe = e_key[cur >> 1];
-							const uint32_t base = (cur & 1u) ? 3u - KO::first_base(xe, K) : KO::last_base(xe);
-							word |= base << ((j & 15u) << 1);
-							if ((j & 15u) == 15u || j + 2 == len) { ps.interior[wo + (j >> 4)] = word; word = 0; }
-							cur = nxt[cur];
-						}
-					}
-				}
-				my_paths += tp;
-				my_words += tw;
-				out_p += tp;
-				out_w += tw;
-			}
-			if (!pass) {
-				// per-warp totals -> exclusive offsets, one pair of global atomics per block
-				if (lane == 0) { s_warp[0][warp] = my_paths; s_warp[1][warp] = my_words; }
-				__syncthreads();
-				if (tid == 0) {
-					uint32_t ap = 0, aw = 0;
-					for (int w2 = 0; w2 < T / 32; ++w2) {
-						const uint32_t vp = s_warp[0][w2], vw = s_warp[1][w2];
-						s_warp[0][w2] = ap; s_warp[1][w2] = aw;
-						ap += vp; aw += vw;
-					}
-					s_base[0] = ap ? atomicAdd(ctr + CTR_PATHS, (unsigned long long)ap) : 0ull;
-					s_base[1] = aw ? atomicAdd(ctr + CTR_PATH_WORDS, (unsigned long long)aw) : 0ull;
-				}
-				__syncthreads();
+				out_n = len;
 			}
 		}
-		n_hidden = __reduce_add_sync(0xffffffffu, n_hidden);
-		if (lane == 0 && n_hidden) atomicAdd(ctr + CTR_KMERS, (unsigned long long)n_hidden);
+		__syncthreads();
+		for (uint32_t i = s_paths + tid; i < n; i += T) ps.n[sb.base + i] = 0;   // the rest of the block's slots hold no path
+		TC(4);
+		if (tid == 0) {
+			if (s_paths) atomicAdd(ctr + CTR_PATHS, (unsigned long long)s_paths);
+			if (s_hidden) atomicAdd(ctr + CTR_KMERS, (unsigned long long)s_hidden);
+		}
 	}
+#ifdef TAGPU_TIMING
+	if ((tid & 31u) == 0) for (int i = 0; i < 5; ++i) atomicAdd(ctr + CTR_JUMP_FLAGS + 56 + i, (unsigned long long)tc[i]);
+#endif
 }
 
 // base i (0 .. k + n - 1) of a path: the first k + 1 from its first (k+1)-mer, the rest from the interior words
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(256) k_insert_paths(PathStore<W> ps, uint64_t 
 	typedef KeyOps<W> KO;
 	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t n_new = 0;
-	if (p < n_paths) {
+	if (p < n_paths && ps.n[p]) {
 		const Key<W> xf = ps.first[p], xl = ps.last[p];
 		const Key<W> km = KO::mask(k);
 		const Key<W> k1 = KO::shr2(xf), k2 = KO::band(xl, km);
@@ -307,7 +308,9 @@ __global__ void __launch_bounds__(256) k_succ_paths(PathStore<W> ps, uint64_t n_
 	if (idx >= 2 * n_paths) return;
 	const uint64_t p = idx >> 1;
 	const uint32_t dir = (uint32_t)idx & 1u;
-	const uint32_t a = dir ? vR[p] : vL[p], b = (dir ? vL[p] : vR[p]) ^ 1u, w = ps.n[p];
+	const uint32_t w = ps.n[p];
+	if (!w) return;                                                  // no path in this slot
+	const uint32_t a = dir ? vR[p] : vL[p], b = (dir ? vL[p] : vR[p]) ^ 1u;
 	const uint32_t ka = kind[a >> 1];
 	if (!(ka & TAGPU_CHAIN)) return;                                 // leaves a node: k_heads_paths
 	const uint32_t cva = (ka & ~TAGPU_CHAIN) * 2u + (a & 1u), kb = kind[b >> 1];
@@ -337,10 +340,9 @@ __global__ void __launch_bounds__(128) k_heads_paths(PathStore<W> ps, uint64_t n
 	bool have = false;
 	uint32_t a = 0, b = 0, w = 0, ord = 0, len = 0, dst = 0, first = TAGPU_NONE, e = 0;
 	Key<W> xf = KO::make(0, 0);
-	if (in) {
+	if (in && (w = ps.n[p]) != 0u) {
 		a = dir ? vR[p] : vL[p];
 		b = (dir ? vL[p] : vR[p]) ^ 1u;
-		w = ps.n[p];
 		const uint32_t ka = kind[a >> 1];
 		if (!(ka & TAGPU_CHAIN)) {                                   // the path leaves a node: it starts an edge
 			have = true;
@@ -399,6 +401,7 @@ __global__ void __launch_bounds__(256) k_interior_paths(PathStore<W> ps, uint64_
 	if (idx >= 2 * n_paths) return;
 	const uint64_t p = idx >> 1;
 	const uint32_t dir = (uint32_t)idx & 1u;
+	if (!ps.n[p]) return;
 	const uint32_t a = dir ? vR[p] : vL[p], ka = kind[a >> 1];
 	if (!(ka & TAGPU_CHAIN)) return;
 	const uint32_t cv = (ka & ~TAGPU_CHAIN) * 2u + (a & 1u);
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(256) k_counts_paths(PathStore<W> ps, uint64_t 
 	typedef KeyOps<W> KO;
 	const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned long long on_edge = 0;
-	if (p < n_paths) {
+	if (p < n_paths && ps.n[p]) {
 		const uint32_t v = vL[p], slot = v >> 1, o = v & 1u, kd = kind[slot];
 		uint32_t e;
 		if (!(kd & TAGPU_CHAIN)) {

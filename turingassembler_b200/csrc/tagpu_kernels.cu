@@ -185,6 +185,8 @@ extern "C" tagpu_ctx *tagpu_create(int device)
 	cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
 	for (int i = 0; i < TAGPU_UPLOAD_CHUNKS_MAX; ++i) cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
 	memset(&ctx->st, 0, sizeof(ctx->st));
+	const char *ct = getenv("TAGPU_CONTRACT");
+	if (ct) ctx->contract = atoi(ct);
 	return ctx;
 }
 
@@ -587,8 +589,8 @@ static int graph_stage_paths(tagpu_ctx *ctx)
 	unsigned long long *ctr = ctx->d_ctr;
 	// ---- level 1: contraction inside the blocks of the solid list
 	PathStore<W> ps;
-	ps.cap_paths = n_solid + 1;
-	ps.cap_words = n_solid / 16 + n_solid / 2 + 16;
+	ps.cap_paths = n_solid + 1;                             // path slots = entries of the solid list (most stay empty)
+	ps.cap_words = n_solid + 16;
 	if (ensure(ctx, ctx->p_first, ps.cap_paths * sizeof(Key<W>)) || ensure(ctx, ctx->p_last, ps.cap_paths * sizeof(Key<W>)) ||
 	    ensure(ctx, ctx->p_n, ps.cap_paths * 4) || ensure(ctx, ctx->p_cnt, ps.cap_paths * 8) || ensure(ctx, ctx->p_off, ps.cap_paths * 8) ||
 	    ensure(ctx, ctx->p_int, ps.cap_words * 4))
@@ -596,29 +598,38 @@ static int graph_stage_paths(tagpu_ctx *ctx)
 	ps.first = (Key<W> *)ctx->p_first.p; ps.last = (Key<W> *)ctx->p_last.p; ps.n = (uint32_t *)ctx->p_n.p;
 	ps.cnt = (unsigned long long *)ctx->p_cnt.p; ps.off = (unsigned long long *)ctx->p_off.p; ps.interior = (uint32_t *)ctx->p_int.p;
 	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctr + CTR_SPARE1, 0, 8, ctx->stream)); }
-	constexpr size_t smem_c = (size_t)TAGPU_CONTRACT_MAXN * sizeof(Key<W>) + (size_t)4 * TAGPU_CONTRACT_MAXN * sizeof(Key<W>) +
-				  (size_t)TAGPU_CONTRACT_MAXN * 4 + (size_t)4 * TAGPU_CONTRACT_MAXN * 4 + (size_t)8 * TAGPU_CONTRACT_MAXN * 2 +
-				  (size_t)2 * TAGPU_CONTRACT_MAXN * 2;
+	constexpr size_t cmax = ContractCfg<W>::MAXN;
+	constexpr size_t smem_c = cmax * sizeof(Key<W>) + 4 * cmax * sizeof(Key<W>) + cmax * 4 + 4 * cmax * 4 + 8 * cmax * 2 + 2 * cmax * 2;
 	static bool attr_done[3] = { false, false, false };
 	if (!attr_done[W]) {
 		CU(cudaFuncSetAttribute(k_contract<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
 		attr_done[W] = true;
 	}
 	if (ctx->n_blocks)
-		LAUNCH_SMEM(k_contract<W>, 3 * ctx->n_sm, TAGPU_CONTRACT_THREADS, smem_c, (const SolidBlock *)ctx->blocks.p, (uint32_t)ctx->n_blocks,
+		LAUNCH_SMEM(k_contract<W>, (W == 1 ? 5 : 7) * ctx->n_sm, TAGPU_CONTRACT_THREADS, smem_c, (const SolidBlock *)ctx->blocks.p, (uint32_t)ctx->n_blocks,
 			    (const Key<W> *)ctx->cur_solid_key, (const uint32_t *)ctx->cur_solid_cnt, k, ctx->log2_buckets, 1, ps, ctr);
 	if (read_counters(ctx)) return -1;
-	const uint64_t n_paths = ctx->h_ctr[CTR_PATHS];
+	const uint64_t n_live_paths = ctx->h_ctr[CTR_PATHS], n_paths = n_solid;   // n_paths: slots the path kernels sweep
+#ifdef TAGPU_TIMING
+	{
+		double tot = 0;
+		for (int i = 0; i < 5; ++i) tot += (double)ctx->h_ctr[CTR_JUMP_FLAGS + 56 + i];
+		fprintf(stderr, "[tagpu timing] k_contract warp-cycles: load %.1f%% build %.1f%% hide %.1f%% links %.1f%% emit %.1f%%; blocks %llu, live paths %llu of %llu\n",
+			100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 56] / tot, 100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 57] / tot, 100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 58] / tot,
+			100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 59] / tot, 100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 60] / tot, (unsigned long long)ctx->n_blocks,
+			(unsigned long long)n_live_paths, (unsigned long long)n_solid);
+	}
+#endif
 	// ---- level 2: the global stage on the paths
-	const uint64_t slots64 = (n_paths * 5) / 2 + 1024;
+	const uint64_t slots64 = (n_live_paths * 5) / 2 + 1024;
 	if (slots64 > (1ull << 30)) return fail(ctx, "k-mer table would need %llu slots (> 2^30)", (unsigned long long)slots64);
 	const uint32_t n_slots = (uint32_t)slots64;
 	ctx->kt_slots = n_slots;
 	const size_t mask_bytes = ((size_t)n_slots + 3) / 4 * 4;
 	if (ensure(ctx, ctx->kt_keys, (size_t)n_slots * sizeof(Key<W>)) || ensure(ctx, ctx->kt_mask, mask_bytes) ||
 	    ensure(ctx, ctx->node_ord, (size_t)n_slots * 4) || ensure(ctx, ctx->vL, (n_paths + 1) * 4) ||
-	    ensure(ctx, ctx->vR, (n_paths + 1) * 4) || ensure(ctx, ctx->node_slot, (2 * n_paths + 1) * 4) ||
-	    ensure(ctx, ctx->node_ebase, (2 * n_paths + 1) * 4) || ensure(ctx, ctx->chain_slot, (2 * n_paths + 1) * 4))
+	    ensure(ctx, ctx->vR, (n_paths + 1) * 4) || ensure(ctx, ctx->node_slot, (2 * n_live_paths + 1) * 4) ||
+	    ensure(ctx, ctx->node_ebase, (2 * n_live_paths + 1) * 4) || ensure(ctx, ctx->chain_slot, (2 * n_live_paths + 1) * 4))
 		return -1;
 	KTab<W> t;
 	t.keys = (Key<W> *)ctx->kt_keys.p;
