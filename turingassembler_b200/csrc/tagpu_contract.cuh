@@ -89,7 +89,8 @@ TAGPU_DI bool tagpu_kmer_is_local(const Key<W> &z, int k, int log2_buckets, uint
 template <int W>
 __global__ void __launch_bounds__(TAGPU_CONTRACT_THREADS)
 k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W> *__restrict__ solid, const uint32_t *__restrict__ solid_cnt,
-	   int k, int log2_buckets, int enable, PathStore<W> ps, unsigned long long *ctr)
+	   int k, int log2_buckets, int enable, PathStore<W> ps, uint32_t *__restrict__ blk_np, uint32_t *__restrict__ blk_nw,
+	   unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
 	constexpr int MAXN = ContractCfg<W>::MAXN, TS_MAX = 4 * MAXN, T = TAGPU_CONTRACT_THREADS;
@@ -132,7 +133,7 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 				ps.first[sb.base + i] = x; ps.last[sb.base + i] = x; ps.n[sb.base + i] = 1u; ps.cnt[sb.base + i] = solid_cnt[sb.base + i];
 				ps.off[sb.base + i] = 0ull;
 			}
-			if (tid == 0) atomicAdd(ctr + CTR_PATHS, (unsigned long long)n);
+			if (tid == 0) { blk_np[blk] = n; blk_nw[blk] = 0; }
 			continue;
 		}
 		uint32_t ts = 64;
@@ -249,13 +250,65 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 		for (uint32_t i = s_paths + tid; i < n; i += T) ps.n[sb.base + i] = 0;   // the rest of the block's slots hold no path
 		TC(4);
 		if (tid == 0) {
-			if (s_paths) atomicAdd(ctr + CTR_PATHS, (unsigned long long)s_paths);
+			blk_np[blk] = s_paths;
+			blk_nw[blk] = s_words;
 			if (s_hidden) atomicAdd(ctr + CTR_KMERS, (unsigned long long)s_hidden);
 		}
 	}
 #ifdef TAGPU_TIMING
 	if ((tid & 31u) == 0) for (int i = 0; i < 5; ++i) atomicAdd(ctr + CTR_JUMP_FLAGS + 56 + i, (unsigned long long)tc[i]);
 #endif
+}
+
+// ---------------------------------------------------------------- dense path arrays
+// single block: exclusive prefix of the per-block path / word counts (in place), totals -> ctr[CTR_PATHS], ctr[CTR_PATH_WORDS]
+__global__ void __launch_bounds__(1024) k_scan_path_counts(uint32_t *__restrict__ blk_np, uint32_t *__restrict__ blk_nw, uint32_t n_blocks, unsigned long long *ctr)
+{
+	__shared__ unsigned long long s_p[1024], s_w[1024];
+	const uint32_t per = (n_blocks + 1023) / 1024, lo = min(threadIdx.x * per, n_blocks), hi = min(lo + per, n_blocks);
+	unsigned long long sp = 0, sw = 0;
+	for (uint32_t i = lo; i < hi; ++i) { sp += blk_np[i]; sw += blk_nw[i]; }
+	s_p[threadIdx.x] = sp;
+	s_w[threadIdx.x] = sw;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned long long ap = 0, aw = 0;
+		for (int t = 0; t < 1024; ++t) {
+			const unsigned long long vp = s_p[t], vw = s_w[t];
+			s_p[t] = ap; s_w[t] = aw;
+			ap += vp; aw += vw;
+		}
+		ctr[CTR_PATHS] = ap;
+		ctr[CTR_PATH_WORDS] = aw;
+	}
+	__syncthreads();
+	unsigned long long ap = s_p[threadIdx.x], aw = s_w[threadIdx.x];
+	for (uint32_t i = lo; i < hi; ++i) {
+		const uint32_t vp = blk_np[i], vw = blk_nw[i];
+		blk_np[i] = (uint32_t)ap; blk_nw[i] = (uint32_t)aw;
+		ap += vp; aw += vw;
+	}
+}
+
+// one warp per block: its paths (packed at the front of the block's slot range) and interior words move to dense arrays
+template <int W>
+__global__ void __launch_bounds__(256) k_pack_paths(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const uint32_t *__restrict__ blk_np,
+						     const uint32_t *__restrict__ blk_nw, unsigned long long n_live, unsigned long long n_words,
+						     PathStore<W> src, PathStore<W> dst)
+{
+	const uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+	if (blk >= n_blocks) return;
+	const SolidBlock sb = blocks[blk];
+	const unsigned long long p0 = blk_np[blk], w0 = blk_nw[blk];
+	const unsigned long long np = (blk + 1 < n_blocks ? blk_np[blk + 1] : n_live) - p0, nw = (blk + 1 < n_blocks ? blk_nw[blk + 1] : n_words) - w0;
+	for (unsigned long long i = lane; i < np; i += 32) {
+		dst.first[p0 + i] = src.first[sb.base + i];
+		dst.last[p0 + i] = src.last[sb.base + i];
+		dst.n[p0 + i] = src.n[sb.base + i];
+		dst.cnt[p0 + i] = src.cnt[sb.base + i];
+		dst.off[p0 + i] = w0 + (src.off[sb.base + i] - sb.base);
+	}
+	for (unsigned long long i = lane; i < nw; i += 32) dst.interior[w0 + i] = src.interior[sb.base + i];
 }
 
 // base i (0 .. k + n - 1) of a path: the first k + 1 from its first (k+1)-mer, the rest from the interior words
