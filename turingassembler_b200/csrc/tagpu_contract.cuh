@@ -83,17 +83,16 @@ TAGPU_DI bool tagpu_kmer_is_local(const Key<W> &z, int k, int log2_buckets, uint
 
 // ---------------------------------------------------------------- contraction of one block in shared memory
 // Oriented entry oe = 2 i + o: o = 0 the stored canonical (k+1)-mer x_i, o = 1 its reverse complement.
-// Output without global bookkeeping: the paths of a block are packed at the front of its own slot range [base, base + n) of
-// the path arrays (the remaining slots get n = 0 = "no path here"), and their interior words are carved out of
-// interior[base, base + n) with a shared-memory bump counter (a path of len entries needs < len words).
+// Output: dense path arrays.  A block first counts its paths and interior words (shared-memory bump counters give every
+// path its place inside the block), reserves the range for all of them with one atomic per global counter
+// (ctr[CTR_PATHS], ctr[CTR_PATH_WORDS]), then writes.  The order of the paths in the arrays is therefore arbitrary.
 template <int W>
 __global__ void __launch_bounds__(TAGPU_CONTRACT_THREADS)
 k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W> *__restrict__ solid, const uint32_t *__restrict__ solid_cnt,
-	   int k, int log2_buckets, int enable, PathStore<W> ps, uint32_t *__restrict__ blk_np, uint32_t *__restrict__ blk_nw,
-	   unsigned long long *ctr)
+	   int k, int log2_buckets, int enable, PathStore<W> ps, unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
-	constexpr int MAXN = ContractCfg<W>::MAXN, TS_MAX = 4 * MAXN, T = TAGPU_CONTRACT_THREADS;
+	constexpr int MAXN = ContractCfg<W>::MAXN, TS_MAX = 4 * MAXN, T = TAGPU_CONTRACT_THREADS, R = MAXN / T;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Key<W> *e_key = reinterpret_cast<Key<W> *>(smem_raw);               // [MAXN]
 	Key<W> *t_key = e_key + MAXN;                                       // [TS_MAX] canonical k-mers, ~key (0 = empty)
@@ -102,6 +101,7 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 	uint16_t *t_out = reinterpret_cast<uint16_t *>(t_mask + TS_MAX);    // [TS_MAX][2] an oriented entry leaving (k-mer, orient)
 	uint16_t *nxt = t_out + 2 * TS_MAX;                                 // [2 MAXN] next oriented entry on the path / END
 	__shared__ uint32_t s_block, s_words, s_paths, s_hidden, s_cand;
+	__shared__ unsigned long long s_pbase, s_wbase;
 	const uint32_t tid = threadIdx.x;
 	const int K = k + 1;
 	const Key<W> kmask = KO::mask(k);
@@ -128,12 +128,14 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 		const uint32_t n = sb.n;
 		if (!enable || sb.flags || n > (uint32_t)MAXN) {
 			// not contractible: every (k+1)-mer is a path of its own
+			if (tid == 0) s_pbase = atomicAdd(ctr + CTR_PATHS, (unsigned long long)n);
+			__syncthreads();
+			const unsigned long long pb = s_pbase;
 			for (uint32_t i = tid; i < n; i += T) {
 				const Key<W> x = solid[sb.base + i];
-				ps.first[sb.base + i] = x; ps.last[sb.base + i] = x; ps.n[sb.base + i] = 1u; ps.cnt[sb.base + i] = solid_cnt[sb.base + i];
-				ps.off[sb.base + i] = 0ull;
+				ps.first[pb + i] = x; ps.last[pb + i] = x; ps.n[pb + i] = 1u; ps.cnt[pb + i] = solid_cnt[sb.base + i];
+				ps.off[pb + i] = 0ull;
 			}
-			if (tid == 0) { blk_np[blk] = n; blk_nw[blk] = 0; }
 			continue;
 		}
 		uint32_t ts = 64;
@@ -210,10 +212,15 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 		__syncthreads();
 		TC(3);
 		// ---- every entry: does one of its orientations head a path that this orientation emits?  (a path is emitted by
-		// its smaller end: head <= reverse complement of its last entry)
-		for (uint32_t i = tid; i < n; i += T) {
-			uint32_t out_n = 0;
-			for (uint32_t o = 0; o < 2 && !out_n; ++o) {
+		// its smaller end: head <= reverse complement of its last entry; an entry emits at most one path)
+		uint32_t r_len[R], r_oe[R], r_last[R], r_pi[R], r_wo[R];
+		unsigned long long r_cs[R];
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			const uint32_t i = tid + (uint32_t)r * T;
+			r_len[r] = 0;
+			if (i >= n) continue;
+			for (uint32_t o = 0; o < 2 && !r_len[r]; ++o) {
 				const uint32_t oe = 2u * i + o;
 				if (nxt[oe ^ 1u] != TAGPU_OE_END) continue;              // not a head: the k-mer before it is hidden
 				uint32_t len = 0, last = oe, cur = oe;
@@ -230,85 +237,42 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 				if (oe > (last ^ 1u)) continue;                           // the twin path emits
 				if (oe == (last ^ 1u) && o == 1) continue;                // (self-twin single entry: emitted once, as o = 0)
 				const uint32_t words = len > 1 ? (len - 1 + 15) >> 4 : 0u;
-				const unsigned long long wo = sb.base + (words ? atomicAdd(&s_words, words) : 0u);
-				const unsigned long long pi = sb.base + atomicAdd(&s_paths, 1u);   // the block's paths are packed at its front
-				const Key<W> xf = o ? KO::rc(e_key[i], K) : e_key[i];
-				const Key<W> xl = (last & 1u) ? KO::rc(e_key[last >> 1], K) : e_key[last >> 1];
-				ps.first[pi] = xf; ps.last[pi] = xl; ps.cnt[pi] = csum; ps.off[pi] = wo; ps.n[pi] = len;
-				uint32_t c2 = nxt[oe], word = 0;
-				for (uint32_t j = 0; j + 1 < len; ++j) {                 // interior base j = last base of the (j + 2)-th entry
-					const Key<W> xe = e_key[c2 >> 1];
-					const uint32_t base = (c2 & 1u) ? 3u - KO::first_base(xe, K) : KO::last_base(xe);
-					word |= base << ((j & 15u) << 1);
-					if ((j & 15u) == 15u || j + 2 == len) { ps.interior[wo + (j >> 4)] = word; word = 0; }
-					c2 = nxt[c2];
-				}
-				out_n = len;
+				r_len[r] = len; r_oe[r] = oe; r_last[r] = last; r_cs[r] = csum;
+				r_wo[r] = words ? atomicAdd(&s_words, words) : 0u;
+				r_pi[r] = atomicAdd(&s_paths, 1u);
 			}
 		}
 		__syncthreads();
-		for (uint32_t i = s_paths + tid; i < n; i += T) ps.n[sb.base + i] = 0;   // the rest of the block's slots hold no path
-		TC(4);
 		if (tid == 0) {
-			blk_np[blk] = s_paths;
-			blk_nw[blk] = s_words;
+			s_pbase = atomicAdd(ctr + CTR_PATHS, (unsigned long long)s_paths);
+			s_wbase = s_words ? atomicAdd(ctr + CTR_PATH_WORDS, (unsigned long long)s_words) : 0ull;
 			if (s_hidden) atomicAdd(ctr + CTR_KMERS, (unsigned long long)s_hidden);
 		}
+		__syncthreads();
+		const unsigned long long pbase = s_pbase, wbase = s_wbase;
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			const uint32_t len = r_len[r];
+			if (!len) continue;
+			const uint32_t oe = r_oe[r], last = r_last[r];
+			const unsigned long long pi = pbase + r_pi[r], wo = wbase + r_wo[r];
+			const Key<W> xf = (oe & 1u) ? KO::rc(e_key[oe >> 1], K) : e_key[oe >> 1];
+			const Key<W> xl = (last & 1u) ? KO::rc(e_key[last >> 1], K) : e_key[last >> 1];
+			ps.first[pi] = xf; ps.last[pi] = xl; ps.cnt[pi] = r_cs[r]; ps.off[pi] = wo; ps.n[pi] = len;
+			uint32_t c2 = nxt[oe], word = 0;
+			for (uint32_t j = 0; j + 1 < len; ++j) {                     // interior base j = last base of the (j + 2)-th entry
+				const Key<W> xe = e_key[c2 >> 1];
+				const uint32_t base = (c2 & 1u) ? 3u - KO::first_base(xe, K) : KO::last_base(xe);
+				word |= base << ((j & 15u) << 1);
+				if ((j & 15u) == 15u || j + 2 == len) { ps.interior[wo + (j >> 4)] = word; word = 0; }
+				c2 = nxt[c2];
+			}
+		}
+		TC(4);
 	}
 #ifdef TAGPU_TIMING
 	if ((tid & 31u) == 0) for (int i = 0; i < 5; ++i) atomicAdd(ctr + CTR_JUMP_FLAGS + 56 + i, (unsigned long long)tc[i]);
 #endif
-}
-
-// ---------------------------------------------------------------- dense path arrays
-// single block: exclusive prefix of the per-block path / word counts (in place), totals -> ctr[CTR_PATHS], ctr[CTR_PATH_WORDS]
-__global__ void __launch_bounds__(1024) k_scan_path_counts(uint32_t *__restrict__ blk_np, uint32_t *__restrict__ blk_nw, uint32_t n_blocks, unsigned long long *ctr)
-{
-	__shared__ unsigned long long s_p[1024], s_w[1024];
-	const uint32_t per = (n_blocks + 1023) / 1024, lo = min(threadIdx.x * per, n_blocks), hi = min(lo + per, n_blocks);
-	unsigned long long sp = 0, sw = 0;
-	for (uint32_t i = lo; i < hi; ++i) { sp += blk_np[i]; sw += blk_nw[i]; }
-	s_p[threadIdx.x] = sp;
-	s_w[threadIdx.x] = sw;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		unsigned long long ap = 0, aw = 0;
-		for (int t = 0; t < 1024; ++t) {
-			const unsigned long long vp = s_p[t], vw = s_w[t];
-			s_p[t] = ap; s_w[t] = aw;
-			ap += vp; aw += vw;
-		}
-		ctr[CTR_PATHS] = ap;
-		ctr[CTR_PATH_WORDS] = aw;
-	}
-	__syncthreads();
-	unsigned long long ap = s_p[threadIdx.x], aw = s_w[threadIdx.x];
-	for (uint32_t i = lo; i < hi; ++i) {
-		const uint32_t vp = blk_np[i], vw = blk_nw[i];
-		blk_np[i] = (uint32_t)ap; blk_nw[i] = (uint32_t)aw;
-		ap += vp; aw += vw;
-	}
-}
-
-// one warp per block: its paths (packed at the front of the block's slot range) and interior words move to dense arrays
-template <int W>
-__global__ void __launch_bounds__(256) k_pack_paths(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const uint32_t *__restrict__ blk_np,
-						     const uint32_t *__restrict__ blk_nw, unsigned long long n_live, unsigned long long n_words,
-						     PathStore<W> src, PathStore<W> dst)
-{
-	const uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-	if (blk >= n_blocks) return;
-	const SolidBlock sb = blocks[blk];
-	const unsigned long long p0 = blk_np[blk], w0 = blk_nw[blk];
-	const unsigned long long np = (blk + 1 < n_blocks ? blk_np[blk + 1] : n_live) - p0, nw = (blk + 1 < n_blocks ? blk_nw[blk + 1] : n_words) - w0;
-	for (unsigned long long i = lane; i < np; i += 32) {
-		dst.first[p0 + i] = src.first[sb.base + i];
-		dst.last[p0 + i] = src.last[sb.base + i];
-		dst.n[p0 + i] = src.n[sb.base + i];
-		dst.cnt[p0 + i] = src.cnt[sb.base + i];
-		dst.off[p0 + i] = w0 + (src.off[sb.base + i] - sb.base);
-	}
-	for (unsigned long long i = lane; i < nw; i += 32) dst.interior[w0 + i] = src.interior[sb.base + i];
 }
 
 // base i (0 .. k + n - 1) of a path: the first k + 1 from its first (k+1)-mer, the rest from the interior words

@@ -54,7 +54,7 @@ struct tagpu_ctx {
 	// build_local_assembly_graph: (k+1)-mers of the flanking contigs appended behind the solid ones (count 0), and the contigs
 	uint64_t n_garbage = 0, n_blocks = 0;                    // n_blocks: directory entries of the local solid list (0 = no directory)
 	bool local_mode = false;
-	Buf blocks, p_first, p_last, p_n, p_cnt, p_off, p_int, d_first, d_last, d_n, d_cnt, d_off, d_int, blk_np, blk_nw, wlast, g_key, comb_key, comb_cnt, g_seq, hj_own, hj_bits, hj_list, hj_jump2;
+	Buf blocks, d_first, d_last, d_n, d_cnt, d_off, d_int, wlast, g_key, comb_key, comb_cnt, g_seq, hj_own, hj_bits, hj_list, hj_jump2;
 	int n_contigs = 0;
 	uint64_t contig_off[4] = { 0 };
 	uint32_t contig_len[4] = { 0 };
@@ -198,7 +198,7 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	dist_release(ctx);
-	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->blocks, &ctx->p_first, &ctx->p_last, &ctx->p_n, &ctx->p_cnt, &ctx->p_off, &ctx->p_int, &ctx->d_first, &ctx->d_last, &ctx->d_n, &ctx->d_cnt, &ctx->d_off, &ctx->d_int, &ctx->blk_np, &ctx->blk_nw, &ctx->wlast, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->hj_own, &ctx->hj_bits, &ctx->hj_list, &ctx->hj_jump2, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->blocks, &ctx->d_first, &ctx->d_last, &ctx->d_n, &ctx->d_cnt, &ctx->d_off, &ctx->d_int, &ctx->wlast, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->hj_own, &ctx->hj_bits, &ctx->hj_list, &ctx->hj_jump2, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
 			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
 	for (Buf *b : bufs)
@@ -587,19 +587,17 @@ static int graph_stage_paths(tagpu_ctx *ctx)
 	const int k = ctx->k;
 	const uint64_t n_solid = ctx->st.n_solid;
 	unsigned long long *ctr = ctx->d_ctr;
-	// ---- level 1: contraction inside the blocks of the solid list (sparse path slots), then dense path arrays
-	PathStore<W> sp;
-	sp.cap_paths = n_solid + 1;                             // one slot per entry of the solid list, most stay empty
-	sp.cap_words = n_solid + 16;
+	// ---- level 1: contraction inside the blocks of the solid list -> dense path arrays (at most one path per solid entry)
+	PathStore<W> ps;
+	ps.cap_paths = n_solid + 1;
+	ps.cap_words = n_solid + 16;
 	const uint32_t n_blocks = (uint32_t)ctx->n_blocks;
-	if (ensure(ctx, ctx->p_first, sp.cap_paths * sizeof(Key<W>)) || ensure(ctx, ctx->p_last, sp.cap_paths * sizeof(Key<W>)) ||
-	    ensure(ctx, ctx->p_n, sp.cap_paths * 4) || ensure(ctx, ctx->p_cnt, sp.cap_paths * 8) || ensure(ctx, ctx->p_off, sp.cap_paths * 8) ||
-	    ensure(ctx, ctx->p_int, sp.cap_words * 4) || ensure(ctx, ctx->blk_np, ((size_t)n_blocks + n_blocks / 8 + 1024) * 4) ||
-	    ensure(ctx, ctx->blk_nw, ((size_t)n_blocks + n_blocks / 8 + 1024) * 4))
+	if (ensure(ctx, ctx->d_first, ps.cap_paths * sizeof(Key<W>)) || ensure(ctx, ctx->d_last, ps.cap_paths * sizeof(Key<W>)) ||
+	    ensure(ctx, ctx->d_n, ps.cap_paths * 4) || ensure(ctx, ctx->d_cnt, ps.cap_paths * 8) || ensure(ctx, ctx->d_off, ps.cap_paths * 8) ||
+	    ensure(ctx, ctx->d_int, ps.cap_words * 4))
 		return -1;
-	sp.first = (Key<W> *)ctx->p_first.p; sp.last = (Key<W> *)ctx->p_last.p; sp.n = (uint32_t *)ctx->p_n.p;
-	sp.cnt = (unsigned long long *)ctx->p_cnt.p; sp.off = (unsigned long long *)ctx->p_off.p; sp.interior = (uint32_t *)ctx->p_int.p;
-	uint32_t *blk_np = (uint32_t *)ctx->blk_np.p, *blk_nw = (uint32_t *)ctx->blk_nw.p;
+	ps.first = (Key<W> *)ctx->d_first.p; ps.last = (Key<W> *)ctx->d_last.p; ps.n = (uint32_t *)ctx->d_n.p;
+	ps.cnt = (unsigned long long *)ctx->d_cnt.p; ps.off = (unsigned long long *)ctx->d_off.p; ps.interior = (uint32_t *)ctx->d_int.p;
 	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctr + CTR_SPARE1, 0, 8, ctx->stream)); }
 	constexpr size_t cmax = ContractCfg<W>::MAXN;
 	constexpr size_t smem_c = cmax * sizeof(Key<W>) + 4 * cmax * sizeof(Key<W>) + cmax * 4 + 4 * cmax * 4 + 8 * cmax * 2 + 2 * cmax * 2;
@@ -608,36 +606,22 @@ static int graph_stage_paths(tagpu_ctx *ctx)
 		CU(cudaFuncSetAttribute(k_contract<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
 		attr_done[W] = true;
 	}
-	if (n_blocks) {
-		LAUNCH_SMEM(k_contract<W>, (W == 1 ? 5 : 7) * ctx->n_sm, TAGPU_CONTRACT_THREADS, smem_c, (const SolidBlock *)ctx->blocks.p, n_blocks,
-			    (const Key<W> *)ctx->cur_solid_key, (const uint32_t *)ctx->cur_solid_cnt, k, ctx->log2_buckets, 1, sp, blk_np, blk_nw, ctr);
-		LAUNCH(k_scan_path_counts, 1, 1024, blk_np, blk_nw, n_blocks, ctr);
-	}
-	if (read_counters(ctx)) return -1;
-	const uint64_t n_paths = ctx->h_ctr[CTR_PATHS], n_words = ctx->h_ctr[CTR_PATH_WORDS];
-	PathStore<W> ps;
-	// (head-room: the block structure, hence these counts, varies a little from build to build with the sub-class splits)
-	ps.cap_paths = n_paths + n_paths / 8 + 1024;
-	ps.cap_words = n_words + n_words / 8 + 1024;
-	if (ensure(ctx, ctx->d_first, ps.cap_paths * sizeof(Key<W>)) || ensure(ctx, ctx->d_last, ps.cap_paths * sizeof(Key<W>)) ||
-	    ensure(ctx, ctx->d_n, ps.cap_paths * 4) || ensure(ctx, ctx->d_cnt, ps.cap_paths * 8) || ensure(ctx, ctx->d_off, ps.cap_paths * 8) ||
-	    ensure(ctx, ctx->d_int, ps.cap_words * 4))
-		return -1;
-	ps.first = (Key<W> *)ctx->d_first.p; ps.last = (Key<W> *)ctx->d_last.p; ps.n = (uint32_t *)ctx->d_n.p;
-	ps.cnt = (unsigned long long *)ctx->d_cnt.p; ps.off = (unsigned long long *)ctx->d_off.p; ps.interior = (uint32_t *)ctx->d_int.p;
 	if (n_blocks)
-		LAUNCH(k_pack_paths<W>, (unsigned)(((size_t)n_blocks * 32 + 255) / 256), 256, (const SolidBlock *)ctx->blocks.p, n_blocks, blk_np, blk_nw,
-		       (unsigned long long)n_paths, (unsigned long long)n_words, sp, ps);
+		LAUNCH_SMEM(k_contract<W>, (W == 1 ? 5 : 7) * ctx->n_sm, TAGPU_CONTRACT_THREADS, smem_c, (const SolidBlock *)ctx->blocks.p, n_blocks,
+			    (const Key<W> *)ctx->cur_solid_key, (const uint32_t *)ctx->cur_solid_cnt, k, ctx->log2_buckets, 1, ps, ctr);
+	if (read_counters(ctx)) return -1;
+	const uint64_t n_paths = ctx->h_ctr[CTR_PATHS];
+	if (n_paths > n_solid) return fail(ctx, "contraction produced more paths (%llu) than solid (k+1)-mers", (unsigned long long)n_paths);
 	// ---- level 2: the global stage on the paths
 	const uint64_t slots64 = (n_paths * 5) / 2 + 1024;
 	if (slots64 > (1ull << 30)) return fail(ctx, "k-mer table would need %llu slots (> 2^30)", (unsigned long long)slots64);
 	const uint32_t n_slots = (uint32_t)slots64;
 	ctx->kt_slots = n_slots;
-	const size_t mask_bytes = ((size_t)n_slots + 3) / 4 * 4, slack = n_slots / 8 + 4096;   // allocation head-room, see above
+	const size_t mask_bytes = ((size_t)n_slots + 3) / 4 * 4, slack = n_slots / 8 + 4096;   // head-room: n_paths varies a little between builds
 	if (ensure(ctx, ctx->kt_keys, ((size_t)n_slots + slack) * sizeof(Key<W>)) || ensure(ctx, ctx->kt_mask, mask_bytes + slack) ||
-	    ensure(ctx, ctx->node_ord, ((size_t)n_slots + slack) * 4) || ensure(ctx, ctx->vL, ps.cap_paths * 4) ||
-	    ensure(ctx, ctx->vR, ps.cap_paths * 4) || ensure(ctx, ctx->node_slot, 2 * ps.cap_paths * 4) ||
-	    ensure(ctx, ctx->node_ebase, 2 * ps.cap_paths * 4) || ensure(ctx, ctx->chain_slot, 2 * ps.cap_paths * 4))
+	    ensure(ctx, ctx->node_ord, ((size_t)n_slots + slack) * 4) || ensure(ctx, ctx->vL, (n_paths + slack) * 4) ||
+	    ensure(ctx, ctx->vR, (n_paths + slack) * 4) || ensure(ctx, ctx->node_slot, 2 * (n_paths + slack) * 4) ||
+	    ensure(ctx, ctx->node_ebase, 2 * (n_paths + slack) * 4) || ensure(ctx, ctx->chain_slot, 2 * (n_paths + slack) * 4))
 		return -1;
 	KTab<W> t;
 	t.keys = (Key<W> *)ctx->kt_keys.p;
