@@ -35,12 +35,11 @@ def check_against_oracle(tagpu, oracle, stream, k, tmp_path, tag="x", ci=2):
     assert st["n_distinct"] == want["n_distinct"]
     assert np.array_equal(hi, want["hi"]) and np.array_equal(lo, want["lo"]) and np.array_equal(cnt, want["count"])
     assert st["sum_solid"] == int(want["count"].astype(np.uint64).sum())
-    # 2. k-mer table with edge masks (the contracted graph stage keeps only the path-end k-mers in its table)
+    # 2. k-mer table with edge masks (after a two-level graph stage the library rebuilds the full table on demand)
     g = oracle.graph(k, want["hi"], want["lo"], want["count"])
-    if not tagpu.contract:
-        khi, klo, kmask = oracle.graph_masks(g)
-        ghi, glo, gmask = sort_keys(*tagpu.kmers())
-        assert np.array_equal(ghi, khi) and np.array_equal(glo, klo) and np.array_equal(gmask, kmask)
+    khi, klo, kmask = oracle.graph_masks(g)
+    ghi, glo, gmask = sort_keys(*tagpu.kmers())
+    assert np.array_equal(ghi, khi) and np.array_equal(glo, klo) and np.array_equal(gmask, kmask)
     # 3. graph, canonically
     ora_bin, gpu_bin = str(tmp_path / f"ora_{tag}.bin"), str(tmp_path / f"gpu_{tag}.bin")
     oracle.save_bin(g, ora_bin)
@@ -265,15 +264,18 @@ def test_list_ranking_variant():
     import sys
     env = dict(os.environ, TAGPU_LIST_RANKING="hj")
     p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-q", "-m", "gpu", "-x",
-                        "-k", "golden or hairpins or edge_cases or every_key_width"], capture_output=True, text=True, env=env, timeout=1200)
+                        "-k", "golden or hairpins or edge_cases or every_key_width or one_level"], capture_output=True, text=True, env=env, timeout=1200)
     assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
 
 
+@pytest.mark.parametrize("contract", [True, False], ids=["two_level", "one_level"])
 @pytest.mark.parametrize("k", [21, 31, 32, 45, 63])
-def test_contracted_graph_stage(tagpu, oracle, k, tmp_path):
-    """Two-level graph stage (csrc/tagpu_contract.cuh): paths contracted inside the bucket groups, then the path-driven
-    global stage — same graph, bit-exact, on golden cases, adversarial topologies and mixed inputs."""
-    tagpu.set_contract(True)
+def test_graph_stage_variants(tagpu, oracle, k, contract, tmp_path):
+    """Both graph stages give the reference's graph, bit-exact, on golden cases, adversarial topologies and mixed inputs:
+    the two-level one (default; csrc/tagpu_contract.cuh: paths contracted inside the bucket groups, then the path-driven
+    global stage) and the one-level one (every k-mer in the HBM table; used for local assembly and multi-GPU builds)."""
+    was = tagpu.contract
+    tagpu.set_contract(contract)
     try:
         for tag, stream in (("p1", case_stream("P1")), ("m1", case_stream("M1")), ("rnd", _reads.gen_stream(60000, 5000, seed=200 + k, sub_err=0.004))):
             check_against_oracle(tagpu, oracle, stream, k, tmp_path, f"ct_{tag}_{k}")
@@ -288,4 +290,4 @@ def test_contracted_graph_stage(tagpu, oracle, k, tmp_path):
         parts += [d + rnd(80), rnd(80) + d, d + rnd(70), rnd(90) + d] * 2 + [b"A" * 300] * 3 + [b"ACGT" * 60] * 3
         check_against_oracle(tagpu, oracle, b"\n".join(parts) + b"\n", k, tmp_path, f"ct_adv_{k}")
     finally:
-        tagpu.set_contract(False)
+        tagpu.set_contract(was)

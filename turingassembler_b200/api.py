@@ -201,7 +201,7 @@ class Tagpu:
         if not self.ctx:
             raise TagpuError("tagpu_create failed: no usable CUDA device (libtagpu has no CPU fallback)")
         self.lib.tagpu_set_cutoff(self.ctx, cutoff)
-        self.contract = False
+        self.contract = os.environ.get("TAGPU_CONTRACT", "1") != "0"   # two-level graph stage (library default: on)
 
     def close(self):
         if getattr(self, "ctx", None):

@@ -34,7 +34,7 @@ struct tagpu_ctx {
 	cudaEvent_t ev_chunk[TAGPU_UPLOAD_CHUNKS_MAX];
 	const uint8_t *h_src = nullptr;    // host source of the read stream while its upload is pending (tagpu_*_host calls)
 	int ci = 2, skip_counts = 0;
-	int contract = 0;                  // two-level graph stage (tagpu_contract.cuh)
+	int contract = 1;                  // two-level graph stage (tagpu_contract.cuh)
 	bool contracted = false;           // the last graph was built that way (hidden k-mers are not in the table)
 	int log2_buckets = 0;              // of the last count stage
 	int k = 0, K = 0, W = 0;
@@ -143,6 +143,8 @@ static int ensure(tagpu_ctx *ctx, Buf &b, size_t bytes, bool *grew = nullptr)
 {
 	if (grew) *grew = false;
 	if (bytes <= b.cap && b.p) return 0;
+	static const bool trace = getenv("TAGPU_TRACE_ALLOC") != nullptr;   // developer aid: a steady-state step must not allocate
+	if (trace) fprintf(stderr, "tagpu: buffer at ctx+%ld grows %zu -> %zu bytes\n", (long)((char *)&b - (char *)ctx), b.cap, bytes);
 	if (b.p) CU(cudaFree(b.p));
 	b.p = nullptr;
 	b.cap = 0;
@@ -151,6 +153,15 @@ static int ensure(tagpu_ctx *ctx, Buf &b, size_t bytes, bool *grew = nullptr)
 	b.cap = want;
 	if (grew) *grew = true;
 	return 0;
+}
+
+// For buffers whose size follows a quantity that varies a little from build to build on the same input (the number of
+// paths of the two-level graph stage and what derives from it): grow with head-room, so that a steady-state step never
+// reallocates (a cudaFree in the middle of a step costs milliseconds).
+static int ensure_slack(tagpu_ctx *ctx, Buf &b, size_t bytes)
+{
+	if (bytes <= b.cap && b.p) return 0;
+	return ensure(ctx, b, bytes + bytes / 8 + 65536);
 }
 
 static uint64_t pow2_at_least(uint64_t x)
@@ -456,6 +467,55 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 	return count_owned<W>(ctx, cfg, peers, 0, solid_cap);
 }
 
+// ------------------------------------------------------------------------------------------------ list ranking
+// jump[cv] = (successor | TAGPU_TERM at a chain end, link weight) -> (terminal, distance to it) for every chain vertex
+static int rank_lists(tagpu_ctx *ctx, unsigned long long *jump, uint32_t n_cv)
+{
+	unsigned long long *ctr = ctx->d_ctr;
+	// all pointer-jumping rounds in one cooperative launch (grid-wide sync between rounds)
+	if (!ctx->jump_grid) {
+		int per_sm = 0;
+		CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jump_all, 512, 0));
+		ctx->jump_grid = ctx->n_sm * (per_sm > 0 ? per_sm : 1);
+	}
+	int max_rounds = 40;
+	// small inputs: plain pointer jumping (the arrays sit in L2); large ones: work-efficient list ranking
+	static const char *rank_env = getenv("TAGPU_LIST_RANKING");      // "hj" / "wyllie" force one of them (tests)
+	const bool hj = rank_env ? !strcmp(rank_env, "hj") : n_cv >= (48u << 20);
+	if (!hj) {
+		uint32_t n_cv_arg = n_cv;
+		void *args[] = { &jump, &n_cv_arg, &ctr, &max_rounds };
+		ProfScope ps_(ctx, "k_jump_all");
+		CU(cudaLaunchCooperativeKernel((void *)k_jump_all, dim3(ctx->jump_grid), dim3(512), args, 0, ctx->stream));
+		++ctx->launches;
+		return 0;
+	}
+	if (ensure_slack(ctx, ctx->hj_own, ((size_t)n_cv + 1) * 8) || ensure_slack(ctx, ctx->hj_bits, ((size_t)n_cv / 32 + 2) * 4) ||
+	    ensure_slack(ctx, ctx->hj_list, ((size_t)n_cv + 1) * 4))
+		return -1;
+	unsigned long long *own = (unsigned long long *)ctx->hj_own.p;
+	uint32_t *bits = (uint32_t *)ctx->hj_bits.p, *list = (uint32_t *)ctx->hj_list.p;
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(own, 0xff, ((size_t)n_cv + 1) * 8, ctx->stream)); }
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctr + CTR_CHAIN, 0, 8, ctx->stream)); }
+	LAUNCH(k_hj_mark, (n_cv + 255) / 256, 256, jump, n_cv, bits, list, own, ctr);
+	if (read_counters(ctx)) return -1;
+	const uint32_t n_spl = (uint32_t)ctx->h_ctr[CTR_CHAIN];
+	// (sized with head-room: the splitter count varies a little from build to build with the table layout)
+	const size_t spl_cap = (size_t)n_spl + 1 > (size_t)n_cv / 16 ? (size_t)n_spl + 1 : (size_t)n_cv / 16;
+	if (ensure(ctx, ctx->hj_jump2, spl_cap * 8)) return -1;
+	unsigned long long *jump2 = (unsigned long long *)ctx->hj_jump2.p;
+	if (n_spl) {
+		LAUNCH(k_hj_walk, (n_spl + 255) / 256, 256, jump, bits, list, n_spl, own, jump2);
+		uint32_t n_arg = n_spl;
+		void *args[] = { &jump2, &n_arg, &ctr, &max_rounds };
+		ProfScope ps_(ctx, "k_jump_all");
+		CU(cudaLaunchCooperativeKernel((void *)k_jump_all, dim3(ctx->jump_grid), dim3(512), args, 0, ctx->stream));
+		++ctx->launches;
+	}
+	LAUNCH(k_hj_finish, (n_cv + 255) / 256, 256, jump, n_cv, own, jump2);
+	return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ graph stage
 template <int W>
 static int graph_stage(tagpu_ctx *ctx)
@@ -513,47 +573,7 @@ static int graph_stage(tagpu_ctx *ctx)
 	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(g.e_seq, 0, seq_cap * 4, ctx->stream)); }
 	if (n_cv) {
 		LAUNCH(k_build_succ<W>, (n_cv + 255) / 256, 256, t, k, n_cv, kind, chain_slot, jump, vsucc, ctr);
-		// all pointer-jumping rounds in one cooperative launch (grid-wide sync between rounds)
-		if (!ctx->jump_grid) {
-			int per_sm = 0;
-			CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jump_all, 512, 0));
-			ctx->jump_grid = ctx->n_sm * (per_sm > 0 ? per_sm : 1);
-		}
-		int max_rounds = 40;
-		// small inputs: plain pointer jumping (the arrays sit in L2); large ones: work-efficient list ranking
-		static const char *rank_env = getenv("TAGPU_LIST_RANKING");      // "hj" / "wyllie" force one of them (tests)
-		const bool hj = rank_env ? !strcmp(rank_env, "hj") : n_cv >= (48u << 20);
-		if (!hj) {
-			uint32_t n_cv_arg = n_cv;
-			void *args[] = { &jump, &n_cv_arg, &ctr, &max_rounds };
-			ProfScope ps_(ctx, "k_jump_all");
-			CU(cudaLaunchCooperativeKernel((void *)k_jump_all, dim3(ctx->jump_grid), dim3(512), args, 0, ctx->stream));
-			++ctx->launches;
-		} else {
-			if (ensure(ctx, ctx->hj_own, ((size_t)n_cv + 1) * 8) || ensure(ctx, ctx->hj_bits, ((size_t)n_cv / 32 + 2) * 4) ||
-			    ensure(ctx, ctx->hj_list, ((size_t)n_cv + 1) * 4))
-				return -1;
-			unsigned long long *own = (unsigned long long *)ctx->hj_own.p;
-			uint32_t *bits = (uint32_t *)ctx->hj_bits.p, *list = (uint32_t *)ctx->hj_list.p;
-			{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(own, 0xff, ((size_t)n_cv + 1) * 8, ctx->stream)); }
-			{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctr + CTR_CHAIN, 0, 8, ctx->stream)); }
-			LAUNCH(k_hj_mark, (n_cv + 255) / 256, 256, jump, n_cv, bits, list, own, ctr);
-			if (read_counters(ctx)) return -1;
-			const uint32_t n_spl = (uint32_t)ctx->h_ctr[CTR_CHAIN];
-			// (sized with head-room: the splitter count varies a little from build to build with the table layout)
-			const size_t spl_cap = (size_t)n_spl + 1 > (size_t)n_cv / 16 ? (size_t)n_spl + 1 : (size_t)n_cv / 16;
-			if (ensure(ctx, ctx->hj_jump2, spl_cap * 8)) return -1;
-			unsigned long long *jump2 = (unsigned long long *)ctx->hj_jump2.p;
-			if (n_spl) {
-				LAUNCH(k_hj_walk, (n_spl + 255) / 256, 256, jump, bits, list, n_spl, own, jump2);
-				uint32_t n_arg = n_spl;
-				void *args[] = { &jump2, &n_arg, &ctr, &max_rounds };
-				ProfScope ps_(ctx, "k_jump_all");
-				CU(cudaLaunchCooperativeKernel((void *)k_jump_all, dim3(ctx->jump_grid), dim3(512), args, 0, ctx->stream));
-				++ctx->launches;
-			}
-			LAUNCH(k_hj_finish, (n_cv + 255) / 256, 256, jump, n_cv, own, jump2);
-		}
+		if (rank_lists(ctx, jump, n_cv)) return -1;
 	}
 	if (n_nodes)
 		LAUNCH(k_edge_heads<W>, (unsigned)((2 * n_nodes + 127) / 128), 128, t, k, (uint32_t)n_nodes, kind, node_slot, node_ebase,
@@ -617,11 +637,11 @@ static int graph_stage_paths(tagpu_ctx *ctx)
 	if (slots64 > (1ull << 30)) return fail(ctx, "k-mer table would need %llu slots (> 2^30)", (unsigned long long)slots64);
 	const uint32_t n_slots = (uint32_t)slots64;
 	ctx->kt_slots = n_slots;
-	const size_t mask_bytes = ((size_t)n_slots + 3) / 4 * 4, slack = n_slots / 8 + 4096;   // head-room: n_paths varies a little between builds
-	if (ensure(ctx, ctx->kt_keys, ((size_t)n_slots + slack) * sizeof(Key<W>)) || ensure(ctx, ctx->kt_mask, mask_bytes + slack) ||
-	    ensure(ctx, ctx->node_ord, ((size_t)n_slots + slack) * 4) || ensure(ctx, ctx->vL, (n_paths + slack) * 4) ||
-	    ensure(ctx, ctx->vR, (n_paths + slack) * 4) || ensure(ctx, ctx->node_slot, 2 * (n_paths + slack) * 4) ||
-	    ensure(ctx, ctx->node_ebase, 2 * (n_paths + slack) * 4) || ensure(ctx, ctx->chain_slot, 2 * (n_paths + slack) * 4))
+	const size_t mask_bytes = ((size_t)n_slots + 3) / 4 * 4;
+	if (ensure_slack(ctx, ctx->kt_keys, (size_t)n_slots * sizeof(Key<W>)) || ensure_slack(ctx, ctx->kt_mask, mask_bytes) ||
+	    ensure_slack(ctx, ctx->node_ord, (size_t)n_slots * 4) || ensure_slack(ctx, ctx->vL, (n_paths + 1) * 4) ||
+	    ensure_slack(ctx, ctx->vR, (n_paths + 1) * 4) || ensure_slack(ctx, ctx->node_slot, (2 * n_paths + 1) * 4) ||
+	    ensure_slack(ctx, ctx->node_ebase, (2 * n_paths + 1) * 4) || ensure_slack(ctx, ctx->chain_slot, (2 * n_paths + 1) * 4))
 		return -1;
 	KTab<W> t;
 	t.keys = (Key<W> *)ctx->kt_keys.p;
@@ -642,9 +662,8 @@ static int graph_stage_paths(tagpu_ctx *ctx)
 	if (n_e > 0xfffffff0ull) return fail(ctx, "too many edges (%llu)", (unsigned long long)n_e);
 	const uint32_t n_cv = (uint32_t)(2 * n_chain);
 	const uint64_t seq_cap = (n_e * (uint64_t)k + 2 * n_solid) / 16 + n_e + 16;
-	if (ensure(ctx, ctx->jump, ((size_t)n_cv + 1) * 8) || ensure(ctx, ctx->vsucc, ((size_t)n_cv + 1) * 4) ||
-	    ensure(ctx, ctx->wlast, ((size_t)n_cv + 1) * 4) ||
-	    ensure(ctx, ctx->vedge, ((size_t)n_cv + 1) * 4) || ensure(ctx, ctx->e_src, (n_e + 1) * 4) ||
+	if (ensure_slack(ctx, ctx->jump, ((size_t)n_cv + 1) * 8) || ensure_slack(ctx, ctx->vsucc, ((size_t)n_cv + 1) * 4) ||
+	    ensure_slack(ctx, ctx->wlast, ((size_t)n_cv + 1) * 4) || ensure_slack(ctx, ctx->vedge, ((size_t)n_cv + 1) * 4) || ensure(ctx, ctx->e_src, (n_e + 1) * 4) ||
 	    ensure(ctx, ctx->e_dst, (n_e + 1) * 4) || ensure(ctx, ctx->e_rc, (n_e + 1) * 4) || ensure(ctx, ctx->e_len, (n_e + 1) * 4) ||
 	    ensure(ctx, ctx->e_count, (n_e + 1) * 8) || ensure(ctx, ctx->e_off, (n_e + 1) * 8) || ensure(ctx, ctx->e_seq, seq_cap * 4))
 		return -1;
@@ -658,17 +677,7 @@ static int graph_stage_paths(tagpu_ctx *ctx)
 	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(g.e_seq, 0, seq_cap * 4, ctx->stream)); }
 	if (n_cv) {
 		LAUNCH(k_succ_paths<W>, (unsigned)((2 * n_paths + 255) / 256), 256, ps, n_paths, vL, vR, kind, jump, vsucc, wlast);
-		if (!ctx->jump_grid) {
-			int per_sm = 0;
-			CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jump_all, 512, 0));
-			ctx->jump_grid = ctx->n_sm * (per_sm > 0 ? per_sm : 1);
-		}
-		int max_rounds = 40;
-		uint32_t n_cv_arg = n_cv;
-		void *args[] = { &jump, &n_cv_arg, &ctr, &max_rounds };
-		ProfScope ps_(ctx, "k_jump_all");
-		CU(cudaLaunchCooperativeKernel((void *)k_jump_all, dim3(ctx->jump_grid), dim3(512), args, 0, ctx->stream));
-		++ctx->launches;
+		if (rank_lists(ctx, jump, n_cv)) return -1;
 	}
 	if (n_paths) {
 		LAUNCH(k_heads_paths<W>, (unsigned)((2 * n_paths + 127) / 128), 128, ps, n_paths, k, t, vL, vR, kind, node_ebase, jump, vsucc, wlast, vedge, g, ctr);
@@ -1087,16 +1096,13 @@ extern "C" int tagpu_copy_solid(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint
 	return 0;
 }
 
-extern "C" int tagpu_copy_kmers(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint8_t *mask)
+// k-mers + masks out of a table on the device (~key stored, 0 = empty slot)
+static int copy_table_entries(tagpu_ctx *ctx, const void *d_keys, const void *d_mask, uint32_t n_slots, uint64_t *hi, uint64_t *lo, uint8_t *mask)
 {
-	if (!ctx->have_graph) return fail(ctx, "no graph result to copy");
-	if (ctx->contracted) return fail(ctx, "the k-mer table of a contracted build holds the path-end k-mers only (tagpu_set_contract(ctx, 0) for the full table)");
-	CU(cudaSetDevice(ctx->device));
-	const uint32_t n_slots = ctx->kt_slots;
 	std::vector<uint8_t> m(n_slots);
 	std::vector<uint64_t> keys((size_t)n_slots * ctx->W);
-	CU(cudaMemcpyAsync(m.data(), ctx->kt_mask.p, n_slots, cudaMemcpyDeviceToHost, ctx->stream));
-	CU(cudaMemcpyAsync(keys.data(), ctx->kt_keys.p, (size_t)n_slots * 8 * ctx->W, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(m.data(), d_mask, n_slots, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(keys.data(), d_keys, (size_t)n_slots * 8 * ctx->W, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	uint64_t o = 0;
 	for (uint32_t s = 0; s < n_slots; ++s) {
@@ -1110,6 +1116,48 @@ extern "C" int tagpu_copy_kmers(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint
 	}
 	if (o != ctx->st.n_kmers) return fail(ctx, "k-mer table holds %llu entries, counted %llu", (unsigned long long)o, (unsigned long long)ctx->st.n_kmers);
 	return 0;
+}
+
+// The two-level graph stage keeps only the path-end k-mers in its table; when a caller asks for the full k-mer table it
+// is built here, on demand, from the solid list (same kernel as the one-level stage) in scratch memory.
+template <int W>
+static int copy_kmers_full_table(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint8_t *mask)
+{
+	const uint64_t n_solid = ctx->st.n_solid, slots64 = (ctx->st.n_kmers * 5) / 2 + 1024;
+	if (slots64 > (1ull << 30)) return fail(ctx, "k-mer table would need %llu slots (> 2^30)", (unsigned long long)slots64);
+	const uint32_t n_slots = (uint32_t)slots64;
+	const size_t mask_bytes = ((size_t)n_slots + 3) / 4 * 4;
+	Buf keys, msk, vl, vr, c;
+	int rc = -1;
+	if (!(ensure(ctx, keys, (size_t)n_slots * sizeof(Key<W>)) || ensure(ctx, msk, mask_bytes) || ensure(ctx, vl, (n_solid + 1) * 4) ||
+	      ensure(ctx, vr, (n_solid + 1) * 4) || ensure(ctx, c, CTR_TOTAL * sizeof(unsigned long long)))) {
+		KTab<W> t;
+		t.keys = (Key<W> *)keys.p;
+		t.mask32 = (uint32_t *)msk.p;
+		t.n_slots = n_slots;
+		rc = 0;
+		if (cudaMemsetAsync(t.keys, 0, (size_t)n_slots * sizeof(Key<W>), ctx->stream) != cudaSuccess ||
+		    cudaMemsetAsync(t.mask32, 0, mask_bytes, ctx->stream) != cudaSuccess ||
+		    cudaMemsetAsync(c.p, 0, CTR_TOTAL * sizeof(unsigned long long), ctx->stream) != cudaSuccess)
+			rc = fail(ctx, "cudaMemsetAsync failed");
+		if (!rc && n_solid) {
+			k_insert_kmers<W><<<(unsigned)((n_solid + 255) / 256), 256, 0, ctx->stream>>>((const Key<W> *)ctx->cur_solid_key, 0ull, n_solid, 0, ctx->k, t,
+												   (uint32_t *)vl.p, (uint32_t *)vr.p, (unsigned long long *)c.p);
+			if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, "k_insert_kmers launch failed");
+		}
+		if (!rc) rc = copy_table_entries(ctx, keys.p, msk.p, n_slots, hi, lo, mask);
+	}
+	Buf *tmp[] = { &keys, &msk, &vl, &vr, &c };
+	for (Buf *b : tmp) if (b->p) cudaFree(b->p);
+	return rc;
+}
+
+extern "C" int tagpu_copy_kmers(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint8_t *mask)
+{
+	if (!ctx->have_graph) return fail(ctx, "no graph result to copy");
+	CU(cudaSetDevice(ctx->device));
+	if (ctx->contracted) return ctx->W == 1 ? copy_kmers_full_table<1>(ctx, hi, lo, mask) : copy_kmers_full_table<2>(ctx, hi, lo, mask);
+	return copy_table_entries(ctx, ctx->kt_keys.p, ctx->kt_mask.p, ctx->kt_slots, hi, lo, mask);
 }
 
 extern "C" int tagpu_copy_graph(tagpu_ctx *ctx, struct tagpu_flat_graph *h)
