@@ -311,13 +311,13 @@ def main():
 
     def step_device():
         if world > 1:
-            return dt.build(d_stream.data_ptr(), n_stream)
+            return dt.build(d_stream.data_ptr(), n_stream, gather_solid=False)
         return t.build_device(d_stream.data_ptr(), n_stream, k)
 
     def step_host():
         # end to end: this rank's reads start in pinned HOST memory; H2D copy, build, stats back to the host
         if world > 1:
-            return dt.build(h_stream.data_ptr(), n_stream, host=True)
+            return dt.build(h_stream.data_ptr(), n_stream, host=True, gather_solid=False)
         return t.build_host((h_stream.data_ptr(), n_stream), k)
 
     def barrier():

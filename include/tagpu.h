@@ -136,7 +136,13 @@ int tagpu_write_kmc_db(tagpu_ctx *ctx, const char *working_dir);   /* KMC_<K>_co
  *           tagpu_dist_count      -> ALL-GATHER of the 4 stats values (doubles as the barrier) ->
  *                                                    (pass 2 over the buckets this rank owns; the counting kernel reads the
  *                                                     records of every rank through NVLink peer loads, overlapped with counting)
- *           tagpu_dist_graph                         (pulls all solid sets over NVLink, builds the graph on every rank)
+ *           tagpu_dist_contract   -> ALL-GATHER of the 4 path values (barrier again) ->
+ *                                                    (two-level graph stage, level 1: every rank contracts ITS solid list
+ *                                                     into unbranched paths, left in its arena)
+ *           tagpu_dist_graph_paths -> BARRIER        (pulls all paths over NVLink peer loads, global stage on every rank;
+ *                                                     the barrier keeps the next partition off regions still being read)
+ *     or    tagpu_dist_graph                         (one-level: pulls all solid sets over NVLink, builds the graph on every
+ *                                                     rank; also the fallback when a rank reports paths_out[3] == 0)
  *
  * All ranks must pass the same n_total_bytes (size of the WHOLE read stream), k and cutoff.  After tagpu_dist_graph the
  * stats / copy / write calls above describe the global result on every rank. */
@@ -148,6 +154,12 @@ int tagpu_dist_partition(tagpu_ctx *ctx, const uint8_t *d_seq_local, uint64_t n_
 int tagpu_dist_partition_host(tagpu_ctx *ctx, const uint8_t *h_seq_local, uint64_t n_local_bytes);
 int tagpu_dist_count(tagpu_ctx *ctx, uint64_t stats_out[4]);
 int tagpu_dist_graph(tagpu_ctx *ctx, const uint64_t *all_stats /* world x 4, rank order */, int with_graph);
+/* paths_out = { paths, interior words, k-mers hidden inside paths, 1 if this rank contracted (0: use tagpu_dist_graph) } */
+int tagpu_dist_contract(tagpu_ctx *ctx, uint64_t paths_out[4]);
+/* with_graph: 1 = graph only (the solid set stays sharded over its owner ranks: tagpu_copy_solid / tagpu_copy_kmers /
+ * tagpu_write_kmc_db fail); 3 = graph, and every rank also pulls the whole solid set */
+int tagpu_dist_graph_paths(tagpu_ctx *ctx, const uint64_t *all_stats /* world x 4 */, const uint64_t *all_paths /* world x 4 */,
+			   int with_graph);
 /* Teardown / re-plan: every rank calls tagpu_dist_disconnect (unmaps the peers' arenas) -> BARRIER -> tagpu_dist_close or a
  * new tagpu_dist_plan (frees its own arena, which nobody maps any more). */
 void tagpu_dist_disconnect(tagpu_ctx *ctx);

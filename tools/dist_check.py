@@ -34,33 +34,45 @@ def main():
         b, e = shard_range(stream, rank, world)
         mine = torch.from_numpy(stream[b:e].copy()).cuda()
         d.plan(stream.size, k)
-        for rep in range(2):                      # twice: the second pass exercises the re-zeroing of the cursors
-            st = d.build(mine.data_ptr(), mine.numel())
-        if rank == 0:
-            ora = _oracle.load()
-            want = ora.count(stream, k + 1)
-            hi, lo, cnt = t.solid()
-            o = np.lexsort((lo, hi))
-            good = (st["n_instances"] == want["n_instances"] and st["n_distinct"] == want["n_distinct"]
-                    and np.array_equal(hi[o], want["hi"]) and np.array_equal(lo[o], want["lo"]) and np.array_equal(cnt[o], want["count"]))
-            g = ora.graph(k, want["hi"], want["lo"], want["count"])
-            khi, klo, kmask = ora.graph_masks(g)
-            ghi, glo, gmask = t.kmers()
-            o = np.lexsort((glo, ghi))
-            good = good and np.array_equal(ghi[o], khi) and np.array_equal(glo[o], klo) and np.array_equal(gmask[o], kmask)
-            good = good and (st["n_kmers"], st["n_v"], st["n_e"], st["n_kp1_on_edge"]) == (
-                g.contents.n_kmer, g.contents.n_v, g.contents.n_e, g.contents.n_kp1_on_edge)
-            tmp = f"/tmp/dist_check_{os.getpid()}"
-            ora.save_bin(g, tmp + "_o.bin")
-            t.write_graph_bin(tmp + "_g.bin")
-            ora.free_graph(g)
-            for mode in (0, 1):
-                bo, to = _oracle.canon_text(ora, tmp + "_o.bin", mode)
-                bg, tg = _oracle.canon_text(ora, tmp + "_g.bin", mode)
-                good = good and bo == 0 and bg == 0 and to == tg
-            print(f"dist_check world={world} genome={genome} pairs={pairs} k={k}: n_inst={st['n_instances']} n_solid={st['n_solid']} "
-                  f"n_v={st['n_v']} n_e={st['n_e']} -> {'PARITY' if good else 'MISMATCH'}", flush=True)
-            ok = ok and good
+        # two-level graph stage with the solid set gathered / left sharded, then the one-level stage; each twice (the
+        # second pass exercises the re-zeroing of the cursors and the reuse of the regions the paths were parked in)
+        for mode, contract, gather in (("two-level", True, True), ("two-level, solid sharded", True, False), ("one-level", False, True)):
+            t.set_contract(contract)
+            for rep in range(2):
+                st = d.build(mine.data_ptr(), mine.numel(), gather_solid=gather)
+            if rank == 0:
+                ora = _oracle.load()
+                want = ora.count(stream, k + 1)
+                good = st["n_instances"] == want["n_instances"] and st["n_distinct"] == want["n_distinct"] and st["n_solid"] == want["hi"].size
+                g = ora.graph(k, want["hi"], want["lo"], want["count"])
+                if gather:
+                    hi, lo, cnt = t.solid()
+                    o = np.lexsort((lo, hi))
+                    good = good and np.array_equal(hi[o], want["hi"]) and np.array_equal(lo[o], want["lo"]) and np.array_equal(cnt[o], want["count"])
+                    khi, klo, kmask = ora.graph_masks(g)
+                    ghi, glo, gmask = t.kmers()
+                    o = np.lexsort((glo, ghi))
+                    good = good and np.array_equal(ghi[o], khi) and np.array_equal(glo[o], klo) and np.array_equal(gmask[o], kmask)
+                else:
+                    try:
+                        t.solid()
+                        good = False if world > 1 else good      # must refuse: the solid set is not on this rank
+                    except Exception:
+                        pass
+                good = good and (st["n_kmers"], st["n_v"], st["n_e"], st["n_kp1_on_edge"]) == (
+                    g.contents.n_kmer, g.contents.n_v, g.contents.n_e, g.contents.n_kp1_on_edge)
+                tmp = f"/tmp/dist_check_{os.getpid()}"
+                ora.save_bin(g, tmp + "_o.bin")
+                t.write_graph_bin(tmp + "_g.bin")
+                ora.free_graph(g)
+                for m in (0, 1):
+                    bo, to = _oracle.canon_text(ora, tmp + "_o.bin", m)
+                    bg, tg = _oracle.canon_text(ora, tmp + "_g.bin", m)
+                    good = good and bo == 0 and bg == 0 and to == tg
+                print(f"dist_check world={world} genome={genome} pairs={pairs} k={k} [{mode}]: n_inst={st['n_instances']} n_solid={st['n_solid']} "
+                      f"n_v={st['n_v']} n_e={st['n_e']} -> {'PARITY' if good else 'MISMATCH'}", flush=True)
+                ok = ok and good
+        t.set_contract(True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     d.close()

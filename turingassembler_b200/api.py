@@ -172,6 +172,10 @@ def load_library() -> C.CDLL:
     lib.tagpu_dist_count.argtypes = [vp, C.POINTER(u64)]
     lib.tagpu_dist_graph.restype = i32
     lib.tagpu_dist_graph.argtypes = [vp, C.POINTER(u64), i32]
+    lib.tagpu_dist_contract.restype = i32
+    lib.tagpu_dist_contract.argtypes = [vp, C.POINTER(u64)]
+    lib.tagpu_dist_graph_paths.restype = i32
+    lib.tagpu_dist_graph_paths.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), i32]
     lib.tagpu_dist_close.argtypes = [vp]
     lib.tagpu_dist_disconnect.argtypes = [vp]
     lib.tagpu_dist_shard_range.restype = None
@@ -300,6 +304,18 @@ class Tagpu:
     def dist_graph(self, all_stats: Sequence[int], with_graph: bool = True):
         arr = (C.c_uint64 * len(all_stats))(*all_stats)
         self._check(self.lib.tagpu_dist_graph(self.ctx, arr, int(with_graph)))
+        return self.stats()
+
+    def dist_contract(self):
+        """Level 1 of the two-level graph stage on this rank's solid set -> [paths, interior words, hidden k-mers, ok]."""
+        out = (C.c_uint64 * 4)()
+        self._check(self.lib.tagpu_dist_contract(self.ctx, out))
+        return list(out)
+
+    def dist_graph_paths(self, all_stats: Sequence[int], all_paths: Sequence[int], gather_solid: bool = False):
+        a = (C.c_uint64 * len(all_stats))(*all_stats)
+        b = (C.c_uint64 * len(all_paths))(*all_paths)
+        self._check(self.lib.tagpu_dist_graph_paths(self.ctx, a, b, 3 if gather_solid else 1))
         return self.stats()
 
     def dist_disconnect(self):

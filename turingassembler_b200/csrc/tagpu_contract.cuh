@@ -275,6 +275,33 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 #endif
 }
 
+// ---------------------------------------------------------------- multi-GPU: paths of every rank into one dense store
+// Every rank contracts its own solid list into a PathStore inside its arena; this kernel pulls all of them over NVLink
+// peer loads (coalesced, grid-strided) into this rank's dense arrays and rebases the interior-word offsets on the way.
+template <int W> struct PathPeers {
+	PathStore<W> src[TAGPU_MAX_RANKS];                       // as mapped on this rank
+	unsigned long long n_paths[TAGPU_MAX_RANKS], n_words[TAGPU_MAX_RANKS], p0[TAGPU_MAX_RANKS], w0[TAGPU_MAX_RANKS];
+	int world;
+};
+
+template <int W>
+__global__ void __launch_bounds__(256) k_gather_paths(const __grid_constant__ PathPeers<W> pp, PathStore<W> dst)
+{
+	const unsigned long long t0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (int r = 0; r < pp.world; ++r) {
+		const PathStore<W> &s = pp.src[r];
+		const unsigned long long p0 = pp.p0[r], w0 = pp.w0[r];
+		for (unsigned long long i = t0; i < pp.n_paths[r]; i += stride) {
+			dst.first[p0 + i] = s.first[i];
+			dst.last[p0 + i] = s.last[i];
+			dst.n[p0 + i] = s.n[i];
+			dst.cnt[p0 + i] = s.cnt[i];
+			dst.off[p0 + i] = s.off[i] + w0;
+		}
+		for (unsigned long long i = t0; i < pp.n_words[r]; i += stride) dst.interior[w0 + i] = s.interior[i];
+	}
+}
+
 // base i (0 .. k + n - 1) of a path: the first k + 1 from its first (k+1)-mer, the rest from the interior words
 template <int W>
 TAGPU_DI uint32_t tagpu_path_base(const PathStore<W> &ps, unsigned long long p, const Key<W> &xf, int k, uint32_t i)

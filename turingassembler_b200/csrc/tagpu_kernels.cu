@@ -36,6 +36,7 @@ struct tagpu_ctx {
 	int ci = 2, skip_counts = 0;
 	int contract = 1;                  // two-level graph stage (tagpu_contract.cuh)
 	bool contracted = false;           // the last graph was built that way (hidden k-mers are not in the table)
+	bool solid_sharded = false;        // multi-GPU build that left the solid set with its owners (only the paths travelled)
 	int log2_buckets = 0;              // of the last count stage
 	int k = 0, K = 0, W = 0;
 	char err[512] = { 0 };
@@ -163,6 +164,8 @@ static int ensure_slack(tagpu_ctx *ctx, Buf &b, size_t bytes)
 	if (bytes <= b.cap && b.p) return 0;
 	return ensure(ctx, b, bytes + bytes / 8 + 65536);
 }
+
+static int ensure_exact(tagpu_ctx *ctx, Buf &b, size_t bytes) { return ensure(ctx, b, bytes); }
 
 static uint64_t pow2_at_least(uint64_t x)
 {
@@ -422,6 +425,7 @@ static int count_owned(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &
 	ctx->st.n_solid = ctx->h_ctr[CTR_SOLID];
 	ctx->st.sum_solid = ctx->h_ctr[CTR_SUM_SOLID];
 	ctx->n_blocks = ctx->h_ctr[CTR_BLOCKS];
+	ctx->log2_buckets = cfg.log2_buckets;
 #ifdef TAGPU_TIMING
 	{
 		const double tot = (double)(ctx->h_ctr[CTR_JUMP_FLAGS + 48] + ctx->h_ctr[CTR_JUMP_FLAGS + 49] + ctx->h_ctr[CTR_JUMP_FLAGS + 50] + ctx->h_ctr[CTR_JUMP_FLAGS + 51] +
@@ -448,7 +452,6 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 	const PartCfg cfg = plan_cfg(n, ctx->K, 1, BC::GROUP_TARGET);
 	const uint32_t n_buckets = 1u << cfg.log2_buckets;
 	ctx->count_stream_bytes = n;
-	ctx->log2_buckets = cfg.log2_buckets;
 	if (ensure(ctx, ctx->regions, (size_t)n_buckets * cfg.cap_records * sizeof(SkRec<W>)) || ensure(ctx, ctx->cursor, (size_t)n_buckets * 8) ||
 	    ensure(ctx, ctx->overflow, (size_t)cfg.overflow_cap * sizeof(SkRec<W>)) ||
 	    ensure(ctx, ctx->overflow_bucket, (size_t)cfg.overflow_cap * 4) || ensure(ctx, ctx->ext_off, (size_t)(n_buckets + 1) * 4) ||
@@ -601,24 +604,57 @@ static int graph_stage(tagpu_ctx *ctx)
 }
 
 // ------------------------------------------------------------------------------------------------ graph stage, two-level (paths)
+// A PathStore for up to cap paths laid out in one flat buffer (the multi-GPU build keeps it in the arena, where the
+// other ranks read it): first | last | cnt | off | n | interior, every part 256-byte aligned.
 template <int W>
-static int graph_stage_paths(tagpu_ctx *ctx)
+static size_t path_store_bytes(uint64_t cap)
 {
-	const int k = ctx->k;
-	const uint64_t n_solid = ctx->st.n_solid;
-	unsigned long long *ctr = ctx->d_ctr;
-	// ---- level 1: contraction inside the blocks of the solid list -> dense path arrays (at most one path per solid entry)
+	auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+	return 2 * al((cap + 1) * sizeof(Key<W>)) + 2 * al((cap + 1) * 8) + al((cap + 1) * 4) + al((cap + 16) * 4);
+}
+
+template <int W>
+static PathStore<W> path_store_at(char *base, uint64_t cap)
+{
+	auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
 	PathStore<W> ps;
-	ps.cap_paths = n_solid + 1;
-	ps.cap_words = n_solid + 16;
-	const uint32_t n_blocks = (uint32_t)ctx->n_blocks;
-	if (ensure(ctx, ctx->d_first, ps.cap_paths * sizeof(Key<W>)) || ensure(ctx, ctx->d_last, ps.cap_paths * sizeof(Key<W>)) ||
-	    ensure(ctx, ctx->d_n, ps.cap_paths * 4) || ensure(ctx, ctx->d_cnt, ps.cap_paths * 8) || ensure(ctx, ctx->d_off, ps.cap_paths * 8) ||
-	    ensure(ctx, ctx->d_int, ps.cap_words * 4))
+	char *p = base;
+	ps.first = (Key<W> *)p; p += al((cap + 1) * sizeof(Key<W>));
+	ps.last = (Key<W> *)p; p += al((cap + 1) * sizeof(Key<W>));
+	ps.cnt = (unsigned long long *)p; p += al((cap + 1) * 8);
+	ps.off = (unsigned long long *)p; p += al((cap + 1) * 8);
+	ps.n = (uint32_t *)p; p += al((cap + 1) * 4);
+	ps.interior = (uint32_t *)p;
+	ps.cap_paths = cap + 1;
+	ps.cap_words = cap + 16;
+	return ps;
+}
+
+// dense path arrays in this context's own buffers
+template <int W>
+static int path_store_own(tagpu_ctx *ctx, uint64_t cap, PathStore<W> *out, bool slack)
+{
+	PathStore<W> ps;
+	ps.cap_paths = cap + 1;
+	ps.cap_words = cap + 16;
+	int (*grow)(tagpu_ctx *, Buf &, size_t) = slack ? ensure_slack : ensure_exact;
+	if (grow(ctx, ctx->d_first, ps.cap_paths * sizeof(Key<W>)) || grow(ctx, ctx->d_last, ps.cap_paths * sizeof(Key<W>)) ||
+	    grow(ctx, ctx->d_n, ps.cap_paths * 4) || grow(ctx, ctx->d_cnt, ps.cap_paths * 8) || grow(ctx, ctx->d_off, ps.cap_paths * 8) ||
+	    grow(ctx, ctx->d_int, ps.cap_words * 4))
 		return -1;
 	ps.first = (Key<W> *)ctx->d_first.p; ps.last = (Key<W> *)ctx->d_last.p; ps.n = (uint32_t *)ctx->d_n.p;
 	ps.cnt = (unsigned long long *)ctx->d_cnt.p; ps.off = (unsigned long long *)ctx->d_off.p; ps.interior = (uint32_t *)ctx->d_int.p;
-	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctr + CTR_SPARE1, 0, 8, ctx->stream)); }
+	*out = ps;
+	return 0;
+}
+
+// ---- level 1: contraction inside the blocks of the local solid list -> dense paths in ps (at most one per solid entry).
+// Leaves the counters in ctx->h_ctr: CTR_PATHS, CTR_PATH_WORDS, and CTR_KMERS = the k-mers hidden inside the paths.
+template <int W>
+static int contract_local(tagpu_ctx *ctx, const PathStore<W> &ps)
+{
+	const uint32_t n_blocks = (uint32_t)ctx->n_blocks;
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->d_ctr + CTR_SPARE1, 0, 8, ctx->stream)); }
 	constexpr size_t cmax = ContractCfg<W>::MAXN;
 	constexpr size_t smem_c = cmax * sizeof(Key<W>) + 4 * cmax * sizeof(Key<W>) + cmax * 4 + 4 * cmax * 4 + 8 * cmax * 2 + 2 * cmax * 2;
 	static bool attr_done[3] = { false, false, false };
@@ -628,10 +664,33 @@ static int graph_stage_paths(tagpu_ctx *ctx)
 	}
 	if (n_blocks)
 		LAUNCH_SMEM(k_contract<W>, (W == 1 ? 5 : 7) * ctx->n_sm, TAGPU_CONTRACT_THREADS, smem_c, (const SolidBlock *)ctx->blocks.p, n_blocks,
-			    (const Key<W> *)ctx->cur_solid_key, (const uint32_t *)ctx->cur_solid_cnt, k, ctx->log2_buckets, 1, ps, ctr);
+			    (const Key<W> *)ctx->cur_solid_key, (const uint32_t *)ctx->cur_solid_cnt, ctx->k, ctx->log2_buckets, 1, ps, ctx->d_ctr);
 	if (read_counters(ctx)) return -1;
-	const uint64_t n_paths = ctx->h_ctr[CTR_PATHS];
-	if (n_paths > n_solid) return fail(ctx, "contraction produced more paths (%llu) than solid (k+1)-mers", (unsigned long long)n_paths);
+	if (ctx->h_ctr[CTR_PATHS] >= ps.cap_paths || ctx->h_ctr[CTR_PATH_WORDS] >= ps.cap_words)
+		return fail(ctx, "contraction produced more paths (%llu, %llu words) than there is room for", (unsigned long long)ctx->h_ctr[CTR_PATHS],
+			    (unsigned long long)ctx->h_ctr[CTR_PATH_WORDS]);
+	return 0;
+}
+
+// ---- level 2: the global stage on n_paths paths.  hidden_elsewhere: k-mers hidden inside the paths of OTHER ranks
+// (this device's CTR_KMERS already holds the ones of its own contraction).
+template <int W>
+static int graph_stage_global(tagpu_ctx *ctx, const PathStore<W> &ps, uint64_t n_paths, uint64_t hidden_elsewhere);
+
+template <int W>
+static int graph_stage_paths(tagpu_ctx *ctx)
+{
+	PathStore<W> ps;
+	if (path_store_own<W>(ctx, ctx->st.n_solid, &ps, false) || contract_local<W>(ctx, ps)) return -1;
+	return graph_stage_global<W>(ctx, ps, ctx->h_ctr[CTR_PATHS], 0);
+}
+
+template <int W>
+static int graph_stage_global(tagpu_ctx *ctx, const PathStore<W> &ps, uint64_t n_paths, uint64_t hidden_elsewhere)
+{
+	const int k = ctx->k;
+	const uint64_t n_solid = ctx->st.n_solid;
+	unsigned long long *ctr = ctx->d_ctr;
 	// ---- level 2: the global stage on the paths
 	const uint64_t slots64 = (n_paths * 5) / 2 + 1024;
 	if (slots64 > (1ull << 30)) return fail(ctx, "k-mer table would need %llu slots (> 2^30)", (unsigned long long)slots64);
@@ -656,7 +715,7 @@ static int graph_stage_paths(tagpu_ctx *ctx)
 	LAUNCH(k_classify<W>, (n_slots + 1023) / 1024, 1024, t, kind, node_slot, node_ebase, chain_slot, ctr);
 	if (read_counters(ctx)) return -1;
 	const uint64_t n_nodes = ctx->h_ctr[CTR_NODES], n_e = ctx->h_ctr[CTR_EDGES], n_chain = ctx->h_ctr[CTR_CHAIN];
-	ctx->st.n_kmers = ctx->h_ctr[CTR_KMERS];
+	ctx->st.n_kmers = ctx->h_ctr[CTR_KMERS] + hidden_elsewhere;
 	ctx->st.n_v = 2 * n_nodes;
 	ctx->st.n_e = n_e;
 	if (n_e > 0xfffffff0ull) return fail(ctx, "too many edges (%llu)", (unsigned long long)n_e);
@@ -707,6 +766,7 @@ static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool wit
 	ctx->k = K - 1;
 	ctx->W = K <= 32 ? 1 : 2;
 	ctx->have_count = ctx->have_graph = false;
+	ctx->solid_sharded = false;
 	ctx->launches = 0;
 	ctx->err[0] = 0;
 	memset(&ctx->st, 0, sizeof(ctx->st));
@@ -768,6 +828,8 @@ struct DistState {
 	char *peer[TAGPU_MAX_RANKS] = { nullptr };      // arena of every rank as mapped here (peer[rank] = arena)
 	bool connected = false;
 	Buf g_key, g_cnt;                               // solid set gathered from all ranks
+	bool have_paths = false;                        // tagpu_dist_contract left this rank's paths at the front of its regions area
+	uint64_t paths_cap = 0;                         // ... laid out for this many (= the rank's solid count)
 };
 
 static void borrow(Buf &b, void *p, size_t bytes)
@@ -902,6 +964,7 @@ static int dist_partition_impl(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_
 		return fail(ctx, "this rank's slice (%llu bytes) is larger than planned (%llu total over %d ranks)", (unsigned long long)n_local_bytes,
 			    (unsigned long long)d->n_total, d->world);
 	ctx->have_count = ctx->have_graph = false;
+	ctx->solid_sharded = false;
 	ctx->launches = 0;
 	ctx->err[0] = 0;
 	memset(&ctx->st, 0, sizeof(ctx->st));
@@ -941,6 +1004,8 @@ extern "C" int tagpu_dist_count(tagpu_ctx *ctx, uint64_t stats_out[4])
 	return 0;
 }
 
+static int dist_gather_solid(tagpu_ctx *ctx, const uint64_t *all_stats, uint64_t n_total);
+
 // all_stats: world x 4 values, the stats_out of every rank in rank order.  Pulls every rank's solid set over NVLink
 // (peer copies out of the mapped arenas), then runs the graph stage on the union.  with_graph = 0 stops after the gather.
 extern "C" int tagpu_dist_graph(tagpu_ctx *ctx, const uint64_t *all_stats, int with_graph)
@@ -951,23 +1016,9 @@ extern "C" int tagpu_dist_graph(tagpu_ctx *ctx, const uint64_t *all_stats, int w
 	uint64_t tot[4] = { 0, 0, 0, 0 };
 	for (int r = 0; r < d->world; ++r)
 		for (int j = 0; j < 4; ++j) tot[j] += all_stats[r * 4 + j];
-	const size_t key = d->W == 1 ? sizeof(Key<1>) : sizeof(Key<2>);
-	if (d->world > 1) {
-		if (ensure(ctx, d->g_key, (tot[2] + 1) * key) || ensure(ctx, d->g_cnt, (tot[2] + 1) * 4)) return -1;
-		uint64_t o = 0;
-		ProfScope ps_(ctx, "peer_gather_solid");
-		for (int r = 0; r < d->world; ++r) {
-			const uint64_t n = all_stats[r * 4 + 2];
-			if (n > d->solid_cap) return fail(ctx, "rank %d reports %llu solid (k+1)-mers, more than the planned %llu", r, (unsigned long long)n, (unsigned long long)d->solid_cap);
-			if (n) {
-				CU(cudaMemcpyAsync((char *)d->g_key.p + o * key, d->peer[r] + d->off_skey, n * key, cudaMemcpyDeviceToDevice, ctx->stream));
-				CU(cudaMemcpyAsync((char *)d->g_cnt.p + o * 4, d->peer[r] + d->off_scnt, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-			}
-			o += n;
-		}
-		ctx->cur_solid_key = d->g_key.p;
-		ctx->cur_solid_cnt = d->g_cnt.p;
-	}
+	if (d->world > 1 && dist_gather_solid(ctx, all_stats, tot[2])) return -1;
+	ctx->solid_sharded = false;
+	ctx->contracted = false;
 	ctx->st.n_instances = tot[0];
 	ctx->st.n_distinct = tot[1];
 	ctx->st.n_solid = tot[2];
@@ -979,6 +1030,117 @@ extern "C" int tagpu_dist_graph(tagpu_ctx *ctx, const uint64_t *all_stats, int w
 		CU(cudaEventRecord(ctx->ev[2], ctx->stream));
 		CU(cudaStreamSynchronize(ctx->stream));
 	}
+	CU(cudaEventElapsedTime(&ctx->st.ms_count, ctx->ev[0], ctx->ev[1]));
+	CU(cudaEventElapsedTime(&ctx->st.ms_graph, ctx->ev[1], ctx->ev[2]));
+	CU(cudaEventElapsedTime(&ctx->st.ms_total, ctx->ev[0], ctx->ev[2]));
+	ctx->st.gpu_launches = ctx->launches;
+	prof_finish(ctx);
+	return 0;
+}
+
+// ---- two-level graph stage across ranks.  After the stats all-gather (every rank has finished counting, so nobody reads
+// anybody's bucket regions any more) each rank contracts ITS OWN solid list into paths, written over the front of its
+// regions area in the arena; paths_out = { paths, interior words, hidden k-mers, 1 if it worked this way }.  The host
+// all-gathers the 4 values (that is the barrier: every rank's paths are complete), then tagpu_dist_graph_paths pulls all
+// paths over NVLink and runs the global stage on them.  If any rank reports 0 in paths_out[3], all fall back to
+// tagpu_dist_graph.  The host must put a barrier between tagpu_dist_graph_paths and the next tagpu_dist_partition
+// (which overwrites the regions the other ranks pull from).
+template <int W>
+static int dist_contract(tagpu_ctx *ctx, uint64_t paths_out[4])
+{
+	DistState *d = ctx->dist;
+	paths_out[0] = paths_out[1] = paths_out[2] = paths_out[3] = 0;
+	d->have_paths = false;
+	const uint64_t n_local = ctx->st.n_solid;
+	const size_t region_bytes = ((size_t)1 << d->cfg.log2_buckets) * d->cfg.cap_records * sizeof(SkRec<W>);
+	if (!ctx->contract || path_store_bytes<W>(n_local) > region_bytes) return 0;   // (not an error: one-level stage instead)
+	if (n_local && !ctx->n_blocks) return 0;
+	const PathStore<W> ps = path_store_at<W>(d->arena + d->off_regions, n_local);
+	if (contract_local<W>(ctx, ps)) return -1;
+	d->have_paths = true;
+	d->paths_cap = n_local;
+	paths_out[0] = ctx->h_ctr[CTR_PATHS];
+	paths_out[1] = ctx->h_ctr[CTR_PATH_WORDS];
+	paths_out[2] = ctx->h_ctr[CTR_KMERS];
+	paths_out[3] = 1;
+	return 0;
+}
+
+extern "C" int tagpu_dist_contract(tagpu_ctx *ctx, uint64_t paths_out[4])
+{
+	DistState *d = ctx->dist;
+	if (!d || !ctx->have_count) return fail(ctx, "tagpu_dist_contract before tagpu_dist_count");
+	CU(cudaSetDevice(ctx->device));
+	return d->W == 1 ? dist_contract<1>(ctx, paths_out) : dist_contract<2>(ctx, paths_out);
+}
+
+static int dist_gather_solid(tagpu_ctx *ctx, const uint64_t *all_stats, uint64_t n_total)
+{
+	DistState *d = ctx->dist;
+	const size_t key = d->W == 1 ? sizeof(Key<1>) : sizeof(Key<2>);
+	if (ensure(ctx, d->g_key, (n_total + 1) * key) || ensure(ctx, d->g_cnt, (n_total + 1) * 4)) return -1;
+	uint64_t o = 0;
+	ProfScope ps_(ctx, "peer_gather_solid");
+	for (int r = 0; r < d->world; ++r) {
+		const uint64_t n = all_stats[r * 4 + 2];
+		if (n > d->solid_cap) return fail(ctx, "rank %d reports %llu solid (k+1)-mers, more than the planned %llu", r, (unsigned long long)n, (unsigned long long)d->solid_cap);
+		if (n) {
+			CU(cudaMemcpyAsync((char *)d->g_key.p + o * key, d->peer[r] + d->off_skey, n * key, cudaMemcpyDeviceToDevice, ctx->stream));
+			CU(cudaMemcpyAsync((char *)d->g_cnt.p + o * 4, d->peer[r] + d->off_scnt, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+		}
+		o += n;
+	}
+	ctx->cur_solid_key = d->g_key.p;
+	ctx->cur_solid_cnt = d->g_cnt.p;
+	return 0;
+}
+
+template <int W>
+static int dist_graph_paths(tagpu_ctx *ctx, const uint64_t *all_stats, const uint64_t *all_paths)
+{
+	DistState *d = ctx->dist;
+	PathPeers<W> pp;
+	memset(&pp, 0, sizeof(pp));
+	pp.world = d->world;
+	uint64_t n_paths = 0, n_words = 0, hidden_elsewhere = 0;
+	for (int r = 0; r < d->world; ++r) {
+		pp.src[r] = path_store_at<W>(d->peer[r] + d->off_regions, all_stats[r * 4 + 2]);
+		pp.n_paths[r] = all_paths[r * 4]; pp.n_words[r] = all_paths[r * 4 + 1];
+		pp.p0[r] = n_paths; pp.w0[r] = n_words;
+		n_paths += pp.n_paths[r]; n_words += pp.n_words[r];
+		if (r != d->rank) hidden_elsewhere += all_paths[r * 4 + 2];
+	}
+	PathStore<W> ps;
+	if (path_store_own<W>(ctx, n_paths > n_words ? n_paths : n_words, &ps, true)) return -1;
+	if (d->world == 1) ps = pp.src[0];                                  // nothing to pull
+	else if (n_paths) LAUNCH(k_gather_paths<W>, 4 * ctx->n_sm, 256, pp, ps);
+	return graph_stage_global<W>(ctx, ps, n_paths, hidden_elsewhere);
+}
+
+// all_paths: world x 4, the paths_out of every rank in rank order.  with_graph: 1 = graph; 3 = graph, and the solid sets of
+// all ranks gathered on every rank as well (for the tagpu_copy_solid / tagpu_copy_kmers / tagpu_write_kmc_db calls).
+extern "C" int tagpu_dist_graph_paths(tagpu_ctx *ctx, const uint64_t *all_stats, const uint64_t *all_paths, int with_graph)
+{
+	DistState *d = ctx->dist;
+	if (!d || !ctx->have_count) return fail(ctx, "tagpu_dist_graph_paths before tagpu_dist_count");
+	if (!d->have_paths) return fail(ctx, "tagpu_dist_graph_paths before tagpu_dist_contract");
+	CU(cudaSetDevice(ctx->device));
+	uint64_t tot[4] = { 0, 0, 0, 0 };
+	for (int r = 0; r < d->world; ++r) {
+		if (!all_paths[r * 4 + 3]) return fail(ctx, "rank %d did not contract its solid set: every rank has to call tagpu_dist_graph instead", r);
+		for (int j = 0; j < 4; ++j) tot[j] += all_stats[r * 4 + j];
+	}
+	ctx->solid_sharded = d->world > 1;
+	if ((with_graph & 2) && d->world > 1) {
+		if (dist_gather_solid(ctx, all_stats, tot[2])) return -1;
+		ctx->solid_sharded = false;
+	}
+	ctx->st.n_instances = tot[0];
+	ctx->st.n_distinct = tot[1];
+	ctx->st.n_solid = tot[2];
+	ctx->st.sum_solid = tot[3];
+	const int rc = d->W == 1 ? dist_graph_paths<1>(ctx, all_stats, all_paths) : dist_graph_paths<2>(ctx, all_stats, all_paths);
+	if (rc) return rc;
 	CU(cudaEventElapsedTime(&ctx->st.ms_count, ctx->ev[0], ctx->ev[1]));
 	CU(cudaEventElapsedTime(&ctx->st.ms_graph, ctx->ev[1], ctx->ev[2]));
 	CU(cudaEventElapsedTime(&ctx->st.ms_total, ctx->ev[0], ctx->ev[2]));
@@ -1079,6 +1241,8 @@ extern "C" int tagpu_get_stats(tagpu_ctx *ctx, struct tagpu_stats *out)
 extern "C" int tagpu_copy_solid(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint32_t *count)
 {
 	if (!ctx->have_count) return fail(ctx, "no count result to copy");
+	if (ctx->solid_sharded)
+		return fail(ctx, "the solid set of this multi-GPU build stayed with its owner ranks (tagpu_dist_graph_paths with_graph = 3 gathers it)");
 	CU(cudaSetDevice(ctx->device));
 	const uint64_t n = ctx->st.n_solid;
 	if (!n) return 0;
@@ -1156,6 +1320,8 @@ extern "C" int tagpu_copy_kmers(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint
 {
 	if (!ctx->have_graph) return fail(ctx, "no graph result to copy");
 	CU(cudaSetDevice(ctx->device));
+	if (ctx->contracted && ctx->solid_sharded)
+		return fail(ctx, "the solid set of this multi-GPU build stayed with its owner ranks (tagpu_dist_graph_paths with_graph = 3 gathers it)");
 	if (ctx->contracted) return ctx->W == 1 ? copy_kmers_full_table<1>(ctx, hi, lo, mask) : copy_kmers_full_table<2>(ctx, hi, lo, mask);
 	return copy_table_entries(ctx, ctx->kt_keys.p, ctx->kt_mask.p, ctx->kt_slots, hi, lo, mask);
 }

@@ -1,13 +1,14 @@
 """Multi-GPU orchestration of the k-mer stage: one process per GPU (include/tagpu.h "multi-GPU").
 
 This module is host plumbing only.  torch.distributed supplies rendezvous, the barriers between phases and the two tiny
-host-side exchanges (IPC handles once, 4 stats values per step); the data path — super-k-mer records travelling to the GPU
-that owns their bucket, and the solid sets travelling back — is done by libtagpu.so itself over NVLink peer memory
-(peer loads inside k_count_buckets, peer copies in tagpu_dist_graph).  The reference has no counterpart: it is a single
+host-side exchanges (IPC handles once, 4 + 4 values per step); the data path — super-k-mer records travelling to the GPU
+that owns their bucket, and the contracted paths (or the solid sets) travelling back — is done by libtagpu.so itself over
+NVLink peer memory (peer loads inside k_count_buckets and k_gather_paths, peer copies in tagpu_dist_graph).  The reference has no counterpart: it is a single
 process (pthreads only).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -37,6 +38,7 @@ class DistTagpu:
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._stats = torch.zeros(4, dtype=torch.int64, device=self.dev)
         self._all = torch.zeros(4 * world, dtype=torch.int64, device=self.dev)
+        self._dirty = False           # the other ranks may still be pulling paths out of this rank's regions
 
     def plan(self, n_total_bytes: int, k: int):
         """Same n_total_bytes / k on every rank.  Allocates this rank's arena and maps everybody else's."""
@@ -54,10 +56,14 @@ class DistTagpu:
         self.dist.all_reduce(self._flag, group=self.group)
         self._sync()
 
-    def build(self, ptr: int, n_local_bytes: int, with_graph: bool = True, host: bool = False) -> dict:
+    def build(self, ptr: int, n_local_bytes: int, with_graph: bool = True, host: bool = False, gather_solid: bool = True) -> dict:
         """One pass of the hot path over this rank's slice of the reads (device address, or pinned host address with
-        host=True); returns the GLOBAL stats on every rank."""
+        host=True); returns the GLOBAL stats on every rank.  gather_solid=False leaves the solid (k+1)-mers sharded over
+        their owner ranks when the two-level graph stage runs (only the contracted paths travel)."""
         t = self.t
+        if self._dirty:
+            self.barrier()
+            self._dirty = False
         if host:
             t.dist_partition_host(ptr, n_local_bytes)
         else:
@@ -65,6 +71,14 @@ class DistTagpu:
         self.barrier()
         local = t.dist_count()
         all_stats = gather_stats(self.dist, self._stats, self._all, local, self.group)
+        if with_graph and t.contract:
+            # level 1 on every rank's own solid set; the all-gather of the 4 values is the barrier before the pull
+            all_paths = gather_stats(self.dist, self._stats, self._all, t.dist_contract(), self.group)
+            if os.environ.get("TAGPU_DIST_DEBUG") and self.rank == 0:
+                print("tagpu dist: stats", all_stats, "paths", all_paths, flush=True)
+            if all(all_paths[4 * r + 3] for r in range(self.world)):
+                self._dirty = True
+                return t.dist_graph_paths(all_stats, all_paths, gather_solid)
         return t.dist_graph(all_stats, with_graph)
 
     def _sync(self):
@@ -72,6 +86,7 @@ class DistTagpu:
             self.torch.cuda.current_stream().synchronize()
 
     def close(self):
+        self._dirty = False
         self.t.dist_disconnect()
         self.barrier()
         self.t.dist_close()
