@@ -26,6 +26,8 @@ WORKLOADS = {
     "C2": dict(genome_len=4_641_652, n_pairs=2_000_000, k=45, seed=1),
     "C1": dict(genome_len=4_641_652, n_pairs=2_000_000, k=31, seed=1),
     "small": dict(genome_len=400_000, n_pairs=150_000, k=45, seed=1),
+    # C4's coverage (42x) and repeat density on a genome that fits one GPU: developer runs of the C4 regime
+    "C4s": dict(genome_len=25_000_000, n_pairs=3_500_000, k=45, seed=4, n_repeats=2_000),
     # BASELINE.json configs[2]: metagenomic mock community, ~20 M pairs, uneven coverage, k0 = 45 (multi-GPU sized: the
     # 6 GB read stream needs >= 2 B200s with today's region sizing)
     "C3": dict(n_genomes=20, n_pairs=20_000_000, k=45, seed=3, genome_len=90_000_000),

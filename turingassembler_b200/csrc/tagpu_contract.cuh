@@ -18,10 +18,21 @@
 #include "tagpu_count.cuh"
 #include "tagpu_graph.cuh"
 
-// (k+1)-mers of a block that k_contract handles (larger blocks stay single): sized so that ~30-40 KB of shared memory per
-// CTA keep 5-7 CTAs on an SM
-template <int W> struct ContractCfg { static constexpr int MAXN = W == 1 ? 512 : 256; };
-constexpr int TAGPU_CONTRACT_THREADS = 128;
+// (k+1)-mers of a block that k_contract handles, in three size classes with a launch each (occupancy falls with the
+// shared memory a block needs, so every block runs in the smallest class that holds it).  SMALL: ~30-40 KB per CTA keep
+// 5-7 CTAs of 128 threads on an SM; that covers nearly all blocks of a deep-coverage read set (a group of ~7700 windows
+// holds ~130 solid (k+1)-mers at 130x).  MEDIUM / LARGE: up to 512 (W = 2 only) / 1024 entries (shallow coverage: a larger
+// share of the windows is distinct and solid).  Still larger blocks, and blocks the count stage had to split by hash
+// class, stay uncontracted (every (k+1)-mer a path of its own).
+template <int W> struct ContractCfg {
+	static constexpr int MAXN_SMALL = W == 1 ? 512 : 256, T_SMALL = 128;
+	static constexpr int MAXN_MEDIUM = 512, T_MEDIUM = 256;            // (W = 1: same size as SMALL, launch skipped)
+	static constexpr int MAXN_LARGE = 1024, T_LARGE = 512;
+};
+template <int W, int MAXN> constexpr size_t tagpu_contract_smem()
+{
+	return (size_t)MAXN * sizeof(Key<W>) + 4 * (size_t)MAXN * sizeof(Key<W>) + (size_t)MAXN * 4 + 4 * (size_t)MAXN * 4 + 8 * (size_t)MAXN * 2 + 2 * (size_t)MAXN * 2;
+}
 constexpr uint32_t TAGPU_OE_END = 0xffffu;
 
 template <int W> struct PathStore {
@@ -86,13 +97,17 @@ TAGPU_DI bool tagpu_kmer_is_local(const Key<W> &z, int k, int log2_buckets, uint
 // Output: dense path arrays.  A block first counts its paths and interior words (shared-memory bump counters give every
 // path its place inside the block), reserves the range for all of them with one atomic per global counter
 // (ctr[CTR_PATHS], ctr[CTR_PATH_WORDS]), then writes.  The order of the paths in the arrays is therefore arbitrary.
-template <int W>
-__global__ void __launch_bounds__(TAGPU_CONTRACT_THREADS)
-k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W> *__restrict__ solid, const uint32_t *__restrict__ solid_cnt,
-	   int k, int log2_buckets, int enable, PathStore<W> ps, unsigned long long *ctr)
+// A launch works through a list of block ids (src; nullptr = the whole directory), takes the contractible blocks of up to
+// MAXN entries and appends the ids of all others to dst[] (counts in ctr[src_ctr] / ctr[dst_ctr]) for the next launch;
+// the last launch (dst == nullptr) also takes the uncontractible ones (copied out as single-entry paths).
+template <int W, int MAXN, int T>
+__global__ void __launch_bounds__(T)
+k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Key<W> *__restrict__ solid, const uint32_t *__restrict__ solid_cnt,
+	   int k, int log2_buckets, const uint32_t *__restrict__ src, int src_ctr, uint32_t *__restrict__ dst, int dst_ctr, PathStore<W> ps,
+	   unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
-	constexpr int MAXN = ContractCfg<W>::MAXN, TS_MAX = 4 * MAXN, T = TAGPU_CONTRACT_THREADS, R = MAXN / T;
+	constexpr int TS_MAX = 4 * MAXN, R = MAXN / T;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Key<W> *e_key = reinterpret_cast<Key<W> *>(smem_raw);               // [MAXN]
 	Key<W> *t_key = e_key + MAXN;                                       // [TS_MAX] canonical k-mers, ~key (0 = empty)
@@ -105,6 +120,7 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 	const uint32_t tid = threadIdx.x;
 	const int K = k + 1;
 	const Key<W> kmask = KO::mask(k);
+	const uint32_t n_blocks = src ? (uint32_t)ctr[src_ctr] : n_directory;   // (the launch before has finished that list)
 	uint32_t next_block = 0;                                            // thread 0: id requested one block ahead
 	if (tid == 0) next_block = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);
 #ifdef TAGPU_TIMING
@@ -122,11 +138,15 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_blocks, const Key<W
 			s_words = 0; s_paths = 0; s_hidden = 0; s_cand = 0;
 		}
 		__syncthreads();
-		const uint32_t blk = s_block;
-		if (blk >= n_blocks) break;
+		if (s_block >= n_blocks) break;
+		const uint32_t blk = src ? src[s_block] : s_block;
 		const SolidBlock sb = blocks[blk];
 		const uint32_t n = sb.n;
-		if (!enable || sb.flags || n > (uint32_t)MAXN) {
+		if (dst && (sb.flags || n > (uint32_t)MAXN)) {                   // for the next launch
+			if (tid == 0) dst[atomicAdd(ctr + dst_ctr, 1ull)] = blk;
+			continue;
+		}
+		if (sb.flags || n > (uint32_t)MAXN) {
 			// not contractible: every (k+1)-mer is a path of its own
 			if (tid == 0) s_pbase = atomicAdd(ctr + CTR_PATHS, (unsigned long long)n);
 			__syncthreads();

@@ -22,7 +22,7 @@ constexpr uint32_t TAGPU_CHAIN = 0x80000000u;   // kind[] entry: chain k-mer (lo
 enum {
 	CTR_INSTANCES = 0, CTR_DISTINCT, CTR_SOLID, CTR_KMERS, CTR_NODES, CTR_EDGES, CTR_SEQ_WORDS,
 	CTR_KP1_ON_EDGE, CTR_ERROR, CTR_SUM_SOLID, CTR_SPARE0, CTR_SPARE1, CTR_CHAIN, CTR_JUMP_ROUNDS, CTR_GROUPS,
-	CTR_BLOCKS, CTR_PATHS, CTR_PATH_WORDS,
+	CTR_BLOCKS, CTR_PATHS, CTR_PATH_WORDS, CTR_SPARE2, CTR_SPARE3,
 	CTR_JUMP_FLAGS /* + 64 */, CTR_TOTAL = CTR_JUMP_FLAGS + 64
 };
 
