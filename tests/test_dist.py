@@ -119,6 +119,94 @@ def test_shard_range_covers_stream_once():
         assert cuts[0][0] == 0 and cuts[-1][1] == n and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
 
 
+class _FakeTagpu:
+    """Records the tagpu_dist_* phases DistTagpu drives (no GPU): the protocol of include/tagpu.h "multi-GPU"."""
+
+    def __init__(self, rank, contract, refuse_rank):
+        self.rank, self.contract, self.refuse_rank, self.calls = rank, contract, refuse_rank, []
+
+    def dist_disconnect(self):
+        self.calls.append("disconnect")
+
+    def dist_plan(self, rank, world, n_total, k):
+        self.calls.append("plan")
+        return bytes([rank]) * 64
+
+    def dist_connect(self, handles):
+        assert handles == [bytes([r]) * 64 for r in range(len(handles))]
+        self.calls.append("connect")
+
+    def dist_partition(self, ptr, n):
+        self.calls.append("partition")
+
+    def dist_count(self):
+        self.calls.append("count")
+        return [100 + self.rank, 50 + self.rank, 10 + self.rank, 40 + self.rank]
+
+    def dist_contract(self):
+        self.calls.append("contract")
+        return [3 + self.rank, 2, 7, 0 if self.rank == self.refuse_rank else 1]
+
+    def dist_graph_paths(self, all_stats, all_paths, gather_solid):
+        self.calls.append(("graph_paths", tuple(all_stats), tuple(all_paths), gather_solid))
+        return {"n_solid": sum(all_stats[2::4])}
+
+    def dist_graph(self, all_stats, with_graph):
+        self.calls.append(("graph", tuple(all_stats), with_graph))
+        return {"n_solid": sum(all_stats[2::4])}
+
+    def dist_close(self):
+        self.calls.append("close")
+
+
+def _protocol_worker(rank, world, port, out_q):
+    import torch.distributed as dist
+    from turingassembler_b200.dist import DistTagpu
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    logs = {}
+    for name, contract, refuse in (("two_level", True, -1), ("refused", True, 1), ("one_level", False, -1)):
+        t = _FakeTagpu(rank, contract, refuse)
+        d = DistTagpu(t, rank, world)
+        d.plan(1000, 31)
+        st1 = d.build(0, 10, gather_solid=False)
+        st2 = d.build(0, 10)
+        d.close()
+        assert st1["n_solid"] == st2["n_solid"] == sum(10 + r for r in range(world))
+        logs[name] = t.calls
+    out_q.put((rank, logs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_phase_protocol_gloo():
+    """Host-side phase order of one multi-GPU build on 2 gloo ranks: the two-level graph stage (contract -> all-gather ->
+    pull paths), its collective fallback when any rank could not contract, and the one-level stage."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_protocol_worker, args=(r, world, 29671, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    stats = tuple(v for r in range(world) for v in (100 + r, 50 + r, 10 + r, 40 + r))
+    for rank in range(world):
+        paths = lambda refuse: tuple(v for r in range(world) for v in (3 + r, 2, 7, 0 if r == refuse else 1))
+        head = ["disconnect", "plan", "connect"]
+        assert got[rank]["two_level"] == head + [
+            "partition", "count", "contract", ("graph_paths", stats, paths(-1), False),
+            "partition", "count", "contract", ("graph_paths", stats, paths(-1), True), "disconnect", "close"]
+        # one rank refused: EVERY rank falls back to the one-level stage, with the same global stats
+        assert got[rank]["refused"] == head + ["partition", "count", "contract", ("graph", stats, True)] * 2 + ["disconnect", "close"]
+        assert got[rank]["one_level"] == head + ["partition", "count", ("graph", stats, True)] * 2 + ["disconnect", "close"]
+
+
 @pytest.mark.gpu
 def test_two_rank_parity_on_gpus():
     import torch
@@ -127,4 +215,4 @@ def test_two_rank_parity_on_gpus():
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, (p.stdout + p.stderr)[-4000:]
-    assert p.stdout.count("PARITY") == 4 and "MISMATCH" not in p.stdout
+    assert p.stdout.count("PARITY") == 12 and "MISMATCH" not in p.stdout     # 4 cases x (two-level, solid sharded, one-level)
