@@ -404,8 +404,10 @@ def main():
                    "n_instances": n_inst, "n_distinct": st["n_distinct"], "n_solid": st["n_solid"], "n_kmers": st["n_kmers"],
                    "n_v": st["n_v"], "n_e": st["n_e"],
                    "parallelism": (f"{world} ranks: reads split 1/{world} per rank, (k+1)-mer buckets hash-partitioned to owner GPUs "
-                                   f"(k_count_buckets reads every rank's records through NVLink peer loads), solid sets gathered over NVLink, graph stage "
-                                   f"replicated") if world > 1 else "1 gpu"},
+                                   f"(k_count_buckets reads every rank's records through NVLink peer loads); graph stage two-level: every rank "
+                                   f"contracts its own solid (k+1)-mers into unbranched paths, the paths are pulled over NVLink (k_gather_paths), "
+                                   f"the path-level global stage runs on every rank; the solid set stays sharded over its owners") if world > 1 else
+                                  "1 gpu; graph stage two-level (k_contract inside the bucket groups, then the path-level global stage)"},
         "stage_ms": {"count": count_ms, "graph": ms_graph / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": TRAFFIC.get(top), "kernel": top, "ms_per_launch": top_ms,
