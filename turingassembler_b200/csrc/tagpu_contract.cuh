@@ -33,7 +33,7 @@ template <int W, int MAXN> constexpr size_t tagpu_contract_smem()
 {
 	return (size_t)MAXN * sizeof(Key<W>) + 4 * (size_t)MAXN * sizeof(Key<W>) + (size_t)MAXN * 4 + 4 * (size_t)MAXN * 4 + 8 * (size_t)MAXN * 2 + 2 * (size_t)MAXN * 2;
 }
-constexpr uint32_t TAGPU_OE_END = 0xffffu;
+constexpr uint32_t TAGPU_OE_END = 0xffffu, TAGPU_OE_PAL = 0x8000u;   // oriented entries are < 2 * 1024
 
 template <int W> struct PathStore {
 	Key<W> *first, *last;             // first / last (k+1)-mer of the path, oriented along the path
@@ -166,9 +166,11 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 		TC(0);
 		// ---- local k-mer table with masks and one leaving entry per (k-mer, orientation)
 		for (uint32_t oe = tid; oe < 2u * n; oe += T) {
-			const Key<W> x = e_key[oe >> 1];
-			const Key<W> y = (oe & 1u) ? KO::rc(x, K) : x;
-			const Key<W> q = KO::shr2(y), qr = KO::rc(q, k);              // head k-mer of the oriented entry
+			// one reverse complement per entry serves both orientations: with y = b0..bk, the head k-mer b0..b(k-1) is
+			// shr2(y) and ITS reverse complement is the low k bases of rc(y)
+			const Key<W> x = e_key[oe >> 1], xr = KO::rc(x, K);
+			const Key<W> y = (oe & 1u) ? xr : x, yr = (oe & 1u) ? x : xr;
+			const Key<W> q = KO::shr2(y), qr = KO::band(yr, kmask);       // head k-mer of the oriented entry
 			const bool fwd = KO::le(q, qr);
 			const Key<W> z = fwd ? q : qr, stored = KO::bnot(z);
 			uint32_t s = (uint32_t)KO::hash(z) & (ts - 1);
@@ -183,7 +185,7 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 			}
 			const uint32_t oz = fwd ? 0u : 1u;
 			atomicOr(t_mask + s, 1u << (oz * 4u + KO::last_base(y)));
-			t_out[2u * s + oz] = (uint16_t)oe;
+			t_out[2u * s + oz] = (uint16_t)(oe | (KO::eq(x, xr) ? TAGPU_OE_PAL : 0u));   // bit 15: palindromic (k+1)-mer
 		}
 		__syncthreads();
 		TC(1);
@@ -197,10 +199,8 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 			// the two (k+1)-mers through z must be two different, non-palindromic entries: a hairpin (z followed by its own
 			// reverse complement) or a palindromic (k+1)-mer would make a path that is its own reverse complement, and
 			// those stay with the (k+1)-mer-level rules of the global stage
-			const uint32_t i0 = t_out[2u * s] >> 1, i1 = t_out[2u * s + 1u] >> 1;
-			if (i0 == i1) continue;
-			const Key<W> x0 = e_key[i0], x1 = e_key[i1];
-			if (KO::eq(x0, KO::rc(x0, K)) || KO::eq(x1, KO::rc(x1, K))) continue;
+			const uint32_t o0 = t_out[2u * s], o1 = t_out[2u * s + 1u];
+			if ((o0 >> 1) == (o1 >> 1) || ((o0 | o1) & TAGPU_OE_PAL)) continue;
 			nxt[atomicAdd(&s_cand, 1u)] = (uint16_t)s;
 		}
 		__syncthreads();
@@ -217,16 +217,16 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 		TC(2);
 		// ---- links: the entry that continues an oriented entry across a hidden k-mer
 		for (uint32_t oe = tid; oe < 2u * n; oe += T) {
-			const Key<W> x = e_key[oe >> 1];
-			const Key<W> y = (oe & 1u) ? KO::rc(x, K) : x;
-			const Key<W> q = KO::band(y, kmask), qr = KO::rc(q, k);       // tail k-mer
+			const Key<W> x = e_key[oe >> 1], xr = KO::rc(x, K);
+			const Key<W> y = (oe & 1u) ? xr : x, yr = (oe & 1u) ? x : xr;
+			const Key<W> q = KO::band(y, kmask), qr = KO::shr2(yr);       // tail k-mer b1..bk, and rc of it = first k bases of rc(y)
 			const bool fwd = KO::le(q, qr);
 			const Key<W> stored = KO::bnot(fwd ? q : qr);
 			uint32_t s = (uint32_t)KO::hash(fwd ? q : qr) & (ts - 1), probes = 0;
 			while (!KO::eq(t_key[s], stored) && probes < ts) { s = (s + 1) & (ts - 1); ++probes; }
 			uint16_t nx = (uint16_t)TAGPU_OE_END;
 			if (probes >= ts) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT);
-			else if (t_mask[s] & 0x100u) nx = t_out[2u * s + (fwd ? 0u : 1u)];
+			else if (t_mask[s] & 0x100u) nx = (uint16_t)(t_out[2u * s + (fwd ? 0u : 1u)] & ~TAGPU_OE_PAL);
 			nxt[oe] = nx;
 		}
 		__syncthreads();
@@ -234,7 +234,6 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 		// ---- every entry: does one of its orientations head a path that this orientation emits?  (a path is emitted by
 		// its smaller end: head <= reverse complement of its last entry; an entry emits at most one path)
 		uint32_t r_len[R], r_oe[R], r_last[R], r_pi[R], r_wo[R];
-		unsigned long long r_cs[R];
 #pragma unroll
 		for (int r = 0; r < R; ++r) {
 			const uint32_t i = tid + (uint32_t)r * T;
@@ -244,10 +243,8 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 				const uint32_t oe = 2u * i + o;
 				if (nxt[oe ^ 1u] != TAGPU_OE_END) continue;              // not a head: the k-mer before it is hidden
 				uint32_t len = 0, last = oe, cur = oe;
-				unsigned long long csum = 0;
 				for (;;) {
 					++len;
-					csum += e_cnt[cur >> 1];
 					last = cur;
 					const uint32_t nx = nxt[cur];
 					if (nx == TAGPU_OE_END) break;
@@ -257,7 +254,7 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 				if (oe > (last ^ 1u)) continue;                           // the twin path emits
 				if (oe == (last ^ 1u) && o == 1) continue;                // (self-twin single entry: emitted once, as o = 0)
 				const uint32_t words = len > 1 ? (len - 1 + 15) >> 4 : 0u;
-				r_len[r] = len; r_oe[r] = oe; r_last[r] = last; r_cs[r] = csum;
+				r_len[r] = len; r_oe[r] = oe; r_last[r] = last;
 				r_wo[r] = words ? atomicAdd(&s_words, words) : 0u;
 				r_pi[r] = atomicAdd(&s_paths, 1u);
 			}
@@ -278,15 +275,18 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 			const unsigned long long pi = pbase + r_pi[r], wo = wbase + r_wo[r];
 			const Key<W> xf = (oe & 1u) ? KO::rc(e_key[oe >> 1], K) : e_key[oe >> 1];
 			const Key<W> xl = (last & 1u) ? KO::rc(e_key[last >> 1], K) : e_key[last >> 1];
-			ps.first[pi] = xf; ps.last[pi] = xl; ps.cnt[pi] = r_cs[r]; ps.off[pi] = wo; ps.n[pi] = len;
+			ps.first[pi] = xf; ps.last[pi] = xl; ps.off[pi] = wo; ps.n[pi] = len;
+			unsigned long long csum = e_cnt[oe >> 1];
 			uint32_t c2 = nxt[oe], word = 0;
 			for (uint32_t j = 0; j + 1 < len; ++j) {                     // interior base j = last base of the (j + 2)-th entry
 				const Key<W> xe = e_key[c2 >> 1];
+				csum += e_cnt[c2 >> 1];
 				const uint32_t base = (c2 & 1u) ? 3u - KO::first_base(xe, K) : KO::last_base(xe);
 				word |= base << ((j & 15u) << 1);
 				if ((j & 15u) == 15u || j + 2 == len) { ps.interior[wo + (j >> 4)] = word; word = 0; }
 				c2 = nxt[c2];
 			}
+			ps.cnt[pi] = csum;
 		}
 		TC(4);
 	}
