@@ -389,8 +389,11 @@ __global__ void __launch_bounds__(256) k_succ_paths(PathStore<W> ps, uint64_t n_
 }
 
 // ---------------------------------------------------------------- C4': edge heads, one thread per path and direction
+// Only one path end in seven starts an edge (leaves a node), and those write k + n bases each: the CTA compacts them
+// in shared memory first, so that the base loop runs on full warps.
+constexpr int TAGPU_HEADS_THREADS = 512;
 template <int W>
-__global__ void __launch_bounds__(128) k_heads_paths(PathStore<W> ps, uint64_t n_paths, int k, KTab<W> t, const uint32_t *__restrict__ vL,
+__global__ void __launch_bounds__(TAGPU_HEADS_THREADS) k_heads_paths(PathStore<W> ps, uint64_t n_paths, int k, KTab<W> t, const uint32_t *__restrict__ vL,
 						      const uint32_t *__restrict__ vR, const uint32_t *__restrict__ kind,
 						      const uint32_t *__restrict__ node_ebase, const unsigned long long *__restrict__ jump,
 						      const uint32_t *__restrict__ vsucc, const uint32_t *__restrict__ wlast, uint32_t *__restrict__ vedge,
@@ -435,19 +438,31 @@ __global__ void __launch_bounds__(128) k_heads_paths(PathStore<W> ps, uint64_t n
 			}
 		}
 	}
+	__shared__ uint32_t s_n;
+	__shared__ unsigned long long s_item[TAGPU_HEADS_THREADS], s_off[TAGPU_HEADS_THREADS];
+	if (threadIdx.x == 0) s_n = 0;
+	__syncthreads();
 	const unsigned long long off = tagpu_warp_alloc(ctr + CTR_SEQ_WORDS, have ? (len + 15u) >> 4 : 0u);
 	if (have) {
 		g.e_src[e] = ord * 2u + (a & 1u); g.e_dst[e] = dst; g.e_len[e] = len; g.e_off[e] = off; g.e_count[e] = 0;
 		if (first != TAGPU_NONE) vedge[first] = e;
-		// first k bases: the node k-mer as the edge sees it; then the w bases of this path
-		const uint32_t n = w;
+		const uint32_t slot = atomicAdd(&s_n, 1u);
+		s_item[slot] = idx;                                          // path and direction
+		s_off[slot] = off;
+	}
+	__syncthreads();
+	for (uint32_t it = threadIdx.x; it < s_n; it += blockDim.x) {
+		const unsigned long long p2 = s_item[it] >> 1, off2 = s_off[it];
+		const uint32_t dir2 = (uint32_t)s_item[it] & 1u, n = ps.n[p2];
+		const Key<W> xf2 = ps.first[p2];
+		// first k bases: the node k-mer as the edge sees it; then the n bases of this path
 		uint32_t word = 0;
 		for (uint32_t i = 0; i < (uint32_t)k + n; ++i) {
 			// forward: path bases 0 .. k+n-1; backward: complement of path bases k+n-1 .. 0
-			const uint32_t base = dir ? 3u - tagpu_path_base<W>(ps, p, xf, k, (uint32_t)k + n - 1u - i) : tagpu_path_base<W>(ps, p, xf, k, i);
+			const uint32_t base = dir2 ? 3u - tagpu_path_base<W>(ps, p2, xf2, k, (uint32_t)k + n - 1u - i) : tagpu_path_base<W>(ps, p2, xf2, k, i);
 			word |= base << ((i & 15u) << 1);
 			if ((i & 15u) == 15u || i + 1 == (uint32_t)k + n) {
-				atomicOr(g.e_seq + off + (i >> 4), word);
+				atomicOr(g.e_seq + off2 + (i >> 4), word);
 				word = 0;
 			}
 		}

@@ -803,7 +803,7 @@ static int graph_stage_global(tagpu_ctx *ctx, const PathStore<W> &ps, uint64_t n
 		if (rank_lists(ctx, jump, n_cv)) return -1;
 	}
 	if (n_paths) {
-		LAUNCH(k_heads_paths<W>, (unsigned)((2 * n_paths + 127) / 128), 128, ps, n_paths, k, t, vL, vR, kind, node_ebase, jump, vsucc, wlast, vedge, g, ctr);
+		LAUNCH(k_heads_paths<W>, (unsigned)((2 * n_paths + TAGPU_HEADS_THREADS - 1) / TAGPU_HEADS_THREADS), TAGPU_HEADS_THREADS, ps, n_paths, k, t, vL, vR, kind, node_ebase, jump, vsucc, wlast, vedge, g, ctr);
 		LAUNCH(k_interior_paths<W>, (unsigned)((2 * n_paths + 255) / 256), 256, ps, n_paths, k, vL, vR, kind, jump, wlast, vedge, g);
 	}
 	if (n_e) LAUNCH(k_rc_links<W>, (unsigned)((n_e + 255) / 256), 256, t, k, (uint32_t)n_e, node_slot, node_ebase, g, ctr);
