@@ -10,8 +10,8 @@
 //   (iii) that mask is 1-in-1-out.
 // Hidden k-mers are interior to a unitig by construction.  k_contract chains the (k+1)-mers of a block across hidden
 // k-mers into PATHS (first / last (k+1)-mer, number of (k+1)-mers, summed count, packed interior bases) entirely in
-// shared memory; the global kernels below are the path-driven, base-weighted counterparts of tagpu_graph.cuh: only the
-// END k-mers of the paths enter the HBM table, and list ranking carries distances in bases.
+// shared memory; the global kernels below are the path-driven, weighted counterparts of tagpu_graph.cuh: only the
+// END k-mers of the paths enter the HBM table, and list ranking carries distances in (k+1)-mers (= bases of the unitig).
 // A path and its reverse complement are one object (like a canonical (k+1)-mer); a cycle made of hidden k-mers only is a
 // node-free component and is dropped here exactly as the reference never emits it.
 #pragma once
