@@ -93,6 +93,17 @@ int tagpu_build_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_bytes, i
 /* Same from host memory: the stream is uploaded inside the call, in chunks overlapped with the partition pass
  * (pass pinned memory — e.g. from tagpu_load_reads — for the copy to be asynchronous). */
 int tagpu_build_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n_bytes, int k);
+
+/* Packed read stream: the same stream with the ASCII -> 2-bit conversion already done on the host, in the tile layout the
+ * CUDA kernels use in shared memory (per 8192 positions: 256 x u64 codes, 32 bases each, first base most significant,
+ * then 256 x u32 invalid masks; 0.375 bytes per position).  tagpu_pack_stream(stream, n, packed, threads) fills a buffer
+ * of tagpu_packed_bytes(n) bytes; the *_packed calls take it with n_positions = n and give bit-identical results to the
+ * ASCII calls at 3/8 of the host-to-device traffic. */
+uint64_t tagpu_packed_bytes(uint64_t n_positions);
+int tagpu_pack_stream(const uint8_t *stream, uint64_t n_bytes, uint8_t *packed, int n_threads);
+int tagpu_build_host_packed(tagpu_ctx *ctx, const uint8_t *h_packed, uint64_t n_positions, int k);
+int tagpu_count_host_packed(tagpu_ctx *ctx, const uint8_t *h_packed, uint64_t n_positions, int K);
+int tagpu_build_device_packed(tagpu_ctx *ctx, const uint8_t *d_packed, uint64_t n_positions, int k);
 /* Counting stage only (what KMC_build_kmer_database needs); ksize_plus_1 = K = k + 1 */
 int tagpu_count_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_bytes, int ksize_plus_1);
 int tagpu_count_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n_bytes, int ksize_plus_1);
@@ -152,6 +163,8 @@ int tagpu_dist_connect(tagpu_ctx *ctx, const void *all_handles /* world x TAGPU_
 int tagpu_dist_partition(tagpu_ctx *ctx, const uint8_t *d_seq_local, uint64_t n_local_bytes);
 /* same, with this rank's slice still in (pinned) host memory: the upload is overlapped with pass 1 */
 int tagpu_dist_partition_host(tagpu_ctx *ctx, const uint8_t *h_seq_local, uint64_t n_local_bytes);
+/* same, with this rank's slice as a packed read stream (packed by the rank itself, positions from the slice start) */
+int tagpu_dist_partition_host_packed(tagpu_ctx *ctx, const uint8_t *h_packed_local, uint64_t n_local_positions);
 int tagpu_dist_count(tagpu_ctx *ctx, uint64_t stats_out[4]);
 int tagpu_dist_graph(tagpu_ctx *ctx, const uint64_t *all_stats /* world x 4, rank order */, int with_graph);
 /* paths_out = { paths, interior words, k-mers hidden inside paths, 1 if this rank contracted (0: use tagpu_dist_graph) } */

@@ -135,7 +135,8 @@ def load_library() -> C.CDLL:
     lib.tagpu_profile_json.argtypes = [vp]
     lib.tagpu_last_error.restype = C.c_char_p
     lib.tagpu_last_error.argtypes = [vp]
-    for name in ("tagpu_build_device", "tagpu_build_host", "tagpu_count_device", "tagpu_count_host"):
+    for name in ("tagpu_build_device", "tagpu_build_host", "tagpu_count_device", "tagpu_count_host",
+                 "tagpu_build_device_packed", "tagpu_build_host_packed", "tagpu_count_host_packed"):
         f = getattr(lib, name)
         f.restype = i32
         f.argtypes = [vp, vp, u64, i32]
@@ -168,6 +169,12 @@ def load_library() -> C.CDLL:
     lib.tagpu_dist_partition.argtypes = [vp, vp, u64]
     lib.tagpu_dist_partition_host.restype = i32
     lib.tagpu_dist_partition_host.argtypes = [vp, vp, u64]
+    lib.tagpu_dist_partition_host_packed.restype = i32
+    lib.tagpu_dist_partition_host_packed.argtypes = [vp, vp, u64]
+    lib.tagpu_packed_bytes.restype = u64
+    lib.tagpu_packed_bytes.argtypes = [u64]
+    lib.tagpu_pack_stream.restype = i32
+    lib.tagpu_pack_stream.argtypes = [vp, u64, vp, i32]
     lib.tagpu_dist_count.restype = i32
     lib.tagpu_dist_count.argtypes = [vp, C.POINTER(u64)]
     lib.tagpu_dist_graph.restype = i32
@@ -259,6 +266,21 @@ class Tagpu:
         del keep
         return self.stats()
 
+    def build_host_packed(self, packed, n_positions: int, k: int):
+        """packed: numpy uint8 array (or host address) from pack_stream(); n_positions = bytes of the ASCII stream."""
+        ptr = C.c_void_p(packed) if isinstance(packed, int) else C.c_void_p(packed.ctypes.data)
+        self._check(self.lib.tagpu_build_host_packed(self.ctx, ptr, n_positions, k))
+        return self.stats()
+
+    def count_host_packed(self, packed, n_positions: int, K: int):
+        ptr = C.c_void_p(packed) if isinstance(packed, int) else C.c_void_p(packed.ctypes.data)
+        self._check(self.lib.tagpu_count_host_packed(self.ctx, ptr, n_positions, K))
+        return self.stats()
+
+    def build_device_packed(self, d_ptr: int, n_positions: int, k: int):
+        self._check(self.lib.tagpu_build_device_packed(self.ctx, C.c_void_p(d_ptr), n_positions, k))
+        return self.stats()
+
     def build_local_host(self, stream, k: int, contigs: Sequence[bytes], contig_cov: Sequence[float]):
         """build_local_assembly_graph on host buffers: reads + flanking contigs (ACGT bytes) with their coverages."""
         ptr, n, keep = _host_buffer(stream)
@@ -295,6 +317,9 @@ class Tagpu:
 
     def dist_partition_host(self, h_ptr: int, n_local_bytes: int):
         self._check(self.lib.tagpu_dist_partition_host(self.ctx, C.c_void_p(h_ptr), n_local_bytes))
+
+    def dist_partition_host_packed(self, h_ptr: int, n_local_positions: int):
+        self._check(self.lib.tagpu_dist_partition_host_packed(self.ctx, C.c_void_p(h_ptr), n_local_positions))
 
     def dist_count(self):
         out = (C.c_uint64 * 4)()
@@ -399,6 +424,22 @@ def shard_range(stream: np.ndarray, rank: int, world: int):
     b, e = C.c_uint64(), C.c_uint64()
     lib.tagpu_dist_shard_range(C.c_void_p(a.ctypes.data), a.size, rank, world, C.byref(b), C.byref(e))
     return b.value, e.value
+
+
+def packed_bytes(n_positions: int) -> int:
+    return int(load_library().tagpu_packed_bytes(n_positions))
+
+
+def pack_stream(stream, threads: int = 8, out: np.ndarray | None = None) -> np.ndarray:
+    """ASCII read stream (bytes / uint8 array) -> packed read stream (include/tagpu.h), packed on the host by libtagpu.so."""
+    ptr, n, keep = _host_buffer(stream)
+    lib = load_library()
+    if out is None:
+        out = np.empty(int(lib.tagpu_packed_bytes(n)), dtype=np.uint8)
+    if lib.tagpu_pack_stream(ptr, n, C.c_void_p(out.ctypes.data), threads) != 0:
+        raise TagpuError("tagpu_pack_stream failed (host and device tile layouts disagree)")
+    del keep
+    return out
 
 
 def free_reads(addr: int):

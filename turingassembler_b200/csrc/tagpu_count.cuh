@@ -45,6 +45,7 @@ struct PartCfg {
 	uint32_t overflow_cap;        // records in the overflow area
 	uint32_t world;               // GPUs sharing the key space (1 = single GPU)
 	uint32_t per_rank;            // buckets owned by each rank: owner(b) = b / per_rank
+	uint32_t packed;              // the read stream is in the packed tile layout (tagpu_extract.cuh), not ASCII
 };
 
 // Where pass 2 finds the records of a bucket: every rank ("source") partitions ITS slice of the reads into its own
@@ -118,7 +119,8 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 	uint32_t *hs = hp + TAGPU_HM_LEN;                   // block-wise suffix minima
 	const int K = cfg.K, m = TAGPU_MINIMIZER_M;
 
-	tagpu_load_tile(seq, n, ((uint64_t)blockIdx.x + tile0) * TAGPU_TILE_BASES, pk, inv);
+	if (cfg.packed) tagpu_load_tile_packed(seq, n, ((uint64_t)blockIdx.x + tile0) * TAGPU_TILE_BASES, pk, inv);
+	else tagpu_load_tile(seq, n, ((uint64_t)blockIdx.x + tile0) * TAGPU_TILE_BASES, pk, inv);
 	__syncthreads();
 
 	// A. hash of the canonical m-mer ending at every position (invalid if the m-mer touches a non-ACGT byte), with the

@@ -66,6 +66,29 @@ TAGPU_DI void tagpu_load_tile(const uint8_t *__restrict__ seq, uint64_t n, uint6
 	}
 }
 
+// The same tile out of a PACKED read stream (include/tagpu.h "packed read stream"): the host (tagpu_pack_stream) has
+// already done the ASCII -> 2-bit conversion in exactly the shared-memory layout above, tile by tile —
+// TAGPU_TILE_WORDS 64-bit code words followed by TAGPU_TILE_WORDS 32-bit invalid masks = 3072 bytes per 8192 positions
+// (0.375 bytes per base instead of 1: that is what crosses PCIe) — so loading a tile is a plain copy.
+constexpr int TAGPU_PACKED_TILE_BYTES = TAGPU_TILE_WORDS * 12;
+TAGPU_DI void tagpu_load_tile_packed(const uint8_t *__restrict__ packed, uint64_t n, uint64_t tile_base, uint64_t *pk, uint32_t *inv)
+{
+	const uint64_t n_words = ((n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES) * TAGPU_TILE_WORDS;   // whole tiles
+	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
+		const long long w = (long long)(tile_base / 32) - TAGPU_HALO_WORDS + j;              // stream word of smem word j
+		uint64_t word = 0;
+		uint32_t bad = 0xffffffffu;
+		if (w >= 0 && (uint64_t)w < n_words) {
+			const uint8_t *tile = packed + ((uint64_t)w / TAGPU_TILE_WORDS) * TAGPU_PACKED_TILE_BYTES;
+			const uint32_t o = (uint32_t)((uint64_t)w % TAGPU_TILE_WORDS);
+			word = __ldg(reinterpret_cast<const uint64_t *>(tile) + o);
+			bad = __ldg(reinterpret_cast<const uint32_t *>(tile + TAGPU_TILE_WORDS * 8) + o);
+		}
+		pk[j] = word;
+		inv[j] = bad;
+	}
+}
+
 // Calls f(canonical_key, pos_in_word) for every valid window of K bases ending in word `wi` (tile-local, >= HALO_WORDS).
 // Returns the number of valid windows.
 template <int W, typename F>

@@ -347,6 +347,81 @@ static void *ingest_phase2(void *raw)
 	return NULL;
 }
 
+/* ------------------------------------------------------------------ packed read stream (include/tagpu.h)
+ * Tile t = stream positions [8192 t, 8192 t + 8192): 256 64-bit code words (32 bases each, first base most significant,
+ * A=0 C=1 G=2 T=3) followed by 256 32-bit invalid masks (bit 31 = first position of the word; set for every byte that
+ * is not A/C/G/T/a/c/g/t and for the positions past the end of the stream).  This is byte for byte what the CUDA tile
+ * loader builds in shared memory from an ASCII stream (tagpu_pack4 in csrc/tagpu_extract.cuh — including the don't-care
+ * code bits it leaves under invalid bytes), done once on the host so that 0.375 bytes per base cross PCIe instead of 1. */
+#define PACK_TILE_WORDS 256
+#define PACK_TILE_BASES (PACK_TILE_WORDS * 32)
+#define PACK_TILE_BYTES (PACK_TILE_WORDS * 12)
+#define PACK_TASK_TILES 64
+
+static uint8_t pack_code[256];     /* bits 1..0: code, bit 2: invalid */
+static pthread_once_t pack_once = PTHREAD_ONCE_INIT;
+static void pack_init(void)
+{
+	for (int b = 0; b < 256; ++b) {
+		unsigned c = ((unsigned)b >> 1) & 3u;       /* A=0 C=1 G=3 T=2 ... */
+		c ^= c >> 1;                                /* ... A=0 C=1 G=2 T=3, and whatever falls out for other bytes */
+		const int u = b & 0xdf;                     /* fold lower case */
+		const int ok = u == 'A' || u == 'C' || u == 'G' || u == 'T';
+		pack_code[b] = (uint8_t)(c | (ok ? 0u : 4u));
+	}
+}
+
+struct pack_job {
+	const uint8_t *stream;
+	uint64_t n, n_tiles;
+	uint8_t *packed;
+};
+
+static void pack_task(size_t task, void *arg)
+{
+	struct pack_job *j = arg;
+	uint64_t t0 = (uint64_t)task * PACK_TASK_TILES, t1 = t0 + PACK_TASK_TILES;
+	if (t1 > j->n_tiles) t1 = j->n_tiles;
+	for (uint64_t t = t0; t < t1; ++t) {
+		uint64_t *pk = (uint64_t *)(j->packed + t * PACK_TILE_BYTES);
+		uint32_t *inv = (uint32_t *)(j->packed + t * PACK_TILE_BYTES + PACK_TILE_WORDS * 8);
+		for (int w = 0; w < PACK_TILE_WORDS; ++w) {
+			const uint64_t g0 = t * PACK_TILE_BASES + (uint64_t)w * 32;
+			uint64_t word = 0;
+			uint32_t bad = 0;
+			if (g0 + 32 <= j->n) {
+				const uint8_t *p = j->stream + g0;
+				for (int q = 0; q < 32; ++q) {
+					const uint32_t c = pack_code[p[q]];
+					word = (word << 2) | (c & 3u);
+					bad = (bad << 1) | (c >> 2);
+				}
+			} else {
+				for (int q = 0; q < 32; ++q) {
+					uint32_t c = 4;                         /* past the end: code 0, invalid */
+					if (g0 + (uint64_t)q < j->n) c = pack_code[j->stream[g0 + q]];
+					word = (word << 2) | (c & 3u);
+					bad = (bad << 1) | (c >> 2);
+				}
+			}
+			pk[w] = word;
+			inv[w] = bad;
+		}
+	}
+}
+
+uint64_t tagpu_packed_bytes(uint64_t n_positions);
+
+int tagpu_pack_stream(const uint8_t *stream, uint64_t n_bytes, uint8_t *packed, int n_threads)
+{
+	if (n_threads < 1) n_threads = 1;
+	pthread_once(&pack_once, pack_init);
+	struct pack_job j = { stream, n_bytes, (n_bytes + PACK_TILE_BASES - 1) / PACK_TILE_BASES, packed };
+	if (j.n_tiles * (uint64_t)PACK_TILE_BYTES != tagpu_packed_bytes(n_bytes)) return -1;   /* host and device layouts disagree */
+	run_tasks((size_t)((j.n_tiles + PACK_TASK_TILES - 1) / PACK_TASK_TILES), n_threads, pack_task, &j);
+	return 0;
+}
+
 int64_t tagpu_load_reads(int n_files, char **files, int n_threads, uint8_t **stream)
 {
 	if (n_threads < 1) n_threads = 1;

@@ -33,6 +33,7 @@ struct tagpu_ctx {
 	cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
 	cudaEvent_t ev_chunk[TAGPU_UPLOAD_CHUNKS_MAX];
 	const uint8_t *h_src = nullptr;    // host source of the read stream while its upload is pending (tagpu_*_host calls)
+	bool src_packed = false;           // the read stream of the current build is in the packed tile layout (tagpu_extract.cuh)
 	int ci = 2, skip_counts = 0;
 	int contract = 1;                  // two-level graph stage (tagpu_contract.cuh)
 	bool contracted = false;           // the last graph was built that way (hidden k-mers are not in the table)
@@ -323,6 +324,7 @@ static PartCfg plan_cfg(uint64_t n_total, int K, int world, uint32_t group_targe
 	if (cap_env && atoi(cap_env) > 0) cfg.cap_records = (uint32_t)atoi(cap_env);
 	cfg.world = (uint32_t)world;
 	cfg.per_rank = (uint32_t)((n_buckets + world - 1) / world);
+	cfg.packed = 0;
 	cfg.overflow_cap = (uint32_t)(n_source / 16 + 4096);
 	if (cap_env && atoi(cap_env) > 0) cfg.overflow_cap = (uint32_t)(n_source / 4 + 4096);
 	return cfg;
@@ -330,9 +332,11 @@ static PartCfg plan_cfg(uint64_t n_total, int K, int world, uint32_t group_targe
 
 // Pass 1 over this rank's reads + the bucket sort of the records that overflowed their region.  Purely local.
 template <int W>
-static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, const PartCfg &cfg)
+static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, const PartCfg &cfg_in)
 {
 	typedef BucketCfg<W> BC;
+	PartCfg cfg = cfg_in;
+	cfg.packed = ctx->src_packed ? 1u : 0u;
 	const uint32_t n_buckets = 1u << cfg.log2_buckets;
 	const size_t smem1 = TAGPU_SMEM_WORDS * 8 + 3 * (size_t)TAGPU_SMEM_WORDS * 4 + 2 * (size_t)TAGPU_HM_LEN * 4;
 	static bool attr_done[3] = { false, false, false };
@@ -349,21 +353,35 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 	} else if (n_tiles) {
 		// The reads are still in host memory (d_seq is our staging buffer): upload them in chunks on a second stream and
 		// run pass 1 over every chunk as soon as it has landed, so the PCIe copy hides the partition pass.  A tile needs
-		// one word of look-ahead, so a launch covers the tiles whose right halo is already on the device.
+		// one word of look-ahead, so a launch covers the tiles whose right halo is already on the device: with an ASCII
+		// stream the copy runs 32 bytes ahead; with a packed stream (whole 3072-byte tiles) the last tile of a chunk waits
+		// for the next chunk.
+		const bool packed = cfg.packed != 0;
 		uint64_t chunk_tiles = n_tiles / TAGPU_UPLOAD_CHUNKS + 1;
-		if (chunk_tiles < 512) chunk_tiles = 512;                // >= 4 MB per copy: small inputs go up in one piece
+		const uint64_t min_tiles = packed ? 1366 : 512;            // >= 4 MB per copy: small inputs go up in one piece
+		if (chunk_tiles < min_tiles) chunk_tiles = min_tiles;
 		const uint8_t *h_src = ctx->h_src;
 		ctx->h_src = nullptr;
-		uint64_t copied = 0, tile0 = 0;
+		const uint64_t total = packed ? n_tiles * (uint64_t)TAGPU_PACKED_TILE_BYTES : n;
+		uint64_t copied = 0, tile0 = 0, up_tile = 0;                // up_tile: tiles whose upload has been issued
 		for (int c = 0; tile0 < n_tiles; ++c) {
-			const uint64_t tile1 = tile0 + chunk_tiles < n_tiles ? tile0 + chunk_tiles : n_tiles;
-			const uint64_t want = tile1 == n_tiles ? n : tile1 * TAGPU_TILE_BASES + 32 * TAGPU_RHALO_WORDS;
+			up_tile = up_tile + chunk_tiles < n_tiles ? up_tile + chunk_tiles : n_tiles;
+			uint64_t want, tile1;
+			if (packed) {
+				want = up_tile * (uint64_t)TAGPU_PACKED_TILE_BYTES;
+				tile1 = up_tile == n_tiles ? n_tiles : up_tile - 1;
+			} else {
+				want = up_tile == n_tiles ? n : up_tile * TAGPU_TILE_BASES + 32 * TAGPU_RHALO_WORDS;
+				tile1 = up_tile;
+			}
+			if (want > total) want = total;
 			if (want > copied) CU(cudaMemcpyAsync((uint8_t *)ctx->seq.p + copied, h_src + copied, want - copied, cudaMemcpyHostToDevice, ctx->copy_stream));
 			copied = want > copied ? want : copied;
 			CU(cudaEventRecord(ctx->ev_chunk[c % TAGPU_UPLOAD_CHUNKS_MAX], ctx->copy_stream));
 			CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c % TAGPU_UPLOAD_CHUNKS_MAX], 0));
-			LAUNCH_SMEM(k_partition<W>, (unsigned)(tile1 - tile0), TAGPU_TILE_THREADS, smem1, d_seq, n, (uint32_t)tile0, cfg, (SkRec<W> *)ctx->regions.p,
-				    (unsigned long long *)ctx->cursor.p, (SkRec<W> *)ctx->overflow.p, (uint32_t *)ctx->overflow_bucket.p, ctx->d_ctr);
+			if (tile1 > tile0)
+				LAUNCH_SMEM(k_partition<W>, (unsigned)(tile1 - tile0), TAGPU_TILE_THREADS, smem1, d_seq, n, (uint32_t)tile0, cfg, (SkRec<W> *)ctx->regions.p,
+					    (unsigned long long *)ctx->cursor.p, (SkRec<W> *)ctx->overflow.p, (uint32_t *)ctx->overflow_bucket.p, ctx->d_ctr);
 			tile0 = tile1;
 		}
 	}
@@ -1009,14 +1027,28 @@ static int upload(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n);
 extern "C" int tagpu_dist_partition(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_local_bytes)
 {
 	ctx->h_src = nullptr;
+	ctx->src_packed = false;
 	return dist_partition_impl(ctx, d_seq, n_local_bytes);
 }
 
 // same with this rank's slice of the reads still in (pinned) host memory: the upload is overlapped with pass 1
 extern "C" int tagpu_dist_partition_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n_local_bytes)
 {
+	ctx->src_packed = false;
 	if (upload(ctx, h_seq, n_local_bytes)) return -1;
 	return dist_partition_impl(ctx, (const uint8_t *)ctx->seq.p, n_local_bytes);
+}
+
+extern "C" uint64_t tagpu_packed_bytes(uint64_t n_positions);
+
+// same with this rank's slice as a packed read stream (packed by the rank itself: positions count from the slice start)
+extern "C" int tagpu_dist_partition_host_packed(tagpu_ctx *ctx, const uint8_t *h_packed, uint64_t n_local_positions)
+{
+	ctx->src_packed = true;
+	if (upload(ctx, h_packed, tagpu_packed_bytes(n_local_positions))) return -1;
+	const int rc = dist_partition_impl(ctx, (const uint8_t *)ctx->seq.p, n_local_positions);
+	ctx->src_packed = false;
+	return rc;
 }
 
 static int dist_partition_impl(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n_local_bytes)
@@ -1238,17 +1270,61 @@ static int upload(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n)
 	return 0;
 }
 
-extern "C" int tagpu_build_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int k) { ctx->h_src = nullptr; return run(ctx, d_seq, n, k + 1, true); }
-extern "C" int tagpu_count_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K) { ctx->h_src = nullptr; return run(ctx, d_seq, n, K, false); }
+extern "C" int tagpu_build_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int k)
+{
+	ctx->h_src = nullptr;
+	ctx->src_packed = false;
+	return run(ctx, d_seq, n, k + 1, true);
+}
+extern "C" int tagpu_count_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K)
+{
+	ctx->h_src = nullptr;
+	ctx->src_packed = false;
+	return run(ctx, d_seq, n, K, false);
+}
 extern "C" int tagpu_build_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n, int k)
 {
+	ctx->src_packed = false;
 	if (upload(ctx, h_seq, n)) return -1;
 	return run(ctx, (const uint8_t *)ctx->seq.p, n, k + 1, true);
 }
 extern "C" int tagpu_count_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n, int K)
 {
+	ctx->src_packed = false;
 	if (upload(ctx, h_seq, n)) return -1;
 	return run(ctx, (const uint8_t *)ctx->seq.p, n, K, false);
+}
+
+// ---- packed read stream (include/tagpu.h): n_positions = bytes of the ASCII stream it was packed from
+extern "C" uint64_t tagpu_packed_bytes(uint64_t n_positions)
+{
+	return (n_positions + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES * (uint64_t)TAGPU_PACKED_TILE_BYTES;
+}
+static int run_packed(tagpu_ctx *ctx, const uint8_t *d_packed, uint64_t n_positions, int K, bool with_graph)
+{
+	static const bool direct = getenv("TAGPU_COUNT_DIRECT") != nullptr;
+	if (direct) return fail(ctx, "TAGPU_COUNT_DIRECT (bring-up cross-check) reads ASCII streams only");
+	ctx->src_packed = true;
+	const int rc = run(ctx, d_packed, n_positions, K, with_graph);
+	ctx->src_packed = false;
+	return rc;
+}
+extern "C" int tagpu_build_device_packed(tagpu_ctx *ctx, const uint8_t *d_packed, uint64_t n_positions, int k)
+{
+	ctx->h_src = nullptr;
+	return run_packed(ctx, d_packed, n_positions, k + 1, true);
+}
+extern "C" int tagpu_build_host_packed(tagpu_ctx *ctx, const uint8_t *h_packed, uint64_t n_positions, int k)
+{
+	ctx->src_packed = true;            // (upload() stages tagpu_packed_bytes bytes and leaves the chunked copy to pass 1)
+	if (upload(ctx, h_packed, tagpu_packed_bytes(n_positions))) return -1;
+	return run_packed(ctx, (const uint8_t *)ctx->seq.p, n_positions, k + 1, true);
+}
+extern "C" int tagpu_count_host_packed(tagpu_ctx *ctx, const uint8_t *h_packed, uint64_t n_positions, int K)
+{
+	ctx->src_packed = true;
+	if (upload(ctx, h_packed, tagpu_packed_bytes(n_positions))) return -1;
+	return run_packed(ctx, (const uint8_t *)ctx->seq.p, n_positions, K, false);
 }
 
 // build_local_assembly_graph: reads + the two flanking contigs of the global graph.
@@ -1261,6 +1337,7 @@ extern "C" int tagpu_build_local_host(tagpu_ctx *ctx, const uint8_t *h_reads, ui
 	if (n_contigs < 0 || n_contigs > 4) return fail(ctx, "at most 4 flanking contigs (got %d)", n_contigs);
 	if (ctx->dist) return fail(ctx, "context is in multi-GPU mode");
 	CU(cudaSetDevice(ctx->device));
+	ctx->src_packed = false;
 	ctx->local_mode = false;
 	ctx->n_garbage = 0;
 	ctx->n_contigs = 0;
