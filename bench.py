@@ -5,8 +5,9 @@
 
 One "step" = one pass of the whole path (count -> solid set -> edge masks -> unitig graph, flat arrays in HBM) over one
 batch of synthetic reads.  At N = 1 the workload is BASELINE.json configs[1] ("C2": E. coli-scale, 2 M pairs x 151 bp,
-k0 = 45, 128-bit keys).  `value` is measured with the read stream already resident in HBM; `e2e` is the same metric
-through the host-buffer C-ABI call (pinned host stream -> H2D -> build -> stats back).  See DESIGN.md "Measurement".
+k0 = 45, 128-bit keys).  `value` is measured with the (ASCII) read stream already resident in HBM; `e2e` is the same metric
+through the host-buffer C-ABI call (pinned host stream -> H2D -> build -> stats back); its host buffer is the packed read
+stream of include/tagpu.h by default (`--host-format ascii` for the byte-per-base stream).  See DESIGN.md "Measurement".
 """
 import argparse
 import json
@@ -270,6 +271,8 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the informative FASTQ-files end-to-end measurement")
+    ap.add_argument("--host-format", default="packed", choices=["ascii", "packed"],
+                    help="e2e leg: the pinned host buffer holds the ASCII read stream, or the packed one (include/tagpu.h; packed outside the timed region)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -302,6 +305,11 @@ def main():
     h_stream = torch.empty(n_stream, dtype=torch.uint8, pin_memory=True)
     h_stream.copy_(d_stream)
     torch.cuda.synchronize()
+    h_packed = None
+    if args.host_format == "packed":
+        from turingassembler_b200.api import pack_stream, packed_bytes
+        h_packed = torch.empty(packed_bytes(n_stream), dtype=torch.uint8, pin_memory=True)
+        pack_stream((h_stream.data_ptr(), n_stream), threads=min(16, os.cpu_count() or 1), out=h_packed.numpy())
 
     t = Tagpu(local_rank)
     stream = torch.cuda.Stream(device=dev)      # one explicit stream for the library's kernels, the copies and the timing events
@@ -318,6 +326,10 @@ def main():
 
     def step_host():
         # end to end: this rank's reads start in pinned HOST memory; H2D copy, build, stats back to the host
+        if h_packed is not None:
+            if world > 1:
+                return dt.build(h_packed.data_ptr(), n_stream, host=True, gather_solid=False, packed=True)
+            return t.build_host_packed(h_packed.data_ptr(), n_stream, k)
         if world > 1:
             return dt.build(h_stream.data_ptr(), n_stream, host=True, gather_solid=False)
         return t.build_host((h_stream.data_ptr(), n_stream), k)
@@ -368,6 +380,12 @@ def main():
         dist.all_reduce(ln)
         launches = int(ln.item())
     tm = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    h2d_packed = 0
+    if h_packed is not None:
+        hb = torch.tensor([h_packed.numel()], device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(hb)
+        h2d_packed = int(hb.item())
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms, ms_e2e = tm.tolist()
@@ -417,7 +435,9 @@ def main():
                      "whole_path": {"achieved": (b_count + b_graph) / (ms_step * 1e-3) / 1e9,
                                     "frac": (b_count + b_graph) / (ms_step * 1e-3) / 1e9 / peak}},
         "e2e": {"value": st_e["n_instances"] / (ms_e2e / args.steps * 1e-3), "unit": "kmers/s",
-                "h2d_bytes_per_step": n_total, "d2h_bytes_per_step": 8 * 140 * world, "ms_per_step": ms_e2e / args.steps},
+                "h2d_bytes_per_step": n_total if h_packed is None else h2d_packed, "d2h_bytes_per_step": 8 * 140 * world,
+                "ms_per_step": ms_e2e / args.steps, "host_format": args.host_format,
+                "n_solid": st_e["n_solid"], "n_e": st_e["n_e"]},
         "gpu_launches": launches,
         "kernels": kernels,
         "clocks": sampler.summary(),

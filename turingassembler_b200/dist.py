@@ -56,7 +56,8 @@ class DistTagpu:
         self.dist.all_reduce(self._flag, group=self.group)
         self._sync()
 
-    def build(self, ptr: int, n_local_bytes: int, with_graph: bool = True, host: bool = False, gather_solid: bool = True) -> dict:
+    def build(self, ptr: int, n_local_bytes: int, with_graph: bool = True, host: bool = False, gather_solid: bool = True,
+              packed: bool = False) -> dict:
         """One pass of the hot path over this rank's slice of the reads (device address, or pinned host address with
         host=True); returns the GLOBAL stats on every rank.  gather_solid=False leaves the solid (k+1)-mers sharded over
         their owner ranks when the two-level graph stage runs (only the contracted paths travel)."""
@@ -64,7 +65,9 @@ class DistTagpu:
         if self._dirty:
             self.barrier()
             self._dirty = False
-        if host:
+        if host and packed:           # ptr: this rank's slice as a packed read stream of n_local_bytes positions
+            t.dist_partition_host_packed(ptr, n_local_bytes)
+        elif host:
             t.dist_partition_host(ptr, n_local_bytes)
         else:
             t.dist_partition(ptr, n_local_bytes)
