@@ -90,3 +90,44 @@ def test_full_size_invariants(tagpu, oracle, k):
     else:
         full = dict(zip(key_full.tolist(), cnt.tolist()))
         assert all(full.get(kk, 0) >= c for kk, c in zip(key_s.tolist(), want["count"].tolist()))
+
+
+def _edge_fingerprints(g):
+    """Numbering-independent multiset of the edges: (length, count, xor and wrapping sum of the 2-bit sequence words)."""
+    off = g["e_off"].astype(np.int64)
+    order = np.argsort(off, kind="stable")
+    starts = off[order]
+    assert starts[0] == 0 and np.all(np.diff(starts) > 0)
+    words = g["e_seq"].astype(np.uint64)
+    x = np.empty(g["n_e"], np.uint64)
+    s = np.empty(g["n_e"], np.uint64)
+    x[order] = np.bitwise_xor.reduceat(words, starts)
+    s[order] = np.add.reduceat(words * np.uint64(0x9E3779B97F4A7C15), starts)
+    keys = (s, x, g["e_count"].astype(np.uint64), g["e_len"].astype(np.uint64))
+    o = np.lexsort(keys)
+    return tuple(a[o] for a in keys)
+
+
+@pytest.mark.parametrize("k", [31, 45])
+def test_full_size_two_level_equals_one_level(tagpu, k):
+    """Both graph stages (two-level with contraction inside the bucket groups, one-level with every k-mer in the HBM table)
+    give the same graph on the full-size workload: same counters and the same multiset of (length, count, sequence) edges."""
+    import torch
+    import bench
+    wl = bench.WORKLOADS["C2"]
+    d = bench.gen_reads_gpu(torch, wl, torch.device("cuda", 0))
+    tagpu.set_cutoff(2)
+    was = tagpu.contract
+    try:
+        tagpu.set_contract(True)
+        st2 = tagpu.build_device(d.data_ptr(), d.numel(), k)
+        fp2 = _edge_fingerprints(tagpu.graph())
+        tagpu.set_contract(False)
+        st1 = tagpu.build_device(d.data_ptr(), d.numel(), k)
+        fp1 = _edge_fingerprints(tagpu.graph())
+    finally:
+        tagpu.set_contract(was)
+    for f in ("n_instances", "n_distinct", "n_solid", "sum_solid", "n_kmers", "n_v", "n_e", "n_kp1_on_edge", "n_seq_words"):
+        assert st1[f] == st2[f], f
+    for a, b in zip(fp1, fp2):
+        assert np.array_equal(a, b)
