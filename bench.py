@@ -5,9 +5,11 @@
 
 One "step" = one pass of the whole path (count -> solid set -> edge masks -> unitig graph, flat arrays in HBM) over one
 batch of synthetic reads.  At N = 1 the workload is BASELINE.json configs[1] ("C2": E. coli-scale, 2 M pairs x 151 bp,
-k0 = 45, 128-bit keys).  `value` is measured with the (ASCII) read stream already resident in HBM; `e2e` is the same metric
-through the host-buffer C-ABI call (pinned host stream -> H2D -> build -> stats back); its host buffer is the packed read
-stream of include/tagpu.h by default (`--host-format ascii` for the byte-per-base stream).  See DESIGN.md "Measurement".
+k0 = 45, 128-bit keys).  `value` is measured with the (ASCII) read stream already resident in HBM.  `e2e` at N = 1 is the
+reference-facing call on FILES (build_graph_from_scratch: FASTQ on a RAM disk -> struct asm_graph_t in host memory, wall
+clock) — the same input the reference arm gets; `e2e_host_stream` / `e2e_host_stream_packed` are the host-BUFFER legs
+(pinned read stream -> H2D -> build -> whole flat graph D2H), which is also what `e2e` is at N > 1.  `--impl reference`
+runs the unmodified reference on the same read set.  See DESIGN.md "Measurement".
 """
 import argparse
 import json
@@ -39,7 +41,8 @@ WORKLOADS = {
 L = 151
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the last `ncu --set full` capture of the C2 workload
 # (profiles/), keyed by kernel; None until such a capture exists for the current kernels
-TRAFFIC = {"k_count_buckets<W>": 0.973014e9 + 0.140346e9, "k_partition<W>": 0.610491e9 + 0.909045e9}  # profiles/r1_ncu_top_kernels_raw.txt
+TRAFFIC = {"C2": {"k_count_buckets<W>": 0.973014e9 + 0.140346e9, "k_partition<W>": 0.610491e9 + 0.909045e9,   # profiles/r1_ncu_top_kernels_raw.txt
+                  "whole_path": None}}
 
 
 N_CHUNKS = 16   # the read set is generated in 16 independently seeded chunks of pairs, so a rank can make just its share
@@ -152,43 +155,67 @@ def algorithmic_bytes(st, k, n_stream):
     return count, graph
 
 
-def files_e2e(torch, h_stream, k, reps=3):
-    """The reference-facing call on FILES: build_graph_from_scratch(k, n_threads, mmem, 1, &R1.fq, &R2.fq, dir, &g)
-    (/root/reference/src/kmer_build.h:17-19) on FASTQ files in a RAM disk -> the caller's struct asm_graph_t in host memory
-    (SURVEY.md §8d T_e2e: parse FASTQ, upload, count, build, copy back, one malloc per node / edge).  Informative only."""
+def write_fastq_pair(reads, td):
+    """Writes a (2 n_pairs, L + 1) uint8 array of reads (R1 block then R2 block, each row = sequence + newline) as the two
+    FASTQ files of SURVEY.md §8d (`@<id>/<mate>`, sequence, `+`, L x `I`) into directory td -> [R1.fq, R2.fq]."""
     import numpy as np
-    from turingassembler_b200 import build_graph_from_scratch
-    a = h_stream.numpy().reshape(-1, L + 1)
+    a = reads.reshape(-1, L + 1)
     n = a.shape[0] // 2
+    paths = []
+    for mate, block in ((1, a[:n]), (2, a[n:])):
+        o = 13 + L + 1
+        rec = np.empty((n, o + 2 + L + 1), np.uint8)
+        ids = np.arange(n)
+        rec[:, 0] = ord("@")
+        for d in range(9):
+            rec[:, 1 + d] = ord("0") + (ids // 10 ** (8 - d)) % 10
+        rec[:, 10] = ord("/"); rec[:, 11] = ord("0") + mate; rec[:, 12] = 10
+        rec[:, 13:o] = block                                  # sequence + newline
+        rec[:, o] = ord("+"); rec[:, o + 1] = 10
+        rec[:, o + 2:o + 2 + L] = ord("I"); rec[:, o + 2 + L] = 10
+        p = os.path.join(td, f"R{mate}.fq")
+        rec.tofile(p)
+        paths.append(p)
+    return paths
+
+
+def workload_string(name):
+    """One description of a workload, used verbatim as config.workload by BOTH arms (tagpu and --impl reference)."""
+    wl = WORKLOADS[name]
+    return (f"{name}: {wl.get('n_genomes', 1)} synthetic genome(s), {wl['genome_len']} bp, {wl['n_pairs']} pairs x {L} bp "
+            f"(0.5% substitutions, 2% of reads with one N), k0={wl['k']} (K={wl['k'] + 1}), cutoff 2, whole read set")
+
+
+def make_reads(torch, wl, device, chunks=None):
+    """The workload's read set (or the given chunks of it): generated on the GPU when there is one — the same bytes in both
+    arms — else with torch's CPU generator (same distribution, other bytes; developer runs without a GPU)."""
+    return gen_reads_gpu(torch, wl, device, chunks)
+
+
+def files_e2e(h_stream, k, steps, warmup=1):
+    """End to end through the reference-facing call on FILES: build_graph_from_scratch(k, n_threads, mmem, 1, &R1.fq,
+    &R2.fq, dir, &g) (/root/reference/src/kmer_build.h:17-19) on FASTQ files in a RAM disk -> the caller's struct
+    asm_graph_t in host memory (SURVEY.md §8d T_e2e: parse FASTQ, H2D, count, build, D2H, one malloc per node / edge).
+    Wall clock around every call; the graph of a step is released (tagpu_free_asm_graph) outside the timed region."""
+    from turingassembler_b200 import build_graph_from_scratch
+    from turingassembler_b200.api import free_asm_graph
     td = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     paths = []
     try:
-        for mate, block in ((1, a[:n]), (2, a[n:])):
-            rec = np.empty((n, 12 + L + 1 + 2 + L + 1), np.uint8)
-            ids = np.arange(n)
-            rec[:, 0] = ord("@")
-            for d in range(9):
-                rec[:, 1 + d] = ord("0") + (ids // 10 ** (8 - d)) % 10
-            rec[:, 10] = ord("/"); rec[:, 11] = ord("0") + mate
-            rec[:, 12:12 + L + 1] = block                      # sequence + newline
-            o = 12 + L + 1
-            rec[:, o] = ord("+"); rec[:, o + 1] = 10
-            rec[:, o + 2:o + 2 + L] = ord("I"); rec[:, o + 2 + L] = 10
-            p = os.path.join(td, f"R{mate}.fq")
-            # header line needs its own newline: "@000000001/1\n"
-            hdr = rec[:, :12]
-            with open(p, "wb") as f:
-                f.write(np.concatenate([hdr, np.full((n, 1), 10, np.uint8), rec[:, 12:]], axis=1).tobytes())
-            paths.append(p)
+        paths = write_fastq_pair(h_stream.numpy(), td)
         threads = os.cpu_count() or 4
         times = []
-        for _ in range(reps + 1):
+        n_e = n_v = seq_bytes = 0
+        for _ in range(warmup + steps):
             t0 = time.perf_counter()
             g = build_graph_from_scratch(k, threads, 32, [paths[0]], [paths[1]], td)
             times.append(time.perf_counter() - t0)
-        sec = sum(times[1:]) / reps
-        return {"ms_per_step": sec * 1e3, "n_e": int(g.n_e), "threads": threads,
-                "what": "build_graph_from_scratch on 2 FASTQ files (RAM disk) -> struct asm_graph_t in host memory"}
+            n_e, n_v = int(g.n_e), int(g.n_v)
+            free_asm_graph(g)
+        sec = sum(times[warmup:]) / steps
+        return {"ms_per_step": sec * 1e3, "n_e": n_e, "n_v": n_v, "threads": threads,
+                "fastq_bytes": sum(os.path.getsize(p) for p in paths),
+                "what": "build_graph_from_scratch on 2 FASTQ files (RAM disk) -> struct asm_graph_t in host memory (wall clock)"}
     finally:
         for p in paths:
             os.remove(p)
@@ -202,31 +229,26 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def reference_cpu(workload, steps, warmup):
-    """Times the reference's own CPU implementation of the path on this box's host cores, all threads, on a BOUNDED sample
-    of the workload (same read length, error model and coverage; a fifth of the genome and of the reads):
-    oracle/_ref/TA_ref build_0 = the unmodified reference sources + oracle/kmc_cpu.c standing in for the absent libkmc.a
-    (kind "reference"); the oracle port's own driver if that binary was not built (kind "port").
-    FASTQ files on a RAM disk -> graph_k_<k>_level_0.bin, i.e. the reference's whole stage including its file I/O."""
+def reference_cpu(workload, steps, warmup, reads=None):
+    """Times the reference's own CPU implementation of the path on this box's host cores, all threads, on the WHOLE workload
+    (the same read set as the tagpu arm): oracle/_ref/TA_ref build_0 = the unmodified reference sources + oracle/kmc_cpu.c
+    standing in for the absent libkmc.a (kind "reference"); the oracle port's own driver if that binary was not built
+    (kind "port").  FASTQ files on a RAM disk -> graph_k_<k>_level_0.bin, i.e. the reference's whole stage, process start
+    and file I/O included.  reads: the read set as a uint8 array (generated here when None)."""
     import _oracle
-    import _reads
     wl = WORKLOADS[workload]
     cores = os.cpu_count() or 1
-    n_pairs = min(wl["n_pairs"], 400_000)
-    genome_len = max(wl["genome_len"] * n_pairs // wl["n_pairs"], 20_000)
-    stream = _reads.gen_stream(genome_len, n_pairs, seed=wl["seed"], n_repeats=8)
-    reads = stream.reshape(-1, L + 1)[:, :L]
+    if reads is None:
+        import torch
+        dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+        reads = make_reads(torch, wl, dev).cpu().numpy()
     ora = _oracle.load()
-    n_inst = ora.count(stream, wl["k"] + 1, ci=2, threads=cores)["n_instances"]
+    n_inst = ora.count(reads, wl["k"] + 1, ci=2, threads=cores)["n_instances"]
     have_ref = os.path.exists(_oracle.TA_REF)
     exe = _oracle.TA_REF if have_ref else os.path.join(ROOT, "oracle", "ta_oracle")
     times = []
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
-        f1, f2 = os.path.join(td, "R1.fq"), os.path.join(td, "R2.fq")
-        q = b"+\n" + b"I" * L + b"\n"
-        for path, block, mate in ((f1, reads[:n_pairs], 1), (f2, reads[n_pairs:], 2)):
-            with open(path, "wb") as f:
-                f.write(b"".join(b"@r%d/%d\n" % (i, mate) + r.tobytes() + b"\n" + q for i, r in enumerate(block)))
+        f1, f2 = write_fastq_pair(reads, td)
         for step in range(warmup + steps):
             out = os.path.join(td, f"out{step}")
             os.makedirs(out)
@@ -241,7 +263,7 @@ def reference_cpu(workload, steps, warmup):
             if step >= warmup:
                 times.append(dt)
     sec = sum(times) / len(times)
-    sample = (f"{2 * n_pairs} reads x {L} bp from a {genome_len} bp genome ({n_inst} (k+1)-mer instances), "
+    sample = (f"the whole workload, {len(times)} run(s): {reads.size // (L + 1)} reads x {L} bp ({n_inst} (k+1)-mer instances), "
               f"FASTQ files -> graph_k_{wl['k']}_level_0.bin via build_0 -t {cores}")
     return {"value": n_inst / sec, "unit": "kmers/s", "cores": cores, "kind": "reference" if have_ref else "port", "sample": sample}, sec
 
@@ -256,10 +278,30 @@ def run_reference(args):
         "impl": "reference", "metric": "kmers_per_sec_counted_and_graph_built", "value": base["value"], "unit": "kmers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u128" if wl["k"] + 1 > 32 else "u64", "data": "synthetic",
-        "config": {"workload": f"{args.workload} (bounded sample): {base['sample']}"},
+        "config": {"workload": workload_string(args.workload)},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+class HostGraph:
+    """Pinned host arrays for tagpu_copy_graph (the flat graph of include/tagpu.h), allocated once with head-room."""
+
+    FIELDS = (("node_mask", "uint8", "n"), ("node_ebase", "int32", "n"), ("e_src", "int32", "e"), ("e_dst", "int32", "e"),
+              ("e_rc", "int32", "e"), ("e_len", "int32", "e"), ("e_count", "int64", "e"), ("e_off", "int64", "e"), ("e_seq", "int32", "w"))
+
+    def __init__(self, torch, st):
+        from turingassembler_b200.api import FlatGraph
+        cap = {"n": st["n_v"] // 2 * 5 // 4 + 1024, "e": st["n_e"] * 5 // 4 + 1024, "w": st["n_seq_words"] * 5 // 4 + 1024}
+        self.cap, self.fg, self.t = cap, FlatGraph(), {}
+        for name, dt, kind in self.FIELDS:
+            self.t[name] = torch.empty(cap[kind], dtype=getattr(torch, dt), pin_memory=True)
+            setattr(self.fg, name, self.t[name].data_ptr())
+
+    def fetch(self, tagpu, st):
+        assert st["n_v"] // 2 <= self.cap["n"] and st["n_e"] <= self.cap["e"] and st["n_seq_words"] <= self.cap["w"]
+        tagpu.copy_graph_into(self.fg)
+        return st["n_v"] // 2 * 5 + st["n_e"] * 32 + st["n_seq_words"] * 4          # bytes copied device -> host
 
 
 def main():
@@ -270,9 +312,8 @@ def main():
     ap.add_argument("--impl", default="tagpu", choices=["tagpu", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-files", action="store_true", help="skip the informative FASTQ-files end-to-end measurement")
-    ap.add_argument("--host-format", default="packed", choices=["ascii", "packed"],
-                    help="e2e leg: the pinned host buffer holds the ASCII read stream, or the packed one (include/tagpu.h; packed outside the timed region)")
+    ap.add_argument("--no-files", action="store_true", help="skip the FASTQ-files end-to-end leg (e2e then falls back to the host-stream leg)")
+    ap.add_argument("--one-level", action="store_true", help="one-level graph stage (developer comparison)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -286,7 +327,6 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = os.environ.get("TAGPU_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -298,20 +338,20 @@ def main():
     n_total = 2 * wl["n_pairs"] * (L + 1)
     if world > 1:
         from turingassembler_b200.dist import DistTagpu
-        d_stream = gen_reads_gpu(torch, wl, dev, range(N_CHUNKS * rank // world, N_CHUNKS * (rank + 1) // world))
+        d_stream = make_reads(torch, wl, dev, range(N_CHUNKS * rank // world, N_CHUNKS * (rank + 1) // world))
     else:
-        d_stream = gen_reads_gpu(torch, wl, dev)
+        d_stream = make_reads(torch, wl, dev)
     n_stream = d_stream.numel()
     h_stream = torch.empty(n_stream, dtype=torch.uint8, pin_memory=True)
     h_stream.copy_(d_stream)
     torch.cuda.synchronize()
-    h_packed = None
-    if args.host_format == "packed":
-        from turingassembler_b200.api import pack_stream, packed_bytes
-        h_packed = torch.empty(packed_bytes(n_stream), dtype=torch.uint8, pin_memory=True)
-        pack_stream((h_stream.data_ptr(), n_stream), threads=min(16, os.cpu_count() or 1), out=h_packed.numpy())
+    from turingassembler_b200.api import pack_stream, packed_bytes
+    h_packed = torch.empty(packed_bytes(n_stream), dtype=torch.uint8, pin_memory=True)
+    pack_stream((h_stream.data_ptr(), n_stream), threads=min(16, os.cpu_count() or 1), out=h_packed.numpy())
 
     t = Tagpu(local_rank)
+    if args.one_level:
+        t.set_contract(False)
     stream = torch.cuda.Stream(device=dev)      # one explicit stream for the library's kernels, the copies and the timing events
     torch.cuda.set_stream(stream)
     t.set_stream(stream.cuda_stream)
@@ -324,15 +364,22 @@ def main():
             return dt.build(d_stream.data_ptr(), n_stream, gather_solid=False)
         return t.build_device(d_stream.data_ptr(), n_stream, k)
 
-    def step_host():
-        # end to end: this rank's reads start in pinned HOST memory; H2D copy, build, stats back to the host
-        if h_packed is not None:
-            if world > 1:
-                return dt.build(h_packed.data_ptr(), n_stream, host=True, gather_solid=False, packed=True)
-            return t.build_host_packed(h_packed.data_ptr(), n_stream, k)
+    host_graph = [None]
+
+    def step_host(packed):
+        # end to end on host buffers: this rank's reads start in pinned HOST memory (ASCII, or the packed stream of
+        # include/tagpu.h); H2D copy, build, and the whole flat graph copied back into pinned host arrays (rank 0)
         if world > 1:
-            return dt.build(h_stream.data_ptr(), n_stream, host=True, gather_solid=False)
-        return t.build_host((h_stream.data_ptr(), n_stream), k)
+            st = (dt.build(h_packed.data_ptr(), n_stream, host=True, gather_solid=False, packed=True) if packed else
+                  dt.build(h_stream.data_ptr(), n_stream, host=True, gather_solid=False))
+        else:
+            st = t.build_host_packed(h_packed.data_ptr(), n_stream, k) if packed else t.build_host((h_stream.data_ptr(), n_stream), k)
+        nb = 0
+        if rank == 0:
+            if host_graph[0] is None:
+                host_graph[0] = HostGraph(torch, st)
+            nb = host_graph[0].fetch(t, st)
+        return st, nb
 
     def barrier():
         if world > 1:
@@ -363,15 +410,32 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     t.set_profile(False)
-    step_host()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        st_e = step_host()
-    e1.record(stream)
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    # order-independent digest of the result of the last timed step (outside every timed region)
+    dg = t.digest()
+    if world > 1:
+        part = torch.tensor([dg["solid_sum"] - (1 << 64) if dg["solid_sum"] >= (1 << 63) else dg["solid_sum"], dg["solid_n"]], device=dev, dtype=torch.int64)
+        xs = torch.tensor([dg["solid_xor"] - (1 << 64) if dg["solid_xor"] >= (1 << 63) else dg["solid_xor"]], device=dev, dtype=torch.int64)
+        if not dg["solid_complete"]:
+            dist.all_reduce(part)                                        # wrapping int64 sums = sums mod 2^64
+            gathered = [torch.zeros_like(xs) for _ in range(world)]
+            dist.all_gather(gathered, xs)
+            x = 0
+            for g_ in gathered:
+                x ^= int(g_.item()) & ((1 << 64) - 1)
+            dg["solid_sum"], dg["solid_n"], dg["solid_xor"] = int(part[0].item()) & ((1 << 64) - 1), int(part[1].item()), x
+    # e2e legs on host buffers (CUDA events on the launching stream, barrier on both sides)
+    e2e_stream = {}
+    for name, packed in (("ascii", False), ("packed", True)):
+        for _ in range(2):
+            step_host(packed)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            st_e, d2h = step_host(packed)
+        e1.record(stream)
+        barrier()
+        e2e_stream[name] = (e0.elapsed_time(e1), d2h)
     sampler.stop_flag = True
     sampler.join()
 
@@ -379,16 +443,13 @@ def main():
         ln = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(ln)
         launches = int(ln.item())
-    tm = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    h2d_packed = 0
-    if h_packed is not None:
-        hb = torch.tensor([h_packed.numel()], device=dev, dtype=torch.int64)
-        if world > 1:
-            dist.all_reduce(hb)
-        h2d_packed = int(hb.item())
+    tm = torch.tensor([ms, e2e_stream["ascii"][0], e2e_stream["packed"][0]], device=dev, dtype=torch.float64)
+    hb = torch.tensor([h_packed.numel(), n_stream], device=dev, dtype=torch.int64)
     if world > 1:
+        dist.all_reduce(hb)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = tm.tolist()
+    h2d_packed, h2d_ascii = (int(x) for x in hb.tolist())
+    ms, ms_e2e_ascii, ms_e2e_packed = tm.tolist()
     if world > 1:
         dt.close()
         dist.barrier()
@@ -401,54 +462,68 @@ def main():
     b_count, b_graph = algorithmic_bytes(st, k, n_total)
     peak, peak_src = peaks()
     count_ms = ms_count / args.steps
-    # dominant kernel = the one with the largest share of the step; its algorithmic bytes:
+    # per-kernel algorithmic bytes, per launch = per rank (1/world of the instances, distinct keys, stream):
     #   k_count_buckets: N_i (W + 8) + N_distinct (W + 4)   (key compare + count read/write, first touch per distinct key)
     #   k_partition:     N_i B_in                            (the ASCII stream is read exactly once)
     W = 8 if k + 1 <= 32 else 16
-    # (per launch = per rank: 1/world of the instances, distinct keys and stream bytes)
     kbytes = {"k_count_buckets<W>": (st["n_instances"] * (W + 8) + st["n_distinct"] * (W + 4)) / world, "k_partition<W>": float(n_total) / world}
     kernels = {name: {"ms_per_launch": v[0] / max(v[1], 1), "launches_per_step": v[1] / args.steps,
                       "share_of_step": v[0] / args.steps / ms_step} for name, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
+    for name, kb in kbytes.items():
+        if name in kernels:
+            ach = kb / (kernels[name]["ms_per_launch"] * 1e-3) / 1e9
+            kernels[name].update({"algorithmic_bytes": kb, "equivalent_gbs": ach, "equivalent_frac_of_hbm_peak": ach / peak,
+                                  "dram_traffic_bytes": TRAFFIC.get(args.workload, {}).get(name) if world == 1 else None})
     top = next(iter(kernels))
-    top_ms = kernels[top]["ms_per_launch"]
-    top_bytes = kbytes.get(top, b_count)
-    achieved = top_bytes / (top_ms * 1e-3) / 1e9
+    whole = (b_count + b_graph) / (ms_step * 1e-3) / 1e9
+    traffic_all = TRAFFIC.get(args.workload, {}).get("whole_path") if world == 1 else None
+    wstr = workload_string(args.workload)
+    gold_path = os.path.join(ROOT, "tests", "golden", "digest_fullsize.json")
+    gold = json.load(open(gold_path)).get(args.workload) if os.path.exists(gold_path) else None
+    digest = {f: dg[f] for f in ("solid_sum", "solid_xor", "solid_n", "edge_sum", "edge_xor", "edge_len_sum", "edge_count_sum", "n_e")}
+    digest["matches_reference_golden"] = (all(digest[f] == gold[f] for f in gold) if gold else None)
     line = {
         "metric": "kmers_per_sec_counted_and_graph_built", "value": value, "unit": "kmers/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u128" if k + 1 > 32 else "u64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl.get('n_genomes', 1)} genome(s), {wl['genome_len']} bp, {wl['n_pairs']} pairs x {L} bp, k0={k} "
-                               f"(K={k + 1}), cutoff 2; {n_total} stream bytes resident in HBM (> L2, no flush needed)",
-                   "n_instances": n_inst, "n_distinct": st["n_distinct"], "n_solid": st["n_solid"], "n_kmers": st["n_kmers"],
-                   "n_v": st["n_v"], "n_e": st["n_e"],
-                   "parallelism": (f"{world} ranks: reads split 1/{world} per rank, (k+1)-mer buckets hash-partitioned to owner GPUs "
-                                   f"(k_count_buckets reads every rank's records through NVLink peer loads); graph stage two-level: every rank "
-                                   f"contracts its own solid (k+1)-mers into unbranched paths, the paths are pulled over NVLink (k_gather_paths), "
-                                   f"the path-level global stage runs on every rank; the solid set stays sharded over its owners") if world > 1 else
-                                  "1 gpu; graph stage two-level (k_contract inside the bucket groups, then the path-level global stage)"},
+        "config": {"workload": wstr},
+        "timed_region": f"{n_total} ASCII stream bytes resident in HBM (> L2, no flush needed) -> flat graph arrays in HBM",
+        "result": {"n_instances": n_inst, "n_distinct": st["n_distinct"], "n_solid": st["n_solid"], "n_kmers": st["n_kmers"],
+                   "n_v": st["n_v"], "n_e": st["n_e"], "digest": digest},
+        "parallelism": (f"{world} ranks: reads split 1/{world} per rank, (k+1)-mer buckets hash-partitioned to owner GPUs "
+                        f"(k_count_buckets reads every rank's records through NVLink peer loads); graph stage two-level: every rank "
+                        f"contracts its own solid (k+1)-mers into unbranched paths, the paths are pulled over NVLink (k_gather_paths), "
+                        f"the path-level global stage runs on every rank; the solid set stays sharded over its owners") if world > 1 else
+                       "1 gpu; graph stage two-level (k_contract inside the bucket groups, then the path-level global stage)",
         "stage_ms": {"count": count_ms, "graph": ms_graph / args.steps},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": TRAFFIC.get(top), "kernel": top, "ms_per_launch": top_ms,
-                     "algorithmic_bytes": top_bytes, "peak_source": peak_src,
+        # the fraction is taken on the WHOLE path (T_core), algorithmic bytes / step time / HBM peak
+        "roofline": {"bound": "hbm", "achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
+                     "traffic": traffic_all, "scope": "whole path (count + graph), SURVEY.md §8d T_core",
+                     "algorithmic_bytes": b_count + b_graph, "peak_source": peak_src, "dominant_kernel": top,
                      "count_stage": {"achieved": b_count / (count_ms * 1e-3) / 1e9, "frac": b_count / (count_ms * 1e-3) / 1e9 / peak,
-                                     "algorithmic_bytes": b_count},
-                     "whole_path": {"achieved": (b_count + b_graph) / (ms_step * 1e-3) / 1e9,
-                                    "frac": (b_count + b_graph) / (ms_step * 1e-3) / 1e9 / peak}},
-        "e2e": {"value": st_e["n_instances"] / (ms_e2e / args.steps * 1e-3), "unit": "kmers/s",
-                "h2d_bytes_per_step": n_total if h_packed is None else h2d_packed, "d2h_bytes_per_step": 8 * 140 * world,
-                "ms_per_step": ms_e2e / args.steps, "host_format": args.host_format,
-                "n_solid": st_e["n_solid"], "n_e": st_e["n_e"]},
+                                     "algorithmic_bytes": b_count}},
         "gpu_launches": launches,
         "kernels": kernels,
         "clocks": sampler.summary(),
     }
+    e_ascii = {"value": n_inst / (ms_e2e_ascii / args.steps * 1e-3), "unit": "kmers/s", "h2d_bytes_per_step": h2d_ascii,
+               "d2h_bytes_per_step": e2e_stream["ascii"][1], "ms_per_step": ms_e2e_ascii / args.steps,
+               "what": "pinned host ASCII read stream -> H2D -> build -> whole flat graph D2H into pinned host arrays (CUDA events)"}
+    e_packed = {"value": n_inst / (ms_e2e_packed / args.steps * 1e-3), "unit": "kmers/s", "h2d_bytes_per_step": h2d_packed,
+                "d2h_bytes_per_step": e2e_stream["packed"][1], "ms_per_step": ms_e2e_packed / args.steps,
+                "what": "same from the PACKED host stream (include/tagpu.h; 2-bit packing done by the ingest side, outside the timed region)"}
+    line["e2e_host_stream"] = e_ascii
+    line["e2e_host_stream_packed"] = e_packed
     if world == 1 and not args.no_files:
-        fe = files_e2e(torch, h_stream, k)
-        fe["value"] = n_inst / (fe["ms_per_step"] * 1e-3)
-        fe["unit"] = "kmers/s"
-        line["e2e_files"] = fe
+        fe = files_e2e(h_stream, k, min(args.steps, 10))
+        line["e2e"] = {"value": n_inst / (fe["ms_per_step"] * 1e-3), "unit": "kmers/s", "h2d_bytes_per_step": n_stream,
+                       "d2h_bytes_per_step": e2e_stream["ascii"][1], "ms_per_step": fe["ms_per_step"], "steps": min(args.steps, 10),
+                       "what": fe["what"], "threads": fe["threads"], "fastq_bytes": fe["fastq_bytes"], "n_e": fe["n_e"],
+                       "same_boundary_as_reference_arm": "input yes (the same FASTQ files); output: struct asm_graph_t in memory, the reference arm also writes the .bin"}
+    else:
+        line["e2e"] = dict(e_ascii)     # multi-GPU: no files entry point; reads start in each rank's pinned host memory
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = reference_cpu(args.workload, 2, 1)[0]
+        line["cpu_baseline"] = reference_cpu(args.workload, 1, 0, h_stream.numpy())[0]
     print(json.dumps(line))
 
 

@@ -80,8 +80,8 @@ void tagpu_set_cutoff(tagpu_ctx *ctx, int ci);
 void tagpu_set_skip_counts(tagpu_ctx *ctx, int skip);
 const char *tagpu_last_error(tagpu_ctx *ctx);
 /* 1 = two-level graph stage: the solid (k+1)-mers are first contracted into paths inside the bucket groups of the count stage
- * (csrc/tagpu_contract.cuh); same graph, but tagpu_copy_kmers is then unavailable (hidden k-mers never reach the table).
- * Single-GPU builds without contig garbage only; everything else uses the one-level stage. */
+ * (csrc/tagpu_contract.cuh); same graph (tagpu_copy_kmers rebuilds the full k-mer table on demand: hidden k-mers never reach
+ * the stage's own table).  Builds with contig garbage (local assembly) always use the one-level stage. */
 void tagpu_set_contract(tagpu_ctx *ctx, int on);
 /* per-kernel CUDA-event timing of the next builds: JSON {"kernel": {"ms": total, "launches": n}, ...} */
 void tagpu_set_profile(tagpu_ctx *ctx, int on);
@@ -132,8 +132,15 @@ struct tagpu_flat_graph {
 };
 int tagpu_copy_graph(tagpu_ctx *ctx, struct tagpu_flat_graph *host_arrays);
 
+/* Order-independent digests of the last build, computed on the device (csrc/tagpu_digest.cuh; same function on the CPU:
+ * oracle/canon_dump.c ora_bin_digest, tests/_digest.py).  out[0..1] sum / xor over the solid (k+1)-mers this context holds,
+ * out[2] how many, out[3] 1 = the whole set / 0 = this rank's share of a sharded multi-GPU build (shares add up);
+ * out[4..5] sum / xor over all edges (length, count, 2-bit sequence), out[6] sum of lengths, out[7] sum of counts, out[8] n_e. */
+int tagpu_digest(tagpu_ctx *ctx, uint64_t out[9]);
+
 /* Host-side materialisation of the last build (tagpu_host.c) */
 int tagpu_fill_asm_graph(tagpu_ctx *ctx, struct asm_graph_t *g);   /* individually malloc'ed seq/adj, SURVEY.md §8b */
+void tagpu_free_asm_graph(struct asm_graph_t *g);                  /* frees a graph filled by tagpu_fill_asm_graph / the level-2 entry points */
 int tagpu_write_graph_bin(tagpu_ctx *ctx, const char *path);       /* save_asm_graph layout, assembly_graph.c:1173-1248 */
 int tagpu_write_kmc_db(tagpu_ctx *ctx, const char *working_dir);   /* KMC_<K>_count.kmc_pre/.kmc_suf of the last count */
 

@@ -172,3 +172,66 @@ int ora_canon_dump(const char *bin_path, const char *out_path, int mode)
 	free(lines); free(seen); free(E); free(n_adj); free(n_rc); free(n_deg); free(buf);
 	return n_bad;
 }
+
+/* ------------------------------------------------------------------ order-independent digest of a graph .bin
+ * CPU restatement of the edge digest libtagpu computes on the device (csrc/tagpu_digest.cuh), evaluated on a .bin in
+ * the save_asm_graph layout — e.g. the reference's own graph_k_<k>_level_0.bin — so that a full-size GPU result can be
+ * compared with the reference without sorting 10^5..10^7 unitigs.  out = { sum, xor, sum of lengths, sum of counts, n_e }. */
+static uint64_t dg_mix64(uint64_t x)
+{
+	x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+	x ^= x >> 27; x *= 0x94d049bb133111ebull;
+	x ^= x >> 31;
+	return x;
+}
+
+int ora_bin_digest(const char *bin_path, uint64_t out[5])
+{
+	FILE *fp = fopen(bin_path, "rb");
+	if (!fp) { perror(bin_path); return -1; }
+	fseek(fp, 0, SEEK_END);
+	long fsz = ftell(fp);
+	fseek(fp, 0, SEEK_SET);
+	uint8_t *buf = malloc(fsz + 8);
+	if (!buf || fread(buf, 1, fsz, fp) != (size_t)fsz) { fclose(fp); free(buf); return -1; }
+	fclose(fp);
+	if (fsz < 28 || memcmp(buf, "asmg", 4)) { free(buf); return -2; }
+	const uint8_t *p = buf + 12, *end = buf + fsz;
+	int64_t n_v, n_e;
+	memcpy(&n_v, p, 8); p += 8;
+	memcpy(&n_e, p, 8); p += 8;
+	for (int64_t u = 0; u < n_v && p + 16 <= end; ++u) {
+		int64_t deg;
+		memcpy(&deg, p + 8, 8);
+		p += 16 + 8 * deg;
+	}
+	uint64_t sum = 0, x = 0, tl = 0, tc = 0, live = 0;
+	for (int64_t e = 0; e < n_e; ++e) {
+		if (p + 16 > end) { free(buf); return -2; }
+		int64_t src;
+		memcpy(&src, p, 8);
+		p += 16;
+		if (src == -1) continue;
+		uint64_t count, len8;
+		memcpy(&count, p + 8, 8);
+		memcpy(&len8, p + 16, 8);
+		p += 24;
+		const uint32_t len = (uint32_t)len8, nw = (len + 15) >> 4;
+		if (p + 4 * (size_t)nw + 4 > end) { free(buf); return -2; }
+		uint64_t hw = 0;
+		for (uint32_t i = 0; i < nw; ++i) {
+			uint32_t w;
+			memcpy(&w, p + 4 * (size_t)i, 4);
+			hw += dg_mix64((uint64_t)w ^ (0x9E3779B97F4A7C15ull * (uint64_t)(i + 1)));
+		}
+		p += 4 * (size_t)nw;
+		uint32_t n_holes;
+		memcpy(&n_holes, p, 4);
+		p += 4 + 8 * (size_t)n_holes;
+		const uint64_t d = dg_mix64(hw ^ dg_mix64(((uint64_t)len << 32) ^ (count * 0xC2B2AE3D27D4EB4Full)));
+		sum += d; x ^= d; tl += len; tc += count; ++live;
+	}
+	free(buf);
+	out[0] = sum; out[1] = x; out[2] = tl; out[3] = tc; out[4] = live;
+	return 0;
+}

@@ -58,6 +58,9 @@ int ora_graph_save_bin(const struct ora_graph *g, const char *path);
 /* Loads an App. C .bin, checks its structural invariants, writes the sorted canonical
  * lines to out_path.  Returns 0 on success, >0 = number of invariant violations, <0 I/O. */
 int ora_canon_dump(const char *bin_path, const char *out_path, int with_topology);
+/* Order-independent digest of the edges of a .bin (same function as libtagpu's tagpu_digest, csrc/tagpu_digest.cuh):
+ * out = { sum, xor, sum of lengths, sum of counts, live edges }.  Returns 0 or <0 on I/O / format errors. */
+int ora_bin_digest(const char *bin_path, uint64_t out[5]);
 
 #ifdef __cplusplus
 }

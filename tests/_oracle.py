@@ -42,6 +42,8 @@ class Oracle:
         lib.ora_graph_save_bin.argtypes = [C.POINTER(OraGraph), C.c_char_p]
         lib.ora_canon_dump.restype = C.c_int
         lib.ora_canon_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        lib.ora_bin_digest.restype = C.c_int
+        lib.ora_bin_digest.argtypes = [C.c_char_p, C.POINTER(C.c_uint64)]
         lib.ora_load_reads.restype = C.c_int64
         lib.ora_load_reads.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p)]
 
@@ -87,6 +89,12 @@ class Oracle:
     def canon(self, bin_path, out_path, mode=0):
         """returns number of structural violations (0 = valid graph)"""
         return self.lib.ora_canon_dump(os.fsencode(bin_path), os.fsencode(out_path), mode)
+
+    def bin_digest(self, bin_path):
+        """Order-independent edge digest of a .bin (oracle/canon_dump.c) in the vocabulary of Tagpu.digest()."""
+        out = (C.c_uint64 * 5)()
+        assert self.lib.ora_bin_digest(os.fsencode(bin_path), out) == 0
+        return {"edge_sum": out[0], "edge_xor": out[1], "edge_len_sum": out[2], "edge_count_sum": out[3], "n_e": out[4]}
 
     def load_reads(self, files):
         arr = (C.c_char_p * len(files))()

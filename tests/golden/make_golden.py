@@ -96,5 +96,20 @@ def make_local_golden(ora):
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+def make_struct_layout():
+    """tests/golden/struct_layout.txt: sizeof / offsetof of the reference's graph structs, printed by a C program compiled
+    against the reference's own headers (tests/test_abi.py compares include/tagpu_graph.h with it, and never rewrites it)."""
+    import pathlib
+    import test_abi
+    with tempfile.TemporaryDirectory() as td:
+        ref = test_abi._layout(pathlib.Path(td), "ref", '#include "assembly_graph.h"\n#include "attribute.h"',
+                               ["-I", test_abi.REF, "-I", os.path.join(test_abi.REF, "src")])
+    with open(os.path.join(HERE, "struct_layout.txt"), "w") as f:
+        f.write(ref)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "layout":
+        make_struct_layout()
+    else:
+        main()

@@ -92,8 +92,9 @@ def test_struct_layout_matches_reference(tmp_path):
     if os.path.isdir(os.path.join(REF, "src")):
         ref = _layout(tmp_path, "ref", '#include "assembly_graph.h"\n#include "attribute.h"',
                       ["-I", REF, "-I", os.path.join(REF, "src")])
-        if not os.path.exists(GOLDEN_LAYOUT) or open(GOLDEN_LAYOUT).read() != ref:
-            open(GOLDEN_LAYOUT, "w").write(ref)  # golden fixture regenerated from the reference headers
+        # the committed fixture (written once by tests/golden/make_golden.py from the reference headers) is never rewritten
+        # here: where the reference is mounted it must still agree with the headers, everywhere it pins our layout
+        assert ref == open(GOLDEN_LAYOUT).read(), "tests/golden/struct_layout.txt no longer matches the reference headers"
         assert ours == ref
     assert ours == open(GOLDEN_LAYOUT).read()
     # the ctypes mirror used by the tests agrees too

@@ -131,3 +131,81 @@ def test_full_size_two_level_equals_one_level(tagpu, k):
         assert st1[f] == st2[f], f
     for a, b in zip(fp1, fp2):
         assert np.array_equal(a, b)
+
+
+def _ref_log_counters(text):
+    """The reference's known-answer log lines (kmer_build.c:758,763,772; assembly_graph.c:1003)."""
+    import re
+    out = {}
+    for name, pat in (("n_kmers", r"Number of kmer: (\d+)"), ("n_v", r"kmer_build\.c:763.*Number of nodes: (\d+)"),
+                      ("n_e", r"kmer_build\.c:763.*Number of edges: (\d+)"), ("n_kp1_on_edge", r"Number of \(k\+1\)-mer on edge: (\d+)"),
+                      ("sum_count", r"sum_count = (\d+)")):
+        m = re.search(pat, text)
+        assert m, f"reference log lacks {name}"
+        out[name] = int(m.group(1))
+    return out
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_full_size_parity_with_reference(tagpu, oracle, name):
+    """BASELINE.json configs[0] / configs[1] at FULL size, bit-exact against the unmodified reference: the bench generator's
+    read set is written as FASTQ, `oracle/_ref/TA_ref build_0 -t $(nproc)` builds graph_k_<k>_level_0.bin from it
+    (/root/reference/src/kmer_build.c:714-786 behind src/process.c:47), and the GPU result must give the same canonical
+    dumps (unitigs and topology), the same log counters, the same solid set with counts as
+    ora_count_stream, and the digest bench.py prints must equal the digest of the reference's .bin (and the committed one)."""
+    import json
+    import shutil
+    import subprocess
+    import tempfile
+    import torch
+    import _digest
+    import _oracle
+    import bench
+    assert os.path.exists(_oracle.TA_REF), "oracle/_ref/TA_ref is missing: run __graft_entry__.build() where /root/reference is mounted"
+    wl = bench.WORKLOADS[name]
+    k = wl["k"]
+    d = bench.gen_reads_gpu(torch, wl, torch.device("cuda", 0))
+    h = d.cpu().numpy()
+    td = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        f1, f2 = bench.write_fastq_pair(h, td)
+        out = os.path.join(td, "ref")
+        os.makedirs(out)
+        p = subprocess.run([_oracle.TA_REF, "build_0", "-1", f1, "-2", f2, "-l", "ust", "-k0", str(k), "-t", str(os.cpu_count() or 4), "-o", out],
+                           capture_output=True, text=True)
+        assert p.returncode == 0, (p.stdout + p.stderr)[-2000:]
+        ref = _ref_log_counters(p.stdout + p.stderr)
+        ref_bin = os.path.join(out, f"graph_k_{k}_level_0.bin")
+        tagpu.set_cutoff(2)
+        st = tagpu.build_device(d.data_ptr(), d.numel(), k)
+        assert (st["n_kmers"], st["n_v"], st["n_e"], st["n_kp1_on_edge"]) == (ref["n_kmers"], ref["n_v"], ref["n_e"], ref["n_kp1_on_edge"])
+        g = tagpu.graph()
+        rc = g["e_rc"].astype(np.int64)
+        assert int(g["e_count"][np.arange(g["n_e"]) <= rc].sum(dtype=np.uint64)) == ref["sum_count"]
+        gpu_bin = os.path.join(td, "gpu.bin")
+        tagpu.write_graph_bin(gpu_bin)
+        for mode in (0, 1):
+            bad_r, txt_r = _oracle.canon_text(oracle, ref_bin, mode)
+            bad_g, txt_g = _oracle.canon_text(oracle, gpu_bin, mode)
+            assert bad_r == 0 and bad_g == 0
+            assert txt_r == txt_g, f"canonical dump (mode {mode}) differs from the reference's"
+            del txt_r, txt_g
+        # solid set with counts
+        want = oracle.count(h, k + 1, ci=2, threads=os.cpu_count() or 4)
+        hi, lo, cnt = tagpu.solid()
+        o = np.lexsort((lo, hi))
+        assert st["n_instances"] == want["n_instances"] and st["n_distinct"] == want["n_distinct"]
+        assert np.array_equal(hi[o], want["hi"]) and np.array_equal(lo[o], want["lo"]) and np.array_equal(cnt[o], want["count"])
+        # digests: device == reference's .bin == oracle's solid set == committed golden
+        dg = tagpu.digest()
+        ref_dg = oracle.bin_digest(ref_bin)
+        assert all(dg[f] == ref_dg[f] for f in ref_dg), (dg, ref_dg)
+        want_s = _digest.solid_digest(want["hi"], want["lo"], want["count"])
+        assert all(dg[f] == want_s[f] for f in want_s)
+        gold_path = os.path.join(ROOT, "tests", "golden", "digest_fullsize.json")
+        gold = json.load(open(gold_path)).get(name) if os.path.exists(gold_path) else None
+        print(f"DIGEST {name}: " + json.dumps({f: dg[f] for f in sorted(dg)}))
+        if gold:
+            assert all(dg[f] == gold[f] for f in gold), (dg, gold)
+    finally:
+        shutil.rmtree(td, ignore_errors=True)

@@ -52,6 +52,13 @@ def check_against_oracle(tagpu, oracle, stream, k, tmp_path, tag="x", ci=2):
         bad_g, txt_g = _oracle.canon_text(oracle, gpu_bin, mode)
         assert bad_o == 0 and bad_g == 0
         assert txt_o == txt_g
+    # 4. the order-independent digests bench.py prints (computed on the device) equal the oracle's
+    import _digest
+    dg = tagpu.digest()
+    want_s = _digest.solid_digest(want["hi"], want["lo"], want["count"])
+    assert dg["solid_complete"] and all(dg[f] == want_s[f] for f in want_s)
+    want_e = oracle.bin_digest(ora_bin)
+    assert all(dg[f] == want_e[f] for f in want_e)
     return st, gpu_bin
 
 

@@ -129,3 +129,37 @@ def test_oracle_vs_compiled_reference(oracle, name, k, tmp_path):
     ora_bin, _ = oracle_build(oracle, _reads.stream_of(r1, r2), k, tmp_path, "x")
     for mode in (0, 1):
         assert _oracle.canon_text(oracle, ref_bin, mode) == _oracle.canon_text(oracle, ora_bin, mode)
+
+
+def test_digest_restatements_agree(oracle, tmp_path):
+    """The edge digest has three statements: CUDA (csrc/tagpu_digest.cuh, checked on the GPU), C over a .bin
+    (oracle/canon_dump.c) and numpy over flat arrays (tests/_digest.py).  The two CPU ones must agree, and the digest must
+    not depend on edge numbering."""
+    import ctypes as C
+    import _digest
+    stream = _reads.gen_stream(40000, 3000, seed=21)
+    for k in (31, 45):
+        cnt = oracle.count(stream, k + 1)
+        g = oracle.graph(k, cnt["hi"], cnt["lo"], cnt["count"])
+        binp = str(tmp_path / f"d{k}.bin")
+        oracle.save_bin(g, binp)
+        gc = g.contents
+        n_e = gc.n_e
+        e_len = np.ctypeslib.as_array(gc.e_len, shape=(n_e,)).copy()
+        e_count = np.ctypeslib.as_array(gc.e_count, shape=(n_e,)).copy()
+        e_off = np.ctypeslib.as_array(C.cast(gc.e_seq_off, C.POINTER(C.c_uint64)), shape=(n_e,)).copy()
+        n_w = int((e_off + ((e_len.astype(np.uint64) + 15) >> 4)).max())
+        e_seq = np.ctypeslib.as_array(C.cast(gc.e_seq, C.POINTER(C.c_uint32)), shape=(n_w,)).copy()
+        oracle.free_graph(g)
+        a = oracle.bin_digest(binp)
+        b = _digest.edge_digest(e_len, e_count, e_off, e_seq)
+        assert a == b and a["n_e"] == n_e > 0
+        perm = np.random.default_rng(k).permutation(n_e)          # renumbered edges: same digest
+        assert _digest.edge_digest(e_len[perm], e_count[perm], e_off[perm], e_seq) == a
+        s1 = _digest.solid_digest(cnt["hi"], cnt["lo"], cnt["count"])
+        p2 = np.random.default_rng(k + 1).permutation(cnt["hi"].size)
+        assert _digest.solid_digest(cnt["hi"][p2], cnt["lo"][p2], cnt["count"][p2]) == s1
+        half = cnt["hi"].size // 2                                  # shares of a sharded set add up
+        sa = _digest.solid_digest(cnt["hi"][:half], cnt["lo"][:half], cnt["count"][:half])
+        sb = _digest.solid_digest(cnt["hi"][half:], cnt["lo"][half:], cnt["count"][half:])
+        assert (sa["solid_sum"] + sb["solid_sum"]) % (1 << 64) == s1["solid_sum"] and sa["solid_xor"] ^ sb["solid_xor"] == s1["solid_xor"]

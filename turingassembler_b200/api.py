@@ -152,8 +152,12 @@ def load_library() -> C.CDLL:
     lib.tagpu_copy_kmers.argtypes = [vp, vp, vp, vp]
     lib.tagpu_copy_graph.restype = i32
     lib.tagpu_copy_graph.argtypes = [vp, C.POINTER(FlatGraph)]
+    lib.tagpu_digest.restype = i32
+    lib.tagpu_digest.argtypes = [vp, C.POINTER(u64)]
     lib.tagpu_fill_asm_graph.restype = i32
     lib.tagpu_fill_asm_graph.argtypes = [vp, C.POINTER(AsmGraph)]
+    lib.tagpu_free_asm_graph.restype = None
+    lib.tagpu_free_asm_graph.argtypes = [C.POINTER(AsmGraph)]
     lib.tagpu_write_graph_bin.restype = i32
     lib.tagpu_write_graph_bin.argtypes = [vp, C.c_char_p]
     lib.tagpu_write_kmc_db.restype = i32
@@ -385,6 +389,18 @@ class Tagpu:
         out.update({name: a[: {"node_mask": nn, "node_ebase": nn, "e_seq": nw}.get(name, ne)] for name, a in arrs.items()})
         return out
 
+    def digest(self) -> dict:
+        """Order-independent digests of the last build, computed on the device (tagpu_digest, include/tagpu.h)."""
+        out = (C.c_uint64 * 9)()
+        self._check(self.lib.tagpu_digest(self.ctx, out))
+        return {"solid_sum": out[0], "solid_xor": out[1], "solid_n": out[2], "solid_complete": bool(out[3]),
+                "edge_sum": out[4], "edge_xor": out[5], "edge_len_sum": out[6], "edge_count_sum": out[7], "n_e": out[8]}
+
+    def copy_graph_into(self, fg: "FlatGraph"):
+        """tagpu_copy_graph into caller-owned (e.g. pinned) host arrays described by a FlatGraph of addresses."""
+        self._check(self.lib.tagpu_copy_graph(self.ctx, C.byref(fg)))
+        return fg
+
     def write_graph_bin(self, path: str):
         self._check(self.lib.tagpu_write_graph_bin(self.ctx, os.fsencode(path)))
 
@@ -440,6 +456,11 @@ def pack_stream(stream, threads: int = 8, out: np.ndarray | None = None) -> np.n
         raise TagpuError("tagpu_pack_stream failed (host and device tile layouts disagree)")
     del keep
     return out
+
+
+def free_asm_graph(g: AsmGraph):
+    """Releases a graph returned by build_graph_from_scratch / Tagpu.fill_asm_graph (tagpu_free_asm_graph)."""
+    load_library().tagpu_free_asm_graph(C.byref(g))
 
 
 def free_reads(addr: int):

@@ -604,6 +604,25 @@ int tagpu_fill_asm_graph(tagpu_ctx *ctx, struct asm_graph_t *g)
 	return 0;
 }
 
+/* Releases what tagpu_fill_asm_graph (or one of the reference entry points above it) allocated, block by block like the
+ * reference's asm_graph_destroy (/root/reference/src/assembly_graph.c:1459-1480); the struct itself stays the caller's. */
+void tagpu_free_asm_graph(struct asm_graph_t *g)
+{
+	if (!g) return;
+	for (gint_t u = 0; g->nodes && u < g->n_v; ++u)
+		free(g->nodes[u].adj);
+	for (gint_t e = 0; g->edges && e < g->n_e; ++e) {
+		free(g->edges[e].seq);
+		free(g->edges[e].p_holes);
+		free(g->edges[e].l_holes);
+	}
+	free(g->nodes);
+	free(g->edges);
+	g->nodes = NULL;
+	g->edges = NULL;
+	g->n_v = g->n_e = 0;
+}
+
 /* save_asm_graph layout (/root/reference/src/assembly_graph.c:1173-1248), streamed straight from the
  * flat arrays without building the pointer-rich struct. */
 int tagpu_write_graph_bin(tagpu_ctx *ctx, const char *path)

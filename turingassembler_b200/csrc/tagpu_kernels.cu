@@ -14,7 +14,7 @@
 #include "../../include/tagpu.h"
 #include "tagpu_contract.cuh"
 #include "tagpu_count.cuh"
-#include "tagpu_count_v1.cuh"
+#include "tagpu_digest.cuh"
 #include "tagpu_extract.cuh"
 #include "tagpu_graph.cuh"
 #include "tagpu_key.cuh"
@@ -45,11 +45,13 @@ struct tagpu_ctx {
 	Buf regions, cursor, overflow, overflow_bucket, ext, ext_off, ext_count, cur_all, ext_all, pex, bsum, grp_end;
 	uint64_t count_stream_bytes = 0;   // bytes of the WHOLE read stream of the current build (all ranks)
 	int n_sm = 0, jump_grid = 0;
-	Buf chain_slot, grp_start;
-	Buf seq, ctab, clist, solid_key, solid_cnt, kt_keys, kt_mask, node_ord, node_slot, node_ebase, vL, vR, jump, vsucc,
+	// per-device launch state (a process may hold contexts on several devices)
+	bool attr_done[3] = { false, false, false };
+	int grid_s[3] = { 0, 0, 0 }, grid_m[3] = { 0, 0, 0 }, grid_l[3] = { 0, 0, 0 };
+	uint64_t n_solid_local = 0;        // entries of the solid list THIS context holds (= st.n_solid unless the set is sharded)
+	Buf chain_slot, grp_start, node_mask;
+	Buf seq, solid_key, solid_cnt, kt_keys, kt_mask, node_ord, node_slot, node_ebase, vL, vR, jump, vsucc,
 		vedge, e_src, e_dst, e_rc, e_len, e_count, e_off, e_seq;
-	uint64_t ctab_slots = 0;
-	int ctab_W = 0;
 	uint32_t kt_slots = 0;
 	bool have_count = false, have_graph = false;
 	void *cur_solid_key = nullptr, *cur_solid_cnt = nullptr; // solid set the graph stage reads (local, or gathered from all ranks)
@@ -168,12 +170,6 @@ static int ensure_slack(tagpu_ctx *ctx, Buf &b, size_t bytes)
 
 static int ensure_exact(tagpu_ctx *ctx, Buf &b, size_t bytes) { return ensure(ctx, b, bytes); }
 
-static uint64_t pow2_at_least(uint64_t x)
-{
-	uint64_t p = 1;
-	while (p < x) p <<= 1;
-	return p;
-}
 
 extern "C" tagpu_ctx *tagpu_create(int device)
 {
@@ -213,7 +209,7 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	dist_release(ctx);
-	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->blocks, &ctx->blk_defer, &ctx->d_first, &ctx->d_last, &ctx->d_n, &ctx->d_cnt, &ctx->d_off, &ctx->d_int, &ctx->wlast, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->hj_own, &ctx->hj_bits, &ctx->hj_list, &ctx->hj_jump2, &ctx->chain_slot, &ctx->grp_start, &ctx->seq, &ctx->ctab, &ctx->clist, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->blocks, &ctx->blk_defer, &ctx->d_first, &ctx->d_last, &ctx->d_n, &ctx->d_cnt, &ctx->d_off, &ctx->d_int, &ctx->wlast, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->hj_own, &ctx->hj_bits, &ctx->hj_list, &ctx->hj_jump2, &ctx->chain_slot, &ctx->grp_start, &ctx->node_mask, &ctx->seq, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
 			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
 	for (Buf *b : bufs)
@@ -252,46 +248,6 @@ static int read_counters(tagpu_ctx *ctx)
 		++ctx->launches;                                                           \
 		CU(cudaGetLastError());                                                    \
 	} while (0)
-
-// ------------------------------------------------------------------------------------------------ count stage
-template <int W>
-static int count_stage(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n)
-{
-	const int K = ctx->K;
-	uint64_t slots = pow2_at_least(n / 2 + 1024);
-	if (slots < (1ull << 20)) slots = 1ull << 20;
-	if (slots > (1ull << 32)) return fail(ctx, "input too large for the direct count table (%llu bytes)", (unsigned long long)n);
-	bool grew;
-	if (ensure(ctx, ctx->ctab, slots * sizeof(CSlot<W>), &grew)) return -1;
-	if (grew || ctx->ctab_W != W || ctx->ctab_slots != slots) {
-		{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->ctab.p, 0, ctx->ctab.cap, ctx->stream)); } // once; afterwards kept clean by k_compact_solid
-		ctx->ctab_W = W;
-		ctx->ctab_slots = slots;
-	}
-	if (ensure(ctx, ctx->clist, (n + 1024) * sizeof(uint32_t))) return -1;
-	const uint64_t n_tiles = (n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES;
-	if (n_tiles)
-		LAUNCH(k_count_direct<W>, (unsigned)n_tiles, TAGPU_TILE_THREADS, d_seq, n, K, (CSlot<W> *)ctx->ctab.p, slots - 1,
-		       (uint32_t *)ctx->clist.p, ctx->d_ctr);
-	if (read_counters(ctx)) return -1;
-	const uint64_t n_distinct = ctx->h_ctr[CTR_DISTINCT];
-	if (ensure(ctx, ctx->solid_key, (n_distinct + 1) * sizeof(Key<W>))) return -1;
-	if (ensure(ctx, ctx->solid_cnt, (n_distinct + 1) * sizeof(uint32_t))) return -1;
-	if (n_distinct)
-		LAUNCH(k_compact_solid<W>, (unsigned)((n_distinct + 1023) / 1024), 1024, (CSlot<W> *)ctx->ctab.p,
-		       (const uint32_t *)ctx->clist.p, ctx->d_ctr, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p,
-		       (uint32_t *)ctx->solid_cnt.p, ctx->d_ctr);
-	if (read_counters(ctx)) return -1;
-	ctx->st.n_instances = ctx->h_ctr[CTR_INSTANCES];
-	ctx->st.n_distinct = n_distinct;
-	ctx->st.n_solid = ctx->h_ctr[CTR_SOLID];
-	ctx->st.sum_solid = ctx->h_ctr[CTR_SUM_SOLID];
-	ctx->cur_solid_key = ctx->solid_key.p;
-	ctx->cur_solid_cnt = ctx->solid_cnt.p;
-	ctx->have_count = true;
-	return 0;
-}
-
 
 // ------------------------------------------------------------------------------------------------ count stage (partitioned)
 #define LAUNCH_SMEM(kernel, grid, block, smem, ...)                                        \
@@ -339,7 +295,7 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 	cfg.packed = ctx->src_packed ? 1u : 0u;
 	const uint32_t n_buckets = 1u << cfg.log2_buckets;
 	const size_t smem1 = TAGPU_SMEM_WORDS * 8 + 3 * (size_t)TAGPU_SMEM_WORDS * 4 + 2 * (size_t)TAGPU_HM_LEN * 4;
-	static bool attr_done[3] = { false, false, false };
+	bool *attr_done = ctx->attr_done;
 	if (!attr_done[W]) {
 		CU(cudaFuncSetAttribute(k_partition<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
 		CU(cudaFuncSetAttribute(k_count_buckets<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BC::SMEM));
@@ -443,6 +399,7 @@ static int count_owned(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &
 	ctx->st.n_solid = ctx->h_ctr[CTR_SOLID];
 	ctx->st.sum_solid = ctx->h_ctr[CTR_SUM_SOLID];
 	ctx->n_blocks = ctx->h_ctr[CTR_BLOCKS];
+	ctx->n_solid_local = ctx->st.n_solid;
 	ctx->log2_buckets = cfg.log2_buckets;
 #ifdef TAGPU_TIMING
 	{
@@ -679,7 +636,7 @@ static int contract_local(tagpu_ctx *ctx, const PathStore<W> &ps)
 	auto k_small = k_contract<W, CC::MAXN_SMALL, CC::T_SMALL>;
 	auto k_medium = k_contract<W, CC::MAXN_MEDIUM, CC::T_MEDIUM>;
 	auto k_large = k_contract<W, CC::MAXN_LARGE, CC::T_LARGE>;
-	static int grid_s[3] = { 0, 0, 0 }, grid_m[3] = { 0, 0, 0 }, grid_l[3] = { 0, 0, 0 };
+	int *grid_s = ctx->grid_s, *grid_m = ctx->grid_m, *grid_l = ctx->grid_l;
 	if (!grid_s[W]) {
 		CU(cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
 		CU(cudaFuncSetAttribute(k_medium, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
@@ -855,9 +812,7 @@ static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool wit
 	if (!ctx->local_mode) { ctx->n_garbage = 0; ctx->n_contigs = 0; }
 	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->d_ctr, 0, CTR_TOTAL * sizeof(unsigned long long), ctx->stream)); }
 	CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-	static const bool direct = getenv("TAGPU_COUNT_DIRECT") != nullptr; // bring-up cross-check only
-	int rc = direct ? (ctx->W == 1 ? count_stage<1>(ctx, d_seq, n) : count_stage<2>(ctx, d_seq, n))
-			: (ctx->W == 1 ? count_stage_partitioned<1>(ctx, d_seq, n) : count_stage_partitioned<2>(ctx, d_seq, n));
+	int rc = ctx->W == 1 ? count_stage_partitioned<1>(ctx, d_seq, n) : count_stage_partitioned<2>(ctx, d_seq, n);
 	if (rc) return rc;
 	CU(cudaEventRecord(ctx->ev[1], ctx->stream));
 	if (with_graph && ctx->n_garbage) {
@@ -875,7 +830,7 @@ static int run(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, int K, bool wit
 		ctx->cur_solid_cnt = ctx->comb_cnt.p;
 	}
 	ctx->contracted = false;
-	if (with_graph && ctx->contract && !ctx->n_garbage && ctx->n_blocks && !direct) {
+	if (with_graph && ctx->contract && !ctx->n_garbage && ctx->n_blocks) {
 		rc = ctx->W == 1 ? graph_stage_paths<1>(ctx) : graph_stage_paths<2>(ctx);
 		if (rc) return rc;
 	} else if (with_graph) {
@@ -1261,12 +1216,7 @@ static int upload(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n)
 {
 	CU(cudaSetDevice(ctx->device));
 	if (ensure(ctx, ctx->seq, n + 64)) return -1;
-	static const bool direct = getenv("TAGPU_COUNT_DIRECT") != nullptr;
-	if (direct) {
-		if (n) CU(cudaMemcpyAsync(ctx->seq.p, h_seq, n, cudaMemcpyHostToDevice, ctx->stream));
-	} else {
-		ctx->h_src = h_seq;            // uploaded chunk by chunk inside partition_local, overlapped with pass 1
-	}
+	ctx->h_src = h_seq;                    // uploaded chunk by chunk inside partition_local, overlapped with pass 1
 	return 0;
 }
 
@@ -1302,8 +1252,6 @@ extern "C" uint64_t tagpu_packed_bytes(uint64_t n_positions)
 }
 static int run_packed(tagpu_ctx *ctx, const uint8_t *d_packed, uint64_t n_positions, int K, bool with_graph)
 {
-	static const bool direct = getenv("TAGPU_COUNT_DIRECT") != nullptr;
-	if (direct) return fail(ctx, "TAGPU_COUNT_DIRECT (bring-up cross-check) reads ASCII streams only");
 	ctx->src_packed = true;
 	const int rc = run(ctx, d_packed, n_positions, K, with_graph);
 	ctx->src_packed = false;
@@ -1467,6 +1415,38 @@ extern "C" int tagpu_copy_kmers(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint
 	return copy_table_entries(ctx, ctx->kt_keys.p, ctx->kt_mask.p, ctx->kt_slots, hi, lo, mask);
 }
 
+// Order-independent digests of the last build (csrc/tagpu_digest.cuh), computed on the device:
+//   out[0], out[1]  sum / xor over the solid (k+1)-mers this context holds; out[2] = how many those are;
+//   out[3]          1 if they are the whole solid set, 0 if only this rank's share of a sharded multi-GPU build
+//                   (sums and xors of the ranks then add up to the digest of the whole set);
+//   out[4], out[5]  sum / xor over all edges; out[6] = sum of edge lengths, out[7] = sum of edge counts, out[8] = n_e.
+extern "C" int tagpu_digest(tagpu_ctx *ctx, uint64_t out[9])
+{
+	if (!ctx->have_count) return fail(ctx, "no result to digest");
+	CU(cudaSetDevice(ctx->device));
+	unsigned long long *d = nullptr;
+	CU(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
+	CU(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), ctx->stream));
+	const uint64_t n_s = ctx->solid_sharded ? ctx->n_solid_local : ctx->st.n_solid;
+	const void *key = ctx->solid_sharded ? ctx->solid_key.p : ctx->cur_solid_key;
+	const void *cnt = ctx->solid_sharded ? ctx->solid_cnt.p : ctx->cur_solid_cnt;
+	if (n_s) {
+		if (ctx->W == 1) k_digest_solid<1><<<4 * ctx->n_sm, 256, 0, ctx->stream>>>((const Key<1> *)key, (const uint32_t *)cnt, n_s, d);
+		else k_digest_solid<2><<<4 * ctx->n_sm, 256, 0, ctx->stream>>>((const Key<2> *)key, (const uint32_t *)cnt, n_s, d);
+	}
+	if (ctx->have_graph && ctx->st.n_e)
+		k_digest_edges<<<4 * ctx->n_sm, 256, 0, ctx->stream>>>((const uint32_t *)ctx->e_len.p, (const unsigned long long *)ctx->e_count.p,
+									(const unsigned long long *)ctx->e_off.p, (const uint32_t *)ctx->e_seq.p, ctx->st.n_e, d + 4);
+	unsigned long long h[8];
+	cudaError_t e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	cudaFree(d);
+	if (e != cudaSuccess) return fail(ctx, "digest failed: %s", cudaGetErrorString(e));
+	out[0] = h[0]; out[1] = h[1]; out[2] = n_s; out[3] = ctx->solid_sharded ? 0 : 1;
+	out[4] = h[4]; out[5] = h[5]; out[6] = h[6]; out[7] = h[7]; out[8] = ctx->have_graph ? ctx->st.n_e : 0;
+	return 0;
+}
+
 extern "C" int tagpu_copy_graph(tagpu_ctx *ctx, struct tagpu_flat_graph *h)
 {
 	if (!ctx->have_graph) return fail(ctx, "no graph result to copy");
@@ -1474,13 +1454,13 @@ extern "C" int tagpu_copy_graph(tagpu_ctx *ctx, struct tagpu_flat_graph *h)
 	const uint64_t n_nodes = ctx->st.n_v / 2, n_e = ctx->st.n_e, n_w = ctx->st.n_seq_words;
 	h->n_nodes = n_nodes; h->n_e = n_e; h->n_seq_words = n_w;
 	if (n_nodes) {
-		std::vector<uint32_t> slot(n_nodes);
-		std::vector<uint8_t> m(ctx->kt_slots);
-		CU(cudaMemcpyAsync(slot.data(), ctx->node_slot.p, n_nodes * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		CU(cudaMemcpyAsync(m.data(), ctx->kt_mask.p, ctx->kt_slots, cudaMemcpyDeviceToHost, ctx->stream));
+		// masks gathered on the device (n_nodes bytes travel instead of the whole table's mask array)
+		if (ensure_slack(ctx, ctx->node_mask, n_nodes + 4)) return -1;
+		k_gather_node_masks<<<(unsigned)((n_nodes + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)ctx->node_slot.p, (const uint32_t *)ctx->kt_mask.p,
+												  n_nodes, (uint8_t *)ctx->node_mask.p);
+		CU(cudaGetLastError());
+		CU(cudaMemcpyAsync(h->node_mask, ctx->node_mask.p, n_nodes, cudaMemcpyDeviceToHost, ctx->stream));
 		CU(cudaMemcpyAsync(h->node_ebase, ctx->node_ebase.p, n_nodes * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		CU(cudaStreamSynchronize(ctx->stream));
-		for (uint64_t i = 0; i < n_nodes; ++i) h->node_mask[i] = m[slot[i]];
 	}
 	if (n_e) {
 		CU(cudaMemcpyAsync(h->e_src, ctx->e_src.p, n_e * 4, cudaMemcpyDeviceToHost, ctx->stream));
