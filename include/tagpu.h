@@ -187,9 +187,28 @@ void tagpu_dist_close(tagpu_ctx *ctx);
 /* [begin, end) of rank's share of a host read stream, cut at read boundaries ('\n') so no window is lost or doubled */
 void tagpu_dist_shard_range(const uint8_t *h_seq, uint64_t n_bytes, int rank, int world, uint64_t *begin, uint64_t *end);
 
+/* Intra-node rendezvous for the phases above (tagpu_host.c): a barrier and an all-gather of <= 8 values per rank over a
+ * POSIX shared-memory segment — microseconds instead of a collective launch plus a device round trip.  Rank 0 creates the
+ * segment; `name` is any string all ranks agree on (the host program distributes it once). */
+struct tagpu_shm;
+struct tagpu_shm *tagpu_shm_open(const char *name, int rank, int world);
+void tagpu_shm_barrier(struct tagpu_shm *s);
+int tagpu_shm_allgather(struct tagpu_shm *s, const uint64_t *mine, int n, uint64_t *all /* world x n */);
+void tagpu_shm_close(struct tagpu_shm *s);
+
 /* FASTQ/FASTA(.gz) files -> pinned host stream of sequence lines joined by '\n' (free with tagpu_free_reads) */
 int64_t tagpu_load_reads(int n_files, char **files, int n_threads, uint8_t **stream);
 void tagpu_free_reads(uint8_t *stream);
+/* The same ingest as an object, so that the upload can chase the parser: open (newline index + sizes: the stream length is
+ * known), start (copy workers fill dst in stream order), ready (bytes of the stream prefix that are final; pass it with the
+ * object to tagpu_set_source_progress before tagpu_build_host / tagpu_count_host), finish (join + release). */
+struct tagpu_ingest;
+struct tagpu_ingest *tagpu_ingest_open(int n_files, char **files, int n_threads);
+uint64_t tagpu_ingest_bytes(const struct tagpu_ingest *ing);
+void tagpu_ingest_start(struct tagpu_ingest *ing, uint8_t *dst);
+uint64_t tagpu_ingest_ready(void *ing);
+void tagpu_ingest_finish(struct tagpu_ingest *ing);
+void tagpu_set_source_progress(tagpu_ctx *ctx, uint64_t (*ready)(void *), void *arg);
 
 #ifdef __cplusplus
 }

@@ -159,10 +159,12 @@ class _FakeTagpu:
         self.calls.append("close")
 
 
-def _protocol_worker(rank, world, port, out_q):
+def _protocol_worker(rank, world, port, out_q, no_shm=False):
     import torch.distributed as dist
     from turingassembler_b200.dist import DistTagpu
 
+    if no_shm:
+        os.environ["TAGPU_NO_SHM"] = "1"      # barriers and counter exchange through torch.distributed collectives
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -170,6 +172,7 @@ def _protocol_worker(rank, world, port, out_q):
     for name, contract, refuse in (("two_level", True, -1), ("refused", True, 1), ("one_level", False, -1)):
         t = _FakeTagpu(rank, contract, refuse)
         d = DistTagpu(t, rank, world)
+        assert (d._shm is None) == no_shm
         d.plan(1000, 31)
         st1 = d.build(0, 10, gather_solid=False)
         st2 = d.build(0, 10)
@@ -181,14 +184,16 @@ def _protocol_worker(rank, world, port, out_q):
     dist.destroy_process_group()
 
 
-def test_phase_protocol_gloo():
+@pytest.mark.parametrize("no_shm", [False, True], ids=["shm_rendezvous", "collectives"])
+def test_phase_protocol_gloo(no_shm):
     """Host-side phase order of one multi-GPU build on 2 gloo ranks: the two-level graph stage (contract -> all-gather ->
-    pull paths), its collective fallback when any rank could not contract, and the one-level stage."""
+    pull paths), its collective fallback when any rank could not contract, and the one-level stage — with the barriers and
+    the counter exchange over the shared-memory segment of libtagpu.so (tagpu_shm_*) and over torch.distributed."""
     import torch.multiprocessing as mp
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_protocol_worker, args=(r, world, 29671, q)) for r in range(world)]
+    procs = [ctx.Process(target=_protocol_worker, args=(r, world, 29671 + int(no_shm), q, no_shm)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=240) for _ in range(world))

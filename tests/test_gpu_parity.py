@@ -212,30 +212,67 @@ def test_dropin_reference_binary(oracle, tmp_path):
         assert bad == 0 and hashlib.md5(txt).hexdigest() == gold["canon0_md5"]
 
 
-def test_bucket_overflow_path(oracle, tmp_path):
-    """TAGPU_REGION_CAP=4 leaves room for four records per bucket region, so nearly every super-k-mer record takes the
-    overflow route (overflow list -> histogram -> scan -> scatter -> read back through ext_off in pass 2).  Runs in a
-    subprocess because the knob is read once per process."""
+_CAPACITY_CODE = (
+    "import sys, numpy as np\n"
+    "sys.path.insert(0, {root!r}); sys.path.insert(0, {here!r})\n"
+    "import _oracle, _reads\n"
+    "from turingassembler_b200 import Tagpu\n"
+    "t = Tagpu(); ora = _oracle.load()\n"
+    "for k, seed in ((31, 3), (45, 4)):\n"
+    "    s = _reads.gen_stream(120000, 12000, seed=seed)\n"
+    "    for rep in range(2):\n"                       # the second build reuses the buffers the first one had to grow
+    "        st = t.build_host(s, k); want = ora.count(s, k + 1)\n"
+    "        hi, lo, cnt = t.solid(); o = np.lexsort((lo, hi))\n"
+    "        assert st['n_instances'] == want['n_instances'] and st['n_distinct'] == want['n_distinct']\n"
+    "        assert np.array_equal(hi[o], want['hi']) and np.array_equal(lo[o], want['lo']) and np.array_equal(cnt[o], want['count'])\n"
+    "        g = ora.graph(k, want['hi'], want['lo'], want['count'])\n"
+    "        assert (st['n_kmers'], st['n_v'], st['n_e']) == (g.contents.n_kmer, g.contents.n_v, g.contents.n_e)\n"
+    "print('CAPACITY-OK')\n")
+
+
+@pytest.mark.parametrize("env", [{"TAGPU_REGION_CAP": "4"}, {"TAGPU_REGION_CAP": "4", "TAGPU_OVERFLOW_CAP": "1000"}, {"TAGPU_SOLID_CAP": "500"}],
+                         ids=["overflow_list", "overflow_list_regrown", "solid_buffer_regrown"])
+def test_capacity_paths(env):
+    """The count stage sizes its buffers from estimates and recovers when an input does not fit them.
+    TAGPU_REGION_CAP=4 leaves room for four records per bucket region, so nearly every super-k-mer record takes the overflow
+    route (overflow list -> histogram -> scan -> scatter -> read back through ext_off in pass 2).  With TAGPU_OVERFLOW_CAP=1000
+    that list is too small as well: pass 1 is repeated with a list sized from what the first attempt counted.
+    TAGPU_SOLID_CAP=500 makes the solid (k+1)-mer buffers too small: pass 2 is repeated with larger ones.  Same results as the
+    oracle in every case.  Subprocess: the knobs are read once per process."""
     import subprocess
     import sys
-    code = (
-        "import sys, numpy as np\n"
-        f"sys.path.insert(0, {repr(os.path.dirname(HERE))}); sys.path.insert(0, {repr(HERE)})\n"
-        "import _oracle, _reads\n"
-        "from turingassembler_b200 import Tagpu\n"
-        "t = Tagpu(); ora = _oracle.load()\n"
-        "for k, seed in ((31, 3), (45, 4)):\n"
-        "    s = _reads.gen_stream(120000, 12000, seed=seed)\n"
-        "    st = t.build_host(s, k); want = ora.count(s, k + 1)\n"
-        "    hi, lo, cnt = t.solid(); o = np.lexsort((lo, hi))\n"
-        "    assert st['n_instances'] == want['n_instances'] and st['n_distinct'] == want['n_distinct']\n"
-        "    assert np.array_equal(hi[o], want['hi']) and np.array_equal(lo[o], want['lo']) and np.array_equal(cnt[o], want['count'])\n"
-        "    g = ora.graph(k, want['hi'], want['lo'], want['count'])\n"
-        "    assert (st['n_kmers'], st['n_v'], st['n_e']) == (g.contents.n_kmer, g.contents.n_v, g.contents.n_e)\n"
-        "print('OVERFLOW-OK')\n")
-    env = dict(os.environ, TAGPU_REGION_CAP="4")
-    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
-    assert p.returncode == 0 and "OVERFLOW-OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+    code = _CAPACITY_CODE.format(root=os.path.dirname(HERE), here=HERE)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **env), timeout=600)
+    assert p.returncode == 0 and "CAPACITY-OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
+def test_skewed_low_complexity_reads(tagpu, oracle, tmp_path):
+    """Inputs whose minimizers pile up in few buckets (SURVEY.md §8d asks for repeat families; real reads add poly-A tails and
+    simple repeats): a genome of diverged copies of one 3 kbp unit with poly-A / dinucleotide / short tandem stretches, read
+    at 60x.  A handful of minimizer sites then receive a large share of the windows — the overflow list, the oversized-group
+    sub-classes of pass 2 and the uncontractible blocks of the graph stage all get exercised — and the result must still
+    equal the oracle's."""
+    rng = np.random.default_rng(77)
+    unit = rng.integers(0, 4, 3000, dtype=np.uint8)
+    parts = []
+    for c in range(40):                                   # a 120 kbp repeat family at ~5 % divergence
+        u = unit.copy()
+        m = rng.random(u.size) < 0.05
+        u[m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+        parts.append(u)
+        parts.append(rng.integers(0, 4, 500, dtype=np.uint8))
+    for _ in range(30):                                   # low-complexity stretches: poly-A, (AC)n, (AAT)n, 200-400 bp each
+        n = int(rng.integers(200, 400))
+        parts.append(np.zeros(n, np.uint8))
+        parts.append(rng.integers(0, 4, 300, dtype=np.uint8))
+        parts.append(np.tile(np.array([0, 1], np.uint8), n // 2))
+        parts.append(rng.integers(0, 4, 300, dtype=np.uint8))
+        parts.append(np.tile(np.array([0, 0, 3], np.uint8), n // 3))
+        parts.append(rng.integers(0, 4, 300, dtype=np.uint8))
+    genome = np.concatenate(parts)
+    stream = _reads.gen_stream(genome.size, int(genome.size * 60 / 302), seed=78, genome=genome)
+    for k in (21, 31, 45):
+        check_against_oracle(tagpu, oracle, stream, k, tmp_path, tag=f"skew{k}")
 
 
 @pytest.mark.skipif(not os.path.exists(_oracle.TA_KMC), reason="oracle/_ref/TA_kmc (reference + libtagpu.so in place of libkmc.a) not built")

@@ -15,7 +15,8 @@ from typing import Sequence
 import numpy as np
 
 IPC_HANDLE_BYTES = 64  # TAGPU_IPC_HANDLE_BYTES
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtagpu.so")
+# TAGPU_LIB: developer override (e.g. a build with -DTAGPU_TIMING); the product library is libtagpu.so next to this file
+LIB_PATH = os.environ.get("TAGPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtagpu.so")
 
 
 class TagpuError(RuntimeError):

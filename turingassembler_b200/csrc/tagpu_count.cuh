@@ -30,6 +30,7 @@ constexpr uint32_t TAGPU_H_INVALID = 0xffffffffu;
 constexpr int TAGPU_HM_POS = TAGPU_SMEM_WORDS * 32;   // positions of the packed tile (incl. halo)
 constexpr int TAGPU_HM_LEN = TAGPU_SMEM_WORDS * 33;   // padded: index q + q/32, so word-major and position-major accesses are both conflict-free
 #define HIDX(q) ((q) + ((q) >> 5))
+constexpr int TAGPU_END_CAP = 896;                    // run ends of a tile handled per emission pass (a tile of 151 bp reads has ~590)
 
 template <int W> struct SkRec;                        // super-k-mer record: bases right-aligned, length in the top byte
 template <> struct __align__(16) SkRec<1> { unsigned long long w[2]; };   // <= 60 bases
@@ -65,25 +66,37 @@ TAGPU_DI uint32_t tagpu_bucket_of(uint32_t minhash, int log2_buckets)
 	return (minhash * 0x85ebca6bu) >> (32 - log2_buckets);
 }
 
-// the 32 bases ending at packed-tile position end_q (inclusive, >= 31), first base most significant
-TAGPU_DI uint64_t tagpu_extract32(const uint64_t *pk, int end_q)
-{
-	const int wi = end_q >> 5, sh = 62 - 2 * (end_q & 31);      // bits of pk[wi] that lie beyond end_q
-	const unsigned __int128 two = ((unsigned __int128)pk[wi > 0 ? wi - 1 : 0] << 64) | pk[wi];
-	return (uint64_t)(two >> sh);
-}
-
+// The n_bases bases that end at packed-tile position end_q (inclusive), right-aligned, as a record with n_windows in its
+// top byte.  pk holds 32 bases per 64-bit word, first base most significant; in 32-bit half-words taken in position order
+// (high half first) the base at position p sits at bit 2 (15 - (p & 15)) of half-word p >> 4, so 32-bit word i of the record
+// is one funnel shift of two neighbouring half-words.  Needs W + 1 words of history: end_q >= 32 (W + 1).
 template <int W>
 TAGPU_DI SkRec<W> tagpu_make_record(const uint64_t *pk, int end_q, int n_bases, int n_windows)
 {
+	constexpr int NOUT = 2 * W + 2;                      // 32-bit words that can hold bases: 49 / 95 of them at most
+	const int wi = end_q >> 5;
+	uint32_t H[2 * W + 4];
+#pragma unroll
+	for (int m = 0; m < W + 2; ++m) {
+		const uint64_t v = pk[wi - (W + 1) + m];
+		H[2 * m] = (uint32_t)(v >> 32);
+		H[2 * m + 1] = (uint32_t)v;
+	}
+	const bool odd = (end_q & 16) != 0;                  // end_q lies in the low half of pk[wi]
+	uint32_t t[2 * W + 3];
+#pragma unroll
+	for (int m = 0; m < 2 * W + 3; ++m) t[m] = odd ? H[m + 1] : H[m];
+	const int sft = 2 * (15 - (end_q & 15)), total_bits = 2 * n_bases;
+	uint32_t out[NOUT];
+#pragma unroll
+	for (int i = 0; i < NOUT; ++i) {
+		const int keep = total_bits - 32 * i;              // bits of word i that belong to the record
+		const uint32_t v = __funnelshift_r(t[2 * W + 2 - i], t[2 * W + 1 - i], sft);
+		out[i] = keep >= 32 ? v : (keep > 0 ? v & ((1u << keep) - 1u) : 0u);
+	}
 	SkRec<W> r;
 #pragma unroll
-	for (int i = 0; i < 2 * W; ++i) {
-		const int have = n_bases - 32 * i;              // bases that belong in word i
-		uint64_t v = have > 0 ? tagpu_extract32(pk, end_q - 32 * i) : 0ull;
-		if (have < 32) v &= have > 0 ? (1ull << (2 * have)) - 1 : 0ull;
-		r.w[i] = v;
-	}
+	for (int j = 0; j < 2 * W; ++j) r.w[j] = j < W + 1 ? (((unsigned long long)out[2 * j + 1] << 32) | out[2 * j]) : 0ull;
 	r.w[2 * W - 1] |= (unsigned long long)n_windows << 56;
 	return r;
 }
@@ -123,34 +136,35 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 	else tagpu_load_tile(seq, n, ((uint64_t)blockIdx.x + tile0) * TAGPU_TILE_BASES, pk, inv);
 	__syncthreads();
 
-	// A. hash of the canonical m-mer ending at every position (invalid if the m-mer touches a non-ACGT byte), with the
-	//    position (mod 64) in the low bits: the minimum over a window then identifies one m-mer OCCURRENCE
+	// A. hash of the canonical m-mer ending at every position, with the position (mod 64) in the low bits: the minimum
+	//    over a window then identifies one m-mer OCCURRENCE.  An m-mer that touches a non-ACGT byte gets a hash like any
+	//    other: it can only be the minimum of a window that contains that byte, i.e. of an invalid window, and those are
+	//    masked out in C1 — so no validity is tracked here.
 	const int w = K - m + 1;
 	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
 		const uint32_t mm = (1u << (2 * m)) - 1;
 		uint32_t fw = j ? (uint32_t)pk[j - 1] & mm : 0u;
 		uint32_t rv = (uint32_t)(tagpu_rc64_full((uint64_t)fw) >> (64 - 2 * m));
-		const uint32_t i1 = j ? inv[j - 1] : 0xffffffffu;
-		int run = i1 ? (__ffs(i1) - 1) : 32;
-		uint64_t cur = pk[j];
-		uint32_t iv = inv[j];
+		const uint64_t cur = pk[j];
+		const uint32_t tag0 = (uint32_t)(j & 1) * 32u;
 		if (w == 32) {
 			// the word IS a van Herk block: hashes stay in registers, prefix minima go to hp, suffix minima to hs
 			uint32_t h[32];
 			uint32_t acc = TAGPU_H_INVALID;
 #pragma unroll
-			for (int i = 0; i < 32; ++i) {
-				const uint32_t c = (uint32_t)(cur >> 62);
-				cur <<= 2;
-				const bool bad = (int)iv < 0;
-				iv <<= 1;
-				fw = ((fw << 2) | c) & mm;
-				rv = (rv >> 2) | ((3u - c) << (2 * (m - 1)));
-				run = bad ? 0 : run + 1;
-				const uint32_t cm = min(fw, rv);
-				h[i] = run >= m ? (((cm * 0x9e3779b1u) & ~63u) | (uint32_t)((j & 1) * 32 + i)) : TAGPU_H_INVALID;
-				acc = min(acc, h[i]);
-				hp[j * 33 + i] = acc;
+			for (int half = 0; half < 2; ++half) {
+				uint32_t cw = half ? (uint32_t)cur : (uint32_t)(cur >> 32);
+#pragma unroll
+				for (int ii = 0; ii < 16; ++ii) {
+					const int i = half * 16 + ii;
+					const uint32_t c = cw >> 30;
+					cw <<= 2;
+					fw = ((fw << 2) | c) & mm;
+					rv = (rv >> 2) | ((c ^ 3u) << (2 * (m - 1)));
+					h[i] = ((min(fw, rv) * 0x9e3779b1u) & ~63u) | (tag0 + (uint32_t)i);
+					acc = min(acc, h[i]);
+					hp[j * 33 + i] = acc;
+				}
 			}
 			acc = TAGPU_H_INVALID;
 #pragma unroll
@@ -159,17 +173,18 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 				hs[j * 33 + i] = acc;
 			}
 		} else {
+#pragma unroll
+			for (int half = 0; half < 2; ++half) {
+				uint32_t cw = half ? (uint32_t)cur : (uint32_t)(cur >> 32);
 #pragma unroll 8
-			for (int i = 0; i < 32; ++i) {
-				const uint32_t c = (uint32_t)(cur >> 62);
-				cur <<= 2;
-				const bool bad = (int)iv < 0;
-				iv <<= 1;
-				fw = ((fw << 2) | c) & mm;
-				rv = (rv >> 2) | ((3u - c) << (2 * (m - 1)));
-				run = bad ? 0 : run + 1;
-				const uint32_t cm = min(fw, rv);
-				hp[j * 33 + i] = run >= m ? (((cm * 0x9e3779b1u) & ~63u) | (uint32_t)((j & 1) * 32 + i)) : TAGPU_H_INVALID;
+				for (int ii = 0; ii < 16; ++ii) {
+					const int i = half * 16 + ii;
+					const uint32_t c = cw >> 30;
+					cw <<= 2;
+					fw = ((fw << 2) | c) & mm;
+					rv = (rv >> 2) | ((c ^ 3u) << (2 * (m - 1)));
+					hp[j * 33 + i] = ((min(fw, rv) * 0x9e3779b1u) & ~63u) | (tag0 + (uint32_t)i);
+				}
 			}
 		}
 	}
@@ -249,34 +264,63 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 	}
 	__syncthreads();
 
-	// C2. every thread emits the runs that END in its word: one record (2-bit bases + window count) appended to the
-	//     bucket of the run's minimizer.
-	const int wi = threadIdx.x + TAGPU_HALO_WORDS;
-	uint32_t ends = 0, B = 0, Bprev = 0;
+	// C2. the runs that END in the tile are laid out as one dense list (block-wide prefix sum over the per-word end masks),
+	//     and then every thread builds and appends one record per iteration — whatever the distribution of run ends over
+	//     the words: one record (2-bit bases + window count) goes to the bucket of the run's minimizer.
+	__shared__ uint16_t s_end[TAGPU_END_CAP];
+	__shared__ uint32_t s_wsum[TAGPU_TILE_THREADS / 32 + 1];
+	const int wi0 = threadIdx.x + TAGPU_HALO_WORDS;
+	uint32_t ends = 0;
 	if (threadIdx.x < TAGPU_TILE_WORDS) {
-		const uint32_t V = vw[wi];
-		B = bw[wi];
-		Bprev = bw[wi - 1];
-		const uint32_t Vn = (V >> 1) | (vw[wi + 1] << 31), Bn = (B >> 1) | (bw[wi + 1] << 31);
+		const uint32_t V = vw[wi0], B = bw[wi0];
+		const uint32_t Vn = (V >> 1) | (vw[wi0 + 1] << 31), Bn = (B >> 1) | (bw[wi0 + 1] << 31);
 		ends = V & (~Vn | Bn);
 	}
-	while (ends) {
-		const int e = __ffs(ends) - 1;
-		ends &= ends - 1;
-		const uint32_t upto = B & (0xffffffffu >> (31 - e));
-		const int st = upto ? 31 - __clz(upto) : -1 - __clz(Bprev);
-		const int nw = e - st + 1, end_q = wi * 32 + e;
-		if (nw > 32) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_RUN_LENGTH); continue; }
-		const uint32_t b = tagpu_bucket_of(tagpu_window_min(hs, hp, end_q, w) >> 6, cfg.log2_buckets);
-		const SkRec<W> rec = tagpu_make_record<W>(pk, end_q, nw + K - 1, nw);
-		const unsigned long long old = atomicAdd(cursor + b, 1ull | ((unsigned long long)nw << 32));
-		const uint32_t idx = (uint32_t)old;
-		if (idx < cfg.cap_records) {
-			regions[(size_t)b * cfg.cap_records + idx] = rec;
-		} else {
-			const unsigned long long o = atomicAdd(ctr + CTR_SPARE0, 1ull);
-			if (o < cfg.overflow_cap) { overflow[o] = rec; overflow_bucket[o] = b; }
-			else atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_BUCKET_OVERFLOW);
+	const uint32_t n_mine = __popc(ends), lane_ = threadIdx.x & 31u, warp_ = threadIdx.x >> 5;
+	uint32_t incl = n_mine;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane_ >= (uint32_t)d) incl += t;
+	}
+	if (lane_ == 31) s_wsum[warp_] = incl;
+	__syncthreads();
+	uint32_t before = 0, n_ends = 0;
+#pragma unroll
+	for (int x = 0; x < TAGPU_TILE_THREADS / 32; ++x) {
+		const uint32_t v = s_wsum[x];
+		before += (uint32_t)x < warp_ ? v : 0u;
+		n_ends += v;
+	}
+	const uint32_t my_first = before + incl - n_mine;
+	for (uint32_t pass0 = 0; pass0 < n_ends; pass0 += TAGPU_END_CAP) {          // (one pass unless the tile is pathological)
+		if (pass0) __syncthreads();
+		uint32_t rank = my_first, rest = ends;
+		while (rest) {
+			const int e = __ffs(rest) - 1;
+			rest &= rest - 1;
+			if (rank >= pass0 && rank < pass0 + TAGPU_END_CAP) s_end[rank - pass0] = (uint16_t)(wi0 * 32 + e);
+			++rank;
+		}
+		__syncthreads();
+		const uint32_t n_pass = min(n_ends - pass0, (uint32_t)TAGPU_END_CAP);
+		for (uint32_t r = threadIdx.x; r < n_pass; r += blockDim.x) {
+			const int end_q = s_end[r], wi = end_q >> 5, e = end_q & 31;
+			const uint32_t upto = bw[wi] & (0xffffffffu >> (31 - e));
+			const int st = upto ? 31 - __clz(upto) : -1 - __clz(bw[wi - 1]);
+			const int nw = e - st + 1;
+			if (nw > 32) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_RUN_LENGTH); continue; }
+			const uint32_t b = tagpu_bucket_of(tagpu_window_min(hs, hp, end_q, w) >> 6, cfg.log2_buckets);
+			const SkRec<W> rec = tagpu_make_record<W>(pk, end_q, nw + K - 1, nw);
+			const unsigned long long old = atomicAdd(cursor + b, 1ull | ((unsigned long long)nw << 32));
+			const uint32_t idx = (uint32_t)old;
+			if (idx < cfg.cap_records) {
+				regions[(size_t)b * cfg.cap_records + idx] = rec;
+			} else {
+				const unsigned long long o = atomicAdd(ctr + CTR_SPARE0, 1ull);
+				if (o < cfg.overflow_cap) { overflow[o] = rec; overflow_bucket[o] = b; }
+				else atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_BUCKET_OVERFLOW);
+			}
 		}
 	}
 	// instance total (the metric's numerator): one atomic per CTA
@@ -367,11 +411,21 @@ __global__ void k_overflow_scatter(const SkRec<W> *__restrict__ overflow, const 
 
 // ---------------------------------------------------------------- pass 2
 template <int W> struct BucketCfg {
-	static constexpr int THREADS = 512;                         // two CTAs per SM: one CTA's barriers / harvest overlap the other's inserts
-	static constexpr int CTAS_PER_SM = 2;
+#ifndef TAGPU_BC_THREADS
+#define TAGPU_BC_THREADS 512
+#define TAGPU_BC_CTAS 2
+#define TAGPU_BC_SLOTS1 7104
+#define TAGPU_BC_SLOTS2 3840
+#endif
+	static constexpr int THREADS = TAGPU_BC_THREADS;            // two CTAs per SM: one CTA's barriers / harvest overlap the other's inserts
+	static constexpr int CTAS_PER_SM = TAGPU_BC_CTAS;
+	static constexpr int NW = W + 1;                            // 64-bit words of a staged record (bases only: <= 49 / <= 95 of them)
+	static constexpr int ROUND = 2 * THREADS;                   // records staged per round
+	static constexpr int ITEM_WINDOWS = 8;                      // windows of one work item: one per lane of an octet
+	static constexpr int ITEMS = ROUND * 32 / ITEM_WINDOWS;     // work items of a round (a record has <= 32 windows)
 	// shared-memory table slots per CTA (any number: the home slot is mulhi(hash, SLOTS)); sized so that two CTAs of
-	// table + record staging + static + the 1 KB the hardware reserves per CTA fit the SM's 228 KB
-	static constexpr int SLOTS = W == 1 ? 7728 : 3840;
+	// table + staging + static + the 1 KB the hardware reserves per CTA fit the SM's 228 KB
+	static constexpr int SLOTS = W == 1 ? TAGPU_BC_SLOTS1 : TAGPU_BC_SLOTS2;
 	static constexpr int MAX_PROBES = 48;                       // a longer probe sequence aborts the attempt (re-run on sub-classes)
 	static constexpr int GROUP_MAX = 64;                        // buckets per group
 	static constexpr int SUB_MAX = 256;                         // (bucket, source rank) pairs per group: group_max = min(GROUP_MAX, SUB_MAX / world)
@@ -379,7 +433,9 @@ template <int W> struct BucketCfg {
 	// Measured on C1/C2 with 1.5x / 2x / 2.5x / 3x SLOTS: 2x is best for 128-bit keys (3x overflows into re-runs), 2.5x-3x
 	// for 64-bit keys; duplicate-record collapse made inserts cheap relative to the per-group harvest.
 	static constexpr uint32_t GROUP_TARGET = W == 1 ? SLOTS * 5 / 2 : SLOTS * 2;
-	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + 2 * THREADS * sizeof(SkRec<W>);
+	// staging area: record words, one 32-bit meta word per record, 16-bit work items; the harvest reuses it for its output
+	static constexpr size_t STAGE_BYTES = (size_t)ROUND * (NW * 8 + 4) + (size_t)ITEMS * 2;
+	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + STAGE_BYTES;
 };
 
 // table hash: the key words are folded to 32 bits (one 32-bit multiply per extra word) and mixed by one more multiply;
@@ -574,16 +630,94 @@ __global__ void __launch_bounds__(TAGPU_SCAN_BLOCK) k_mark_groups(const unsigned
 	if (b + 1 == n_owned) grp_end[g] = n_owned;
 }
 
-// Persistent CTAs pull groups of buckets from a global counter.  The CTA stages the group's records in shared memory
-// (canonical orientation, duplicates collapsed), splits the live windows into THREADS equal contiguous segments and every
-// thread ROLLS the forward / reverse-complement keys through its segment (re-seeding only at record boundaries),
-// inserting the canonical key into the CTA's shared-memory table.
+// One 64-byte descriptor per group id, so that the counting kernel's group set-up is ONE (prefetched) global load instead of
+// a chain of dependent ones: { first owned bucket, buckets (0 = empty group id), windows, flags, record prefix over the
+// group's (bucket, source) pairs: rpre[0 .. n_pairs] }.  Groups with more than TAGPU_DESC_PAIRS pairs or more than
+// group_max buckets are flagged SLOW: the kernel then walks grp_first / grp_end / cur_all itself.
+constexpr uint32_t TAGPU_DESC_PAIRS = 11, TAGPU_DESC_SLOW = 1u;
+struct __align__(16) GroupDesc { uint32_t b0, nbk, windows, flags, rpre[TAGPU_DESC_PAIRS + 1]; };
+
+__global__ void __launch_bounds__(256) k_group_desc(const uint32_t *__restrict__ grp_first, const uint32_t *__restrict__ grp_end,
+						    const unsigned long long *__restrict__ cur_all, uint32_t world, uint32_t group_max,
+						    const unsigned long long *ctr, GroupDesc *__restrict__ desc)
+{
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= (uint32_t)ctr[CTR_GROUPS]) return;
+	GroupDesc d;
+	d.b0 = 0; d.nbk = 0; d.windows = 0; d.flags = 0;
+#pragma unroll
+	for (int i = 0; i <= (int)TAGPU_DESC_PAIRS; ++i) d.rpre[i] = 0;
+	const uint32_t bs = grp_first[g];
+	if (bs != TAGPU_NONE) {
+		const uint32_t nbk = grp_end[g] - bs;
+		d.b0 = bs;
+		d.nbk = nbk;
+		if (nbk > group_max || nbk * world > TAGPU_DESC_PAIRS) d.flags = TAGPU_DESC_SLOW;
+		else {
+			uint32_t acc = 0, win = 0;
+			for (uint32_t i = 0; i < nbk * world; ++i) {
+				const unsigned long long cur = cur_all[(size_t)bs * world + i];
+				d.rpre[i] = acc;
+				acc += (uint32_t)cur;
+				win += (uint32_t)(cur >> 32);
+			}
+			d.rpre[nbk * world] = acc;
+			d.windows = win;
+		}
+	}
+	desc[g] = d;
+}
+
+// ---------------------------------------------------------------- staged records
+// A staged record = the bases of a super-k-mer in canonical orientation, right-aligned in NW = W + 1 64-bit words
+// (W = 1: <= 49 bases, W = 2: <= 95), plus one meta word: windows in bits 0..7, multiplicity in bits 8..15.
+template <int W> struct StagedRec { unsigned long long w[W + 1]; };
+
+// window j (0 = leftmost) of a staged record with n windows: the K bases that start sh = 2 (n - 1 - j) <= 62 bits above the
+// right end.  32-bit funnel shifts: sh = 32 a + b, word i of the result = (r[a + i + 1] : r[a + i]) >> b.
+TAGPU_DI Key<1> tagpu_staged_window(const StagedRec<1> &r, int sh, int K)
+{
+	const uint32_t r0 = (uint32_t)r.w[0], r1 = (uint32_t)(r.w[0] >> 32), r2 = (uint32_t)r.w[1], r3 = (uint32_t)(r.w[1] >> 32);
+	const bool a = sh >= 32;
+	const uint32_t t0 = a ? r1 : r0, t1 = a ? r2 : r1, t2 = a ? r3 : r2;
+	const uint32_t o0 = __funnelshift_r(t0, t1, sh), o1 = __funnelshift_r(t1, t2, sh);   // (shift taken mod 32)
+	Key<1> k;
+	k.lo = ((unsigned long long)o1 << 32) | o0;
+	if (K < 32) k.lo &= (1ull << (2 * K)) - 1;
+	return k;
+}
+TAGPU_DI Key<2> tagpu_staged_window(const StagedRec<2> &r, int sh, int K)
+{
+	const uint32_t r0 = (uint32_t)r.w[0], r1 = (uint32_t)(r.w[0] >> 32), r2 = (uint32_t)r.w[1], r3 = (uint32_t)(r.w[1] >> 32),
+		       r4 = (uint32_t)r.w[2], r5 = (uint32_t)(r.w[2] >> 32);
+	const bool a = sh >= 32;
+	const uint32_t t0 = a ? r1 : r0, t1 = a ? r2 : r1, t2 = a ? r3 : r2, t3 = a ? r4 : r3, t4 = a ? r5 : r4;
+	const uint32_t o0 = __funnelshift_r(t0, t1, sh), o1 = __funnelshift_r(t1, t2, sh), o2 = __funnelshift_r(t2, t3, sh),
+		       o3 = __funnelshift_r(t3, t4, sh);
+	Key<2> k;
+	k.lo = ((unsigned long long)o1 << 32) | o0;
+	k.hi = ((unsigned long long)o3 << 32) | o2;
+	return KeyOps<2>::band(k, KeyOps<2>::mask(K));
+}
+
+// Persistent CTAs pull groups of buckets from a global counter and count one group at a time in the CTA's
+// shared-memory table.  A group is processed in rounds of <= ROUND records:
 //
-// Per group the CTA meets at five barriers only.  Everything with a global round trip is taken off the critical path:
-// the id of the next group is fetched while the current one is being counted, and the output offset of the harvest
-// (one global atomic) travels while the solid keys are compacted into the shared-memory staging area.
+//   stage    every thread loads two records (coalesced: consecutive lanes, consecutive records), brings them into
+//            canonical orientation and stages them in shared memory; equal records among the 32 of a warp collapse into
+//            one representative with a multiplicity;
+//   items    every live record of n windows becomes ceil(n / 8) work items (record, c); a block-wide prefix sum lays the
+//            items of the round out as one dense list;
+//   insert   an OCTET of lanes takes an item: lane q extracts window 8 c + q straight from the staged record (two funnel
+//            shifts — no rolling, no dependence on the neighbouring window), reverse-complements it, and inserts the
+//            canonical key into the table (LDS probe, ATOMS.CAS claim, ATOMS.ADD of the multiplicity).  All lanes of a warp
+//            do the same thing in every iteration; only the probe outcome diverges.
+//
+// Everything with a global round trip is off the critical path: the id of the next group is fetched while the current
+// one is being counted, and the output offset of the harvest (one global atomic) travels while the solid keys are
+// compacted into the staging area.
 #ifdef TAGPU_TIMING
-#define TM_DECL() long long tm_setup = 0, tm_insert = 0, tm_wait = 0, tm_harvest = 0, tm_ha = 0, tm_hb = 0, tm_iters = 0, tm_failed = 0, tm_t = clock64()
+#define TM_DECL() long long tm_setup = 0, tm_insert = 0, tm_wait = 0, tm_harvest = 0, tm_ha = 0, tm_hb = 0, tm_iters = 0, tm_failed = 0, tm_stage = 0, tm_t = clock64()
 #define TM_ADD(x) do { long long n_ = clock64(); x += n_ - tm_t; tm_t = n_; } while (0)
 #else
 #define TM_DECL()
@@ -594,53 +728,90 @@ template <int W>
 __global__ void __launch_bounds__(BucketCfg<W>::THREADS, BucketCfg<W>::CTAS_PER_SM)
 k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uint32_t first_bucket, uint32_t cap_records,
 		const unsigned long long *__restrict__ cur_all, const uint32_t *__restrict__ ext_all, const uint32_t *__restrict__ grp_first,
-		const uint32_t *__restrict__ grp_end, uint32_t group_max, int K, uint32_t ci, Key<W> *__restrict__ solid, uint32_t *__restrict__ solid_cnt, unsigned long long solid_cap,
-		SolidBlock *__restrict__ blocks, uint32_t blocks_cap, unsigned long long *ctr)
+		const uint32_t *__restrict__ grp_end, const GroupDesc *__restrict__ desc, uint32_t group_max, int K, uint32_t ci, Key<W> *__restrict__ solid,
+		uint32_t *__restrict__ solid_cnt, unsigned long long solid_cap, SolidBlock *__restrict__ blocks, uint32_t blocks_cap, unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
 	typedef BucketCfg<W> C;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Key<W> *t_key = reinterpret_cast<Key<W> *>(smem_raw);
 	uint32_t *t_cnt = reinterpret_cast<uint32_t *>(t_key + C::SLOTS);
-	SkRec<W> *s_rec = reinterpret_cast<SkRec<W> *>(t_cnt + C::SLOTS);
-	// during the harvest the record staging area holds the compacted solid (key, count) pairs of the group
-	constexpr uint32_t OUT_CAP = 2 * C::THREADS * sizeof(SkRec<W>) / (sizeof(Key<W>) + 4);
-	Key<W> *o_key = reinterpret_cast<Key<W> *>(s_rec);
+	unsigned char *stage = reinterpret_cast<unsigned char *>(t_cnt + C::SLOTS);
+	StagedRec<W> *s_rec = reinterpret_cast<StagedRec<W> *>(stage);
+	uint32_t *s_meta = reinterpret_cast<uint32_t *>(s_rec + C::ROUND);
+	uint16_t *s_item = reinterpret_cast<uint16_t *>(s_meta + C::ROUND);
+	// during the harvest the staging area holds the compacted solid (key, count) pairs of the group
+	constexpr uint32_t OUT_CAP = (uint32_t)(C::STAGE_BYTES / (sizeof(Key<W>) + 4));
+	Key<W> *o_key = reinterpret_cast<Key<W> *>(stage);
 	uint32_t *o_cnt = reinterpret_cast<uint32_t *>(o_key + OUT_CAP);
 	constexpr uint32_t TOP_NONE = 0xffffffffu;
-	__shared__ uint32_t s_b0, s_nb, s_bs, s_be, s_top, s_claims, s_overflow, s_sp, s_warp_solid[C::THREADS / 32], s_stack[64];
-	__shared__ uint16_t s_scan[2 * C::THREADS + 2];              // live windows of the round before the k-th live record
-	__shared__ uint16_t s_live[2 * C::THREADS];                  // staged index of the k-th live record
+	__shared__ uint32_t s_b0, s_nb, s_bs, s_be, s_top, s_claims, s_overflow, s_sp, s_nsolid, s_nout, s_pf, s_pf_n, s_warp_solid[C::THREADS / 32], s_stack[64];
 	__shared__ uint32_t s_rpre[C::SUB_MAX + 1];                  // per (bucket, source) pair of the group: records before it
 	__shared__ unsigned long long s_out_base;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	constexpr uint32_t N_WARPS = C::THREADS / 32;
-	const Key<W> kmask = KO::mask(K);
 	const uint32_t n_groups = (uint32_t)ctr[CTR_GROUPS];
 	TM_DECL();
 
 	for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) { t_key[i] = KO::make(0, 0); t_cnt[i] = 0; }
-	// thread 0 always holds the id of the NEXT group in a register (requested one group ahead)
-	uint32_t next_group = 0;
-	if (tid == 0) { next_group = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull); s_bs = 0; s_be = 0; }
+	// Group ids come from a global counter.  Lane 0 of warp 0 keeps a queue of two: id1, whose 64-byte descriptor already sits
+	// in the registers of lanes 0..3 (loaded while the group before was counted), and id2, whose atomicAdd is still in
+	// flight.  So the set-up of a group touches no global memory unless the group is flagged SLOW.
+	uint32_t id1 = 0, id2 = 0;
+	uint4 dd = make_uint4(0, 0, 0, 0);
+	if (warp == 0) {
+		if (lane == 0) { id1 = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull); id2 = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull); s_bs = 0; s_be = 0; s_pf = TAGPU_NONE; }
+		const uint32_t g1 = __shfl_sync(0xffffffffu, id1, 0);
+		if (lane < 4 && g1 < n_groups) dd = __ldg(reinterpret_cast<const uint4 *>(desc + g1) + lane);
+	}
 
 	for (;;) {
 		__syncthreads();                                            // B0: previous group fully harvested, staging area free
 		if (warp == 0) {
-			// ---- group setup by warp 0: next <= group_max buckets of the current group id (or of the next non-empty
-			// one), record prefix over their (bucket, source) pairs, first hash class on the stack
+			// ---- group setup by warp 0: the next group id (skipping empty ones) or the rest of an oversized one
 			uint32_t bs = s_bs, be = s_be;
+			bool fast = false;
+			uint4 dcur = make_uint4(0, 0, 0, 0);
 			while (bs >= be) {
-				const uint32_t grp = __shfl_sync(0xffffffffu, next_group, 0);
+				const uint32_t grp = __shfl_sync(0xffffffffu, id1, 0);
 				if (grp >= n_groups) { bs = be = TAGPU_NONE; break; }
-				if (lane == 0) next_group = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);   // lands during the inserts
-				bs = grp_first[grp];
-				be = bs == TAGPU_NONE ? 0u : grp_end[grp];
-				if (bs == TAGPU_NONE) bs = 0;                                          // empty group id: take the next one
+				dcur = dd;
+				if (lane == 0) { id1 = id2; id2 = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull); }    // lands during the inserts
+				const uint32_t g1 = __shfl_sync(0xffffffffu, id1, 0);                                 // (requested a whole group ago)
+				dd = make_uint4(0, 0, 0, 0);
+				if (lane < 4 && g1 < n_groups) dd = __ldg(reinterpret_cast<const uint4 *>(desc + g1) + lane);   // consumed at the next set-up
+				const uint32_t d_b0 = __shfl_sync(0xffffffffu, dcur.x, 0), d_nbk = __shfl_sync(0xffffffffu, dcur.y, 0),
+					       d_flags = __shfl_sync(0xffffffffu, dcur.w, 0);
+				if (!d_nbk) continue;                                                              // empty group id
+				bs = d_b0; be = d_b0 + d_nbk;
+				fast = !(d_flags & TAGPU_DESC_SLOW);
 			}
 			if (bs == TAGPU_NONE) {
 				if (lane == 0) s_nb = TAGPU_NONE;
+			} else if (fast) {
+				// everything comes out of the descriptor registers: lanes 1..3 hold rpre[0..11]
+				const uint32_t b0 = bs, nb = (be - bs) * world;
+				if (lane >= 1 && lane < 4) {
+					const uint32_t base = 4u * (lane - 1u);
+					if (base + 0u <= nb) s_rpre[base + 0u] = dcur.x;
+					if (base + 1u <= nb) s_rpre[base + 1u] = dcur.y;
+					if (base + 2u <= nb) s_rpre[base + 2u] = dcur.z;
+					if (base + 3u <= nb) s_rpre[base + 3u] = dcur.w;
+				}
+				if (lane == 0) {
+					const uint32_t tot_inst = dcur.z;
+					uint32_t L = 0;                                  // a single oversized bucket starts on 2^L hash classes
+					while (L < 5 && (tot_inst >> L) > 2u * C::GROUP_TARGET) ++L;
+					uint32_t sp = 0;
+					for (uint32_t c = 1; c < (1u << L); ++c) s_stack[sp++] = (L << 24) | c;
+					s_sp = sp;
+					s_top = L << 24;
+					s_claims = 0; s_overflow = 0; s_nsolid = 0; s_nout = 0;
+					s_b0 = b0; s_nb = nb;
+					s_bs = be; s_be = be;
+				}
 			} else {
+				// SLOW: many pairs (multi-GPU, tiny buckets) or more buckets than one table takes: walk the cursors
 				const uint32_t b0 = bs, nb = min(be - bs, group_max) * world;
 				uint32_t tot_inst = 0, carry = 0;
 				for (uint32_t i0 = 0; i0 < nb; i0 += 32) {
@@ -666,7 +837,7 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 					for (uint32_t c = 1; c < (1u << L); ++c) s_stack[sp++] = (L << 24) | c;
 					s_sp = sp;
 					s_top = L << 24;                                 // class 0 of level L goes first
-					s_claims = 0; s_overflow = 0;
+					s_claims = 0; s_overflow = 0; s_nsolid = 0; s_nout = 0;
 					s_b0 = b0; s_nb = nb;
 					s_bs = b0 + nb / world; s_be = be;
 				}
@@ -680,24 +851,22 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 		for (;;) {                                                  // one iteration per hash class (L, cls) of the group
 			const uint32_t top = s_top;
 			const uint32_t L = top >> 24, cls = top & 0xffffffu;
-			// ---- insert every window of the group that belongs to hash class (L, cls).
-			// The CTA works in lock step on rounds of <= 2 * THREADS records: every thread stages two adjacent records
-			// (canonical orientation; duplicates among the 32 records of a warp collapse into one with a multiplicity),
-			// a block-wide prefix sum of the live window counts follows, and then the live windows of the round are cut
-			// into THREADS equal contiguous segments — one per thread, whatever the records look like.
-			const uint32_t n_rounds = (n_recs + 2u * C::THREADS - 1u) / (2u * C::THREADS);
-			const uint32_t per_round = n_rounds ? (n_recs + n_rounds - 1u) / n_rounds : 0u;   // rounds of equal size
+			uint32_t n_claimed = 0, n_became_solid = 0;                 // this thread's share of the class's distinct / solid keys
+			// ---- insert every window of the group that belongs to hash class (L, cls), in rounds of equal size
+			const uint32_t n_rounds = (n_recs + (uint32_t)C::ROUND - 1u) / (uint32_t)C::ROUND;
+			const uint32_t per_round = n_rounds ? (n_recs + n_rounds - 1u) / n_rounds : 0u;
 			for (uint32_t rbase = 0; rbase < n_recs; rbase += per_round) {
-				if (rbase) __syncthreads();                         // the previous round's records are no longer needed
+				if (rbase) __syncthreads();                         // the previous round's records and items are no longer needed
 				if (*(volatile uint32_t *)&s_overflow) break;
 				const uint32_t n_round = min(per_round, n_recs - rbase);
-				uint32_t n_eff[2];
+				// ---- stage: records tid and tid + THREADS of the round
+				uint32_t n_items_mine[2];
 #pragma unroll
 				for (int h = 0; h < 2; ++h) {
-					const uint32_t idx = 2u * tid + h;
+					const uint32_t idx = tid + (uint32_t)h * C::THREADS;
 					const bool have = idx < n_round;
 					uint32_t my_n = 0, rhash = 0x80000000u | lane;   // lanes without a record never match anybody
-					SkRec<W> canon;
+					StagedRec<W> canon;
 					if (have) {
 						const uint32_t g_idx = rbase + idx;
 						uint32_t lo = 0, hi = nb;                        // pair of record g_idx: last i with s_rpre[i] <= g_idx
@@ -714,27 +883,40 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 						my_n = (uint32_t)(pre.w[2 * W - 1] >> 56);
 						pre.w[2 * W - 1] &= 0x00ffffffffffffffull;
 						const SkRec<W> rc = tagpu_record_rc(pre, (int)my_n + K - 1);
-						canon = tagpu_record_less<W>(rc, pre) ? rc : pre;
-						canon.w[2 * W - 1] = (canon.w[2 * W - 1] & 0x0000ffffffffffffull) | ((unsigned long long)my_n << 56);
+						const bool flip = tagpu_record_less<W>(rc, pre);
+#pragma unroll
+						for (int q = 0; q < W + 1; ++q) canon.w[q] = flip ? rc.w[q] : pre.w[q];
 						s_rec[idx] = canon;
-						rhash = tagpu_record_hash<W>(canon);
+						uint32_t x = 0;
+#pragma unroll
+						for (int q = 0; q < W + 1; ++q) {
+							x = (x ^ (uint32_t)canon.w[q]) * 0x85ebca6bu;
+							x = (x ^ (uint32_t)(canon.w[q] >> 32)) * 0xc2b2ae35u;
+						}
+						rhash = ((x ^ (x >> 15)) & 0x7fffff00u) | my_n;  // equal records have equal window counts
 					}
 					const uint32_t peers_eq = __match_any_sync(0xffffffffu, rhash);
 					const uint32_t leader = (uint32_t)__ffs(peers_eq) - 1u;
 					__syncwarp();
-					const bool dup = have && leader != lane && tagpu_record_equal<W>(s_rec[2u * (tid - lane + leader) + h], canon);
-					const uint32_t dup_mask = __ballot_sync(0xffffffffu, dup);
-					if (have && !dup) {                                  // multiplicity in bits 48..55 of the staged record
-						const unsigned long long mult = leader == lane ? 1u + (uint32_t)__popc(peers_eq & dup_mask) : 1u;
-						s_rec[idx].w[2 * W - 1] = canon.w[2 * W - 1] | (mult << 48);
+					bool dup = false;
+					if (have && leader != lane) {
+						const StagedRec<W> lead = s_rec[idx - lane + leader];
+						dup = true;
+#pragma unroll
+						for (int q = 0; q < W + 1; ++q) dup = dup && lead.w[q] == canon.w[q];
 					}
-					__syncwarp();
-					n_eff[h] = dup ? 0u : my_n;                          // a duplicate is counted through its representative
+					const uint32_t dup_mask = __ballot_sync(0xffffffffu, dup);
+					uint32_t items = 0;
+					if (have && !dup) {
+						const uint32_t mult = leader == lane ? 1u + (uint32_t)__popc(peers_eq & dup_mask) : 1u;
+						s_meta[idx] = my_n | (mult << 8);
+						items = (my_n + (uint32_t)C::ITEM_WINDOWS - 1u) / (uint32_t)C::ITEM_WINDOWS;
+					}
+					n_items_mine[h] = items;                             // a duplicate is counted through its representative
 				}
-				// block-wide exclusive prefix over the LIVE records only (rank in the high half, windows in the low half of
-				// one packed word): s_live[k] = staged index of the k-th live record, s_scan[k] = live windows before it
-				const uint32_t pair = ((n_eff[0] ? 1u : 0u) + (n_eff[1] ? 1u : 0u)) << 16 | (n_eff[0] + n_eff[1]);
-				uint32_t incl = pair;
+				// ---- items: block-wide exclusive prefix over the items of the live records
+				const uint32_t mine_items = n_items_mine[0] + n_items_mine[1];
+				uint32_t incl = mine_items;
 #pragma unroll
 				for (int d = 1; d < 32; d <<= 1) {
 					uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -743,152 +925,105 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 				if (lane == 31) s_warp_solid[warp] = incl;
 				__syncthreads();
 				const uint32_t wt = lane < N_WARPS ? s_warp_solid[lane] : 0u;
-				const uint32_t tot_packed = __reduce_add_sync(0xffffffffu, wt);
-				const uint32_t total = tot_packed & 0xffffu, n_live = tot_packed >> 16;
-				uint32_t excl = __reduce_add_sync(0xffffffffu, lane < warp ? wt : 0u) + incl - pair;
-				// When the round leaves room behind its records (the usual case), every live record also gets its first
-				// window precomputed — forward and reverse complement — so that re-seeding in the window loop, which
-				// some lane of a warp does in almost every iteration, is two loads instead of funnel shifts and an rc.
-				const bool have_seeds = n_round + n_live <= 2u * C::THREADS;
+				const uint32_t n_items = __reduce_add_sync(0xffffffffu, wt);
+				uint32_t o_item = __reduce_add_sync(0xffffffffu, lane < warp ? wt : 0u) + incl - mine_items;
 #pragma unroll
 				for (int h = 0; h < 2; ++h)
-					if (n_eff[h]) {
-						const uint32_t rank = excl >> 16;
-						s_live[rank] = (uint16_t)(2u * tid + h);
-						s_scan[rank] = (uint16_t)excl;
-						excl += (1u << 16) + n_eff[h];
-						if (have_seeds) {
-							const Key<W> f0 = tagpu_record_window(s_rec[2u * tid + h], 2 * ((int)n_eff[h] - 1), K);
-							const Key<W> r0 = KO::rc(f0, K);
-							SkRec<W> sd;
-							if (W == 1) { sd.w[0] = f0.lo; sd.w[1] = r0.lo; }
-							else { sd.w[0] = f0.lo; sd.w[1] = KO::hi(f0); sd.w[2 * W - 2] = r0.lo; sd.w[2 * W - 1] = KO::hi(r0); }
-							s_rec[n_round + rank] = sd;
-						}
-					}
-				if (tid == 0) s_scan[n_live] = (uint16_t)total;
-				__syncthreads();                                    // staged records + prefix visible to everybody
-				const uint32_t seg = (total + C::THREADS - 1) / C::THREADS;
-				const uint32_t t0 = min(total, tid * seg), t1 = min(total, t0 + seg);
-				uint32_t left = t1 - t0;
-				if (left) {
-					uint32_t lo = 0, hi = n_live;                        // owner of window t0: last live record k with s_scan[k] <= t0
-					while (hi - lo > 1) {
-						const uint32_t mid = (lo + hi) >> 1;
-						if (s_scan[mid] <= t0) lo = mid; else hi = mid;
-					}
-					uint32_t r = lo;
-					const SkRec<W> *rp = s_rec + s_live[r];
-					unsigned long long wl = rp->w[2 * W - 1];
-					int n_r = (int)(wl >> 56), j = (int)(t0 - s_scan[r]);
-					uint32_t mult = (uint32_t)(wl >> 48) & 0xffu;
-					unsigned long long w0 = rp->w[0];
-					Key<W> fw = tagpu_record_window(*rp, 2 * (n_r - 1 - j), K);
-					Key<W> rv = KO::rc(fw, K);
+					for (uint32_t c = 0; c < n_items_mine[h]; ++c)
+						s_item[o_item++] = (uint16_t)((tid + (uint32_t)h * C::THREADS) | (c << 11));
+				TM_ADD(tm_stage);
+				__syncthreads();                                    // staged records, meta words and items visible to everybody
+				// ---- insert: one item per octet and iteration, one window per lane
+				const uint32_t q = lane & 7u;
+				for (uint32_t ibase = warp * 4u; ibase < n_items; ibase += N_WARPS * 4u) {
+					const uint32_t it = ibase + (lane >> 3);
+					if (*(volatile uint32_t *)&s_overflow) break;
+					if (it >= n_items) continue;
+					const uint32_t item = s_item[it];
+					const uint32_t idx = item & 0x7ffu, j = (item >> 11) * (uint32_t)C::ITEM_WINDOWS + q;
+					const uint32_t meta = s_meta[idx], n_r = meta & 0xffu, mult = (meta >> 8) & 0xffu;
+					if (j >= n_r) continue;
+					const StagedRec<W> rec = s_rec[idx];
+					const Key<W> fw = tagpu_staged_window(rec, 2 * (int)(n_r - 1u - j), K);
+					const Key<W> rv = KO::rc(fw, K);
+					const Key<W> key = KO::le(fw, rv) ? fw : rv;
+					const uint32_t h = tagpu_table_hash<W>(key);
+					if (L && (h & ((1u << L) - 1u)) != cls) continue;
+					// probe: the hit / claim decision is the only divergent part
+					const Key<W> stored = KO::bnot(key);
+					uint32_t slot = __umulhi(h, (uint32_t)C::SLOTS);
+					int probes = 0;
 					for (;;) {
-						const Key<W> key = KO::le(fw, rv) ? fw : rv;
-						const uint32_t h = tagpu_table_hash<W>(key);
-						if (!L || (h & ((1u << L) - 1u)) == cls) {
-							// probe: the hit / claim decision is the only divergent part; the count increment is shared
-							const Key<W> stored = KO::bnot(key);
-							uint32_t slot = __umulhi(h, (uint32_t)C::SLOTS);
-							int probes = 0;
-							for (;;) {
-								const Key<W> have = t_key[slot];
-								if (KO::eq(have, stored)) break;
-								if (KO::is_zero(have) || ktab_maybe_torn<W>(have)) {
-									const Key<W> old = ktab_cas<W>(t_key + slot, stored);   // ATOMS.CAS.64 / .128
-									if (KO::is_zero(old) || KO::eq(old, stored)) break;
-								}
-								slot = slot + 1 == C::SLOTS ? 0u : slot + 1;
-								if (++probes > C::MAX_PROBES) { s_overflow = 1; break; }       // table too full: re-run on sub-classes
-							}
-							atomicAdd(t_cnt + slot, mult);
+						const Key<W> have = t_key[slot];
+						if (KO::eq(have, stored)) break;
+						if (KO::is_zero(have) || ktab_maybe_torn<W>(have)) {
+							const Key<W> old = ktab_cas<W>(t_key + slot, stored);   // ATOMS.CAS.64 / .128
+							if (KO::is_zero(old)) { ++n_claimed; break; }
+							if (KO::eq(old, stored)) break;
 						}
-						if (!--left) break;
-						if (++j == n_r) {                                    // next live record: re-seed from the staged record
-							rp = s_rec + s_live[++r];
-							wl = rp->w[2 * W - 1];
-							n_r = (int)(wl >> 56);
-							mult = (uint32_t)(wl >> 48) & 0xffu;
-							j = 0;
-							w0 = rp->w[0];
-							if (have_seeds) {
-								const SkRec<W> sd = s_rec[n_round + r];
-								fw = KO::make(W == 1 ? 0ull : sd.w[1], sd.w[0]);
-								rv = KO::make(W == 1 ? 0ull : sd.w[2 * W - 1], W == 1 ? sd.w[1] : sd.w[2 * W - 2]);
-							} else {
-								fw = tagpu_record_window(*rp, 2 * (n_r - 1), K);
-								rv = KO::rc(fw, K);
-							}
-						} else {                                             // next window of the same record: roll one base
-							const uint32_t c = (uint32_t)(w0 >> (2 * (n_r - 1 - j))) & 3u;
-							fw = KO::push(fw, c, kmask);
-							rv = KO::push_front(rv, 3u - c, K);
-						}
+						slot = slot + 1 == C::SLOTS ? 0u : slot + 1;
+						if (++probes > C::MAX_PROBES) { s_overflow = 1; break; }       // table too full: re-run on sub-classes
 					}
+					// exactly one insert takes a key across the cutoff: the harvest knows its size before it starts
+					const uint32_t before_add = atomicAdd(t_cnt + slot, mult);
+					n_became_solid += (before_add < ci && before_add + mult >= ci) ? 1u : 0u;
 				}
 			}
+			n_claimed = __reduce_add_sync(0xffffffffu, n_claimed);
+			n_became_solid = __reduce_add_sync(0xffffffffu, n_became_solid);
+			if (lane == 0) {
+				if (n_claimed) atomicAdd(&s_claims, n_claimed);
+				if (n_became_solid) atomicAdd(&s_nsolid, n_became_solid);
+			}
+			if (tid == 0) { s_pf = dd.x; s_pf_n = dd.y; }               // next group's buckets (its descriptor has landed): see the prefetch below
 			TM_ADD(tm_insert);
-			__syncthreads();                                        // B2: all inserts of this class are in the table
+			__syncthreads();                                        // B2: all inserts of this class are in the table, counters complete
 			TM_ADD(tm_wait);
-			// ---- harvest (or discard on overflow) and leave the table zeroed
+			// ---- harvest (or discard on overflow) in ONE pass over the table, which is left zeroed.  The number of solid keys
+			// is known (counted by the inserts), so the global output range is requested first and travels during the pass.
 			const bool failed = *(volatile uint32_t *)&s_overflow != 0;
-			uint32_t mine = 0, used = 0;
-			if (!failed)
-				for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) {
-					const uint32_t c = t_cnt[i];
-					mine += c >= ci ? 1u : 0u;
-					used += c ? 1u : 0u;
-				}
-			used = __reduce_add_sync(0xffffffffu, used);
-			if (lane == 0 && used) atomicAdd(&s_claims, used);
-			uint32_t incl = mine;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-				if (lane >= (uint32_t)d) incl += t;
-			}
-			if (lane == 31) s_warp_solid[warp] = incl;
-			TM_ADD(tm_ha);
-			__syncthreads();                                        // B3: per-warp solid totals (and s_claims) are complete
-			// every warp derives its own offset from the per-warp totals (no second scan phase)
-			const uint32_t wt = lane < N_WARPS ? s_warp_solid[lane] : 0u;
-			const uint32_t n_out = __reduce_add_sync(0xffffffffu, wt);
-			const uint32_t before = __reduce_add_sync(0xffffffffu, lane < warp ? wt : 0u);
+			const uint32_t n_out = failed ? 0u : s_nsolid, n_claims = s_claims;
 			const bool staged = n_out <= OUT_CAP;                       // else (huge group) write straight to the global arrays
+			unsigned long long out_base = 0;
 			if (tid == 0) {
-				// the global offset is requested now and consumed after the compaction pass
-				s_out_base = n_out ? atomicAdd(ctr + CTR_SOLID, (unsigned long long)n_out) : 0ull;
-				if (!failed) atomicAdd(ctr + CTR_DISTINCT, (unsigned long long)s_claims);
-				if (n_out) {                                         // directory of the solid list, for the graph stage
-					const uint32_t id = (uint32_t)atomicAdd(ctr + CTR_BLOCKS, 1ull);
-					if (id < blocks_cap) {
-						SolidBlock sb;
-						sb.base = s_out_base; sb.n = n_out; sb.b0 = first_bucket + b0; sb.nbk = nb / world;
-						sb.flags = (L || !staged) ? 1u : 0u;
-						blocks[id] = sb;
-					} else atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_BLOCKS);
+				out_base = n_out ? atomicAdd(ctr + CTR_SOLID, (unsigned long long)n_out) : 0ull;
+				if (!failed) atomicAdd(ctr + CTR_DISTINCT, (unsigned long long)n_claims);
+				if (!staged) s_out_base = out_base;
+			}
+			// while the table is scanned: pull the records of the next group's buckets towards L2 (single GPU: local regions)
+			if (world == 1) {
+				const uint32_t pb = s_pf, pn = s_pf_n, bkt = tid >> 5;
+				if (pb != TAGPU_NONE && bkt < pn) {
+					const char *line = reinterpret_cast<const char *>(peers.regions[0] + ((size_t)first_bucket + pb + bkt) * cap_records) + (size_t)lane * 128u;
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
 				}
-				// next hash class: children of a failed class first, then whatever is left on the stack
-				uint32_t sp = s_sp;
-				if (failed) {
-					if (L >= 16 || sp + 2 > 64) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_TABLE_FULL);
-					else {
-						s_stack[sp++] = ((L + 1) << 24) | cls;
-						s_stack[sp++] = ((L + 1) << 24) | (cls + (1u << L));
-					}
-				}
-				s_top = sp ? s_stack[--sp] : TOP_NONE;
-				s_sp = sp;
-				s_claims = 0; s_overflow = 0;
 			}
 			if (!staged) __syncthreads();                           // (rare) the direct path needs s_out_base now
 			const unsigned long long gbase = staged ? 0ull : s_out_base;
-			uint32_t o = before + incl - mine;
+			// every thread takes the slots tid, tid + THREADS, ...: all their counts are loaded first (independent loads), the
+			// thread's solid keys get consecutive places behind one warp-wide prefix sum and ONE shared-memory atomic per warp
 			unsigned long long sum = 0;
-			for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) {
-				const uint32_t c = t_cnt[i];
+			constexpr int HR = (C::SLOTS + C::THREADS - 1) / C::THREADS;
+			uint32_t hc[HR];
+			uint32_t n_mine = 0;
+#pragma unroll
+			for (int r = 0; r < HR; ++r) {
+				const uint32_t i = tid + (uint32_t)r * C::THREADS;
+				hc[r] = i < (uint32_t)C::SLOTS ? t_cnt[i] : 0u;
+				n_mine += (!failed && hc[r] >= ci && hc[r] != 0u) ? 1u : 0u;
+			}
+			uint32_t h_incl = n_mine;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xffffffffu, h_incl, d);
+				if (lane >= (uint32_t)d) h_incl += t;
+			}
+			uint32_t o = 0;
+			if (lane == 31 && h_incl) o = atomicAdd(&s_nout, h_incl);
+			o = __shfl_sync(0xffffffffu, o, 31) + h_incl - n_mine;
+#pragma unroll
+			for (int r = 0; r < HR; ++r) {
+				const uint32_t i = tid + (uint32_t)r * C::THREADS, c = hc[r];
 				if (c) {
 					if (!failed && c >= ci) {
 						const Key<W> key = KO::bnot(t_key[i]);
@@ -904,11 +1039,35 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 #pragma unroll
 			for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
 			if (lane == 0 && sum) atomicAdd(ctr + CTR_SUM_SOLID, sum);
+			if (tid == 0) {
+				s_out_base = out_base;
+				if (n_out) {                                         // directory of the solid list, for the graph stage
+					const uint32_t id = (uint32_t)atomicAdd(ctr + CTR_BLOCKS, 1ull);
+					if (id < blocks_cap) {
+						SolidBlock sb;
+						sb.base = out_base; sb.n = n_out; sb.b0 = first_bucket + b0; sb.nbk = nb / world;
+						sb.flags = (L || !staged) ? 1u : 0u;
+						blocks[id] = sb;
+					} else atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_BLOCKS);
+				}
+				// next hash class: children of a failed class first, then whatever is left on the stack
+				uint32_t sp = s_sp;
+				if (failed) {
+					if (L >= 16 || sp + 2 > 64) atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_TABLE_FULL);
+					else {
+						s_stack[sp++] = ((L + 1) << 24) | cls;
+						s_stack[sp++] = ((L + 1) << 24) | (cls + (1u << L));
+					}
+				}
+				s_top = sp ? s_stack[--sp] : TOP_NONE;
+				s_sp = sp;
+			}
 			TM_ADD(tm_hb);
 #ifdef TAGPU_TIMING
 			tm_iters += 1; tm_failed += failed ? 1 : 0;
 #endif
 			__syncthreads();                                        // B4: table zeroed, compacted output + s_out_base + s_top visible
+			if (tid == 0) { s_claims = 0; s_overflow = 0; s_nsolid = 0; s_nout = 0; }   // (read by everybody before B4; next used after the next barrier)
 			if (staged) {
 				const unsigned long long base = s_out_base;
 				for (uint32_t i = tid; i < n_out; i += C::THREADS)
@@ -923,13 +1082,14 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 		}
 	}
 #ifdef TAGPU_TIMING
-	if (lane == 0) {          // cycles summed over all warps: setup / insert / wait at the post-insert barrier / harvest
+	if (lane == 0) {          // cycles summed over all warps: setup / stage / insert / wait at the post-insert barrier / harvest
 		atomicAdd(ctr + CTR_JUMP_FLAGS + 48, (unsigned long long)tm_setup);
 		atomicAdd(ctr + CTR_JUMP_FLAGS + 49, (unsigned long long)tm_insert);
 		atomicAdd(ctr + CTR_JUMP_FLAGS + 50, (unsigned long long)tm_wait);
 		atomicAdd(ctr + CTR_JUMP_FLAGS + 51, (unsigned long long)tm_harvest);
 		atomicAdd(ctr + CTR_JUMP_FLAGS + 52, (unsigned long long)tm_ha);
 		atomicAdd(ctr + CTR_JUMP_FLAGS + 53, (unsigned long long)tm_hb);
+		atomicAdd(ctr + CTR_JUMP_FLAGS + 56, (unsigned long long)tm_stage);
 		if (warp == 0) { atomicAdd(ctr + CTR_JUMP_FLAGS + 54, (unsigned long long)tm_iters); atomicAdd(ctr + CTR_JUMP_FLAGS + 55, (unsigned long long)tm_failed); }
 	}
 #endif

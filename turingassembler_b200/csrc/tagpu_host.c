@@ -28,6 +28,7 @@ void tagpu_pinned_free(void *p);
 int tagpu_ctx_k(tagpu_ctx *ctx);
 int tagpu_ctx_K(tagpu_ctx *ctx);
 int tagpu_ctx_cutoff(tagpu_ctx *ctx);
+void tagpu_set_source_progress(tagpu_ctx *ctx, uint64_t (*ready)(void *), void *arg);
 
 #define TAGPU_FATAL(...)                                                        \
 	do {                                                                    \
@@ -203,75 +204,155 @@ static void run_tasks(size_t n_tasks, int n_threads, void (*fn)(size_t, void *),
 		pthread_join(th[i], NULL);
 }
 
-/* ---- plain (uncompressed) FASTQ, exact and parallel: the file is cut into chunks; newlines are counted per chunk, a
- * prefix sum gives every chunk the number of the line it starts in, and then every chunk copies the bytes that lie on
- * sequence lines (line 2 of every 4, /root/reference/src/get_buffer.c:339-348) — no record-boundary guessing. */
-#define INGEST_CHUNK ((size_t)16 << 20)
+/* ---- plain (uncompressed) FASTQ, exact and parallel.  The file is cut into chunks.  Pass 1 (one task per chunk) builds
+ * the chunk's newline index — the offsets of its '\n' bytes, found 32 bytes at a time — so the text is scanned ONCE; a
+ * prefix sum over the counts gives every chunk the number of the line it starts in.  Sizing then only walks the index
+ * (sequence = line 2 of every 4, /root/reference/src/get_buffer.c:339-348 — no record-boundary guessing), and pass 2
+ * copies the sequence lines, chunk by chunk in stream order, while the caller may already upload the finished prefix
+ * (tagpu_ingest_ready). */
+#define INGEST_CHUNK ((size_t)4 << 20)
 
 struct pfq {
 	struct read_file *f;
-	int fd;
 	size_t n_chunks;
 	int mapped;        /* txt is an mmap of the file */
 	size_t *nl;        /* newlines in chunk, then: line number of the chunk's first byte */
+	size_t *n_idx;     /* entries of idx[c] */
+	uint32_t **idx;    /* newline offsets relative to the chunk start */
 	size_t *out;       /* sequence bytes of the chunk, then: their offset in dst */
+	unsigned char *has_cr; /* the chunk holds a '\r' somewhere: its lines need the CRLF checks */
 };
 
 static void pfq_read(size_t c, void *raw)
 {
 	struct pfq *p = raw;
 	size_t lo = c * INGEST_CHUNK, hi = lo + INGEST_CHUNK < p->f->n_txt ? lo + INGEST_CHUNK : p->f->n_txt;
+	int fd = open(p->f->path, O_RDONLY);
+	if (fd < 0)
+		TAGPU_FATAL("cannot open %s", p->f->path);
 	while (lo < hi) {
-		ssize_t r = pread(p->fd, p->f->txt + lo, hi - lo, (off_t)lo);
+		ssize_t r = pread(fd, p->f->txt + lo, hi - lo, (off_t)lo);
 		if (r <= 0)
 			TAGPU_FATAL("cannot read %s", p->f->path);
 		lo += (size_t)r;
 	}
+	close(fd);
 }
 
-static void pfq_count_nl(size_t c, void *raw)
+static uint32_t *idx_room(uint32_t *v, size_t n, size_t *cap, size_t want)
 {
-	struct pfq *p = raw;
-	const uint8_t *t = p->f->txt;
-	size_t lo = c * INGEST_CHUNK, hi = lo + INGEST_CHUNK < p->f->n_txt ? lo + INGEST_CHUNK : p->f->n_txt, n = 0;
-	while (lo < hi) {
-		const uint8_t *q = memchr(t + lo, '\n', hi - lo);
+	if (n + want <= *cap)
+		return v;
+	while (n + want > *cap)
+		*cap = *cap ? *cap * 2 : 65536;
+	v = realloc(v, *cap * sizeof(uint32_t));
+	if (!v)
+		TAGPU_FATAL("out of host memory for the newline index");
+	return v;
+}
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2")))
+static uint32_t *scan_newlines_avx2(const uint8_t *t, size_t n, uint32_t *v, size_t *n_out, size_t *cap, int *has_cr)
+{
+	const __m256i nl = _mm256_set1_epi8('\n'), cr = _mm256_set1_epi8('\r');
+	__m256i any_cr = _mm256_setzero_si256();
+	size_t i = 0, k = *n_out;
+	for (; i + 32 <= n; i += 32) {
+		const __m256i x = _mm256_loadu_si256((const __m256i *)(t + i));
+		unsigned m = (unsigned)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, nl));
+		any_cr = _mm256_or_si256(any_cr, _mm256_cmpeq_epi8(x, cr));
+		if (!m)
+			continue;
+		v = idx_room(v, k, cap, 32);
+		while (m) {
+			v[k++] = (uint32_t)(i + (size_t)__builtin_ctz(m));
+			m &= m - 1;
+		}
+	}
+	*has_cr = _mm256_movemask_epi8(any_cr) != 0;
+	for (; i < n; ++i) {
+		if (t[i] == '\r')
+			*has_cr = 1;
+		if (t[i] == '\n') {
+			v = idx_room(v, k, cap, 1);
+			v[k++] = (uint32_t)i;
+		}
+	}
+	*n_out = k;
+	return v;
+}
+#endif
+
+/* newline offsets of t[0, n); *has_cr = 0 only if no '\r' occurs in it (then no line of the chunk needs a CRLF check) */
+static uint32_t *scan_newlines(const uint8_t *t, size_t n, size_t *n_out, int *has_cr)
+{
+	uint32_t *v = NULL;
+	size_t cap = 0, k = 0;
+#if defined(__x86_64__)
+	if (__builtin_cpu_supports("avx2")) {
+		v = scan_newlines_avx2(t, n, v, &k, &cap, has_cr);
+		*n_out = k;
+		return v;
+	}
+#endif
+	*has_cr = 1;
+	size_t lo = 0;
+	while (lo < n) {
+		const uint8_t *q = memchr(t + lo, '\n', n - lo);
 		if (!q)
 			break;
-		++n;
+		v = idx_room(v, k, &cap, 1);
+		v[k++] = (uint32_t)(q - t);
 		lo = (size_t)(q - t) + 1;
 	}
-	p->nl[c] = n;
+	*n_out = k;
+	return v;
 }
 
-/* bytes [lo, hi) of the chunk that lie on sequence lines; with dst != NULL they are copied.  A '\r' right before the
- * line's '\n' is dropped; a last sequence line without a newline gets one. */
+static void pfq_index(size_t c, void *raw)
+{
+	struct pfq *p = raw;
+	const size_t lo = c * INGEST_CHUNK, hi = lo + INGEST_CHUNK < p->f->n_txt ? lo + INGEST_CHUNK : p->f->n_txt;
+	int has_cr;
+	p->idx[c] = scan_newlines(p->f->txt + lo, hi - lo, &p->n_idx[c], &has_cr);
+	p->has_cr[c] = (unsigned char)has_cr;
+	p->nl[c] = p->n_idx[c];
+}
+
+/* bytes [lo, hi) of the chunk that lie on sequence lines; with dst != NULL they are copied.  Lines are taken from the
+ * chunk's newline index.  A '\r' right before the line's '\n' is dropped; a last sequence line without a newline gets one. */
 static size_t pfq_walk(struct pfq *p, size_t c, uint8_t *dst)
 {
 	const uint8_t *t = p->f->txt;
-	const size_t n = p->f->n_txt;
-	size_t lo = c * INGEST_CHUNK, hi = lo + INGEST_CHUNK < n ? lo + INGEST_CHUNK : n, line = p->nl[c], o = 0;
-	while (lo < hi) {
-		const uint8_t *q = memchr(t + lo, '\n', hi - lo);
-		size_t e = q ? (size_t)(q - t) : hi;                 /* end of this line's bytes inside the chunk */
-		if ((line & 3) == 1) {
-			size_t len = e - lo;
-			const int ends_line = q != NULL || e == n;       /* the line really ends at e (not just the chunk) */
-			if (len && ends_line && t[e - 1] == '\r')
-				--len;
-			else if (len && !ends_line && e == hi && t[e - 1] == '\r' && hi < n && t[hi] == '\n')
-				--len;                                   /* "\r" | "\n" split by the chunk border */
-			if (dst) memcpy(dst + o, t + lo, len);
-			o += len;
-			if (q || e == n) {                               /* terminate the read (also when the file lacks the last newline) */
-				if (dst) dst[o] = '\n';
-				++o;
-			}
+	const size_t n = p->f->n_txt, base = c * INGEST_CHUNK;
+	const uint32_t *ix = p->idx[c];
+	const size_t n_ix = p->n_idx[c];
+	size_t lo = base, hi = lo + INGEST_CHUNK < n ? lo + INGEST_CHUNK : n, line = p->nl[c], o = 0;
+	const int cr = p->has_cr[c];
+	/* segment i of the chunk = [previous newline + 1, newline i), the last one runs to the end of the chunk; only the
+	 * segments on sequence lines are looked at: i == (1 - line) mod 4 */
+	for (size_t i = (5 - (line & 3)) & 3; i <= n_ix; i += 4) {
+		const size_t s = i ? base + ix[i - 1] + 1 : lo;
+		const int has_nl = i < n_ix;
+		const size_t e = has_nl ? base + ix[i] : hi;         /* end of this line's bytes inside the chunk */
+		if (s >= hi && !has_nl)
+			break;                                           /* the chunk ends exactly behind a newline */
+		size_t len = e - s;
+		const int ends_line = has_nl || e == n;              /* the line really ends at e (not just the chunk) */
+		if (!cr)
+			;                                                /* no '\r' in this chunk: nothing to strip */
+		else if (len && ends_line && t[e - 1] == '\r')
+			--len;
+		else if (len && !ends_line && e == hi && t[e - 1] == '\r' && hi < n && t[hi] == '\n')
+			--len;                                           /* "\r" | "\n" split by the chunk border */
+		if (dst) memcpy(dst + o, t + s, len);
+		o += len;
+		if (ends_line) {                                     /* terminate the read (also when the file lacks the last newline) */
+			if (dst) dst[o] = '\n';
+			++o;
 		}
-		if (!q)
-			break;
-		++line;
-		lo = e + 1;
 	}
 	return o;
 }
@@ -282,13 +363,7 @@ static void pfq_size(size_t c, void *raw)
 	p->out[c] = pfq_walk(p, c, NULL);
 }
 
-static void pfq_copy(size_t c, void *raw)
-{
-	struct pfq *p = raw;
-	pfq_walk(p, c, p->f->dst + p->out[c]);
-}
-
-/* returns 1 and fills f->txt / n_txt / n_seq (+ keeps per-chunk tables in *keep) if the file is plain FASTQ */
+/* returns 1 and fills f->txt / n_txt / n_seq (+ the per-chunk tables in *p) if the file is plain FASTQ */
 static int pfq_open(struct read_file *f, int n_threads, struct pfq *p)
 {
 	int fd = open(f->path, O_RDONLY);
@@ -302,32 +377,39 @@ static int pfq_open(struct read_file *f, int n_threads, struct pfq *p)
 	}
 	memset(p, 0, sizeof(*p));
 	p->f = f;
-	p->fd = fd;
 	f->n_txt = (size_t)st.st_size;
 	p->n_chunks = (f->n_txt + INGEST_CHUNK - 1) / INGEST_CHUNK;
 	p->nl = calloc(p->n_chunks + 1, sizeof(size_t));
+	p->n_idx = calloc(p->n_chunks + 1, sizeof(size_t));
+	p->idx = calloc(p->n_chunks + 1, sizeof(uint32_t *));
 	p->out = calloc(p->n_chunks + 1, sizeof(size_t));
+	p->has_cr = calloc(p->n_chunks + 1, 1);
 	/* map the file (page-cache pages, no copy); fall back to reading it into memory */
 	void *m = mmap(NULL, f->n_txt, PROT_READ, MAP_PRIVATE, fd, 0);
+	close(fd);
 	if (m != MAP_FAILED) {
 		f->txt = m;
 		p->mapped = 1;
-		madvise(m, f->n_txt, MADV_SEQUENTIAL);
 	} else {
 		f->txt = malloc(f->n_txt + 1);
 		if (!f->txt)
 			TAGPU_FATAL("out of host memory reading %s", f->path);
 		run_tasks(p->n_chunks, n_threads, pfq_read, p);
 	}
-	close(fd);
-	run_tasks(p->n_chunks, n_threads, pfq_count_nl, p);
-	size_t acc = 0;
-	for (size_t c = 0; c < p->n_chunks; ++c) { size_t v = p->nl[c]; p->nl[c] = acc; acc += v; }
-	run_tasks(p->n_chunks, n_threads, pfq_size, p);
-	acc = 0;
-	for (size_t c = 0; c < p->n_chunks; ++c) { size_t v = p->out[c]; p->out[c] = acc; acc += v; }
-	f->n_seq = acc;
 	return 1;
+}
+
+static void pfq_close(struct pfq *p)
+{
+	if (p->mapped) munmap(p->f->txt, p->f->n_txt);
+	else free(p->f->txt);
+	for (size_t c = 0; c < p->n_chunks; ++c)
+		free(p->idx[c]);
+	free(p->idx);
+	free(p->n_idx);
+	free(p->nl);
+	free(p->out);
+	free(p->has_cr);
 }
 
 static void *ingest_phase1(void *raw)
@@ -422,47 +504,152 @@ int tagpu_pack_stream(const uint8_t *stream, uint64_t n_bytes, uint8_t *packed, 
 	return 0;
 }
 
-int64_t tagpu_load_reads(int n_files, char **files, int n_threads, uint8_t **stream)
+/* ---- ingest as an object: open (index + sizes: the stream length is known), start (copy workers fill the caller's buffer
+ * in stream order), ready (bytes of the stream PREFIX that are complete — the upload chases the parser with it), finish. */
+struct ing_task {
+	int file;
+	size_t chunk;      /* plain FASTQ: chunk of the file; other formats: the whole file */
+	size_t end;        /* stream offset behind this task's bytes */
+};
+
+struct tagpu_ingest {
+	int n_files, n_threads, n_workers;
+	struct read_file *f;
+	struct pfq *pq;
+	int *plain;
+	size_t total, n_tasks, next, cursor;
+	struct ing_task *task;
+	volatile unsigned char *done;
+	pthread_t *th;
+};
+
+static void *ingest_worker(void *raw)
+{
+	struct tagpu_ingest *g = raw;
+	for (;;) {
+		const size_t t = __sync_fetch_and_add(&g->next, 1);
+		if (t >= g->n_tasks)
+			return NULL;
+		const struct ing_task *k = g->task + t;
+		if (g->plain[k->file]) {
+			struct pfq *p = g->pq + k->file;
+			pfq_walk(p, k->chunk, p->f->dst + p->out[k->chunk]);
+		} else {
+			ingest_phase2(g->f + k->file);
+		}
+		__sync_synchronize();
+		g->done[t] = 1;
+	}
+}
+
+struct tagpu_ingest *tagpu_ingest_open(int n_files, char **files, int n_threads)
 {
 	if (n_threads < 1) n_threads = 1;
-	struct read_file *f = calloc(n_files, sizeof(*f));
-	struct pfq *pq = calloc(n_files, sizeof(*pq));
-	int *plain = calloc(n_files, sizeof(int));
-	pthread_t *th = calloc(n_files, sizeof(pthread_t));
+	if (n_threads > 64) n_threads = 64;
+	struct tagpu_ingest *g = calloc(1, sizeof(*g));
+	g->n_files = n_files;
+	g->n_threads = n_threads;
+	g->f = calloc(n_files ? n_files : 1, sizeof(*g->f));
+	g->pq = calloc(n_files ? n_files : 1, sizeof(*g->pq));
+	g->plain = calloc(n_files ? n_files : 1, sizeof(int));
+	pthread_t *th = calloc(n_files ? n_files : 1, sizeof(pthread_t));
 	/* plain FASTQ files: parallel inside the file; everything else (gzip, FASTA): one thread per file */
 	for (int i = 0; i < n_files; ++i) {
-		f[i].path = files[i];
-		plain[i] = pfq_open(f + i, n_threads, pq + i);
+		g->f[i].path = files[i];
+		g->plain[i] = pfq_open(g->f + i, n_threads, g->pq + i);
+		if (!g->plain[i]) pthread_create(th + i, NULL, ingest_phase1, g->f + i);
 	}
-	for (int i = 0; i < n_files; ++i)
-		if (!plain[i]) pthread_create(th + i, NULL, ingest_phase1, f + i);
-	size_t total = 0;
+	const int trace = getenv("TAGPU_TRACE_INGEST") != NULL;
+	double t_a = now_s(), t_idx = 0, t_size = 0;
 	for (int i = 0; i < n_files; ++i) {
-		if (!plain[i]) pthread_join(th[i], NULL);
-		total += f[i].n_seq;
+		if (!g->plain[i]) continue;
+		struct pfq *p = g->pq + i;
+		run_tasks(p->n_chunks, n_threads, pfq_index, p);
+		t_idx += now_s() - t_a; t_a = now_s();
+		size_t acc = 0;
+		for (size_t c = 0; c < p->n_chunks; ++c) { size_t v = p->nl[c]; p->nl[c] = acc; acc += v; }
+		run_tasks(p->n_chunks, n_threads, pfq_size, p);
+		acc = 0;
+		for (size_t c = 0; c < p->n_chunks; ++c) { size_t v = p->out[c]; p->out[c] = acc; acc += v; }
+		p->out[p->n_chunks] = acc;
+		g->f[i].n_seq = acc;
+		t_size += now_s() - t_a; t_a = now_s();
 	}
-	uint8_t *s = stream_buffer(total + 64);
-	size_t o = 0;
+	if (trace) fprintf(stderr, "[tagpu] ingest: newline index %.1f ms, sizing %.1f ms\n", t_idx * 1e3, t_size * 1e3);
 	for (int i = 0; i < n_files; ++i) {
-		f[i].dst = s + o;
-		o += f[i].n_seq;
-		if (!plain[i]) pthread_create(th + i, NULL, ingest_phase2, f + i);
+		if (!g->plain[i]) pthread_join(th[i], NULL);
+		g->total += g->f[i].n_seq;
+		g->n_tasks += g->plain[i] ? g->pq[i].n_chunks : 1;
 	}
-	for (int i = 0; i < n_files; ++i) {
-		if (plain[i]) {
-			run_tasks(pq[i].n_chunks, n_threads, pfq_copy, pq + i);
-			if (pq[i].mapped) munmap(f[i].txt, f[i].n_txt);
-			else free(f[i].txt);
-			free(pq[i].nl);
-			free(pq[i].out);
-		}
-	}
-	for (int i = 0; i < n_files; ++i)
-		if (!plain[i]) pthread_join(th[i], NULL);
-	free(f);
-	free(pq);
-	free(plain);
 	free(th);
+	g->task = calloc(g->n_tasks ? g->n_tasks : 1, sizeof(*g->task));
+	g->done = calloc(g->n_tasks ? g->n_tasks : 1, 1);
+	size_t t = 0, o = 0;
+	for (int i = 0; i < n_files; ++i) {
+		if (g->plain[i]) {
+			for (size_t c = 0; c < g->pq[i].n_chunks; ++c, ++t) {
+				g->task[t].file = i;
+				g->task[t].chunk = c;
+				g->task[t].end = o + g->pq[i].out[c + 1];
+			}
+		} else {
+			g->task[t].file = i;
+			g->task[t].end = o + g->f[i].n_seq;
+			++t;
+		}
+		o += g->f[i].n_seq;
+	}
+	return g;
+}
+
+uint64_t tagpu_ingest_bytes(const struct tagpu_ingest *g) { return g->total; }
+
+void tagpu_ingest_start(struct tagpu_ingest *g, uint8_t *dst)
+{
+	size_t o = 0;
+	for (int i = 0; i < g->n_files; ++i) {
+		g->f[i].dst = dst + o;
+		o += g->f[i].n_seq;
+	}
+	g->n_workers = g->n_tasks < (size_t)g->n_threads ? (int)g->n_tasks : g->n_threads;
+	g->th = calloc(g->n_workers ? g->n_workers : 1, sizeof(pthread_t));
+	for (int i = 0; i < g->n_workers; ++i)
+		pthread_create(g->th + i, NULL, ingest_worker, g);
+}
+
+/* bytes of the stream prefix that are complete; monotone; to be polled by ONE thread (void * so that it can serve as the
+ * progress callback of tagpu_set_source_progress) */
+uint64_t tagpu_ingest_ready(void *raw)
+{
+	struct tagpu_ingest *g = raw;
+	while (g->cursor < g->n_tasks && g->done[g->cursor])
+		++g->cursor;
+	__sync_synchronize();
+	return g->cursor == g->n_tasks ? g->total : (g->cursor ? g->task[g->cursor - 1].end : 0);
+}
+
+void tagpu_ingest_finish(struct tagpu_ingest *g)
+{
+	for (int i = 0; i < g->n_workers; ++i)
+		pthread_join(g->th[i], NULL);
+	for (int i = 0; i < g->n_files; ++i)
+		if (g->plain[i]) pfq_close(g->pq + i);
+	free(g->th);
+	free(g->task);
+	free((void *)g->done);
+	free(g->f);
+	free(g->pq);
+	free(g->plain);
+	free(g);
+}
+
+int64_t tagpu_load_reads(int n_files, char **files, int n_threads, uint8_t **stream)
+{
+	struct tagpu_ingest *g = tagpu_ingest_open(n_files, files, n_threads);
+	const size_t total = g->total;
+	uint8_t *s = stream_buffer(total + 64);
+	tagpu_ingest_start(g, s);
+	tagpu_ingest_finish(g);
 	*stream = s;
 	return (int64_t)total;
 }
@@ -789,17 +976,37 @@ static int64_t gather_files(int n_files, char **files_1, char **files_2, int n_t
 	return n;
 }
 
+/* files_1[0..n) ++ files_2[0..n) (/root/reference/src/kmer_build.c:733-735) opened for ingest: index + sizes done, the
+ * stream length known; the copy into the pinned stream buffer then runs while the GPU layer already uploads the finished
+ * prefix (tagpu_set_source_progress) */
+static struct tagpu_ingest *open_pairs(int n_files, char **files_1, char **files_2, int n_threads)
+{
+	if (n_files < 0)
+		TAGPU_FATAL("n_files < 0 (contig-file mode) is not supported by the GPU path");
+	char **all = malloc(2 * (size_t)n_files * sizeof(char *) + 1);
+	memcpy(all, files_1, n_files * sizeof(char *));
+	memcpy(all + n_files, files_2, n_files * sizeof(char *));
+	struct tagpu_ingest *ing = tagpu_ingest_open(2 * n_files, all, n_threads);
+	free(all);
+	return ing;
+}
+
 static void stage_entry(int ksize, int n_threads, int n_files, char **files_1, char **files_2, char *work_dir,
 			struct asm_graph_t *g, int skip_counts)
 {
 	tagpu_ctx *ctx = global_ctx();
 	double t0 = now_s();
-	uint8_t *stream;
-	int64_t n = gather_files(n_files, files_1, files_2, n_threads, &stream);
+	struct tagpu_ingest *ing = open_pairs(n_files, files_1, files_2, n_threads);
+	const uint64_t n = tagpu_ingest_bytes(ing);
+	uint8_t *stream = stream_buffer(n + 64);
 	double t1 = now_s();
+	/* the copy workers fill `stream` in order; pass 1 on the GPU chases them chunk by chunk */
+	tagpu_ingest_start(ing, stream);
 	tagpu_set_skip_counts(ctx, skip_counts);
-	if (tagpu_build_host(ctx, stream, (uint64_t)n, ksize))
+	tagpu_set_source_progress(ctx, tagpu_ingest_ready, ing);
+	if (tagpu_build_host(ctx, stream, n, ksize))
 		TAGPU_FATAL("GPU graph build failed: %s", tagpu_last_error(ctx));
+	tagpu_ingest_finish(ing);
 	tagpu_free_reads(stream);
 	double t2 = now_s();
 	if (getenv("TAGPU_WRITE_KMC_DB") && tagpu_write_kmc_db(ctx, work_dir))
@@ -814,7 +1021,7 @@ static void stage_entry(int ksize, int n_threads, int n_files, char **files_1, c
 	if (tagpu_fill_asm_graph(ctx, g))
 		TAGPU_FATAL("cannot materialise the assembly graph: %s", tagpu_last_error(ctx));
 	double t3 = now_s();
-	fprintf(stderr, "[tagpu] k=%d: %lu (k+1)-mer instances, %lu solid; ingest %.3f s, H2D+GPU %.3f s (device %.3f ms), "
+	fprintf(stderr, "[tagpu] k=%d: %lu (k+1)-mer instances, %lu solid; read index %.3f s, parse + H2D + GPU %.3f s (device %.3f ms), "
 			"graph materialisation %.3f s\n", ksize, (unsigned long)st.n_instances, (unsigned long)st.n_solid,
 		t1 - t0, t2 - t1, st.ms_total, t3 - t2);
 }
@@ -890,10 +1097,14 @@ int KMC_build_kmer_database(int ksize, const char *working_dir, int n_threads, i
 {
 	(void)mmem;
 	tagpu_ctx *ctx = global_ctx();
-	uint8_t *stream;
-	int64_t n = tagpu_load_reads(n_files, files, n_threads, &stream);
-	if (tagpu_count_host(ctx, stream, (uint64_t)n, ksize))
+	struct tagpu_ingest *ing = tagpu_ingest_open(n_files, files, n_threads);
+	const uint64_t n = tagpu_ingest_bytes(ing);
+	uint8_t *stream = stream_buffer(n + 64);
+	tagpu_ingest_start(ing, stream);
+	tagpu_set_source_progress(ctx, tagpu_ingest_ready, ing);
+	if (tagpu_count_host(ctx, stream, n, ksize))
 		TAGPU_FATAL("GPU k-mer counting failed: %s", tagpu_last_error(ctx));
+	tagpu_ingest_finish(ing);
 	tagpu_free_reads(stream);
 	if (tagpu_write_kmc_db(ctx, working_dir))
 		TAGPU_FATAL("cannot write the KMC database into %s", working_dir);
@@ -905,4 +1116,118 @@ int KMC_arg_kmer_count(int argc, char *argv[])
 	(void)argc; (void)argv;
 	fprintf(stderr, "[tagpu] KMC_arg_kmer_count is not on the hot path and is not implemented\n");
 	return -1;
+}
+
+/* ------------------------------------------------------------------ intra-node rendezvous for the multi-GPU phases
+ * The ranks of a multi-GPU build are processes on ONE box (include/tagpu.h "multi-GPU").  Between the phases of a step they
+ * need a barrier and an all-gather of a handful of counters; doing that with a collective library costs tens of
+ * microseconds and a device round trip each time, several times per step of a few milliseconds.  This is the same thing
+ * over a POSIX shared-memory segment: a sense-reversing barrier (spin, then yield) and double-buffered slots of 8 values
+ * per rank.  Rank 0 creates the segment under a name the host program distributes (torch.distributed broadcast, MPI, ...). */
+#include <sched.h>
+
+#define TAGPU_SHM_VALUES 8
+#define TAGPU_SHM_MAX_RANKS 64
+
+struct tagpu_shm_seg {
+	volatile uint32_t count, gen;
+	uint32_t world, pad;
+	volatile uint64_t slot[2][TAGPU_SHM_MAX_RANKS][TAGPU_SHM_VALUES];
+};
+
+struct tagpu_shm {
+	struct tagpu_shm_seg *seg;
+	int rank, world, parity, owner;
+	char name[128];
+};
+
+struct tagpu_shm *tagpu_shm_open(const char *name, int rank, int world)
+{
+	if (world < 1 || world > TAGPU_SHM_MAX_RANKS || rank < 0 || rank >= world)
+		return NULL;
+	struct tagpu_shm *s = calloc(1, sizeof(*s));
+	snprintf(s->name, sizeof(s->name), "/%s", name[0] == '/' ? name + 1 : name);
+	s->rank = rank;
+	s->world = world;
+	int fd = -1;
+	if (rank == 0) {
+		shm_unlink(s->name);
+		fd = shm_open(s->name, O_CREAT | O_EXCL | O_RDWR, 0600);
+		if (fd < 0 || ftruncate(fd, sizeof(struct tagpu_shm_seg)) != 0) {
+			perror("tagpu_shm_open");
+			free(s);
+			return NULL;
+		}
+		s->owner = 1;
+	} else {
+		for (int tries = 0; tries < 200000 && fd < 0; ++tries) {          /* up to ~20 s for rank 0 to get there */
+			fd = shm_open(s->name, O_RDWR, 0600);
+			struct stat st;
+			if (fd >= 0 && (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(struct tagpu_shm_seg))) {
+				close(fd);
+				fd = -1;
+			}
+			if (fd < 0) usleep(100);
+		}
+		if (fd < 0) {
+			free(s);
+			return NULL;
+		}
+	}
+	s->seg = mmap(NULL, sizeof(struct tagpu_shm_seg), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	close(fd);
+	if (s->seg == MAP_FAILED) {
+		free(s);
+		return NULL;
+	}
+	if (rank == 0) {
+		s->seg->world = (uint32_t)world;                          /* (a fresh segment is zero-filled) */
+		__sync_synchronize();
+	}
+	return s;
+}
+
+void tagpu_shm_barrier(struct tagpu_shm *s)
+{
+	struct tagpu_shm_seg *g = s->seg;
+	const uint32_t gen = g->gen;
+	if (__sync_add_and_fetch(&g->count, 1) == (uint32_t)s->world) {
+		g->count = 0;
+		__sync_synchronize();
+		g->gen = gen + 1;
+	} else {
+		for (unsigned spins = 0; g->gen == gen; ++spins) {
+			if (spins < 4096) __builtin_ia32_pause();
+			else sched_yield();
+		}
+	}
+	__sync_synchronize();
+}
+
+/* all[r * n + i] = value i of rank r; n <= 8.  Contains one barrier: on return every rank has contributed. */
+int tagpu_shm_allgather(struct tagpu_shm *s, const uint64_t *mine, int n, uint64_t *all)
+{
+	if (n < 0 || n > TAGPU_SHM_VALUES)
+		return -1;
+	struct tagpu_shm_seg *g = s->seg;
+	const int p = s->parity;
+	for (int i = 0; i < n; ++i)
+		g->slot[p][s->rank][i] = mine[i];
+	__sync_synchronize();
+	tagpu_shm_barrier(s);
+	for (int r = 0; r < s->world; ++r)
+		for (int i = 0; i < n; ++i)
+			all[r * n + i] = g->slot[p][r][i];
+	s->parity = p ^ 1;    /* the slots of this call are only overwritten two calls later: everybody has read them by then */
+	return 0;
+}
+
+void tagpu_shm_close(struct tagpu_shm *s)
+{
+	if (!s)
+		return;
+	munmap(s->seg, sizeof(struct tagpu_shm_seg));
+	if (s->owner)
+		shm_unlink(s->name);
+	free(s);
 }

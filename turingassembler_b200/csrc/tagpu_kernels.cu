@@ -10,6 +10,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include "../../include/tagpu.h"
 #include "tagpu_contract.cuh"
@@ -19,7 +20,7 @@
 #include "tagpu_graph.cuh"
 #include "tagpu_key.cuh"
 
-constexpr int TAGPU_UPLOAD_CHUNKS = 16;      // pieces the host read stream is uploaded in (copy overlapped with pass 1)
+constexpr int TAGPU_UPLOAD_CHUNKS = 32;      // pieces the host read stream is uploaded in (copy overlapped with pass 1)
 constexpr int TAGPU_UPLOAD_CHUNKS_MAX = 32;
 
 struct Buf {
@@ -33,6 +34,8 @@ struct tagpu_ctx {
 	cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
 	cudaEvent_t ev_chunk[TAGPU_UPLOAD_CHUNKS_MAX];
 	const uint8_t *h_src = nullptr;    // host source of the read stream while its upload is pending (tagpu_*_host calls)
+	uint64_t (*src_ready)(void *) = nullptr;   // optional: bytes of the host stream's prefix that are final (the ingest may still
+	void *src_ready_arg = nullptr;             // be writing behind it); consulted before every chunk upload of the NEXT host build
 	bool src_packed = false;           // the read stream of the current build is in the packed tile layout (tagpu_extract.cuh)
 	int ci = 2, skip_counts = 0;
 	int contract = 1;                  // two-level graph stage (tagpu_contract.cuh)
@@ -48,8 +51,10 @@ struct tagpu_ctx {
 	// per-device launch state (a process may hold contexts on several devices)
 	bool attr_done[3] = { false, false, false };
 	int grid_s[3] = { 0, 0, 0 }, grid_m[3] = { 0, 0, 0 }, grid_l[3] = { 0, 0, 0 };
+	uint64_t budget_n = 0;
+	size_t budget = 0;                 // count_budget(): memory the count stage planned with for a stream of budget_n bytes
 	uint64_t n_solid_local = 0;        // entries of the solid list THIS context holds (= st.n_solid unless the set is sharded)
-	Buf chain_slot, grp_start, node_mask;
+	Buf chain_slot, grp_start, grp_desc, node_mask;
 	Buf seq, solid_key, solid_cnt, kt_keys, kt_mask, node_ord, node_slot, node_ebase, vL, vR, jump, vsucc,
 		vedge, e_src, e_dst, e_rc, e_len, e_count, e_off, e_seq;
 	uint32_t kt_slots = 0;
@@ -209,7 +214,7 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	dist_release(ctx);
-	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->blocks, &ctx->blk_defer, &ctx->d_first, &ctx->d_last, &ctx->d_n, &ctx->d_cnt, &ctx->d_off, &ctx->d_int, &ctx->wlast, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->hj_own, &ctx->hj_bits, &ctx->hj_list, &ctx->hj_jump2, &ctx->chain_slot, &ctx->grp_start, &ctx->node_mask, &ctx->seq, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
+	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->blocks, &ctx->blk_defer, &ctx->d_first, &ctx->d_last, &ctx->d_n, &ctx->d_cnt, &ctx->d_off, &ctx->d_int, &ctx->wlast, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->hj_own, &ctx->hj_bits, &ctx->hj_list, &ctx->hj_jump2, &ctx->chain_slot, &ctx->grp_start, &ctx->grp_desc, &ctx->node_mask, &ctx->seq, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
 			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
 	for (Buf *b : bufs)
@@ -224,6 +229,15 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	delete ctx;
 }
 
+// Progress callback for the NEXT host build / count: ready(arg) = bytes at the front of the host stream that are final.
+// The chunked upload of pass 1 waits for it chunk by chunk, so parsing the read files and uploading them overlap
+// (tagpu_host.c: tagpu_ingest_ready).  Only the ASCII host calls consult it; it is cleared after one use.
+extern "C" void tagpu_set_source_progress(tagpu_ctx *ctx, uint64_t (*ready)(void *), void *arg)
+{
+	ctx->src_ready = ready;
+	ctx->src_ready_arg = arg;
+}
+
 extern "C" void tagpu_set_stream(tagpu_ctx *ctx, void *s) { ctx->stream = s ? (cudaStream_t)s : ctx->own_stream; }
 extern "C" void tagpu_set_cutoff(tagpu_ctx *ctx, int ci) { ctx->ci = ci < 1 ? 1 : ci; }
 extern "C" void tagpu_set_skip_counts(tagpu_ctx *ctx, int skip) { ctx->skip_counts = skip; }
@@ -232,11 +246,12 @@ extern "C" void tagpu_set_profile(tagpu_ctx *ctx, int on) { ctx->profile = on; }
 extern "C" void tagpu_set_contract(tagpu_ctx *ctx, int on) { ctx->contract = on; }
 extern "C" const char *tagpu_profile_json(tagpu_ctx *ctx) { return ctx->prof_json.c_str(); }
 
-static int read_counters(tagpu_ctx *ctx)
+// allow: error bits the caller handles itself (capacity overflows it can recover from by re-running a pass)
+static int read_counters(tagpu_ctx *ctx, unsigned long long allow = 0)
 {
 	CU(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, CTR_TOTAL * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	if (ctx->h_ctr[CTR_ERROR])
+	if (ctx->h_ctr[CTR_ERROR] & ~allow)
 		return fail(ctx, "device-side invariant violated (error bits 0x%llx)", ctx->h_ctr[CTR_ERROR]);
 	return 0;
 }
@@ -259,8 +274,11 @@ static int read_counters(tagpu_ctx *ctx)
 	} while (0)
 
 // Sizing of the bucket space for a read stream of n_total bytes shared by `world` ranks.  Every rank computes the same
-// plan, so bucket -> owner and all region geometry agree without communication.
-static PartCfg plan_cfg(uint64_t n_total, int K, int world, uint32_t group_target)
+// plan, so bucket -> owner and all region geometry agree without communication.  Capacities are ESTIMATES: a record
+// that does not fit its bucket's region goes to the overflow list, and a single-GPU build whose overflow list or solid
+// buffer turns out too small re-runs the pass in question with buffers sized from what the first attempt counted
+// (partition_local / count_owned), so no input is refused for its shape.
+static PartCfg plan_cfg(uint64_t n_total, int K, int world, uint32_t group_target, size_t rec_bytes, size_t budget_bytes)
 {
 	// bucket count: buckets are packed into groups of ~GROUP_TARGET windows by k_group_buckets; fine buckets keep the
 	// packing tight although bucket sizes are skewed (CV ~0.9).  Guess: windows ~ stream bytes, a fifth of them distinct.
@@ -272,18 +290,41 @@ static PartCfg plan_cfg(uint64_t n_total, int K, int world, uint32_t group_targe
 	PartCfg cfg;
 	cfg.K = K;
 	cfg.log2_buckets = log2p;
-	// region capacity at each source: ~5x the mean bucket (a super-k-mer record holds ~14 windows on 151 bp reads; the
-	// estimate assumes 10); what does not fit spills to the overflow list, which is sorted by bucket after the pass.
-	// TAGPU_REGION_CAP overrides it (tests use a tiny value to drive everything through the overflow path).
-	cfg.cap_records = (uint32_t)(n_source / 10 / n_buckets * 5 + 64);
+	// records per source: a super-k-mer holds ~(w + 1) / 2 of the w = K - 14 windows that can share a minimizer, and a
+	// window takes >= 1 stream byte: n_source / max(2, (w + 1) / 2) overestimates by ~1.4x on 151 bp reads.
+	const int w = K - TAGPU_MINIMIZER_M + 1;
+	const uint64_t rec_est = n_source / (uint64_t)(w + 1 >= 4 ? (w + 1) / 2 : 2) + 1;
+	// region capacity at each source: 4x the estimated mean bucket (CV ~0.9: a fraction of a percent of the records
+	// spills), less if the regions would take more than the memory budget — the overflow list absorbs the difference
+	uint64_t cap = rec_est * 4 / n_buckets + 64;
+	if (budget_bytes && n_buckets * cap * rec_bytes > budget_bytes) {
+		const uint64_t fit = budget_bytes / rec_bytes / n_buckets, floor_cap = rec_est * 3 / 2 / n_buckets + 64;
+		cap = fit > floor_cap ? fit : floor_cap;
+	}
+	cfg.cap_records = (uint32_t)cap;
+	// TAGPU_REGION_CAP overrides it (tests use a tiny value to drive everything through the overflow path)
 	static const char *cap_env = getenv("TAGPU_REGION_CAP");
 	if (cap_env && atoi(cap_env) > 0) cfg.cap_records = (uint32_t)atoi(cap_env);
 	cfg.world = (uint32_t)world;
 	cfg.per_rank = (uint32_t)((n_buckets + world - 1) / world);
 	cfg.packed = 0;
-	cfg.overflow_cap = (uint32_t)(n_source / 16 + 4096);
-	if (cap_env && atoi(cap_env) > 0) cfg.overflow_cap = (uint32_t)(n_source / 4 + 4096);
+	cfg.overflow_cap = (uint32_t)(rec_est / 8 + 4096);
+	if (cap_env && atoi(cap_env) > 0) cfg.overflow_cap = (uint32_t)(rec_est + 4096);
+	static const char *ov_env = getenv("TAGPU_OVERFLOW_CAP");       // tests: force the re-run with a grown overflow list
+	if (ov_env && atoi(ov_env) > 0) cfg.overflow_cap = (uint32_t)atoi(ov_env);
 	return cfg;
+}
+
+// device memory the count stage may plan with: what is free plus what this context's regions already hold.  Asked once
+// per stream size (cudaMemGetInfo is a synchronous driver call of a few hundred microseconds).
+static size_t count_budget(tagpu_ctx *ctx, uint64_t n)
+{
+	if (ctx->budget_n == n && ctx->budget) return ctx->budget;
+	size_t free_b = 0, total_b = 0;
+	if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+	ctx->budget_n = n;
+	ctx->budget = (free_b + ctx->regions.cap) / 2;
+	return ctx->budget;
 }
 
 // Pass 1 over this rank's reads + the bucket sort of the records that overflowed their region.  Purely local.
@@ -301,8 +342,9 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 		CU(cudaFuncSetAttribute(k_count_buckets<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BC::SMEM));
 		attr_done[W] = true;
 	}
-	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)n_buckets * 8, ctx->stream)); }
 	const uint64_t n_tiles = (n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES;
+	for (int attempt = 0;; ++attempt) {
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)n_buckets * 8, ctx->stream)); }
 	if (n_tiles && !ctx->h_src) {
 		LAUNCH_SMEM(k_partition<W>, (unsigned)n_tiles, TAGPU_TILE_THREADS, smem1, d_seq, n, 0u, cfg, (SkRec<W> *)ctx->regions.p,
 			    (unsigned long long *)ctx->cursor.p, (SkRec<W> *)ctx->overflow.p, (uint32_t *)ctx->overflow_bucket.p, ctx->d_ctr);
@@ -331,6 +373,8 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 				tile1 = up_tile;
 			}
 			if (want > total) want = total;
+			if (ctx->src_ready && want > copied)                    // the parser is still filling the host stream: wait for this chunk
+				while (ctx->src_ready(ctx->src_ready_arg) < want) usleep(20);
 			if (want > copied) CU(cudaMemcpyAsync((uint8_t *)ctx->seq.p + copied, h_src + copied, want - copied, cudaMemcpyHostToDevice, ctx->copy_stream));
 			copied = want > copied ? want : copied;
 			CU(cudaEventRecord(ctx->ev_chunk[c % TAGPU_UPLOAD_CHUNKS_MAX], ctx->copy_stream));
@@ -341,8 +385,18 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 			tile0 = tile1;
 		}
 	}
-	ctx->h_src = nullptr;
-	if (read_counters(ctx)) return -1;
+	ctx->h_src = nullptr;                                       // (a second attempt reads the stream from the device)
+	ctx->src_ready = nullptr;
+	if (read_counters(ctx, TAGPU_ERR_BUCKET_OVERFLOW)) return -1;
+	if (!(ctx->h_ctr[CTR_ERROR] & TAGPU_ERR_BUCKET_OVERFLOW)) break;
+	// the overflow list was too small: CTR_SPARE0 counted every record that wanted a place in it.  Grow and repeat the pass.
+	const uint64_t need = ctx->h_ctr[CTR_SPARE0] + ctx->h_ctr[CTR_SPARE0] / 8 + 4096;
+	if (ctx->dist || attempt || need > 0xffffffffull)
+		return fail(ctx, "bucket overflow list too small (%llu records wanted, room for %u)", (unsigned long long)ctx->h_ctr[CTR_SPARE0], cfg.overflow_cap);
+	if (ensure(ctx, ctx->overflow, need * sizeof(SkRec<W>)) || ensure(ctx, ctx->overflow_bucket, need * 4)) return -1;
+	cfg.overflow_cap = (uint32_t)need;
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->d_ctr, 0, CTR_TOTAL * sizeof(unsigned long long), ctx->stream)); }
+	}
 	ctx->st.n_instances = ctx->h_ctr[CTR_INSTANCES];
 	const uint64_t n_over = ctx->h_ctr[CTR_SPARE0];
 	if (n_over) {
@@ -364,10 +418,31 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 	return 0;
 }
 
+template <int W>
+static int count_owned_once(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &peers, uint32_t first_bucket, uint64_t solid_cap);
+
 // Pass 2 over the buckets [first_bucket, first_bucket + n_owned) — all of them when world == 1 — reading every source's
 // records through `peers`.  solid_cap bounds the output arrays.
 template <int W>
 static int count_owned(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &peers, uint32_t first_bucket, uint64_t solid_cap)
+{
+	for (int attempt = 0;; ++attempt) {
+		const int rc = count_owned_once<W>(ctx, cfg, peers, first_bucket, solid_cap);
+		if (rc <= 0) return rc;
+		// rc == 1: more solid (k+1)-mers than the buffers hold.  The records are still in the regions: size the buffers
+		// from the count of this attempt and run pass 2 again (single GPU; the arena of a multi-GPU build is fixed).
+		if (ctx->dist || attempt)
+			return fail(ctx, "solid (k+1)-mer buffer too small (%llu > %llu)", (unsigned long long)ctx->st.n_solid, (unsigned long long)solid_cap);
+		solid_cap = ctx->st.n_solid + ctx->st.n_solid / 16 + 4096;
+		if (ensure(ctx, ctx->solid_key, solid_cap * sizeof(Key<W>)) || ensure(ctx, ctx->solid_cnt, solid_cap * 4)) return -1;
+		const int reset[] = { CTR_DISTINCT, CTR_SOLID, CTR_SUM_SOLID, CTR_BLOCKS };
+		for (int c : reset) CU(cudaMemsetAsync(ctx->d_ctr + c, 0, 8, ctx->stream));
+	}
+}
+
+// one attempt: 0 = done, -1 = error, 1 = solid_cap exceeded (nothing else wrong)
+template <int W>
+static int count_owned_once(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &peers, uint32_t first_bucket, uint64_t solid_cap)
 {
 	typedef BucketCfg<W> BC;
 	const uint32_t n_buckets = 1u << cfg.log2_buckets, world = cfg.world;
@@ -379,6 +454,7 @@ static int count_owned(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &
 	if (ensure(ctx, ctx->cur_all, ((size_t)cfg.per_rank * world + 1) * 8) || ensure(ctx, ctx->ext_all, ((size_t)cfg.per_rank * world + 1) * 4) ||
 	    ensure(ctx, ctx->pex, ((size_t)cfg.per_rank + 1) * 8) || ensure(ctx, ctx->bsum, ((size_t)n_scan_blocks + 1) * 8) ||
 	    ensure(ctx, ctx->grp_start, n_groups_cap * 4) || ensure(ctx, ctx->grp_end, n_groups_cap * 4) ||
+	    ensure(ctx, ctx->grp_desc, n_groups_cap * sizeof(GroupDesc)) ||
 	    ensure(ctx, ctx->blocks, (2 * n_groups_cap + 4096) * sizeof(SolidBlock)))
 		return -1;
 	const uint32_t blocks_cap = (uint32_t)(2 * n_groups_cap + 4096);
@@ -389,9 +465,11 @@ static int count_owned(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &
 		LAUNCH(k_scan_blocks, 1, 1024, (unsigned long long *)ctx->bsum.p, n_scan_blocks, (uint32_t)BC::GROUP_TARGET, ctx->d_ctr);
 		LAUNCH(k_mark_groups, n_scan_blocks, TAGPU_SCAN_BLOCK, (const unsigned long long *)ctx->pex.p, (const unsigned long long *)ctx->bsum.p, n_owned,
 		       (uint32_t)BC::GROUP_TARGET, (uint32_t *)ctx->grp_start.p, (uint32_t *)ctx->grp_end.p);
+		LAUNCH(k_group_desc, (unsigned)((n_groups_cap + 255) / 256), 256, (const uint32_t *)ctx->grp_start.p, (const uint32_t *)ctx->grp_end.p,
+		       (const unsigned long long *)ctx->cur_all.p, world, group_max, (const unsigned long long *)ctx->d_ctr, (GroupDesc *)ctx->grp_desc.p);
 		LAUNCH_SMEM(k_count_buckets<W>, BC::CTAS_PER_SM * ctx->n_sm, BC::THREADS, BC::SMEM, peers, world, first_bucket, cfg.cap_records,
 			    (const unsigned long long *)ctx->cur_all.p, (const uint32_t *)ctx->ext_all.p, (const uint32_t *)ctx->grp_start.p,
-			    (const uint32_t *)ctx->grp_end.p, group_max, cfg.K, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p,
+			    (const uint32_t *)ctx->grp_end.p, (const GroupDesc *)ctx->grp_desc.p, group_max, cfg.K, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p,
 			    (unsigned long long)solid_cap, (SolidBlock *)ctx->blocks.p, blocks_cap, ctx->d_ctr);
 	}
 	if (read_counters(ctx)) return -1;
@@ -403,17 +481,15 @@ static int count_owned(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &
 	ctx->log2_buckets = cfg.log2_buckets;
 #ifdef TAGPU_TIMING
 	{
-		const double tot = (double)(ctx->h_ctr[CTR_JUMP_FLAGS + 48] + ctx->h_ctr[CTR_JUMP_FLAGS + 49] + ctx->h_ctr[CTR_JUMP_FLAGS + 50] + ctx->h_ctr[CTR_JUMP_FLAGS + 51] +
-					  ctx->h_ctr[CTR_JUMP_FLAGS + 52] + ctx->h_ctr[CTR_JUMP_FLAGS + 53]);
-		fprintf(stderr, "[tagpu timing] harvest pass A %.1f%%  pass B %.1f%%  rest(copy+syncs) %.1f%%; class iterations %llu, failed %llu\n",
-			100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 52] / tot, 100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 53] / tot, 100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 51] / tot,
-			(unsigned long long)ctx->h_ctr[CTR_JUMP_FLAGS + 54], (unsigned long long)ctx->h_ctr[CTR_JUMP_FLAGS + 55]);
-		fprintf(stderr, "[tagpu timing] k_count_buckets warp-cycles: setup %.1f%%  insert %.1f%%  barrier-wait %.1f%%  harvest %.1f%%  (groups %llu)\n",
-			100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 48] / tot, 100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 49] / tot, 100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 50] / tot,
-			100.0 * ctx->h_ctr[CTR_JUMP_FLAGS + 51] / tot, (unsigned long long)ctx->h_ctr[CTR_GROUPS]);
+		const unsigned long long *t = ctx->h_ctr + CTR_JUMP_FLAGS;
+		const double tot = (double)(t[48] + t[49] + t[50] + t[51] + t[52] + t[53] + t[56]);
+		fprintf(stderr, "[tagpu timing] k_count_buckets warp-cycles: setup %.1f%%  stage+items %.1f%%  insert %.1f%%  wait at barrier %.1f%%  "
+				"harvest A %.1f%%  B %.1f%%  copy-out %.1f%%; class iterations %llu (failed %llu), groups %llu\n",
+			100.0 * t[48] / tot, 100.0 * t[56] / tot, 100.0 * t[49] / tot, 100.0 * t[50] / tot, 100.0 * t[52] / tot, 100.0 * t[53] / tot,
+			100.0 * t[51] / tot, (unsigned long long)t[54], (unsigned long long)t[55], (unsigned long long)ctx->h_ctr[CTR_GROUPS]);
 	}
 #endif
-	if (ctx->st.n_solid > solid_cap) return fail(ctx, "solid (k+1)-mer buffer too small (%llu > %llu)", (unsigned long long)ctx->st.n_solid, (unsigned long long)solid_cap);
+	if (ctx->st.n_solid > solid_cap) return 1;
 	ctx->cur_solid_key = ctx->solid_key.p;
 	ctx->cur_solid_cnt = ctx->solid_cnt.p;
 	ctx->have_count = true;
@@ -424,7 +500,7 @@ template <int W>
 static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n)
 {
 	typedef BucketCfg<W> BC;
-	const PartCfg cfg = plan_cfg(n, ctx->K, 1, BC::GROUP_TARGET);
+	const PartCfg cfg = plan_cfg(n, ctx->K, 1, BC::GROUP_TARGET, sizeof(SkRec<W>), count_budget(ctx, n));
 	const uint32_t n_buckets = 1u << cfg.log2_buckets;
 	ctx->count_stream_bytes = n;
 	if (ensure(ctx, ctx->regions, (size_t)n_buckets * cfg.cap_records * sizeof(SkRec<W>)) || ensure(ctx, ctx->cursor, (size_t)n_buckets * 8) ||
@@ -432,8 +508,14 @@ static int count_stage_partitioned(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_
 	    ensure(ctx, ctx->overflow_bucket, (size_t)cfg.overflow_cap * 4) || ensure(ctx, ctx->ext_off, (size_t)(n_buckets + 1) * 4) ||
 	    ensure(ctx, ctx->ext_count, (size_t)n_buckets * 4))
 		return -1;
-	// every solid key owns >= ci instances and there are fewer windows than stream bytes
-	const uint64_t solid_cap = n / (uint64_t)ctx->ci + 1;
+	// an estimate (a twelfth of the windows solid, where windows <= stream bytes): count_owned re-runs pass 2 with larger
+	// buffers if the input is shallower than that.  TAGPU_SOLID_CAP: tests force the re-run.
+	uint64_t solid_cap = n / 12 + (1u << 20);
+	if (solid_cap > n / (uint64_t)ctx->ci + 1) solid_cap = n / (uint64_t)ctx->ci + 1;      // (never more than can exist)
+	static const char *sc_env = getenv("TAGPU_SOLID_CAP");
+	if (sc_env && atoll(sc_env) > 0) solid_cap = (uint64_t)atoll(sc_env);
+	if (ctx->solid_key.cap / sizeof(Key<W>) > solid_cap && ctx->solid_cnt.cap / 4 > solid_cap && !sc_env)
+		solid_cap = ctx->solid_key.cap / sizeof(Key<W>) < ctx->solid_cnt.cap / 4 ? ctx->solid_key.cap / sizeof(Key<W>) : ctx->solid_cnt.cap / 4;
 	if (ensure(ctx, ctx->solid_key, solid_cap * sizeof(Key<W>)) || ensure(ctx, ctx->solid_cnt, solid_cap * 4)) return -1;
 	if (partition_local<W>(ctx, d_seq, n, cfg)) return -1;
 	CountPeers<W> peers;
@@ -925,8 +1007,8 @@ extern "C" int tagpu_dist_plan(tagpu_ctx *ctx, int rank, int world, uint64_t n_t
 	ctx->count_stream_bytes = n_total_bytes;
 	d->W = K <= 32 ? 1 : 2;
 	ctx->K = K; ctx->k = k; ctx->W = d->W;
-	d->cfg = plan_cfg(n_total_bytes, K, world, d->W == 1 ? BucketCfg<1>::GROUP_TARGET : BucketCfg<2>::GROUP_TARGET);
 	const size_t rec = d->W == 1 ? sizeof(SkRec<1>) : sizeof(SkRec<2>), key = d->W == 1 ? sizeof(Key<1>) : sizeof(Key<2>);
+	d->cfg = plan_cfg(n_total_bytes, K, world, d->W == 1 ? BucketCfg<1>::GROUP_TARGET : BucketCfg<2>::GROUP_TARGET, rec, 0);
 	const size_t n_buckets = (size_t)1 << d->cfg.log2_buckets;
 	// owned windows ~ N_i / world, bucket ownership is uneven: 1.5x head-room (checked, see count_owned)
 	d->solid_cap = n_total_bytes / world / (uint64_t)ctx->ci * 3 / 2 + (1u << 20);
@@ -1235,14 +1317,16 @@ extern "C" int tagpu_count_device(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t
 extern "C" int tagpu_build_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n, int k)
 {
 	ctx->src_packed = false;
-	if (upload(ctx, h_seq, n)) return -1;
-	return run(ctx, (const uint8_t *)ctx->seq.p, n, k + 1, true);
+	const int rc = upload(ctx, h_seq, n) ? -1 : run(ctx, (const uint8_t *)ctx->seq.p, n, k + 1, true);
+	ctx->src_ready = nullptr;          // (one use only, also when the build failed before the upload)
+	return rc;
 }
 extern "C" int tagpu_count_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n, int K)
 {
 	ctx->src_packed = false;
-	if (upload(ctx, h_seq, n)) return -1;
-	return run(ctx, (const uint8_t *)ctx->seq.p, n, K, false);
+	const int rc = upload(ctx, h_seq, n) ? -1 : run(ctx, (const uint8_t *)ctx->seq.p, n, K, false);
+	ctx->src_ready = nullptr;
+	return rc;
 }
 
 // ---- packed read stream (include/tagpu.h): n_positions = bytes of the ASCII stream it was packed from

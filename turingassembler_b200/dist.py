@@ -39,6 +39,34 @@ class DistTagpu:
         self._stats = torch.zeros(4, dtype=torch.int64, device=self.dev)
         self._all = torch.zeros(4 * world, dtype=torch.int64, device=self.dev)
         self._dirty = False           # the other ranks may still be pulling paths out of this rank's regions
+        self._shm = None
+        self._open_shm()
+
+    def _open_shm(self):
+        """Intra-node rendezvous (tagpu_shm_*, include/tagpu.h): barrier and counter exchange over a shared-memory segment,
+        a few microseconds each instead of a collective launch + device round trip.  Rank 0 picks the name; if the
+        segment cannot be opened everywhere (ranks on different hosts) the torch.distributed collectives stay in use."""
+        import ctypes as C
+        import uuid
+        if os.environ.get("TAGPU_NO_SHM"):
+            return
+        from .api import load_library
+        lib = self._lib = load_library()
+        lib.tagpu_shm_open.restype = C.c_void_p
+        lib.tagpu_shm_open.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        lib.tagpu_shm_barrier.argtypes = [C.c_void_p]
+        lib.tagpu_shm_allgather.restype = C.c_int
+        lib.tagpu_shm_allgather.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_uint64)]
+        lib.tagpu_shm_close.argtypes = [C.c_void_p]
+        name = [f"tagpu_{os.getpid()}_{uuid.uuid4().hex[:12]}" if self.rank == 0 else None]
+        self.dist.broadcast_object_list(name, src=self.dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        shm = lib.tagpu_shm_open(name[0].encode(), self.rank, self.world)
+        ok = self.torch.tensor([1 if shm else 0], dtype=self.torch.int32, device=self.dev)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()):
+            self._shm = shm
+        elif shm:
+            lib.tagpu_shm_close(shm)
 
     def plan(self, n_total_bytes: int, k: int):
         """Same n_total_bytes / k on every rank.  Allocates this rank's arena and maps everybody else's."""
@@ -53,6 +81,10 @@ class DistTagpu:
         # A 4-byte all-reduce followed by a host wait: a true barrier whatever stream the library launches on (the
         # tagpu_dist_* phases synchronise their own stream before returning, so "every rank called barrier()" means
         # "every rank's previous phase is complete and visible").
+        if self._shm:
+            self._sync()
+            self._lib.tagpu_shm_barrier(self._shm)
+            return
         self.dist.all_reduce(self._flag, group=self.group)
         self._sync()
 
@@ -73,16 +105,27 @@ class DistTagpu:
             t.dist_partition(ptr, n_local_bytes)
         self.barrier()
         local = t.dist_count()
-        all_stats = gather_stats(self.dist, self._stats, self._all, local, self.group)
+        all_stats = self._gather(local)
         if with_graph and t.contract:
             # level 1 on every rank's own solid set; the all-gather of the 4 values is the barrier before the pull
-            all_paths = gather_stats(self.dist, self._stats, self._all, t.dist_contract(), self.group)
+            all_paths = self._gather(t.dist_contract())
             if os.environ.get("TAGPU_DIST_DEBUG") and self.rank == 0:
                 print("tagpu dist: stats", all_stats, "paths", all_paths, flush=True)
             if all(all_paths[4 * r + 3] for r in range(self.world)):
                 self._dirty = True
                 return t.dist_graph_paths(all_stats, all_paths, gather_solid)
         return t.dist_graph(all_stats, with_graph)
+
+    def _gather(self, local):
+        """all-gather of 4 counters per rank -> flat list in rank order; doubles as a barrier"""
+        if self._shm:
+            import ctypes as C
+            mine = (C.c_uint64 * 4)(*[int(v) for v in local])
+            out = (C.c_uint64 * (4 * self.world))()
+            if self._lib.tagpu_shm_allgather(self._shm, mine, 4, out) != 0:
+                raise RuntimeError("tagpu_shm_allgather failed")
+            return list(out)
+        return gather_stats(self.dist, self._stats, self._all, local, self.group)
 
     def _sync(self):
         if self.on_gpu:
@@ -93,6 +136,10 @@ class DistTagpu:
         self.t.dist_disconnect()
         self.barrier()
         self.t.dist_close()
+        if self._shm:
+            self.barrier()
+            self._lib.tagpu_shm_close(self._shm)
+            self._shm = None
 
 
 def exchange_bytes(dist, blob: bytes, world: int, group=None):
