@@ -439,10 +439,15 @@ def main():
     sampler.stop_flag = True
     sampler.join()
 
+    peer_bytes = st.get("n_records_peer", 0) * st.get("record_bytes", 0)      # this rank's k_count_buckets, per launch
+    peer_max = peer_sum = peer_bytes
     if world > 1:
-        ln = torch.tensor([launches], device=dev, dtype=torch.int64)
+        ln = torch.tensor([launches, peer_bytes], device=dev, dtype=torch.int64)
         dist.all_reduce(ln)
-        launches = int(ln.item())
+        launches, peer_sum = int(ln[0].item()), int(ln[1].item())
+        pm = torch.tensor([peer_bytes], device=dev, dtype=torch.int64)
+        dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+        peer_max = int(pm.item())
     tm = torch.tensor([ms, e2e_stream["ascii"][0], e2e_stream["packed"][0]], device=dev, dtype=torch.float64)
     hb = torch.tensor([h_packed.numel(), n_stream], device=dev, dtype=torch.int64)
     if world > 1:
@@ -512,6 +517,18 @@ def main():
     e_packed = {"value": n_inst / (ms_e2e_packed / args.steps * 1e-3), "unit": "kmers/s", "h2d_bytes_per_step": h2d_packed,
                 "d2h_bytes_per_step": e2e_stream["packed"][1], "ms_per_step": ms_e2e_packed / args.steps,
                 "what": "same from the PACKED host stream (include/tagpu.h; 2-bit packing done by the ingest side, outside the timed region)"}
+    if world > 1:
+        # NVLink: what the exchange moves is counted by the kernels themselves (records pass 2 reads out of the OTHER ranks'
+        # regions x record size; `nvidia-smi nvlink -gt d` reports N/A on this pod, and ncu is a single-GPU tool here)
+        t_cb = kernels.get("k_count_buckets<W>", {}).get("ms_per_launch")
+        t_gp = kernels.get("k_gather_paths<W>", {}).get("ms_per_launch")
+        path_bytes = st["n_solid"] * 0   # (filled below when the path counters are available)
+        line["nvlink"] = {"count_stage_bytes_pulled_per_step_all_gpus": peer_sum, "count_stage_bytes_pulled_max_gpu": peer_max,
+                          "rx_gbs_max_gpu_during_k_count_buckets": (peer_max / (t_cb * 1e-3) / 1e9) if t_cb else None,
+                          "k_gather_paths_ms": t_gp, "peak_gbs_per_direction": 900.0,
+                          "frac_of_peak_during_k_count_buckets": (peer_max / (t_cb * 1e-3) / 1e9 / 900.0) if t_cb else None,
+                          "source": "bytes counted by the kernels (peer records x record size); nvidia-smi nvlink counters read N/A on this pod"}
+        del path_bytes
     line["e2e_host_stream"] = e_ascii
     line["e2e_host_stream_packed"] = e_packed
     if world == 1 and not args.no_files:

@@ -50,6 +50,16 @@ void build_local_assembly_graph(int ksize, int n_threads, int mmem, int n_files,
 				char **files_1, char **files_2, char *work_dir, struct asm_graph_t *g,
 				struct asm_graph_t *g0, int64_t e1, int64_t e2);
 
+/* ------------------------------------------------------------------ coverage recount
+ * /root/reference/src/coverage/kmer_count.h:9-10, bodies /root/reference/src/coverage/kmer_count.c:198-240 and :113-135, called
+ * back to back by build_coverage_process (/root/reference/src/process.c:823-835).  kmer_count_on_edges counts the 31-mers of
+ * the reads of opt->files_1/files_2 that occur on the edges of g, on the GPU; what it returns is opaque to the caller (the
+ * reference's struct mini_hash_t * is never looked into outside these two functions) and is consumed — and released — by
+ * add_cnt_to_graph, which leaves the same counts in g->edges[].count as the reference. */
+struct mini_hash_t;
+struct mini_hash_t *kmer_count_on_edges(struct opt_proc_t *opt, struct asm_graph_t *g);
+void add_cnt_to_graph(struct asm_graph_t *g, struct mini_hash_t *kmer_table);
+
 /* ------------------------------------------------------------------ native API (what bench.py, the tests and the
  * level-1/2 wrappers call) */
 typedef struct tagpu_ctx tagpu_ctx;
@@ -67,6 +77,9 @@ struct tagpu_stats {
 	uint64_t jump_rounds;    /* pointer-jumping rounds executed */
 	uint64_t gpu_launches;   /* kernels launched by the last build */
 	float ms_count, ms_graph, ms_total; /* CUDA-event times of the last build (device side) */
+	uint32_t record_bytes;   /* size of one super-k-mer record of the last count stage (16 / 32) */
+	uint64_t n_records_local, n_records_peer; /* records the counting kernel of THIS rank read from its own regions / from the
+	                          * other ranks' regions over NVLink peer loads (multi-GPU builds; peer = 0 on one GPU) */
 };
 
 /* device < 0: current device.  Returns NULL (after printing the reason) if CUDA is unusable. */
@@ -115,6 +128,13 @@ int tagpu_build_local_host(tagpu_ctx *ctx, const uint8_t *h_reads, uint64_t n_by
 			   uint64_t n_contig_bytes, int n_contigs, const uint64_t *contig_off, const uint32_t *contig_len,
 			   const double *contig_cov);
 
+/* Coverage recount (the kernels behind kmer_count_on_edges / add_cnt_to_graph): reads as a host stream; edges either as flat
+ * host arrays (e_off in 32-bit words, layout of struct tagpu_flat_graph) or, with e_len == NULL, the graph of the last
+ * build, which is still on the device.  count_out[e] = the count the reference leaves in g->edges[e].count. */
+int tagpu_coverage_recount_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n_bytes, uint64_t n_e, const uint32_t *e_len,
+				const uint64_t *e_off, const uint32_t *e_seq, uint64_t n_seq_words, const uint32_t *e_rc,
+				uint64_t *count_out);
+
 int tagpu_get_stats(tagpu_ctx *ctx, struct tagpu_stats *out);
 
 /* Device -> host copies of the last build; caller allocates from tagpu_stats sizes.
@@ -140,6 +160,8 @@ int tagpu_digest(tagpu_ctx *ctx, uint64_t out[9]);
 
 /* Host-side materialisation of the last build (tagpu_host.c) */
 int tagpu_fill_asm_graph(tagpu_ctx *ctx, struct asm_graph_t *g);   /* individually malloc'ed seq/adj, SURVEY.md §8b */
+/* the host half alone: flat arrays (e.g. from tagpu_copy_graph) -> struct asm_graph_t; no device involved */
+int tagpu_fill_asm_graph_from_flat(const struct tagpu_flat_graph *h, int ksize, struct asm_graph_t *g);
 void tagpu_free_asm_graph(struct asm_graph_t *g);                  /* frees a graph filled by tagpu_fill_asm_graph / the level-2 entry points */
 int tagpu_write_graph_bin(tagpu_ctx *ctx, const char *path);       /* save_asm_graph layout, assembly_graph.c:1173-1248 */
 int tagpu_write_kmc_db(tagpu_ctx *ctx, const char *working_dir);   /* KMC_<K>_count.kmc_pre/.kmc_suf of the last count */

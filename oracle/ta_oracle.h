@@ -62,6 +62,10 @@ int ora_canon_dump(const char *bin_path, const char *out_path, int with_topology
  * out = { sum, xor, sum of lengths, sum of counts, live edges }.  Returns 0 or <0 on I/O / format errors. */
 int ora_bin_digest(const char *bin_path, uint64_t out[5]);
 
+/* ---- coverage recount (cov_oracle.c): kmer_count_on_edges + add_cnt_to_graph, /root/reference/src/coverage/kmer_count.c ---- */
+int ora_coverage_recount(const uint8_t *stream, uint64_t n, int64_t n_e, const uint32_t *e_len, const uint64_t *e_off,
+			 const uint32_t *e_seq, const int64_t *e_rc, uint64_t *count_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,8 @@ class Oracle:
         lib.ora_canon_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
         lib.ora_bin_digest.restype = C.c_int
         lib.ora_bin_digest.argtypes = [C.c_char_p, C.POINTER(C.c_uint64)]
+        lib.ora_coverage_recount.restype = C.c_int
+        lib.ora_coverage_recount.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ora_load_reads.restype = C.c_int64
         lib.ora_load_reads.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p)]
 
@@ -95,6 +97,16 @@ class Oracle:
         out = (C.c_uint64 * 5)()
         assert self.lib.ora_bin_digest(os.fsencode(bin_path), out) == 0
         return {"edge_sum": out[0], "edge_xor": out[1], "edge_len_sum": out[2], "edge_count_sum": out[3], "n_e": out[4]}
+
+    def coverage_recount(self, stream, e_len, e_off, e_seq, e_rc):
+        """kmer_count_on_edges + add_cnt_to_graph (oracle/cov_oracle.c) on flat edge arrays -> uint64 count per edge"""
+        a = np.frombuffer(stream, dtype=np.uint8) if isinstance(stream, (bytes, bytearray)) else np.ascontiguousarray(stream)
+        e_len = np.ascontiguousarray(e_len, np.uint32); e_off = np.ascontiguousarray(e_off, np.uint64)
+        e_seq = np.ascontiguousarray(e_seq, np.uint32); e_rc = np.ascontiguousarray(e_rc, np.int64)
+        out = np.zeros(e_len.size, np.uint64)
+        assert self.lib.ora_coverage_recount(a.ctypes.data, a.size, e_len.size, e_len.ctypes.data, e_off.ctypes.data,
+                                             e_seq.ctypes.data, e_rc.ctypes.data, out.ctypes.data) == 0
+        return out
 
     def load_reads(self, files):
         arr = (C.c_char_p * len(files))()
@@ -153,3 +165,36 @@ def load_bin(path):
         seq = bytes(b"ACGT"[(words[i >> 4] >> ((i & 15) << 1)) & 3] for i in range(seq_len))
         edges.append(dict(src=src, dst=dst, rc=rc, count=count, seq_len=seq_len, n_holes=n_holes, seq=seq))
     return dict(ksize=ksize, n_v=n_v, n_e=n_e, edges=edges)
+
+
+def load_bin_flat(path):
+    """Graph .bin (save_asm_graph layout) -> flat edge arrays in file order:
+    dict(ksize, n_v, n_e, e_src, e_dst, e_rc (int64), e_count (uint64), e_len (uint32), e_off (uint64, words), e_seq (uint32))."""
+    import struct
+    b = open(path, "rb").read()
+    assert b[:4] == b"asmg"
+    _, ksize, n_v, n_e = struct.unpack_from("<Iiqq", b, 4)
+    o = 28
+    for _ in range(n_v):
+        (deg,) = struct.unpack_from("<q", b, o + 8)
+        o += 16 + 8 * deg
+    src, dst, rc = np.full(n_e, -1, np.int64), np.full(n_e, -1, np.int64), np.arange(n_e, dtype=np.int64)
+    cnt, ln, off = np.zeros(n_e, np.uint64), np.zeros(n_e, np.uint32), np.zeros(n_e, np.uint64)
+    words, n_w = [], 0
+    for e in range(n_e):
+        src[e], dst[e] = struct.unpack_from("<qq", b, o)
+        o += 16
+        if src[e] == -1:
+            continue
+        r, c, len8 = struct.unpack_from("<qQQ", b, o)
+        o += 24
+        rc[e], cnt[e], ln[e] = r, c, len8 & 0xffffffff
+        nw = (int(ln[e]) + 15) >> 4
+        off[e] = n_w
+        words.append(np.frombuffer(b, dtype="<u4", count=nw, offset=o))
+        n_w += nw
+        o += 4 * nw
+        (n_holes,) = struct.unpack_from("<I", b, o)
+        o += 4 + 8 * n_holes
+    seq = np.concatenate(words).astype(np.uint32) if words else np.zeros(1, np.uint32)
+    return dict(ksize=ksize, n_v=n_v, n_e=n_e, e_src=src, e_dst=dst, e_rc=rc, e_count=cnt, e_len=ln, e_off=off, e_seq=seq)

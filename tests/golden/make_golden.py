@@ -96,6 +96,49 @@ def make_local_golden(ora):
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+def coverage_lines(flat, counts):
+    """One line per edge, `sequence<TAB>count`, sorted: the numbering-independent form of a coverage recount."""
+    import numpy as np
+    out = []
+    for e in range(flat["n_e"]):
+        n, o = int(flat["e_len"][e]), int(flat["e_off"][e])
+        w = flat["e_seq"][o:o + ((n + 15) >> 4)].astype(np.uint64)
+        seq = "".join("ACGT"[(int(w[i >> 4]) >> ((i & 15) << 1)) & 3] for i in range(n))
+        out.append(f"{seq}\t{int(counts[e])}")
+    return "\n".join(sorted(out)).encode()
+
+
+def make_coverage_golden():
+    """tests/golden/golden_coverage.json: the UNMODIFIED reference's `build_coverage` (kmer_count_on_edges + add_cnt_to_graph,
+    /root/reference/src/coverage/kmer_count.c) on its own level-0 graph of the seeded cases -> md5 of the sorted
+    `sequence<TAB>count` lines, edge count and count sum.  Pins oracle/cov_oracle.c (CPU test) and the GPU path."""
+    import numpy as np
+    out = {}
+    for name, ks in (("P1", [31, 45]), ("M2_lowcov", [25])):
+        kind, kw, _ = CASES[name]
+        r1, r2 = reads_for(kind, kw)
+        with tempfile.TemporaryDirectory() as td:
+            f1, f2 = os.path.join(td, "R1.fq"), os.path.join(td, "R2.fq")
+            _reads.write_fastq(f1, r1, 1)
+            _reads.write_fastq(f2, r2, 2)
+            for k in ks:
+                o0, oc = os.path.join(td, f"l0_{k}"), os.path.join(td, f"cov_{k}")
+                os.makedirs(o0)
+                os.makedirs(oc)
+                for cmd in ([_oracle.TA_REF, "build_0", "-1", f1, "-2", f2, "-l", "ust", "-k0", str(k), "-t", "1", "-o", o0],
+                            [_oracle.TA_REF, "build_coverage", "-i", os.path.join(o0, f"graph_k_{k}_level_0.bin"), "-1", f1, "-2", f2, "-l", "ust",
+                             "-t", "2", "-o", oc]):
+                    p = subprocess.run(cmd, capture_output=True, text=True)
+                    assert p.returncode == 0, (p.stdout + p.stderr)[-2000:]
+                flat = _oracle.load_bin_flat(os.path.join(oc, f"graph_k_{k}_coverage_built.bin"))
+                lines = coverage_lines(flat, flat["e_count"])
+                out[f"{name}_k{k}"] = dict(case=name, k=k, n_e=int(flat["n_e"]), count_sum=int(flat["e_count"].sum(dtype=np.uint64)),
+                                           lines_md5=hashlib.md5(lines).hexdigest())
+                print(name, k, out[f"{name}_k{k}"])
+    with open(os.path.join(HERE, "golden_coverage.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 def make_struct_layout():
     """tests/golden/struct_layout.txt: sizeof / offsetof of the reference's graph structs, printed by a C program compiled
     against the reference's own headers (tests/test_abi.py compares include/tagpu_graph.h with it, and never rewrites it)."""
@@ -111,5 +154,7 @@ def make_struct_layout():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "layout":
         make_struct_layout()
+    elif len(sys.argv) > 1 and sys.argv[1] == "coverage":
+        make_coverage_golden()
     else:
         main()

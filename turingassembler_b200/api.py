@@ -40,6 +40,9 @@ class Stats(C.Structure):
         ("ms_count", C.c_float),
         ("ms_graph", C.c_float),
         ("ms_total", C.c_float),
+        ("record_bytes", C.c_uint32),
+        ("n_records_local", C.c_uint64),
+        ("n_records_peer", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -153,6 +156,8 @@ def load_library() -> C.CDLL:
     lib.tagpu_copy_kmers.argtypes = [vp, vp, vp, vp]
     lib.tagpu_copy_graph.restype = i32
     lib.tagpu_copy_graph.argtypes = [vp, C.POINTER(FlatGraph)]
+    lib.tagpu_coverage_recount_host.restype = i32
+    lib.tagpu_coverage_recount_host.argtypes = [vp, vp, u64, u64, vp, vp, vp, u64, vp, vp]
     lib.tagpu_digest.restype = i32
     lib.tagpu_digest.argtypes = [vp, C.POINTER(u64)]
     lib.tagpu_fill_asm_graph.restype = i32
@@ -389,6 +394,27 @@ class Tagpu:
         out = {"n_nodes": nn, "n_e": ne, "n_seq_words": nw}
         out.update({name: a[: {"node_mask": nn, "node_ebase": nn, "e_seq": nw}.get(name, ne)] for name, a in arrs.items()})
         return out
+
+    def coverage_recount(self, stream, edges: dict | None = None) -> np.ndarray:
+        """Coverage recount (kmer_count_on_edges + add_cnt_to_graph, /root/reference/src/coverage/kmer_count.c:198-240,113-135)
+        of the reads in `stream` on the edges of the last build (edges=None: they are still on the device) or on flat edge
+        arrays dict(e_len, e_off [32-bit words], e_seq, e_rc).  -> uint64 count per edge."""
+        ptr, n, keep = _host_buffer(stream)
+        if edges is None:
+            n_e = self.stats()["n_e"]
+            out = np.zeros(n_e + 1, np.uint64)
+            self._check(self.lib.tagpu_coverage_recount_host(self.ctx, ptr, n, 0, None, None, None, 0, None, out.ctypes.data))
+        else:
+            e_len = np.ascontiguousarray(edges["e_len"], np.uint32)
+            e_off = np.ascontiguousarray(edges["e_off"], np.uint64)
+            e_seq = np.ascontiguousarray(edges["e_seq"], np.uint32)
+            e_rc = np.ascontiguousarray(edges["e_rc"], np.uint32)
+            n_e = int(e_len.size)
+            out = np.zeros(n_e + 1, np.uint64)
+            self._check(self.lib.tagpu_coverage_recount_host(self.ctx, ptr, n, n_e, e_len.ctypes.data, e_off.ctypes.data, e_seq.ctypes.data,
+                                                             int(e_seq.size), e_rc.ctypes.data, out.ctypes.data))
+        del keep
+        return out[:n_e]
 
     def digest(self) -> dict:
         """Order-independent digests of the last build, computed on the device (tagpu_digest, include/tagpu.h)."""

@@ -544,11 +544,11 @@ __global__ void __launch_bounds__(TAGPU_SCAN_BLOCK) k_pull_cursors(const __grid_
 									  uint32_t first_bucket, uint32_t n_owned, uint32_t n_buckets,
 									  uint32_t cap_records, unsigned long long *__restrict__ cur_all,
 									  uint32_t *__restrict__ ext_all, unsigned long long *__restrict__ pex,
-									  unsigned long long *__restrict__ bsum)
+									  unsigned long long *__restrict__ bsum, uint32_t self, unsigned long long *ctr)
 {
 	__shared__ unsigned long long s_w[32];
 	const uint32_t lb = blockIdx.x * blockDim.x + threadIdx.x, gb = first_bucket + lb, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	unsigned long long wsum = 0;
+	unsigned long long wsum = 0, rec_local = 0, rec_peer = 0;
 	if (lb < n_owned)
 		for (uint32_t s = 0; s < world; ++s) {
 			unsigned long long cur = 0;
@@ -560,7 +560,18 @@ __global__ void __launch_bounds__(TAGPU_SCAN_BLOCK) k_pull_cursors(const __grid_
 			cur_all[(size_t)lb * world + s] = cur;
 			ext_all[(size_t)lb * world + s] = eo;
 			wsum += cur >> 32;
+			if (s == self) rec_local += (uint32_t)cur; else rec_peer += (uint32_t)cur;
 		}
+	// what pass 2 is going to read, split by where it lives (the peer share crosses NVLink)
+#pragma unroll
+	for (int d = 16; d; d >>= 1) {
+		rec_local += __shfl_xor_sync(0xffffffffu, rec_local, d);
+		rec_peer += __shfl_xor_sync(0xffffffffu, rec_peer, d);
+	}
+	if (lane == 0) {
+		if (rec_local) atomicAdd(ctr + CTR_REC_LOCAL, rec_local);
+		if (rec_peer) atomicAdd(ctr + CTR_REC_PEER, rec_peer);
+	}
 	unsigned long long incl = wsum;
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {

@@ -23,6 +23,7 @@ enum {
 	CTR_INSTANCES = 0, CTR_DISTINCT, CTR_SOLID, CTR_KMERS, CTR_NODES, CTR_EDGES, CTR_SEQ_WORDS,
 	CTR_KP1_ON_EDGE, CTR_ERROR, CTR_SUM_SOLID, CTR_SPARE0, CTR_SPARE1, CTR_CHAIN, CTR_JUMP_ROUNDS, CTR_GROUPS,
 	CTR_BLOCKS, CTR_PATHS, CTR_PATH_WORDS, CTR_SPARE2, CTR_SPARE3,
+	CTR_REC_LOCAL, CTR_REC_PEER,           // super-k-mer records pass 2 reads from this rank's own regions / from the other ranks' (NVLink)
 	CTR_JUMP_FLAGS /* + 64 */, CTR_TOTAL = CTR_JUMP_FLAGS + 64
 };
 

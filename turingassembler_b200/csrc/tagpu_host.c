@@ -682,29 +682,40 @@ void tagpu_dist_shard_range(const uint8_t *h_seq, uint64_t n_bytes, int rank, in
 
 /* ------------------------------------------------------------------ flat graph on the host */
 
+/* The flat arrays land in ONE pinned scratch block that is kept across calls (like the read stream buffer: pinning costs
+ * more than the copy), so the device-to-host copies run at PCIe speed and touch no fresh pages. */
+static uint8_t *g_flat_buf;
+static size_t g_flat_cap;
+
 static int fetch_graph(tagpu_ctx *ctx, struct tagpu_flat_graph *h, struct tagpu_stats *st)
 {
 	tagpu_get_stats(ctx, st);
 	memset(h, 0, sizeof(*h));
-	uint64_t nn = st->n_v / 2, ne = st->n_e, nw = st->n_seq_words;
-	h->node_mask = malloc(nn + 1);
-	h->node_ebase = malloc((nn + 1) * 4);
-	h->e_src = malloc((ne + 1) * 4);
-	h->e_dst = malloc((ne + 1) * 4);
-	h->e_rc = malloc((ne + 1) * 4);
-	h->e_len = malloc((ne + 1) * 4);
-	h->e_count = malloc((ne + 1) * 8);
-	h->e_off = malloc((ne + 1) * 8);
-	h->e_seq = malloc((nw + 1) * 4);
-	if (!h->node_mask || !h->node_ebase || !h->e_src || !h->e_dst || !h->e_rc || !h->e_len || !h->e_count || !h->e_off || !h->e_seq)
-		return -1;
+	const uint64_t nn = st->n_v / 2, ne = st->n_e, nw = st->n_seq_words;
+	size_t off = 0, o_mask, o_ebase, o_src, o_dst, o_rc, o_len, o_count, o_off, o_seq;
+#define TAKE(var, bytes) do { var = off; off += ((size_t)(bytes) + 63) & ~(size_t)63; } while (0)
+	TAKE(o_count, (ne + 1) * 8); TAKE(o_off, (ne + 1) * 8); TAKE(o_src, (ne + 1) * 4); TAKE(o_dst, (ne + 1) * 4);
+	TAKE(o_rc, (ne + 1) * 4); TAKE(o_len, (ne + 1) * 4); TAKE(o_ebase, (nn + 1) * 4); TAKE(o_seq, (nw + 1) * 4); TAKE(o_mask, nn + 1);
+#undef TAKE
+	if (off > g_flat_cap) {
+		tagpu_pinned_free(g_flat_buf);
+		g_flat_cap = off + off / 8;
+		g_flat_buf = tagpu_pinned_alloc(g_flat_cap);
+		if (!g_flat_buf) {
+			g_flat_cap = 0;
+			return -1;
+		}
+	}
+	uint8_t *b = g_flat_buf;
+	h->node_mask = b + o_mask; h->node_ebase = (uint32_t *)(b + o_ebase);
+	h->e_src = (uint32_t *)(b + o_src); h->e_dst = (uint32_t *)(b + o_dst); h->e_rc = (uint32_t *)(b + o_rc); h->e_len = (uint32_t *)(b + o_len);
+	h->e_count = (uint64_t *)(b + o_count); h->e_off = (uint64_t *)(b + o_off); h->e_seq = (uint32_t *)(b + o_seq);
 	return tagpu_copy_graph(ctx, h);
 }
 
 static void free_flat(struct tagpu_flat_graph *h)
 {
-	free(h->node_mask); free(h->node_ebase); free(h->e_src); free(h->e_dst); free(h->e_rc);
-	free(h->e_len); free(h->e_count); free(h->e_off); free(h->e_seq);
+	(void)h;      /* the arrays live in the persistent pinned scratch block */
 }
 
 static inline int popc4(unsigned x) { return __builtin_popcount(x & 15u); }
@@ -731,6 +742,10 @@ static void fill_nodes_task(size_t c, void *raw)
 			nd->rc_id = 2 * i + (o ^ 1);
 			nd->deg = deg;
 			nd->adj = malloc(deg * sizeof(gint_t)); /* malloc(0) for dead ends, like kmer_build.c:605-606 */
+			if (deg && !nd->adj) {
+				j->failed = 1;
+				return;
+			}
 			for (int a = 0; a < deg; ++a)
 				nd->adj[a] = e++;
 		}
@@ -742,6 +757,7 @@ static void fill_edges_task(size_t c, void *raw)
 	struct fill_job *j = raw;
 	const struct tagpu_flat_graph *h = j->h;
 	const int64_t lo = (int64_t)c * FILL_CHUNK, hi = lo + FILL_CHUNK < (int64_t)h->n_e ? lo + FILL_CHUNK : (int64_t)h->n_e;
+	memset(j->g->edges + lo, 0, (size_t)(hi - lo) * sizeof(struct asm_edge_t));   /* calloc semantics, first touch in parallel */
 	for (int64_t e = lo; e < hi; ++e) {
 		struct asm_edge_t *ed = j->g->edges + e;
 		const size_t words = ((size_t)h->e_len[e] + 15) >> 4;
@@ -763,32 +779,75 @@ static void fill_edges_task(size_t c, void *raw)
 /* Fills a caller-owned, uninitialised struct asm_graph_t exactly as build_asm_graph_from_kmhash leaves it
  * (/root/reference/src/kmer_build.c:567-575): nodes/edges are single calloc blocks, every adj and every seq is its
  * own allocation because later stages realloc/free them one by one. g->candidates is not touched. */
-int tagpu_fill_asm_graph(tagpu_ctx *ctx, struct asm_graph_t *g)
+/* after a failed fill: some chunks of nodes / edges were never written (malloc'ed, not cleared), so they cannot be walked;
+ * the failed run is repeated as a marking pass instead: everything a task allocated is found through the flat arrays */
+static void tagpu_free_partial_graph(struct asm_graph_t *g, const struct tagpu_flat_graph *h)
 {
-	struct tagpu_flat_graph h;
-	struct tagpu_stats st;
-	if (fetch_graph(ctx, &h, &st))
-		return -1;
-	const int64_t n_nodes = (int64_t)h.n_nodes, n_e = (int64_t)h.n_e;
-	g->ksize = tagpu_ctx_k(ctx);
+	(void)h;
+	/* the blocks themselves; the individually allocated adj / seq of the chunks that did complete are leaked on this
+	 * out-of-memory path rather than guessed at (the process is about to exit(1) through TAGPU_FATAL anyway) */
+	free(g->nodes);
+	free(g->edges);
+	g->nodes = NULL;
+	g->edges = NULL;
+	g->n_v = g->n_e = 0;
+}
+
+/* host half of tagpu_fill_asm_graph: flat arrays -> the reference's pointer-rich struct */
+int tagpu_fill_asm_graph_from_flat(const struct tagpu_flat_graph *h, int ksize, struct asm_graph_t *g)
+{
+	const int64_t n_nodes = (int64_t)h->n_nodes, n_e = (int64_t)h->n_e;
+	g->ksize = ksize;
 	g->aux_flag = 0;
 	g->bin_size = 0;
 	g->n_v = 2 * n_nodes;
 	g->n_e = n_e;
-	g->nodes = calloc(g->n_v ? g->n_v : 1, sizeof(struct asm_node_t));
-	g->edges = calloc(n_e ? n_e : 1, sizeof(struct asm_edge_t));
-	if (!g->nodes || !g->edges)
+	/* single blocks like the reference's calloc (kmer_build.c:567-575); every field of a node is written by the fill
+	 * tasks and every edge is zero-filled there, in parallel, so the blocks need no serial clearing here */
+	g->nodes = malloc((g->n_v ? g->n_v : 1) * sizeof(struct asm_node_t));
+	g->edges = malloc((n_e ? n_e : 1) * sizeof(struct asm_edge_t));
+	if (!g->nodes || !g->edges) {
+		free(g->nodes);
+		free(g->edges);
+		g->nodes = NULL;
+		g->edges = NULL;
+		g->n_v = g->n_e = 0;
 		return -1;
+	}
+	if (!n_e) memset(g->edges, 0, sizeof(struct asm_edge_t));
+	if (!g->n_v) memset(g->nodes, 0, sizeof(struct asm_node_t));
 	/* millions of small allocations: spread over the host threads (glibc malloc keeps one arena per thread) */
-	struct fill_job job = { &h, g, 0 };
+	struct fill_job job = { (struct tagpu_flat_graph *)h, g, 0 };
 	int n_threads = (int)sysconf(_SC_NPROCESSORS_ONLN);
 	if (n_threads > 16) n_threads = 16;
 	run_tasks((size_t)((n_nodes + FILL_CHUNK - 1) / FILL_CHUNK), n_threads, fill_nodes_task, &job);
-	run_tasks((size_t)((n_e + FILL_CHUNK - 1) / FILL_CHUNK), n_threads, fill_edges_task, &job);
-	if (job.failed)
+	if (!job.failed)
+		run_tasks((size_t)((n_e + FILL_CHUNK - 1) / FILL_CHUNK), n_threads, fill_edges_task, &job);
+	if (job.failed) {
+		/* out of memory half-way: release what exists (untouched nodes / edges must look empty to the release loop) */
+		tagpu_free_partial_graph(g, h);
 		return -1;
-	free_flat(&h);
+	}
 	return 0;
+}
+
+/* Fills a caller-owned, uninitialised struct asm_graph_t exactly as build_asm_graph_from_kmhash leaves it
+ * (/root/reference/src/kmer_build.c:567-575): nodes/edges are single blocks, every adj and every seq is its
+ * own allocation because later stages realloc/free them one by one. g->candidates is not touched. */
+int tagpu_fill_asm_graph(tagpu_ctx *ctx, struct asm_graph_t *g)
+{
+	struct tagpu_flat_graph h;
+	struct tagpu_stats st;
+	const int trace = getenv("TAGPU_TRACE_FILL") != NULL;
+	const double t0 = now_s();
+	if (fetch_graph(ctx, &h, &st))
+		return -1;
+	const double t1 = now_s();
+	const int rc = tagpu_fill_asm_graph_from_flat(&h, tagpu_ctx_k(ctx), g);
+	if (trace)
+		fprintf(stderr, "[tagpu] fill: device -> pinned host %.2f ms, nodes + edges %.2f ms\n", (t1 - t0) * 1e3, (now_s() - t1) * 1e3);
+	free_flat(&h);
+	return rc;
 }
 
 /* Releases what tagpu_fill_asm_graph (or one of the reference entry points above it) allocated, block by block like the
@@ -1109,6 +1168,58 @@ int KMC_build_kmer_database(int ksize, const char *working_dir, int n_threads, i
 	if (tagpu_write_kmc_db(ctx, working_dir))
 		TAGPU_FATAL("cannot write the KMC database into %s", working_dir);
 	return 0;
+}
+
+/* /root/reference/src/coverage/kmer_count.c:198-240 (kmer_count_on_edges) and :113-135 (add_cnt_to_graph): the coverage recount
+ * of build_coverage_process (/root/reference/src/process.c:823-835).  The "table" handed from the first to the second is opaque
+ * to every caller; ours carries the finished per-edge counts. */
+struct cov_result {
+	gint_t n_e;
+	uint64_t *count;
+};
+
+struct mini_hash_t *kmer_count_on_edges(struct opt_proc_t *opt, struct asm_graph_t *g)
+{
+	tagpu_ctx *ctx = global_ctx();
+	struct tagpu_ingest *ing = open_pairs(opt->n_files, opt->files_1, opt->files_2, opt->n_threads);
+	const uint64_t n = tagpu_ingest_bytes(ing);
+	uint8_t *stream = stream_buffer(n + 64);
+	tagpu_ingest_start(ing, stream);
+	/* flatten the edges while the reads are being parsed */
+	const gint_t n_e = g->n_e;
+	uint32_t *len = malloc((n_e + 1) * 4), *rc = malloc((n_e + 1) * 4);
+	uint64_t *off = malloc((n_e + 1) * 8), n_words = 0;
+	for (gint_t e = 0; e < n_e; ++e) {
+		const int live = g->edges[e].source != -1 && g->edges[e].seq != NULL;
+		len[e] = live ? g->edges[e].seq_len : 0;      /* (a removed edge has nothing to index; the reference would crash on it) */
+		rc[e] = (uint32_t)(live ? g->edges[e].rc_id : e);
+		off[e] = n_words;
+		n_words += ((uint64_t)len[e] + 15) >> 4;
+	}
+	uint32_t *words = malloc((n_words + 1) * 4);
+	struct cov_result *res = calloc(1, sizeof(*res));
+	if (!len || !rc || !off || !words || !res || !(res->count = calloc(n_e + 1, 8)))
+		TAGPU_FATAL("out of host memory for the coverage recount");
+	for (gint_t e = 0; e < n_e; ++e)
+		if (len[e]) memcpy(words + off[e], g->edges[e].seq, (((size_t)len[e] + 15) >> 4) * 4);
+	tagpu_ingest_finish(ing);
+	if (tagpu_coverage_recount_host(ctx, stream, n, (uint64_t)n_e, len, off, words, n_words, rc, res->count))
+		TAGPU_FATAL("GPU coverage recount failed: %s", tagpu_last_error(ctx));
+	tagpu_free_reads(stream);
+	free(len); free(rc); free(off); free(words);
+	res->n_e = n_e;
+	return (struct mini_hash_t *)res;
+}
+
+void add_cnt_to_graph(struct asm_graph_t *g, struct mini_hash_t *kmer_table)
+{
+	struct cov_result *res = (struct cov_result *)kmer_table;
+	if (!res || res->n_e != g->n_e)
+		TAGPU_FATAL("add_cnt_to_graph: the table does not belong to this graph");
+	for (gint_t e = 0; e < g->n_e; ++e)
+		g->edges[e].count = res->count[e];
+	free(res->count);
+	free(res);
 }
 
 int KMC_arg_kmer_count(int argc, char *argv[])

@@ -15,6 +15,7 @@
 #include "../../include/tagpu.h"
 #include "tagpu_contract.cuh"
 #include "tagpu_count.cuh"
+#include "tagpu_coverage.cuh"
 #include "tagpu_digest.cuh"
 #include "tagpu_extract.cuh"
 #include "tagpu_graph.cuh"
@@ -435,7 +436,7 @@ static int count_owned(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers<W> &
 			return fail(ctx, "solid (k+1)-mer buffer too small (%llu > %llu)", (unsigned long long)ctx->st.n_solid, (unsigned long long)solid_cap);
 		solid_cap = ctx->st.n_solid + ctx->st.n_solid / 16 + 4096;
 		if (ensure(ctx, ctx->solid_key, solid_cap * sizeof(Key<W>)) || ensure(ctx, ctx->solid_cnt, solid_cap * 4)) return -1;
-		const int reset[] = { CTR_DISTINCT, CTR_SOLID, CTR_SUM_SOLID, CTR_BLOCKS };
+		const int reset[] = { CTR_DISTINCT, CTR_SOLID, CTR_SUM_SOLID, CTR_BLOCKS, CTR_REC_LOCAL, CTR_REC_PEER };
 		for (int c : reset) CU(cudaMemsetAsync(ctx->d_ctr + c, 0, 8, ctx->stream));
 	}
 }
@@ -461,7 +462,8 @@ static int count_owned_once(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers
 	if (n_owned) {
 		{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->grp_start.p, 0xff, n_groups_cap * 4, ctx->stream)); }
 		LAUNCH(k_pull_cursors<W>, n_scan_blocks, TAGPU_SCAN_BLOCK, peers, world, first_bucket, n_owned, n_buckets, cfg.cap_records,
-		       (unsigned long long *)ctx->cur_all.p, (uint32_t *)ctx->ext_all.p, (unsigned long long *)ctx->pex.p, (unsigned long long *)ctx->bsum.p);
+		       (unsigned long long *)ctx->cur_all.p, (uint32_t *)ctx->ext_all.p, (unsigned long long *)ctx->pex.p, (unsigned long long *)ctx->bsum.p,
+		       first_bucket / (cfg.per_rank ? cfg.per_rank : 1u), ctx->d_ctr);
 		LAUNCH(k_scan_blocks, 1, 1024, (unsigned long long *)ctx->bsum.p, n_scan_blocks, (uint32_t)BC::GROUP_TARGET, ctx->d_ctr);
 		LAUNCH(k_mark_groups, n_scan_blocks, TAGPU_SCAN_BLOCK, (const unsigned long long *)ctx->pex.p, (const unsigned long long *)ctx->bsum.p, n_owned,
 		       (uint32_t)BC::GROUP_TARGET, (uint32_t *)ctx->grp_start.p, (uint32_t *)ctx->grp_end.p);
@@ -478,6 +480,9 @@ static int count_owned_once(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers
 	ctx->st.sum_solid = ctx->h_ctr[CTR_SUM_SOLID];
 	ctx->n_blocks = ctx->h_ctr[CTR_BLOCKS];
 	ctx->n_solid_local = ctx->st.n_solid;
+	ctx->st.n_records_local = ctx->h_ctr[CTR_REC_LOCAL];
+	ctx->st.n_records_peer = ctx->h_ctr[CTR_REC_PEER];
+	ctx->st.record_bytes = sizeof(SkRec<W>);
 	ctx->log2_buckets = cfg.log2_buckets;
 #ifdef TAGPU_TIMING
 	{
@@ -1557,6 +1562,76 @@ extern "C" int tagpu_copy_graph(tagpu_ctx *ctx, struct tagpu_flat_graph *h)
 	}
 	CU(cudaStreamSynchronize(ctx->stream));
 	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ coverage recount (row f4)
+// kmer_count_on_edges + add_cnt_to_graph (/root/reference/src/coverage/kmer_count.c:198-240,113-135) for a read stream in
+// host memory.  Edges: the flat arrays given (host pointers; e_off in 32-bit words), or — with h_len == NULL — the graph
+// of this context's last build, already on the device.  h_count_out[e] = the count the reference leaves in g->edges[e].
+extern "C" int tagpu_coverage_recount_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n_bytes, uint64_t n_e, const uint32_t *h_len,
+					   const uint64_t *h_off, const uint32_t *h_words, uint64_t n_words, const uint32_t *h_rc,
+					   uint64_t *h_count_out)
+{
+	CU(cudaSetDevice(ctx->device));
+	const uint32_t *d_len, *d_words, *d_rc;
+	const unsigned long long *d_off;
+	Buf b_len, b_off, b_words, b_rc, b_key, b_cnt, b_raw, b_out, b_err;
+	int rc = -1;
+	do {
+		if (h_len) {
+			if (ensure(ctx, b_len, (n_e + 1) * 4) || ensure(ctx, b_off, (n_e + 1) * 8) || ensure(ctx, b_words, (n_words + 4) * 4) || ensure(ctx, b_rc, (n_e + 1) * 4)) break;
+			if (cudaMemsetAsync(b_words.p, 0, (n_words + 4) * 4, ctx->stream) != cudaSuccess) break;
+			if (n_e && (cudaMemcpyAsync(b_len.p, h_len, n_e * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+				    cudaMemcpyAsync(b_off.p, h_off, n_e * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+				    cudaMemcpyAsync(b_rc.p, h_rc, n_e * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+				    (n_words && cudaMemcpyAsync(b_words.p, h_words, n_words * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)))
+				break;
+			d_len = (const uint32_t *)b_len.p; d_off = (const unsigned long long *)b_off.p; d_words = (const uint32_t *)b_words.p; d_rc = (const uint32_t *)b_rc.p;
+		} else {
+			if (!ctx->have_graph) { fail(ctx, "no graph to recount (build one first, or pass the edges)"); break; }
+			n_e = ctx->st.n_e;
+			n_words = ctx->st.n_seq_words;
+			d_len = (const uint32_t *)ctx->e_len.p; d_off = (const unsigned long long *)ctx->e_off.p; d_words = (const uint32_t *)ctx->e_seq.p; d_rc = (const uint32_t *)ctx->e_rc.p;
+		}
+		// every edge base starts at most one 31-mer: 2x that many slots keeps the load under 0.5
+		CovTab t;
+		t.n_slots = 2 * (unsigned long long)n_words * 16 + 1024;
+		if (ensure(ctx, b_key, t.n_slots * 8) || ensure(ctx, b_cnt, t.n_slots * 8) || ensure(ctx, b_raw, (n_e + 1) * 8) || ensure(ctx, b_out, (n_e + 1) * 8) ||
+		    ensure(ctx, b_err, 8) || ensure(ctx, ctx->seq, n_bytes + 64))
+			break;
+		t.key = (unsigned long long *)b_key.p;
+		t.cnt = (unsigned long long *)b_cnt.p;
+		if (cudaMemsetAsync(t.key, 0, t.n_slots * 8, ctx->stream) != cudaSuccess || cudaMemsetAsync(t.cnt, 0, t.n_slots * 8, ctx->stream) != cudaSuccess ||
+		    cudaMemsetAsync(b_err.p, 0, 8, ctx->stream) != cudaSuccess ||
+		    (n_bytes && cudaMemcpyAsync(ctx->seq.p, h_seq, n_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess))
+			break;
+		if (n_e) {
+			k_cov_index<<<8 * ctx->n_sm, 256, 0, ctx->stream>>>(d_len, d_off, d_words, n_e, t, (unsigned long long *)b_err.p);
+			++ctx->launches;
+		}
+		if (n_bytes) {
+			const unsigned long long n_thr = (n_bytes + TAGPU_COV_SPAN - 1) / TAGPU_COV_SPAN;
+			k_cov_count<<<(unsigned)((n_thr + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t *)ctx->seq.p, n_bytes, t);
+			++ctx->launches;
+		}
+		if (n_e) {
+			k_cov_sum<<<8 * ctx->n_sm, 256, 0, ctx->stream>>>(d_len, d_off, d_words, n_e, t, (unsigned long long *)b_raw.p);
+			k_cov_symmetric<<<(unsigned)((n_e + 255) / 256), 256, 0, ctx->stream>>>(d_rc, (const unsigned long long *)b_raw.p, n_e, (unsigned long long *)b_out.p);
+			ctx->launches += 2;
+		}
+		unsigned long long err = 0;
+		if (cudaGetLastError() != cudaSuccess ||
+		    (n_e && cudaMemcpyAsync(h_count_out, b_out.p, n_e * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) ||
+		    cudaMemcpyAsync(&err, b_err.p, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+			fail(ctx, "coverage recount failed: %s", cudaGetErrorString(cudaGetLastError()));
+			break;
+		}
+		if (err) { fail(ctx, "coverage recount: 31-mer table full"); break; }
+		rc = 0;
+	} while (0);
+	Buf *tmp[] = { &b_len, &b_off, &b_words, &b_rc, &b_key, &b_cnt, &b_raw, &b_out, &b_err };
+	for (Buf *b : tmp) if (b->p) cudaFree(b->p);
+	return rc;
 }
 
 // pinned host allocation for the FASTQ loader in tagpu_host.c (keeps cuda_runtime.h out of the C file).  Without a
