@@ -202,6 +202,12 @@ int tagpu_dist_contract(tagpu_ctx *ctx, uint64_t paths_out[4]);
  * tagpu_write_kmc_db fail); 3 = graph, and every rank also pulls the whole solid set */
 int tagpu_dist_graph_paths(tagpu_ctx *ctx, const uint64_t *all_stats /* world x 4 */, const uint64_t *all_paths /* world x 4 */,
 			   int with_graph);
+/* The whole step above in ONE call, with the barriers and counter exchanges taken from a tagpu_shm segment (below): no
+ * host-language round trip between the kernels of a step.  src_kind: 0 = device stream, 1 = pinned host ASCII stream,
+ * 2 = pinned host packed stream (n = positions).  flags: 1 = build the graph, 2 = also gather the solid sets on every rank,
+ * 4 = the previous step used the two-level stage (*used_paths was 1): barrier first, peers may still be pulling paths. */
+struct tagpu_shm;
+int tagpu_dist_step(tagpu_ctx *ctx, struct tagpu_shm *shm, const uint8_t *src, uint64_t n, int src_kind, int flags, int *used_paths);
 /* Teardown / re-plan: every rank calls tagpu_dist_disconnect (unmaps the peers' arenas) -> BARRIER -> tagpu_dist_close or a
  * new tagpu_dist_plan (frees its own arena, which nobody maps any more). */
 void tagpu_dist_disconnect(tagpu_ctx *ctx);
@@ -212,7 +218,6 @@ void tagpu_dist_shard_range(const uint8_t *h_seq, uint64_t n_bytes, int rank, in
 /* Intra-node rendezvous for the phases above (tagpu_host.c): a barrier and an all-gather of <= 8 values per rank over a
  * POSIX shared-memory segment — microseconds instead of a collective launch plus a device round trip.  Rank 0 creates the
  * segment; `name` is any string all ranks agree on (the host program distributes it once). */
-struct tagpu_shm;
 struct tagpu_shm *tagpu_shm_open(const char *name, int rank, int world);
 void tagpu_shm_barrier(struct tagpu_shm *s);
 int tagpu_shm_allgather(struct tagpu_shm *s, const uint64_t *mine, int n, uint64_t *all /* world x n */);
@@ -230,6 +235,12 @@ uint64_t tagpu_ingest_bytes(const struct tagpu_ingest *ing);
 void tagpu_ingest_start(struct tagpu_ingest *ing, uint8_t *dst);
 uint64_t tagpu_ingest_ready(void *ing);
 void tagpu_ingest_finish(struct tagpu_ingest *ing);
+/* Fused variant (what the entry points use): open scans nothing, tagpu_ingest_bytes is an UPPER BOUND of the stream length
+ * (half of a plain FASTQ file), the workers index + size + copy each chunk in one pass and pad the buffer behind the true
+ * end with '\n' — positions that hold no window — so the consumer processes `bound` bytes.  finish_fused returns the true
+ * length, or -1 if a file holds more sequence than the bound (then use tagpu_ingest_open: exact sizes, two passes). */
+struct tagpu_ingest *tagpu_ingest_open_fused(int n_files, char **files, int n_threads);
+int64_t tagpu_ingest_finish_fused(struct tagpu_ingest *ing);
 void tagpu_set_source_progress(tagpu_ctx *ctx, uint64_t (*ready)(void *), void *arg);
 
 #ifdef __cplusplus

@@ -193,6 +193,8 @@ def load_library() -> C.CDLL:
     lib.tagpu_dist_contract.argtypes = [vp, C.POINTER(u64)]
     lib.tagpu_dist_graph_paths.restype = i32
     lib.tagpu_dist_graph_paths.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), i32]
+    lib.tagpu_dist_step.restype = i32
+    lib.tagpu_dist_step.argtypes = [vp, vp, vp, u64, i32, i32, C.POINTER(i32)]
     lib.tagpu_dist_close.argtypes = [vp]
     lib.tagpu_dist_disconnect.argtypes = [vp]
     lib.tagpu_dist_shard_range.restype = None
@@ -352,6 +354,12 @@ class Tagpu:
         b = (C.c_uint64 * len(all_paths))(*all_paths)
         self._check(self.lib.tagpu_dist_graph_paths(self.ctx, a, b, 3 if gather_solid else 1))
         return self.stats()
+
+    def dist_step(self, shm, ptr: int, n: int, src_kind: int, flags: int):
+        """One whole multi-GPU step in a single call (tagpu_dist_step) -> (global stats, used_paths)."""
+        used = C.c_int(0)
+        self._check(self.lib.tagpu_dist_step(self.ctx, C.c_void_p(shm), C.c_void_p(ptr), n, src_kind, flags, C.byref(used)))
+        return self.stats(), used.value
 
     def dist_disconnect(self):
         self.lib.tagpu_dist_disconnect(self.ctx)

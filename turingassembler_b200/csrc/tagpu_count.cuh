@@ -432,9 +432,12 @@ template <int W> struct BucketCfg {
 	// a group is closed once it holds this many windows: ~0.3-0.4 load if a sixth of the windows are distinct keys.
 	// Measured on C1/C2 with 1.5x / 2x / 2.5x / 3x SLOTS: 2x is best for 128-bit keys (3x overflows into re-runs), 2.5x-3x
 	// for 64-bit keys; duplicate-record collapse made inserts cheap relative to the per-group harvest.
-	static constexpr uint32_t GROUP_TARGET = W == 1 ? SLOTS * 5 / 2 : SLOTS * 2;
+#ifndef TAGPU_GT2
+#define TAGPU_GT2 8           /* group target of the 128-bit path in quarters of the slot count (developer sweeps) */
+#endif
+	static constexpr uint32_t GROUP_TARGET = W == 1 ? SLOTS * 5 / 2 : SLOTS * TAGPU_GT2 / 4;
 	// staging area: record words, one 32-bit meta word per record, 16-bit work items; the harvest reuses it for its output
-	static constexpr size_t STAGE_BYTES = (size_t)ROUND * (NW * 8 + 4) + (size_t)ITEMS * 2;
+	static constexpr size_t STAGE_BYTES = (size_t)ROUND * (NW * 8 + 4) + (size_t)ITEMS * 2 + 16;   // (+ the overflow flag)
 	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + STAGE_BYTES;
 };
 
@@ -751,12 +754,16 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 	StagedRec<W> *s_rec = reinterpret_cast<StagedRec<W> *>(stage);
 	uint32_t *s_meta = reinterpret_cast<uint32_t *>(s_rec + C::ROUND);
 	uint16_t *s_item = reinterpret_cast<uint16_t *>(s_meta + C::ROUND);
+	// "table too full" flag of the current class: in the dynamic area, whose address is one add away from a register (a
+	// static __shared__ variable costs a special-register read per access, and the insert loop polls this one)
+	volatile uint32_t *s_overflow_p = reinterpret_cast<volatile uint32_t *>(s_item + C::ITEMS);
+#define s_overflow (*s_overflow_p)
 	// during the harvest the staging area holds the compacted solid (key, count) pairs of the group
-	constexpr uint32_t OUT_CAP = (uint32_t)(C::STAGE_BYTES / (sizeof(Key<W>) + 4));
+	constexpr uint32_t OUT_CAP = (uint32_t)((C::STAGE_BYTES - 16) / (sizeof(Key<W>) + 4));    // (the overflow flag at the end is not part of it)
 	Key<W> *o_key = reinterpret_cast<Key<W> *>(stage);
 	uint32_t *o_cnt = reinterpret_cast<uint32_t *>(o_key + OUT_CAP);
 	constexpr uint32_t TOP_NONE = 0xffffffffu;
-	__shared__ uint32_t s_b0, s_nb, s_bs, s_be, s_top, s_claims, s_overflow, s_sp, s_nsolid, s_nout, s_pf, s_pf_n, s_warp_solid[C::THREADS / 32], s_stack[64];
+	__shared__ uint32_t s_b0, s_nb, s_bs, s_be, s_top, s_claims, s_sp, s_nsolid, s_nout, s_pf, s_pf_n, s_warp_solid[C::THREADS / 32], s_stack[64];
 	__shared__ uint32_t s_rpre[C::SUB_MAX + 1];                  // per (bucket, source) pair of the group: records before it
 	__shared__ unsigned long long s_out_base;
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -868,7 +875,7 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 			const uint32_t per_round = n_rounds ? (n_recs + n_rounds - 1u) / n_rounds : 0u;
 			for (uint32_t rbase = 0; rbase < n_recs; rbase += per_round) {
 				if (rbase) __syncthreads();                         // the previous round's records and items are no longer needed
-				if (*(volatile uint32_t *)&s_overflow) break;
+				if (s_overflow) break;
 				const uint32_t n_round = min(per_round, n_recs - rbase);
 				// ---- stage: records tid and tid + THREADS of the round
 				uint32_t n_items_mine[2];
@@ -948,7 +955,7 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 				const uint32_t q = lane & 7u;
 				for (uint32_t ibase = warp * 4u; ibase < n_items; ibase += N_WARPS * 4u) {
 					const uint32_t it = ibase + (lane >> 3);
-					if (*(volatile uint32_t *)&s_overflow) break;
+					if (s_overflow) break;
 					if (it >= n_items) continue;
 					const uint32_t item = s_item[it];
 					const uint32_t idx = item & 0x7ffu, j = (item >> 11) * (uint32_t)C::ITEM_WINDOWS + q;
@@ -964,16 +971,27 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 					const Key<W> stored = KO::bnot(key);
 					uint32_t slot = __umulhi(h, (uint32_t)C::SLOTS);
 					int probes = 0;
+					// linear probing, two slots per iteration: both are loaded together, then examined in probe order — the
+					// lanes of a warp leave the loop after about half as many (divergent) iterations
 					for (;;) {
-						const Key<W> have = t_key[slot];
+						const uint32_t slot1 = slot + 1 == C::SLOTS ? 0u : slot + 1;
+						const Key<W> have = t_key[slot], have1 = t_key[slot1];
 						if (KO::eq(have, stored)) break;
 						if (KO::is_zero(have) || ktab_maybe_torn<W>(have)) {
 							const Key<W> old = ktab_cas<W>(t_key + slot, stored);   // ATOMS.CAS.64 / .128
 							if (KO::is_zero(old)) { ++n_claimed; break; }
 							if (KO::eq(old, stored)) break;
 						}
+						slot = slot1;                                            // the first slot holds another key
+						if (KO::eq(have1, stored)) break;
+						if (KO::is_zero(have1) || ktab_maybe_torn<W>(have1)) {
+							const Key<W> old = ktab_cas<W>(t_key + slot, stored);
+							if (KO::is_zero(old)) { ++n_claimed; break; }
+							if (KO::eq(old, stored)) break;
+						}
 						slot = slot + 1 == C::SLOTS ? 0u : slot + 1;
-						if (++probes > C::MAX_PROBES) { s_overflow = 1; break; }       // table too full: re-run on sub-classes
+						probes += 2;
+						if (probes > C::MAX_PROBES) { s_overflow = 1; break; }        // table too full: re-run on sub-classes
 					}
 					// exactly one insert takes a key across the cutoff: the harvest knows its size before it starts
 					const uint32_t before_add = atomicAdd(t_cnt + slot, mult);
@@ -992,7 +1010,7 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 			TM_ADD(tm_wait);
 			// ---- harvest (or discard on overflow) in ONE pass over the table, which is left zeroed.  The number of solid keys
 			// is known (counted by the inserts), so the global output range is requested first and travels during the pass.
-			const bool failed = *(volatile uint32_t *)&s_overflow != 0;
+			const bool failed = s_overflow != 0;
 			const uint32_t n_out = failed ? 0u : s_nsolid, n_claims = s_claims;
 			const bool staged = n_out <= OUT_CAP;                       // else (huge group) write straight to the global arrays
 			unsigned long long out_base = 0;
@@ -1105,3 +1123,4 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 	}
 #endif
 }
+#undef s_overflow

@@ -216,6 +216,7 @@ struct pfq {
 	struct read_file *f;
 	size_t n_chunks;
 	int mapped;        /* txt is an mmap of the file */
+	int fd;            /* kept open: the fused ingest preads chunks into worker-private buffers */
 	size_t *nl;        /* newlines in chunk, then: line number of the chunk's first byte */
 	size_t *n_idx;     /* entries of idx[c] */
 	uint32_t **idx;    /* newline offsets relative to the chunk start */
@@ -311,22 +312,36 @@ static uint32_t *scan_newlines(const uint8_t *t, size_t n, size_t *n_out, int *h
 	return v;
 }
 
-static void pfq_index(size_t c, void *raw)
+/* ct = the chunk's text (ct[0] = byte c * INGEST_CHUNK of the file) */
+static void pfq_index_at(struct pfq *p, size_t c, const uint8_t *ct)
 {
-	struct pfq *p = raw;
 	const size_t lo = c * INGEST_CHUNK, hi = lo + INGEST_CHUNK < p->f->n_txt ? lo + INGEST_CHUNK : p->f->n_txt;
 	int has_cr;
-	p->idx[c] = scan_newlines(p->f->txt + lo, hi - lo, &p->n_idx[c], &has_cr);
+	p->idx[c] = scan_newlines(ct, hi - lo, &p->n_idx[c], &has_cr);
 	p->has_cr[c] = (unsigned char)has_cr;
 	p->nl[c] = p->n_idx[c];
 }
 
+static void pfq_index(size_t c, void *raw)
+{
+	struct pfq *p = raw;
+	pfq_index_at(p, c, p->f->txt + c * INGEST_CHUNK);
+}
+
 /* bytes [lo, hi) of the chunk that lie on sequence lines; with dst != NULL they are copied.  Lines are taken from the
  * chunk's newline index.  A '\r' right before the line's '\n' is dropped; a last sequence line without a newline gets one. */
+static size_t pfq_walk_at(struct pfq *p, size_t c, uint8_t *dst, const uint8_t *ct);
+
 static size_t pfq_walk(struct pfq *p, size_t c, uint8_t *dst)
 {
-	const uint8_t *t = p->f->txt;
+	return pfq_walk_at(p, c, dst, p->f->txt + c * INGEST_CHUNK);
+}
+
+/* ct = the chunk's text plus ONE byte of look-ahead when the file goes on (ct[0] = byte c * INGEST_CHUNK of the file) */
+static size_t pfq_walk_at(struct pfq *p, size_t c, uint8_t *dst, const uint8_t *ct)
+{
 	const size_t n = p->f->n_txt, base = c * INGEST_CHUNK;
+	const uint8_t *t = ct - base;                            /* so that t[file offset] addresses the chunk's bytes */
 	const uint32_t *ix = p->idx[c];
 	const size_t n_ix = p->n_idx[c];
 	size_t lo = base, hi = lo + INGEST_CHUNK < n ? lo + INGEST_CHUNK : n, line = p->nl[c], o = 0;
@@ -386,7 +401,7 @@ static int pfq_open(struct read_file *f, int n_threads, struct pfq *p)
 	p->has_cr = calloc(p->n_chunks + 1, 1);
 	/* map the file (page-cache pages, no copy); fall back to reading it into memory */
 	void *m = mmap(NULL, f->n_txt, PROT_READ, MAP_PRIVATE, fd, 0);
-	close(fd);
+	p->fd = fd;
 	if (m != MAP_FAILED) {
 		f->txt = m;
 		p->mapped = 1;
@@ -401,6 +416,7 @@ static int pfq_open(struct read_file *f, int n_threads, struct pfq *p)
 
 static void pfq_close(struct pfq *p)
 {
+	close(p->fd);
 	if (p->mapped) munmap(p->f->txt, p->f->n_txt);
 	else free(p->f->txt);
 	for (size_t c = 0; c < p->n_chunks; ++c)
@@ -509,7 +525,10 @@ int tagpu_pack_stream(const uint8_t *stream, uint64_t n_bytes, uint8_t *packed, 
 struct ing_task {
 	int file;
 	size_t chunk;      /* plain FASTQ: chunk of the file; other formats: the whole file */
-	size_t end;        /* stream offset behind this task's bytes */
+	volatile size_t end;   /* stream offset behind this task's bytes */
+	/* fused mode: published by the task before (line number of the chunk's first byte, stream offset of its bytes) */
+	volatile size_t line0, out0;
+	volatile unsigned char ready;
 };
 
 struct tagpu_ingest {
@@ -521,17 +540,78 @@ struct tagpu_ingest {
 	struct ing_task *task;
 	volatile unsigned char *done;
 	pthread_t *th;
+	/* fused mode (tagpu_ingest_open_fused): `total` is an upper bound; the true length is known when the last chunk is sized */
+	int fused;
+	uint8_t *dst;
+	volatile size_t true_total;
+	volatile int overflowed;   /* a file held more sequence bytes than the bound allows: the stream is unusable */
 };
 
 static void *ingest_worker(void *raw)
 {
 	struct tagpu_ingest *g = raw;
+	uint8_t *chunk_buf = NULL;
 	for (;;) {
 		const size_t t = __sync_fetch_and_add(&g->next, 1);
-		if (t >= g->n_tasks)
+		if (t >= g->n_tasks) {
+			free(chunk_buf);
 			return NULL;
-		const struct ing_task *k = g->task + t;
-		if (g->plain[k->file]) {
+		}
+		struct ing_task *k = g->task + t;
+		if (g->fused) {
+			/* one pass over the text: index the chunk, wait for the line number / stream offset the chunk before publishes,
+			 * size the chunk from its index, publish for the next one, then copy */
+			struct pfq *p = g->plain[k->file] ? g->pq + k->file : NULL;
+			const uint8_t *ct = NULL;
+			if (p) {
+				/* the chunk is read into this worker's own buffer (one kernel copy out of the page cache, no page fault per
+				 * 4 KB of a fresh mapping) and stays cache-warm for the sizing and the copy that follow */
+				const size_t lo = k->chunk * INGEST_CHUNK, want = (lo + INGEST_CHUNK + 1 < p->f->n_txt ? lo + INGEST_CHUNK + 1 : p->f->n_txt) - lo;
+				if (!chunk_buf && !(chunk_buf = malloc(INGEST_CHUNK + 64)))
+					TAGPU_FATAL("out of host memory for an ingest buffer");
+				size_t got = 0;
+				while (got < want) {
+					const ssize_t r = pread(p->fd, chunk_buf + got, want - got, (off_t)(lo + got));
+					if (r <= 0)
+						TAGPU_FATAL("cannot read %s", p->f->path);
+					got += (size_t)r;
+				}
+				ct = chunk_buf;
+				pfq_index_at(p, k->chunk, ct);
+			}
+			for (unsigned spins = 0; !k->ready; ++spins) {
+				if (spins < 1024) __builtin_ia32_pause();
+				else sched_yield();
+			}
+			__sync_synchronize();
+			size_t size;
+			if (p) {
+				const size_t n_nl = p->nl[k->chunk];
+				p->nl[k->chunk] = k->line0;
+				size = pfq_walk_at(p, k->chunk, NULL, ct);
+				if (t + 1 < g->n_tasks) g->task[t + 1].line0 = g->task[t + 1].file == k->file ? k->line0 + n_nl : 0;
+			} else {
+				size = g->f[k->file].n_seq;
+				if (t + 1 < g->n_tasks) g->task[t + 1].line0 = 0;
+			}
+			const size_t end = k->out0 + size;
+			if (end > g->total) g->overflowed = 1;
+			k->end = end;
+			if (t + 1 < g->n_tasks) {
+				g->task[t + 1].out0 = end;
+				__sync_synchronize();
+				g->task[t + 1].ready = 1;
+			} else {
+				g->true_total = end;
+			}
+			if (!g->overflowed) {
+				if (p) pfq_walk_at(p, k->chunk, g->dst + k->out0, ct);
+				else { g->f[k->file].dst = g->dst + k->out0; ingest_phase2(g->f + k->file); }
+				/* the last task pads the buffer up to the announced length: '\n' positions hold no window */
+				if (t + 1 == g->n_tasks && end < g->total) memset(g->dst + end, '\n', g->total - end);
+			}
+			if (t + 1 == g->n_tasks) k->end = g->total;
+		} else if (g->plain[k->file]) {
 			struct pfq *p = g->pq + k->file;
 			pfq_walk(p, k->chunk, p->f->dst + p->out[k->chunk]);
 		} else {
@@ -602,16 +682,66 @@ struct tagpu_ingest *tagpu_ingest_open(int n_files, char **files, int n_threads)
 	return g;
 }
 
+/* Fused variant: nothing is scanned here.  The stream length returned by tagpu_ingest_bytes is an UPPER BOUND (half of a
+ * plain FASTQ file: a record holds at least as many quality as sequence bytes); the workers index, size and copy every
+ * chunk in one pass over the text and pad the buffer behind the true end with '\n' (positions that hold no window), so a
+ * consumer simply processes `bound` bytes.  tagpu_ingest_finish_fused reports the true length, or -1 if a file turned out
+ * to hold more sequence than the bound (not FASTQ-shaped: use tagpu_ingest_open, which sizes exactly). */
+struct tagpu_ingest *tagpu_ingest_open_fused(int n_files, char **files, int n_threads)
+{
+	if (n_threads < 1) n_threads = 1;
+	if (n_threads > 64) n_threads = 64;
+	struct tagpu_ingest *g = calloc(1, sizeof(*g));
+	g->n_files = n_files;
+	g->n_threads = n_threads;
+	g->fused = 1;
+	g->f = calloc(n_files ? n_files : 1, sizeof(*g->f));
+	g->pq = calloc(n_files ? n_files : 1, sizeof(*g->pq));
+	g->plain = calloc(n_files ? n_files : 1, sizeof(int));
+	pthread_t *th = calloc(n_files ? n_files : 1, sizeof(pthread_t));
+	for (int i = 0; i < n_files; ++i) {
+		g->f[i].path = files[i];
+		g->plain[i] = pfq_open(g->f + i, n_threads, g->pq + i);
+		if (!g->plain[i]) pthread_create(th + i, NULL, ingest_phase1, g->f + i);
+	}
+	for (int i = 0; i < n_files; ++i) {
+		if (!g->plain[i]) pthread_join(th[i], NULL);
+		g->total += g->plain[i] ? g->f[i].n_txt / 2 + 2 : g->f[i].n_seq;
+		g->n_tasks += g->plain[i] ? g->pq[i].n_chunks : 1;
+	}
+	free(th);
+	g->task = calloc(g->n_tasks ? g->n_tasks : 1, sizeof(*g->task));
+	g->done = calloc(g->n_tasks ? g->n_tasks : 1, 1);
+	size_t t = 0;
+	for (int i = 0; i < n_files; ++i) {
+		if (g->plain[i]) {
+			for (size_t c = 0; c < g->pq[i].n_chunks; ++c, ++t) {
+				g->task[t].file = i;
+				g->task[t].chunk = c;
+			}
+		} else {
+			g->task[t].file = i;
+			++t;
+		}
+	}
+	if (g->n_tasks) g->task[0].ready = 1;          /* line 0, offset 0 */
+	else g->total = 0;
+	return g;
+}
+
 uint64_t tagpu_ingest_bytes(const struct tagpu_ingest *g) { return g->total; }
 
 void tagpu_ingest_start(struct tagpu_ingest *g, uint8_t *dst)
 {
+	g->dst = dst;
 	size_t o = 0;
 	for (int i = 0; i < g->n_files; ++i) {
 		g->f[i].dst = dst + o;
 		o += g->f[i].n_seq;
 	}
 	g->n_workers = g->n_tasks < (size_t)g->n_threads ? (int)g->n_tasks : g->n_threads;
+	const long n_cpu = sysconf(_SC_NPROCESSORS_ONLN);             /* the fused workers wait for each other in task order: */
+	if (g->fused && n_cpu > 0 && g->n_workers > n_cpu) g->n_workers = (int)n_cpu;   /* never more of them than cores */
 	g->th = calloc(g->n_workers ? g->n_workers : 1, sizeof(pthread_t));
 	for (int i = 0; i < g->n_workers; ++i)
 		pthread_create(g->th + i, NULL, ingest_worker, g);
@@ -628,10 +758,27 @@ uint64_t tagpu_ingest_ready(void *raw)
 	return g->cursor == g->n_tasks ? g->total : (g->cursor ? g->task[g->cursor - 1].end : 0);
 }
 
+static void ingest_release(struct tagpu_ingest *g);
+
 void tagpu_ingest_finish(struct tagpu_ingest *g)
 {
 	for (int i = 0; i < g->n_workers; ++i)
 		pthread_join(g->th[i], NULL);
+	ingest_release(g);
+}
+
+/* joins the workers of a fused ingest: true stream length, or -1 (see tagpu_ingest_open_fused) */
+int64_t tagpu_ingest_finish_fused(struct tagpu_ingest *g)
+{
+	for (int i = 0; i < g->n_workers; ++i)
+		pthread_join(g->th[i], NULL);
+	const int64_t n = g->overflowed ? -1 : (int64_t)(g->n_tasks ? g->true_total : 0);
+	ingest_release(g);
+	return n;
+}
+
+static void ingest_release(struct tagpu_ingest *g)
+{
 	for (int i = 0; i < g->n_files; ++i)
 		if (g->plain[i]) pfq_close(g->pq + i);
 	free(g->th);
@@ -645,13 +792,26 @@ void tagpu_ingest_finish(struct tagpu_ingest *g)
 
 int64_t tagpu_load_reads(int n_files, char **files, int n_threads, uint8_t **stream)
 {
-	struct tagpu_ingest *g = tagpu_ingest_open(n_files, files, n_threads);
-	const size_t total = g->total;
-	uint8_t *s = stream_buffer(total + 64);
-	tagpu_ingest_start(g, s);
-	tagpu_ingest_finish(g);
+	/* one pass over the text (fused); a file that is not FASTQ-shaped enough for the size bound is re-read with exact sizes */
+	int64_t total = -1;
+	uint8_t *s = NULL;
+	struct tagpu_ingest *g;
+	if (!getenv("TAGPU_INGEST_TWO_PASS")) {                    /* (developer knob: compare the two ingest schedules) */
+		g = tagpu_ingest_open_fused(n_files, files, n_threads);
+		s = stream_buffer(g->total + 64);
+		tagpu_ingest_start(g, s);
+		total = tagpu_ingest_finish_fused(g);
+	}
+	if (total < 0) {
+		if (s) tagpu_free_reads(s);
+		g = tagpu_ingest_open(n_files, files, n_threads);
+		total = (int64_t)g->total;
+		s = stream_buffer((size_t)total + 64);
+		tagpu_ingest_start(g, s);
+		tagpu_ingest_finish(g);
+	}
 	*stream = s;
-	return (int64_t)total;
+	return total;
 }
 
 void tagpu_free_reads(uint8_t *stream)
@@ -1038,14 +1198,14 @@ static int64_t gather_files(int n_files, char **files_1, char **files_2, int n_t
 /* files_1[0..n) ++ files_2[0..n) (/root/reference/src/kmer_build.c:733-735) opened for ingest: index + sizes done, the
  * stream length known; the copy into the pinned stream buffer then runs while the GPU layer already uploads the finished
  * prefix (tagpu_set_source_progress) */
-static struct tagpu_ingest *open_pairs(int n_files, char **files_1, char **files_2, int n_threads)
+static struct tagpu_ingest *open_pairs(int n_files, char **files_1, char **files_2, int n_threads, int fused)
 {
 	if (n_files < 0)
 		TAGPU_FATAL("n_files < 0 (contig-file mode) is not supported by the GPU path");
 	char **all = malloc(2 * (size_t)n_files * sizeof(char *) + 1);
 	memcpy(all, files_1, n_files * sizeof(char *));
 	memcpy(all + n_files, files_2, n_files * sizeof(char *));
-	struct tagpu_ingest *ing = tagpu_ingest_open(2 * n_files, all, n_threads);
+	struct tagpu_ingest *ing = fused ? tagpu_ingest_open_fused(2 * n_files, all, n_threads) : tagpu_ingest_open(2 * n_files, all, n_threads);
 	free(all);
 	return ing;
 }
@@ -1054,19 +1214,26 @@ static void stage_entry(int ksize, int n_threads, int n_files, char **files_1, c
 			struct asm_graph_t *g, int skip_counts)
 {
 	tagpu_ctx *ctx = global_ctx();
-	double t0 = now_s();
-	struct tagpu_ingest *ing = open_pairs(n_files, files_1, files_2, n_threads);
-	const uint64_t n = tagpu_ingest_bytes(ing);
-	uint8_t *stream = stream_buffer(n + 64);
-	double t1 = now_s();
-	/* the copy workers fill `stream` in order; pass 1 on the GPU chases them chunk by chunk */
-	tagpu_ingest_start(ing, stream);
+	double t0 = now_s(), t1 = t0;
 	tagpu_set_skip_counts(ctx, skip_counts);
-	tagpu_set_source_progress(ctx, tagpu_ingest_ready, ing);
-	if (tagpu_build_host(ctx, stream, n, ksize))
-		TAGPU_FATAL("GPU graph build failed: %s", tagpu_last_error(ctx));
-	tagpu_ingest_finish(ing);
-	tagpu_free_reads(stream);
+	for (int fused = getenv("TAGPU_INGEST_TWO_PASS") ? 0 : 1; fused >= 0; --fused) {
+		/* fused ingest: the workers index, size and copy each chunk in one pass while pass 1 on the GPU chases them; the
+		 * announced stream length is an upper bound and the buffer is padded with '\n' (no windows there).  Files that do
+		 * not respect the bound (not FASTQ-shaped) take the two-pass ingest with exact sizes. */
+		struct tagpu_ingest *ing = open_pairs(n_files, files_1, files_2, n_threads, fused);
+		const uint64_t n = tagpu_ingest_bytes(ing);
+		uint8_t *stream = stream_buffer(n + 64);
+		t1 = now_s();
+		tagpu_ingest_start(ing, stream);
+		tagpu_set_source_progress(ctx, tagpu_ingest_ready, ing);
+		if (tagpu_build_host(ctx, stream, n, ksize))
+			TAGPU_FATAL("GPU graph build failed: %s", tagpu_last_error(ctx));
+		int64_t true_n = (int64_t)n;
+		if (fused) true_n = tagpu_ingest_finish_fused(ing);
+		else tagpu_ingest_finish(ing);
+		tagpu_free_reads(stream);
+		if (true_n >= 0) break;
+	}
 	double t2 = now_s();
 	if (getenv("TAGPU_WRITE_KMC_DB") && tagpu_write_kmc_db(ctx, work_dir))
 		TAGPU_FATAL("cannot write the KMC database into %s", work_dir);
@@ -1080,7 +1247,7 @@ static void stage_entry(int ksize, int n_threads, int n_files, char **files_1, c
 	if (tagpu_fill_asm_graph(ctx, g))
 		TAGPU_FATAL("cannot materialise the assembly graph: %s", tagpu_last_error(ctx));
 	double t3 = now_s();
-	fprintf(stderr, "[tagpu] k=%d: %lu (k+1)-mer instances, %lu solid; read index %.3f s, parse + H2D + GPU %.3f s (device %.3f ms), "
+	fprintf(stderr, "[tagpu] k=%d: %lu (k+1)-mer instances, %lu solid; open %.3f s, parse + H2D + GPU %.3f s (device %.3f ms), "
 			"graph materialisation %.3f s\n", ksize, (unsigned long)st.n_instances, (unsigned long)st.n_solid,
 		t1 - t0, t2 - t1, st.ms_total, t3 - t2);
 }
@@ -1156,15 +1323,20 @@ int KMC_build_kmer_database(int ksize, const char *working_dir, int n_threads, i
 {
 	(void)mmem;
 	tagpu_ctx *ctx = global_ctx();
-	struct tagpu_ingest *ing = tagpu_ingest_open(n_files, files, n_threads);
-	const uint64_t n = tagpu_ingest_bytes(ing);
-	uint8_t *stream = stream_buffer(n + 64);
-	tagpu_ingest_start(ing, stream);
-	tagpu_set_source_progress(ctx, tagpu_ingest_ready, ing);
-	if (tagpu_count_host(ctx, stream, n, ksize))
-		TAGPU_FATAL("GPU k-mer counting failed: %s", tagpu_last_error(ctx));
-	tagpu_ingest_finish(ing);
-	tagpu_free_reads(stream);
+	for (int fused = 1; fused >= 0; --fused) {
+		struct tagpu_ingest *ing = fused ? tagpu_ingest_open_fused(n_files, files, n_threads) : tagpu_ingest_open(n_files, files, n_threads);
+		const uint64_t n = tagpu_ingest_bytes(ing);
+		uint8_t *stream = stream_buffer(n + 64);
+		tagpu_ingest_start(ing, stream);
+		tagpu_set_source_progress(ctx, tagpu_ingest_ready, ing);
+		if (tagpu_count_host(ctx, stream, n, ksize))
+			TAGPU_FATAL("GPU k-mer counting failed: %s", tagpu_last_error(ctx));
+		int64_t true_n = (int64_t)n;
+		if (fused) true_n = tagpu_ingest_finish_fused(ing);
+		else tagpu_ingest_finish(ing);
+		tagpu_free_reads(stream);
+		if (true_n >= 0) break;
+	}
 	if (tagpu_write_kmc_db(ctx, working_dir))
 		TAGPU_FATAL("cannot write the KMC database into %s", working_dir);
 	return 0;
@@ -1181,11 +1353,9 @@ struct cov_result {
 struct mini_hash_t *kmer_count_on_edges(struct opt_proc_t *opt, struct asm_graph_t *g)
 {
 	tagpu_ctx *ctx = global_ctx();
-	struct tagpu_ingest *ing = open_pairs(opt->n_files, opt->files_1, opt->files_2, opt->n_threads);
-	const uint64_t n = tagpu_ingest_bytes(ing);
-	uint8_t *stream = stream_buffer(n + 64);
-	tagpu_ingest_start(ing, stream);
-	/* flatten the edges while the reads are being parsed */
+	uint8_t *stream;
+	const uint64_t n = (uint64_t)gather_files(opt->n_files, opt->files_1, opt->files_2, opt->n_threads, &stream);
+	/* flatten the edges */
 	const gint_t n_e = g->n_e;
 	uint32_t *len = malloc((n_e + 1) * 4), *rc = malloc((n_e + 1) * 4);
 	uint64_t *off = malloc((n_e + 1) * 8), n_words = 0;
@@ -1202,7 +1372,6 @@ struct mini_hash_t *kmer_count_on_edges(struct opt_proc_t *opt, struct asm_graph
 		TAGPU_FATAL("out of host memory for the coverage recount");
 	for (gint_t e = 0; e < n_e; ++e)
 		if (len[e]) memcpy(words + off[e], g->edges[e].seq, (((size_t)len[e] + 15) >> 4) * 4);
-	tagpu_ingest_finish(ing);
 	if (tagpu_coverage_recount_host(ctx, stream, n, (uint64_t)n_e, len, off, words, n_words, rc, res->count))
 		TAGPU_FATAL("GPU coverage recount failed: %s", tagpu_last_error(ctx));
 	tagpu_free_reads(stream);

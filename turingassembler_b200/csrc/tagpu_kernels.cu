@@ -1287,6 +1287,52 @@ extern "C" int tagpu_dist_graph_paths(tagpu_ctx *ctx, const uint64_t *all_stats,
 	return 0;
 }
 
+// One whole multi-GPU step in a single call: the phases above with the barriers and counter exchanges between them taken
+// from a tagpu_shm segment (tagpu_host.c), so that no host-language round trip sits between the kernels of a step.
+// src_kind: 0 = device stream, 1 = pinned host ASCII stream, 2 = pinned host packed stream (n = positions).
+// flags: bit 0 = build the graph, bit 1 = also gather the solid sets on every rank, bit 2 = the previous step left paths in
+// the arenas that other ranks may still be pulling (barrier first).  Returns 0, or -1 (error text in tagpu_last_error);
+// *used_paths tells whether the two-level stage ran (then the caller sets bit 2 for the next step).
+struct tagpu_shm;
+extern "C" void tagpu_shm_barrier(struct tagpu_shm *s);
+extern "C" int tagpu_shm_allgather(struct tagpu_shm *s, const uint64_t *mine, int n, uint64_t *all);
+
+extern "C" int tagpu_dist_step(tagpu_ctx *ctx, struct tagpu_shm *shm, const uint8_t *src, uint64_t n, int src_kind, int flags, int *used_paths)
+{
+	DistState *d = ctx->dist;
+	if (!d || !d->connected || !shm) return fail(ctx, "tagpu_dist_step before tagpu_dist_plan / tagpu_dist_connect, or without a rendezvous segment");
+	*used_paths = 0;
+	if (flags & 4) tagpu_shm_barrier(shm);
+	int rc = src_kind == 0 ? tagpu_dist_partition(ctx, src, n) : src_kind == 1 ? tagpu_dist_partition_host(ctx, src, n) : tagpu_dist_partition_host_packed(ctx, src, n);
+	// a failing rank still has to meet the others at every rendezvous of the step, or they would wait for ever
+	uint64_t mine[4] = { 0, 0, 0, 0 }, all_stats[4 * TAGPU_MAX_RANKS], all_paths[4 * TAGPU_MAX_RANKS];
+	tagpu_shm_barrier(shm);
+	if (!rc) rc = tagpu_dist_count(ctx, mine);
+	const uint64_t bad = ~0ull;
+	if (rc) mine[0] = bad;
+	tagpu_shm_allgather(shm, mine, 4, all_stats);
+	bool any_bad = false;
+	for (int r = 0; r < d->world; ++r) any_bad = any_bad || all_stats[4 * r] == bad;
+	if (any_bad) return rc ? rc : fail(ctx, "another rank failed in the count stage");
+	const bool with_graph = (flags & 1) != 0;
+	if (with_graph && ctx->contract) {
+		uint64_t paths[4] = { 0, 0, 0, 0 };
+		rc = tagpu_dist_contract(ctx, paths);
+		if (rc) { paths[0] = bad; paths[3] = 0; }
+		tagpu_shm_allgather(shm, paths, 4, all_paths);
+		bool all_ok = true;
+		for (int r = 0; r < d->world; ++r) {
+			if (all_paths[4 * r] == bad) return rc ? rc : fail(ctx, "another rank failed in the contraction");
+			all_ok = all_ok && all_paths[4 * r + 3] != 0;
+		}
+		if (all_ok) {
+			*used_paths = 1;
+			return tagpu_dist_graph_paths(ctx, all_stats, all_paths, (flags & 2) ? 3 : 1);
+		}
+	}
+	return tagpu_dist_graph(ctx, all_stats, with_graph ? 1 : 0);
+}
+
 extern "C" void tagpu_dist_disconnect(tagpu_ctx *ctx)
 {
 	cudaSetDevice(ctx->device);

@@ -94,6 +94,13 @@ class DistTagpu:
         host=True); returns the GLOBAL stats on every rank.  gather_solid=False leaves the solid (k+1)-mers sharded over
         their owner ranks when the two-level graph stage runs (only the contracted paths travel)."""
         t = self.t
+        if self._shm and hasattr(t, "dist_step"):
+            # the whole step in one C call (tagpu_dist_step): barriers and counter exchanges over the shared-memory segment
+            kind = 2 if (host and packed) else 1 if host else 0
+            flags = (1 if with_graph else 0) | (2 if gather_solid else 0) | (4 if self._dirty else 0)
+            st, used_paths = t.dist_step(self._shm, ptr, n_local_bytes, kind, flags)
+            self._dirty = bool(used_paths)
+            return st
         if self._dirty:
             self.barrier()
             self._dirty = False
