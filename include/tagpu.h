@@ -137,6 +137,28 @@ int tagpu_coverage_recount_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n
 
 int tagpu_get_stats(tagpu_ctx *ctx, struct tagpu_stats *out);
 
+/* Many local builds in flight (row f1; the reference's caller is a sequential loop over thousands of gaps,
+ * /root/reference/src/build_bridge.c:1036-1062): n_jobs independent tagpu_build_local_host builds worked through by n_ctx
+ * contexts (<= 64; kept across calls), each with its own CUDA stream and host thread, so that the small kernels of
+ * different gaps overlap on the device.  Per job: inputs as for tagpu_build_local_host; cutoff (0 = 2); g = NULL or a
+ * caller-owned struct to fill like build_local_assembly_graph does; rc and stats are set on return.  Returns 0 if every
+ * job succeeded. */
+struct tagpu_local_job {
+	const uint8_t *reads;
+	uint64_t n_bytes;
+	int k, cutoff;
+	const uint8_t *contigs;
+	uint64_t n_contig_bytes;
+	int n_contigs;
+	const uint64_t *contig_off;
+	const uint32_t *contig_len;
+	const double *contig_cov;
+	struct asm_graph_t *g;
+	int rc;
+	struct tagpu_stats stats;
+};
+int tagpu_build_local_batch(int device, int n_ctx, struct tagpu_local_job *jobs, int n_jobs);
+
 /* Device -> host copies of the last build; caller allocates from tagpu_stats sizes.
  * Keys are (hi, lo) pairs of the 2-bit packed mer, first base most significant. Order is unspecified. */
 int tagpu_copy_solid(tagpu_ctx *ctx, uint64_t *hi, uint64_t *lo, uint32_t *count);         /* n_solid each */

@@ -42,3 +42,15 @@ with tempfile.TemporaryDirectory() as td:
                                capture_output=True, text=True)
             best = min(best, time.perf_counter() - t0)
         print(f"CPU  reference build_local_assembly_graph via TA_local_ref (process start + load g0 + FASTQ + build + save, {os.cpu_count()} threads): {best * 1e3:.1f} ms")
+
+    # ---- many gaps in flight (tagpu_build_local_batch): the caller's loop runs over thousands of gaps
+    from turingassembler_b200.api import build_local_batch
+    n_jobs = int(os.environ.get("LOCAL_BENCH_JOBS", "1024"))
+    job = dict(stream=lc["stream"], k=lc["lk"], contigs=lc["contigs"], covs=lc["covs"])
+    for n_ctx in (1, 4, 8, 16, 32):
+        build_local_batch([job] * min(n_jobs, 4 * n_ctx), n_ctx)          # warm the contexts
+        t0 = time.perf_counter()
+        stats, _ = build_local_batch([job] * n_jobs, n_ctx)
+        dt = time.perf_counter() - t0
+        assert all(s_["n_e"] == st["n_e"] and s_["n_solid"] == st["n_solid"] for s_ in stats)
+        print(f"GPU  tagpu_build_local_batch: {n_jobs} gaps on {n_ctx:2d} contexts: {dt / n_jobs * 1e3:.3f} ms per gap, {n_jobs / dt:.0f} gaps/s")

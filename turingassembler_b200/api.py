@@ -112,6 +112,14 @@ class AsmGraph(C.Structure):
     ]
 
 
+class LocalJob(C.Structure):
+    """struct tagpu_local_job (include/tagpu.h)"""
+    _fields_ = [("reads", C.c_void_p), ("n_bytes", C.c_uint64), ("k", C.c_int), ("cutoff", C.c_int),
+                ("contigs", C.c_void_p), ("n_contig_bytes", C.c_uint64), ("n_contigs", C.c_int),
+                ("contig_off", C.POINTER(C.c_uint64)), ("contig_len", C.POINTER(C.c_uint32)), ("contig_cov", C.POINTER(C.c_double)),
+                ("g", C.POINTER(AsmGraph)), ("rc", C.c_int), ("stats", Stats)]
+
+
 _lib = None
 
 
@@ -150,6 +158,8 @@ def load_library() -> C.CDLL:
     lib.build_local_assembly_graph.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_char_p,
                                                C.POINTER(AsmGraph), C.POINTER(AsmGraph), C.c_int64, C.c_int64]
     lib.tagpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.tagpu_build_local_batch.restype = i32
+    lib.tagpu_build_local_batch.argtypes = [i32, i32, C.POINTER(LocalJob), i32]
     lib.tagpu_copy_solid.restype = i32
     lib.tagpu_copy_solid.argtypes = [vp, vp, vp, vp]
     lib.tagpu_copy_kmers.restype = i32
@@ -491,6 +501,36 @@ def pack_stream(stream, threads: int = 8, out: np.ndarray | None = None) -> np.n
         raise TagpuError("tagpu_pack_stream failed (host and device tile layouts disagree)")
     del keep
     return out
+
+
+def build_local_batch(jobs, n_ctx: int = 8, device: int = 0, fill: bool = False):
+    """tagpu_build_local_batch: `jobs` = list of dict(stream=bytes/ndarray, k=int, contigs=[bytes], covs=[float]).
+    -> (list of stats dicts, list of AsmGraph or None).  The builds run concurrently on n_ctx contexts."""
+    lib = load_library()
+    arr = (LocalJob * len(jobs))()
+    keep, graphs = [], []
+    for j, job in zip(arr, jobs):
+        a = np.frombuffer(job["stream"], dtype=np.uint8) if isinstance(job["stream"], (bytes, bytearray)) else np.ascontiguousarray(job["stream"])
+        txt = b"".join(c + b"\n" for c in job["contigs"])
+        nc = len(job["contigs"])
+        offs, o = [], 0
+        for c in job["contigs"]:
+            offs.append(o)
+            o += len(c) + 1
+        off_a, len_a, cov_a = (C.c_uint64 * nc)(*offs), (C.c_uint32 * nc)(*[len(c) for c in job["contigs"]]), (C.c_double * nc)(*job["covs"])
+        txt_b = C.create_string_buffer(txt, len(txt) + 1)
+        g = AsmGraph() if fill else None
+        keep.append((a, txt_b, off_a, len_a, cov_a, g))
+        graphs.append(g)
+        j.reads, j.n_bytes, j.k, j.cutoff = a.ctypes.data, a.size, job["k"], job.get("cutoff", 2)
+        j.contigs, j.n_contig_bytes, j.n_contigs = C.cast(txt_b, C.c_void_p), len(txt), nc
+        j.contig_off, j.contig_len, j.contig_cov = off_a, len_a, cov_a
+        j.g = C.pointer(g) if fill else None
+    rc = lib.tagpu_build_local_batch(device, n_ctx, arr, len(jobs))
+    if rc != 0:
+        raise TagpuError(f"tagpu_build_local_batch: {sum(1 for j in arr if j.rc)} of {len(jobs)} jobs failed")
+    del keep
+    return [j.stats.as_dict() for j in arr], graphs
 
 
 def free_asm_graph(g: AsmGraph):

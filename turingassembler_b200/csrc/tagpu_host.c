@@ -994,19 +994,25 @@ int tagpu_fill_asm_graph_from_flat(const struct tagpu_flat_graph *h, int ksize, 
 /* Fills a caller-owned, uninitialised struct asm_graph_t exactly as build_asm_graph_from_kmhash leaves it
  * (/root/reference/src/kmer_build.c:567-575): nodes/edges are single blocks, every adj and every seq is its
  * own allocation because later stages realloc/free them one by one. g->candidates is not touched. */
+static pthread_mutex_t g_flat_lock = PTHREAD_MUTEX_INITIALIZER;   /* the pinned scratch block is shared by all contexts */
+
 int tagpu_fill_asm_graph(tagpu_ctx *ctx, struct asm_graph_t *g)
 {
 	struct tagpu_flat_graph h;
 	struct tagpu_stats st;
 	const int trace = getenv("TAGPU_TRACE_FILL") != NULL;
 	const double t0 = now_s();
-	if (fetch_graph(ctx, &h, &st))
+	pthread_mutex_lock(&g_flat_lock);
+	if (fetch_graph(ctx, &h, &st)) {
+		pthread_mutex_unlock(&g_flat_lock);
 		return -1;
+	}
 	const double t1 = now_s();
 	const int rc = tagpu_fill_asm_graph_from_flat(&h, tagpu_ctx_k(ctx), g);
 	if (trace)
 		fprintf(stderr, "[tagpu] fill: device -> pinned host %.2f ms, nodes + edges %.2f ms\n", (t1 - t0) * 1e3, (now_s() - t1) * 1e3);
 	free_flat(&h);
+	pthread_mutex_unlock(&g_flat_lock);
 	return rc;
 }
 
@@ -1310,6 +1316,72 @@ void build_local_assembly_graph(int ksize, int n_threads, int mmem, int n_files,
 	fprintf(stderr, "[tagpu] Number of (k+1)-mer on edge: %lu\n", (unsigned long)st.n_kp1_on_edge);   /* :1032 */
 	if (tagpu_fill_asm_graph(ctx, g))
 		TAGPU_FATAL("cannot materialise the assembly graph: %s", tagpu_last_error(ctx));
+}
+
+/* ------------------------------------------------------------------ many local builds in flight (row f1)
+ * The reference calls build_local_assembly_graph in a sequential loop over thousands of gaps
+ * (/root/reference/src/build_bridge.c:1036-1062), each a build of a few thousand reads: on a GPU one such build is a chain
+ * of ~30 tiny kernels and a handful of read-backs, i.e. launch latency.  The key spaces of different gaps must stay
+ * separate, so the gaps are not merged into one build; instead n_ctx contexts — each with its own CUDA stream, buffers
+ * and host thread — work through the job list concurrently and the small kernels of different gaps overlap on the GPU. */
+struct local_batch {
+	struct tagpu_local_job *jobs;
+	int n_jobs, next, device;
+};
+
+static tagpu_ctx *g_pool[64];
+static pthread_mutex_t g_pool_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static void *local_batch_worker(void *raw)
+{
+	struct local_batch *b = raw;
+	tagpu_ctx *ctx = NULL;
+	int slot = -1;
+	pthread_mutex_lock(&g_pool_lock);                       /* contexts are kept across calls: creating one allocates streams and events */
+	for (int i = 0; i < 64 && slot < 0; ++i)
+		if (g_pool[i]) { ctx = g_pool[i]; g_pool[i] = NULL; slot = i; }
+	pthread_mutex_unlock(&g_pool_lock);
+	if (!ctx) ctx = tagpu_create(b->device);
+	for (;;) {
+		const int j = __sync_fetch_and_add(&b->next, 1);
+		if (j >= b->n_jobs)
+			break;
+		struct tagpu_local_job *job = b->jobs + j;
+		if (!ctx) { job->rc = -1; continue; }
+		tagpu_set_cutoff(ctx, job->cutoff > 0 ? job->cutoff : 2);
+		tagpu_set_skip_counts(ctx, 0);
+		job->rc = tagpu_build_local_host(ctx, job->reads, job->n_bytes, job->k, job->contigs, job->n_contig_bytes, job->n_contigs,
+						 job->contig_off, job->contig_len, job->contig_cov);
+		if (!job->rc) {
+			tagpu_get_stats(ctx, &job->stats);
+			if (job->g) job->rc = tagpu_fill_asm_graph(ctx, job->g);
+		}
+	}
+	if (ctx) {
+		pthread_mutex_lock(&g_pool_lock);
+		for (int i = 0; i < 64; ++i)
+			if (!g_pool[i]) { g_pool[i] = ctx; ctx = NULL; break; }
+		pthread_mutex_unlock(&g_pool_lock);
+		if (ctx) tagpu_destroy(ctx);
+	}
+	return NULL;
+}
+
+int tagpu_build_local_batch(int device, int n_ctx, struct tagpu_local_job *jobs, int n_jobs)
+{
+	if (n_ctx < 1) n_ctx = 1;
+	if (n_ctx > 64) n_ctx = 64;
+	if (n_ctx > n_jobs) n_ctx = n_jobs;
+	struct local_batch b = { jobs, n_jobs, 0, device };
+	pthread_t th[64];
+	for (int i = 0; i < n_ctx; ++i)
+		pthread_create(th + i, NULL, local_batch_worker, &b);
+	for (int i = 0; i < n_ctx; ++i)
+		pthread_join(th[i], NULL);
+	int bad = 0;
+	for (int j = 0; j < n_jobs; ++j)
+		bad += jobs[j].rc != 0;
+	return bad ? -1 : 0;
 }
 
 void build_initial_graph(struct opt_proc_t *opt, int ksize, struct asm_graph_t *g)
