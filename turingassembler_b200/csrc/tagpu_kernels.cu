@@ -469,7 +469,12 @@ static int count_owned_once(tagpu_ctx *ctx, const PartCfg &cfg, const CountPeers
 		       (uint32_t)BC::GROUP_TARGET, (uint32_t *)ctx->grp_start.p, (uint32_t *)ctx->grp_end.p);
 		LAUNCH(k_group_desc, (unsigned)((n_groups_cap + 255) / 256), 256, (const uint32_t *)ctx->grp_start.p, (const uint32_t *)ctx->grp_end.p,
 		       (const unsigned long long *)ctx->cur_all.p, world, group_max, (const unsigned long long *)ctx->d_ctr, (GroupDesc *)ctx->grp_desc.p);
-		LAUNCH_SMEM(k_count_buckets<W>, BC::CTAS_PER_SM * ctx->n_sm, BC::THREADS, BC::SMEM, peers, world, first_bucket, cfg.cap_records,
+		// persistent CTAs, but never more than there can be groups: a tiny build (local assembly: a few hundred KB of reads)
+		// then occupies a few SMs and the builds of other contexts overlap with it (tagpu_build_local_batch)
+		const uint64_t full_grid = (uint64_t)BC::CTAS_PER_SM * ctx->n_sm;
+		static const bool full_grids = getenv("TAGPU_FULL_GRIDS") != nullptr;     // developer A/B: always the whole device
+		const unsigned count_grid = (unsigned)(!full_grids && n_groups_cap < full_grid ? n_groups_cap : full_grid);
+		LAUNCH_SMEM(k_count_buckets<W>, count_grid, BC::THREADS, BC::SMEM, peers, world, first_bucket, cfg.cap_records,
 			    (const unsigned long long *)ctx->cur_all.p, (const uint32_t *)ctx->ext_all.p, (const uint32_t *)ctx->grp_start.p,
 			    (const uint32_t *)ctx->grp_end.p, (const GroupDesc *)ctx->grp_desc.p, group_max, cfg.K, (uint32_t)ctx->ci, (Key<W> *)ctx->solid_key.p, (uint32_t *)ctx->solid_cnt.p,
 			    (unsigned long long)solid_cap, (SolidBlock *)ctx->blocks.p, blocks_cap, ctx->d_ctr);
@@ -551,7 +556,11 @@ static int rank_lists(tagpu_ctx *ctx, unsigned long long *jump, uint32_t n_cv)
 		uint32_t n_cv_arg = n_cv;
 		void *args[] = { &jump, &n_cv_arg, &ctr, &max_rounds };
 		ProfScope ps_(ctx, "k_jump_all");
-		CU(cudaLaunchCooperativeKernel((void *)k_jump_all, dim3(ctx->jump_grid), dim3(512), args, 0, ctx->stream));
+		// (a cooperative launch needs all its CTAs co-resident: a small list takes a small grid, so that the launches of
+		// several contexts fit on the device side by side)
+		static const bool full_grids = getenv("TAGPU_FULL_GRIDS") != nullptr;
+		const unsigned need = (n_cv + 511u) / 512u, jg = !full_grids && need < (unsigned)ctx->jump_grid ? (need ? need : 1u) : (unsigned)ctx->jump_grid;
+		CU(cudaLaunchCooperativeKernel((void *)k_jump_all, dim3(jg), dim3(512), args, 0, ctx->stream));
 		++ctx->launches;
 		return 0;
 	}
@@ -748,7 +757,7 @@ static int contract_local(tagpu_ctx *ctx, const PathStore<W> &ps)
 		{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->d_ctr + CTR_SPARE2, 0, 16, ctx->stream)); }   // and CTR_SPARE3
 		{
 			ProfScope ps_(ctx, "k_contract<W>");
-			k_small<<<grid_s[W], CC::T_SMALL, smem_s, ctx->stream>>>(blocks, n_blocks, solid, solid_cnt, ctx->k, ctx->log2_buckets, none, 0, list1,
+			k_small<<<(n_blocks < (uint32_t)grid_s[W] ? n_blocks : (uint32_t)grid_s[W]), CC::T_SMALL, smem_s, ctx->stream>>>(blocks, n_blocks, solid, solid_cnt, ctx->k, ctx->log2_buckets, none, 0, list1,
 										 (int)CTR_SPARE2, ps, ctx->d_ctr);
 			++ctx->launches;
 			CU(cudaGetLastError());
@@ -758,7 +767,7 @@ static int contract_local(tagpu_ctx *ctx, const PathStore<W> &ps)
 		if (medium) {
 			{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->d_ctr + CTR_SPARE1, 0, 8, ctx->stream)); }
 			ProfScope ps_(ctx, "k_contract_medium<W>");
-			k_medium<<<grid_m[W], CC::T_MEDIUM, smem_m, ctx->stream>>>(blocks, n_blocks, solid, solid_cnt, ctx->k, ctx->log2_buckets, list1,
+			k_medium<<<(n_blocks < (uint32_t)grid_m[W] ? n_blocks : (uint32_t)grid_m[W]), CC::T_MEDIUM, smem_m, ctx->stream>>>(blocks, n_blocks, solid, solid_cnt, ctx->k, ctx->log2_buckets, list1,
 										   (int)CTR_SPARE2, list2, (int)CTR_SPARE3, ps, ctx->d_ctr);
 			++ctx->launches;
 			CU(cudaGetLastError());
@@ -768,7 +777,7 @@ static int contract_local(tagpu_ctx *ctx, const PathStore<W> &ps)
 		{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->d_ctr + CTR_SPARE1, 0, 8, ctx->stream)); }
 		{
 			ProfScope ps_(ctx, "k_contract_large<W>");
-			k_large<<<grid_l[W], CC::T_LARGE, smem_l, ctx->stream>>>(blocks, n_blocks, solid, solid_cnt, ctx->k, ctx->log2_buckets, rest, rest_ctr,
+			k_large<<<(n_blocks < (uint32_t)grid_l[W] ? n_blocks : (uint32_t)grid_l[W]), CC::T_LARGE, smem_l, ctx->stream>>>(blocks, n_blocks, solid, solid_cnt, ctx->k, ctx->log2_buckets, rest, rest_ctr,
 										 (uint32_t *)nullptr, 0, ps, ctx->d_ctr);
 			++ctx->launches;
 			CU(cudaGetLastError());
