@@ -1109,49 +1109,109 @@ struct kmc_trailer {
 
 /* Writes what /root/reference/src/KMC_reader.c:22-74 (prefix file) and :204-256 (suffix records) read back:
  * records sorted by value, prefix LUT over the top lut_prefix_length bases, 4-byte little-endian counters. */
+/* The records must be sorted by value, and the prefix file needs the number of records per lut_prefix_length-base prefix
+ * anyway: so the sort is a parallel bucket sort on exactly that prefix (per-chunk histograms -> offsets -> scatter, all
+ * chunks in parallel), followed by an independent qsort inside every prefix bucket, buckets in parallel. */
+#define KMC_SORT_CHUNKS 64
+
+struct kmc_sort {
+	const uint64_t *hi, *lo;
+	const uint32_t *cnt;
+	uint64_t n, n_lut;
+	int shift;                 /* 2 * suffix bases: key >> shift = prefix */
+	uint64_t *hist;            /* [KMC_SORT_CHUNKS][n_lut]: counts, then scatter cursors */
+	const uint64_t *lut;       /* [n_lut + 1] first record of every prefix */
+	struct solid_rec *rec;
+};
+
+static inline uint64_t kmc_prefix(const struct kmc_sort *k, uint64_t i)
+{
+	const unsigned __int128 x = ((unsigned __int128)k->hi[i] << 64) | k->lo[i];
+	return (uint64_t)(x >> k->shift);
+}
+
+static void kmc_hist_task(size_t c, void *raw)
+{
+	struct kmc_sort *k = raw;
+	const uint64_t lo = k->n * c / KMC_SORT_CHUNKS, hi = k->n * (c + 1) / KMC_SORT_CHUNKS;
+	uint64_t *h = k->hist + c * k->n_lut;
+	for (uint64_t i = lo; i < hi; ++i)
+		++h[kmc_prefix(k, i)];
+}
+
+static void kmc_scatter_task(size_t c, void *raw)
+{
+	struct kmc_sort *k = raw;
+	const uint64_t lo = k->n * c / KMC_SORT_CHUNKS, hi = k->n * (c + 1) / KMC_SORT_CHUNKS;
+	uint64_t *cur = k->hist + c * k->n_lut;
+	for (uint64_t i = lo; i < hi; ++i) {
+		struct solid_rec *r = k->rec + cur[kmc_prefix(k, i)]++;
+		r->hi = k->hi[i]; r->lo = k->lo[i]; r->cnt = k->cnt[i];
+	}
+}
+
+static void kmc_bucket_sort_task(size_t t, void *raw)
+{
+	struct kmc_sort *k = raw;
+	/* task t sorts the prefixes [t * 64, t * 64 + 64) */
+	for (uint64_t b = t * 64; b < (t + 1) * 64 && b < k->n_lut; ++b)
+		if (k->lut[b + 1] - k->lut[b] > 1)
+			qsort(k->rec + k->lut[b], k->lut[b + 1] - k->lut[b], sizeof(*k->rec), cmp_solid_rec);
+}
+
 int tagpu_write_kmc_db(tagpu_ctx *ctx, const char *working_dir)
 {
 	struct tagpu_stats st;
 	tagpu_get_stats(ctx, &st);
 	const int K = tagpu_ctx_K(ctx);
 	const uint64_t n = st.n_solid;
-	uint64_t *hi = malloc((n + 1) * 8), *lo = malloc((n + 1) * 8);
-	uint32_t *cnt = malloc((n + 1) * 4);
-	struct solid_rec *rec = malloc((n + 1) * sizeof(*rec));
-	if (!hi || !lo || !cnt || !rec || tagpu_copy_solid(ctx, hi, lo, cnt))
-		return -1;
-	for (uint64_t i = 0; i < n; ++i) {
-		rec[i].hi = hi[i]; rec[i].lo = lo[i]; rec[i].cnt = cnt[i];
-	}
-	free(hi); free(lo); free(cnt);
-	qsort(rec, n, sizeof(*rec), cmp_solid_rec);
-
 	const int p = (K % 4) + 4, suf_bases = K - p, suf_bytes = suf_bases / 4;
 	const uint64_t n_lut = (uint64_t)1 << (2 * p);
-	uint64_t *lut = calloc(n_lut + 1, 8);
+	int rc = -1, n_threads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+	if (n_threads > 32) n_threads = 32;
+	if (n_threads < 1) n_threads = 1;
+	FILE *fs = NULL, *fp = NULL;
+	uint64_t *hi = malloc((n + 1) * 8), *lo = malloc((n + 1) * 8), *lut = calloc(n_lut + 1, 8);
+	uint64_t *hist = calloc((size_t)KMC_SORT_CHUNKS * n_lut, 8);
+	uint32_t *cnt = malloc((n + 1) * 4);
+	struct solid_rec *rec = malloc((n + 1) * sizeof(*rec));
 	char path[4096];
+	if (!hi || !lo || !cnt || !rec || !lut || !hist || tagpu_copy_solid(ctx, hi, lo, cnt))
+		goto done;
+	struct kmc_sort ks = { hi, lo, cnt, n, n_lut, 2 * suf_bases, hist, lut, rec };
+	run_tasks(KMC_SORT_CHUNKS, n_threads, kmc_hist_task, &ks);
+	/* lut[b] = records before prefix b; hist[c][b] becomes the place of chunk c's first record with prefix b */
+	uint64_t acc = 0;
+	for (uint64_t b = 0; b < n_lut; ++b) {
+		lut[b] = acc;
+		for (int c = 0; c < KMC_SORT_CHUNKS; ++c) {
+			const uint64_t v = hist[(size_t)c * n_lut + b];
+			hist[(size_t)c * n_lut + b] = acc;
+			acc += v;
+		}
+	}
+	lut[n_lut] = acc;
+	run_tasks(KMC_SORT_CHUNKS, n_threads, kmc_scatter_task, &ks);
+	run_tasks((size_t)((n_lut + 63) / 64), n_threads, kmc_bucket_sort_task, &ks);
+
 	snprintf(path, sizeof(path), "%s/KMC_%d_count.kmc_suf", working_dir, K);
-	FILE *fs = fopen(path, "wb");
-	if (!fs) { perror(path); return -1; }
+	fs = fopen(path, "wb");
+	if (!fs) { perror(path); goto done; }
 	setvbuf(fs, NULL, _IOFBF, 1 << 22);
 	fwrite("KMCS", 1, 4, fs);
 	for (uint64_t i = 0; i < n; ++i) {
 		unsigned __int128 x = ((unsigned __int128)rec[i].hi << 64) | rec[i].lo;
 		uint8_t out[40];
-		++lut[(uint64_t)(x >> (2 * suf_bases)) + 1];
 		for (int j = 0; j < suf_bytes; ++j)
 			out[j] = (uint8_t)(x >> (8 * (suf_bytes - 1 - j)));
 		memcpy(out + suf_bytes, &rec[i].cnt, 4);
 		fwrite(out, 1, suf_bytes + 4, fs);
 	}
 	fwrite("KMCS", 1, 4, fs);
-	fclose(fs);
-	free(rec);
-	for (uint64_t i = 0; i < n_lut; ++i)
-		lut[i + 1] += lut[i];
+	if (ferror(fs)) goto done;
 	snprintf(path, sizeof(path), "%s/KMC_%d_count.kmc_pre", working_dir, K);
-	FILE *fp = fopen(path, "wb");
-	if (!fp) { perror(path); return -1; }
+	fp = fopen(path, "wb");
+	if (!fp) { perror(path); goto done; }
 	const uint32_t sigmap[2] = { 0, 0 };
 	struct kmc_trailer t;
 	memset(&t, 0, sizeof(t));
@@ -1165,9 +1225,12 @@ int tagpu_write_kmc_db(tagpu_ctx *ctx, const char *working_dir)
 	fwrite(&t, sizeof(t), 1, fp);
 	fwrite(&trailer_size, 4, 1, fp);
 	fwrite("KMCP", 1, 4, fp);
-	fclose(fp);
-	free(lut);
-	return 0;
+	rc = ferror(fp) ? -1 : 0;
+done:	/* one exit: nothing leaks on the early returns */
+	if (fs) fclose(fs);
+	if (fp) fclose(fp);
+	free(hi); free(lo); free(cnt); free(rec); free(lut); free(hist);
+	return rc;
 }
 
 /* ------------------------------------------------------------------ the reference's entry points */
