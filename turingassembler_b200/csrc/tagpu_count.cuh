@@ -30,7 +30,7 @@ constexpr uint32_t TAGPU_H_INVALID = 0xffffffffu;
 constexpr int TAGPU_HM_POS = TAGPU_SMEM_WORDS * 32;   // positions of the packed tile (incl. halo)
 constexpr int TAGPU_HM_LEN = TAGPU_SMEM_WORDS * 33;   // padded: index q + q/32, so word-major and position-major accesses are both conflict-free
 #define HIDX(q) ((q) + ((q) >> 5))
-constexpr int TAGPU_END_CAP = 896;                    // run ends of a tile handled per emission pass (a tile of 151 bp reads has ~590)
+constexpr int TAGPU_END_CAP = 896 * TAGPU_TILE_WORDS / 256;                    // run ends of a tile handled per emission pass (a tile of 151 bp reads has ~590)
 
 template <int W> struct SkRec;                        // super-k-mer record: bases right-aligned, length in the top byte
 template <> struct __align__(16) SkRec<1> { unsigned long long w[2]; };   // <= 60 bases
@@ -142,29 +142,31 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 	//    masked out in C1 — so no validity is tracked here.
 	const int w = K - m + 1;
 	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
+		// No rolling state: the m-mer ending at position i is a 30-bit field of the packed stream (one funnel shift of two
+		// 16-base half-words), and its reverse complement is the mirrored field of the reverse-complemented half-words.
+		// Half-words in stream order: p_lo (positions -16..-1), c_hi (0..15), c_lo (16..31); reversed: r0 = rc(c_lo),
+		// r1 = rc(c_hi), r2 = rc(p_lo), where the m-mer ending at i ends at reversed index 45 - i.
 		const uint32_t mm = (1u << (2 * m)) - 1;
-		uint32_t fw = j ? (uint32_t)pk[j - 1] & mm : 0u;
-		uint32_t rv = (uint32_t)(tagpu_rc64_full((uint64_t)fw) >> (64 - 2 * m));
 		const uint64_t cur = pk[j];
+		const uint32_t p_lo = j ? (uint32_t)pk[j - 1] : 0u, c_hi = (uint32_t)(cur >> 32), c_lo = (uint32_t)cur;
+		const uint32_t r0 = tagpu_rc32_full(c_lo), r1 = tagpu_rc32_full(c_hi), r2 = tagpu_rc32_full(p_lo);
 		const uint32_t tag0 = (uint32_t)(j & 1) * 32u;
+		auto mmer_hash = [&](int i) -> uint32_t {                  // i is a compile-time constant after unrolling
+			const uint32_t fw = (i < 16 ? __funnelshift_r(c_hi, p_lo, 30 - 2 * i) : __funnelshift_r(c_lo, c_hi, 30 - 2 * (i - 16))) & mm;
+			const int e = 45 - i;
+			const uint32_t rv = (e >= 32 ? __funnelshift_r(r2, r1, 30 - 2 * (e - 32))
+					     : e >= 16 ? __funnelshift_r(r1, r0, 30 - 2 * (e - 16)) : r0 >> (30 - 2 * e)) & mm;
+			return ((min(fw, rv) * 0x9e3779b1u) & ~63u) | (tag0 + (uint32_t)i);
+		};
 		if (w == 32) {
 			// the word IS a van Herk block: hashes stay in registers, prefix minima go to hp, suffix minima to hs
 			uint32_t h[32];
 			uint32_t acc = TAGPU_H_INVALID;
 #pragma unroll
-			for (int half = 0; half < 2; ++half) {
-				uint32_t cw = half ? (uint32_t)cur : (uint32_t)(cur >> 32);
-#pragma unroll
-				for (int ii = 0; ii < 16; ++ii) {
-					const int i = half * 16 + ii;
-					const uint32_t c = cw >> 30;
-					cw <<= 2;
-					fw = ((fw << 2) | c) & mm;
-					rv = (rv >> 2) | ((c ^ 3u) << (2 * (m - 1)));
-					h[i] = ((min(fw, rv) * 0x9e3779b1u) & ~63u) | (tag0 + (uint32_t)i);
-					acc = min(acc, h[i]);
-					hp[j * 33 + i] = acc;
-				}
+			for (int i = 0; i < 32; ++i) {
+				h[i] = mmer_hash(i);
+				acc = min(acc, h[i]);
+				hp[j * 33 + i] = acc;
 			}
 			acc = TAGPU_H_INVALID;
 #pragma unroll
@@ -174,18 +176,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 			}
 		} else {
 #pragma unroll
-			for (int half = 0; half < 2; ++half) {
-				uint32_t cw = half ? (uint32_t)cur : (uint32_t)(cur >> 32);
-#pragma unroll 8
-				for (int ii = 0; ii < 16; ++ii) {
-					const int i = half * 16 + ii;
-					const uint32_t c = cw >> 30;
-					cw <<= 2;
-					fw = ((fw << 2) | c) & mm;
-					rv = (rv >> 2) | ((c ^ 3u) << (2 * (m - 1)));
-					hp[j * 33 + i] = ((min(fw, rv) * 0x9e3779b1u) & ~63u) | (tag0 + (uint32_t)i);
-				}
-			}
+			for (int i = 0; i < 32; ++i) hp[j * 33 + i] = mmer_hash(i);
 		}
 	}
 	__syncthreads();
@@ -250,12 +241,26 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 		else if (extra > 0) smear(extra);
 		const uint32_t vmask = __brev(~c);                          // bit i = position i of this word ends a valid window
 		const uint32_t pv = ~b & 1u;                                // ... and so does the last position of the word before
-		uint32_t pm = tagpu_window_min(hs, hp, j * 32 - 1, w), ne = 0;
+		uint32_t ne = 0;
+		if (w == 32) {
+			// window ending at j * 32 + i = suffix of word j - 1 from position i + 1 on, plus prefix of word j up to i: every
+			// index is the thread's base plus a constant
+			const uint32_t *hs_prev = hs + (j - 1) * 33, *hp_cur = hp + j * 33;
+			uint32_t pm = min(hs_prev[0], hp_cur[-2]);                     // (hp_cur[-2] = hp[(j - 1) * 33 + 31])
 #pragma unroll
-		for (int i = 0; i < 32; ++i) {
-			const uint32_t cm = tagpu_window_min(hs, hp, j * 32 + i, w);
-			ne |= (cm != pm ? 1u : 0u) << i;
-			pm = cm;
+			for (int i = 0; i < 32; ++i) {
+				const uint32_t cm = min(hs_prev[i + 1 + (i == 31 ? 1 : 0)], hp_cur[i]);   // (i == 31: hs[j * 33])
+				ne |= (cm != pm ? 1u : 0u) << i;
+				pm = cm;
+			}
+		} else {
+			uint32_t pm = tagpu_window_min(hs, hp, j * 32 - 1, w);
+#pragma unroll
+			for (int i = 0; i < 32; ++i) {
+				const uint32_t cm = tagpu_window_min(hs, hp, j * 32 + i, w);
+				ne |= (cm != pm ? 1u : 0u) << i;
+				pm = cm;
+			}
 		}
 		const uint32_t bmask = vmask & (~((vmask << 1) | pv) | ne | (w > 32 ? 1u : 0u));
 		vw[j] = vmask;
@@ -420,7 +425,11 @@ template <int W> struct BucketCfg {
 	static constexpr int THREADS = TAGPU_BC_THREADS;            // two CTAs per SM: one CTA's barriers / harvest overlap the other's inserts
 	static constexpr int CTAS_PER_SM = TAGPU_BC_CTAS;
 	static constexpr int NW = W + 1;                            // 64-bit words of a staged record (bases only: <= 49 / <= 95 of them)
-	static constexpr int ROUND = 2 * THREADS;                   // records staged per round
+	// records staged per round (<= 2 * THREADS: a thread stages up to two).  A staged record is kept in BOTH orientations
+	// (see "orientation of a window" below), so the round is smaller than 2 * THREADS; a group of GROUP_TARGET windows
+	// holds ~550 records of 151 bp reads and still fits one round.
+	static constexpr bool DUAL = W == 2;                        // 64-bit keys: one rc64 per window is cheaper than a second staged copy
+	static constexpr int ROUND = DUAL ? 608 : 2 * THREADS;
 	static constexpr int ITEM_WINDOWS = 8;                      // windows of one work item: one per lane of an octet
 	static constexpr int ITEMS = ROUND * 32 / ITEM_WINDOWS;     // work items of a round (a record has <= 32 windows)
 	// shared-memory table slots per CTA (any number: the home slot is mulhi(hash, SLOTS)); sized so that two CTAs of
@@ -437,7 +446,7 @@ template <int W> struct BucketCfg {
 #endif
 	static constexpr uint32_t GROUP_TARGET = W == 1 ? SLOTS * 5 / 2 : SLOTS * TAGPU_GT2 / 4;
 	// staging area: record words, one 32-bit meta word per record, 16-bit work items; the harvest reuses it for its output
-	static constexpr size_t STAGE_BYTES = (size_t)ROUND * (NW * 8 + 4) + (size_t)ITEMS * 2 + 16;   // (+ the overflow flag)
+	static constexpr size_t STAGE_BYTES = (size_t)ROUND * ((DUAL ? 2 : 1) * NW * 8 + 4) + (size_t)ITEMS * 2 + 16;   // (+ the overflow flag)
 	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + STAGE_BYTES;
 };
 
@@ -751,8 +760,8 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 	Key<W> *t_key = reinterpret_cast<Key<W> *>(smem_raw);
 	uint32_t *t_cnt = reinterpret_cast<uint32_t *>(t_key + C::SLOTS);
 	unsigned char *stage = reinterpret_cast<unsigned char *>(t_cnt + C::SLOTS);
-	StagedRec<W> *s_rec = reinterpret_cast<StagedRec<W> *>(stage);
-	uint32_t *s_meta = reinterpret_cast<uint32_t *>(s_rec + C::ROUND);
+	StagedRec<W> *s_rec = reinterpret_cast<StagedRec<W> *>(stage);       // [0, ROUND): canonical orientation, [ROUND, 2 ROUND): its reverse complement
+	uint32_t *s_meta = reinterpret_cast<uint32_t *>(s_rec + (C::DUAL ? 2 : 1) * C::ROUND);
 	uint16_t *s_item = reinterpret_cast<uint16_t *>(s_meta + C::ROUND);
 	// "table too full" flag of the current class: in the dynamic area, whose address is one add away from a register (a
 	// static __shared__ variable costs a special-register read per access, and the insert loop polls this one)
@@ -769,6 +778,10 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	constexpr uint32_t N_WARPS = C::THREADS / 32;
 	const uint32_t n_groups = (uint32_t)ctr[CTR_GROUPS];
+	// central stretch of a K-mer that decides its orientation in the table: cb = 16 (K even) or 15 (K odd) bases, c_low bits
+	// above the K-mer's right end
+	const uint32_t c_bases = 16u - ((uint32_t)K & 1u), c_low = (uint32_t)K - c_bases, c_drop = 32u - 2u * c_bases,
+		       c_mask = 0xffffffffu >> c_drop;
 	TM_DECL();
 
 	for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) { t_key[i] = KO::make(0, 0); t_cnt[i] = 0; }
@@ -896,6 +909,7 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 						uint32_t lb = b0 + i, src = 0;
 						if (world > 1) { lb = b0 + i / world; src = i - (i / world) * world; }
 						const size_t gb = (size_t)first_bucket + lb;     // the source indexes its regions by global bucket id
+						// (requesting both records of the thread before looking at either was measured: slower, 3.43 -> 3.82 ms)
 						SkRec<W> pre = g < cap_records ? peers.regions[src][gb * cap_records + g]
 									       : peers.ext[src][ext_all[(size_t)lb * world + src] + (g - cap_records)];
 						my_n = (uint32_t)(pre.w[2 * W - 1] >> 56);
@@ -905,6 +919,12 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 #pragma unroll
 						for (int q = 0; q < W + 1; ++q) canon.w[q] = flip ? rc.w[q] : pre.w[q];
 						s_rec[idx] = canon;
+						if constexpr (C::DUAL) {
+							StagedRec<W> other;
+#pragma unroll
+							for (int q = 0; q < W + 1; ++q) other.w[q] = flip ? pre.w[q] : rc.w[q];
+							s_rec[C::ROUND + idx] = other;
+						}
 						uint32_t x = 0;
 #pragma unroll
 						for (int q = 0; q < W + 1; ++q) {
@@ -953,6 +973,8 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 				__syncthreads();                                    // staged records, meta words and items visible to everybody
 				// ---- insert: one item per octet and iteration, one window per lane
 				const uint32_t q = lane & 7u;
+				// (a shared item cursor instead of this static split was measured: slower, 3.82 -> 3.88 ms at C2 — the atomic's
+				// latency per iteration costs more than the imbalance at the barrier behind the loop)
 				for (uint32_t ibase = warp * 4u; ibase < n_items; ibase += N_WARPS * 4u) {
 					const uint32_t it = ibase + (lane >> 3);
 					if (s_overflow) break;
@@ -961,10 +983,29 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 					const uint32_t idx = item & 0x7ffu, j = (item >> 11) * (uint32_t)C::ITEM_WINDOWS + q;
 					const uint32_t meta = s_meta[idx], n_r = meta & 0xffu, mult = (meta >> 8) & 0xffu;
 					if (j >= n_r) continue;
-					const StagedRec<W> rec = s_rec[idx];
-					const Key<W> fw = tagpu_staged_window(rec, 2 * (int)(n_r - 1u - j), K);
-					const Key<W> rv = KO::rc(fw, K);
-					const Key<W> key = KO::le(fw, rv) ? fw : rv;
+					// orientation of a window: the table key is the window x or its reverse complement, whichever has the
+					// smaller CENTRAL cb bases (a symmetric stretch around the middle of the K-mer: the central bases of rc(x)
+					// are the reverse complement of those of x, so x and rc(x) agree on the choice).  That is one 32-bit
+					// reverse complement instead of a K-base one, and the chosen orientation is then cut out of the record
+					// staged in that orientation.  Central palindromes (4^-8 of the even-K windows) compare the full keys.
+					const int sh_fw = 2 * (int)(n_r - 1u - j), sh_rv = 2 * (int)j;
+					Key<W> key;
+					if constexpr (C::DUAL) {
+						const uint32_t *rw = reinterpret_cast<const uint32_t *>(s_rec + idx);
+						const uint32_t c_off = (uint32_t)sh_fw + c_low, ca = c_off >> 5;
+						const uint32_t cen = __funnelshift_r(rw[ca], rw[ca + 1], c_off) & c_mask;
+						const uint32_t cen_rc = tagpu_rc32_full(cen) >> c_drop;
+						const bool fwd = cen < cen_rc;
+						key = tagpu_staged_window(s_rec[fwd ? idx : (uint32_t)C::ROUND + idx], fwd ? sh_fw : sh_rv, K);
+						if (cen == cen_rc) {
+							const Key<W> rv = tagpu_staged_window(s_rec[idx], sh_fw, K);
+							key = KO::le(key, rv) ? key : rv;
+						}
+					} else {
+						const Key<W> fw = tagpu_staged_window(s_rec[idx], sh_fw, K);
+						const Key<W> rv = KO::rc(fw, K);
+						key = KO::le(fw, rv) ? fw : rv;
+					}
 					const uint32_t h = tagpu_table_hash<W>(key);
 					if (L && (h & ((1u << L) - 1u)) != cls) continue;
 					// probe: the hit / claim decision is the only divergent part
@@ -977,14 +1018,14 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 						const uint32_t slot1 = slot + 1 == C::SLOTS ? 0u : slot + 1;
 						const Key<W> have = t_key[slot], have1 = t_key[slot1];
 						if (KO::eq(have, stored)) break;
-						if (KO::is_zero(have) || ktab_maybe_torn<W>(have)) {
+						if (ktab_empty_or_torn<W>(have)) {
 							const Key<W> old = ktab_cas<W>(t_key + slot, stored);   // ATOMS.CAS.64 / .128
 							if (KO::is_zero(old)) { ++n_claimed; break; }
 							if (KO::eq(old, stored)) break;
 						}
 						slot = slot1;                                            // the first slot holds another key
 						if (KO::eq(have1, stored)) break;
-						if (KO::is_zero(have1) || ktab_maybe_torn<W>(have1)) {
+						if (ktab_empty_or_torn<W>(have1)) {
 							const Key<W> old = ktab_cas<W>(t_key + slot, stored);
 							if (KO::is_zero(old)) { ++n_claimed; break; }
 							if (KO::eq(old, stored)) break;
@@ -1057,7 +1098,11 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 					if (!failed && c >= ci) {
 						const Key<W> key = KO::bnot(t_key[i]);
 						if (staged) { o_key[o] = key; o_cnt[o] = c; }
-						else if (gbase + o < solid_cap) { solid[gbase + o] = key; solid_cnt[gbase + o] = c; }
+						else if (gbase + o < solid_cap) {                   // (rare: huge group) canonical form right here
+							const Key<W> krc = KO::rc(key, K);
+							solid[gbase + o] = KO::le(key, krc) ? key : krc;
+							solid_cnt[gbase + o] = c;
+						}
 						sum += c;
 						++o;
 					}
@@ -1101,7 +1146,10 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 				const unsigned long long base = s_out_base;
 				for (uint32_t i = tid; i < n_out; i += C::THREADS)
 					if (base + i < solid_cap) {                     // the host reports the overflow (n_solid > solid_cap)
-						solid[base + i] = o_key[i];
+						// the table key is the centrally-oriented representative: the solid list holds canonical (k+1)-mers,
+						// min(x, rc(x)) — converted here, on the dense copy-out of the few keys that made the cutoff
+						const Key<W> key = o_key[i], krc = KO::rc(key, K);
+						solid[base + i] = KO::le(key, krc) ? key : krc;
 						solid_cnt[base + i] = o_cnt[i];
 					}
 			}

@@ -9,22 +9,31 @@
 #pragma once
 #include "tagpu_key.cuh"
 
-constexpr int TAGPU_TILE_THREADS = 288;              // >= SMEM_WORDS: every per-word phase (halo words included) is ONE pass over the threads
-constexpr int TAGPU_TILE_WORDS = 256;               // words whose positions are window ends
+#ifndef TAGPU_TILE_WORDS_DEF
+#define TAGPU_TILE_WORDS_DEF 256
+#define TAGPU_TILE_THREADS_DEF 288
+#endif
+constexpr int TAGPU_TILE_THREADS = TAGPU_TILE_THREADS_DEF;   // >= SMEM_WORDS: every per-word phase (halo words included) is ONE pass over the threads
+constexpr int TAGPU_TILE_WORDS = TAGPU_TILE_WORDS_DEF;       // words whose positions are window ends
 constexpr int TAGPU_HALO_WORDS = 3;                 // 96 bases to the left: K <= 64 of history for a window, plus the 31 windows a super-k-mer may reach back
 constexpr int TAGPU_RHALO_WORDS = 1;                // one word to the right: whether a super-k-mer ends at the tile's last position depends on the next window
 constexpr int TAGPU_TILE_BASES = TAGPU_TILE_WORDS * 32;
 constexpr int TAGPU_SMEM_WORDS = TAGPU_TILE_WORDS + TAGPU_HALO_WORDS + TAGPU_RHALO_WORDS;
 
 // 4 ASCII bytes (byte 0 = first base) -> 8 bits of codes (first base in bits 7..6) + 4 invalid bits (first base = bit 3)
+// Validity without byte-wise compares (the SIMD video instructions are emulated on sm_100): the 2-bit code of a byte picks
+// the letter it would have to be out of "ACGT" (one PRMT); the byte is a base iff it equals that letter, case folded.
 TAGPU_DI void tagpu_pack4(uint32_t w, uint32_t &codes, uint32_t &inv)
 {
 	uint32_t c = (w >> 1) & 0x03030303u;        // A=0 C=1 G=3 T=2
 	c ^= (c >> 1) & 0x01010101u;                // A=0 C=1 G=2 T=3
 	codes = (c * 0x40100401u) >> 24;
-	uint32_t u = w & 0xdfdfdfdfu;               // fold lower case
-	uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
-	inv = (((~ok) & 0x01010101u) * 0x08040201u) >> 24 & 0xfu;
+	const uint32_t t = c | (c >> 4);            // byte 0: c0 | c1 << 4, byte 2: c2 | c3 << 4
+	const uint32_t sel = __byte_perm(t, 0u, 0x4420u);              // selector nibbles c0, c1, c2, c3
+	const uint32_t expect = __byte_perm(0x54474341u, 0u, sel);    // "ACGT"[code] per byte
+	const uint32_t diff = (w & 0xdfdfdfdfu) ^ expect;             // fold lower case; zero byte <=> valid base
+	const uint32_t nz = (((diff & 0x7f7f7f7fu) + 0x7f7f7f7fu) | diff) & 0x80808080u;   // bit 7 of every non-zero byte
+	inv = ((nz >> 7) * 0x08040201u) >> 24 & 0xfu;
 }
 
 // Packs the tile that owns window-end positions [tile_base, tile_base + TILE_BASES) into pk/inv.

@@ -101,6 +101,10 @@ template <> TAGPU_DI Key<2> ktab_cas<2>(Key<2> *p, const Key<2> &stored)
 template <int W> TAGPU_DI bool ktab_maybe_torn(const Key<W> &v);
 template <> TAGPU_DI bool ktab_maybe_torn<1>(const Key<1> &) { return false; }
 template <> TAGPU_DI bool ktab_maybe_torn<2>(const Key<2> &v) { return v.lo == 0 || v.hi == 0; }
+// is_zero(v) || ktab_maybe_torn(v) in one test
+template <int W> TAGPU_DI bool ktab_empty_or_torn(const Key<W> &v);
+template <> TAGPU_DI bool ktab_empty_or_torn<1>(const Key<1> &v) { return v.lo == 0; }
+template <> TAGPU_DI bool ktab_empty_or_torn<2>(const Key<2> &v) { return v.lo == 0 || v.hi == 0; }
 
 // insert-or-find; *claimed = true if this call created the entry
 template <int W>

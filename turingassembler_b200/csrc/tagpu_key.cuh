@@ -29,6 +29,13 @@ TAGPU_DI uint64_t tagpu_rc64_full(uint64_t x)
 	return ((x & 0xaaaaaaaaaaaaaaaaull) >> 1) | ((x & 0x5555555555555555ull) << 1);
 }
 
+// the same for the 16 digits of a 32-bit word
+TAGPU_DI uint32_t tagpu_rc32_full(uint32_t x)
+{
+	x = __brev(~x);
+	return ((x & 0xaaaaaaaau) >> 1) | ((x & 0x55555555u) << 1);
+}
+
 template <int W> struct KeyOps;
 
 template <> struct KeyOps<1> {
