@@ -63,7 +63,9 @@ template <> TAGPU_DI void tagpu_left_align<2>(const Key<2> &z, int k, uint64_t &
 }
 
 // (i) + (ii) for the k-mer z: home bucket in [b0, b0 + nbk) and no potentially foreign extension.
-// Forward and reverse-complement m-mers are both rolled (3 + 3 operations per base), two bases per iteration.
+// No rolling state: with z left-aligned in 16-base words, the m-mer ending at base 16 q + i is a 30-bit field of the word
+// pair (q - 1, q), and its reverse complement the mirrored field of the pair's reverse-complemented words (the scheme of
+// k_partition's phase A) — 8 operations per m-mer, all shift amounts compile-time constants.
 template <int W>
 TAGPU_DI bool tagpu_kmer_is_local(const Key<W> &z, int k, int log2_buckets, uint32_t b0, uint32_t nbk)
 {
@@ -71,20 +73,30 @@ TAGPU_DI bool tagpu_kmer_is_local(const Key<W> &z, int k, int log2_buckets, uint
 	const uint32_t mm = (1u << (2 * m)) - 1u;
 	uint64_t hi, lo;
 	tagpu_left_align<W>(z, k, hi, lo);
-	uint32_t mu = 0xffffffffu, fw = 0, rv = 0, head = 0;
-	for (int i = 0; i < k; ++i) {
-		const uint32_t c = (uint32_t)(hi >> 62);
-		hi = (hi << 2) | (lo >> 62);
-		lo <<= 2;
-		fw = ((fw << 2) | c) & mm;
-		rv = (rv >> 2) | ((3u - c) << (2 * (m - 1)));
-		if (i == m - 2) head = fw;                                  // first m - 1 bases
-		if (i >= m - 1) mu = min(mu, (min(fw, rv) * 0x9e3779b1u) >> 6);
+	uint32_t Z[2 * W], R[2 * W];
+	Z[0] = (uint32_t)(hi >> 32); Z[1] = (uint32_t)hi;
+	if constexpr (W == 2) { Z[2] = (uint32_t)(lo >> 32); Z[3] = (uint32_t)lo; }
+#pragma unroll
+	for (int q = 0; q < 2 * W; ++q) R[q] = tagpu_rc32_full(Z[q]);
+	uint32_t mu = 0xffffffffu;
+#pragma unroll
+	for (int q = 0; q < 2 * W; ++q) {
+		if (16 * q >= k) break;
+		const uint32_t zq = Z[q], zp = q ? Z[q - 1] : 0u, rq = R[q], rp = q ? R[q - 1] : 0u;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) {
+			const int e = 16 * q + i;                                   // last base of the m-mer
+			if (e < m - 1) continue;
+			const uint32_t fw = __funnelshift_r(zq, zp, 30 - 2 * i) & mm;
+			const uint32_t rv = (4 + 2 * i < 32 ? __funnelshift_r(rp, rq, 4 + 2 * i) : rq >> (4 + 2 * i - 32)) & mm;
+			const uint32_t h = (min(fw, rv) * 0x9e3779b1u) >> 6;
+			mu = e < k ? min(mu, h) : mu;
+		}
 	}
 	const uint32_t b = tagpu_bucket_of(mu, log2_buckets);
 	if (b < b0 || b >= b0 + nbk) return false;
 	// right extensions: last m-1 bases of z + c; left extensions: c + first m-1 bases of z
-	const uint32_t tail = fw & (mm >> 2);
+	const uint32_t tail = (uint32_t)z.lo & (mm >> 2), head = Z[0] >> (32 - 2 * (m - 1));
 	for (uint32_t c = 0; c < 4; ++c) {
 		if (tagpu_mmer_hash26((tail << 2) | c) < mu) return false;
 		if (tagpu_mmer_hash26((c << (2 * (m - 1))) | head) < mu) return false;
@@ -107,7 +119,7 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 	   unsigned long long *ctr)
 {
 	typedef KeyOps<W> KO;
-	constexpr int TS_MAX = 4 * MAXN, R = MAXN / T;
+	constexpr int TS_MAX = 4 * MAXN;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Key<W> *e_key = reinterpret_cast<Key<W> *>(smem_raw);               // [MAXN]
 	Key<W> *t_key = e_key + MAXN;                                       // [TS_MAX] canonical k-mers, ~key (0 = empty)
@@ -115,7 +127,7 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 	uint32_t *t_mask = e_cnt + MAXN;                                    // [TS_MAX] local edge mask (low 8 bits), bit 8 = hidden
 	uint16_t *t_out = reinterpret_cast<uint16_t *>(t_mask + TS_MAX);    // [TS_MAX][2] an oriented entry leaving (k-mer, orient)
 	uint16_t *nxt = t_out + 2 * TS_MAX;                                 // [2 MAXN] next oriented entry on the path / END
-	__shared__ uint32_t s_block, s_words, s_paths, s_hidden, s_cand;
+	__shared__ uint32_t s_block, s_words, s_paths, s_hidden, s_cand, s_cand2;
 	__shared__ unsigned long long s_pbase, s_wbase;
 	const uint32_t tid = threadIdx.x;
 	const int K = k + 1;
@@ -135,7 +147,7 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 		if (tid == 0) {
 			s_block = next_block;
 			if (next_block < n_blocks) next_block = (uint32_t)atomicAdd(ctr + CTR_SPARE1, 1ull);
-			s_words = 0; s_paths = 0; s_hidden = 0; s_cand = 0;
+			s_words = 0; s_paths = 0; s_hidden = 0; s_cand = 0; s_cand2 = 0;
 		}
 		__syncthreads();
 		if (s_block >= n_blocks) break;
@@ -231,33 +243,32 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 		}
 		__syncthreads();
 		TC(3);
-		// ---- every entry: does one of its orientations head a path that this orientation emits?  (a path is emitted by
-		// its smaller end: head <= reverse complement of its last entry; an entry emits at most one path)
-		uint32_t r_len[R], r_oe[R], r_last[R], r_pi[R], r_wo[R];
-#pragma unroll
-		for (int r = 0; r < R; ++r) {
-			const uint32_t i = tid + (uint32_t)r * T;
-			r_len[r] = 0;
-			if (i >= n) continue;
-			for (uint32_t o = 0; o < 2 && !r_len[r]; ++o) {
-				const uint32_t oe = 2u * i + o;
-				if (nxt[oe ^ 1u] != TAGPU_OE_END) continue;              // not a head: the k-mer before it is hidden
-				uint32_t len = 0, last = oe, cur = oe;
-				for (;;) {
-					++len;
-					last = cur;
-					const uint32_t nx = nxt[cur];
-					if (nx == TAGPU_OE_END) break;
-					if (len > 2u * n) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT); break; }
-					cur = nx;
-				}
-				if (oe > (last ^ 1u)) continue;                           // the twin path emits
-				if (oe == (last ^ 1u) && o == 1) continue;                // (self-twin single entry: emitted once, as o = 0)
-				const uint32_t words = len > 1 ? (len - 1 + 15) >> 4 : 0u;
-				r_len[r] = len; r_oe[r] = oe; r_last[r] = last;
-				r_wo[r] = words ? atomicAdd(&s_words, words) : 0u;
-				r_pi[r] = atomicAdd(&s_paths, 1u);
+		// ---- heads.  One oriented entry in eight heads a path; they are compacted first (the table arrays are dead after the
+		// link phase: t_out holds the list of heads, t_key the records of the paths to emit), so that the serial walks run on
+		// dense lanes.  A path is emitted by its smaller end: head <= reverse complement of its last entry.
+		uint16_t *h_list = t_out;                                       // [<= 2 n] oriented entries that head a path
+		uint4 *p_list = reinterpret_cast<uint4 *>(t_key);                // [<= n] { oe | last << 16, len, path index, word offset }
+		for (uint32_t oe = tid; oe < 2u * n; oe += T)
+			if (nxt[oe ^ 1u] == TAGPU_OE_END) h_list[atomicAdd(&s_cand2, 1u)] = (uint16_t)oe;   // (else: the k-mer before it is hidden)
+		__syncthreads();
+		for (uint32_t hI = tid; hI < s_cand2; hI += T) {
+			const uint32_t oe = h_list[hI];
+			uint32_t len = 0, last = oe, cur = oe;
+			for (;;) {
+				++len;
+				last = cur;
+				const uint32_t nx = nxt[cur];
+				if (nx == TAGPU_OE_END) break;
+				if (len > 2u * n) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_CONTRACT); break; }
+				cur = nx;
 			}
+			if (oe > (last ^ 1u)) continue;                               // the twin path emits
+			// (a single entry is a head in both orientations and is emitted once, as orientation 0; a path that is its own
+			// twin, oe == last ^ 1, has one head only and is emitted by it)
+			const uint32_t words = len > 1 ? (len - 1 + 15) >> 4 : 0u;
+			const uint32_t wo = words ? atomicAdd(&s_words, words) : 0u;
+			const uint32_t pi = atomicAdd(&s_paths, 1u);
+			p_list[pi] = make_uint4(oe | (last << 16), len, pi, wo);
 		}
 		__syncthreads();
 		if (tid == 0) {
@@ -267,12 +278,10 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 		}
 		__syncthreads();
 		const unsigned long long pbase = s_pbase, wbase = s_wbase;
-#pragma unroll
-		for (int r = 0; r < R; ++r) {
-			const uint32_t len = r_len[r];
-			if (!len) continue;
-			const uint32_t oe = r_oe[r], last = r_last[r];
-			const unsigned long long pi = pbase + r_pi[r], wo = wbase + r_wo[r];
+		for (uint32_t pI = tid; pI < s_paths; pI += T) {
+			const uint4 rec = p_list[pI];
+			const uint32_t oe = rec.x & 0xffffu, last = rec.x >> 16, len = rec.y;
+			const unsigned long long pi = pbase + rec.z, wo = wbase + rec.w;
 			const Key<W> xf = (oe & 1u) ? KO::rc(e_key[oe >> 1], K) : e_key[oe >> 1];
 			const Key<W> xl = (last & 1u) ? KO::rc(e_key[last >> 1], K) : e_key[last >> 1];
 			ps.first[pi] = xf; ps.last[pi] = xl; ps.off[pi] = wo; ps.n[pi] = len;
@@ -329,6 +338,59 @@ TAGPU_DI uint32_t tagpu_path_base(const PathStore<W> &ps, unsigned long long p, 
 	if (i <= (uint32_t)k) return KeyOps<W>::base_at(xf, k + 1, (int)i);
 	const uint32_t j = i - (uint32_t)k - 1u;
 	return (ps.interior[ps.off[p] + (j >> 4)] >> ((j & 15u) << 1)) & 3u;
+}
+
+// The k + n bases of a path as a little-endian 2-bit stream (base i at bits 2 i, 2 i + 1 — the layout of the edge sequences,
+// /root/reference/src/assembly_graph.h:182-187), 32 bits at a time: the k + 1 bases of the first (k+1)-mer with their order
+// reversed (= rc(x) with the complement undone), followed by the interior words shifted by 2 (k + 1) bits.  The emission
+// kernels cut whole output words out of it with funnel shifts instead of fetching the bases one by one.
+template <int W> struct PathBits {
+	uint32_t s[2 * W + 1];           // the first (k+1)-mer, base 0 in the lowest bits (one zero word behind it)
+	const uint32_t *interior;        // interior words of the path
+	int n_int;                       // how many
+	int a, b;                        // 2 (k + 1) = 32 a + b
+
+	TAGPU_DI PathBits(const PathStore<W> &ps, unsigned long long p, const Key<W> &xf, int k, uint32_t n)
+	{
+		typedef KeyOps<W> KO;
+		const Key<W> r = KO::rc(xf, k + 1), m = KO::mask(k + 1);
+		s[0] = (uint32_t)(r.lo ^ m.lo); s[1] = (uint32_t)((r.lo ^ m.lo) >> 32);
+		if constexpr (W == 2) { s[2] = (uint32_t)(r.hi ^ m.hi); s[3] = (uint32_t)((r.hi ^ m.hi) >> 32); }
+		s[2 * W] = 0;
+		interior = ps.interior + ps.off[p];
+		n_int = n > 1u ? (int)((n - 1u + 15u) >> 4) : 0;
+		a = (2 * (k + 1)) >> 5; b = (2 * (k + 1)) & 31;
+	}
+	TAGPU_DI uint32_t int_word(int j) const { return j >= 0 && j < n_int ? interior[j] : 0u; }
+	TAGPU_DI uint32_t key_word(int q) const
+	{
+		uint32_t v = 0;
+#pragma unroll
+		for (int i = 0; i <= 2 * W; ++i) v = q == i ? s[i] : v;
+		return v;
+	}
+	// word q of the stream (0 outside of it)
+	TAGPU_DI uint32_t word(int q) const
+	{
+		if (q < a) return q < 0 ? 0u : key_word(q);
+		const int j = q - a;
+		return (j == 0 ? key_word(a) : 0u) | __funnelshift_l(int_word(j - 1), int_word(j), b);
+	}
+	// the 32 bits that start at bit `lo` of the stream (any alignment, may start before the stream or end behind it)
+	TAGPU_DI uint32_t bits(int lo) const
+	{
+		const int q = lo >> 5;                                   // (arithmetic shift: floor)
+		return __funnelshift_r(word(q), word(q + 1), lo & 31);
+	}
+};
+
+// 32-bit mask of the output bases [lo, hi) of the word that holds bases 16 w .. 16 w + 15
+TAGPU_DI uint32_t tagpu_base_mask(int w, int lo, int hi)
+{
+	const int first = max(lo - 16 * w, 0), end = min(hi - 16 * w, 16);
+	if (end <= first) return 0u;
+	const uint32_t upto = end >= 16 ? 0xffffffffu : (1u << (2 * end)) - 1u;
+	return upto & ~((1u << (2 * first)) - 1u);                   // (first < 16 here)
 }
 
 // ---------------------------------------------------------------- B': end k-mers of the paths into the HBM table
@@ -455,16 +517,14 @@ __global__ void __launch_bounds__(TAGPU_HEADS_THREADS) k_heads_paths(PathStore<W
 		const unsigned long long p2 = s_item[it] >> 1, off2 = s_off[it];
 		const uint32_t dir2 = (uint32_t)s_item[it] & 1u, n = ps.n[p2];
 		const Key<W> xf2 = ps.first[p2];
-		// first k bases: the node k-mer as the edge sees it; then the n bases of this path
-		uint32_t word = 0;
-		for (uint32_t i = 0; i < (uint32_t)k + n; ++i) {
-			// forward: path bases 0 .. k+n-1; backward: complement of path bases k+n-1 .. 0
-			const uint32_t base = dir2 ? 3u - tagpu_path_base<W>(ps, p2, xf2, k, (uint32_t)k + n - 1u - i) : tagpu_path_base<W>(ps, p2, xf2, k, i);
-			word |= base << ((i & 15u) << 1);
-			if ((i & 15u) == 15u || i + 1 == (uint32_t)k + n) {
-				atomicOr(g.e_seq + off2 + (i >> 4), word);
-				word = 0;
-			}
+		// first k bases: the node k-mer as the edge sees it; then the n bases of this path.  Forward: stream words as they
+		// are; backward: the reverse complement of the stream, i.e. output word w = rc of the 16 bases that end at base L - 16 w
+		const PathBits<W> pb(ps, p2, xf2, k, n);
+		const int L = k + (int)n, n_words = (L + 15) >> 4;
+		for (int w = 0; w < n_words; ++w) {
+			uint32_t word = dir2 ? tagpu_rc32_full(pb.bits(2 * (L - 16 * w - 16))) : pb.word(w);
+			word &= tagpu_base_mask(w, 0, L);
+			if (word) atomicOr(g.e_seq + off2 + w, word);
 		}
 	}
 }
@@ -492,9 +552,14 @@ __global__ void __launch_bounds__(256) k_interior_paths(PathStore<W> ps, uint64_
 	const uint32_t pos = (uint32_t)k + wlast[tr] + (uint32_t)(jt >> 32), n = ps.n[p];
 	const Key<W> xf = ps.first[p];
 	const unsigned long long off = g.e_off[e];
-	for (uint32_t i = 0; i < n; ++i) {
-		const uint32_t base = dir ? 3u - tagpu_path_base<W>(ps, p, xf, k, n - 1u - i) : tagpu_path_base<W>(ps, p, xf, k, (uint32_t)k + i);
-		atomicOr(g.e_seq + off + ((pos + i) >> 4), base << (((pos + i) & 15u) << 1));
+	// output bases [pos, pos + n) of the edge: forward = stream bases k .. k + n - 1, backward = complement of bases n - 1 .. 0
+	const PathBits<W> pb(ps, p, xf, k, n);
+	const int lo = (int)pos, hi = (int)(pos + n);
+	for (int w = lo >> 4; w <= (hi - 1) >> 4; ++w) {
+		// output base o = 16 w + i: forward <- stream base k + o - pos; backward <- complement of stream base n - 1 - (o - pos)
+		uint32_t word = dir ? tagpu_rc32_full(pb.bits(2 * ((int)n - 16 - 16 * w + lo))) : pb.bits(2 * (k + 16 * w - lo));
+		word &= tagpu_base_mask(w, lo, hi);
+		if (word) atomicOr(g.e_seq + off + w, word);
 	}
 	if (cv != (tr ^ 1u)) vedge[cv] = e;
 }

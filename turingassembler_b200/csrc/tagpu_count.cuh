@@ -27,10 +27,7 @@
 
 constexpr int TAGPU_MINIMIZER_M = 15;                 // m-mer length (30 bits): long enough that one m-mer value ~ one genomic site
 constexpr uint32_t TAGPU_H_INVALID = 0xffffffffu;
-constexpr int TAGPU_HM_POS = TAGPU_SMEM_WORDS * 32;   // positions of the packed tile (incl. halo)
-constexpr int TAGPU_HM_LEN = TAGPU_SMEM_WORDS * 33;   // padded: index q + q/32, so word-major and position-major accesses are both conflict-free
 #define HIDX(q) ((q) + ((q) >> 5))
-constexpr int TAGPU_END_CAP = 896 * TAGPU_TILE_WORDS / 256;                    // run ends of a tile handled per emission pass (a tile of 151 bp reads has ~590)
 
 template <int W> struct SkRec;                        // super-k-mer record: bases right-aligned, length in the top byte
 template <> struct __align__(16) SkRec<1> { unsigned long long w[2]; };   // <= 60 bases
@@ -117,23 +114,24 @@ TAGPU_DI uint32_t tagpu_window_min(const uint32_t *hs, const uint32_t *hp, int q
 // collapses before counting (tagpu_count.cuh: "duplicate records").  A run is emitted by the tile that contains its END;
 // the 96-base left halo lets it reach back to its start, the right halo word tells whether the run ends at the tile's
 // last position.
-template <int W>
-__global__ void __launch_bounds__(TAGPU_TILE_THREADS)
+template <int W, int TW>
+__global__ void __launch_bounds__(TileCfg<TW>::THREADS)
 k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg cfg, SkRec<W> *__restrict__ regions,
 	    unsigned long long *__restrict__ cursor, SkRec<W> *__restrict__ overflow, uint32_t *__restrict__ overflow_bucket,
 	    unsigned long long *ctr)
 {
+	typedef TileCfg<TW> T;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	uint64_t *pk = reinterpret_cast<uint64_t *>(smem_raw);
-	uint32_t *inv = reinterpret_cast<uint32_t *>(pk + TAGPU_SMEM_WORDS);
-	uint32_t *vw = inv + TAGPU_SMEM_WORDS;              // per word: bit i = position i ends a valid window
-	uint32_t *bw = vw + TAGPU_SMEM_WORDS;               // per word: bit i = position i starts a run
-	uint32_t *hp = bw + TAGPU_SMEM_WORDS;               // m-mer (hash, position) per position, then block-wise prefix minima (in place)
-	uint32_t *hs = hp + TAGPU_HM_LEN;                   // block-wise suffix minima
+	uint32_t *inv = reinterpret_cast<uint32_t *>(pk + T::SMEM_WORDS);
+	uint32_t *vw = inv + T::SMEM_WORDS;              // per word: bit i = position i ends a valid window
+	uint32_t *bw = vw + T::SMEM_WORDS;               // per word: bit i = position i starts a run
+	uint32_t *hp = bw + T::SMEM_WORDS;               // m-mer (hash, position) per position, then block-wise prefix minima (in place)
+	uint32_t *hs = hp + T::HM_LEN;                   // block-wise suffix minima
 	const int K = cfg.K, m = TAGPU_MINIMIZER_M;
 
-	if (cfg.packed) tagpu_load_tile_packed(seq, n, ((uint64_t)blockIdx.x + tile0) * TAGPU_TILE_BASES, pk, inv);
-	else tagpu_load_tile(seq, n, ((uint64_t)blockIdx.x + tile0) * TAGPU_TILE_BASES, pk, inv);
+	if (cfg.packed) tagpu_load_tile_packed<TW>(seq, n, ((uint64_t)blockIdx.x + tile0) * T::BASES, pk, inv);
+	else tagpu_load_tile<TW>(seq, n, ((uint64_t)blockIdx.x + tile0) * T::BASES, pk, inv);
 	__syncthreads();
 
 	// A. hash of the canonical m-mer ending at every position, with the position (mod 64) in the low bits: the minimum
@@ -141,7 +139,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 	//    other: it can only be the minimum of a window that contains that byte, i.e. of an invalid window, and those are
 	//    masked out in C1 — so no validity is tracked here.
 	const int w = K - m + 1;
-	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
+	for (int j = threadIdx.x; j < T::SMEM_WORDS; j += blockDim.x) {
 		// No rolling state: the m-mer ending at position i is a 30-bit field of the packed stream (one funnel shift of two
 		// 16-base half-words), and its reverse complement is the mirrored field of the reverse-complemented half-words.
 		// Half-words in stream order: p_lo (positions -16..-1), c_hi (0..15), c_lo (16..31); reversed: r0 = rc(c_lo),
@@ -186,9 +184,9 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 	//    forwards with a running prefix minimum and replaces hs[q - w + 1] by the minimum of window q — so afterwards
 	//    hs[q - w + 1] IS the minimizer of the window ending at q.  Everything a thread writes (the hs region of block
 	//    b - 1) is read only by itself, so the two passes need no barrier between them; hp stays read-only.
-	const int n_blocks = w == 32 ? 0 : (TAGPU_HM_POS + w - 1) / w;     // (w == 32: done in phase A)
+	const int n_blocks = w == 32 ? 0 : (T::HM_POS + w - 1) / w;     // (w == 32: done in phase A)
 	for (int blk = threadIdx.x; blk < n_blocks; blk += blockDim.x) {
-		const int lo = blk * w, hi = min(lo + w, TAGPU_HM_POS);
+		const int lo = blk * w, hi = min(lo + w, T::HM_POS);
 		// (both passes are unrolled by four with the loads issued first: the chain through `acc` is only the min)
 		uint32_t acc = TAGPU_H_INVALID;
 		int q = lo - 1;
@@ -226,9 +224,8 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 	//     is invalid or has another minimizer occurrence.  With w > 32 a run could outgrow a record, so word starts cut too.
 	//     The valid mask is bit-parallel: a window is valid iff no invalid base lies in the K positions it covers, i.e.
 	//     the invalid masks of this word and the two before it, OR-smeared over K positions (log steps).
-	static_assert(TAGPU_TILE_THREADS >= TAGPU_SMEM_WORDS, "per-word phases assume one word per thread");
 	uint32_t n_win = 0;
-	for (int j = threadIdx.x + 1; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
+	for (int j = threadIdx.x + 1; j < T::SMEM_WORDS; j += blockDim.x) {
 		uint32_t a = j >= 2 ? inv[j - 2] : 0xffffffffu, b = inv[j - 1], c = inv[j];     // position order a:b:c, first position = MSB
 		auto smear = [&](int sft) {                                  // x |= x >> sft over the 96-bit sequence, 0 < sft < 32
 			const uint32_t nc = __funnelshift_r(c, b, sft), nb_ = __funnelshift_r(b, a, sft), na = a >> sft;
@@ -265,18 +262,18 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 		const uint32_t bmask = vmask & (~((vmask << 1) | pv) | ne | (w > 32 ? 1u : 0u));
 		vw[j] = vmask;
 		bw[j] = bmask;
-		if (j >= TAGPU_HALO_WORDS && j < TAGPU_HALO_WORDS + TAGPU_TILE_WORDS) n_win += __popc(vmask);
+		if (j >= TAGPU_HALO_WORDS && j < TAGPU_HALO_WORDS + T::WORDS) n_win += __popc(vmask);
 	}
 	__syncthreads();
 
 	// C2. the runs that END in the tile are laid out as one dense list (block-wide prefix sum over the per-word end masks),
 	//     and then every thread builds and appends one record per iteration — whatever the distribution of run ends over
 	//     the words: one record (2-bit bases + window count) goes to the bucket of the run's minimizer.
-	__shared__ uint16_t s_end[TAGPU_END_CAP];
-	__shared__ uint32_t s_wsum[TAGPU_TILE_THREADS / 32 + 1];
+	__shared__ uint16_t s_end[T::END_CAP];
+	__shared__ uint32_t s_wsum[T::THREADS / 32 + 1];
 	const int wi0 = threadIdx.x + TAGPU_HALO_WORDS;
 	uint32_t ends = 0;
-	if (threadIdx.x < TAGPU_TILE_WORDS) {
+	if (threadIdx.x < T::WORDS) {
 		const uint32_t V = vw[wi0], B = bw[wi0];
 		const uint32_t Vn = (V >> 1) | (vw[wi0 + 1] << 31), Bn = (B >> 1) | (bw[wi0 + 1] << 31);
 		ends = V & (~Vn | Bn);
@@ -292,23 +289,23 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 	__syncthreads();
 	uint32_t before = 0, n_ends = 0;
 #pragma unroll
-	for (int x = 0; x < TAGPU_TILE_THREADS / 32; ++x) {
+	for (int x = 0; x < T::THREADS / 32; ++x) {
 		const uint32_t v = s_wsum[x];
 		before += (uint32_t)x < warp_ ? v : 0u;
 		n_ends += v;
 	}
 	const uint32_t my_first = before + incl - n_mine;
-	for (uint32_t pass0 = 0; pass0 < n_ends; pass0 += TAGPU_END_CAP) {          // (one pass unless the tile is pathological)
+	for (uint32_t pass0 = 0; pass0 < n_ends; pass0 += T::END_CAP) {          // (one pass unless the tile is pathological)
 		if (pass0) __syncthreads();
 		uint32_t rank = my_first, rest = ends;
 		while (rest) {
 			const int e = __ffs(rest) - 1;
 			rest &= rest - 1;
-			if (rank >= pass0 && rank < pass0 + TAGPU_END_CAP) s_end[rank - pass0] = (uint16_t)(wi0 * 32 + e);
+			if (rank >= pass0 && rank < pass0 + T::END_CAP) s_end[rank - pass0] = (uint16_t)(wi0 * 32 + e);
 			++rank;
 		}
 		__syncthreads();
-		const uint32_t n_pass = min(n_ends - pass0, (uint32_t)TAGPU_END_CAP);
+		const uint32_t n_pass = min(n_ends - pass0, (uint32_t)T::END_CAP);
 		for (uint32_t r = threadIdx.x; r < n_pass; r += blockDim.x) {
 			const int end_q = s_end[r], wi = end_q >> 5, e = end_q & 31;
 			const uint32_t upto = bw[wi] & (0xffffffffu >> (31 - e));
@@ -429,7 +426,10 @@ template <int W> struct BucketCfg {
 	// (see "orientation of a window" below), so the round is smaller than 2 * THREADS; a group of GROUP_TARGET windows
 	// holds ~550 records of 151 bp reads and still fits one round.
 	static constexpr bool DUAL = W == 2;                        // 64-bit keys: one rc64 per window is cheaper than a second staged copy
-	static constexpr int ROUND = DUAL ? 608 : 2 * THREADS;
+#ifndef TAGPU_BC_ROUND2
+#define TAGPU_BC_ROUND2 608
+#endif
+	static constexpr int ROUND = DUAL ? TAGPU_BC_ROUND2 : 2 * THREADS;
 	static constexpr int ITEM_WINDOWS = 8;                      // windows of one work item: one per lane of an octet
 	static constexpr int ITEMS = ROUND * 32 / ITEM_WINDOWS;     // work items of a round (a record has <= 32 windows)
 	// shared-memory table slots per CTA (any number: the home slot is mulhi(hash, SLOTS)); sized so that two CTAs of

@@ -9,16 +9,25 @@
 #pragma once
 #include "tagpu_key.cuh"
 
-#ifndef TAGPU_TILE_WORDS_DEF
-#define TAGPU_TILE_WORDS_DEF 256
-#define TAGPU_TILE_THREADS_DEF 288
-#endif
-constexpr int TAGPU_TILE_THREADS = TAGPU_TILE_THREADS_DEF;   // >= SMEM_WORDS: every per-word phase (halo words included) is ONE pass over the threads
-constexpr int TAGPU_TILE_WORDS = TAGPU_TILE_WORDS_DEF;       // words whose positions are window ends
+// Tile geometry of pass 1, by the number of 32-base words whose positions are window ends.  256 words (8192 bases, 288
+// threads, 74 KB of shared memory: 3 CTAs per SM) is the general tile; 128 words (160 threads, 38 KB: 5-6 CTAs per SM) hides
+// the tile load and the barriers better and is used where the per-word work is lightest (w = 32, the default k0 = 45:
+// 1.40 -> 1.29 ms at C2; the general-w path loses with it, 2.05 -> 2.14 ms at C1).
 constexpr int TAGPU_HALO_WORDS = 3;                 // 96 bases to the left: K <= 64 of history for a window, plus the 31 windows a super-k-mer may reach back
 constexpr int TAGPU_RHALO_WORDS = 1;                // one word to the right: whether a super-k-mer ends at the tile's last position depends on the next window
+template <int TW> struct TileCfg {
+	static constexpr int WORDS = TW;
+	static constexpr int THREADS = TW == 256 ? 288 : 160;      // >= SMEM_WORDS: every per-word phase (halo words included) is ONE pass over the threads
+	static constexpr int BASES = TW * 32;
+	static constexpr int SMEM_WORDS = TW + TAGPU_HALO_WORDS + TAGPU_RHALO_WORDS;
+	static constexpr int HM_POS = SMEM_WORDS * 32;             // positions of the packed tile (incl. halo)
+	static constexpr int HM_LEN = SMEM_WORDS * 33;             // padded: index q + q/32, so word-major and position-major accesses are both conflict-free
+	static constexpr int END_CAP = 896 * TW / 256;             // run ends of a tile handled per emission pass (a 256-word tile of 151 bp reads has ~590)
+	static constexpr size_t SMEM = (size_t)SMEM_WORDS * 8 + 3 * (size_t)SMEM_WORDS * 4 + 2 * (size_t)HM_LEN * 4;
+	static_assert(THREADS >= SMEM_WORDS, "per-word phases assume one word per thread");
+};
+constexpr int TAGPU_TILE_WORDS = 256;               // the general tile, and the tile of the PACKED stream layout (include/tagpu.h)
 constexpr int TAGPU_TILE_BASES = TAGPU_TILE_WORDS * 32;
-constexpr int TAGPU_SMEM_WORDS = TAGPU_TILE_WORDS + TAGPU_HALO_WORDS + TAGPU_RHALO_WORDS;
 
 // 4 ASCII bytes (byte 0 = first base) -> 8 bits of codes (first base in bits 7..6) + 4 invalid bits (first base = bit 3)
 // Validity without byte-wise compares (the SIMD video instructions are emulated on sm_100): the 2-bit code of a byte picks
@@ -38,10 +47,11 @@ TAGPU_DI void tagpu_pack4(uint32_t w, uint32_t &codes, uint32_t &inv)
 
 // Packs the tile that owns window-end positions [tile_base, tile_base + TILE_BASES) into pk/inv.
 // smem word j covers stream positions tile_base - 32 HALO_WORDS + 32 j .. +31.
+template <int TW>
 TAGPU_DI void tagpu_load_tile(const uint8_t *__restrict__ seq, uint64_t n, uint64_t tile_base,
 			       uint64_t *pk, uint32_t *inv)
 {
-	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
+	for (int j = threadIdx.x; j < TileCfg<TW>::SMEM_WORDS; j += blockDim.x) {
 		long long g0 = (long long)tile_base - 32 * TAGPU_HALO_WORDS + 32ll * j;
 		uint64_t word = 0;
 		uint32_t bad = 0;
@@ -80,10 +90,11 @@ TAGPU_DI void tagpu_load_tile(const uint8_t *__restrict__ seq, uint64_t n, uint6
 // TAGPU_TILE_WORDS 64-bit code words followed by TAGPU_TILE_WORDS 32-bit invalid masks = 3072 bytes per 8192 positions
 // (0.375 bytes per base instead of 1: that is what crosses PCIe) — so loading a tile is a plain copy.
 constexpr int TAGPU_PACKED_TILE_BYTES = TAGPU_TILE_WORDS * 12;
+template <int TW>
 TAGPU_DI void tagpu_load_tile_packed(const uint8_t *__restrict__ packed, uint64_t n, uint64_t tile_base, uint64_t *pk, uint32_t *inv)
 {
-	const uint64_t n_words = ((n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES) * TAGPU_TILE_WORDS;   // whole tiles
-	for (int j = threadIdx.x; j < TAGPU_SMEM_WORDS; j += blockDim.x) {
+	const uint64_t n_words = ((n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES) * TAGPU_TILE_WORDS;   // whole tiles of the packed layout
+	for (int j = threadIdx.x; j < TileCfg<TW>::SMEM_WORDS; j += blockDim.x) {
 		const long long w = (long long)(tile_base / 32) - TAGPU_HALO_WORDS + j;              // stream word of smem word j
 		uint64_t word = 0;
 		uint32_t bad = 0xffffffffu;

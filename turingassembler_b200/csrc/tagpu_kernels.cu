@@ -51,6 +51,7 @@ struct tagpu_ctx {
 	int n_sm = 0, jump_grid = 0;
 	// per-device launch state (a process may hold contexts on several devices)
 	bool attr_done[3] = { false, false, false };
+	bool attr_done_part[4] = { false, false, false, false };   // k_partition<W, TW>: [(W - 1) * 2 + (TW == 128)]
 	int grid_s[3] = { 0, 0, 0 }, grid_m[3] = { 0, 0, 0 }, grid_l[3] = { 0, 0, 0 };
 	uint64_t budget_n = 0;
 	size_t budget = 0;                 // count_budget(): memory the count stage planned with for a stream of budget_n bytes
@@ -266,9 +267,10 @@ static int read_counters(tagpu_ctx *ctx, unsigned long long allow = 0)
 	} while (0)
 
 // ------------------------------------------------------------------------------------------------ count stage (partitioned)
-#define LAUNCH_SMEM(kernel, grid, block, smem, ...)                                        \
+#define LAUNCH_SMEM(kernel, grid, block, smem, ...) LAUNCH_SMEM_NAMED(#kernel, kernel, grid, block, smem, __VA_ARGS__)
+#define LAUNCH_SMEM_NAMED(name, kernel, grid, block, smem, ...)                            \
 	do {                                                                               \
-		ProfScope ps_(ctx, #kernel);                                               \
+		ProfScope ps_(ctx, name);                                                  \
 		kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);             \
 		++ctx->launches;                                                           \
 		CU(cudaGetLastError());                                                    \
@@ -328,50 +330,44 @@ static size_t count_budget(tagpu_ctx *ctx, uint64_t n)
 	return ctx->budget;
 }
 
-// Pass 1 over this rank's reads + the bucket sort of the records that overflowed their region.  Purely local.
-template <int W>
-static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, const PartCfg &cfg_in)
+// One pass-1 sweep over the stream with tiles of TW words (TileCfg).  Reads that are still in host memory (ctx->h_src; d_seq
+// is our staging buffer then) are uploaded in chunks on a second stream and partitioned chunk by chunk, so that the PCIe
+// copy hides the pass.  Chunks are counted in 256-word tiles, the unit of the packed stream layout; a launch covers the
+// kernel tiles whose right halo word is already on the device: with an ASCII stream the copy runs 32 bytes ahead, with a
+// packed stream (whole 3072-byte tiles) the last 256-word tile of a chunk waits for the next chunk.
+template <int W, int TW>
+static int partition_sweep(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, const PartCfg &cfg)
 {
-	typedef BucketCfg<W> BC;
-	PartCfg cfg = cfg_in;
-	cfg.packed = ctx->src_packed ? 1u : 0u;
-	const uint32_t n_buckets = 1u << cfg.log2_buckets;
-	const size_t smem1 = TAGPU_SMEM_WORDS * 8 + 3 * (size_t)TAGPU_SMEM_WORDS * 4 + 2 * (size_t)TAGPU_HM_LEN * 4;
-	bool *attr_done = ctx->attr_done;
-	if (!attr_done[W]) {
-		CU(cudaFuncSetAttribute(k_partition<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-		CU(cudaFuncSetAttribute(k_count_buckets<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BC::SMEM));
-		attr_done[W] = true;
+	typedef TileCfg<TW> T;
+	const size_t smem1 = T::SMEM;
+	bool *attr_done = ctx->attr_done_part + (W - 1) * 2 + (TW == 256 ? 0 : 1);
+	if (!*attr_done) {
+		CU((cudaFuncSetAttribute(k_partition<W, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)));
+		*attr_done = true;
 	}
-	const uint64_t n_tiles = (n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES;
-	for (int attempt = 0;; ++attempt) {
-	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)n_buckets * 8, ctx->stream)); }
+	constexpr uint64_t F = TAGPU_TILE_WORDS / TW;                 // kernel tiles per 256-word tile
+	const uint64_t n_tiles = (n + T::BASES - 1) / T::BASES, n_big = (n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES;
 	if (n_tiles && !ctx->h_src) {
-		LAUNCH_SMEM(k_partition<W>, (unsigned)n_tiles, TAGPU_TILE_THREADS, smem1, d_seq, n, 0u, cfg, (SkRec<W> *)ctx->regions.p,
+		LAUNCH_SMEM_NAMED("k_partition<W>", (k_partition<W, TW>), (unsigned)n_tiles, T::THREADS, smem1, d_seq, n, 0u, cfg, (SkRec<W> *)ctx->regions.p,
 			    (unsigned long long *)ctx->cursor.p, (SkRec<W> *)ctx->overflow.p, (uint32_t *)ctx->overflow_bucket.p, ctx->d_ctr);
 	} else if (n_tiles) {
-		// The reads are still in host memory (d_seq is our staging buffer): upload them in chunks on a second stream and
-		// run pass 1 over every chunk as soon as it has landed, so the PCIe copy hides the partition pass.  A tile needs
-		// one word of look-ahead, so a launch covers the tiles whose right halo is already on the device: with an ASCII
-		// stream the copy runs 32 bytes ahead; with a packed stream (whole 3072-byte tiles) the last tile of a chunk waits
-		// for the next chunk.
 		const bool packed = cfg.packed != 0;
-		uint64_t chunk_tiles = n_tiles / TAGPU_UPLOAD_CHUNKS + 1;
-		const uint64_t min_tiles = packed ? 1366 : 512;            // >= 4 MB per copy: small inputs go up in one piece
-		if (chunk_tiles < min_tiles) chunk_tiles = min_tiles;
+		uint64_t chunk_big = n_big / TAGPU_UPLOAD_CHUNKS + 1;
+		const uint64_t min_big = packed ? 1366 : 512;              // >= 4 MB per copy: small inputs go up in one piece
+		if (chunk_big < min_big) chunk_big = min_big;
 		const uint8_t *h_src = ctx->h_src;
 		ctx->h_src = nullptr;
-		const uint64_t total = packed ? n_tiles * (uint64_t)TAGPU_PACKED_TILE_BYTES : n;
-		uint64_t copied = 0, tile0 = 0, up_tile = 0;                // up_tile: tiles whose upload has been issued
+		const uint64_t total = packed ? n_big * (uint64_t)TAGPU_PACKED_TILE_BYTES : n;
+		uint64_t copied = 0, tile0 = 0, up_big = 0;                 // up_big: 256-word tiles whose upload has been issued
 		for (int c = 0; tile0 < n_tiles; ++c) {
-			up_tile = up_tile + chunk_tiles < n_tiles ? up_tile + chunk_tiles : n_tiles;
+			up_big = up_big + chunk_big < n_big ? up_big + chunk_big : n_big;
 			uint64_t want, tile1;
 			if (packed) {
-				want = up_tile * (uint64_t)TAGPU_PACKED_TILE_BYTES;
-				tile1 = up_tile == n_tiles ? n_tiles : up_tile - 1;
+				want = up_big * (uint64_t)TAGPU_PACKED_TILE_BYTES;
+				tile1 = up_big == n_big ? n_tiles : (up_big - 1) * F;
 			} else {
-				want = up_tile == n_tiles ? n : up_tile * TAGPU_TILE_BASES + 32 * TAGPU_RHALO_WORDS;
-				tile1 = up_tile;
+				want = up_big == n_big ? n : up_big * TAGPU_TILE_BASES + 32 * TAGPU_RHALO_WORDS;
+				tile1 = up_big == n_big ? n_tiles : up_big * F;
 			}
 			if (want > total) want = total;
 			if (ctx->src_ready && want > copied)                    // the parser is still filling the host stream: wait for this chunk
@@ -381,11 +377,33 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 			CU(cudaEventRecord(ctx->ev_chunk[c % TAGPU_UPLOAD_CHUNKS_MAX], ctx->copy_stream));
 			CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c % TAGPU_UPLOAD_CHUNKS_MAX], 0));
 			if (tile1 > tile0)
-				LAUNCH_SMEM(k_partition<W>, (unsigned)(tile1 - tile0), TAGPU_TILE_THREADS, smem1, d_seq, n, (uint32_t)tile0, cfg, (SkRec<W> *)ctx->regions.p,
+				LAUNCH_SMEM_NAMED("k_partition<W>", (k_partition<W, TW>), (unsigned)(tile1 - tile0), T::THREADS, smem1, d_seq, n, (uint32_t)tile0, cfg, (SkRec<W> *)ctx->regions.p,
 					    (unsigned long long *)ctx->cursor.p, (SkRec<W> *)ctx->overflow.p, (uint32_t *)ctx->overflow_bucket.p, ctx->d_ctr);
 			tile0 = tile1;
 		}
 	}
+	return 0;
+}
+
+// Pass 1 over this rank's reads + the bucket sort of the records that overflowed their region.  Purely local.
+template <int W>
+static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, const PartCfg &cfg_in)
+{
+	typedef BucketCfg<W> BC;
+	PartCfg cfg = cfg_in;
+	cfg.packed = ctx->src_packed ? 1u : 0u;
+	const uint32_t n_buckets = 1u << cfg.log2_buckets;
+	bool *attr_done = ctx->attr_done;
+	if (!attr_done[W]) {
+		CU(cudaFuncSetAttribute(k_count_buckets<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BC::SMEM));
+		attr_done[W] = true;
+	}
+	// small tiles where the per-word work is lightest (TileCfg); TAGPU_TILE_WORDS=256|128 forces one (developer A/B)
+	static const char *tile_env = getenv("TAGPU_TILE_WORDS");
+	const bool small_tile = tile_env ? atoi(tile_env) == 128 : cfg.K - TAGPU_MINIMIZER_M + 1 == 32;
+	for (int attempt = 0;; ++attempt) {
+	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)n_buckets * 8, ctx->stream)); }
+	if (small_tile ? partition_sweep<W, 128>(ctx, d_seq, n, cfg) : partition_sweep<W, 256>(ctx, d_seq, n, cfg)) return -1;
 	ctx->h_src = nullptr;                                       // (a second attempt reads the stream from the device)
 	ctx->src_ready = nullptr;
 	if (read_counters(ctx, TAGPU_ERR_BUCKET_OVERFLOW)) return -1;
