@@ -300,7 +300,7 @@ k_contract(const SolidBlock *__restrict__ blocks, uint32_t n_directory, const Ke
 		TC(4);
 	}
 #ifdef TAGPU_TIMING
-	if ((tid & 31u) == 0) for (int i = 0; i < 5; ++i) atomicAdd(ctr + CTR_JUMP_FLAGS + 56 + i, (unsigned long long)tc[i]);
+	if ((tid & 31u) == 0) for (int i = 0; i < 5; ++i) atomicAdd(ctr + CTR_JUMP_FLAGS + 57 + i, (unsigned long long)tc[i]);
 #endif
 }
 

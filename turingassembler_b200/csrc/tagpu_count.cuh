@@ -425,7 +425,10 @@ template <int W> struct BucketCfg {
 	// records staged per round (<= 2 * THREADS: a thread stages up to two).  A staged record is kept in BOTH orientations
 	// (see "orientation of a window" below), so the round is smaller than 2 * THREADS; a group of GROUP_TARGET windows
 	// holds ~550 records of 151 bp reads and still fits one round.
-	static constexpr bool DUAL = W == 2;                        // 64-bit keys: one rc64 per window is cheaper than a second staged copy
+#ifndef TAGPU_BC_DUAL
+#define TAGPU_BC_DUAL 1
+#endif
+	static constexpr bool DUAL = W == 2 && TAGPU_BC_DUAL;                        // 64-bit keys: one rc64 per window is cheaper than a second staged copy
 #ifndef TAGPU_BC_ROUND2
 #define TAGPU_BC_ROUND2 608
 #endif
@@ -975,21 +978,21 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 				const uint32_t q = lane & 7u;
 				// (a shared item cursor instead of this static split was measured: slower, 3.82 -> 3.88 ms at C2 — the atomic's
 				// latency per iteration costs more than the imbalance at the barrier behind the loop)
-				for (uint32_t ibase = warp * 4u; ibase < n_items; ibase += N_WARPS * 4u) {
-					const uint32_t it = ibase + (lane >> 3);
-					if (s_overflow) break;
-					if (it >= n_items) continue;
-					const uint32_t item = s_item[it];
+				// key of window q of item `it` (branch-free up to the rare central palindrome, so that the two derivations of an
+				// iteration interleave): returns false if there is no such window or it belongs to another hash class
+				auto derive = [&](uint32_t it, Key<W> &key, uint32_t &mult, uint32_t &h) -> bool {
+					const bool in = it < n_items;
+					const uint32_t item = s_item[in ? it : 0u];
 					const uint32_t idx = item & 0x7ffu, j = (item >> 11) * (uint32_t)C::ITEM_WINDOWS + q;
-					const uint32_t meta = s_meta[idx], n_r = meta & 0xffu, mult = (meta >> 8) & 0xffu;
-					if (j >= n_r) continue;
+					const uint32_t meta = s_meta[idx], n_r = meta & 0xffu;
+					mult = (meta >> 8) & 0xffu;
+					const bool have = in && j < n_r;
 					// orientation of a window: the table key is the window x or its reverse complement, whichever has the
 					// smaller CENTRAL cb bases (a symmetric stretch around the middle of the K-mer: the central bases of rc(x)
 					// are the reverse complement of those of x, so x and rc(x) agree on the choice).  That is one 32-bit
 					// reverse complement instead of a K-base one, and the chosen orientation is then cut out of the record
 					// staged in that orientation.  Central palindromes (4^-8 of the even-K windows) compare the full keys.
-					const int sh_fw = 2 * (int)(n_r - 1u - j), sh_rv = 2 * (int)j;
-					Key<W> key;
+					const int sh_fw = have ? 2 * (int)(n_r - 1u - j) : 0, sh_rv = have ? 2 * (int)j : 0;
 					if constexpr (C::DUAL) {
 						const uint32_t *rw = reinterpret_cast<const uint32_t *>(s_rec + idx);
 						const uint32_t c_off = (uint32_t)sh_fw + c_low, ca = c_off >> 5;
@@ -1006,9 +1009,11 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 						const Key<W> rv = KO::rc(fw, K);
 						key = KO::le(fw, rv) ? fw : rv;
 					}
-					const uint32_t h = tagpu_table_hash<W>(key);
-					if (L && (h & ((1u << L) - 1u)) != cls) continue;
-					// probe: the hit / claim decision is the only divergent part
+					h = tagpu_table_hash<W>(key);
+					return have && (!L || (h & ((1u << L) - 1u)) == cls);
+				};
+				// probe + count: the hit / claim decision is the only divergent part
+				auto insert = [&](const Key<W> &key, uint32_t mult, uint32_t h) {
 					const Key<W> stored = KO::bnot(key);
 					uint32_t slot = __umulhi(h, (uint32_t)C::SLOTS);
 					int probes = 0;
@@ -1037,6 +1042,16 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 					// exactly one insert takes a key across the cutoff: the harvest knows its size before it starts
 					const uint32_t before_add = atomicAdd(t_cnt + slot, mult);
 					n_became_solid += (before_add < ci && before_add + mult >= ci) ? 1u : 0u;
+				};
+				// two items per octet and iteration: the two key derivations are independent instruction streams (measured against
+				// one item per iteration: 3.43 -> 3.40 ms at C2)
+				for (uint32_t ibase = warp * 8u; ibase < n_items; ibase += N_WARPS * 8u) {
+					if (s_overflow) break;
+					Key<W> key_a, key_b;
+					uint32_t mult_a, mult_b, h_a, h_b;
+					const bool ok_a = derive(ibase + (lane >> 3), key_a, mult_a, h_a), ok_b = derive(ibase + 4u + (lane >> 3), key_b, mult_b, h_b);
+					if (ok_a) insert(key_a, mult_a, h_a);
+					if (ok_b) insert(key_b, mult_b, h_b);
 				}
 			}
 			n_claimed = __reduce_add_sync(0xffffffffu, n_claimed);

@@ -802,6 +802,14 @@ static int contract_local(tagpu_ctx *ctx, const PathStore<W> &ps)
 		}
 	}
 	if (read_counters(ctx)) return -1;
+#ifdef TAGPU_TIMING
+	{
+		const unsigned long long *t = ctx->h_ctr + CTR_JUMP_FLAGS + 57;
+		const double tot = (double)(t[0] + t[1] + t[2] + t[3] + t[4]);
+		fprintf(stderr, "[tagpu timing] k_contract warp-cycles: load %.1f%%  table %.1f%%  hide test %.1f%%  links %.1f%%  walk + output %.1f%%\n",
+			100.0 * t[0] / tot, 100.0 * t[1] / tot, 100.0 * t[2] / tot, 100.0 * t[3] / tot, 100.0 * t[4] / tot);
+	}
+#endif
 	static const bool trace = getenv("TAGPU_TRACE_CONTRACT") != nullptr;
 	if (trace)
 		fprintf(stderr, "tagpu: contraction of %llu solid (k+1)-mers in %u blocks -> %llu paths, %llu interior words, %llu k-mers hidden\n",
