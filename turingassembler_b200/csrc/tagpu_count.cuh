@@ -270,7 +270,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 	//     and then every thread builds and appends one record per iteration — whatever the distribution of run ends over
 	//     the words: one record (2-bit bases + window count) goes to the bucket of the run's minimizer.
 	__shared__ uint16_t s_end[T::END_CAP];
-	__shared__ uint32_t s_wsum[T::THREADS / 32 + 1];
+	__shared__ uint32_t s_wsum[T::THREADS / 32 + 1], s_winsum[T::THREADS / 32 + 1];
 	const int wi0 = threadIdx.x + TAGPU_HALO_WORDS;
 	uint32_t ends = 0;
 	if (threadIdx.x < T::WORDS) {
@@ -286,14 +286,19 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 		if (lane_ >= (uint32_t)d) incl += t;
 	}
 	if (lane_ == 31) s_wsum[warp_] = incl;
+	// (the instance total — the metric's numerator — rides on the same barrier: per-warp sums, one global atomic per CTA)
+	n_win = __reduce_add_sync(0xffffffffu, n_win);
+	if (lane_ == 0) s_winsum[warp_] = n_win;
 	__syncthreads();
-	uint32_t before = 0, n_ends = 0;
+	uint32_t before = 0, n_ends = 0, n_inst = 0;
 #pragma unroll
 	for (int x = 0; x < T::THREADS / 32; ++x) {
 		const uint32_t v = s_wsum[x];
 		before += (uint32_t)x < warp_ ? v : 0u;
 		n_ends += v;
+		n_inst += s_winsum[x];
 	}
+	if (threadIdx.x == 0 && n_inst) atomicAdd(ctr + CTR_INSTANCES, (unsigned long long)n_inst);
 	const uint32_t my_first = before + incl - n_mine;
 	for (uint32_t pass0 = 0; pass0 < n_ends; pass0 += T::END_CAP) {          // (one pass unless the tile is pathological)
 		if (pass0) __syncthreads();
@@ -325,14 +330,6 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 			}
 		}
 	}
-	// instance total (the metric's numerator): one atomic per CTA
-	__shared__ uint32_t s_inst;
-	if (threadIdx.x == 0) s_inst = 0;
-	__syncthreads();
-	n_win = __reduce_add_sync(0xffffffffu, n_win);
-	if ((threadIdx.x & 31) == 0 && n_win) atomicAdd(&s_inst, n_win);
-	__syncthreads();
-	if (threadIdx.x == 0 && s_inst) atomicAdd(ctr + CTR_INSTANCES, (unsigned long long)s_inst);
 }
 
 // ---------------------------------------------------------------- overflow handling (only launched when a bucket region filled up)
