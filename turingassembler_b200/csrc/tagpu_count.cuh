@@ -98,13 +98,17 @@ TAGPU_DI SkRec<W> tagpu_make_record(const uint64_t *pk, int end_q, int n_bases, 
 	return r;
 }
 
-// Minimizer (hash, position) of the window ending at tile position q.  General case: phase B left it at hs[q - w + 1].
-// w == 32 (k0 = 45, the reference's default): the van Herk blocks coincide with the 32-position words, phase A leaves
-// per-word prefix minima in hp and suffix minima in hs, and the window is a suffix of one word plus a prefix of the next.
+// Minimizer (hash, position) of the window ending at tile position q (q >= w - 1).  B = the largest power of two <= w:
+// phase A leaves prefix minima (hp) and suffix minima (hs) inside B-aligned blocks of positions, so the minimum over any B
+// consecutive positions is one suffix entry and one prefix entry, and a window of w = B + d positions is the union of the
+// two B-ranges at its ends (min is idempotent, the overlap does not matter; the position bits in the low end of a hash keep
+// the LEFTMOST of equal hashes the minimum, whichever range it is found in).
+template <int B>
 TAGPU_DI uint32_t tagpu_window_min(const uint32_t *hs, const uint32_t *hp, int q, int w)
 {
-	const int s = max(q - w + 1, 0);
-	return w == 32 ? min(hs[HIDX(s)], hp[HIDX(q)]) : hs[HIDX(s)];
+	uint32_t m = min(hs[HIDX(q - B + 1)], hp[HIDX(q)]);
+	if (w != B) m = min(m, min(hs[HIDX(q - w + 1)], hp[HIDX(q - (w - B))]));
+	return m;
 }
 
 // ---------------------------------------------------------------- pass 1
@@ -114,8 +118,8 @@ TAGPU_DI uint32_t tagpu_window_min(const uint32_t *hs, const uint32_t *hp, int q
 // collapses before counting (tagpu_count.cuh: "duplicate records").  A run is emitted by the tile that contains its END;
 // the 96-base left halo lets it reach back to its start, the right halo word tells whether the run ends at the tile's
 // last position.
-template <int W, int TW>
-__global__ void __launch_bounds__(TileCfg<TW>::THREADS)
+template <int W, int TW, int B, bool EXACT>                    // EXACT: w == B is known at compile time (the kernel of the default k0 = 45 holds no code for w > B)
+__global__ void __launch_bounds__(TileCfg<TW>::THREADS, TileCfg<TW>::MIN_CTAS)
 k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg cfg, SkRec<W> *__restrict__ regions,
 	    unsigned long long *__restrict__ cursor, SkRec<W> *__restrict__ overflow, uint32_t *__restrict__ overflow_bucket,
 	    unsigned long long *ctr)
@@ -156,66 +160,19 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 					     : e >= 16 ? __funnelshift_r(r1, r0, 30 - 2 * (e - 16)) : r0 >> (30 - 2 * e)) & mm;
 			return ((min(fw, rv) * 0x9e3779b1u) & ~63u) | (tag0 + (uint32_t)i);
 		};
-		if (w == 32) {
-			// the word IS a van Herk block: hashes stay in registers, prefix minima go to hp, suffix minima to hs
-			uint32_t h[32];
-			uint32_t acc = TAGPU_H_INVALID;
-#pragma unroll
-			for (int i = 0; i < 32; ++i) {
-				h[i] = mmer_hash(i);
-				acc = min(acc, h[i]);
-				hp[j * 33 + i] = acc;
-			}
-			acc = TAGPU_H_INVALID;
-#pragma unroll
-			for (int i = 31; i >= 0; --i) {
-				acc = min(acc, h[i]);
-				hs[j * 33 + i] = acc;
-			}
-		} else {
-#pragma unroll
-			for (int i = 0; i < 32; ++i) hp[j * 33 + i] = mmer_hash(i);
-		}
-	}
-	__syncthreads();
-
-	// B. sliding minimum over the w = K - m + 1 m-mers of every window (van Herk / Gil-Werman): positions are cut into
-	//    blocks of w.  The thread of block b first writes the suffix minima of block b - 1 into hs, then walks block b
-	//    forwards with a running prefix minimum and replaces hs[q - w + 1] by the minimum of window q — so afterwards
-	//    hs[q - w + 1] IS the minimizer of the window ending at q.  Everything a thread writes (the hs region of block
-	//    b - 1) is read only by itself, so the two passes need no barrier between them; hp stays read-only.
-	const int n_blocks = w == 32 ? 0 : (T::HM_POS + w - 1) / w;     // (w == 32: done in phase A)
-	for (int blk = threadIdx.x; blk < n_blocks; blk += blockDim.x) {
-		const int lo = blk * w, hi = min(lo + w, T::HM_POS);
-		// (both passes are unrolled by four with the loads issued first: the chain through `acc` is only the min)
+		// hashes stay in registers; prefix minima inside the B-aligned blocks of the word go to hp, suffix minima to hs
+		uint32_t h[32];
 		uint32_t acc = TAGPU_H_INVALID;
-		int q = lo - 1;
-		const int stop = max(lo - w, 0);
-		for (; q - 3 >= stop; q -= 4) {
-			const uint32_t h0 = hp[HIDX(q)], h1 = hp[HIDX(q - 1)], h2 = hp[HIDX(q - 2)], h3 = hp[HIDX(q - 3)];
-			const uint32_t a0 = min(acc, h0), a1 = min(a0, h1), a2 = min(a1, h2), a3 = min(a2, h3);
-			hs[HIDX(q)] = a0; hs[HIDX(q - 1)] = a1; hs[HIDX(q - 2)] = a2; hs[HIDX(q - 3)] = a3;
-			acc = a3;
+#pragma unroll
+		for (int i = 0; i < 32; ++i) {
+			h[i] = mmer_hash(i);
+			acc = i % B == 0 ? h[i] : min(acc, h[i]);
+			hp[j * 33 + i] = acc;
 		}
-		for (; q >= stop; --q) { acc = min(acc, hp[HIDX(q)]); hs[HIDX(q)] = acc; }
-		acc = TAGPU_H_INVALID;
-		q = lo;
-		// windows q = lo .. hi - 1 store at sidx = q - w + 1; the last one of a full block (sidx == lo) is the block minimum:
-		// the first suffix minimum the thread of block b + 1 writes to the same slot (same value, never read here)
-		if (lo - w + 1 >= 0)
-			for (; q + 3 < hi && q + 3 - w + 1 < lo; q += 4) {
-				const int sidx = q - w + 1;
-				const uint32_t h0 = hp[HIDX(q)], h1 = hp[HIDX(q + 1)], h2 = hp[HIDX(q + 2)], h3 = hp[HIDX(q + 3)];
-				const uint32_t s0 = hs[HIDX(sidx)], s1 = hs[HIDX(sidx + 1)], s2 = hs[HIDX(sidx + 2)], s3 = hs[HIDX(sidx + 3)];
-				const uint32_t a0 = min(acc, h0), a1 = min(a0, h1), a2 = min(a1, h2), a3 = min(a2, h3);
-				hs[HIDX(sidx)] = min(a0, s0); hs[HIDX(sidx + 1)] = min(a1, s1); hs[HIDX(sidx + 2)] = min(a2, s2); hs[HIDX(sidx + 3)] = min(a3, s3);
-				acc = a3;
-			}
-		for (; q < hi; ++q) {
-			acc = min(acc, hp[HIDX(q)]);
-			const int sidx = q - w + 1;
-			if (sidx == lo) hs[HIDX(sidx)] = acc;
-			else if (sidx >= 0) hs[HIDX(sidx)] = min(acc, hs[HIDX(sidx)]);
+#pragma unroll
+		for (int i = 31; i >= 0; --i) {
+			acc = i % B == B - 1 ? h[i] : min(acc, h[i]);
+			hs[j * 33 + i] = acc;
 		}
 	}
 	__syncthreads();
@@ -238,23 +195,34 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 		else if (extra > 0) smear(extra);
 		const uint32_t vmask = __brev(~c);                          // bit i = position i of this word ends a valid window
 		const uint32_t pv = ~b & 1u;                                // ... and so does the last position of the word before
+		// minimizer of the window ending at position i of this word (i = -1: the last position of the word before), see
+		// tagpu_window_min: every index is the thread's base plus a compile-time constant, or — for the second B-range of a
+		// window with w > B — plus a constant behind a base shifted by d = w - B resp. w - 1 positions (the padding word
+		// between two words of 32 positions is stepped over where the shifted position falls into an earlier word)
 		uint32_t ne = 0;
-		if (w == 32) {
-			// window ending at j * 32 + i = suffix of word j - 1 from position i + 1 on, plus prefix of word j up to i: every
-			// index is the thread's base plus a constant
-			const uint32_t *hs_prev = hs + (j - 1) * 33, *hp_cur = hp + j * 33;
-			uint32_t pm = min(hs_prev[0], hp_cur[-2]);                     // (hp_cur[-2] = hp[(j - 1) * 33 + 31])
+		const uint32_t *hpj = hp + j * 33, *hsj = hs + j * 33;
+		const int d = w - B;
+		auto rel = [](int p) { return p >= 0 ? p : (p >= -32 ? p - 1 : p - 2); };   // position relative to the word -> padded index
+		auto min_b = [&](int i) -> uint32_t { return min(hsj[rel(i - B + 1)], hpj[rel(i)]); };   // (i: compile-time constant after unrolling)
+		auto min_w = [&](int i) -> uint32_t {
+			const int p1 = i - d, p2 = i - w + 1;
+			int i2 = j * 33 + p2 - (p2 < 0 ? 1 : 0) - (p2 < -32 ? 1 : 0);
+			if (B == 32) i2 = max(i2, 0);                           // (w > 33 in the first halo word: no window of the tile reaches there)
+			return min(min_b(i), min(hs[i2], hpj[p1 - (p1 < 0 ? 1 : 0)]));
+		};
+		if (EXACT || d == 0) {                                      // w = B (the default k0 = 45: w = 32): one B-range is the window
+			uint32_t pm = min_b(-1);
 #pragma unroll
 			for (int i = 0; i < 32; ++i) {
-				const uint32_t cm = min(hs_prev[i + 1 + (i == 31 ? 1 : 0)], hp_cur[i]);   // (i == 31: hs[j * 33])
+				const uint32_t cm = min_b(i);
 				ne |= (cm != pm ? 1u : 0u) << i;
 				pm = cm;
 			}
 		} else {
-			uint32_t pm = tagpu_window_min(hs, hp, j * 32 - 1, w);
+			uint32_t pm = min_w(-1);
 #pragma unroll
 			for (int i = 0; i < 32; ++i) {
-				const uint32_t cm = tagpu_window_min(hs, hp, j * 32 + i, w);
+				const uint32_t cm = min_w(i);
 				ne |= (cm != pm ? 1u : 0u) << i;
 				pm = cm;
 			}
@@ -274,9 +242,9 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 	const int wi0 = threadIdx.x + TAGPU_HALO_WORDS;
 	uint32_t ends = 0;
 	if (threadIdx.x < T::WORDS) {
-		const uint32_t V = vw[wi0], B = bw[wi0];
-		const uint32_t Vn = (V >> 1) | (vw[wi0 + 1] << 31), Bn = (B >> 1) | (bw[wi0 + 1] << 31);
-		ends = V & (~Vn | Bn);
+		const uint32_t V = vw[wi0], S = bw[wi0];
+		const uint32_t Vn = (V >> 1) | (vw[wi0 + 1] << 31), Sn = (S >> 1) | (bw[wi0 + 1] << 31);
+		ends = V & (~Vn | Sn);
 	}
 	const uint32_t n_mine = __popc(ends), lane_ = threadIdx.x & 31u, warp_ = threadIdx.x >> 5;
 	uint32_t incl = n_mine;
@@ -317,7 +285,7 @@ k_partition(const uint8_t *__restrict__ seq, uint64_t n, uint32_t tile0, PartCfg
 			const int st = upto ? 31 - __clz(upto) : -1 - __clz(bw[wi - 1]);
 			const int nw = e - st + 1;
 			if (nw > 32) { atomicOr(ctr + CTR_ERROR, (unsigned long long)TAGPU_ERR_RUN_LENGTH); continue; }
-			const uint32_t b = tagpu_bucket_of(tagpu_window_min(hs, hp, end_q, w) >> 6, cfg.log2_buckets);
+			const uint32_t b = tagpu_bucket_of(tagpu_window_min<B>(hs, hp, end_q, EXACT ? B : w) >> 6, cfg.log2_buckets);
 			const SkRec<W> rec = tagpu_make_record<W>(pk, end_q, nw + K - 1, nw);
 			const unsigned long long old = atomicAdd(cursor + b, 1ull | ((unsigned long long)nw << 32));
 			const uint32_t idx = (uint32_t)old;

@@ -9,15 +9,19 @@
 #pragma once
 #include "tagpu_key.cuh"
 
-// Tile geometry of pass 1, by the number of 32-base words whose positions are window ends.  256 words (8192 bases, 288
-// threads, 74 KB of shared memory: 3 CTAs per SM) is the general tile; 128 words (160 threads, 38 KB: 5-6 CTAs per SM) hides
-// the tile load and the barriers better and is used where the per-word work is lightest (w = 32, the default k0 = 45:
-// 1.40 -> 1.29 ms at C2; the general-w path loses with it, 2.05 -> 2.14 ms at C1).
+// Tile geometry of pass 1, by the number of 32-base words whose positions are window ends.  128 words (4096 bases, 160
+// threads, 38 KB of shared memory: 6 CTAs per SM) is what pass 1 uses: many small CTAs hide the tile load and the barriers
+// better than 256 words (288 threads, 74 KB: 3 CTAs per SM) — 1.40 -> 1.29 ms at C2 (w = 32), 1.89 -> 1.68 ms at C1 (w = 18).
+// The 256-word geometry remains the tile of the packed stream layout and a developer switch (TAGPU_TILE_WORDS=256).
 constexpr int TAGPU_HALO_WORDS = 3;                 // 96 bases to the left: K <= 64 of history for a window, plus the 31 windows a super-k-mer may reach back
 constexpr int TAGPU_RHALO_WORDS = 1;                // one word to the right: whether a super-k-mer ends at the tile's last position depends on the next window
 template <int TW> struct TileCfg {
 	static constexpr int WORDS = TW;
 	static constexpr int THREADS = TW == 256 ? 288 : 160;      // >= SMEM_WORDS: every per-word phase (halo words included) is ONE pass over the threads
+#ifndef TAGPU_TILE_MIN_CTAS
+#define TAGPU_TILE_MIN_CTAS 6
+#endif
+	static constexpr int MIN_CTAS = TW == 256 ? 3 : TAGPU_TILE_MIN_CTAS;         // CTAs per SM the shared memory allows: the register budget follows (launch bounds)
 	static constexpr int BASES = TW * 32;
 	static constexpr int SMEM_WORDS = TW + TAGPU_HALO_WORDS + TAGPU_RHALO_WORDS;
 	static constexpr int HM_POS = SMEM_WORDS * 32;             // positions of the packed tile (incl. halo)

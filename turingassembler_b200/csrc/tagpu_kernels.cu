@@ -51,7 +51,7 @@ struct tagpu_ctx {
 	int n_sm = 0, jump_grid = 0;
 	// per-device launch state (a process may hold contexts on several devices)
 	bool attr_done[3] = { false, false, false };
-	bool attr_done_part[4] = { false, false, false, false };   // k_partition<W, TW>: [(W - 1) * 2 + (TW == 128)]
+	bool attr_done_part[16] = {};                               // k_partition<W, TW, B, EXACT>: [((W - 1) * 2 + (TW == 128)) * 4 + log2(B) - 2]
 	int grid_s[3] = { 0, 0, 0 }, grid_m[3] = { 0, 0, 0 }, grid_l[3] = { 0, 0, 0 };
 	uint64_t budget_n = 0;
 	size_t budget = 0;                 // count_budget(): memory the count stage planned with for a stream of budget_n bytes
@@ -335,20 +335,20 @@ static size_t count_budget(tagpu_ctx *ctx, uint64_t n)
 // copy hides the pass.  Chunks are counted in 256-word tiles, the unit of the packed stream layout; a launch covers the
 // kernel tiles whose right halo word is already on the device: with an ASCII stream the copy runs 32 bytes ahead, with a
 // packed stream (whole 3072-byte tiles) the last 256-word tile of a chunk waits for the next chunk.
-template <int W, int TW>
+template <int W, int TW, int B, bool EXACT>
 static int partition_sweep(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, const PartCfg &cfg)
 {
 	typedef TileCfg<TW> T;
 	const size_t smem1 = T::SMEM;
-	bool *attr_done = ctx->attr_done_part + (W - 1) * 2 + (TW == 256 ? 0 : 1);
+	bool *attr_done = ctx->attr_done_part + (((W - 1) * 2 + (TW == 256 ? 0 : 1)) * 4 + (B == 4 ? 0 : B == 8 ? 1 : B == 16 ? 2 : 3)) * 2 + (EXACT ? 1 : 0);
 	if (!*attr_done) {
-		CU((cudaFuncSetAttribute(k_partition<W, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)));
+		CU((cudaFuncSetAttribute(k_partition<W, TW, B, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)));
 		*attr_done = true;
 	}
 	constexpr uint64_t F = TAGPU_TILE_WORDS / TW;                 // kernel tiles per 256-word tile
 	const uint64_t n_tiles = (n + T::BASES - 1) / T::BASES, n_big = (n + TAGPU_TILE_BASES - 1) / TAGPU_TILE_BASES;
 	if (n_tiles && !ctx->h_src) {
-		LAUNCH_SMEM_NAMED("k_partition<W>", (k_partition<W, TW>), (unsigned)n_tiles, T::THREADS, smem1, d_seq, n, 0u, cfg, (SkRec<W> *)ctx->regions.p,
+		LAUNCH_SMEM_NAMED("k_partition<W>", (k_partition<W, TW, B, EXACT>), (unsigned)n_tiles, T::THREADS, smem1, d_seq, n, 0u, cfg, (SkRec<W> *)ctx->regions.p,
 			    (unsigned long long *)ctx->cursor.p, (SkRec<W> *)ctx->overflow.p, (uint32_t *)ctx->overflow_bucket.p, ctx->d_ctr);
 	} else if (n_tiles) {
 		const bool packed = cfg.packed != 0;
@@ -377,7 +377,7 @@ static int partition_sweep(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 			CU(cudaEventRecord(ctx->ev_chunk[c % TAGPU_UPLOAD_CHUNKS_MAX], ctx->copy_stream));
 			CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c % TAGPU_UPLOAD_CHUNKS_MAX], 0));
 			if (tile1 > tile0)
-				LAUNCH_SMEM_NAMED("k_partition<W>", (k_partition<W, TW>), (unsigned)(tile1 - tile0), T::THREADS, smem1, d_seq, n, (uint32_t)tile0, cfg, (SkRec<W> *)ctx->regions.p,
+				LAUNCH_SMEM_NAMED("k_partition<W>", (k_partition<W, TW, B, EXACT>), (unsigned)(tile1 - tile0), T::THREADS, smem1, d_seq, n, (uint32_t)tile0, cfg, (SkRec<W> *)ctx->regions.p,
 					    (unsigned long long *)ctx->cursor.p, (SkRec<W> *)ctx->overflow.p, (uint32_t *)ctx->overflow_bucket.p, ctx->d_ctr);
 			tile0 = tile1;
 		}
@@ -398,12 +398,24 @@ static int partition_local(tagpu_ctx *ctx, const uint8_t *d_seq, uint64_t n, con
 		CU(cudaFuncSetAttribute(k_count_buckets<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BC::SMEM));
 		attr_done[W] = true;
 	}
-	// small tiles where the per-word work is lightest (TileCfg); TAGPU_TILE_WORDS=256|128 forces one (developer A/B)
+	// 128-word tiles (TileCfg) unless TAGPU_TILE_WORDS=256 asks for the large ones (developer A/B)
 	static const char *tile_env = getenv("TAGPU_TILE_WORDS");
-	const bool small_tile = tile_env ? atoi(tile_env) == 128 : cfg.K - TAGPU_MINIMIZER_M + 1 == 32;
+	const bool small_tile = tile_env ? atoi(tile_env) != 256 : true;
 	for (int attempt = 0;; ++attempt) {
 	{ ProfScope ps_(ctx, "memset"); CU(cudaMemsetAsync(ctx->cursor.p, 0, (size_t)n_buckets * 8, ctx->stream)); }
-	if (small_tile ? partition_sweep<W, 128>(ctx, d_seq, n, cfg) : partition_sweep<W, 256>(ctx, d_seq, n, cfg)) return -1;
+	// B = the largest power of two <= w (tagpu_window_min): 64-bit keys have w = 4 .. 18, 128-bit keys w = 19 .. 50
+	const int w = cfg.K - TAGPU_MINIMIZER_M + 1;
+	int rc;
+	if constexpr (W == 1) {
+		if (w >= 16) rc = small_tile ? partition_sweep<W, 128, 16, false>(ctx, d_seq, n, cfg) : partition_sweep<W, 256, 16, false>(ctx, d_seq, n, cfg);
+		else if (w >= 8) rc = small_tile ? partition_sweep<W, 128, 8, false>(ctx, d_seq, n, cfg) : partition_sweep<W, 256, 8, false>(ctx, d_seq, n, cfg);
+		else rc = small_tile ? partition_sweep<W, 128, 4, false>(ctx, d_seq, n, cfg) : partition_sweep<W, 256, 4, false>(ctx, d_seq, n, cfg);
+	} else {
+		if (w == 32) rc = small_tile ? partition_sweep<W, 128, 32, true>(ctx, d_seq, n, cfg) : partition_sweep<W, 256, 32, true>(ctx, d_seq, n, cfg);
+		else if (w > 32) rc = small_tile ? partition_sweep<W, 128, 32, false>(ctx, d_seq, n, cfg) : partition_sweep<W, 256, 32, false>(ctx, d_seq, n, cfg);
+		else rc = small_tile ? partition_sweep<W, 128, 16, false>(ctx, d_seq, n, cfg) : partition_sweep<W, 256, 16, false>(ctx, d_seq, n, cfg);
+	}
+	if (rc) return -1;
 	ctx->h_src = nullptr;                                       // (a second attempt reads the stream from the device)
 	ctx->src_ready = nullptr;
 	if (read_counters(ctx, TAGPU_ERR_BUCKET_OVERFLOW)) return -1;
