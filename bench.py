@@ -41,9 +41,9 @@ WORKLOADS = {
 L = 151
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the last `ncu --set full` capture of the C2 workload
 # (profiles/), keyed by kernel; None until such a capture exists for the current kernels
-TRAFFIC = {"C2": {"k_count_buckets<W>": 1.369880e9 + 0.143385e9, "k_partition<W>": 0.610175e9 + 0.909848e9,   # profiles/r2_ncu_top_kernels_raw.txt
+TRAFFIC = {"C2": {"k_count_buckets<W>": 1.370291e9 + 0.143480e9, "k_partition<W>": 0.610127e9 + 0.908919e9,   # profiles/r2_ncu_top_kernels_raw.txt
                   # all kernel launches of one build (profiles/r2_dram_bytes_C2.csv; the 12 memsets of a step, ~0.1 GB, are not in it)
-                  "whole_path": 4.320926e9}}
+                  "whole_path": 4.311797e9}}
 
 
 N_CHUNKS = 16   # the read set is generated in 16 independently seeded chunks of pairs, so a rank can make just its share
