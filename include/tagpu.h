@@ -251,6 +251,18 @@ void tagpu_free_reads(uint8_t *stream);
 /* The same ingest as an object, so that the upload can chase the parser: open (newline index + sizes: the stream length is
  * known), start (copy workers fill dst in stream order), ready (bytes of the stream prefix that are final; pass it with the
  * object to tagpu_set_source_progress before tagpu_build_host / tagpu_count_host), finish (join + release). */
+/* Raw FASTQ files on the device (the files entry points use it for plain FASTQ when TAGPU_DEVICE_PARSE=1): the host reads the files into a pinned ring
+ * (tagpu_raw_ring), sends the slots up (tagpu_raw_put; tagpu_raw_slot_wait tells when a slot may be overwritten) into one
+ * device buffer (tagpu_raw_begin; file f at byte off[f], 256-aligned), and the device parses the records — the sequence is
+ * line 2 of every 4, /root/reference/src/get_buffer.c:339-348 — and builds.  ends_nl[f]: the file's last byte is a newline.
+ * tagpu_parse_fastq_device only parses and returns the stream length (h_out, if not NULL, receives the stream). */
+void *tagpu_raw_ring(tagpu_ctx *ctx, size_t bytes);
+int tagpu_raw_begin(tagpu_ctx *ctx, uint64_t total_bytes);
+int tagpu_raw_put(tagpu_ctx *ctx, uint64_t dev_off, const void *host, uint64_t bytes, int slot);
+int tagpu_raw_slot_wait(tagpu_ctx *ctx, int slot);
+int64_t tagpu_parse_fastq_device(tagpu_ctx *ctx, int n_files, const uint64_t *off, const uint64_t *len, const uint8_t *ends_nl, uint8_t *h_out);
+int tagpu_build_fastq_device(tagpu_ctx *ctx, int n_files, const uint64_t *off, const uint64_t *len, const uint8_t *ends_nl, int k, int with_graph);
+
 struct tagpu_ingest;
 struct tagpu_ingest *tagpu_ingest_open(int n_files, char **files, int n_threads);
 uint64_t tagpu_ingest_bytes(const struct tagpu_ingest *ing);

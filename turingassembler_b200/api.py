@@ -178,6 +178,18 @@ def load_library() -> C.CDLL:
     lib.tagpu_write_graph_bin.argtypes = [vp, C.c_char_p]
     lib.tagpu_write_kmc_db.restype = i32
     lib.tagpu_write_kmc_db.argtypes = [vp, C.c_char_p]
+    lib.tagpu_raw_ring.restype = vp
+    lib.tagpu_raw_ring.argtypes = [vp, C.c_size_t]
+    lib.tagpu_raw_begin.restype = i32
+    lib.tagpu_raw_begin.argtypes = [vp, u64]
+    lib.tagpu_raw_put.restype = i32
+    lib.tagpu_raw_put.argtypes = [vp, u64, vp, u64, i32]
+    lib.tagpu_raw_slot_wait.restype = i32
+    lib.tagpu_raw_slot_wait.argtypes = [vp, i32]
+    lib.tagpu_parse_fastq_device.restype = C.c_int64
+    lib.tagpu_parse_fastq_device.argtypes = [vp, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_uint8), vp]
+    lib.tagpu_build_fastq_device.restype = i32
+    lib.tagpu_build_fastq_device.argtypes = [vp, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_uint8), i32, i32]
     lib.tagpu_load_reads.restype = C.c_int64
     lib.tagpu_load_reads.argtypes = [i32, C.POINTER(C.c_char_p), i32, C.POINTER(vp)]
     lib.tagpu_free_reads.argtypes = [vp]
@@ -302,6 +314,38 @@ class Tagpu:
     def build_device_packed(self, d_ptr: int, n_positions: int, k: int):
         self._check(self.lib.tagpu_build_device_packed(self.ctx, C.c_void_p(d_ptr), n_positions, k))
         return self.stats()
+
+    def parse_fastq(self, blobs: Sequence[bytes]) -> bytes:
+        """Raw FASTQ file contents -> the read stream, parsed on the device (tagpu_parse_fastq_device; what the files entry
+        points do with plain FASTQ, here fed from memory: the bytes go up through the pinned ring in 1 MB pieces)."""
+        n = len(blobs)
+        off, ln, nl = (C.c_uint64 * n)(), (C.c_uint64 * n)(), (C.c_uint8 * n)()
+        total = 0
+        for i, b in enumerate(blobs):
+            off[i], ln[i], nl[i] = total, len(b), 1 if b.endswith(b"\n") else 0
+            total += (len(b) + 255) & ~255
+        slot, n_slots = 1 << 20, 4
+        ring = self.lib.tagpu_raw_ring(self.ctx, slot * n_slots)
+        if not ring:
+            raise TagpuError("cannot allocate the pinned ring")
+        self._check(self.lib.tagpu_raw_begin(self.ctx, total))
+        c = 0
+        for i, b in enumerate(blobs):
+            for o in range(0, len(b), slot):
+                piece = b[o:o + slot]
+                s_ = c % n_slots
+                if c >= n_slots:
+                    self._check(self.lib.tagpu_raw_slot_wait(self.ctx, s_))
+                C.memmove(ring + s_ * slot, piece, len(piece))
+                self._check(self.lib.tagpu_raw_put(self.ctx, off[i] + o, C.c_void_p(ring + s_ * slot), len(piece), s_))
+                c += 1
+        m = self.lib.tagpu_parse_fastq_device(self.ctx, n, off, ln, nl, None)
+        if m < 0:
+            raise TagpuError(f"tagpu_parse_fastq_device returned {m}: {self.lib.tagpu_last_error(self.ctx).decode()}")
+        out = np.empty(max(m, 1), dtype=np.uint8)
+        m2 = self.lib.tagpu_parse_fastq_device(self.ctx, n, off, ln, nl, C.c_void_p(out.ctypes.data))
+        assert m2 == m
+        return out[:m].tobytes()
 
     def build_local_host(self, stream, k: int, contigs: Sequence[bytes], contig_cov: Sequence[float]):
         """build_local_assembly_graph on host buffers: reads + flanking contigs (ACGT bytes) with their coverages."""

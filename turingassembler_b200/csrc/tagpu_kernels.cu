@@ -18,6 +18,7 @@
 #include "tagpu_coverage.cuh"
 #include "tagpu_digest.cuh"
 #include "tagpu_extract.cuh"
+#include "tagpu_fastq.cuh"
 #include "tagpu_graph.cuh"
 #include "tagpu_key.cuh"
 
@@ -30,6 +31,8 @@ struct Buf {
 };
 
 struct DistState;
+constexpr int TAGPU_RAW_SLOTS_MAX = 64;
+
 struct tagpu_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
@@ -51,12 +54,18 @@ struct tagpu_ctx {
 	int n_sm = 0, jump_grid = 0;
 	// per-device launch state (a process may hold contexts on several devices)
 	bool attr_done[3] = { false, false, false };
-	bool attr_done_part[16] = {};                               // k_partition<W, TW, B, EXACT>: [((W - 1) * 2 + (TW == 128)) * 4 + log2(B) - 2]
+	bool attr_done_part[32] = {};                               // k_partition<W, TW, B, EXACT>: [(((W - 1) * 2 + (TW == 128)) * 4 + log2(B) - 2) * 2 + EXACT]
 	int grid_s[3] = { 0, 0, 0 }, grid_m[3] = { 0, 0, 0 }, grid_l[3] = { 0, 0, 0 };
 	uint64_t budget_n = 0;
 	size_t budget = 0;                 // count_budget(): memory the count stage planned with for a stream of budget_n bytes
 	uint64_t n_solid_local = 0;        // entries of the solid list THIS context holds (= st.n_solid unless the set is sharded)
 	Buf chain_slot, grp_start, grp_desc, node_mask;
+	// raw FASTQ on the device (tagpu_fastq.cuh): file bytes, per-block newline counts / bases, per-record bounds and offsets
+	Buf raw, fq_cnt, fq_base, fq_tot, fq_lo, fq_hi, fq_len, fq_off;
+	void *raw_ring = nullptr;          // pinned ring the host reads the files into (tagpu_raw_ring)
+	size_t raw_ring_bytes = 0;
+	cudaEvent_t ev_slot[TAGPU_RAW_SLOTS_MAX], ev_raw = nullptr;
+	bool ev_slot_made = false;
 	Buf seq, solid_key, solid_cnt, kt_keys, kt_mask, node_ord, node_slot, node_ebase, vL, vR, jump, vsucc,
 		vedge, e_src, e_dst, e_rc, e_len, e_count, e_off, e_seq;
 	uint32_t kt_slots = 0;
@@ -218,11 +227,17 @@ extern "C" void tagpu_destroy(tagpu_ctx *ctx)
 	dist_release(ctx);
 	Buf *bufs[] = { &ctx->regions, &ctx->cursor, &ctx->overflow, &ctx->overflow_bucket, &ctx->ext, &ctx->ext_off, &ctx->ext_count, &ctx->cur_all, &ctx->ext_all, &ctx->pex, &ctx->bsum, &ctx->grp_end, &ctx->blocks, &ctx->blk_defer, &ctx->d_first, &ctx->d_last, &ctx->d_n, &ctx->d_cnt, &ctx->d_off, &ctx->d_int, &ctx->wlast, &ctx->g_key, &ctx->comb_key, &ctx->comb_cnt, &ctx->g_seq, &ctx->hj_own, &ctx->hj_bits, &ctx->hj_list, &ctx->hj_jump2, &ctx->chain_slot, &ctx->grp_start, &ctx->grp_desc, &ctx->node_mask, &ctx->seq, &ctx->solid_key, &ctx->solid_cnt, &ctx->kt_keys, &ctx->kt_mask,
 			&ctx->node_ord, &ctx->node_slot, &ctx->node_ebase, &ctx->vL, &ctx->vR, &ctx->jump, &ctx->vsucc, &ctx->vedge,
-			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq };
+			&ctx->e_src, &ctx->e_dst, &ctx->e_rc, &ctx->e_len, &ctx->e_count, &ctx->e_off, &ctx->e_seq,
+			&ctx->raw, &ctx->fq_cnt, &ctx->fq_base, &ctx->fq_tot, &ctx->fq_lo, &ctx->fq_hi, &ctx->fq_len, &ctx->fq_off };
 	for (Buf *b : bufs)
 		if (b->p) cudaFree(b->p);
 	cudaFree(ctx->d_ctr);
 	cudaFreeHost(ctx->h_ctr);
+	if (ctx->raw_ring) cudaFreeHost(ctx->raw_ring);
+	if (ctx->ev_slot_made) {
+		for (int i = 0; i < TAGPU_RAW_SLOTS_MAX; ++i) cudaEventDestroy(ctx->ev_slot[i]);
+		cudaEventDestroy(ctx->ev_raw);
+	}
 	for (int i = 0; i < 4; ++i) cudaEventDestroy(ctx->ev[i]);
 	for (int i = 0; i < TAGPU_UPLOAD_CHUNKS_MAX; ++i) cudaEventDestroy(ctx->ev_chunk[i]);
 	cudaStreamDestroy(ctx->copy_stream);
@@ -1455,6 +1470,133 @@ extern "C" int tagpu_count_host_packed(tagpu_ctx *ctx, const uint8_t *h_packed, 
 	ctx->src_packed = true;
 	if (upload(ctx, h_packed, tagpu_packed_bytes(n_positions))) return -1;
 	return run_packed(ctx, (const uint8_t *)ctx->seq.p, n_positions, K, false);
+}
+
+// ------------------------------------------------------------------------------------------------ raw FASTQ files on the device
+// The files entry points read plain FASTQ files into a pinned ring (one kernel copy per byte, no parsing on the host), the
+// ring's slots go up as they fill, and the records are parsed here (tagpu_fastq.cuh).
+extern "C" void *tagpu_raw_ring(tagpu_ctx *ctx, size_t bytes)
+{
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+	if (ctx->raw_ring_bytes < bytes) {
+		if (ctx->raw_ring) cudaFreeHost(ctx->raw_ring);
+		ctx->raw_ring = nullptr;
+		ctx->raw_ring_bytes = 0;
+		if (cudaMallocHost(&ctx->raw_ring, bytes) != cudaSuccess) { cudaGetLastError(); ctx->raw_ring = nullptr; return nullptr; }
+		ctx->raw_ring_bytes = bytes;
+	}
+	if (!ctx->ev_slot_made) {
+		for (int i = 0; i < TAGPU_RAW_SLOTS_MAX; ++i) cudaEventCreateWithFlags(&ctx->ev_slot[i], cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&ctx->ev_raw, cudaEventDisableTiming);
+		ctx->ev_slot_made = true;
+	}
+	return ctx->raw_ring;
+}
+
+extern "C" int tagpu_raw_begin(tagpu_ctx *ctx, uint64_t total_bytes)
+{
+	CU(cudaSetDevice(ctx->device));
+	return ensure(ctx, ctx->raw, total_bytes + 256);
+}
+
+// bytes of a ring slot -> the device file buffer at dev_off (asynchronous; tagpu_raw_slot_wait tells when the slot is free again)
+extern "C" int tagpu_raw_put(tagpu_ctx *ctx, uint64_t dev_off, const void *h, uint64_t bytes, int slot)
+{
+	if (slot < 0 || slot >= TAGPU_RAW_SLOTS_MAX || !ctx->ev_slot_made) return fail(ctx, "tagpu_raw_put: bad slot %d", slot);
+	CU(cudaMemcpyAsync((uint8_t *)ctx->raw.p + dev_off, h, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+	CU(cudaEventRecord(ctx->ev_slot[slot], ctx->copy_stream));
+	return 0;
+}
+extern "C" int tagpu_raw_slot_wait(tagpu_ctx *ctx, int slot)
+{
+	CU(cudaEventSynchronize(ctx->ev_slot[slot]));
+	return 0;
+}
+
+static int scan_u32(tagpu_ctx *ctx, const uint32_t *in, uint64_t n, unsigned long long *out, unsigned long long *d_total)
+{
+	const uint64_t per = 1024ull * TAGPU_SCAN_ITEMS, nb = (n + per - 1) / per;
+	if (ensure(ctx, ctx->fq_tot, (nb + 1) * 8)) return -1;
+	unsigned long long *tot = (unsigned long long *)ctx->fq_tot.p;
+	if (nb) LAUNCH(k_scan_a, (unsigned)nb, 1024, in, n, out, tot);
+	LAUNCH(k_scan_b, 1, 1024, tot, nb, d_total);
+	if (nb) LAUNCH(k_scan_c, (unsigned)nb, 1024, out, n, (const unsigned long long *)tot);
+	return 0;
+}
+
+// raw file bytes (ctx->raw at off[f], len[f] bytes, ends_nl[f]: the last byte is a newline) -> the read stream in ctx->seq;
+// returns its length, -1 on error
+static int64_t parse_fastq(tagpu_ctx *ctx, int n_files, const uint64_t *off, const uint64_t *len, const uint8_t *ends_nl)
+{
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+	uint64_t bound = 64;
+	for (int f = 0; f < n_files; ++f) bound += len[f] / 2 + 2;
+	if (ensure(ctx, ctx->seq, bound)) return -1;
+	// everything the ring sent up must have landed before the first kernel reads it
+	if (ctx->ev_slot_made) {
+		if (cudaEventRecord(ctx->ev_raw, ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_raw, 0) != cudaSuccess) return -1;
+	}
+	unsigned long long *d_total = ctx->d_ctr + CTR_SPARE3;          // (scratch: the counters are reset by the build that follows)
+	uint64_t acc = 0;
+	for (int f = 0; f < n_files; ++f) {
+		const uint8_t *raw = (const uint8_t *)ctx->raw.p + off[f];
+		const uint64_t n = len[f], n_blk = (n + TAGPU_FQ_BLOCK_BYTES - 1) / TAGPU_FQ_BLOCK_BYTES;
+		if (!n) continue;
+		if (ensure(ctx, ctx->fq_cnt, (n_blk + 1) * 4) || ensure(ctx, ctx->fq_base, (n_blk + 1) * 8)) return -1;
+		LAUNCH(k_fq_count, (unsigned)n_blk, TAGPU_FQ_THREADS, raw, n, (uint32_t *)ctx->fq_cnt.p);
+		if (scan_u32(ctx, (const uint32_t *)ctx->fq_cnt.p, n_blk, (unsigned long long *)ctx->fq_base.p, d_total)) return -1;
+		unsigned long long n_nl = 0;
+		if (cudaMemcpyAsync(&n_nl, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+		// sequence lines = lines 1, 5, 9, ...; an unterminated last line counts if it is one of them
+		const bool tail = !ends_nl[f] && (n_nl & 3ull) == 1ull;
+		const uint64_t n_rec = (n_nl + 2) / 4 + (tail ? 1 : 0);
+		if (!n_rec) continue;
+		if (ensure(ctx, ctx->fq_lo, n_rec * 8) || ensure(ctx, ctx->fq_hi, n_rec * 8) || ensure(ctx, ctx->fq_len, n_rec * 4) || ensure(ctx, ctx->fq_off, n_rec * 8)) return -1;
+		unsigned long long *lo = (unsigned long long *)ctx->fq_lo.p, *hi = (unsigned long long *)ctx->fq_hi.p, *o = (unsigned long long *)ctx->fq_off.p;
+		LAUNCH(k_fq_mark, (unsigned)n_blk, TAGPU_FQ_THREADS, raw, n, (const unsigned long long *)ctx->fq_base.p, lo, hi, n_rec);
+		if (tail && cudaMemcpyAsync(hi + (n_rec - 1), &n, 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return -1;
+		LAUNCH(k_fq_len, (unsigned)((n_rec + 255) / 256), 256, raw, (const unsigned long long *)lo, hi, n_rec, (uint32_t *)ctx->fq_len.p);
+		if (scan_u32(ctx, (const uint32_t *)ctx->fq_len.p, n_rec, o, d_total)) return -1;
+		unsigned long long n_out = 0;
+		if (cudaMemcpyAsync(&n_out, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+		if (acc + n_out + 64 > ctx->seq.cap) {
+			// more sequence than half the bytes of the files (not FASTQ-shaped, e.g. no quality lines): grow, keeping the streams so far
+			void *grown = nullptr;
+			const size_t cap = (size_t)(acc + n_out + 64) * 2;
+			if (cudaMalloc(&grown, cap) != cudaSuccess) { cudaGetLastError(); return -1; }
+			if (acc && cudaMemcpyAsync(grown, ctx->seq.p, acc, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) return -1;
+			if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+			cudaFree(ctx->seq.p);
+			ctx->seq.p = grown;
+			ctx->seq.cap = cap;
+		}
+		LAUNCH(k_fq_copy, (unsigned)((n_rec * 32 + 255) / 256), 256, raw, (const unsigned long long *)lo, (const unsigned long long *)hi,
+		       (const unsigned long long *)o, n_rec, (uint8_t *)ctx->seq.p + acc);
+		acc += n_out;
+	}
+	return (int64_t)acc;
+}
+
+// test / tool entry: parse only, optionally copy the stream back (h_out must hold the returned number of bytes: call twice)
+extern "C" int64_t tagpu_parse_fastq_device(tagpu_ctx *ctx, int n_files, const uint64_t *off, const uint64_t *len, const uint8_t *ends_nl, uint8_t *h_out)
+{
+	ctx->launches = 0;
+	const int64_t n = parse_fastq(ctx, n_files, off, len, ends_nl);
+	if (n < 0) return n;
+	if (h_out && n && (cudaMemcpyAsync(h_out, ctx->seq.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)) return -1;
+	if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+	return n;
+}
+
+// parse + build (with_graph) or count only; k = node size (the count stage works on K = k + 1)
+extern "C" int tagpu_build_fastq_device(tagpu_ctx *ctx, int n_files, const uint64_t *off, const uint64_t *len, const uint8_t *ends_nl, int k, int with_graph)
+{
+	ctx->h_src = nullptr;
+	ctx->src_packed = false;
+	ctx->src_ready = nullptr;
+	const int64_t n = parse_fastq(ctx, n_files, off, len, ends_nl);
+	if (n < 0) return fail(ctx, "FASTQ parsing on the device failed (%s)", cudaGetErrorString(cudaGetLastError()));
+	return run(ctx, (const uint8_t *)ctx->seq.p, (uint64_t)n, k + 1, with_graph != 0);
 }
 
 // build_local_assembly_graph: reads + the two flanking contigs of the global graph.
