@@ -381,7 +381,7 @@ template <int W> struct BucketCfg {
 #ifndef TAGPU_BC_THREADS
 #define TAGPU_BC_THREADS 512
 #define TAGPU_BC_CTAS 2
-#define TAGPU_BC_SLOTS1 7104
+#define TAGPU_BC_SLOTS1 6752
 #define TAGPU_BC_SLOTS2 3840
 #endif
 	static constexpr int THREADS = TAGPU_BC_THREADS;            // two CTAs per SM: one CTA's barriers / harvest overlap the other's inserts
@@ -414,7 +414,14 @@ template <int W> struct BucketCfg {
 #endif
 	static constexpr uint32_t GROUP_TARGET = W == 1 ? SLOTS * 5 / 2 : SLOTS * TAGPU_GT2 / 4;
 	// staging area: record words, one 32-bit meta word per record, 16-bit work items; the harvest reuses it for its output
-	static constexpr size_t STAGE_BYTES = (size_t)ROUND * ((DUAL ? 2 : 1) * NW * 8 + 4) + (size_t)ITEMS * 2 + 16;   // (+ the overflow flag)
+	// CTA-wide duplicate table of a round (the representatives of the warps meet in it): pays with 64-bit keys, whose groups
+	// hold 2.5 x as many windows (C1: 2.76 -> 2.58 ms), not with 128-bit keys (C2: 3.39 -> 3.41 ms)
+#ifndef TAGPU_BC_DD1
+#define TAGPU_BC_DD1 1024
+#define TAGPU_BC_DD2 0
+#endif
+	static constexpr int DD_SLOTS = W == 1 ? TAGPU_BC_DD1 : TAGPU_BC_DD2;
+	static constexpr size_t STAGE_BYTES = (size_t)ROUND * ((DUAL ? 2 : 1) * NW * 8 + 4) + (size_t)ITEMS * 2 + 16 + (size_t)DD_SLOTS * 4;   // (+ the overflow flag)
 	static constexpr size_t SMEM = SLOTS * (sizeof(Key<W>) + 4) + STAGE_BYTES;
 };
 
@@ -734,9 +741,10 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 	// "table too full" flag of the current class: in the dynamic area, whose address is one add away from a register (a
 	// static __shared__ variable costs a special-register read per access, and the insert loop polls this one)
 	volatile uint32_t *s_overflow_p = reinterpret_cast<volatile uint32_t *>(s_item + C::ITEMS);
+	uint32_t *s_dd = reinterpret_cast<uint32_t *>(s_item + C::ITEMS) + 4;     // [DD_SLOTS] duplicate table of a round (behind the flag)
 #define s_overflow (*s_overflow_p)
 	// during the harvest the staging area holds the compacted solid (key, count) pairs of the group
-	constexpr uint32_t OUT_CAP = (uint32_t)((C::STAGE_BYTES - 16) / (sizeof(Key<W>) + 4));    // (the overflow flag at the end is not part of it)
+	constexpr uint32_t OUT_CAP = (uint32_t)((C::STAGE_BYTES - 16 - (size_t)C::DD_SLOTS * 4) / (sizeof(Key<W>) + 4));    // (the overflow flag and the duplicate table at the end are not part of it)
 	Key<W> *o_key = reinterpret_cast<Key<W> *>(stage);
 	uint32_t *o_cnt = reinterpret_cast<uint32_t *>(o_key + OUT_CAP);
 	constexpr uint32_t TOP_NONE = 0xffffffffu;
@@ -753,6 +761,7 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 	TM_DECL();
 
 	for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) { t_key[i] = KO::make(0, 0); t_cnt[i] = 0; }
+	for (uint32_t i = tid; i < (uint32_t)C::DD_SLOTS; i += C::THREADS) s_dd[i] = 0;
 	// Group ids come from a global counter.  Lane 0 of warp 0 keeps a queue of two: id1, whose 64-byte descriptor already sits
 	// in the registers of lanes 0..3 (loaded while the group before was counted), and id2, whose atomicAdd is still in
 	// flight.  So the set-up of a group touches no global memory unless the group is flagged SLOW.
@@ -917,6 +926,28 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 						const uint32_t mult = leader == lane ? 1u + (uint32_t)__popc(peers_eq & dup_mask) : 1u;
 						s_meta[idx] = my_n | (mult << 8);
 						items = (my_n + (uint32_t)C::ITEM_WINDOWS - 1u) / (uint32_t)C::ITEM_WINDOWS;
+						if constexpr (C::DD_SLOTS > 0) {
+						// the representatives of the warps meet in a small table of the round (slot = index of the first record
+						// with this hash + 1): an equal record that got there first takes this one's multiplicity
+						__threadfence_block();                           // s_rec[idx] and s_meta[idx] before the claim
+						uint32_t ds = (rhash >> 8) & (uint32_t)(C::DD_SLOTS - 1);   // (the low byte of rhash is the window count)
+						for (;;) {
+							const uint32_t old = atomicCAS(s_dd + ds, 0u, idx + 1u);
+							if (!old) break;
+							const uint32_t other = old - 1u;
+							const StagedRec<W> o_rec = s_rec[other];
+							bool same = (s_meta[other] & 0xffu) == my_n;
+#pragma unroll
+							for (int q = 0; q < W + 1; ++q) same = same && o_rec.w[q] == canon.w[q];
+							if (same) {
+								atomicAdd(s_meta + other, mult << 8);
+								s_meta[idx] = 0;
+								items = 0;
+								break;
+							}
+							ds = (ds + 1u) & (uint32_t)(C::DD_SLOTS - 1);
+						}
+						}
 					}
 					n_items_mine[h] = items;                             // a duplicate is counted through its representative
 				}
@@ -939,6 +970,7 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 						s_item[o_item++] = (uint16_t)((tid + (uint32_t)h * C::THREADS) | (c << 11));
 				TM_ADD(tm_stage);
 				__syncthreads();                                    // staged records, meta words and items visible to everybody
+				for (uint32_t i = tid; i < (uint32_t)C::DD_SLOTS; i += C::THREADS) s_dd[i] = 0;   // (next used behind at least one barrier)
 				// ---- insert: one item per octet and iteration, one window per lane
 				const uint32_t q = lane & 7u;
 				// (a shared item cursor instead of this static split was measured: slower, 3.82 -> 3.88 ms at C2 — the atomic's
@@ -950,7 +982,7 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 					const uint32_t item = s_item[in ? it : 0u];
 					const uint32_t idx = item & 0x7ffu, j = (item >> 11) * (uint32_t)C::ITEM_WINDOWS + q;
 					const uint32_t meta = s_meta[idx], n_r = meta & 0xffu;
-					mult = (meta >> 8) & 0xffu;
+					mult = meta >> 8;
 					const bool have = in && j < n_r;
 					// orientation of a window: the table key is the window x or its reverse complement, whichever has the
 					// smaller CENTRAL cb bases (a symmetric stretch around the middle of the K-mer: the central bases of rc(x)
