@@ -503,10 +503,12 @@ def main():
                        "1 gpu; graph stage two-level (k_contract inside the bucket groups, then the path-level global stage)",
         "stage_ms": {"count": count_ms, "graph": ms_graph / args.steps},
         # the fraction is taken on the WHOLE path (T_core), algorithmic bytes / step time / HBM peak
-        "roofline": {"bound": "hbm", "achieved": whole, "peak": peak, "unit": "GB/s", "frac": whole / peak,
-                     "traffic": traffic_all, "scope": "whole path (count + graph), SURVEY.md §8d T_core",
+        # (N GPUs: the whole job's bytes against N x the per-GPU peak)
+        "roofline": {"bound": "hbm", "achieved": whole, "peak": peak * world, "unit": "GB/s", "frac": whole / (peak * world),
+                     "traffic": traffic_all, "scope": "whole path (count + graph), SURVEY.md §8d T_core"
+                                                      + (f"; aggregate of {world} GPUs against {world} x the per-GPU peak" if world > 1 else ""),
                      "algorithmic_bytes": b_count + b_graph, "peak_source": peak_src, "dominant_kernel": top,
-                     "count_stage": {"achieved": b_count / (count_ms * 1e-3) / 1e9, "frac": b_count / (count_ms * 1e-3) / 1e9 / peak,
+                     "count_stage": {"achieved": b_count / (count_ms * 1e-3) / 1e9, "frac": b_count / (count_ms * 1e-3) / 1e9 / (peak * world),
                                      "algorithmic_bytes": b_count}},
         "gpu_launches": launches,
         "kernels": kernels,
