@@ -398,6 +398,7 @@ template <int W> struct BucketCfg {
 #define TAGPU_BC_ROUND2 608
 #endif
 	static constexpr int ROUND = DUAL ? TAGPU_BC_ROUND2 : 2 * THREADS;
+	static_assert(ROUND <= 2 * THREADS && ROUND <= 1024, "a thread stages at most two records of a round; item words hold 10 index bits");
 	static constexpr int ITEM_WINDOWS = 8;                      // windows of one work item: one per lane of an octet
 	static constexpr int ITEMS = ROUND * 32 / ITEM_WINDOWS;     // work items of a round (a record has <= 32 windows)
 	// shared-memory table slots per CTA (any number: the home slot is mulhi(hash, SLOTS)); sized so that two CTAs of
@@ -761,7 +762,8 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 	TM_DECL();
 
 	for (uint32_t i = tid; i < C::SLOTS; i += C::THREADS) { t_key[i] = KO::make(0, 0); t_cnt[i] = 0; }
-	for (uint32_t i = tid; i < (uint32_t)C::DD_SLOTS; i += C::THREADS) s_dd[i] = 0;
+	if constexpr (C::DD_SLOTS > 0)
+		for (uint32_t i = tid; i < (uint32_t)C::DD_SLOTS; i += C::THREADS) s_dd[i] = 0;
 	// Group ids come from a global counter.  Lane 0 of warp 0 keeps a queue of two: id1, whose 64-byte descriptor already sits
 	// in the registers of lanes 0..3 (loaded while the group before was counted), and id2, whose atomicAdd is still in
 	// flight.  So the set-up of a group touches no global memory unless the group is flagged SLOW.
@@ -970,7 +972,8 @@ k_count_buckets(const __grid_constant__ CountPeers<W> peers, uint32_t world, uin
 						s_item[o_item++] = (uint16_t)((tid + (uint32_t)h * C::THREADS) | (c << 11));
 				TM_ADD(tm_stage);
 				__syncthreads();                                    // staged records, meta words and items visible to everybody
-				for (uint32_t i = tid; i < (uint32_t)C::DD_SLOTS; i += C::THREADS) s_dd[i] = 0;   // (next used behind at least one barrier)
+				if constexpr (C::DD_SLOTS > 0)
+					for (uint32_t i = tid; i < (uint32_t)C::DD_SLOTS; i += C::THREADS) s_dd[i] = 0;   // (next used behind at least one barrier)
 				// ---- insert: one item per octet and iteration, one window per lane
 				const uint32_t q = lane & 7u;
 				// (a shared item cursor instead of this static split was measured: slower, 3.82 -> 3.88 ms at C2 — the atomic's

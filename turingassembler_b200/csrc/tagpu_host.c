@@ -1338,8 +1338,7 @@ static int build_files_on_device(tagpu_ctx *ctx, int n_files, char **files, int 
 	uint64_t *len = calloc(n_files, 8), *dev_off = calloc(n_files, 8), total = 0;
 	uint8_t *ends_nl = calloc(n_files, 1);
 	int ok = 1, n_open = 0;
-	static const char *max_env;
-	max_env = getenv("TAGPU_RAW_MAX_BYTES");
+	const char *max_env = getenv("TAGPU_RAW_MAX_BYTES");
 	const uint64_t max_total = max_env ? strtoull(max_env, NULL, 10) : (uint64_t)48 << 30;
 	for (int i = 0; i < n_files && ok; ++i) {
 		struct stat st;
