@@ -251,6 +251,11 @@ void tagpu_free_reads(uint8_t *stream);
 /* The same ingest as an object, so that the upload can chase the parser: open (newline index + sizes: the stream length is
  * known), start (copy workers fill dst in stream order), ready (bytes of the stream prefix that are final; pass it with the
  * object to tagpu_set_source_progress before tagpu_build_host / tagpu_count_host), finish (join + release). */
+/* Contig-file mode of the stage entry points (n_files < 0, /root/reference/src/kmer_build.c:722-731,779-781): the graph from
+ * stream A (reads + contig file), without counts, then the edge counts from the solid (k+1)-mers of stream B (the reads alone,
+ * assign_count_kedge_multi over a second database: on an edge -> the edge and its twin get the count, else ignored). */
+int tagpu_build_host_counts_from(tagpu_ctx *ctx, const uint8_t *h_a, uint64_t n_a, const uint8_t *h_b, uint64_t n_b, int k);
+
 /* Raw FASTQ files on the device (the files entry points use it for plain FASTQ when TAGPU_DEVICE_PARSE=1): the host reads the files into a pinned ring
  * (tagpu_raw_ring), sends the slots up (tagpu_raw_put; tagpu_raw_slot_wait tells when a slot may be overwritten) into one
  * device buffer (tagpu_raw_begin; file f at byte off[f], 256-aligned), and the device parses the records — the sequence is

@@ -43,6 +43,10 @@ echo "built $OUT/TA_ref"
 gcc $CFLAGS -c "$HERE/local_ref_main.c" -o "$OUT/obj/local_ref_main.o"
 g++ -pthread -o "$OUT/TA_local_ref" $(ls "$OUT"/obj/src_*.o | grep -v src_main.o) "$OUT/obj/local_ref_main.o" "$OUT/obj/kmc_cpu_shim.o" $LIBS
 echo "built $OUT/TA_local_ref"
+# the contig-file mode of build_graph_from_scratch (n_files < 0) is set by no sub-command either: same recipe
+gcc $CFLAGS -c "$HERE/contig_ref_main.c" -o "$OUT/obj/contig_ref_main.o"
+g++ -pthread -o "$OUT/TA_contig_ref" $(ls "$OUT"/obj/src_*.o | grep -v src_main.o) "$OUT/obj/contig_ref_main.o" "$OUT/obj/kmc_cpu_shim.o" $LIBS
+echo "built $OUT/TA_contig_ref"
 
 TAGPU=$HERE/../turingassembler_b200/libtagpu.so
 if [ -f "$TAGPU" ]; then
@@ -67,4 +71,7 @@ if [ -f "$TAGPU" ]; then
 	g++ -pthread -o "$OUT/TA_local_gpu" $(echo "$OBJS" | tr ' ' '\n' | grep -v src_main.o) "$OUT/obj/dropin_local_kmer_build.o" \
 		"$OUT/obj/local_ref_main.o" -L "$HERE/../turingassembler_b200" -ltagpu -Wl,-rpath,'$ORIGIN/../../turingassembler_b200' $LIBS
 	echo "built $OUT/TA_local_gpu"
+	g++ -pthread -o "$OUT/TA_contig_gpu" $(echo "$OBJS" | tr ' ' '\n' | grep -v src_main.o) "$OUT/obj/dropin_kmer_build.o" \
+		"$OUT/obj/contig_ref_main.o" -L "$HERE/../turingassembler_b200" -ltagpu -Wl,-rpath,'$ORIGIN/../../turingassembler_b200' $LIBS
+	echo "built $OUT/TA_contig_gpu"
 fi

@@ -70,3 +70,33 @@ def local_case(oracle, name, workdir):
     covs = [g0["edges"][e]["count"] * 1.0 / (g0["edges"][e]["seq_len"] - (g0["edges"][e]["n_holes"] + 1) * g0["ksize"]) for e in (e1, e2)]
     lr1, lr2 = r1[: spec["n_pairs"]], r2[: spec["n_pairs"]]
     return dict(g0_bin=g0_bin, e1=e1, e2=e2, contigs=contigs, covs=covs, r1=lr1, r2=lr2, stream=_reads.stream_of(lr1, lr2), lk=spec["lk"])
+
+
+# ---- contig-file mode of build_graph_from_scratch (n_files < 0, /root/reference/src/kmer_build.c:722-731,779-781): reads of
+# `case` + a contig FASTA: a novel sequence written twice (its (k+1)-mers become solid through the contig file alone and get
+# no read count), two reads of the set (they lift (k+1)-mers seen once in the reads over the cutoff), and a sequence with N
+CONTIG_CASES = {
+    "G1": dict(case="P1", k=31),
+    "G2": dict(case="P1", k=45),
+    "G3": dict(case="M2_lowcov", k=25),
+}
+
+
+def contig_case(name):
+    """-> dict(r1, r2, contigs (list of str), k)"""
+    import random
+    spec = CONTIG_CASES[name]
+    kind, kw, _ = CASES[spec["case"]]
+    r1, r2 = reads_for(kind, kw)
+    rnd = random.Random(1000 + len(name) + spec["k"])
+    novel = "".join(rnd.choice("ACGT") for _ in range(400))
+    with_n = novel[:150] + "N" + r1[3][:120]
+    return dict(r1=r1, r2=r2, contigs=[novel, novel, r1[5], r2[7], with_n, r1[5][:90] + r2[9]], k=spec["k"])
+
+
+def write_fasta(path, seqs, width=70):
+    with open(path, "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(">contig%d\n" % i)
+            for o in range(0, len(s), width):
+                f.write(s[o:o + width] + "\n")

@@ -62,6 +62,44 @@ def main():
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(golden, f, indent=1, sort_keys=True)
     make_local_golden(ora)
+    make_contig_golden(ora)
+
+
+def make_contig_golden(ora):
+    """Contig-file mode of build_graph_from_scratch (n_files < 0): the UNMODIFIED reference function, reached through
+    oracle/contig_ref_main.c (oracle/_ref/TA_contig_ref), on the cases of tests/_cases.py:CONTIG_CASES
+    -> tests/golden/golden_contig.json (with and without the count pass)."""
+    from _cases import CONTIG_CASES, contig_case, write_fasta
+    exe = os.path.join(os.path.dirname(_oracle.TA_REF), "TA_contig_ref")
+    assert os.path.exists(exe), "build oracle/_ref/TA_contig_ref first: make -C oracle ref"
+    out = {}
+    for name in CONTIG_CASES:
+        c = contig_case(name)
+        with tempfile.TemporaryDirectory() as td:
+            f1, f2, fc = (os.path.join(td, x) for x in ("R1.fq", "R2.fq", "contigs.fa"))
+            _reads.write_fastq(f1, c["r1"], 1)
+            _reads.write_fastq(f2, c["r2"], 2)
+            write_fasta(fc, c["contigs"])
+            rec = dict(k=c["k"], contig_len=[len(x) for x in c["contigs"]])
+            for without in (0, 1):
+                binp = os.path.join(td, f"contig{without}.bin")
+                p = subprocess.run([exe, str(c["k"]), f1, f2, fc, td, binp, "1", str(without)], capture_output=True, text=True)
+                log = p.stdout + p.stderr
+                assert p.returncode == 0, log[-2000:]
+                g = lambda pat: int(re.search(pat, log).group(1))
+                tag = "nocount_" if without else ""
+                rec.update({tag + "n_kmers": g(r"Number of kmer: (\d+)"), tag + "n_v": g(r"Number of nodes: (\d+)"),
+                            tag + "n_e": g(r"Number of edges: (\d+)")})
+                if not without:
+                    rec["n_kp1_on_edge"] = g(r"\(k\+1\)-mer on edge: (\d+)")
+                for mode in (0, 1):
+                    bad, txt = _oracle.canon_text(ora, binp, mode)
+                    assert bad == 0
+                    rec[f"{tag}canon{mode}_md5"] = hashlib.md5(txt).hexdigest()
+            out[name] = rec
+            print(name, rec)
+    with open(os.path.join(HERE, "golden_contig.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
 
 
 def make_local_golden(ora):

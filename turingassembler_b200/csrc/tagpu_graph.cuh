@@ -522,6 +522,44 @@ __global__ void __launch_bounds__(256) k_edge_counts(const Key<W> *__restrict__ 
 	if ((threadIdx.x & 31) == 0 && on_edge) atomicAdd(ctr + CTR_KP1_ON_EDGE, (unsigned long long)on_edge);
 }
 
+// ---------------------------------------------------------------- C7'': edge counts from ANOTHER solid set (contig-file mode)
+// /root/reference/src/kmer_build.c:695-710,779-780: with a contig file among the inputs (n_files < 0) the graph is built from
+// reads + contig, and the edge counts come from a second database counted on the reads alone — assign_count_kedge_multi over
+// its (k+1)-mers: found on an edge -> the edge and its twin get the count, not found -> ignored.  The (k+1)-mers are not
+// the ones the table was built from, so the edge is found by lookup: left k-mer in the full k-mer table (one-level graph
+// stage), out-bit of the last base set, node -> edge slot by rank, chain vertex -> vedge.
+template <int W>
+__global__ void __launch_bounds__(256) k_edge_counts_lookup(const Key<W> *__restrict__ keys, const uint32_t *__restrict__ cnt, uint64_t n, int k,
+							     KTab<W> t, const uint32_t *__restrict__ kind, const uint32_t *__restrict__ node_ebase,
+							     const uint32_t *__restrict__ vedge, FlatGraph g, unsigned long long *ctr)
+{
+	typedef KeyOps<W> KO;
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t on_edge = 0;
+	if (i < n) {
+		const Key<W> x = keys[i];
+		const Key<W> k1 = KO::shr2(x), r1 = KO::rc(k1, k);
+		const uint32_t c1 = KO::last_base(x);
+		const bool f1 = KO::le(k1, r1);
+		const uint32_t slot = ktab_find<W>(t, f1 ? k1 : r1);
+		if (slot != TAGPU_NONE) {
+			const uint32_t o = f1 ? 0u : 1u, kd = kind[slot];
+			const uint32_t m = ktab_mask_of<W>(t, slot), nib = o ? (m >> 4) : (m & 15u);
+			if ((nib >> c1) & 1u) {
+				const uint32_t e = !(kd & TAGPU_CHAIN) ? node_ebase[kd] + (o ? DEG4(m) : 0u) + tagpu_rank4(nib, c1)
+								       : vedge[(kd & ~TAGPU_CHAIN) * 2u + o];
+				if (e != TAGPU_NONE) {
+					atomicAdd(g.e_count + e, (unsigned long long)cnt[i]);
+					atomicAdd(g.e_count + g.e_rc[e], (unsigned long long)cnt[i]);
+					on_edge = 1;
+				}
+			}
+		}
+	}
+	on_edge = __reduce_add_sync(0xffffffffu, on_edge);
+	if ((threadIdx.x & 31) == 0 && on_edge) atomicAdd(ctr + CTR_KP1_ON_EDGE, (unsigned long long)on_edge);
+}
+
 // ---------------------------------------------------------------- C8: assign_count_garbage (build_local_assembly_graph only)
 // /root/reference/src/kmer_build.c:890-926, called with ksize + 1 (:1040-1041): every (k+1)-mer of the flanking contig
 // EXCEPT ITS FIRST (the loop tests i + 1 > k + 1) that lies on an edge of the new graph lifts that edge (and its twin) to

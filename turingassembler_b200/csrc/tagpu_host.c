@@ -1252,10 +1252,10 @@ static tagpu_ctx *global_ctx(void)
 
 static int64_t gather_files(int n_files, char **files_1, char **files_2, int n_threads, uint8_t **stream)
 {
-	/* files_1[0..n) ++ files_2[0..n): /root/reference/src/kmer_build.c:733-735.  n_files < 0 is the reference's dormant
-	 * "contig file appended" mode (kmer_build.c:677-679,722-731) that no CLI path sets. */
+	/* files_1[0..n) ++ files_2[0..n): /root/reference/src/kmer_build.c:733-735.  (n_files < 0, the contig-file mode, exists for
+	 * the global stage entry points only — stage_entry — not for the callers of this function.) */
 	if (n_files < 0)
-		TAGPU_FATAL("n_files < 0 (contig-file mode) is not supported by the GPU path");
+		TAGPU_FATAL("n_files < 0 (contig-file mode) is a mode of build_graph_from_scratch only");
 	char **all = malloc(2 * (size_t)n_files * sizeof(char *));
 	memcpy(all, files_1, n_files * sizeof(char *));
 	memcpy(all + n_files, files_2, n_files * sizeof(char *));
@@ -1422,6 +1422,31 @@ static void stage_entry(int ksize, int n_threads, int n_files, char **files_1, c
 		on_device = build_files_on_device(ctx, 2 * n_files, all, n_threads, ksize, 1) == 0;
 		free(all);
 	}
+	/* n_files < 0: the reference's contig-file mode (/root/reference/src/kmer_build.c:677-679,722-731,779-781).  files_2 holds
+	 * the R2 files, then ONE contig file, then the 2 |n_files| read files the edge counts are taken from.  The graph comes from
+	 * files_1 ++ files_2[0 .. |n_files|] (the contig included); without counts that is all, with counts a second count pass
+	 * over the read files alone supplies them. */
+	if (n_files < 0) {
+		const int n = -n_files;
+		char **set_a = malloc((2 * (size_t)n + 1) * sizeof(char *));
+		memcpy(set_a, files_1, n * sizeof(char *));
+		memcpy(set_a + n, files_2, ((size_t)n + 1) * sizeof(char *));
+		uint8_t *sa = NULL, *sb = NULL;
+		const int64_t na = tagpu_load_reads(2 * n + 1, set_a, n_threads, &sa);
+		t1 = now_s();
+		if (skip_counts) {
+			if (tagpu_build_host(ctx, sa, (uint64_t)na, ksize))
+				TAGPU_FATAL("GPU graph build failed: %s", tagpu_last_error(ctx));
+		} else {
+			const int64_t nb = tagpu_load_reads(2 * n, files_2 + n + 1, n_threads, &sb);
+			if (tagpu_build_host_counts_from(ctx, sa, (uint64_t)na, sb, (uint64_t)nb, ksize))
+				TAGPU_FATAL("GPU graph build failed: %s", tagpu_last_error(ctx));
+			tagpu_free_reads(sb);
+		}
+		tagpu_free_reads(sa);
+		free(set_a);
+		on_device = -1;
+	}
 	for (int fused = getenv("TAGPU_INGEST_TWO_PASS") ? 0 : 1; fused >= 0 && !on_device; --fused) {
 		/* fused ingest: the workers index, size and copy each chunk in one pass while pass 1 on the GPU chases them; the
 		 * announced stream length is an upper bound and the buffer is padded with '\n' (no windows there).  Files that do
@@ -1455,7 +1480,7 @@ static void stage_entry(int ksize, int n_threads, int n_files, char **files_1, c
 	double t3 = now_s();
 	fprintf(stderr, "[tagpu] k=%d: %lu (k+1)-mer instances, %lu solid; open %.3f s, %s + H2D + GPU %.3f s (device build %.3f ms), "
 			"graph materialisation %.3f s\n", ksize, (unsigned long)st.n_instances, (unsigned long)st.n_solid,
-		t1 - t0, on_device ? "read (records parsed on the GPU)" : "parse", t2 - t1, st.ms_total, t3 - t2);
+		t1 - t0, on_device > 0 ? "read (records parsed on the GPU)" : "parse", t2 - t1, st.ms_total, t3 - t2);
 }
 
 void build_graph_from_scratch(int ksize, int n_threads, int mmem, int n_files, char **files_1, char **files_2,

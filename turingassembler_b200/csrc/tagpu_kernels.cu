@@ -1434,6 +1434,55 @@ extern "C" int tagpu_build_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n
 	ctx->src_ready = nullptr;          // (one use only, also when the build failed before the upload)
 	return rc;
 }
+// Contig-file mode of the stage entry points (n_files < 0, /root/reference/src/kmer_build.c:722-731,779-781): the graph
+// from stream A (reads + the contig file), its edge counts from the solid (k+1)-mers of stream B (the reads alone).
+// A is built with the one-level graph stage (the count lookup needs every k-mer in the table); B then goes through the
+// count stage only — it shares no buffer with the graph — and k_edge_counts_lookup replaces A's edge counts by B's.
+template <int W>
+static int counts_from_current_solid(tagpu_ctx *ctx, uint64_t n_b, uint64_t n_e)
+{
+	KTab<W> t;
+	t.keys = (Key<W> *)ctx->kt_keys.p;
+	t.mask32 = (uint32_t *)ctx->kt_mask.p;
+	t.n_slots = ctx->kt_slots;
+	FlatGraph g;
+	g.e_src = (uint32_t *)ctx->e_src.p; g.e_dst = (uint32_t *)ctx->e_dst.p; g.e_rc = (uint32_t *)ctx->e_rc.p;
+	g.e_len = (uint32_t *)ctx->e_len.p; g.e_count = (unsigned long long *)ctx->e_count.p;
+	g.e_off = (unsigned long long *)ctx->e_off.p; g.e_seq = (uint32_t *)ctx->e_seq.p;
+	// (graph A was built with its own counts, for "Number of (k+1)-mer on edge" — the size of the reference's edge index,
+	// kmer_build.c:772 —; they are dropped here and replaced by B's)
+	CU(cudaMemsetAsync(g.e_count, 0, (size_t)(n_e + 1) * 8, ctx->stream));
+	if (n_b)
+		LAUNCH(k_edge_counts_lookup<W>, (unsigned)((n_b + 255) / 256), 256, (const Key<W> *)ctx->cur_solid_key, (const uint32_t *)ctx->cur_solid_cnt, n_b,
+		       ctx->k, t, (const uint32_t *)ctx->node_ord.p, (const uint32_t *)ctx->node_ebase.p, (const uint32_t *)ctx->vedge.p, g, ctx->d_ctr);
+	return read_counters(ctx);
+}
+
+extern "C" int tagpu_build_host_counts_from(tagpu_ctx *ctx, const uint8_t *h_a, uint64_t n_a, const uint8_t *h_b, uint64_t n_b, int k)
+{
+	const int contract = ctx->contract, skip = ctx->skip_counts;
+	ctx->contract = 0;
+	ctx->skip_counts = 0;
+	ctx->src_packed = false;
+	int rc = upload(ctx, h_a, n_a) ? -1 : run(ctx, (const uint8_t *)ctx->seq.p, n_a, k + 1, true);
+	ctx->src_ready = nullptr;
+	ctx->contract = contract;
+	ctx->skip_counts = skip;
+	if (rc) return rc;
+	const tagpu_stats st_a = ctx->st;
+	rc = upload(ctx, h_b, n_b) ? -1 : run(ctx, (const uint8_t *)ctx->seq.p, n_b, k + 1, false);
+	if (rc) return rc;
+	const uint64_t n_solid_b = ctx->st.n_solid;
+	rc = ctx->W == 1 ? counts_from_current_solid<1>(ctx, n_solid_b, st_a.n_e) : counts_from_current_solid<2>(ctx, n_solid_b, st_a.n_e);
+	if (rc) return rc;
+	// the result is graph A; all figures (instances, distinct, solid, (k+1)-mers on edges) are those of A's (k+1)-mer set
+	ctx->st = st_a;
+	ctx->have_graph = true;
+	ctx->have_count = false;           // (the solid list on the device is B's, not the graph's)
+	ctx->contracted = false;
+	return 0;
+}
+
 extern "C" int tagpu_count_host(tagpu_ctx *ctx, const uint8_t *h_seq, uint64_t n, int K)
 {
 	ctx->src_packed = false;
