@@ -413,7 +413,10 @@ template <int W> struct BucketCfg {
 #ifndef TAGPU_GT2
 #define TAGPU_GT2 8           /* group target of the 128-bit path in quarters of the slot count (developer sweeps) */
 #endif
-	static constexpr uint32_t GROUP_TARGET = W == 1 ? SLOTS * 5 / 2 : SLOTS * TAGPU_GT2 / 4;
+#ifndef TAGPU_GT1
+#define TAGPU_GT1 10          /* the same for the 64-bit path */
+#endif
+	static constexpr uint32_t GROUP_TARGET = W == 1 ? SLOTS * TAGPU_GT1 / 4 : SLOTS * TAGPU_GT2 / 4;
 	// staging area: record words, one 32-bit meta word per record, 16-bit work items; the harvest reuses it for its output
 	// CTA-wide duplicate table of a round (the representatives of the warps meet in it): pays with 64-bit keys, whose groups
 	// hold 2.5 x as many windows (C1: 2.76 -> 2.58 ms), not with 128-bit keys (C2: 3.39 -> 3.41 ms)
